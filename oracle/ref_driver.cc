@@ -1,0 +1,188 @@
+// oracle/ref_driver.cc -- TEST INFRASTRUCTURE (not product code).
+//
+// A small command-line driver of OUR OWN that links the UNMODIFIED reference objects
+// (oracle/_ref/libref_{f,d}.a, built by oracle/Makefile from /root/reference/src) and calls the
+// reference's own entry points for the DP hot path on in-memory sequences:
+//
+//   scores   : alnScoreD(const Seq*[2], const Simmtx*, int*)            reference src/fwd2d1.cc:324
+//   dist     : calcdist(mSeq**, nn, DynScr)                             reference src/phyl.cc:318
+//   align    : align2(mSeq*[2], PwdM*, VTYPE*, Gsinfo*)                 reference src/maln2.cc:1875
+//   matrix   : dump of Simmtx::mtx as the reference built it            reference src/simmtx.cc:282-445
+//
+// It is used (a) to freeze golden vectors under tests/golden/ (tools/make_golden.py), (b) to pin the
+// C restatement in oracle/oracle.c, (c) as bench.py's cpu_baseline "reference" leg (dist/scores timing).
+// Output is plain text on stdout, one record per line, parsed by tools/refio.py.
+//
+// usage: ref_driver <cmd> <multi-fasta> [key=value ...]
+//   keys: mtx=blosum62|pam   u= v= sh= threads= lcl= ls= u1= k1= tgapf= molc=p|n rep=
+#include "aln.h"
+#include "vmf.h"
+#include "wln.h"
+#include "mseq.h"
+#include "maln.h"
+#include "mgaps.h"
+#include "autocomp.h"
+#include "phyl.h"
+#include "consreg.h"
+#include "fspscore.h"
+#include <sys/time.h>
+#include <string>
+#include <vector>
+
+void usage() {}
+template <class seq_t> void AlnServer<seq_t>::setparam(int) {}
+template <class seq_t> int AlnServer<seq_t>::localoption(int&, const char**&) { return 0; }
+
+static double now_s()
+{
+	struct timeval tv; gettimeofday(&tv, 0);
+	return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+static const char* kv(int argc, const char** argv, const char* key, const char* dflt)
+{
+	size_t	kl = strlen(key);
+	for (int i = 3; i < argc; ++i)
+	    if (!strncmp(argv[i], key, kl) && argv[i][kl] == '=') return argv[i] + kl + 1;
+	return dflt;
+}
+
+static std::vector<mSeq*> read_all(const char* fn)
+{
+	std::vector<mSeq*> v;
+	FILE*	fd = fopen(fn, "r");
+	if (!fd) fatal("cannot open %s\n", fn);
+	for (;;) {
+	    mSeq*	sd = new mSeq();
+	    if (!sd->fgetseq(fd)) { delete sd; break; }
+	    sd->sid = (int) v.size();
+	    v.push_back(sd);
+	}
+	fclose(fd);
+	return v;
+}
+
+static void print_vt(double x) { printf("%.17g", x); }
+
+int main(int argc, const char** argv)
+{
+	if (argc < 3) {
+	    fputs("usage: ref_driver scores|dist|align|matrix fasta [key=value ...]\n", stderr);
+	    return 1;
+	}
+	std::string cmd = argv[1];
+	const char* mtxname = kv(argc, argv, "mtx", "blosum62");
+	const char* molc = kv(argc, argv, "molc", "p");
+	bool	isprot = *molc == 'p';
+
+	optimize(GLOBAL, MAXIMUM);
+	if (isprot) setdefPprm(250, 2., 9.);
+	alprm.sh = atoi(kv(argc, argv, "sh", "-60"));
+	const char* s;
+	if ((s = kv(argc, argv, "u", 0)))  alprm.u = atof(s);
+	if ((s = kv(argc, argv, "v", 0)))  alprm.v = atof(s);
+	if ((s = kv(argc, argv, "u1", 0))) alprm.u1 = atof(s);
+	if ((s = kv(argc, argv, "k1", 0))) alprm.k1 = atoi(s);
+	if ((s = kv(argc, argv, "ls", 0))) alprm.ls = atoi(s);
+	if ((s = kv(argc, argv, "tgapf", 0))) alprm.tgapf = atof(s);
+	algmode.lcl = atoi(kv(argc, argv, "lcl", "0"));
+	algmode.bnd = atoi(kv(argc, argv, "bnd", "1"));
+	algmode.crs = atoi(kv(argc, argv, "crs", "0"));
+	algmode.mlt = 1;
+	algmode.mns = 1;
+	algmode.thr = 0;
+	OutPrm.trimend = false;
+	thread_num = atoi(kv(argc, argv, "threads", "0"));
+	int	rep = atoi(kv(argc, argv, "rep", "1"));
+	if (strcmp(mtxname, "pam")) mdm_file[0] = mtxname;
+
+	std::vector<mSeq*> seqs = read_all(argv[2]);
+	int	nn = (int) seqs.size();
+	if (!nn) fatal("no sequence\n");
+	prePwd(seqs[0]->inex.molc);
+	Simmtx*	sm = getSimmtx(0);
+	printf("#ref_driver cmd=%s n=%d vtype=%s u=%g v=%g u1=%g k1=%d ls=%d sh=%d tgapf=%g scale=%g lcl=%d threads=%d\n",
+	    cmd.c_str(), nn, sizeof(VTYPE) == 8? "f64": "f32",
+	    alprm.u, alprm.v, alprm.u1, alprm.k1, alprm.ls, alprm.sh, alprm.tgapf, alprm.scale,
+	    (int) algmode.lcl, thread_num);
+
+	if (cmd == "matrix") {
+	    printf("dim %d\n", sm->dim);
+	    for (int i = 0; i < sm->dim; ++i) {
+		for (int j = 0; j < sm->dim; ++j) {
+		    if (j) putchar(' ');
+		    print_vt(sm->mtx[i][j]);
+		}
+		putchar('\n');
+	    }
+	} else if (cmd == "seqs") {		// residue codes as the reference encodes them
+	    for (int i = 0; i < nn; ++i) {
+		printf("seq %d %d %d %d :", i, seqs[i]->len, seqs[i]->left, seqs[i]->right);
+		for (int p = 0; p < seqs[i]->len; ++p) printf(" %d", *seqs[i]->at(p));
+		putchar('\n');
+	    }
+	} else if (cmd == "scores") {		// alnScoreD per pair, elem(i,j) order, i<j: a=seq i, b=seq j
+	    double	t0 = now_s();
+	    for (int r = 0; r < rep; ++r)
+	    for (int j = 1; j < nn; ++j) {
+		for (int i = 0; i < j; ++i) {
+		    const Seq*	sq[2] = {seqs[i], seqs[j]};
+		    if (algmode.lcl && !(algmode.lcl & 16)) {
+			seqs[i]->exg_seq(algmode.lcl & 1, algmode.lcl & 2);
+			seqs[j]->exg_seq(algmode.lcl & 4, algmode.lcl & 8);
+			int	ends[2];
+			VTYPE	scr = alnScoreD(sq, sm, ends);
+			if (!r) { printf("score %d %d ", i, j); print_vt(scr); printf(" %d %d\n", ends[0], ends[1]); }
+		    } else {
+			VTYPE	scr = alnScoreD(sq, sm, 0);
+			if (!r) { printf("score %d %d ", i, j); print_vt(scr); putchar('\n'); }
+		    }
+		}
+	    }
+	    printf("time %.6f\n", now_s() - t0);
+	} else if (cmd == "dist") {		// calcdist(seqs, nn, DynScr): the all-vs-all guide-tree step
+	    double	t0 = now_s();
+	    FTYPE*	dist = 0;
+	    for (int r = 0; r < rep; ++r) {
+		delete[] dist;
+		dist = calcdist(&seqs[0], nn, DynScr);
+	    }
+	    double	t1 = now_s();
+	    if (!atoi(kv(argc, argv, "quiet", "0")))
+	    for (int k = 0; k < ncomb(nn); ++k) { printf("dist %d ", k); print_vt(dist[k]); putchar('\n'); }
+	    printf("time %.6f\n", (t1 - t0) / rep);
+	    delete[] dist;
+	} else if (cmd == "align") {		// align2 per pair (i<j): score + stdskl-normalised corner list
+	    double	t0 = now_s();
+	    for (int j = 1; j < nn; ++j) {
+		for (int i = 0; i < j; ++i) {
+		    mSeq*	sq[2] = {seqs[i], seqs[j]};
+		    if (algmode.lcl & 16) { sq[0]->exg_seq(1, 1); sq[1]->exg_seq(1, 1); }
+		    else {
+			sq[0]->exg_seq(algmode.lcl & 1, algmode.lcl & 2);
+			sq[1]->exg_seq(algmode.lcl & 4, algmode.lcl & 8);
+		    }
+		    PwdM*	pwd = new PwdM(sq);
+		    Gsinfo	gsi;
+		    VTYPE	scr = 0;
+		    SKL*	skl = align2(sq, pwd, &scr, &gsi);
+		    printf("align %d %d swp=%d mode=%d ", i, j, pwd->swp, pwd->alnmode);
+		    print_vt(scr);
+		    if (!skl) printf(" skl 0\n");
+		    else {
+			printf(" skl %d %d :", skl->n, skl->m);
+			for (int k = 1; k <= skl->n; ++k) printf(" %d %d", skl[k].m, skl[k].n);
+			putchar('\n');
+		    }
+		    printf("fstat %d %d ", i, j);
+		    print_vt(gsi.fstat.val); printf(" %g %g %g %g\n", (double) gsi.fstat.mch,
+			(double) gsi.fstat.mmc, (double) gsi.fstat.gap, (double) gsi.fstat.unp);
+		    gsi.skl = 0;
+		    delete[] skl;
+		    delete pwd;
+		}
+	    }
+	    printf("time %.6f\n", now_s() - t0);
+	} else fatal("unknown command %s\n", cmd.c_str());
+	return 0;
+}
