@@ -1,0 +1,72 @@
+/* oracle/oracle.h -- CPU restatement of the prrn_aln DP hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * liboracle.so; the product (libprrn_gpu.so) never does and has no CPU fallback.
+ *
+ * Parity status: PINNED.  Every function here is checked (tests/test_oracle_vs_reference.py, golden
+ * vectors under tests/golden/ produced by tools/make_golden.py from the unmodified reference built
+ * by oracle/Makefile) against the reference's own outputs: alnScoreD scores, calcdist distance
+ * vectors, align2 scores + stdskl corner lists.
+ *
+ * The restatement is written in plain row-major (m, n) order with an explicit band test; the
+ * reference scans anti-diagonals in place (fwd2d1.cc:136-160) or rows in diagonal coordinates
+ * (fwd2c.h:359-482).  Each function cites the reference lines it follows.
+ */
+#ifndef PRRN_ORACLE_H
+#define PRRN_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* A view of one sequence as the reference's Seq presents it to the DP (seq.h:253-438):
+ * residue codes res[0..len), operated window [left, right), end-gap flags inex.exgl / inex.exgr. */
+typedef struct {
+    const uint8_t *res;
+    int32_t len, left, right;
+    int32_t exgl, exgr;
+} orc_seq;
+
+/* Scalars of ALPRM (seq.h:27-28) + algmode.lcl that the path reads. */
+typedef struct {
+    double u, v, scale, tgapf;  /* alprm.u, .v, .scale, .tgapf   (float in the reference)          */
+    double u1;                  /* alprm.u1   long-gap extension                                     */
+    int32_t k1, ls, sh;         /* alprm.k1, .ls, .sh                                                */
+    int32_t lcl;                /* algmode.lcl                                                       */
+    int32_t vtype;              /* 0: float VTYPE (aln build), 1: double VTYPE (prrn build)          */
+} orc_params;
+
+typedef struct { int32_t lw, up, width; } orc_window;
+
+/* stripe(): reference src/aln2.cc:156-174 */
+void orc_stripe(const orc_seq *a, const orc_seq *b, int sh, orc_window *w);
+
+/* number of (m,n) cells the reference loops visit for this pair (SURVEY.md 8(d) cell definition;
+ * loop bounds fwd2d1.cc:137-146 == fwd2c.h:364-374) */
+int64_t orc_band_cells(const orc_seq *a, const orc_seq *b, int sh);
+
+/* alnScoreD(), global / semi-global branch without `ends` (Fwd2d ctor + forwardD + lastD):
+ * reference src/fwd2d1.cc:57-90, 136-160, 97-134, 324-337.  mtx is dim x dim row-major in the
+ * VTYPE of p->vtype (passed as double; values are rounded to float when vtype == 0). */
+double orc_aln_score_d(const orc_seq *a, const orc_seq *b, const double *mtx, int dim,
+                       const orc_params *p);
+
+/* selfAlnScr(): reference src/aln2.cc:54-64 (many == 1) */
+double orc_self_score(const orc_seq *a, const double *mtx, int dim, const orc_params *p);
+
+/* alnscore2dist() global branch + dpscore()'s denominator and x100:
+ * reference src/aln2.cc:289-334 (else-branch :321-333), src/phyl.cc:221-251.
+ * self_a/self_b are selfscr() values (phyl.cc:253-261, sumwt == 1 for single sequences). */
+double orc_score2dist(double scr, int la, int lb, double self_a, double self_b, const orc_params *p);
+
+/* calcdist(seqs, nn, DynScr) for single sequences: reference src/phyl.cc:318-342.
+ * dist[elem(i,j)], elem(i,j) = j(j-1)/2 + i for i < j (cmn.h:115); a = seq i, b = seq j.
+ * raw_scores (optional) receives alnScoreD per pair in the same order. */
+void orc_calcdist(const orc_seq *seqs, int nn, const double *mtx, int dim, const orc_params *p,
+                  double *dist, double *raw_scores);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

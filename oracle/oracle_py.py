@@ -1,0 +1,101 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs, never by the product package (prrn_aln_b200 has no CPU fallback).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class OrcSeq(C.Structure):
+    _fields_ = [("res", C.POINTER(C.c_uint8)), ("len", C.c_int32), ("left", C.c_int32),
+                ("right", C.c_int32), ("exgl", C.c_int32), ("exgr", C.c_int32)]
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("u", C.c_double), ("v", C.c_double), ("scale", C.c_double), ("tgapf", C.c_double),
+                ("u1", C.c_double), ("k1", C.c_int32), ("ls", C.c_int32), ("sh", C.c_int32),
+                ("lcl", C.c_int32), ("vtype", C.c_int32)]
+
+
+class OrcWindow(C.Structure):
+    _fields_ = [("lw", C.c_int32), ("up", C.c_int32), ("width", C.c_int32)]
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "port"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_aln_score_d.restype = C.c_double
+        L.orc_aln_score_d.argtypes = [C.POINTER(OrcSeq), C.POINTER(OrcSeq), C.POINTER(C.c_double),
+                                      C.c_int, C.POINTER(OrcParams)]
+        L.orc_self_score.restype = C.c_double
+        L.orc_self_score.argtypes = [C.POINTER(OrcSeq), C.POINTER(C.c_double), C.c_int,
+                                     C.POINTER(OrcParams)]
+        L.orc_band_cells.restype = C.c_int64
+        L.orc_band_cells.argtypes = [C.POINTER(OrcSeq), C.POINTER(OrcSeq), C.c_int]
+        L.orc_stripe.restype = None
+        L.orc_stripe.argtypes = [C.POINTER(OrcSeq), C.POINTER(OrcSeq), C.c_int, C.POINTER(OrcWindow)]
+        L.orc_calcdist.restype = None
+        L.orc_calcdist.argtypes = [C.POINTER(OrcSeq), C.c_int, C.POINTER(C.c_double), C.c_int,
+                                   C.POINTER(OrcParams), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _LIB = L
+    return _LIB
+
+
+def params(u=2.0, v=9.0, scale=1.0, tgapf=1.0, u1=0.6, k1=7, ls=1, sh=-60, lcl=0, vtype=0):
+    return OrcParams(u, v, scale, tgapf, u1, k1, ls, sh, lcl, vtype)
+
+
+def seq(codes, left=None, right=None, exgl=0, exgr=0):
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    s = OrcSeq(codes.ctypes.data_as(C.POINTER(C.c_uint8)), len(codes),
+               0 if left is None else left, len(codes) if right is None else right, exgl, exgr)
+    s._keep = codes
+    return s
+
+
+def _mtx(mtx):
+    m = np.ascontiguousarray(mtx, dtype=np.float64)
+    return m, m.ctypes.data_as(C.POINTER(C.c_double)), m.shape[0]
+
+
+def aln_score_d(a, b, mtx, p):
+    m, mp, dim = _mtx(mtx)
+    return lib().orc_aln_score_d(C.byref(a), C.byref(b), mp, dim, C.byref(p))
+
+
+def band_cells(a, b, sh):
+    return lib().orc_band_cells(C.byref(a), C.byref(b), sh)
+
+
+def stripe(a, b, sh):
+    w = OrcWindow()
+    lib().orc_stripe(C.byref(a), C.byref(b), sh, C.byref(w))
+    return w.lw, w.up, w.width
+
+
+def calcdist(seqs, mtx, p, want_scores=True):
+    """seqs: list of OrcSeq.  Returns (dist[n(n-1)/2], raw scores) in elem(i,j) order."""
+    n = len(seqs)
+    arr = (OrcSeq * n)(*seqs)
+    m, mp, dim = _mtx(mtx)
+    npair = n * (n - 1) // 2
+    dist = np.zeros(npair, dtype=np.float64)
+    raw = np.zeros(npair, dtype=np.float64)
+    lib().orc_calcdist(arr, n, mp, dim, C.byref(p), dist.ctypes.data_as(C.POINTER(C.c_double)),
+                       raw.ctypes.data_as(C.POINTER(C.c_double)) if want_scores else None)
+    return dist, raw

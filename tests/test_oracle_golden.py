@@ -1,0 +1,35 @@
+"""The oracle (oracle/oracle.c) against golden vectors frozen from the unmodified reference
+(tools/make_golden.py -> tests/golden/*.json).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names
+from prrn_aln_b200 import seqcode
+
+
+def _oracle_params(O, g):
+    h = g["params"]
+    return O.params(u=float(h["u"]), v=float(h["v"]), scale=float(h["scale"]), tgapf=float(h["tgapf"]),
+                    u1=float(h["u1"]), k1=int(h["k1"]), ls=int(h["ls"]), sh=int(h["sh"]),
+                    lcl=int(h["lcl"]), vtype=1 if h["vtype"] == "f64" else 0)
+
+
+@pytest.mark.parametrize("name", golden_names("score_"))
+def test_scores_and_dist_bit_exact(oracle, name):
+    g = golden(name)
+    enc = [seqcode.encode_dna(s) if g["dna"] else seqcode.encode_protein(s) for s in g["seqs"]]
+    p = _oracle_params(oracle, g)
+    dist, raw = oracle.calcdist([oracle.seq(e) for e in enc], np.array(g["matrix"]), p)
+    assert np.array_equal(raw, np.array(g["scores"])), "alnScoreD scores differ from the reference"
+    assert np.array_equal(dist, np.array(g["dist"])), "calcdist vector differs from the reference"
+
+
+def test_band_cells_matches_loop_bounds(oracle):
+    a = oracle.seq(np.zeros(10, np.uint8) + 3)
+    b = oracle.seq(np.zeros(14, np.uint8) + 3)
+    lw, up, width = oracle.stripe(a, b, -50)
+    assert (lw, up, width) == (-5, 9, 17)
+    cells = sum(min(m + up + 1, 14) - max(m + lw, 0) for m in range(10))
+    assert oracle.band_cells(a, b, -50) == cells
+    # absolute shoulder wider than the matrix -> full rectangle
+    assert oracle.band_cells(a, b, 1000) == 140

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Freeze golden vectors by running the UNMODIFIED reference (oracle/_ref/ref_driver_{f,d}, built by
+oracle/Makefile from /root/reference/src) on fixed-seed inputs.  Only runs where /root/reference was
+present at build time (this container); the JSON files it writes under tests/golden/ are committed
+and are what travels to the GPU box.
+
+    python tools/make_golden.py            # (re)generate everything
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+import gen_synth  # noqa: E402
+import refio  # noqa: E402
+from prrn_aln_b200 import seqcode  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+TMP = "/tmp/prrn_golden"
+
+
+def score_case(name, seqs, flavour="f", dna=False, **kv):
+    """alnScoreD per pair + calcdist(DynScr) vector + the Simmtx the reference built."""
+    os.makedirs(TMP, exist_ok=True)
+    fa = os.path.join(TMP, name + ".fa")
+    gen_synth.write_fasta(fa, seqs)
+    extra = dict(kv)
+    if dna:
+        extra["molc"] = "n"
+    sc = refio.run("scores", fa, flavour=flavour, **extra)
+    mt = refio.run("matrix", fa, flavour=flavour, **extra)
+    ds = refio.run("dist", fa, flavour=flavour, **extra)
+    n = len(seqs)
+    scores = [sc["scores"][(i, j)] for j in range(1, n) for i in range(j)]
+    rec = dict(name=name, kind="score", flavour=flavour, dna=dna, params=sc["header"], args=kv,
+               seqs=seqs, matrix=mt["matrix"].tolist(), scores=scores, dist=ds["dist"].tolist())
+    with open(os.path.join(GOLD, name + ".json"), "w") as f:
+        json.dump(rec, f)
+    print("wrote", name, "pairs", len(scores))
+
+
+def sample_pair():
+    """C1: the sample/pas ce13a1 x ce13a2 pair of sample/test.sh (annotation lines stripped)."""
+    out = []
+    for nm in ("ce13a1", "ce13a2"):
+        path = os.path.join("/root/reference/sample/pas", nm)
+        s = []
+        with open(path) as f:
+            for line in f:
+                if line[0] in ">;#":
+                    continue
+                s.append("".join(c for c in line.strip() if c.isalpha()))
+        out.append("".join(s))
+    return out
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    p24 = gen_synth.synth_set(24, 120, 0.1, 0.6, 11)
+    score_case("score_p24_blosum62", p24)
+    score_case("score_p24_sh20", p24, sh=-20)
+    score_case("score_p24_sh3", gen_synth.synth_set(24, 150, 0.2, 0.9, 12), sh=3)
+    score_case("score_p24_sh0", gen_synth.synth_set(24, 150, 0.2, 0.9, 12), sh=0)
+    score_case("score_p24_u3v11", p24, u=3, v=11)
+    score_case("score_p24_tgapf05", p24, tgapf=0.5)
+    score_case("score_p24_tgapf0", p24, tgapf=0.0, sh=-30)
+    score_case("score_p24_pam_f32", p24, mtx="pam")
+    score_case("score_p24_pam_f64", p24, flavour="d", mtx="pam")
+    # ragged lengths, including very short sequences
+    rag = [s[:k] for s, k in zip(gen_synth.synth_set(20, 300, 0.1, 0.7, 21),
+                                 [1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 300, 17, 64, 65, 31, 32, 33, 250])]
+    score_case("score_ragged", rag)
+    score_case("score_c2_first40", gen_synth.config_set("c2", 40))
+    score_case("score_c5a_first40", gen_synth.config_set("c5a", 40))
+    long_ = gen_synth.synth_set(6, 1300, 0.1, 0.5, 31)
+    score_case("score_long1300", long_)
+    score_case("score_c1_ce13a", sample_pair(), sh=-50)
+
+
+if __name__ == "__main__":
+    if not refio.available("f"):
+        sys.exit("oracle/_ref is not built: run `make -C oracle ref` where /root/reference exists")
+    main()

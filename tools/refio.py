@@ -1,0 +1,72 @@
+"""Run oracle/_ref/ref_driver_{f,d} (the unmodified reference) and parse its text output.
+TEST INFRASTRUCTURE: used by tools/make_golden.py, tests/ (when oracle/_ref exists) and bench.py's
+cpu_baseline / --impl reference legs."""
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def driver(flavour="f"):
+    return os.path.join(REFDIR, "ref_driver_" + flavour)
+
+
+def available(flavour="f"):
+    return os.path.exists(driver(flavour)) and os.path.exists(os.path.join(REFDIR, "table", "blosum62"))
+
+
+def run(cmd, fasta, flavour="f", timeout=3600, **kv):
+    env = dict(os.environ, ALN_TAB=os.path.join(REFDIR, "table"))
+    args = [driver(flavour), cmd, fasta] + ["%s=%s" % (k, v) for k, v in kv.items()]
+    out = subprocess.run(args, env=env, capture_output=True, text=True, timeout=timeout)
+    if out.returncode != 0:
+        raise RuntimeError("ref_driver failed (%d): %s" % (out.returncode, out.stderr[-2000:]))
+    return parse(out.stdout)
+
+
+def parse(text):
+    r = {"header": None, "scores": {}, "ends": {}, "dist": [], "aligns": {}, "fstat": {}, "time": None,
+         "matrix": None, "seqs": {}}
+    lines = text.splitlines()
+    i = 0
+    while i < len(lines):
+        t = lines[i].split()
+        i += 1
+        if not t:
+            continue
+        if t[0].startswith("#ref_driver"):
+            r["header"] = dict(x.split("=", 1) for x in t[1:])
+        elif t[0] == "score":
+            r["scores"][(int(t[1]), int(t[2]))] = float(t[3])
+            if len(t) > 4:
+                r["ends"][(int(t[1]), int(t[2]))] = (int(t[4]), int(t[5]))
+        elif t[0] == "dist":
+            r["dist"].append(float(t[2]))
+        elif t[0] == "time":
+            r["time"] = float(t[1])
+        elif t[0] == "dim":
+            dim = int(t[1])
+            r["matrix"] = np.array([[float(x) for x in lines[i + k].split()] for k in range(dim)])
+            i += dim
+        elif t[0] == "seq":
+            r["seqs"][int(t[1])] = dict(len=int(t[2]), left=int(t[3]), right=int(t[4]),
+                                         codes=[int(x) for x in t[6:]])
+        elif t[0] == "align":
+            key = (int(t[1]), int(t[2]))
+            swp = int(t[3].split("=")[1])
+            mode = int(t[4].split("=")[1])
+            scr = float(t[5])
+            skl = None
+            if t[6] == "skl" and t[7] != "0":
+                n = int(t[7])
+                flag = int(t[8])
+                v = [int(x) for x in t[10:10 + 2 * n]]
+                skl = dict(n=n, flag=flag, pts=list(zip(v[0::2], v[1::2])))
+            r["aligns"][key] = dict(swp=swp, mode=mode, score=scr, skl=skl)
+        elif t[0] == "fstat":
+            r["fstat"][(int(t[1]), int(t[2]))] = [float(x) for x in t[3:]]
+    r["dist"] = np.array(r["dist"])
+    return r
