@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DP forward fill (BASELINE.json config 2).
+
+One "step" = one all-vs-all `calcdist(DynScr)` pass (reference src/phyl.cc:318) over the synthetic
+protein set: score-only banded affine Gotoh fill for every pair + the distance epilogue.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3            # our arm (CUDA, sm_100a)
+  python bench.py --impl reference --steps 2 --warmup 1    # the reference's own CPU code on host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...        # pairs sharded over N GPUs + NCCL all-gather
+
+Prints ONE JSON line (rank 0).  `value` = GCUPS over the cells the reference's loops visit
+(SURVEY.md 8(d)), inputs resident in HBM; `e2e` = the same through the host-buffer C-ABI call
+(H2D of sequences + matrix, D2H of the distance vector inside the timed region).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+import gen_synth  # noqa: E402
+from prrn_aln_b200 import seqcode  # noqa: E402
+
+BASE_N = 1000               # config 2: 1,000 proteins of ~400 aa
+SH = -60                    # prrn5 default band shoulder (src/prrn5.cc:1272)
+OPS_PER_CELL = 9            # 5 add + 4 max per cell, affine score-only
+DPX_OPS_PER_INSTR = 2       # one viaddmax / vimax3 retires two of those scalar operations
+CPU_SAMPLE_N = 400          # bounded CPU sample: first 400 sequences (79,800 pairs, ~1.1e10 cells)
+
+
+def blosum62_matrix():
+    with open(os.path.join(ROOT, "tests", "golden", "score_p24_blosum62.json")) as f:
+        return np.array(json.load(f)["matrix"])
+
+
+def workload(n_gpus):
+    """Weak scaling: M sequences with M(M-1)/2 ~= n_gpus * C(1000,2); same generator, seed 1."""
+    m = BASE_N if n_gpus == 1 else int(round((1 + math.sqrt(1 + 8.0 * n_gpus * BASE_N * (BASE_N - 1) / 2)) / 2))
+    seqs = gen_synth.synth_set(m, 400, 0.1, 0.6, 1)
+    return seqs
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(seqs, threads, reps=1):
+    """Time the reference's own calcdist (oracle/_ref/ref_driver_d, unmodified reference objects) --
+    or the oracle port when the reference build is absent -- on the host cores.  Returns
+    (gcups, kind, cores, seconds, cells)."""
+    import prrn_aln_b200 as P
+    enc = [seqcode.encode_protein(s) for s in seqs]
+    cells = P.calcdist_cells(P.SeqSet(enc), P.Params(P.ALPRM(sh=SH)))
+    import refio
+    if refio.available("d"):
+        fa = "/tmp/prrn_bench_cpu_%d.fa" % os.getpid()
+        gen_synth.write_fasta(fa, seqs)
+        r = refio.run("dist", fa, flavour="d", threads=threads, sh=SH, quiet=1, rep=reps)
+        os.unlink(fa)
+        return cells / r["time"] / 1e9, "reference", max(threads, 1), r["time"], cells
+    import oracle_py as O
+    M = blosum62_matrix()
+    t0 = time.time()
+    O.calcdist([O.seq(e) for e in enc], M, O.params(sh=SH, vtype=1), want_scores=False)
+    dt = time.time() - t0
+    return cells / dt / 1e9, "port", 1, dt, cells
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    seqs = workload(1)[:CPU_SAMPLE_N]
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_reference_run(seqs[:100], threads)
+    t_tot, cells_tot, kind, cores = 0.0, 0, "port", 1
+    for _ in range(args.steps):
+        g, kind, cores, dt, cells = cpu_reference_run(seqs, threads)
+        t_tot += dt
+        cells_tot += cells
+    val = cells_tot / t_tot / 1e9
+    sample = "first %d of the 1000 sequences (%d pairs, %.3g cells) per step" % (
+        CPU_SAMPLE_N, CPU_SAMPLE_N * (CPU_SAMPLE_N - 1) // 2, cells_tot / args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": "DP GCUPS (all-pairs calcdist, band cells)", "value": val, "unit": "GCUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 all-vs-all calcdist(DynScr): 1000 x ~400 aa synthetic proteins (seed 1), "
+                               "BLOSUM62 u=2 v=9 sh=-60; CPU arm runs a bounded sample", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import prrn_aln_b200 as P
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    seqs = workload(world)
+    enc = [seqcode.encode_protein(s) for s in seqs]
+    ss = P.SeqSet(enc)
+    M = blosum62_matrix()
+    prm = P.Params(P.ALPRM(sh=SH), vtype=1)     # prrn build: FTYPE = double
+    npair = ss.n * (ss.n - 1) // 2
+    chunk = (npair + world - 1) // world
+    k0, k1 = min(rank * chunk, npair), min((rank + 1) * chunk, npair)
+    cells_total = P.calcdist_cells(ss, prm)
+    cells_mine = P.calcdist_cells(ss, prm, k0, k1)
+
+    ctx = P.Context(local)
+    dseqs = ctx.upload(ss)
+    stream = torch.cuda.current_stream()
+    d_shard = torch.empty(chunk, dtype=torch.float64, device="cuda")
+    d_all = torch.empty(chunk * world, dtype=torch.float64, device="cuda") if world > 1 else d_shard
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def step_dev():
+        nl = ctx.calcdist_dev(dseqs, prm, M, k0, k1, d_shard.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_shard)
+        return nl
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)            # evict L2 between timed iterations (outside the events)
+        ev[i][0].record(stream)
+        launches += step_dev()
+        ev[i][1].record(stream)
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    gcups = cells_total * args.steps / (ms_total * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C-ABI call: H2D (sequences, matrix) + D2H (distances)
+    pin_out = torch.empty(max(k1 - k0, 1), dtype=torch.float64).pin_memory()
+    out_np = pin_out.numpy()
+    res_pin = torch.from_numpy(ss.res.copy()).pin_memory()
+    ss_pin = P.SeqSet(enc)
+    ss_pin.res = res_pin.numpy()
+    for _ in range(2):
+        ctx.calcdist(ss_pin, prm, M, k0, k1, out=out_np)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.calcdist(ss_pin, prm, M, k0, k1, out=out_np)
+        checksum = float(out_np[:8].sum())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_gcups = cells_total * args.steps / float(t.item()) / 1e9
+    h2d = int(ss.res.nbytes + ss.offs.nbytes + 2 * ss.lens.nbytes + ss.n + M.size * 4)
+    d2h = int((k1 - k0) * 8)
+
+    # ---- roofline of the dominant kernel (the fill): DPX issue rate measured on this device
+    peak32, peak16 = ctx.dpx_peak()
+    achieved = gcups / world * OPS_PER_CELL              # per GPU, Gop/s of algorithmic add/max
+    peak = peak32 * DPX_OPS_PER_INSTR
+    roofline = {"bound": "dpx-int32 issue", "achieved": achieved, "peak": peak, "unit": "Gop/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "measured here: pg_dpx_peak register-only __viaddmax_s32 chains = %.0f G thread-instr/s "
+                               "(x2 scalar ops each); MEASURED_PEAKS.json has no integer peak" % peak32,
+                "ops_per_cell": OPS_PER_CELL, "kernel_instr_per_cell": 4,
+                "issue_frac": gcups / world * 4 / peak32, "dpx_s16x2_ginstr": peak16,
+                "hbm_bytes_per_step": h2d + d2h}
+
+    out = {
+        "metric": "DP GCUPS (all-pairs calcdist, band cells)", "value": gcups, "unit": "GCUPS", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "C2 all-vs-all calcdist(DynScr): %d x ~400 aa synthetic proteins (seed 1), %d pairs, "
+                               "BLOSUM62 u=2 v=9 sh=-60, prrn (double) build semantics; pairs sharded over %d GPU(s)"
+                               % (ss.n, npair, world),
+                   "pairs": npair, "cells": cells_total, "full_matrix_cells": int(sum(
+                       int(ss.lens[j]) * int(ss.lens[:j].sum()) for j in range(1, ss.n))),
+                   "l2": "256 MB buffer written between timed iterations", "collective": "nccl all_gather" if world > 1 else None},
+        "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = workload(1)[:CPU_SAMPLE_N]
+        g, kind, cores, dtc, cells = cpu_reference_run(sample, os.cpu_count() or 1)
+        out["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": cores, "kind": kind,
+                               "sample": "first %d of the 1000 sequences: %d pairs, %.3g cells, %.2f s" % (
+                                   CPU_SAMPLE_N, CPU_SAMPLE_N * (CPU_SAMPLE_N - 1) // 2, cells, dtc)}
+    if rank == 0:
+        print(json.dumps(out))
+    ctx.free_seqs(dseqs)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,101 @@
+/* include/prrn_gpu.h -- C ABI of libprrn_gpu.so: the B200 (sm_100a) implementation of the
+ * prrn_aln dynamic-programming forward fill.
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this line.  Every entry point names
+ * the reference interface it stands behind (file:line into ogotoh/prrn_aln `src/`).  The reference
+ * has no FFI of its own: these are the calls a maintainer binds from the C++ drivers (see
+ * INTEGRATION.md for the shim that re-points alnScoreD / calcdist / alignC at this library).
+ *
+ * There is NO CPU fallback: every compute call fails with PG_ERR_NO_DEVICE / PG_ERR_CUDA when the
+ * CUDA device or kernels are unavailable, and with PG_ERR_UNSUPPORTED for modes not built yet.
+ */
+#ifndef PRRN_GPU_H
+#define PRRN_GPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK               0
+#define PG_ERR_NO_DEVICE    1   /* no CUDA device / driver                                          */
+#define PG_ERR_CUDA         2   /* a CUDA runtime call or kernel failed (pg_last_error has text)   */
+#define PG_ERR_ARG          3   /* invalid argument                                                */
+#define PG_ERR_UNSUPPORTED  4   /* mode exists in the reference but is not implemented here yet    */
+#define PG_ERR_RANGE        5   /* scores would overflow the integer kernels' range                */
+
+typedef struct pg_context pg_context;
+
+/* Mirror of the reference's ALPRM (src/seq.h:27-28), field for field. */
+typedef struct {
+    float u, v, u0, u1, v0, tgapf, thr, scale, maxsp, gamma;
+    int32_t k1, ls, sh, mtx_no;
+} pg_alprm;
+
+/* The scalars the path reads besides ALPRM. */
+typedef struct {
+    pg_alprm alprm;
+    int32_t lcl;        /* algmode.lcl (src/clib.h:37-55): 0 global; bits 1,2,4,8 free ends; 16 SWG   */
+    int32_t vtype;      /* VTYPE of the caller's build: 0 float (aln), 1 double (prrn, -DDVAL=1)      */
+} pg_params;
+
+/* A set of sequences as the reference's Seq objects present them to the DP (src/seq.h:253-438):
+ * residue codes (1 byte/residue, src/cmn.h:110-112), concatenated; sequence i occupies
+ * res[offs[i] .. offs[i]+lens[i]).  left/right = operated window (NULL: 0 / len);
+ * exg[i] bit0 = inex.exgl, bit1 = inex.exgr (NULL: 0). */
+typedef struct {
+    const uint8_t *res;
+    const int64_t *offs;
+    const int32_t *lens;
+    const int32_t *left;
+    const int32_t *right;
+    const uint8_t *exg;
+    int32_t nseq;
+} pg_seqs;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int  pg_create(int device, pg_context **out);
+void pg_destroy(pg_context *ctx);
+const char *pg_last_error(const pg_context *ctx);   /* valid with ctx == NULL after pg_create failed */
+const char *pg_version(void);
+
+/* ---- per-call level: stands behind
+ *   VTYPE alnScoreD(const Seq* seqs[2], const Simmtx* sm, int* ends)          src/fwd2d1.cc:324-337
+ * for a batch of (a, b) pairs.  mtx = Simmtx::mtx flattened dim x dim in the caller's VTYPE
+ * (float when vtype == 0, double when 1).  out_scores[p] receives the score in that VTYPE.
+ * out_ends (nullable, 2 ints per pair) is the `ends` output of the semi-global variant. */
+int pg_score_pairs(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx, const int32_t *b_idx,
+                   int64_t npairs, const pg_params *prm, const void *mtx, int32_t dim,
+                   void *out_scores, int32_t *out_ends);
+
+/* ---- batch level: stands behind
+ *   FTYPE* calcdist(mSeq** sbuf, int nn, DistCal realign = DynScr)            src/phyl.cc:318-342
+ * (selfscr :253-261, dpscore :221-251, alnscore2dist src/aln2.cc:289-334) for single sequences.
+ * Fills out_dist[k - k_begin] for the condensed indices k in [k_begin, k_end), k = elem(i,j) =
+ * j(j-1)/2 + i, i < j (src/cmn.h:115), a = sequence i, b = sequence j; values 100*(1 - ...)
+ * in FTYPE (float when vtype == 0, double when 1).  [k_begin, k_end) is the shard of one rank. */
+int pg_calcdist(pg_context *ctx, const pg_seqs *seqs, const pg_params *prm, const void *mtx,
+                int32_t dim, int64_t k_begin, int64_t k_end, void *out_dist);
+
+/* ---- device-resident variants (inputs already in HBM; used for sharded multi-GPU runs) ------ */
+typedef struct pg_dev_seqs pg_dev_seqs;
+int  pg_seqs_upload(pg_context *ctx, const pg_seqs *seqs, pg_dev_seqs **out);
+void pg_seqs_free(pg_context *ctx, pg_dev_seqs *d);
+/* d_out_dist: DEVICE pointer to (k_end - k_begin) FTYPE values; stream: cudaStream_t or NULL.
+ * Asynchronous with respect to the host; *n_launches (nullable) receives the number of kernels. */
+int pg_calcdist_dev(pg_context *ctx, pg_dev_seqs *seqs, const pg_params *prm, const void *mtx,
+                    int32_t dim, int64_t k_begin, int64_t k_end, void *d_out_dist, void *stream,
+                    int32_t *n_launches);
+
+/* ---- measurement helpers ------------------------------------------------------------------- */
+/* Number of DP cells the reference's loops visit for the pairs k in [k_begin, k_end)
+ * (rows m in window, columns in the stripe() band; src/aln2.cc:156-174). */
+int64_t pg_calcdist_cells(const pg_seqs *seqs, const pg_params *prm, int64_t k_begin, int64_t k_end);
+/* Register-only DPX micro-benchmark: measured issue rate of __viaddmax_s32 / __vimax3_s32 chains,
+ * in 1e9 thread-instructions per second for the whole device; the roofline denominator. */
+int pg_dpx_peak(pg_context *ctx, double *gops_s32, double *gops_s16x2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,91 @@
+// pg_internal.h -- shared declarations between the C ABI (pg_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/prrn_gpu.h"
+
+// ---- device view of a sequence set ---------------------------------------------------------------
+struct PgDevSeqs {
+    const uint8_t* res;     // concatenated residue codes
+    const int64_t* offs;    // [nseq]
+    const int32_t* left;    // [nseq] window start (absolute within the sequence)
+    const int32_t* wlen;    // [nseq] window length  right - left
+    const uint8_t* flags;   // [nseq] bit0 exgl, bit1 exgr, bit2 left != 0, bit3 right != len
+    int32_t nseq;
+};
+
+// epilogue selector of the score kernel
+enum PgEpilogue {
+    PG_EPI_SCORE_F32 = 0,   // VTYPE float score        (alnScoreD, aln build)
+    PG_EPI_SCORE_F64 = 1,   // VTYPE double score       (alnScoreD, prrn build)
+    PG_EPI_DIST_F32 = 2,    // 100*(1 - (scr + u|dl|/2)/sqrt(self_a self_b)) in float  (dpscore)
+    PG_EPI_DIST_F64 = 3,    // same in double
+};
+
+// One work item = one query (rows) against a run of subjects (columns); one CTA builds the query
+// profile once and its warps take the subjects.
+struct PgItem {
+    int32_t q;          // sequence index of the rows
+    int32_t sub_begin;  // implicit mode: first subject sequence index; explicit: index into pair_s[]
+    int32_t sub_end;
+    int32_t pad;
+};
+
+struct K1Args {
+    PgDevSeqs seqs;
+    const PgItem* items;
+    int32_t nitems;
+    int32_t* counter;           // dynamic item counter (zeroed before launch)
+    // explicit pair mode (pg_score_pairs): subject index and output slot per sorted pair
+    const int32_t* pair_s;      // nullptr => implicit all-vs-all: subject = sub index, out = elem(q,s)-k_begin
+    const int64_t* pair_out;
+    const uint8_t* pair_swap;   // explicit mode: 1 if (rows, cols) = (b, a) of the caller's pair
+    int64_t k_begin, k_end;     // implicit mode: only k in [k_begin, k_end) is written
+    const int32_t* mtx;         // dim x dim integer scores
+    int32_t dim;
+    int32_t u, v;               // integer uu, vv
+    int32_t sh;
+    int32_t tgapf_zero;         // 1 when tgapf == 0 (free terminal gaps at true sequence ends)
+    float u_f32;                // alprm.u as float for the distance epilogue
+    const int32_t* self;        // per-sequence self scores (dist epilogues)
+    int32_t epilogue;
+    void* out;
+    int2* rowbuf;               // multi-pass scratch: [grid warps][rowbuf_stride]
+    int64_t rowbuf_stride;
+};
+
+struct pg_dev_seqs {
+    PgDevSeqs v;
+    void* blob;                 // single device allocation holding everything
+    std::vector<int32_t> h_wlen;    // host copies needed to build work items
+    int32_t max_wlen;
+    int32_t max_code;           // largest residue code inside the windows
+    uint8_t present[256];       // which residue codes occur inside the windows
+};
+
+struct pg_context {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    std::string err;
+    // reusable device workspace
+    void* d_items; size_t items_cap;
+    void* d_mtx; size_t mtx_cap;
+    void* d_self; size_t self_cap;
+    void* d_rowbuf; size_t rowbuf_cap;
+    void* d_out; size_t out_cap;
+    void* d_pairs; size_t pairs_cap;
+    int32_t* d_counter;
+};
+
+// kernels (k1_score.cu)
+cudaError_t k1_launch(const K1Args& a, int grid_blocks, cudaStream_t st);
+int k1_rows_per_pass();
+int k1_warps_per_block();
+int k1_blocks_per_sm();
+cudaError_t k1_self_launch(const PgDevSeqs& s, const int32_t* mtx, int dim, int32_t* self, cudaStream_t st);
+// dpx_peak.cu
+cudaError_t dpx_peak_run(int sm_count, cudaStream_t st, double* gops_s32, double* gops_s16x2);

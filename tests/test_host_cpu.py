@@ -1,0 +1,85 @@
+"""CPU-side checks of the product's host logic: the C-ABI library loads and exports every symbol the
+header declares, the cell counter matches the oracle's loop-bound definition, and the kernel's
+per-lane recurrence / band logic (k1_core.cuh, compiled for the host) reproduces the reference."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden, golden_names
+import prrn_aln_b200 as P
+from prrn_aln_b200 import seqcode
+
+
+def test_library_loads_and_exports_declared_symbols():
+    L = P.load_library()
+    names = P.declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(L, n), "libprrn_gpu.so does not export " + n
+    assert b"sm_100a" in L.pg_version()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(P.PgError) as e:
+        P.Context(0)
+    assert e.value.code == 1 and "no CPU fallback" in str(e.value)
+
+
+def test_cell_count_matches_oracle(oracle):
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 2, 7, 33, 100, 257, 400, 513]
+    enc = [rng.integers(3, 23, size=n).astype(np.uint8) for n in lens]
+    ss = P.SeqSet(enc)
+    for sh in (-60, -50, -100, -5, 0, 3, 50, 1000):
+        prm = P.Params(P.ALPRM(sh=sh))
+        want = 0
+        for j in range(1, len(enc)):
+            for i in range(j):
+                want += oracle.band_cells(oracle.seq(enc[i]), oracle.seq(enc[j]), sh)
+        assert P.calcdist_cells(ss, prm) == want, sh
+    # a sub-range of the condensed index
+    prm = P.Params(P.ALPRM(sh=-60))
+    n = len(enc)
+    tot = sum(P.calcdist_cells(ss, prm, k, k + 1) for k in range(n * (n - 1) // 2))
+    assert tot == P.calcdist_cells(ss, prm)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = os.path.join(ROOT, "tests", "host_emul", "k1_emul.cc")
+    out = os.path.join(ROOT, "tests", "host_emul", "libk1emul.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", out, src])
+    L = C.CDLL(out)
+    L.k1_emul_score.restype = C.c_int
+    return L
+
+
+def _emul_score(L, q, s, mtx, u, v, sh, R):
+    q = np.ascontiguousarray(q, np.uint8)
+    s = np.ascontiguousarray(s, np.uint8)
+    m = np.ascontiguousarray(mtx, np.int32)
+    return L.k1_emul_score(q.ctypes.data_as(C.c_void_p), len(q), s.ctypes.data_as(C.c_void_p), len(s),
+                           m.ctypes.data_as(C.c_void_p), m.shape[0], u, v, sh, -v, -u, -v, -u, R)
+
+
+@pytest.mark.parametrize("name", ["score_p24_blosum62", "score_p24_sh3", "score_p24_sh0", "score_p24_u3v11",
+                                  "score_ragged", "score_long1300", "score_c1_ce13a"])
+def test_kernel_recurrence_emulation_matches_reference(emul, name):
+    """k1_core.cuh (the code the CUDA kernel runs per lane), emulated warp-wide on the host."""
+    g = golden(name)
+    enc = [seqcode.encode_protein(x) for x in g["seqs"]]
+    M = np.array(g["matrix"]).astype(np.int32)
+    u, v, sh = int(float(g["params"]["u"])), int(float(g["params"]["v"])), int(g["params"]["sh"])
+    n = len(enc)
+    for R in (4, 16):
+        for j in range(1, n):
+            for i in range(j):
+                want = g["scores"][j * (j - 1) // 2 + i]
+                assert _emul_score(emul, enc[i], enc[j], M, u, v, sh, R) == want
+                assert _emul_score(emul, enc[j], enc[i], M, u, v, sh, R) == want  # rows/cols swapped
