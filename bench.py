@@ -186,7 +186,8 @@ def main():
 
     ctx = P.Context(local)
     dseqs = ctx.upload(ss)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()         # a real (non-default) stream: kernels, NCCL and timing events share it
+    torch.cuda.set_stream(stream)
     d_shard = torch.empty(chunk, dtype=torch.float64, device="cuda")
     d_all = torch.empty(chunk * world, dtype=torch.float64, device="cuda") if world > 1 else d_shard
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2

@@ -29,7 +29,9 @@ def _params(g):
 
 
 def _integer_case(g):
-    M = np.array(g["matrix"])
+    # codes 3..22 are the 20 standard residues of the synthetic sets; the reference leaves a few
+    # entries of rarely used codes (e.g. mtx[SEC][SEC]) uninitialised, so only look at those rows
+    M = np.array(g["matrix"])[3:23, 3:23]
     return float(g["params"]["tgapf"]) == 1.0 and np.all(M == np.rint(M))
 
 
