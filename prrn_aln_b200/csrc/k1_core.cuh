@@ -172,7 +172,7 @@ static inline int k1_emulate_pair(const uint8_t* q, const uint8_t* s, const K1Ge
                 const int mbase = pbase + t * R;
                 int h_up, f_up;
                 if (t == 0) {
-                    if (pass == 0) { h_up = k1_top(g, n); f_up = K1_NEG; }
+                    if (pass == 0) { h_up = k1_top(g, n); f_up = K1_ADDMAX(h_up, negv, K1_NEG); }
                     else { h_up = rowH[n]; f_up = rowF[n]; }
                 } else { h_up = send_h[prv][t - 1]; f_up = send_f[prv][t - 1]; }
                 int kL, kU;

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k1_score_kernel(const 
                     if (n >= 0 && n < LS && lane < lanes) {
                         int h_up = recv_h, f_up = recv_f;
                         if (lane == 0) {
-                            if (pass == 0) { h_up = k1_top(g, n); f_up = K1_NEG; }
+                            if (pass == 0) { h_up = k1_top(g, n); f_up = K1_ADDMAX(h_up, negv, K1_NEG); }  // gg may open from the boundary row (fwd2d1.cc:148)
                             else { int2 v = __ldcg(rowbuf + n); h_up = v.x; f_up = v.y; }
                         }
                         // band poke: rows on diagonal lw / up+1 lose their horizontal input

@@ -175,3 +175,22 @@ def test_full_size_properties_c2(ctx, oracle):
     idx = list(range(0, n, 50))
     sc = ctx.score_pairs(ss, idx, idx, prm, M)
     assert np.array_equal(sc.astype(np.float64), np.array([self_s[i] for i in idx]))
+
+
+def test_fuzz_small_adversarial_pairs(ctx, oracle):
+    """Thousands of tiny pairs (lengths 1..40, small alphabets, narrow bands, v down to 0) in one
+    batch per parameter set: band cuts and boundary openings decide these scores."""
+    M = np.array(golden("score_p24_blosum62")["matrix"])
+    rng = np.random.default_rng(77)
+    for sh, u, v in ((0, 1, 0), (1, 2, 9), (3, 3, 5), (-30, 2, 1), (-100, 1, 12), (2, 2, 9)):
+        enc = []
+        for _ in range(600):
+            hi = 3 + int(rng.choice([2, 4, 20]))
+            enc.append(rng.integers(3, hi, size=int(rng.integers(1, 40))).astype(np.uint8))
+        ia = rng.integers(0, len(enc), size=3000).astype(np.int32)
+        ib = rng.integers(0, len(enc), size=3000).astype(np.int32)
+        prm = P.Params(P.ALPRM(u=u, v=v, sh=sh))
+        got = ctx.score_pairs(P.SeqSet(enc), ia, ib, prm, M)
+        op = oracle.params(u=u, v=v, sh=sh)
+        want = np.array([oracle.aln_score_d(oracle.seq(enc[i]), oracle.seq(enc[j]), M, op) for i, j in zip(ia, ib)])
+        assert np.array_equal(got.astype(np.float64), want), (sh, u, v)

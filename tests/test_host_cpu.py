@@ -83,3 +83,23 @@ def test_kernel_recurrence_emulation_matches_reference(emul, name):
                 want = g["scores"][j * (j - 1) // 2 + i]
                 assert _emul_score(emul, enc[i], enc[j], M, u, v, sh, R) == want
                 assert _emul_score(emul, enc[j], enc[i], M, u, v, sh, R) == want  # rows/cols swapped
+
+
+def test_kernel_recurrence_fuzz_small_adversarial(emul, oracle):
+    """Tiny sequences, tiny alphabets, narrow bands, v in {0..12}: the corner cases where band cuts
+    and boundary openings decide the score (found a top-boundary vertical-open bug in round 1)."""
+    M = np.array(golden("score_p24_blosum62")["matrix"])
+    Mi = np.nan_to_num(M).astype(np.int32)
+    rng = np.random.default_rng(2024)
+    for _ in range(4000):
+        la, lb = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        hi = 3 + int(rng.choice([2, 4, 20]))
+        a = rng.integers(3, hi, size=la).astype(np.uint8)
+        b = rng.integers(3, hi, size=lb).astype(np.uint8)
+        sh = int(rng.choice([-100, -60, -30, -10, 0, 1, 2, 3, 5, 100]))
+        u, v = int(rng.choice([1, 2, 3])), int(rng.choice([0, 1, 5, 9, 12]))
+        want = oracle.aln_score_d(oracle.seq(a), oracle.seq(b), M, oracle.params(u=u, v=v, sh=sh))
+        R = int(rng.choice([4, 8, 16]))
+        got = emul.k1_emul_score(a.ctypes.data_as(C.c_void_p), la, b.ctypes.data_as(C.c_void_p), lb,
+                                 Mi.ctypes.data_as(C.c_void_p), 25, u, v, sh, -v, -u, -v, -u, R)
+        assert got == want, (la, lb, sh, u, v, R)
