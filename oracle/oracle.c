@@ -202,3 +202,219 @@ void orc_calcdist(const orc_seq *seqs, int nn, const double *mtx, int dim, const
         }
     free(self);
 }
+
+/* ================================================================================================
+ * Pairwise alignment with path: Fwd2c<DPunit>::forwardB for two single sequences (NGP).
+ * Rows are swept in (m, n) order with rolling rows of records {val, dir, ptr}; the record store is
+ * a plain growable array (the reference's Vmf is a linked list of 7,680-record blocks).
+ * ================================================================================================ */
+enum { O_DEAD = 0, O_DIAG = 2, O_NEWD = 3, O_VERT = 4, O_HORI = 8, O_NEWV = 12, O_NEWH = 13 }; /* aln.h:47-52 */
+static int o_isdiag(int d) { d &= 15; return d == 2 || d == 3; }                     /* aln.h:60-62 */
+static int o_isvert(int d) { d &= 15; return d == 4 || d == 5 || d == 6 || d == 7 || d == 12; }
+static int o_ishori(int d) { d &= 15; return d == 8 || d == 9 || d == 10 || d == 11 || d == 13; }
+
+typedef struct { int32_t m, n; long p; } o_rec;
+typedef struct { o_rec *v; long n, cap; } o_store;
+static long o_add(o_store *s, int m, int n, long p)
+{
+    if (s->n == s->cap) { s->cap = s->cap ? 2 * s->cap : 1024; s->v = (o_rec *)realloc(s->v, sizeof(o_rec) * (size_t)s->cap); }
+    s->v[s->n].m = m; s->v[s->n].n = n; s->v[s->n].p = p;
+    return s->n++;
+}
+
+#define DEFINE_ALIGN_NGP(VT, SUFFIX, NEVSEL_V)                                                       \
+typedef struct { VT val; int dir; long ptr; } o_unit_##SUFFIX;                                      \
+static int align_ngp_##SUFFIX(const orc_seq *a, const orc_seq *b, const double *mtx, int dim,       \
+                              const orc_params *p, double *score, orc_skl *out, int cap)            \
+{                                                                                                   \
+    typedef o_unit_##SUFFIX U;                                                                      \
+    /* PwdB::PwdB (aln2.cc:97-117), PwdM::resetuab (maln2.cc:227-243), single sequences: Vab = scale */\
+    const float fu = (float)p->u, fv = (float)p->v, fu1 = (float)p->u1, fsc = (float)p->scale;      \
+    const VT Vab = (VT)(fsc * 1 * 1);                                                               \
+    const VT BasicGOP = (VT)(-fv * Vab), BasicGEP = (VT)(-fu * Vab), LongGEP = (VT)(-fu1 * Vab);    \
+    const VT diffu = LongGEP - BasicGEP;                                                            \
+    const VT LongGOP = BasicGOP - diffu * p->k1;                                                    \
+    const int Noll = p->ls < 2 ? 2 : (p->ls > 3 ? 3 : p->ls);                                       \
+    const int codonk1 = p->ls == 3 ? p->k1 : (INT_MAX / 8 * 7); /* LARGEN */                        \
+    /* Fwd2c ctor (fwd2c.h:85-86): FTYPE ratios; FTYPE == VT in both builds */                      \
+    const VT u2divu1 = BasicGEP < 0 ? (VT)LongGEP / BasicGEP : 0;                                   \
+    const VT v2divv1 = BasicGOP < 0 ? (VT)LongGOP / BasicGOP : 0;                                   \
+    const VT Basic_GOP = (VT)(-fsc * fv);          /* maln2.cc:232; vgop(x) = Basic_GOP * x */      \
+    const VT unp = (VT)(1 * 1 * -fu);              /* unp1 (maln.h:185) with cfq = efq = 1 */       \
+    orc_window w;                                                                                   \
+    orc_stripe(a, b, p->sh, &w);                                                                    \
+    const int lw = w.lw, up = w.up;                                                                 \
+    const int al = a->left, ar = a->right, bl = b->left, br = b->right;                             \
+    const U black = {NEVSEL_V, 0, 0};                                                               \
+    o_store st = {0, 0, 0};                                                                         \
+    o_add(&st, 0, 0, 0);                           /* skip 0-th record (fwd2c.h:361) */             \
+    /* rows over columns n in [bl-1, br): slot j = n - bl + 1.  Hp/Gp/G2p = row m-1 */              \
+    const int NB = br - bl + 2;                                                                     \
+    U *buf = (U *)malloc(sizeof(U) * 6 * (size_t)NB);                                               \
+    U *Hp = buf, *Gp = buf + NB, *G2p = buf + 2 * NB, *Hc = buf + 3 * NB, *Gc = buf + 4 * NB, *G2c = buf + 5 * NB;\
+    for (int j = 0; j < NB; ++j) Hp[j] = Gp[j] = G2p[j] = Hc[j] = Gc[j] = G2c[j] = black;            \
+    /* initB (fwd2c.h:138-176): origin + boundary row */                                            \
+    Hp[0].val = 0; Hp[0].dir = O_DIAG; Hp[0].ptr = o_add(&st, al, bl, 0);                            \
+    {                                                                                               \
+        int rr = br - al; if (up < rr) rr = up;                                                     \
+        int r0 = bl - al;                                                                           \
+        for (int r = r0 + 1, k = 1; r <= rr; ++r, ++k) {                                            \
+            const U *src = &Hp[k - 1];                                                              \
+            VT gnp = o_ishori(src->dir) ? (VT)0 : (VT)(Basic_GOP * 1);  /* gapopen(h-1,..,-1) */     \
+            gnp = (k < codonk1) ? gnp + unp : (VT)(v2divv1 * gnp + u2divu1 * unp);                  \
+            Hp[k].dir = o_isvert(src->dir) ? O_NEWH : O_HORI;                                       \
+            Hp[k].val = src->val + gnp; Hp[k].ptr = src->ptr;                                       \
+        }                                                                                           \
+    }                                                                                               \
+    /* boundary column values H(m, bl-1), m = al .. : computed incrementally below */               \
+    U colprev = Hp[0];                                                                              \
+    int colk = 0;                                                                                   \
+    const int rr_col = (bl - ar > lw) ? bl - ar : lw;   /* lowest diagonal the column reaches */     \
+    for (int m = al; m < ar; ++m) {                                                                 \
+        const int n0 = ORC_MAX(m + lw, bl), n9 = ORC_MIN(m + up + 1, br);                           \
+        const double *srow = mtx + (size_t)a->res[m] * dim;                                         \
+        /* boundary column cell of this row: diagonal r = bl-1-m, exists while r >= rr_col */        \
+        {                                                                                           \
+            int r = bl - 1 - m;                                                                     \
+            if (r >= rr_col) {                                                                      \
+                ++colk;                                                                             \
+                VT gnp = o_isvert(colprev.dir) ? (VT)0 : (VT)(Basic_GOP * 1);                       \
+                gnp = (colk < codonk1) ? gnp + unp : (VT)(v2divv1 * gnp + u2divu1 * unp);           \
+                U c; c.dir = o_ishori(colprev.dir) ? O_NEWV : O_VERT;                               \
+                c.val = colprev.val + gnp; c.ptr = colprev.ptr;                                     \
+                colprev = c; Hc[0] = c;                                                             \
+            } else Hc[0] = black;                                                                   \
+        }                                                                                           \
+        U f1 = black, f2 = black;                                                                   \
+        for (int n = n0; n < n9; ++n) {                                                             \
+            const int j = n - bl + 1;                                                               \
+            const int above_inband = (n - m + 1 <= up);  /* H[r+1]/G[r+1] sentinel otherwise */      \
+            const U habove = above_inband ? Hp[j] : black, gabove = above_inband ? Gp[j] : black;   \
+            const U g2above = above_inband ? G2p[j] : black;                                        \
+            const U hleft = (n - 1 >= n0 || n - 1 == bl - 1) ? Hc[j - 1] : black;                   \
+            /* diagonal (fwd2c.h:395-398) */                                                        \
+            U h = Hp[j - 1];                                                                        \
+            h.dir = o_isdiag(h.dir) ? O_DIAG : O_NEWD;                                              \
+            h.val = h.val + ((VT)srow[b->res[n]] + (VT)0);                                          \
+            U g = black, g2 = black;                                                                \
+            const U *mx = &g;                                                                       \
+            VT gop = 0, gnp;                                                                        \
+            if (m > al) {                                                                           \
+                /* vertical (fwd2c.h:401-409) */                                                    \
+                gnp = o_isvert(gabove.dir) ? (VT)0 : Basic_GOP;                                     \
+                gop = o_isvert(habove.dir) ? (VT)0 : Basic_GOP;                                     \
+                if (!o_isvert(habove.dir) && habove.val + gop > gabove.val + gnp) {                 \
+                    g.dir = o_ishori(habove.dir) ? O_NEWV : O_VERT; g.val = habove.val + gop; g.ptr = habove.ptr;\
+                } else {                                                                            \
+                    g.dir = o_ishori(gabove.dir) ? O_NEWV : O_VERT; g.val = gabove.val + gnp; g.ptr = gabove.ptr;\
+                }                                                                                   \
+                g.val += unp;                                                                       \
+                if (Noll == 3) {                   /* vertical2 (fwd2c.h:411-420) */                \
+                    gnp = (VT)(v2divv1 * (o_isvert(g2above.dir) ? (VT)0 : Basic_GOP));              \
+                    gop = (VT)(v2divv1 * gop);                                                      \
+                    if (!o_isvert(habove.dir) && habove.val + gop > g2above.val + gnp) {            \
+                        g2.dir = o_ishori(habove.dir) ? O_NEWV : O_VERT; g2.val = habove.val + gop; g2.ptr = habove.ptr;\
+                    } else {                                                                        \
+                        g2.dir = o_ishori(g2above.dir) ? O_NEWV : O_VERT; g2.val = g2above.val + gnp; g2.ptr = g2above.ptr;\
+                    }                                                                               \
+                    g2.val += (VT)(u2divu1 * unp);                                                  \
+                    if (g2.val > mx->val) mx = &g2;                                                 \
+                }                                                                                   \
+            } else {                                                                                \
+                /* first row: the g rows keep whatever the buffer holds = black (fwd2c.cc:39) */    \
+                g = black; g2 = black;                                                              \
+            }                                                                                       \
+            if (n > bl) {                                                                           \
+                /* horizontal (fwd2c.h:422-431) */                                                  \
+                gnp = o_ishori(f1.dir) ? (VT)0 : Basic_GOP;                                         \
+                gop = o_ishori(hleft.dir) ? (VT)0 : Basic_GOP;                                      \
+                if (!o_ishori(hleft.dir) && hleft.val + gop > f1.val + gnp) {                       \
+                    U t; t.dir = o_isvert(hleft.dir) ? O_NEWH : O_HORI; t.val = hleft.val + gop; t.ptr = hleft.ptr; f1 = t;\
+                } else {                                                                            \
+                    f1.dir = o_isvert(f1.dir) ? O_NEWH : O_HORI; f1.val = f1.val + gnp;             \
+                }                                                                                   \
+                f1.val += unp;                                                                      \
+                if (f1.val >= mx->val) mx = &f1;                                                    \
+                if (Noll == 3) {                   /* horizontal2 (fwd2c.h:433-442) */              \
+                    gnp = (VT)(v2divv1 * (o_ishori(f2.dir) ? (VT)0 : Basic_GOP));                   \
+                    gop = (VT)(v2divv1 * gop);                                                      \
+                    if (!o_ishori(hleft.dir) && hleft.val + gop > f2.val + gnp) {                   \
+                        U t; t.dir = o_isvert(hleft.dir) ? O_NEWH : O_HORI; t.val = hleft.val + gop; t.ptr = hleft.ptr; f2 = t;\
+                    } else {                                                                        \
+                        f2.dir = o_isvert(f2.dir) ? O_NEWH : O_HORI; f2.val = f2.val + gnp;         \
+                    }                                                                               \
+                    f2.val += (VT)(u2divu1 * unp);                                                  \
+                    if (f2.val >= mx->val) mx = &f2;                                                \
+                }                                                                                   \
+            }                                                                                       \
+            if (mx->val > h.val) h = *mx;          /* fwd2c.h:453 */                                \
+            if (h.dir == O_NEWD || h.dir == O_NEWV || h.dir == O_NEWH)                              \
+                h.ptr = o_add(&st, m, n, h.ptr);   /* fwd2c.h:465-467 */                            \
+            Hc[j] = h; Gc[j] = g; G2c[j] = g2;                                                      \
+        }                                                                                           \
+        U *t;                                                                                       \
+        t = Hp; Hp = Hc; Hc = t; t = Gp; Gp = Gc; Gc = t; t = G2p; G2p = G2c; G2c = t;              \
+    }                                                                                               \
+    /* result cell H[b.right - a.right] = H(ar-1, br-1) (fwd2c.h:475-481) */                        \
+    U last = Hp[br - 1 - bl + 1];                                                                   \
+    long pp = o_add(&st, ar, br, last.ptr);                                                         \
+    *score = (double)last.val;                                                                      \
+    /* Vmf::traceback (vmf.cc:103-119) */                                                           \
+    int cnt = 0, ok = 1;                                                                            \
+    for (long q = pp;; q = st.v[q].p) {                                                             \
+        if (cnt + 1 >= cap) { ok = 0; break; }                                                      \
+        out[++cnt].m = st.v[q].m; out[cnt].n = st.v[q].n;                                           \
+        if (!st.v[q].p) break;                                                                      \
+    }                                                                                               \
+    out[0].m = 0; out[0].n = cnt;                                                                   \
+    free(buf); free(st.v);                                                                          \
+    return ok ? cnt : -1;                                                                           \
+}
+
+DEFINE_ALIGN_NGP(float, f32, (-(FLT_MAX / 16 * 7)))
+DEFINE_ALIGN_NGP(double, f64, (-(DBL_MAX / 16 * 7)))
+
+int orc_align_ngp(const orc_seq *a, const orc_seq *b, const double *mtx, int dim, const orc_params *p,
+                  double *score, orc_skl *out, int cap)
+{
+    return p->vtype ? align_ngp_f64(a, b, mtx, dim, p, score, out, cap)
+                    : align_ngp_f32(a, b, mtx, dim, p, score, out, cap);
+}
+
+static int o_sklcmp(const void *x, const void *y)
+{
+    const orc_skl *a = (const orc_skl *)x, *b = (const orc_skl *)y;
+    int d = a->m - b->m;
+    return d ? d : a->n - b->n;
+}
+
+int orc_stdskl(const orc_skl *skl, orc_skl *out)
+{   /* gaps.cc:139-175 */
+    int num = skl[0].n;
+    if (num < 2) { for (int i = 0; i <= num; ++i) out[i] = skl[i]; return num; }
+    orc_skl *org = (orc_skl *)malloc(sizeof(orc_skl) * (size_t)num);
+    memcpy(org, skl + 1, sizeof(orc_skl) * (size_t)num);
+    qsort(org, (size_t)num, sizeof(orc_skl), o_sklcmp);
+    orc_skl *wrk = out + 1;
+    int pr = 2, prv = 0;
+    for (int i = 1; i < num; ++i) {
+        int dm = org[i].m - org[prv].m, dn = org[i].n - org[prv].n;
+        if (!dm && !dn) continue;
+        if (dm < 0 || dn < 0) continue;
+        int dd = dm < dn ? dm : dn;
+        int df = dn - dm;
+        if (df) df = df > 0 ? 1 : -1;
+        if (dd && df) {
+            if (pr) *wrk++ = org[prv];
+            wrk->m = org[prv].m + dd; wrk->n = org[prv].n + dd; ++wrk;
+        } else if (df != pr || !dm)
+            *wrk++ = org[prv];
+        pr = df;
+        prv = i;
+    }
+    *wrk++ = org[prv];
+    int cnt = (int)(wrk - out - 1);
+    out[0].n = cnt; out[0].m = skl[0].m;
+    free(org);
+    return cnt;
+}

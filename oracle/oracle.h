@@ -66,6 +66,21 @@ double orc_score2dist(double scr, int la, int lb, double self_a, double self_b, 
 void orc_calcdist(const orc_seq *seqs, int nn, const double *mtx, int dim, const orc_params *p,
                   double *dist, double *raw_scores);
 
+/* ---- pairwise alignment with path (NGP: two single, ungapped sequences) ------------------------ */
+typedef struct { int32_t m, n; } orc_skl;
+
+/* alignC<DPunit>() = Fwd2c<DPunit>::Fwd2c + initB + forwardB + Vmf::traceback for two single
+ * sequences without internal gaps and without nil ends (global mode, tgapf == 1, thickness == 1):
+ * reference src/fwd2c.h:81-100,138-176,359-482,670-677; src/fwd2c.cc:32-102; src/vmf.cc:103-119.
+ * Affine (ls < 3) or two-piece (ls == 3, src/fwd2c.h:411-442).  Writes the corner list in Vmf
+ * back-walk order into out[0..cap) exactly as alignC returns it (out[0].n = count) and returns the
+ * number of corners, or -1 if cap is too small.  *score receives the DP score. */
+int orc_align_ngp(const orc_seq *a, const orc_seq *b, const double *mtx, int dim, const orc_params *p,
+                  double *score, orc_skl *out, int cap);
+
+/* stdskl(): reference src/gaps.cc:139-175.  skl[0].n = count; normalises in place into out
+ * (capacity 2*count+2); returns the new count. */
+int orc_stdskl(const orc_skl *skl, orc_skl *out);
 #ifdef __cplusplus
 }
 #endif

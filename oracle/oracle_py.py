@@ -99,3 +99,29 @@ def calcdist(seqs, mtx, p, want_scores=True):
     lib().orc_calcdist(arr, n, mp, dim, C.byref(p), dist.ctypes.data_as(C.POINTER(C.c_double)),
                        raw.ctypes.data_as(C.POINTER(C.c_double)) if want_scores else None)
     return dist, raw
+
+
+class OrcSkl(C.Structure):
+    _fields_ = [("m", C.c_int32), ("n", C.c_int32)]
+
+
+def align_ngp(a, b, mtx, p, std=True):
+    """alignC<DPunit> restatement (+ stdskl when std): returns (score, [(m, n), ...])."""
+    L = lib()
+    L.orc_align_ngp.restype = C.c_int
+    L.orc_align_ngp.argtypes = [C.POINTER(OrcSeq), C.POINTER(OrcSeq), C.POINTER(C.c_double), C.c_int,
+                                C.POINTER(OrcParams), C.POINTER(C.c_double), C.POINTER(OrcSkl), C.c_int]
+    L.orc_stdskl.restype = C.c_int
+    L.orc_stdskl.argtypes = [C.POINTER(OrcSkl), C.POINTER(OrcSkl)]
+    m, mp, dim = _mtx(mtx)
+    cap = 2 * (a.len + b.len) + 8
+    out = (OrcSkl * cap)()
+    scr = C.c_double(0)
+    cnt = L.orc_align_ngp(C.byref(a), C.byref(b), mp, dim, C.byref(p), C.byref(scr), out, cap)
+    if cnt < 0:
+        raise RuntimeError("corner list overflow")
+    if std:
+        out2 = (OrcSkl * (2 * cnt + 4))()
+        cnt = L.orc_stdskl(out, out2)
+        out = out2
+    return scr.value, [(out[i].m, out[i].n) for i in range(1, cnt + 1)]

@@ -33,3 +33,16 @@ def test_band_cells_matches_loop_bounds(oracle):
     assert oracle.band_cells(a, b, -50) == cells
     # absolute shoulder wider than the matrix -> full rectangle
     assert oracle.band_cells(a, b, 1000) == 140
+
+
+@pytest.mark.parametrize("name", golden_names("align_"))
+def test_alignment_scores_and_corner_lists_bit_exact(oracle, name):
+    """orc_align_ngp + orc_stdskl against align2 (alignC<DPunit> + stdskl) of the reference."""
+    g = golden(name)
+    enc = [seqcode.encode_protein(s) for s in g["seqs"]]
+    p = _oracle_params(oracle, g)
+    M = np.array(g["matrix"])
+    for pr in g["pairs"]:
+        scr, pts = oracle.align_ngp(oracle.seq(enc[pr["i"]]), oracle.seq(enc[pr["j"]]), M, p)
+        assert scr == pr["score"], (pr["i"], pr["j"])
+        assert pts == [tuple(x) for x in pr["skl"]], (pr["i"], pr["j"])

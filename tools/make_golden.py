@@ -42,6 +42,27 @@ def score_case(name, seqs, flavour="f", dna=False, **kv):
     print("wrote", name, "pairs", len(scores))
 
 
+def align_case(name, seqs, flavour="f", **kv):
+    """align2 per pair (alignC<DPunit> + stdskl): score and normalised corner list."""
+    os.makedirs(TMP, exist_ok=True)
+    fa = os.path.join(TMP, name + ".fa")
+    gen_synth.write_fasta(fa, seqs)
+    al = refio.run("align", fa, flavour=flavour, **kv)
+    mt = refio.run("matrix", fa, flavour=flavour, **kv)
+    n = len(seqs)
+    pairs = []
+    for j in range(1, n):
+        for i in range(j):
+            r = al["aligns"][(i, j)]
+            assert r["swp"] == 0
+            pairs.append(dict(i=i, j=j, mode=r["mode"], score=r["score"], skl=r["skl"]["pts"], fstat=al["fstat"][(i, j)]))
+    rec = dict(name=name, kind="align", flavour=flavour, params=al["header"], args=kv, seqs=seqs,
+               matrix=mt["matrix"].tolist(), pairs=pairs)
+    with open(os.path.join(GOLD, name + ".json"), "w") as f:
+        json.dump(rec, f)
+    print("wrote", name, "pairs", len(pairs))
+
+
 def sample_pair():
     """C1: the sample/pas ce13a1 x ce13a2 pair of sample/test.sh (annotation lines stripped)."""
     out = []
@@ -78,6 +99,19 @@ def main():
     long_ = gen_synth.synth_set(6, 1300, 0.1, 0.5, 31)
     score_case("score_long1300", long_)
     score_case("score_c1_ce13a", sample_pair(), sh=-50)
+    # alignments with path (align2 -> alignC<DPunit> -> stdskl)
+    p16 = p24[:16]
+    align_case("align_p16_blosum62", p16)
+    align_case("align_p16_sh3", gen_synth.synth_set(16, 150, 0.2, 0.9, 12), sh=3)
+    align_case("align_p16_u3v11", p16, u=3, v=11)
+    align_case("align_p16_twopiece_u1_1", p16, ls=3, u1=1)
+    align_case("align_p16_twopiece_default", p16, ls=3)
+    align_case("align_p16_twopiece_f64", p16, flavour="d", ls=3)
+    align_case("align_p16_pam_f32", p16, mtx="pam")
+    align_case("align_ragged", rag[:14])
+    align_case("align_c2_first12", gen_synth.config_set("c2", 12))
+    align_case("align_long1300", long_[:4])
+    align_case("align_c1_ce13a", sample_pair(), sh=-50)
 
 
 if __name__ == "__main__":
