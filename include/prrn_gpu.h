@@ -68,6 +68,21 @@ int pg_score_pairs(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx, c
                    int64_t npairs, const pg_params *prm, const void *mtx, int32_t dim,
                    void *out_scores, int32_t *out_ends);
 
+/* ---- per-call level: stands behind
+ *   template<class recd_t> SKL* alignC(mSeq* seqs[2], PwdM* pwd, VTYPE* scr, ...)   src/fwd2c.h:670-677
+ * for recd_t = DPunit (alnmode NGP_ALB: two single sequences, no internal gaps), i.e. the
+ * Fwd2c<DPunit> ctor + initB + forwardB + Vmf::traceback chain (src/fwd2c.h:81-176,359-482,
+ * src/vmf.cc:103-119) that align2 (src/maln2.cc:1888-1910) reaches, for a batch of (a, b) pairs.
+ * out_scores[p] = *scr in the caller's VTYPE.  The corner lists come back concatenated:
+ * (*out_pts)[(*out_offs)[p] .. (*out_offs)[p+1]) are skl[1..n] of pair p in Vmf back-walk order,
+ * exactly what alignC returns (the caller runs stdskl, src/gaps.cc:139, as align2 does).
+ * Both arrays are allocated by the library and released with pg_free. */
+typedef struct { int32_t m, n; } pg_skl;        /* SKL of src/cmn.h:124 */
+int pg_align_pairs(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx, const int32_t *b_idx,
+                   int64_t npairs, const pg_params *prm, const void *mtx, int32_t dim,
+                   void *out_scores, int64_t **out_offs, pg_skl **out_pts);
+void pg_free(void *p);
+
 /* ---- batch level: stands behind
  *   FTYPE* calcdist(mSeq** sbuf, int nn, DistCal realign = DynScr)            src/phyl.cc:318-342
  * (selfscr :253-261, dpscore :221-251, alnscore2dist src/aln2.cc:289-334) for single sequences.

@@ -80,6 +80,11 @@ def load_library():
     L.pg_destroy.restype = None
     L.pg_score_pairs.argtypes = [C.c_void_p, C.POINTER(_PgSeqs), C.c_void_p, C.c_void_p, C.c_int64,
                                  C.POINTER(Params), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.pg_align_pairs.argtypes = [C.c_void_p, C.POINTER(_PgSeqs), C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.POINTER(Params), C.c_void_p, C.c_int32, C.c_void_p,
+                                 C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32))]
+    L.pg_free.argtypes = [C.c_void_p]
+    L.pg_free.restype = None
     L.pg_calcdist.argtypes = [C.c_void_p, C.POINTER(_PgSeqs), C.POINTER(Params), C.c_void_p, C.c_int32,
                               C.c_int64, C.c_int64, C.c_void_p]
     L.pg_seqs_upload.argtypes = [C.c_void_p, C.POINTER(_PgSeqs), C.POINTER(C.c_void_p)]
@@ -175,6 +180,27 @@ class Context:
                                           C.byref(prm), m.ctypes.data, m.shape[0], out.ctypes.data, None))
         return out
 
+    # -- per-call level: batch of alignC<DPunit> ------------------------------------------------
+    def align_pairs(self, seqs, a_idx, b_idx, prm, mtx):
+        """Returns (scores, [corner array (n x 2, Vmf back-walk order) per pair]) as alignC does."""
+        a = np.ascontiguousarray(a_idx, dtype=np.int32)
+        b = np.ascontiguousarray(b_idx, dtype=np.int32)
+        m = _mtx_for(prm, mtx)
+        out = np.empty(len(a), dtype=prm.ftype)
+        offs = C.POINTER(C.c_int64)()
+        pts = C.POINTER(C.c_int32)()
+        cs = seqs.c_struct()
+        self._check(self.L.pg_align_pairs(self.h, C.byref(cs), a.ctypes.data, b.ctypes.data, len(a), C.byref(prm),
+                                          m.ctypes.data, m.shape[0], out.ctypes.data, C.byref(offs), C.byref(pts)))
+        try:
+            o = np.ctypeslib.as_array(offs, shape=(len(a) + 1,)).copy()
+            total = int(o[-1])
+            p = np.ctypeslib.as_array(pts, shape=(max(total, 1) * 2,)).copy()[:2 * total].reshape(-1, 2)
+        finally:
+            self.L.pg_free(offs)
+            self.L.pg_free(pts)
+        return out, [p[o[i]:o[i + 1]] for i in range(len(a))]
+
     # -- batch level: calcdist(DynScr) ------------------------------------------------------------
     def calcdist(self, seqs, prm, mtx, k_begin=0, k_end=None, out=None):
         npair = seqs.n * (seqs.n - 1) // 2
@@ -236,6 +262,44 @@ def alnScoreD(seqs, sm, prm=None, pairs=None, device=0):
     a = [p[0] for p in pairs]
     b = [p[1] for p in pairs]
     return _ctx(device).score_pairs(seqs, a, b, prm, sm)
+
+
+def stdskl(corners):
+    """SKL* stdskl(SKL** pskl) -- reference src/gaps.cc:139-175 -- the normalisation align2 applies to
+    the corner list alignC returns: sort by (m, n), drop repeats / inconsistent points, interpolate
+    the corner between a diagonal run and the gap that follows it."""
+    pts = sorted((int(m), int(n)) for m, n in corners)
+    if len(pts) < 2:
+        return pts
+    out = []
+    pr = 2
+    prv = pts[0]
+    for cur in pts[1:]:
+        dm, dn = cur[0] - prv[0], cur[1] - prv[1]
+        if (not dm and not dn) or dm < 0 or dn < 0:
+            continue
+        dd = min(dm, dn)
+        df = (dn > dm) - (dn < dm)
+        if dd and df:
+            if pr:
+                out.append(prv)
+            out.append((prv[0] + dd, prv[1] + dd))
+        elif df != pr or not dm:
+            out.append(prv)
+        pr = df
+        prv = cur
+    out.append(prv)
+    return out
+
+
+def align2(seqs, sm, prm=None, pairs=None, device=0):
+    """SKL* align2(mSeq* seqs[2], PwdM*, VTYPE* scr, Gsinfo*) -- reference src/maln2.cc:1875 -- for
+    alnmode NGP_ALB (two single sequences): alignC<DPunit> on the GPU + stdskl.  Returns
+    (scores, [normalised corner list per pair])."""
+    prm = prm or Params()
+    pairs = [(0, 1)] if pairs is None else pairs
+    scores, raw = _ctx(device).align_pairs(seqs, [p[0] for p in pairs], [p[1] for p in pairs], prm, sm)
+    return scores, [stdskl(r) for r in raw]
 
 
 def calcdist(seqs, sm, prm=None, device=0, k_begin=0, k_end=None):

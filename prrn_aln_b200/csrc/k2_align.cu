@@ -1,0 +1,195 @@
+// k2_align.cu -- kernel K2: pairwise banded affine alignment WITH path for two single sequences.
+//
+// Stands behind alignC<DPunit> (reference src/fwd2c.h:670-677: Fwd2c ctor :81, initB :138,
+// forwardB :359, Vmf::traceback src/vmf.cc:103): global NGP mode, thickness 1 (no nil ends),
+// integer scoring.  Two kernels:
+//   k2_fill_kernel   the K1 machine mapping (CTA = query profile, warp = alignment, lane = 16 rows,
+//                    systolic wavefront) + 4 direction bits per cell, one coalesced 256-byte store
+//                    per warp-step in wavefront order (k2_core.cuh);
+//   k2_trace_kernel  one thread per alignment: walks the bits back, replays the path forward with
+//                    the reference's record rules and emits the corner list in Vmf back-walk order.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "k2_core.cuh"
+#include "pg_internal.h"
+
+namespace {
+
+constexpr int R = 16;
+constexpr int NW = 8;
+constexpr int ROWS_PER_PASS = 32 * R;
+constexpr int MAXDIM = 32;
+constexpr int BLOCKS_PER_SM = 2;
+constexpr unsigned FULL = 0xffffffffu;
+
+__host__ __device__ inline size_t smem_bytes(int dim)
+{
+    return (size_t)(dim + NW) * (R / 4) * 32 * sizeof(int4) + 16;
+}
+
+__global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k2_fill_kernel(const K2Args a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int4* const sm_prof = reinterpret_cast<int4*>(smem_raw);
+    int4* const sm_poke = sm_prof + a.dim * (R / 4) * 32;
+    int* const sm_item = reinterpret_cast<int*>(sm_poke + NW * (R / 4) * 32);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int gwarp = blockIdx.x * NW + warp;
+    const int negv = -a.v;
+
+    for (;;) {
+        if (tid == 0) *sm_item = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int it = *sm_item;
+        if (it >= a.nitems) break;
+        const PgItem item = a.items[it];
+        const int qi = item.q;
+        const uint8_t* q = a.seqs.res + a.seqs.offs[qi] + a.seqs.left[qi];
+        const int LQ = a.seqs.wlen[qi];
+        const int npass = LQ > 0 ? (LQ + ROWS_PER_PASS - 1) / ROWS_PER_PASS : 1;
+
+        for (int pass = 0; pass < npass; ++pass) {
+            const int pbase = pass * ROWS_PER_PASS;
+            {
+                int* p = reinterpret_cast<int*>(sm_prof);
+                const int total = a.dim * 32 * R;
+                for (int idx = tid; idx < total; idx += NW * 32) {
+                    int letter = idx / (32 * R);
+                    int rem = idx - letter * (32 * R);
+                    int j = rem >> 7, ln = (rem >> 2) & 31, c = rem & 3;
+                    int row = pbase + ln * R + j * 4 + c;
+                    p[idx] = row < LQ ? a.mtx[(int)q[row] * a.dim + letter] + 2 * a.u : 0;
+                }
+            }
+            __syncthreads();
+
+            const int rows_here = min(LQ - pbase, ROWS_PER_PASS);
+            const int lanes = (rows_here + R - 1) / R;
+            const int mbase = pbase + lane * R;
+            const bool last_pass = pass == npass - 1;
+
+            for (int sub = item.sub_begin + warp, ord = 0; sub < item.sub_end; sub += NW, ++ord) {
+                const int si = a.pair_s[sub];
+                const uint8_t* s = a.seqs.res + a.seqs.offs[si] + a.seqs.left[si];
+                const int LS = a.seqs.wlen[si];
+                K1Geom g;
+                g.LQ = LQ; g.LS = LS; g.u = a.u; g.v = a.v;
+                k1_band(LQ, LS, a.sh, &g.lw, &g.up);
+                g.topOpen = -a.v; g.topExt = -a.u; g.leftOpen = -a.v; g.leftExt = -a.u;
+                if (LQ == 0 || LS == 0) {
+                    if (lane == 0 && pass == 0) a.score[sub] = 0;       // align2: nogap_skl, score untouched
+                    continue;
+                }
+                int2* rowbuf = a.rowbuf ? a.rowbuf + ((int64_t)gwarp * a.rowbuf_stride + (int64_t)ord * LS) : nullptr;
+                unsigned long long* words = a.dirs + a.dir_off[sub] + ((int64_t)pass * (LS + 31)) * 32 + lane;
+
+                K2Lane<R> L;
+                k2_lane_init(L, g, mbase);
+                const int lwm = g.lw + mbase;
+                const int upm = g.up + 1 + mbase;
+                int recv_h = K1_NEG, recv_g = K1_NEG;
+                const int4* pp = sm_prof + lane;
+                int4* pk = sm_poke + warp * ((R / 4) * 32) + lane;
+                const int nsteps = LS + lanes - 1;
+
+                for (int step = 0; step < nsteps; ++step) {
+                    const int n = step - lane;
+                    int h_dn = K1_NEG, g_dn = K1_NEG;
+                    if (n >= 0 && n < LS && lane < lanes) {
+                        int h_up = recv_h, g_up = recv_g;
+                        if (lane == 0) {
+                            if (pass == 0) { h_up = k1_top(g, n); g_up = K1_NEG; }
+                            else { int2 v = __ldcg(rowbuf + n); h_up = v.x; g_up = v.y; }
+                        }
+                        const int kL = n - lwm, kU = n - upm;
+                        if ((unsigned)kL < (unsigned)R || (unsigned)kU < (unsigned)R) {
+#pragma unroll
+                            for (int j = 0; j < R / 4; ++j)
+                                pk[j * 32] = make_int4(L.E[4 * j], L.E[4 * j + 1], L.E[4 * j + 2], L.E[4 * j + 3]);
+                            int* pki = reinterpret_cast<int*>(pk);
+                            if ((unsigned)kL < (unsigned)R) pki[(kL >> 2) * 128 + (kL & 3)] = K1_NEG;
+                            if ((unsigned)kU < (unsigned)R) pki[(kU >> 2) * 128 + (kU & 3)] = K1_NEG;
+#pragma unroll
+                            for (int j = 0; j < R / 4; ++j) {
+                                int4 v = pk[j * 32];
+                                L.E[4 * j] = v.x; L.E[4 * j + 1] = v.y; L.E[4 * j + 2] = v.z; L.E[4 * j + 3] = v.w;
+                            }
+                        }
+                        const int letter = __ldg(s + n);
+                        const int4* pl = pp + letter * ((R / 4) * 32);
+                        int sc[R];
+#pragma unroll
+                        for (int j = 0; j < R / 4; ++j) {
+                            int4 v = pl[j * 32];
+                            sc[4 * j] = v.x; sc[4 * j + 1] = v.y; sc[4 * j + 2] = v.z; sc[4 * j + 3] = v.w;
+                        }
+                        const unsigned long long bits =
+                            k2_lane_step(L, sc, negv, h_up, g_up, mbase == 0, &h_dn, &g_dn);
+                        __stcs(words + (int64_t)step * 32, bits);       // streaming: written once, read by the trace
+                        if (lane == 31 && !last_pass) __stcg(rowbuf + n, make_int2(h_dn, g_dn));
+                    }
+                    recv_h = __shfl_up_sync(FULL, h_dn, 1);
+                    recv_g = __shfl_up_sync(FULL, g_dn, 1);
+                }
+
+                if (last_pass) {
+                    const int tl = (rows_here - 1) / R, kf = (rows_here - 1) % R;
+                    int val = 0;
+#pragma unroll
+                    for (int k = 0; k < R; ++k)
+                        if (k == kf) val = L.H[k];
+                    val = __shfl_sync(FULL, val, tl);
+                    if (lane == 0) a.score[sub] = val - (LQ + LS) * a.u;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// one thread per alignment
+__global__ void __launch_bounds__(128) k2_trace_kernel(const K2Args a, int npairs)
+{
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gridDim.x * blockDim.x) {
+        const int qi = a.pair_q[p], si = a.pair_s[p];
+        const int LQ = a.seqs.wlen[qi], LS = a.seqs.wlen[si];
+        const int ql = a.seqs.left[qi], sl = a.seqs.left[si];
+        const int64_t off = a.len_off[p];
+        int* out = a.out_pts + 2 * off;
+        if (LQ == 0 || LS == 0) {       // nogap_skl (aln2.cc:30-40) in back-walk order
+            out[0] = ql + LQ; out[1] = sl + LS; out[2] = ql; out[3] = sl;
+            a.out_cnt[p] = 2;
+            continue;
+        }
+        a.out_cnt[p] = k2_trace(a.dirs + a.dir_off[p], LQ, LS, R, ql, sl, a.moves + off, a.recs + off, out);
+    }
+}
+
+}  // namespace
+
+int k2_rows_per_lane() { return R; }
+int k2_warps_per_block() { return NW; }
+int k2_blocks_per_sm() { return BLOCKS_PER_SM; }
+
+cudaError_t k2_fill_launch(const K2Args& a, int grid_blocks, cudaStream_t st)
+{
+    if (a.dim < 1 || a.dim > MAXDIM) return cudaErrorInvalidValue;
+    const size_t smem = smem_bytes(a.dim);
+    cudaError_t e = cudaFuncSetAttribute(k2_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes(MAXDIM));
+    if (e != cudaSuccess) return e;
+    k2_fill_kernel<<<grid_blocks, NW * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t k2_trace_launch(const K2Args& a, int npairs, cudaStream_t st)
+{
+    int blocks = (npairs + 127) / 128;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k2_trace_kernel<<<blocks, 128, 0, st>>>(a, npairs);
+    return cudaGetLastError();
+}

@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "k1_core.cuh"
+#include "k2_core.cuh"
 #include "pg_internal.h"
 
 static std::string g_create_err;
@@ -56,7 +56,8 @@ extern "C" int pg_create(int device, pg_context** out)
     pg_context* c = new pg_context();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    c->d_items = c->d_mtx = c->d_self = c->d_rowbuf = c->d_out = c->d_pairs = nullptr;
+    c->d_items = c->d_mtx = c->d_self = c->d_rowbuf = c->d_out = c->d_pairs = c->d_dirs = c->d_trace = nullptr;
+    c->dirs_cap = c->trace_cap = 0;
     c->items_cap = c->mtx_cap = c->self_cap = c->rowbuf_cap = c->out_cap = c->pairs_cap = 0;
     c->d_counter = nullptr;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -75,7 +76,7 @@ extern "C" void pg_destroy(pg_context* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_items); cudaFree(c->d_mtx); cudaFree(c->d_self); cudaFree(c->d_rowbuf);
-    cudaFree(c->d_out); cudaFree(c->d_pairs); cudaFree(c->d_counter);
+    cudaFree(c->d_out); cudaFree(c->d_pairs); cudaFree(c->d_counter); cudaFree(c->d_dirs); cudaFree(c->d_trace);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -421,6 +422,163 @@ extern "C" int pg_score_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
     }
     pg_seqs_free(c, d);
     return rc;
+}
+
+// ---- alignment with path (alignC<DPunit> batch) ------------------------------------------------
+extern "C" void pg_free(void* p) { free(p); }
+
+static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_idx, const int32_t* b_idx,
+                              int64_t npairs, const pg_params* prm, const void* mtx, int32_t dim,
+                              void* out_scores, int64_t** out_offs, pg_skl** out_pts)
+{
+    if (!c) return PG_ERR_ARG;
+    if (!s || !prm || !mtx || npairs < 0 || !out_offs || !out_pts || (npairs && (!a_idx || !b_idx || !out_scores)))
+        return fail(c, PG_ERR_ARG, "pg_align_pairs: NULL / bad argument");
+    *out_offs = nullptr;
+    *out_pts = nullptr;
+    if (npairs > 0x7fffffff) return fail(c, PG_ERR_ARG, "pg_align_pairs: too many pairs in one call");
+    if (dim < 1 || dim > 32) return fail(c, PG_ERR_ARG, "dim must be in [1, 32]");
+    if (prm->alprm.ls >= 3)
+        return fail(c, PG_ERR_UNSUPPORTED, "two-piece gap penalty (ls == 3, fwd2c.h:411-442) is not built yet");
+    for (int64_t p = 0; p < npairs; ++p)
+        if (a_idx[p] < 0 || a_idx[p] >= s->nseq || b_idx[p] < 0 || b_idx[p] >= s->nseq)
+            return fail(c, PG_ERR_ARG, "pg_align_pairs: sequence index out of range");
+    int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * (size_t)(npairs + 1));
+    if (!offs) return fail(c, PG_ERR_ARG, "out of host memory");
+    offs[0] = 0;
+    if (npairs == 0) { *out_offs = offs; *out_pts = (pg_skl*)malloc(sizeof(pg_skl)); return PG_OK; }
+    pg_dev_seqs* d = nullptr;
+    int rc = pg_seqs_upload(c, s, &d);
+    if (rc) { free(offs); return rc; }
+    IntScoring sc;
+    if (d->max_code >= dim) rc = fail(c, PG_ERR_ARG, "residue code outside the substitution matrix");
+    if (!rc) rc = make_int_scoring(c, prm, mtx, dim, d->present, &sc);
+    if (rc) { pg_seqs_free(c, d); free(offs); return rc; }
+
+    // rows = a, columns = b (the tie rules of forwardB are not symmetric); sort by a for profile reuse
+    std::vector<int32_t> order(npairs);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return a_idx[x] < a_idx[y]; });
+    const int Rr = k2_rows_per_lane(), NWv = k2_warps_per_block(), rpp = 32 * Rr;
+    const int grid = c->sm_count * k2_blocks_per_sm();
+    const size_t esz = prm->vtype ? sizeof(double) : sizeof(float);
+    const size_t DIR_BUDGET_WORDS = (size_t)3 << 30;      // 24 GB of direction words per launch
+    std::vector<int32_t> h_score(npairs), h_cnt(npairs);
+    std::vector<int64_t> h_lenoff(npairs + 1);
+    std::vector<int32_t> h_pts;
+    cudaError_t e = cudaSuccess;
+    std::vector<std::vector<pg_skl>> lists;    // not used; corner lists are compacted below
+    std::vector<pg_skl> all_pts;
+    std::vector<int64_t> cnt_by_orig(npairs);
+    std::vector<int64_t> start_sorted(npairs);
+
+    for (int64_t c0 = 0; c0 < npairs && !rc;) {
+        // ---- chunk of sorted pairs whose direction words fit the budget
+        std::vector<int32_t> pq, ps;
+        std::vector<int64_t> diroff, lenoff;
+        size_t words = 0;
+        int64_t lens = 0;
+        int64_t c1 = c0;
+        bool multipass = false;
+        int max_ls = 0;
+        while (c1 < npairs) {
+            const int qa = a_idx[order[c1]], sb = b_idx[order[c1]];
+            const size_t w = (size_t)k2_words_per_pair(d->h_wlen[qa], d->h_wlen[sb], Rr);
+            if (c1 > c0 && words + w > DIR_BUDGET_WORDS) break;
+            pq.push_back(qa); ps.push_back(sb);
+            diroff.push_back((int64_t)words); lenoff.push_back(lens);
+            words += w;
+            lens += d->h_wlen[qa] + d->h_wlen[sb] + 8;
+            if (d->h_wlen[qa] > rpp) multipass = true;
+            max_ls = std::max(max_ls, d->h_wlen[sb]);
+            ++c1;
+        }
+        const int64_t np = c1 - c0;
+        // ---- work items: runs of equal query, NW subjects per warp round
+        std::vector<PgItem> items;
+        int64_t ch = (np + (int64_t)8 * grid - 1) / ((int64_t)8 * grid);
+        ch = std::max<int64_t>(NWv, std::min<int64_t>(ch, 8 * NWv));
+        ch = (ch + NWv - 1) / NWv * NWv;
+        for (int64_t p = 0; p < np;) {
+            int64_t e2 = p;
+            while (e2 < np && pq[e2] == pq[p]) ++e2;
+            const int64_t cc = d->h_wlen[pq[p]] > rpp ? NWv : ch;
+            for (int64_t i = p; i < e2; i += cc) {
+                PgItem it; it.q = pq[p]; it.sub_begin = (int32_t)i; it.sub_end = (int32_t)std::min<int64_t>(i + cc, e2); it.pad = 0;
+                items.push_back(it);
+            }
+            p = e2;
+        }
+        std::stable_sort(items.begin(), items.end(), [&](const PgItem& x, const PgItem& y) {
+            return (int64_t)d->h_wlen[x.q] * (x.sub_end - x.sub_begin) > (int64_t)d->h_wlen[y.q] * (y.sub_end - y.sub_begin);
+        });
+        // ---- device buffers
+        K1Args k1a;
+        memset(&k1a, 0, sizeof(k1a));
+        rc = stage_common(c, c->stream, sc, dim, items, multipass, grid, max_ls, &k1a);
+        if (rc) break;
+        // pairs blob: pair_q | pair_s | dir_off | len_off | score | cnt
+        size_t o_q = 0, o_s = up256(o_q + 4 * np), o_do = up256(o_s + 4 * np), o_lo = up256(o_do + 8 * np),
+               o_sc = up256(o_lo + 8 * np), o_cn = up256(o_sc + 4 * np), pbytes = up256(o_cn + 4 * np);
+        if ((rc = ensure_cap(c, &c->d_pairs, &c->pairs_cap, pbytes))) break;
+        if ((rc = ensure_cap(c, &c->d_dirs, &c->dirs_cap, std::max<size_t>(words, 1) * 8))) break;
+        // trace blob: moves (1 B) | recs (12 B) | out (8 B) per unit of len
+        size_t o_mv = 0, o_rc = up256(o_mv + (size_t)lens), o_out = up256(o_rc + 12 * (size_t)lens),
+               tbytes = up256(o_out + 8 * (size_t)lens);
+        if ((rc = ensure_cap(c, &c->d_trace, &c->trace_cap, tbytes))) break;
+        char* pb = (char*)c->d_pairs;
+        e = cudaMemcpyAsync(pb + o_q, pq.data(), 4 * np, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pb + o_s, ps.data(), 4 * np, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pb + o_do, diroff.data(), 8 * np, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pb + o_lo, lenoff.data(), 8 * np, cudaMemcpyHostToDevice, c->stream);
+        K2Args a;
+        memset(&a, 0, sizeof(a));
+        a.seqs = d->v;
+        a.items = k1a.items; a.nitems = k1a.nitems; a.counter = k1a.counter;
+        a.pair_q = (const int32_t*)(pb + o_q); a.pair_s = (const int32_t*)(pb + o_s);
+        a.dir_off = (const int64_t*)(pb + o_do); a.len_off = (const int64_t*)(pb + o_lo);
+        a.dirs = (unsigned long long*)c->d_dirs;
+        a.mtx = k1a.mtx; a.dim = dim; a.u = sc.u; a.v = sc.v; a.sh = prm->alprm.sh;
+        a.score = (int32_t*)(pb + o_sc);
+        a.rowbuf = k1a.rowbuf; a.rowbuf_stride = k1a.rowbuf_stride;
+        char* tb = (char*)c->d_trace;
+        a.moves = (unsigned char*)(tb + o_mv); a.recs = (K2Rec*)(tb + o_rc); a.out_pts = (int32_t*)(tb + o_out);
+        a.out_cnt = (int32_t*)(pb + o_cn);
+        if (e == cudaSuccess) e = k2_fill_launch(a, grid, c->stream);
+        if (e == cudaSuccess) e = k2_trace_launch(a, (int)np, c->stream);
+        h_pts.resize(2 * (size_t)lens);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_score.data() + c0, pb + o_sc, 4 * np, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt.data() + c0, pb + o_cn, 4 * np, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_pts.data(), tb + o_out, 8 * (size_t)lens, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { rc = fail(c, PG_ERR_CUDA, std::string("pg_align_pairs: ") + cudaGetErrorString(e)); break; }
+        // ---- compact this chunk's corner lists (sorted order) into all_pts
+        for (int64_t p = 0; p < np; ++p) {
+            start_sorted[c0 + p] = (int64_t)all_pts.size();
+            const int32_t* src = h_pts.data() + 2 * lenoff[p];
+            for (int k = 0; k < h_cnt[c0 + p]; ++k) { pg_skl q; q.m = src[2 * k]; q.n = src[2 * k + 1]; all_pts.push_back(q); }
+        }
+        c0 = c1;
+    }
+    pg_seqs_free(c, d);
+    if (rc) { free(offs); return rc; }
+    // ---- back to the caller's pair order
+    for (int64_t p = 0; p < npairs; ++p) cnt_by_orig[order[p]] = h_cnt[p];
+    for (int64_t p = 0; p < npairs; ++p) offs[p + 1] = offs[p] + cnt_by_orig[p];
+    pg_skl* pts = (pg_skl*)malloc(sizeof(pg_skl) * (size_t)std::max<int64_t>(offs[npairs], 1));
+    if (!pts) { free(offs); return fail(c, PG_ERR_ARG, "out of host memory"); }
+    for (int64_t p = 0; p < npairs; ++p) {
+        const int64_t o = order[p];
+        memcpy(pts + offs[o], all_pts.data() + start_sorted[p], sizeof(pg_skl) * (size_t)h_cnt[p]);
+        if (prm->vtype) ((double*)out_scores)[o] = (double)h_score[p];
+        else ((float*)out_scores)[o] = (float)h_score[p];
+    }
+    (void)esz;
+    *out_offs = offs;
+    *out_pts = pts;
+    return PG_OK;
 }
 
 // ---- measurement helpers ----------------------------------------------------------------------

@@ -57,6 +57,31 @@ struct K1Args {
     int64_t rowbuf_stride;
 };
 
+struct K2Rec;
+
+// arguments of the alignment-with-path kernels (k2_align.cu); pairs are sorted by query
+struct K2Args {
+    PgDevSeqs seqs;
+    const PgItem* items;
+    int32_t nitems;
+    int32_t* counter;
+    const int32_t* pair_q;      // [npairs] rows sequence (a)
+    const int32_t* pair_s;      // [npairs] columns sequence (b)
+    const int64_t* dir_off;     // [npairs] offset (in 64-bit words) of the pair's direction words
+    const int64_t* len_off;     // [npairs] prefix sum of (LQ + LS + 8): scratch / output offsets
+    unsigned long long* dirs;   // direction bits, wavefront order (k2_core.cuh)
+    const int32_t* mtx;
+    int32_t dim;
+    int32_t u, v, sh;
+    int32_t* score;             // [npairs] integer DP score (sorted order)
+    int2* rowbuf;
+    int64_t rowbuf_stride;
+    unsigned char* moves;       // trace scratch
+    K2Rec* recs;                // trace scratch
+    int32_t* out_pts;           // corner lists, 2 ints per corner, Vmf back-walk order
+    int32_t* out_cnt;           // [npairs]
+};
+
 struct pg_dev_seqs {
     PgDevSeqs v;
     void* blob;                 // single device allocation holding everything
@@ -78,6 +103,8 @@ struct pg_context {
     void* d_rowbuf; size_t rowbuf_cap;
     void* d_out; size_t out_cap;
     void* d_pairs; size_t pairs_cap;
+    void* d_dirs; size_t dirs_cap;
+    void* d_trace; size_t trace_cap;
     int32_t* d_counter;
 };
 
@@ -87,5 +114,11 @@ int k1_rows_per_pass();
 int k1_warps_per_block();
 int k1_blocks_per_sm();
 cudaError_t k1_self_launch(const PgDevSeqs& s, const int32_t* mtx, int dim, int32_t* self, cudaStream_t st);
+// k2_align.cu
+cudaError_t k2_fill_launch(const K2Args& a, int grid_blocks, cudaStream_t st);
+cudaError_t k2_trace_launch(const K2Args& a, int npairs, cudaStream_t st);
+int k2_rows_per_lane();
+int k2_warps_per_block();
+int k2_blocks_per_sm();
 // dpx_peak.cu
 cudaError_t dpx_peak_run(int sm_count, cudaStream_t st, double* gops_s32, double* gops_s16x2);

@@ -1,0 +1,124 @@
+"""Parity of the CUDA alignment path (pg_align_pairs: alignC<DPunit> on the GPU + the host-side
+stdskl) with the reference's align2: scores and corner lists, bit-exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names
+import prrn_aln_b200 as P
+from prrn_aln_b200 import seqcode
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import gen_synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = P.Context(0)
+    yield c
+    c.close()
+
+
+def _params(g):
+    h = g["params"]
+    a = P.ALPRM(u=float(h["u"]), v=float(h["v"]), tgapf=float(h["tgapf"]), scale=float(h["scale"]),
+                u1=float(h["u1"]), k1=int(h["k1"]), ls=int(h["ls"]), sh=int(h["sh"]))
+    return P.Params(a, lcl=int(h["lcl"]), vtype=1 if h["vtype"] == "f64" else 0)
+
+
+def _supported(g):
+    M = np.array(g["matrix"])[3:23, 3:23]
+    return int(g["params"]["ls"]) < 3 and np.all(M == np.rint(M))
+
+
+AFFINE_INT = [n for n in golden_names("align_") if _supported(golden(n))]
+OTHERS = [n for n in golden_names("align_") if not _supported(golden(n))]
+
+
+@pytest.mark.parametrize("name", AFFINE_INT)
+def test_golden_alignments_bit_exact(ctx, name):
+    g = golden(name)
+    enc = [seqcode.encode_protein(s) for s in g["seqs"]]
+    ia = [p["i"] for p in g["pairs"]]
+    ib = [p["j"] for p in g["pairs"]]
+    scores, raw = ctx.align_pairs(P.SeqSet(enc), ia, ib, _params(g), np.array(g["matrix"]))
+    for k, p in enumerate(g["pairs"]):
+        assert float(scores[k]) == p["score"], (p["i"], p["j"])
+        assert P.stdskl(raw[k]) == [tuple(x) for x in p["skl"]], (p["i"], p["j"])
+
+
+@pytest.mark.parametrize("name", OTHERS)
+def test_unsupported_alignment_modes_fail_loudly(ctx, name):
+    g = golden(name)
+    enc = [seqcode.encode_protein(s) for s in g["seqs"]]
+    with pytest.raises(P.PgError) as e:
+        ctx.align_pairs(P.SeqSet(enc), [0], [1], _params(g), np.array(g["matrix"]))
+    assert e.value.code == 4
+
+
+def test_raw_corner_lists_match_oracle_fuzz(ctx, oracle):
+    """Tiny adversarial pairs: the raw Vmf back-walk lists (before stdskl) must be identical."""
+    M = np.array(golden("score_p24_blosum62")["matrix"])
+    rng = np.random.default_rng(99)
+    for sh, u, v in ((0, 1, 0), (1, 2, 9), (3, 3, 5), (-30, 2, 1), (-100, 1, 12)):
+        enc = []
+        for _ in range(300):
+            hi = 3 + int(rng.choice([2, 4, 20]))
+            enc.append(rng.integers(3, hi, size=int(rng.integers(1, 40))).astype(np.uint8))
+        ia = rng.integers(0, len(enc), size=1500).astype(np.int32)
+        ib = rng.integers(0, len(enc), size=1500).astype(np.int32)
+        prm = P.Params(P.ALPRM(u=u, v=v, sh=sh))
+        scores, raw = ctx.align_pairs(P.SeqSet(enc), ia, ib, prm, M)
+        op = oracle.params(u=u, v=v, sh=sh)
+        for k in range(len(ia)):
+            osc, olist = oracle.align_ngp(oracle.seq(enc[ia[k]]), oracle.seq(enc[ib[k]]), M, op, std=False)
+            assert float(scores[k]) == osc, (sh, u, v, k)
+            assert [tuple(x) for x in raw[k].tolist()] == olist, (sh, u, v, k)
+
+
+def test_all_pairs_c2_subset_and_path_properties(ctx, oracle):
+    """aln -ie style all-pairs alignment of 60 C2 sequences: sample vs oracle; every path is a valid
+    monotone lattice path from (0,0) to (La,Lb) whose re-scored value equals the reported score."""
+    seqs = gen_synth.config_set("c2", 60)
+    enc = [seqcode.encode_protein(s) for s in seqs]
+    M = np.array(golden("score_p24_blosum62")["matrix"])
+    n = len(enc)
+    ia = [i for j in range(1, n) for i in range(j)]
+    ib = [j for j in range(1, n) for i in range(j)]
+    prm = P.Params()
+    scores, raw = ctx.align_pairs(P.SeqSet(enc), ia, ib, prm, M)
+    op = oracle.params()
+    rng = np.random.default_rng(5)
+    for k in rng.choice(len(ia), size=120, replace=False):
+        osc, olist = oracle.align_ngp(oracle.seq(enc[ia[k]]), oracle.seq(enc[ib[k]]), M, op, std=True)
+        assert float(scores[k]) == osc
+        assert P.stdskl(raw[k]) == olist
+    u, v = 2, 9
+    for k in range(0, len(ia), 7):
+        a, b = enc[ia[k]], enc[ib[k]]
+        pts = P.stdskl(raw[k])
+        assert pts[0] == (0, 0) and pts[-1] == (len(a), len(b))
+        s = 0
+        for (m0, n0), (m1, n1) in zip(pts[:-1], pts[1:]):
+            dm, dn = m1 - m0, n1 - n0
+            assert dm >= 0 and dn >= 0 and (dm == dn or dm == 0 or dn == 0)
+            if dm == dn:
+                s += sum(M[a[m0 + t], b[n0 + t]] for t in range(dm))
+            else:
+                s -= v + u * (dm + dn)
+        assert s == float(scores[k]), k
+
+
+def test_long_pair_multi_pass(ctx, oracle):
+    seqs = gen_synth.synth_set(2, 2600, 0.1, 0.3, 41)
+    enc = [seqcode.encode_protein(s) for s in seqs]
+    M = np.array(golden("score_p24_blosum62")["matrix"])
+    scores, raw = ctx.align_pairs(P.SeqSet(enc), [0, 1], [1, 0], P.Params(), M)
+    for k, (i, j) in enumerate(((0, 1), (1, 0))):
+        osc, olist = oracle.align_ngp(oracle.seq(enc[i]), oracle.seq(enc[j]), M, oracle.params(), std=False)
+        assert float(scores[k]) == osc
+        assert [tuple(x) for x in raw[k].tolist()] == olist

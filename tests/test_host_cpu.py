@@ -103,3 +103,55 @@ def test_kernel_recurrence_fuzz_small_adversarial(emul, oracle):
         got = emul.k1_emul_score(a.ctypes.data_as(C.c_void_p), la, b.ctypes.data_as(C.c_void_p), lb,
                                  Mi.ctypes.data_as(C.c_void_p), 25, u, v, sh, -v, -u, -v, -u, R)
         assert got == want, (la, lb, sh, u, v, R)
+
+
+@pytest.fixture(scope="module")
+def emul2():
+    src = os.path.join(ROOT, "tests", "host_emul", "k2_emul.cc")
+    out = os.path.join(ROOT, "tests", "host_emul", "libk2emul.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", out, src])
+    L = C.CDLL(out)
+    L.k2_emul_align.restype = C.c_int
+    return L
+
+
+def _emul_align(L, q, s, Mi, u, v, sh, R):
+    q = np.ascontiguousarray(q, np.uint8)
+    s = np.ascontiguousarray(s, np.uint8)
+    out = np.zeros(2 * (len(q) + len(s) + 8), np.int32)
+    sc = C.c_int(0)
+    n = L.k2_emul_align(q.ctypes.data_as(C.c_void_p), len(q), s.ctypes.data_as(C.c_void_p), len(s),
+                        Mi.ctypes.data_as(C.c_void_p), Mi.shape[0], u, v, sh, R, out.ctypes.data_as(C.c_void_p),
+                        C.byref(sc))
+    return sc.value, [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(n)]
+
+
+@pytest.mark.parametrize("name", ["align_p16_blosum62", "align_p16_sh3", "align_p16_u3v11", "align_ragged",
+                                  "align_long1300", "align_c1_ce13a"])
+def test_alignment_kernel_emulation_matches_reference(emul2, name):
+    """k2_core.cuh (direction bits, traceback, record replay) + host stdskl against align2 goldens."""
+    g = golden(name)
+    enc = [seqcode.encode_protein(x) for x in g["seqs"]]
+    Mi = np.nan_to_num(np.array(g["matrix"])).astype(np.int32)
+    u, v, sh = int(float(g["params"]["u"])), int(float(g["params"]["v"])), int(g["params"]["sh"])
+    for p in g["pairs"]:
+        for R in (4, 16):
+            sc, raw = _emul_align(emul2, enc[p["i"]], enc[p["j"]], Mi, u, v, sh, R)
+            assert sc == p["score"]
+            assert P.stdskl(raw) == [tuple(x) for x in p["skl"]]
+
+
+def test_alignment_kernel_emulation_fuzz(emul2, oracle):
+    M = np.array(golden("score_p24_blosum62")["matrix"])
+    Mi = np.nan_to_num(M).astype(np.int32)
+    rng = np.random.default_rng(31)
+    for _ in range(3000):
+        la, lb = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        hi = 3 + int(rng.choice([2, 4, 20]))
+        a = rng.integers(3, hi, size=la).astype(np.uint8)
+        b = rng.integers(3, hi, size=lb).astype(np.uint8)
+        sh = int(rng.choice([-100, -60, -30, -10, 0, 1, 2, 3, 5, 100]))
+        u, v = int(rng.choice([1, 2, 3])), int(rng.choice([0, 1, 5, 9, 12]))
+        osc, olist = oracle.align_ngp(oracle.seq(a), oracle.seq(b), M, oracle.params(u=u, v=v, sh=sh), std=False)
+        sc, raw = _emul_align(emul2, a, b, Mi, u, v, sh, int(rng.choice([4, 8, 16])))
+        assert sc == osc and raw == olist, (la, lb, sh, u, v)
