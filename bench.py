@@ -179,8 +179,8 @@ def main():
     M = blosum62_matrix()
     prm = P.Params(P.ALPRM(sh=SH), vtype=1)     # prrn build: FTYPE = double
     npair = ss.n * (ss.n - 1) // 2
-    chunk = (npair + world - 1) // world
-    k0, k1 = min(rank * chunk, npair), min((rank + 1) * chunk, npair)
+    from prrn_aln_b200 import sharding
+    k0, k1, chunk = sharding.shard_range(npair, world, rank)
     cells_total = P.calcdist_cells(ss, prm)
     cells_mine = P.calcdist_cells(ss, prm, k0, k1)
 

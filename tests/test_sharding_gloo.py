@@ -1,0 +1,68 @@
+"""world_size-2 (and 3) gloo test of the N>1 host logic: shard ranges of the condensed index and
+the single all-gather that assembles the distance vector.  The compute leg is a stand-in here (the
+product has no CPU path); the GPU tests check that real shards concatenate to the full vector."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from prrn_aln_b200 import sharding
+import prrn_aln_b200 as P
+
+
+def test_shard_ranges_cover_everything():
+    for npair in (0, 1, 5, 499500, 49995000):
+        for world in (1, 2, 3, 4, 8):
+            cov = []
+            for r in range(world):
+                k0, k1, chunk = sharding.shard_range(npair, world, r)
+                assert 0 <= k0 <= k1 <= npair and k1 - k0 <= chunk
+                cov.append((k0, k1))
+            assert cov[0][0] == 0 and cov[-1][1] == npair
+            assert all(cov[i][1] == cov[i + 1][0] for i in range(world - 1))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nseq, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(1)
+    enc = [rng.integers(3, 23, size=int(rng.integers(5, 30))).astype(np.uint8) for _ in range(nseq)]
+    seqs = P.SeqSet(enc)
+
+    def compute(k0, k1):            # stand-in "distance": a function of k only
+        return np.arange(k0, k1, dtype=np.float64) * 0.5 + 1.0
+
+    full = sharding.calcdist_sharded(None, seqs, None, None, rank, world, dist, compute)
+    npair = nseq * (nseq - 1) // 2
+    ok = bool(torch.equal(full, torch.arange(npair, dtype=torch.float64) * 0.5 + 1.0))
+    q.put((rank, ok, int(full.numel())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nseq", [(2, 11), (3, 7), (2, 2)])
+def test_all_gather_assembles_condensed_vector(world, nseq):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nseq, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert all(n == nseq * (nseq - 1) // 2 for _, _, n in res)
