@@ -11,10 +11,12 @@
 #include <string>
 #include <vector>
 
+#include "k1p_core.cuh"
 #include "k2_core.cuh"
 #include "pg_internal.h"
 
 static std::string g_create_err;
+static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 #define PG_CUDA(ctx, call)                                                                      \
     do {                                                                                        \
@@ -181,6 +183,12 @@ extern "C" int pg_seqs_upload(pg_context* c, const pg_seqs* s, pg_dev_seqs** out
     d->v.nseq = n;
     d->h_wlen = wlen;
     d->max_wlen = maxw;
+    d->min_wlen = n ? *std::min_element(wlen.begin(), wlen.end()) : 0;
+    d->plan_k0 = d->plan_k1 = -1;
+    d->d_plan = nullptr;
+    d->plan_nitems = 0;
+    d->plan_nsubs = 0;
+    d->plan_multipass = false;
     // residues must index the matrix: remember the largest code
     uint8_t mx = 0;
     memset(d->present, 0, sizeof(d->present));
@@ -198,6 +206,7 @@ extern "C" void pg_seqs_free(pg_context* c, pg_dev_seqs* d)
     if (!d) return;
     if (c) cudaSetDevice(c->device);
     cudaFree(d->blob);
+    cudaFree(d->d_plan);
     delete d;
 }
 
@@ -244,6 +253,78 @@ static void build_calcdist_items(const pg_dev_seqs* d, int64_t k0, int64_t k1, i
         int64_t ca = (int64_t)d->h_wlen[a.q] * (a.sub_end - a.sub_begin);
         int64_t cb = (int64_t)d->h_wlen[b.q] * (b.sub_end - b.sub_begin);
         return ca > cb;
+    });
+}
+
+// ---- packed plan: query pairs of similar length x subjects, every pair {x, y} exactly once ---------
+// Rows J = [jlo, jhi] of the condensed triangle are the queries of this range.  Subjects are
+//   (a) the sequences below jlo: every (j in J, i < jlo) pair -- both halves valid;
+//   (b) the other members of J, assigned by a round-robin tournament over J sorted by length:
+//       {x, y} goes to x iff (pos(y) - pos(x)) mod |J| in [1, (|J|-1)/2] (antipodal ties to the
+//       smaller position), so two queries adjacent in the sorted order share all but one subject.
+// Partial first / last rows of the range are trimmed by the per-pair range test.
+static void build_packed_plan(const pg_dev_seqs* d, int64_t k0, int64_t k1, int grid_blocks,
+                              std::vector<PgItem2>* items, std::vector<uint32_t>* subs, bool* multipass)
+{
+    items->clear();
+    subs->clear();
+    *multipass = false;
+    if (k1 <= k0) return;
+    const int NWv = k1p_warps_per_block(), rpp = k1p_rows_per_pass();
+    const int jlo = row_of_k(k0), jhi = row_of_k(k1 - 1);
+    const int nJ = jhi - jlo + 1;
+    std::vector<int> J(nJ);
+    std::iota(J.begin(), J.end(), jlo);
+    std::stable_sort(J.begin(), J.end(), [&](int x, int y) { return d->h_wlen[x] < d->h_wlen[y]; });
+    auto in_range = [&](int x, int y) {
+        const int64_t hi = x > y ? x : y, lo = x > y ? y : x;
+        const int64_t k = hi * (hi - 1) / 2 + lo;
+        return k >= k0 && k < k1;
+    };
+    const int h = (nJ - 1) / 2;
+    auto assigned = [&](int px, int py) {       // does the pair of positions (px, py) belong to px ?
+        int dd = py - px;
+        if (dd < 0) dd += nJ;
+        if (dd >= 1 && dd <= h) return true;
+        return (nJ % 2 == 0) && dd == nJ / 2 && px < nJ / 2;
+    };
+    int64_t total = k1 - k0;
+    int64_t ch = (total / 2 + (int64_t)16 * grid_blocks - 1) / ((int64_t)16 * grid_blocks);
+    ch = std::max<int64_t>(NWv, std::min<int64_t>(ch, 32 * NWv));
+    ch = (ch + NWv - 1) / NWv * NWv;
+    std::vector<uint32_t> list;
+    for (int p = 0; p < nJ; p += 2) {
+        const int qa = J[p], qb = p + 1 < nJ ? J[p + 1] : J[p];
+        const bool has_b = p + 1 < nJ;
+        list.clear();
+        for (int s = 0; s < jlo; ++s) {                      // (a) rectangle part
+            const uint32_t va = in_range(qa, s), vb = has_b && in_range(qb, s);
+            if (va | vb) list.push_back((uint32_t)s | (va << 30) | (vb << 31));
+        }
+        const int span = h + 2 + (nJ % 2 == 0 ? 1 : 0);     // (b) tournament part
+        for (int t = 1; t <= nJ - 1 && t <= span + nJ / 2; ++t) {
+            const int py = (p + t) % nJ;
+            uint32_t va = py != p && assigned(p, py) && in_range(qa, J[py]);
+            uint32_t vb = has_b && py != p + 1 && assigned(p + 1, py) && in_range(qb, J[py]);
+            if (va | vb) list.push_back((uint32_t)J[py] | (va << 30) | (vb << 31));
+        }
+        const bool mp = std::max(d->h_wlen[qa], d->h_wlen[qb]) > rpp;
+        if (mp) *multipass = true;
+        const int64_t cc = mp ? NWv : ch;
+        for (size_t i = 0; i < list.size(); i += cc) {
+            PgItem2 it;
+            it.q0 = qa; it.q1 = qb;
+            it.sub_begin = (int32_t)subs->size();
+            const size_t e = std::min(list.size(), i + (size_t)cc);
+            subs->insert(subs->end(), list.begin() + i, list.begin() + e);
+            it.sub_end = (int32_t)subs->size();
+            items->push_back(it);
+        }
+    }
+    std::stable_sort(items->begin(), items->end(), [&](const PgItem2& x, const PgItem2& y) {
+        int64_t cx = (int64_t)std::max(d->h_wlen[x.q0], d->h_wlen[x.q1]) * (x.sub_end - x.sub_begin);
+        int64_t cy = (int64_t)std::max(d->h_wlen[y.q0], d->h_wlen[y.q1]) * (y.sub_end - y.sub_begin);
+        return cx > cy;
     });
 }
 
@@ -295,6 +376,66 @@ extern "C" int pg_calcdist_dev(pg_context* c, pg_dev_seqs* d, const pg_params* p
     // everything (staging copies, self-score kernel, fill kernel) is ordered on one stream
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     const int grid = c->sm_count * k1_blocks_per_sm();
+    // ---- packed int16x2 path when every value provably fits 16 bits (k1p_fits)
+    {
+        int smax = -1 << 30, smin = 1 << 30;
+        for (int i = 0; i < dim; ++i)
+            for (int j = 0; j < dim; ++j)
+                if (d->present[i] && d->present[j]) {
+                    smax = std::max(smax, sc.mtx[i * dim + j] + 2 * sc.u);
+                    smin = std::min(smin, sc.mtx[i * dim + j] + 2 * sc.u);
+                }
+        const char* force = getenv("PG_FORCE_INT32");
+        const bool packed = !(force && force[0] == '1') && d->min_wlen >= 1 && n >= 2 &&
+                            k1p_fits(smax, smin, sc.v, d->max_wlen);
+        if (packed) {
+            if (d->plan_k0 != k_begin || d->plan_k1 != k_end || !d->d_plan) {
+                std::vector<PgItem2> items2;
+                std::vector<uint32_t> subs;
+                bool mp = false;
+                build_packed_plan(d, k_begin, k_end, grid, &items2, &subs, &mp);
+                if (d->d_plan) { PG_CUDA(c, cudaStreamSynchronize(st)); PG_CUDA(c, cudaFree(d->d_plan)); d->d_plan = nullptr; }
+                const size_t ib = up256(sizeof(PgItem2) * std::max<size_t>(items2.size(), 1));
+                PG_CUDA(c, cudaMalloc(&d->d_plan, ib + sizeof(uint32_t) * std::max<size_t>(subs.size(), 1)));
+                if (!items2.empty())
+                    PG_CUDA(c, cudaMemcpyAsync(d->d_plan, items2.data(), sizeof(PgItem2) * items2.size(), cudaMemcpyHostToDevice, st));
+                if (!subs.empty())
+                    PG_CUDA(c, cudaMemcpyAsync((char*)d->d_plan + ib, subs.data(), sizeof(uint32_t) * subs.size(), cudaMemcpyHostToDevice, st));
+                d->plan_k0 = k_begin; d->plan_k1 = k_end;
+                d->plan_nitems = (int32_t)items2.size();
+                d->plan_nsubs = (int64_t)subs.size();
+                d->plan_multipass = mp;
+            }
+            K1PArgs a;
+            memset(&a, 0, sizeof(a));
+            a.seqs = d->v;
+            if ((rc = ensure_cap(c, &c->d_mtx, &c->mtx_cap, sizeof(int32_t) * sc.mtx.size()))) return rc;
+            PG_CUDA(c, cudaMemcpyAsync(c->d_mtx, sc.mtx.data(), sizeof(int32_t) * sc.mtx.size(), cudaMemcpyHostToDevice, st));
+            if (d->plan_multipass) {
+                size_t stride = (size_t)d->max_wlen + 8;
+                if ((rc = ensure_cap(c, &c->d_rowbuf, &c->rowbuf_cap, sizeof(uint2) * stride * (size_t)grid * k1p_warps_per_block()))) return rc;
+                a.rowbuf = (uint2*)c->d_rowbuf;
+                a.rowbuf_stride = (int64_t)stride;
+            }
+            PG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int32_t), st));
+            if ((rc = ensure_cap(c, &c->d_self, &c->self_cap, sizeof(int32_t) * std::max<size_t>(n, 1)))) return rc;
+            PG_CUDA(c, k1_self_launch(d->v, (const int32_t*)c->d_mtx, dim, (int32_t*)c->d_self, st));
+            const size_t ib = up256(sizeof(PgItem2) * std::max<size_t>((size_t)d->plan_nitems, 1));
+            a.items = (const PgItem2*)d->d_plan;
+            a.nitems = d->plan_nitems;
+            a.counter = c->d_counter;
+            a.subs = (const uint32_t*)((char*)d->d_plan + ib);
+            a.k_begin = k_begin; a.k_end = k_end;
+            a.mtx = (const int32_t*)c->d_mtx; a.dim = dim; a.u = sc.u; a.v = sc.v; a.sh = prm->alprm.sh;
+            a.u_f32 = prm->alprm.u;
+            a.self = (const int32_t*)c->d_self;
+            a.epilogue = prm->vtype ? PG_EPI_DIST_F64 : PG_EPI_DIST_F32;
+            a.out = d_out_dist;
+            PG_CUDA(c, k1p_launch(a, c->sm_count * k1p_blocks_per_sm(), st));
+            if (n_launches) *n_launches = 2;
+            return PG_OK;
+        }
+    }
     std::vector<PgItem> items;
     bool multipass = false;
     build_calcdist_items(d, k_begin, k_end, grid, &items, &multipass);
@@ -427,7 +568,6 @@ extern "C" int pg_score_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
 // ---- alignment with path (alignC<DPunit> batch) ------------------------------------------------
 extern "C" void pg_free(void* p) { free(p); }
 
-static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_idx, const int32_t* b_idx,
                               int64_t npairs, const pg_params* prm, const void* mtx, int32_t dim,

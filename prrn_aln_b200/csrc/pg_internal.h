@@ -57,6 +57,30 @@ struct K1Args {
     int64_t rowbuf_stride;
 };
 
+// packed (int16 x 2) score kernel: a pair of queries against a run of subjects
+struct PgItem2 {
+    int32_t q0, q1;
+    int32_t sub_begin, sub_end;     // range in subs[]
+};
+
+struct K1PArgs {
+    PgDevSeqs seqs;
+    const PgItem2* items;
+    int32_t nitems;
+    int32_t* counter;
+    const uint32_t* subs;       // subject index | half-0 valid << 30 | half-1 valid << 31
+    int64_t k_begin, k_end;
+    const int32_t* mtx;
+    int32_t dim;
+    int32_t u, v, sh;
+    float u_f32;
+    const int32_t* self;
+    int32_t epilogue;
+    void* out;
+    uint2* rowbuf;
+    int64_t rowbuf_stride;
+};
+
 struct K2Rec;
 
 // arguments of the alignment-with-path kernels (k2_align.cu); pairs are sorted by query
@@ -89,6 +113,13 @@ struct pg_dev_seqs {
     int32_t max_wlen;
     int32_t max_code;           // largest residue code inside the windows
     uint8_t present[256];       // which residue codes occur inside the windows
+    int32_t min_wlen;
+    // cached packed plan of the last calcdist range (schedule only, no results)
+    int64_t plan_k0, plan_k1;
+    void* d_plan;               // PgItem2[nitems] | subs[nsubs]
+    int32_t plan_nitems;
+    int64_t plan_nsubs;
+    bool plan_multipass;
 };
 
 struct pg_context {
@@ -114,6 +145,11 @@ int k1_rows_per_pass();
 int k1_warps_per_block();
 int k1_blocks_per_sm();
 cudaError_t k1_self_launch(const PgDevSeqs& s, const int32_t* mtx, int dim, int32_t* self, cudaStream_t st);
+// k1p_score.cu
+cudaError_t k1p_launch(const K1PArgs& a, int grid_blocks, cudaStream_t st);
+int k1p_rows_per_pass();
+int k1p_warps_per_block();
+int k1p_blocks_per_sm();
 // k2_align.cu
 cudaError_t k2_fill_launch(const K2Args& a, int grid_blocks, cudaStream_t st);
 cudaError_t k2_trace_launch(const K2Args& a, int npairs, cudaStream_t st);

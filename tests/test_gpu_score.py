@@ -91,6 +91,25 @@ def test_against_oracle_c2_subset(ctx, oracle):
         assert np.array_equal(got.astype(np.float64), want), (sh, vt)
 
 
+def test_int32_and_packed_kernels_agree(ctx, oracle, monkeypatch):
+    """calcdist runs the packed int16x2 kernel when values provably fit 16 bits; PG_FORCE_INT32=1
+    routes the same call through the int32 kernel.  Both must equal the oracle."""
+    seqs = gen_synth.config_set("c2", 70) + gen_synth.synth_set(5, 900, 0.1, 0.5, 9)
+    enc = [seqcode.encode_protein(s) for s in seqs]
+    M = np.array(golden("score_p24_blosum62")["matrix"])
+    ss = P.SeqSet(enc)
+    for sh in (-60, 7):
+        prm = P.Params(P.ALPRM(sh=sh), vtype=1)
+        want, _ = oracle.calcdist([oracle.seq(e) for e in enc], M, oracle.params(sh=sh, vtype=1))
+        monkeypatch.delenv("PG_FORCE_INT32", raising=False)
+        packed = ctx.calcdist(ss, prm, M)
+        monkeypatch.setenv("PG_FORCE_INT32", "1")
+        plain = ctx.calcdist(ss, prm, M)
+        monkeypatch.delenv("PG_FORCE_INT32", raising=False)
+        assert np.array_equal(packed, want), sh
+        assert np.array_equal(plain, want), sh
+
+
 def test_sharded_ranges_concatenate(ctx):
     seqs = gen_synth.config_set("c5a", 60)
     enc = [seqcode.encode_protein(s) for s in seqs]

@@ -155,3 +155,48 @@ def test_alignment_kernel_emulation_fuzz(emul2, oracle):
         osc, olist = oracle.align_ngp(oracle.seq(a), oracle.seq(b), M, oracle.params(u=u, v=v, sh=sh), std=False)
         sc, raw = _emul_align(emul2, a, b, Mi, u, v, sh, int(rng.choice([4, 8, 16])))
         assert sc == osc and raw == olist, (la, lb, sh, u, v)
+
+
+@pytest.fixture(scope="module")
+def emulp():
+    src = os.path.join(ROOT, "tests", "host_emul", "k1p_emul.cc")
+    out = os.path.join(ROOT, "tests", "host_emul", "libk1pemul.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", out, src])
+    return C.CDLL(out)
+
+
+def test_packed_int16x2_recurrence_emulation(emulp, oracle):
+    """k1p_core.cuh: two alignments per register with int16 wrap-around arithmetic emulated on the
+    host; small adversarial cases + realistic lengths incl. multi-pass and unequal query lengths."""
+    M = np.array(golden("score_p24_blosum62")["matrix"])
+    Mi = np.nan_to_num(M).astype(np.int32)
+
+    def run(q0, q1, s, u, v, sh, R):
+        o0, o1 = C.c_int(0), C.c_int(0)
+        emulp.k1p_emul_score2(q0.ctypes.data_as(C.c_void_p), len(q0), q1.ctypes.data_as(C.c_void_p), len(q1),
+                              s.ctypes.data_as(C.c_void_p), len(s), Mi.ctypes.data_as(C.c_void_p), 25, u, v, sh, R,
+                              C.byref(o0), C.byref(o1))
+        return o0.value, o1.value
+
+    rng = np.random.default_rng(8)
+    for _ in range(2500):
+        hi = 3 + int(rng.choice([2, 4, 20]))
+        q0, q1, s = (rng.integers(3, hi, size=int(rng.integers(1, 40))).astype(np.uint8) for _ in range(3))
+        sh = int(rng.choice([-100, -60, -30, -10, 0, 1, 2, 3, 5, 100]))
+        u, v = int(rng.choice([1, 2, 3])), int(rng.choice([0, 1, 5, 9, 12]))
+        p = oracle.params(u=u, v=v, sh=sh)
+        want = (oracle.aln_score_d(oracle.seq(q0), oracle.seq(s), M, p), oracle.aln_score_d(oracle.seq(q1), oracle.seq(s), M, p))
+        assert run(q0, q1, s, u, v, sh, int(rng.choice([4, 8, 16]))) == want
+    g = golden("score_long1300")
+    enc = [seqcode.encode_protein(x) for x in g["seqs"]]
+    enc += [enc[0][:300], enc[1][:513]]
+    p = oracle.params()
+    for a in range(0, len(enc) - 1, 2):
+        for b in range(len(enc)):
+            want = (oracle.aln_score_d(oracle.seq(enc[a]), oracle.seq(enc[b]), M, p),
+                    oracle.aln_score_d(oracle.seq(enc[a + 1]), oracle.seq(enc[b]), M, p))
+            assert run(enc[a], enc[a + 1], enc[b], 2, 9, -60, 16) == want
+    # the 16-bit range proof obligation
+    assert emulp.k1p_emul_fits(15, 0, 9, 1300) == 1
+    assert emulp.k1p_emul_fits(15, 0, 9, 2200) == 0
+    assert emulp.k1p_emul_fits(13, -2, 9, 1300) == 1
