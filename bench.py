@@ -237,8 +237,11 @@ def main():
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         ctx.calcdist(ss_pin, prm, M, k0, k1, out=out_np)
         checksum = float(out_np[:8].sum())
+        if os.environ.get("BENCH_DEBUG"):
+            print("e2e step %.2f ms" % ((time.perf_counter() - t1) * 1e3), file=sys.stderr)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")

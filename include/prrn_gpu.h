@@ -106,6 +106,10 @@ int pg_calcdist_dev(pg_context *ctx, pg_dev_seqs *seqs, const pg_params *prm, co
 /* Number of DP cells the reference's loops visit for the pairs k in [k_begin, k_end)
  * (rows m in window, columns in the stripe() band; src/aln2.cc:156-174). */
 int64_t pg_calcdist_cells(const pg_seqs *seqs, const pg_params *prm, int64_t k_begin, int64_t k_end);
+/* Host-only: the schedule of the packed score kernel for a condensed range -- number of work items,
+ * number of (query pair, subject) slots, and per-k coverage counts (each must be 1).  Test aid. */
+int pg_debug_packed_plan(const pg_seqs *seqs, int64_t k_begin, int64_t k_end, int32_t grid_blocks,
+                         int64_t *nitems, int64_t *nslots, uint8_t *cover);
 /* Register-only DPX micro-benchmark: measured issue rate of __viaddmax_s32 / __vimax3_s32 chains,
  * in 1e9 thread-instructions per second for the whole device; the roofline denominator. */
 int pg_dpx_peak(pg_context *ctx, double *gops_s32, double *gops_s16x2);

@@ -94,6 +94,8 @@ def load_library():
                                   C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     L.pg_calcdist_cells.restype = C.c_int64
     L.pg_calcdist_cells.argtypes = [C.POINTER(_PgSeqs), C.POINTER(Params), C.c_int64, C.c_int64]
+    L.pg_debug_packed_plan.argtypes = [C.POINTER(_PgSeqs), C.c_int64, C.c_int64, C.c_int32,
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]
     L.pg_dpx_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _LIB = L
     return L
@@ -242,6 +244,21 @@ def calcdist_cells(seqs, prm, k_begin=0, k_end=None):
     k_end = npair if k_end is None else k_end
     cs = seqs.c_struct()
     return load_library().pg_calcdist_cells(C.byref(cs), C.byref(prm), k_begin, k_end)
+
+
+def packed_plan_coverage(seqs, k_begin=0, k_end=None, grid_blocks=444):
+    """Host-only: (work items, (query pair, subject) slots, coverage count per condensed index) of
+    the packed score kernel's schedule; every count must be 1."""
+    npair = seqs.n * (seqs.n - 1) // 2
+    k_end = npair if k_end is None else k_end
+    cover = np.zeros(max(k_end - k_begin, 1), dtype=np.uint8)
+    ni, ns = C.c_int64(0), C.c_int64(0)
+    cs = seqs.c_struct()
+    rc = load_library().pg_debug_packed_plan(C.byref(cs), k_begin, k_end, grid_blocks, C.byref(ni), C.byref(ns),
+                                             cover.ctypes.data)
+    if rc:
+        raise PgError(rc, "pg_debug_packed_plan")
+    return ni.value, ns.value, cover[:max(k_end - k_begin, 0)]
 
 
 _DEFAULT_CTX = {}

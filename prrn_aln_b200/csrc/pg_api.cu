@@ -58,8 +58,8 @@ extern "C" int pg_create(int device, pg_context** out)
     pg_context* c = new pg_context();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    c->d_items = c->d_mtx = c->d_self = c->d_rowbuf = c->d_out = c->d_pairs = c->d_dirs = c->d_trace = nullptr;
-    c->dirs_cap = c->trace_cap = 0;
+    c->d_items = c->d_mtx = c->d_self = c->d_rowbuf = c->d_out = c->d_pairs = c->d_dirs = c->d_trace = c->d_seqblob = c->d_planbuf = nullptr;
+    c->dirs_cap = c->trace_cap = c->seqblob_cap = c->planbuf_cap = 0;
     c->items_cap = c->mtx_cap = c->self_cap = c->rowbuf_cap = c->out_cap = c->pairs_cap = 0;
     c->d_counter = nullptr;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -78,7 +78,7 @@ extern "C" void pg_destroy(pg_context* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_items); cudaFree(c->d_mtx); cudaFree(c->d_self); cudaFree(c->d_rowbuf);
-    cudaFree(c->d_out); cudaFree(c->d_pairs); cudaFree(c->d_counter); cudaFree(c->d_dirs); cudaFree(c->d_trace);
+    cudaFree(c->d_out); cudaFree(c->d_pairs); cudaFree(c->d_counter); cudaFree(c->d_dirs); cudaFree(c->d_trace); cudaFree(c->d_seqblob); cudaFree(c->d_planbuf);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -131,7 +131,16 @@ static int make_int_scoring(pg_context* c, const pg_params* prm, const void* mtx
 }
 
 // ---- sequences --------------------------------------------------------------------------------
+static int seqs_upload_impl(pg_context* c, const pg_seqs* s, pg_dev_seqs** out, bool in_ctx);
+
 extern "C" int pg_seqs_upload(pg_context* c, const pg_seqs* s, pg_dev_seqs** out)
+{
+    return seqs_upload_impl(c, s, out, false);
+}
+
+// in_ctx: place the blob in the context's reusable workspace (host-buffer entry points call this
+// once per call; a cudaMalloc/cudaFree pair per call costs milliseconds and occasional long stalls)
+static int seqs_upload_impl(pg_context* c, const pg_seqs* s, pg_dev_seqs** out, bool in_ctx)
 {
     if (!c) return PG_ERR_ARG;
     if (!s || !out || s->nseq < 0 || (s->nseq > 0 && (!s->res || !s->offs || !s->lens)))
@@ -162,8 +171,16 @@ extern "C" int pg_seqs_upload(pg_context* c, const pg_seqs* s, pg_dev_seqs** out
            bytes = up16(o_flags + n + 16);
     pg_dev_seqs* d = new pg_dev_seqs();
     d->blob = nullptr;
-    cudaError_t e = cudaMalloc(&d->blob, bytes);
-    if (e != cudaSuccess) { delete d; return fail(c, PG_ERR_CUDA, std::string("cudaMalloc(seqs): ") + cudaGetErrorString(e)); }
+    d->owns = !in_ctx;
+    cudaError_t e = cudaSuccess;
+    if (in_ctx) {
+        int rc0 = ensure_cap(c, &c->d_seqblob, &c->seqblob_cap, bytes);
+        if (rc0) { delete d; return rc0; }
+        d->blob = c->d_seqblob;
+    } else {
+        e = cudaMalloc(&d->blob, bytes);
+        if (e != cudaSuccess) { delete d; return fail(c, PG_ERR_CUDA, std::string("cudaMalloc(seqs): ") + cudaGetErrorString(e)); }
+    }
     char* b = (char*)d->blob;
     e = cudaMemcpyAsync(b + o_res, s->res, (size_t)total, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(b + o_offs, s->offs, sizeof(int64_t) * n, cudaMemcpyHostToDevice, c->stream);
@@ -172,7 +189,8 @@ extern "C" int pg_seqs_upload(pg_context* c, const pg_seqs* s, pg_dev_seqs** out
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(b + o_flags, flags.data(), n, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // host staging vectors die at return
     if (e != cudaSuccess) {
-        cudaFree(d->blob); delete d;
+        if (d->owns) cudaFree(d->blob);
+        delete d;
         return fail(c, PG_ERR_CUDA, std::string("upload seqs: ") + cudaGetErrorString(e));
     }
     d->v.res = (const uint8_t*)(b + o_res);
@@ -189,6 +207,7 @@ extern "C" int pg_seqs_upload(pg_context* c, const pg_seqs* s, pg_dev_seqs** out
     d->plan_nitems = 0;
     d->plan_nsubs = 0;
     d->plan_multipass = false;
+    d->plan_cap = 0;
     // residues must index the matrix: remember the largest code
     uint8_t mx = 0;
     memset(d->present, 0, sizeof(d->present));
@@ -205,8 +224,10 @@ extern "C" void pg_seqs_free(pg_context* c, pg_dev_seqs* d)
 {
     if (!d) return;
     if (c) cudaSetDevice(c->device);
-    cudaFree(d->blob);
-    cudaFree(d->d_plan);
+    if (d->owns) {
+        cudaFree(d->blob);
+        cudaFree(d->d_plan);
+    }
     delete d;
 }
 
@@ -394,9 +415,17 @@ extern "C" int pg_calcdist_dev(pg_context* c, pg_dev_seqs* d, const pg_params* p
                 std::vector<uint32_t> subs;
                 bool mp = false;
                 build_packed_plan(d, k_begin, k_end, grid, &items2, &subs, &mp);
-                if (d->d_plan) { PG_CUDA(c, cudaStreamSynchronize(st)); PG_CUDA(c, cudaFree(d->d_plan)); d->d_plan = nullptr; }
                 const size_t ib = up256(sizeof(PgItem2) * std::max<size_t>(items2.size(), 1));
-                PG_CUDA(c, cudaMalloc(&d->d_plan, ib + sizeof(uint32_t) * std::max<size_t>(subs.size(), 1)));
+                const size_t need = ib + sizeof(uint32_t) * std::max<size_t>(subs.size(), 1);
+                if (d->owns) {
+                    if (d->d_plan && d->plan_cap < need) {
+                        PG_CUDA(c, cudaStreamSynchronize(st)); PG_CUDA(c, cudaFree(d->d_plan)); d->d_plan = nullptr;
+                    }
+                    if (!d->d_plan) { PG_CUDA(c, cudaMalloc(&d->d_plan, need)); d->plan_cap = need; }
+                } else {
+                    if ((rc = ensure_cap(c, &c->d_planbuf, &c->planbuf_cap, need))) return rc;
+                    d->d_plan = c->d_planbuf;
+                }
                 if (!items2.empty())
                     PG_CUDA(c, cudaMemcpyAsync(d->d_plan, items2.data(), sizeof(PgItem2) * items2.size(), cudaMemcpyHostToDevice, st));
                 if (!subs.empty())
@@ -469,7 +498,7 @@ extern "C" int pg_calcdist(pg_context* c, const pg_seqs* s, const pg_params* prm
     if (!c) return PG_ERR_ARG;
     if (!s || !prm) return fail(c, PG_ERR_ARG, "pg_calcdist: NULL argument");
     pg_dev_seqs* d = nullptr;
-    int rc = pg_seqs_upload(c, s, &d);
+    int rc = seqs_upload_impl(c, s, &d, true);
     if (rc) return rc;
     const size_t esz = prm->vtype ? sizeof(double) : sizeof(float);
     const size_t cnt = k_end > k_begin ? (size_t)(k_end - k_begin) : 0;
@@ -502,7 +531,7 @@ extern "C" int pg_score_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
         if (a_idx[p] < 0 || a_idx[p] >= s->nseq || b_idx[p] < 0 || b_idx[p] >= s->nseq)
             return fail(c, PG_ERR_ARG, "pg_score_pairs: sequence index out of range");
     pg_dev_seqs* d = nullptr;
-    if ((rc = pg_seqs_upload(c, s, &d))) return rc;
+    if ((rc = seqs_upload_impl(c, s, &d, true))) return rc;
     if (d->max_code >= dim) { pg_seqs_free(c, d); return fail(c, PG_ERR_ARG, "residue code outside the substitution matrix"); }
     IntScoring sc;
     if ((rc = make_int_scoring(c, prm, mtx, dim, d->present, &sc))) { pg_seqs_free(c, d); return rc; }
@@ -590,7 +619,7 @@ extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
     offs[0] = 0;
     if (npairs == 0) { *out_offs = offs; *out_pts = (pg_skl*)malloc(sizeof(pg_skl)); return PG_OK; }
     pg_dev_seqs* d = nullptr;
-    int rc = pg_seqs_upload(c, s, &d);
+    int rc = seqs_upload_impl(c, s, &d, true);
     if (rc) { free(offs); return rc; }
     IntScoring sc;
     if (d->max_code >= dim) rc = fail(c, PG_ERR_ARG, "residue code outside the substitution matrix");
@@ -760,6 +789,43 @@ extern "C" int64_t pg_calcdist_cells(const pg_seqs* s, const pg_params* prm, int
         for (int64_t i = i0; i < i1; ++i) cells += band_cells_closed(wl((int)i), lb, prm->alprm.sh);
     }
     return cells;
+}
+
+// Host-only view of the packed schedule (no device needed): how many (query pair, subject) slots the
+// plan has and how often every condensed index k in [k_begin, k_end) is covered (must be exactly 1).
+extern "C" int pg_debug_packed_plan(const pg_seqs* s, int64_t k_begin, int64_t k_end, int32_t grid_blocks,
+                                    int64_t* nitems, int64_t* nslots, uint8_t* cover)
+{
+    if (!s || k_end < k_begin) return PG_ERR_ARG;
+    pg_dev_seqs d;
+    d.owns = false; d.blob = nullptr; d.d_plan = nullptr;
+    d.h_wlen.resize(s->nseq);
+    d.max_wlen = 0;
+    for (int i = 0; i < s->nseq; ++i) {
+        d.h_wlen[i] = (s->right ? s->right[i] : s->lens[i]) - (s->left ? s->left[i] : 0);
+        d.max_wlen = std::max(d.max_wlen, d.h_wlen[i]);
+    }
+    std::vector<PgItem2> items;
+    std::vector<uint32_t> subs;
+    bool mp = false;
+    build_packed_plan(&d, k_begin, k_end, grid_blocks, &items, &subs, &mp);
+    if (nitems) *nitems = (int64_t)items.size();
+    if (nslots) *nslots = (int64_t)subs.size();
+    if (cover) {
+        memset(cover, 0, (size_t)(k_end - k_begin));
+        for (const PgItem2& it : items)
+            for (int32_t p = it.sub_begin; p < it.sub_end; ++p) {
+                const int64_t si = subs[p] & 0x3fffffffu;
+                const int64_t q[2] = {it.q0, it.q1};
+                for (int h = 0; h < 2; ++h)
+                    if ((subs[p] >> (30 + h)) & 1u) {
+                        const int64_t hi = std::max(q[h], si), lo = std::min(q[h], si);
+                        const int64_t k = hi * (hi - 1) / 2 + lo;
+                        if (k >= k_begin && k < k_end && cover[k - k_begin] < 255) ++cover[k - k_begin];
+                    }
+            }
+    }
+    return PG_OK;
 }
 
 extern "C" int pg_dpx_peak(pg_context* c, double* gops_s32, double* gops_s16x2)

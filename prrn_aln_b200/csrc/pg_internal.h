@@ -120,6 +120,8 @@ struct pg_dev_seqs {
     int32_t plan_nitems;
     int64_t plan_nsubs;
     bool plan_multipass;
+    bool owns;                  // false: blob / plan live in the context's reusable workspace
+    size_t plan_cap;
 };
 
 struct pg_context {
@@ -135,6 +137,8 @@ struct pg_context {
     void* d_out; size_t out_cap;
     void* d_pairs; size_t pairs_cap;
     void* d_dirs; size_t dirs_cap;
+    void* d_seqblob; size_t seqblob_cap;
+    void* d_planbuf; size_t planbuf_cap;
     void* d_trace; size_t trace_cap;
     int32_t* d_counter;
 };

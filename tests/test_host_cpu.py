@@ -200,3 +200,20 @@ def test_packed_int16x2_recurrence_emulation(emulp, oracle):
     assert emulp.k1p_emul_fits(15, 0, 9, 1300) == 1
     assert emulp.k1p_emul_fits(15, 0, 9, 2200) == 0
     assert emulp.k1p_emul_fits(13, -2, 9, 1300) == 1
+
+
+def test_packed_plan_covers_every_pair_exactly_once():
+    """The tournament schedule of the packed kernel (query pairs x subjects with two valid bits):
+    every condensed index of the requested range exactly once, for full triangles and shards."""
+    rng = np.random.default_rng(12)
+    for n in (2, 3, 4, 5, 8, 9, 64, 301):
+        enc = [rng.integers(3, 23, size=int(rng.integers(1, 600))).astype(np.uint8) for _ in range(n)]
+        ss = P.SeqSet(enc)
+        npair = n * (n - 1) // 2
+        ranges = [(0, npair)] + [(npair * r // w, npair * (r + 1) // w) for w in (2, 3, 8) for r in range(w)]
+        ranges += [(1, 1), (npair - 1, npair)]
+        for k0, k1 in ranges:
+            items, slots, cover = P.packed_plan_coverage(ss, k0, k1)
+            assert np.all(cover == 1), (n, k0, k1)
+            if k1 - k0 > 1000:
+                assert 2 * slots <= 1.05 * (k1 - k0) + 2 * n     # halves are almost never idle
