@@ -35,6 +35,7 @@ BASE_N = 1000               # config 2: 1,000 proteins of ~400 aa
 SH = -60                    # prrn5 default band shoulder (src/prrn5.cc:1272)
 OPS_PER_CELL = 9            # 5 add + 4 max per cell, affine score-only
 DPX_OPS_PER_INSTR = 2       # one viaddmax / vimax3 retires two of those scalar operations
+TRAFFIC_NCU = None          # dram bytes per launch of the fill kernel from the committed ncu capture (profiles/)
 CPU_SAMPLE_N = 400          # bounded CPU sample: first 400 sequences (79,800 pairs, ~1.1e10 cells)
 
 
@@ -253,20 +254,22 @@ def main():
 
     # ---- roofline of the dominant kernel (the fill): DPX issue rate measured on this device
     peak32, peak16 = ctx.dpx_peak()
+    # The C2 workload fits 16 bits (k1p_fits), so the fill runs the packed int16x2 kernel: one DPX
+    # instruction retires 2 scalar ops on each of 2 packed cells.  Peak = measured s16x2 issue rate x 4.
     achieved = gcups / world * OPS_PER_CELL              # per GPU, Gop/s of algorithmic add/max
-    peak = peak32 * DPX_OPS_PER_INSTR
-    roofline = {"bound": "dpx-int32 issue", "achieved": achieved, "peak": peak, "unit": "Gop/s",
-                "frac": achieved / peak, "traffic": None,
-                "peak_source": "measured here: pg_dpx_peak register-only __viaddmax_s32 chains = %.0f G thread-instr/s "
-                               "(x2 scalar ops each); MEASURED_PEAKS.json has no integer peak" % peak32,
-                "ops_per_cell": OPS_PER_CELL, "kernel_instr_per_cell": 4,
-                "issue_frac": gcups / world * 4 / peak32, "dpx_s16x2_ginstr": peak16,
+    peak = peak16 * DPX_OPS_PER_INSTR * 2
+    roofline = {"bound": "dpx-int16x2 issue", "achieved": achieved, "peak": peak, "unit": "Gop/s",
+                "frac": achieved / peak, "traffic": TRAFFIC_NCU,
+                "peak_source": "measured here: pg_dpx_peak register-only __viaddmax_s16x2 chains = %.0f G thread-instr/s "
+                               "(x2 scalar ops x2 packed cells each); MEASURED_PEAKS.json has no integer peak" % peak16,
+                "ops_per_cell": OPS_PER_CELL, "kernel_dpx_instr_per_cell": 2,
+                "issue_frac": gcups / world * 2 / peak16, "dpx_s32_ginstr": peak32,
                 "hbm_bytes_per_step": h2d + d2h}
 
     out = {
         "metric": "DP GCUPS (all-pairs calcdist, band cells)", "value": gcups, "unit": "GCUPS", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
         "config": {"workload": "C2 all-vs-all calcdist(DynScr): %d x ~400 aa synthetic proteins (seed 1), %d pairs, "
                                "BLOSUM62 u=2 v=9 sh=-60, prrn (double) build semantics; pairs sharded over %d GPU(s)"
                                % (ss.n, npair, world),

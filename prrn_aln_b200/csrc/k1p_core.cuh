@@ -79,18 +79,22 @@ PG_HD void k1p_lane_init(K1PLane<R>& L, const K1Geom& g0, const K1Geom& g1, int 
 }
 
 template <int R>
-PG_HD void k1p_lane_step(K1PLane<R>& L, const unsigned* sc, unsigned negv2, unsigned h_up, unsigned f_up,
+PG_HD void k1p_lane_step(K1PLane<R>& L, unsigned* sc, unsigned negv2, unsigned h_up, unsigned f_up,
                          unsigned* h_dn, unsigned* f_dn)
 {
-    unsigned diag = L.hdiag;
+    // phase 1 (independent per row): t_k = max(diag_k + S'_k, E_k), written over sc[k]; the old
+    // H[k] is consumed here, so phase 2 can write the new H[k] in place without register moves
+    sc[0] = K1P_ADDMAX(L.hdiag, sc[0], L.E[0]);
+#pragma unroll
+    for (int k = 1; k < R; ++k) sc[k] = K1P_ADDMAX(L.H[k - 1], sc[k], L.E[k]);
+    // phase 2: the vertical chain (one dependent instruction per row) and the eager horizontal state
     unsigned f = f_up;
     unsigned h = h_up;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-        unsigned t = K1P_ADDMAX(diag, sc[k], L.E[k]);
+        const unsigned t = sc[k];
         h = K1P_MAX(t, f);
         f = K1P_ADDMAX(t, negv2, f);
-        diag = L.H[k];
         L.H[k] = h;
         L.E[k] = K1P_ADDMAX(h, negv2, L.E[k]);
     }

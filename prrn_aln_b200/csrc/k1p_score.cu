@@ -19,16 +19,16 @@
 
 namespace {
 
-constexpr int R = 16;
+constexpr int RMAX = 16;        // largest rows-per-lane variant
 constexpr int NW = 8;
-constexpr int ROWS_PER_PASS = 32 * R;
 constexpr int MAXDIM = 32;
 constexpr int BLOCKS_PER_SM = 3;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int QMAX = RMAX / 4;
 
 __host__ __device__ inline size_t smem_bytes(int dim)
 {
-    return (size_t)(dim + NW) * (R / 4) * 32 * sizeof(uint4) + 16;
+    return (size_t)(dim + NW) * QMAX * 32 * sizeof(uint4) + 16;
 }
 
 __device__ __forceinline__ void store_result(const K1PArgs& a, int score, int qi, int si, int LQ, int LS)
@@ -56,157 +56,196 @@ __device__ __forceinline__ void store_result(const K1PArgs& a, int score, int qi
     }
 }
 
-__global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k1p_score_kernel(const K1PArgs a)
+// One work item with R rows per lane (R in {8,10,12,14,16}: the host picks the smallest variant whose
+// 32*R rows hold the longer query, so that 400-residue queries fill 29 of 32 lanes instead of 25).
+// The profile keeps the [letter][quad][lane][4] layout with Q = ceil(R/4) quads per lane.
+template <int R>
+__device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& item, uint4* sm_prof, uint4* sm_poke)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4* const sm_prof = reinterpret_cast<uint4*>(smem_raw);
-    uint4* const sm_poke = sm_prof + a.dim * (R / 4) * 32;
-    int* const sm_item = reinterpret_cast<int*>(sm_poke + NW * (R / 4) * 32);
+    constexpr int Q = (R + 3) / 4;
+    constexpr int RP = 4 * Q;
+    constexpr int ROWS_PER_PASS = 32 * R;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int gwarp = blockIdx.x * NW + warp;
     const unsigned negv2 = k1p_pack(-a.v, -a.v);
     const unsigned neg2 = k1p_pack(K1P_NEG, K1P_NEG);
+    const int qi0 = item.q0, qi1 = item.q1;
+    const uint8_t* q0 = a.seqs.res + a.seqs.offs[qi0] + a.seqs.left[qi0];
+    const uint8_t* q1 = a.seqs.res + a.seqs.offs[qi1] + a.seqs.left[qi1];
+    const int LQ0 = a.seqs.wlen[qi0], LQ1 = a.seqs.wlen[qi1];
+    const int LQ = max(LQ0, LQ1);
+    const int npass = LQ > 0 ? (LQ + ROWS_PER_PASS - 1) / ROWS_PER_PASS : 1;
 
+    for (int pass = 0; pass < npass; ++pass) {
+        const int pbase = pass * ROWS_PER_PASS;
+        {
+            unsigned* p = reinterpret_cast<unsigned*>(sm_prof);
+            const int total = a.dim * 32 * RP;
+            for (int idx = tid; idx < total; idx += NW * 32) {
+                int letter = idx / (32 * RP);
+                int rem = idx - letter * (32 * RP);
+                int j = rem >> 7, ln = (rem >> 2) & 31, c = rem & 3;
+                int kk = j * 4 + c;
+                int row = pbase + ln * R + kk;
+                bool ok = kk < R;
+                int s0 = ok && row < LQ0 ? a.mtx[(int)q0[row] * a.dim + letter] + 2 * a.u : 0;
+                int s1 = ok && row < LQ1 ? a.mtx[(int)q1[row] * a.dim + letter] + 2 * a.u : 0;
+                p[idx] = k1p_pack(s0, s1);
+            }
+        }
+        __syncthreads();
+
+        const int rows_here = min(LQ - pbase, ROWS_PER_PASS);
+        const int lanes = (rows_here + R - 1) / R;
+        const int mbase = pbase + lane * R;
+        const bool last_pass = pass == npass - 1;
+        const bool fin0 = LQ0 > pbase && LQ0 <= pbase + ROWS_PER_PASS;
+        const bool fin1 = LQ1 > pbase && LQ1 <= pbase + ROWS_PER_PASS;
+        const int r0 = LQ0 - 1 - pbase, r1 = LQ1 - 1 - pbase;
+
+        for (int sub = item.sub_begin + warp, ord = 0; sub < item.sub_end; sub += NW, ++ord) {
+            const unsigned ent = a.subs[sub];
+            const int si = (int)(ent & 0x3fffffffu);
+            const bool v0 = (ent >> 30) & 1u, v1 = (ent >> 31) & 1u;
+            const uint8_t* s = a.seqs.res + a.seqs.offs[si] + a.seqs.left[si];
+            const int LS = a.seqs.wlen[si];
+            K1Geom g0, g1;
+            g0.LQ = LQ0; g0.LS = LS; g0.u = a.u; g0.v = a.v;
+            g1.LQ = LQ1; g1.LS = LS; g1.u = a.u; g1.v = a.v;
+            k1_band(LQ0, LS, a.sh, &g0.lw, &g0.up);
+            k1_band(LQ1, LS, a.sh, &g1.lw, &g1.up);
+            g0.topOpen = g1.topOpen = g0.leftOpen = g1.leftOpen = -a.v;
+            g0.topExt = g1.topExt = g0.leftExt = g1.leftExt = -a.u;
+            if (LS == 0 || LQ0 == 0 || LQ1 == 0) {
+                // empty sequences never reach this kernel (the host routes such batches to the
+                // int32 kernel); kept for safety: the score is a boundary value
+                if (lane == 0 && pass == 0) {
+                    if (v0) store_result(a, (LQ0 == 0 ? k1_top(g0, LS - 1) : k1_left(g0, LQ0 - 1)) - (LQ0 + LS) * a.u, qi0, si, LQ0, LS);
+                    if (v1) store_result(a, (LQ1 == 0 ? k1_top(g1, LS - 1) : k1_left(g1, LQ1 - 1)) - (LQ1 + LS) * a.u, qi1, si, LQ1, LS);
+                }
+                continue;
+            }
+            uint2* rowbuf = a.rowbuf ? a.rowbuf + ((int64_t)gwarp * a.rowbuf_stride + (int64_t)ord * LS) : nullptr;
+
+            K1PLane<R> L;
+            k1p_lane_init(L, g0, g1, mbase, negv2);
+            const int lwm0 = g0.lw + mbase, upm0 = g0.up + 1 + mbase;
+            const int lwm1 = g1.lw + mbase, upm1 = g1.up + 1 + mbase;
+            // top boundary of pass 0 as seen by lane 0 (n == step): base + (n+1)*slope while inside
+            // the band, then -inf; warp-uniform, so it costs two selects per step instead of a branch
+            const int tslope = g0.topExt + g0.u;
+            unsigned recv_h = neg2, recv_f = neg2;
+            const uint4* pp = sm_prof + lane;
+            uint4* pk = sm_poke + warp * (QMAX * 32) + lane;
+            const int nsteps = LS + lanes - 1;
+            const bool lane0 = lane == 0;
+
+            for (int step = 0; step < nsteps; ++step) {
+                const int n = step - lane;
+                unsigned h_dn = neg2, f_dn = neg2;
+                if (n >= 0 && n < LS && lane < lanes) {
+                    unsigned h_up = recv_h, f_up = recv_f;
+                    if (pass == 0) {
+                        const int kk = step + 1;
+                        const int t0 = kk <= g0.up ? g0.topOpen + kk * tslope : K1P_NEG;
+                        const int t1 = kk <= g1.up ? g1.topOpen + kk * tslope : K1P_NEG;
+                        const unsigned topv = k1p_pack(t0, t1);
+                        const unsigned topf = K1P_ADDMAX(topv, negv2, neg2);
+                        h_up = lane0 ? topv : h_up;
+                        f_up = lane0 ? topf : f_up;
+                    } else if (lane0) {
+                        uint2 v = __ldcg(rowbuf + n); h_up = v.x; f_up = v.y;
+                    }
+                    const int kL0 = n - lwm0, kU0 = n - upm0, kL1 = n - lwm1, kU1 = n - upm1;
+                    if ((unsigned)kL0 < (unsigned)R || (unsigned)kU0 < (unsigned)R ||
+                        (unsigned)kL1 < (unsigned)R || (unsigned)kU1 < (unsigned)R) {
+#pragma unroll
+                        for (int j = 0; j < Q; ++j)
+                            pk[j * 32] = make_uint4(L.E[4 * j], 4 * j + 1 < R ? L.E[4 * j + 1] : 0u,
+                                                    4 * j + 2 < R ? L.E[4 * j + 2] : 0u, 4 * j + 3 < R ? L.E[4 * j + 3] : 0u);
+                        short* pks = reinterpret_cast<short*>(pk);
+                        if ((unsigned)kL0 < (unsigned)R) pks[(kL0 >> 2) * 256 + (kL0 & 3) * 2] = (short)K1P_NEG;
+                        if ((unsigned)kU0 < (unsigned)R) pks[(kU0 >> 2) * 256 + (kU0 & 3) * 2] = (short)K1P_NEG;
+                        if ((unsigned)kL1 < (unsigned)R) pks[(kL1 >> 2) * 256 + (kL1 & 3) * 2 + 1] = (short)K1P_NEG;
+                        if ((unsigned)kU1 < (unsigned)R) pks[(kU1 >> 2) * 256 + (kU1 & 3) * 2 + 1] = (short)K1P_NEG;
+#pragma unroll
+                        for (int j = 0; j < Q; ++j) {
+                            uint4 v = pk[j * 32];
+                            L.E[4 * j] = v.x;
+                            if (4 * j + 1 < R) L.E[4 * j + 1] = v.y;
+                            if (4 * j + 2 < R) L.E[4 * j + 2] = v.z;
+                            if (4 * j + 3 < R) L.E[4 * j + 3] = v.w;
+                        }
+                    }
+                    const int letter = __ldg(s + n);
+                    const uint4* pl = pp + letter * (Q * 32);
+                    unsigned sc[RP];
+#pragma unroll
+                    for (int j = 0; j < Q; ++j) {
+                        uint4 v = pl[j * 32];
+                        sc[4 * j] = v.x; sc[4 * j + 1] = v.y; sc[4 * j + 2] = v.z; sc[4 * j + 3] = v.w;
+                    }
+                    k1p_lane_step(L, sc, negv2, h_up, f_up, &h_dn, &f_dn);
+                    if (lane == 31 && !last_pass) __stcg(rowbuf + n, make_uint2(h_dn, f_dn));
+                }
+                recv_h = __shfl_up_sync(FULL, h_dn, 1);
+                recv_f = __shfl_up_sync(FULL, f_dn, 1);
+            }
+
+            if (fin0 || fin1) {
+                unsigned val0 = 0, val1 = 0;
+                const int k0f = r0 >= 0 ? r0 % R : -1, k1f = r1 >= 0 ? r1 % R : -1;
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    if (k == k0f) val0 = L.H[k];
+                    if (k == k1f) val1 = L.H[k];
+                }
+                val0 = __shfl_sync(FULL, val0, (r0 >= 0 ? r0 / R : 0) & 31);
+                val1 = __shfl_sync(FULL, val1, (r1 >= 0 ? r1 / R : 0) & 31);
+                if (lane == 0) {
+                    if (fin0 && v0) store_result(a, k1p_lo(val0) - (LQ0 + LS) * a.u, qi0, si, LQ0, LS);
+                    if (fin1 && v1) store_result(a, k1p_hi(val1) - (LQ1 + LS) * a.u, qi1, si, LQ1, LS);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k1p_score_kernel(const K1PArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* const sm_prof = reinterpret_cast<uint4*>(smem_raw);
+    uint4* const sm_poke = sm_prof + a.dim * QMAX * 32;
+    int* const sm_item = reinterpret_cast<int*>(sm_poke + NW * QMAX * 32);
     for (;;) {
-        if (tid == 0) *sm_item = atomicAdd(a.counter, 1);
+        if (threadIdx.x == 0) *sm_item = atomicAdd(a.counter, 1);
         __syncthreads();
         const int it = *sm_item;
         if (it >= a.nitems) break;
         const PgItem2 item = a.items[it];
-        const int qi0 = item.q0, qi1 = item.q1;
-        const uint8_t* q0 = a.seqs.res + a.seqs.offs[qi0] + a.seqs.left[qi0];
-        const uint8_t* q1 = a.seqs.res + a.seqs.offs[qi1] + a.seqs.left[qi1];
-        const int LQ0 = a.seqs.wlen[qi0], LQ1 = a.seqs.wlen[qi1];
-        const int LQ = max(LQ0, LQ1);
-        const int npass = LQ > 0 ? (LQ + ROWS_PER_PASS - 1) / ROWS_PER_PASS : 1;
-
-        for (int pass = 0; pass < npass; ++pass) {
-            const int pbase = pass * ROWS_PER_PASS;
-            {
-                unsigned* p = reinterpret_cast<unsigned*>(sm_prof);
-                const int total = a.dim * 32 * R;
-                for (int idx = tid; idx < total; idx += NW * 32) {
-                    int letter = idx / (32 * R);
-                    int rem = idx - letter * (32 * R);
-                    int j = rem >> 7, ln = (rem >> 2) & 31, c = rem & 3;
-                    int row = pbase + ln * R + j * 4 + c;
-                    int s0 = row < LQ0 ? a.mtx[(int)q0[row] * a.dim + letter] + 2 * a.u : 0;
-                    int s1 = row < LQ1 ? a.mtx[(int)q1[row] * a.dim + letter] + 2 * a.u : 0;
-                    p[idx] = k1p_pack(s0, s1);
-                }
-            }
-            __syncthreads();
-
-            const int rows_here = min(LQ - pbase, ROWS_PER_PASS);
-            const int lanes = (rows_here + R - 1) / R;
-            const int mbase = pbase + lane * R;
-            const bool last_pass = pass == npass - 1;
-            // which half finishes in this pass, and where
-            const bool fin0 = LQ0 > pbase && LQ0 <= pbase + ROWS_PER_PASS;
-            const bool fin1 = LQ1 > pbase && LQ1 <= pbase + ROWS_PER_PASS;
-            const int r0 = LQ0 - 1 - pbase, r1 = LQ1 - 1 - pbase;
-
-            for (int sub = item.sub_begin + warp, ord = 0; sub < item.sub_end; sub += NW, ++ord) {
-                const unsigned ent = a.subs[sub];
-                const int si = (int)(ent & 0x3fffffffu);
-                const bool v0 = (ent >> 30) & 1u, v1 = (ent >> 31) & 1u;
-                const uint8_t* s = a.seqs.res + a.seqs.offs[si] + a.seqs.left[si];
-                const int LS = a.seqs.wlen[si];
-                K1Geom g0, g1;
-                g0.LQ = LQ0; g0.LS = LS; g0.u = a.u; g0.v = a.v;
-                g1.LQ = LQ1; g1.LS = LS; g1.u = a.u; g1.v = a.v;
-                k1_band(LQ0, LS, a.sh, &g0.lw, &g0.up);
-                k1_band(LQ1, LS, a.sh, &g1.lw, &g1.up);
-                g0.topOpen = g1.topOpen = g0.leftOpen = g1.leftOpen = -a.v;
-                g0.topExt = g1.topExt = g0.leftExt = g1.leftExt = -a.u;
-                if (LS == 0 || LQ0 == 0 || LQ1 == 0) {
-                    // degenerate halves are boundary values; a non-degenerate partner is handled by
-                    // the host, which never packs an empty sequence with a non-empty one
-                    if (lane == 0 && pass == 0) {
-                        if (v0) store_result(a, (LQ0 == 0 ? k1_top(g0, LS - 1) : k1_left(g0, LQ0 - 1)) - (LQ0 + LS) * a.u, qi0, si, LQ0, LS);
-                        if (v1) store_result(a, (LQ1 == 0 ? k1_top(g1, LS - 1) : k1_left(g1, LQ1 - 1)) - (LQ1 + LS) * a.u, qi1, si, LQ1, LS);
-                    }
-                    continue;
-                }
-                uint2* rowbuf = a.rowbuf ? a.rowbuf + ((int64_t)gwarp * a.rowbuf_stride + (int64_t)ord * LS) : nullptr;
-
-                K1PLane<R> L;
-                k1p_lane_init(L, g0, g1, mbase, negv2);
-                const int lwm0 = g0.lw + mbase, upm0 = g0.up + 1 + mbase;
-                const int lwm1 = g1.lw + mbase, upm1 = g1.up + 1 + mbase;
-                unsigned recv_h = neg2, recv_f = neg2;
-                const uint4* pp = sm_prof + lane;
-                uint4* pk = sm_poke + warp * ((R / 4) * 32) + lane;
-                const int nsteps = LS + lanes - 1;
-
-                for (int step = 0; step < nsteps; ++step) {
-                    const int n = step - lane;
-                    unsigned h_dn = neg2, f_dn = neg2;
-                    if (n >= 0 && n < LS && lane < lanes) {
-                        unsigned h_up = recv_h, f_up = recv_f;
-                        if (lane == 0) {
-                            if (pass == 0) {
-                                h_up = k1p_pack(k1p_top(g0, n), k1p_top(g1, n));
-                                f_up = K1P_ADDMAX(h_up, negv2, neg2);
-                            } else { uint2 v = __ldcg(rowbuf + n); h_up = v.x; f_up = v.y; }
-                        }
-                        const int kL0 = n - lwm0, kU0 = n - upm0, kL1 = n - lwm1, kU1 = n - upm1;
-                        if ((unsigned)kL0 < (unsigned)R || (unsigned)kU0 < (unsigned)R ||
-                            (unsigned)kL1 < (unsigned)R || (unsigned)kU1 < (unsigned)R) {
-#pragma unroll
-                            for (int j = 0; j < R / 4; ++j)
-                                pk[j * 32] = make_uint4(L.E[4 * j], L.E[4 * j + 1], L.E[4 * j + 2], L.E[4 * j + 3]);
-                            short* pks = reinterpret_cast<short*>(pk);
-                            if ((unsigned)kL0 < (unsigned)R) pks[(kL0 >> 2) * 256 + (kL0 & 3) * 2] = (short)K1P_NEG;
-                            if ((unsigned)kU0 < (unsigned)R) pks[(kU0 >> 2) * 256 + (kU0 & 3) * 2] = (short)K1P_NEG;
-                            if ((unsigned)kL1 < (unsigned)R) pks[(kL1 >> 2) * 256 + (kL1 & 3) * 2 + 1] = (short)K1P_NEG;
-                            if ((unsigned)kU1 < (unsigned)R) pks[(kU1 >> 2) * 256 + (kU1 & 3) * 2 + 1] = (short)K1P_NEG;
-#pragma unroll
-                            for (int j = 0; j < R / 4; ++j) {
-                                uint4 v = pk[j * 32];
-                                L.E[4 * j] = v.x; L.E[4 * j + 1] = v.y; L.E[4 * j + 2] = v.z; L.E[4 * j + 3] = v.w;
-                            }
-                        }
-                        const int letter = __ldg(s + n);
-                        const uint4* pl = pp + letter * ((R / 4) * 32);
-                        unsigned sc[R];
-#pragma unroll
-                        for (int j = 0; j < R / 4; ++j) {
-                            uint4 v = pl[j * 32];
-                            sc[4 * j] = v.x; sc[4 * j + 1] = v.y; sc[4 * j + 2] = v.z; sc[4 * j + 3] = v.w;
-                        }
-                        k1p_lane_step(L, sc, negv2, h_up, f_up, &h_dn, &f_dn);
-                        if (lane == 31 && !last_pass) __stcg(rowbuf + n, make_uint2(h_dn, f_dn));
-                    }
-                    recv_h = __shfl_up_sync(FULL, h_dn, 1);
-                    recv_f = __shfl_up_sync(FULL, f_dn, 1);
-                }
-
-                if (fin0 || fin1) {
-                    unsigned val0 = 0, val1 = 0;
-#pragma unroll
-                    for (int k = 0; k < R; ++k) {
-                        if (k == (r0 & (R - 1))) val0 = L.H[k];
-                        if (k == (r1 & (R - 1))) val1 = L.H[k];
-                    }
-                    val0 = __shfl_sync(FULL, val0, (r0 / R) & 31);
-                    val1 = __shfl_sync(FULL, val1, (r1 / R) & 31);
-                    if (lane == 0) {
-                        if (fin0 && v0) store_result(a, k1p_lo(val0) - (LQ0 + LS) * a.u, qi0, si, LQ0, LS);
-                        if (fin1 && v1) store_result(a, k1p_hi(val1) - (LQ1 + LS) * a.u, qi1, si, LQ1, LS);
-                    }
-                }
-            }
-            __syncthreads();
+        switch (item.rows) {
+        case 8:  process_item<8>(a, item, sm_prof, sm_poke); break;
+        case 10: process_item<10>(a, item, sm_prof, sm_poke); break;
+        case 12: process_item<12>(a, item, sm_prof, sm_poke); break;
+        case 14: process_item<14>(a, item, sm_prof, sm_poke); break;
+        default: process_item<16>(a, item, sm_prof, sm_poke); break;
         }
     }
 }
 
 }  // namespace
 
-int k1p_rows_per_pass() { return ROWS_PER_PASS; }
+int k1p_rows_per_pass() { return 32 * RMAX; }
+int k1p_pick_rows(int lq)
+{
+    const int opts[5] = {8, 10, 12, 14, 16};
+    for (int i = 0; i < 5; ++i)
+        if (lq <= 32 * opts[i]) return opts[i];
+    return 16;
+}
 int k1p_warps_per_block() { return NW; }
 int k1p_blocks_per_sm() { return BLOCKS_PER_SM; }
 

@@ -335,6 +335,8 @@ static void build_packed_plan(const pg_dev_seqs* d, int64_t k0, int64_t k1, int 
         for (size_t i = 0; i < list.size(); i += cc) {
             PgItem2 it;
             it.q0 = qa; it.q1 = qb;
+            it.rows = k1p_pick_rows(std::max(d->h_wlen[qa], d->h_wlen[qb]));
+            it.pad[0] = it.pad[1] = it.pad[2] = 0;
             it.sub_begin = (int32_t)subs->size();
             const size_t e = std::min(list.size(), i + (size_t)cc);
             subs->insert(subs->end(), list.begin() + i, list.begin() + e);

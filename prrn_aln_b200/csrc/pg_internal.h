@@ -61,6 +61,8 @@ struct K1Args {
 struct PgItem2 {
     int32_t q0, q1;
     int32_t sub_begin, sub_end;     // range in subs[]
+    int32_t rows;                   // rows per lane of the kernel variant (8, 10, 12, 14 or 16)
+    int32_t pad[3];
 };
 
 struct K1PArgs {
@@ -152,6 +154,7 @@ cudaError_t k1_self_launch(const PgDevSeqs& s, const int32_t* mtx, int dim, int3
 // k1p_score.cu
 cudaError_t k1p_launch(const K1PArgs& a, int grid_blocks, cudaStream_t st);
 int k1p_rows_per_pass();
+int k1p_pick_rows(int lq);
 int k1p_warps_per_block();
 int k1p_blocks_per_sm();
 // k2_align.cu
