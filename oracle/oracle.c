@@ -152,10 +152,185 @@ static double aln_score_d_##SUFFIX(const orc_seq *a, const orc_seq *b, const dou
 DEFINE_SCORE_D(float, f32, (-(FLT_MAX / 16 * 7)))
 DEFINE_SCORE_D(double, f64, (-(DBL_MAX / 16 * 7)))
 
+
+/* ---- Smith-Waterman-Gotoh score: Fwd2d ctor + swgforwardD (fwd2d1.cc:57-90, 162-189) ----------- */
+#define DEFINE_SCORE_SWG(VT, SUFFIX, NEVSEL_V)                                                      \
+static double aln_score_swg_##SUFFIX(const orc_seq *a, const orc_seq *b, const double *mtx, int dim,\
+                                     const orc_params *p)                                           \
+{                                                                                                   \
+    const VT uu = (VT)((float)p->u * (float)p->scale);                                              \
+    const VT vv = (VT)((float)p->v * (float)p->scale);                                              \
+    const float tgapf = (float)p->tgapf;                                                            \
+    orc_window w;                                                                                   \
+    orc_stripe(a, b, p->sh, &w);                                                                    \
+    const int lw = w.lw, up = w.up, W = w.width;                                                    \
+    const int al = a->left, ar = a->right, bl = b->left, br = b->right;                             \
+    const int r0 = bl - al;                                                                         \
+    VT *bnd = (VT *)malloc(sizeof(VT) * (size_t)W);                                                 \
+    VT *BND = bnd - lw + 1;                                                                         \
+    for (int r = lw; r <= up; ++r) BND[r] = 0;                                                      \
+    if (!a->exgl) {                                                                                 \
+        float ltg = al ? 1.f : tgapf;                                                               \
+        VT gp = (VT)(-vv * ltg), ge = (VT)(-uu * ltg);                                              \
+        for (int r = r0 + 1; r <= up; ++r) BND[r] = gp += ge;                                       \
+    }                                                                                               \
+    if (!b->exgl) {                                                                                 \
+        float ltg = bl ? 1.f : tgapf;                                                               \
+        VT gp = (VT)(-vv * ltg), ge = (VT)(-uu * ltg);                                              \
+        for (int r = r0 - 1; r >= lw; --r) BND[r] = gp += ge;                                       \
+    }                                                                                               \
+    const int NB = br - bl + 2;                                                                     \
+    VT *buf = (VT *)malloc(sizeof(VT) * 4 * (size_t)NB);                                            \
+    VT *Hp = buf, *Gp = buf + NB, *Hc = buf + 2 * NB, *Gc = buf + 3 * NB;                           \
+    for (int n = bl - 1; n < br; ++n) {                                                             \
+        int r = n - (al - 1);                                                                       \
+        Hp[n - bl + 1] = (r >= lw && r <= up) ? BND[r] : (VT)ORC_NEG_INT;                           \
+        Gp[n - bl + 1] = NEVSEL_V;                                                                  \
+    }                                                                                               \
+    VT maxh = NEVSEL_V;                                                                             \
+    const VT vzero = 0;                                                                             \
+    for (int m = al; m < ar; ++m) {                                                                 \
+        const int n0 = ORC_MAX(m + lw, bl), n9 = ORC_MIN(m + up + 1, br);                           \
+        const double *srow = mtx + (size_t)a->res[m] * dim;                                         \
+        { int r = bl - 1 - m; Hc[0] = (r >= lw && r <= up) ? BND[r] : (VT)ORC_NEG_INT; }            \
+        VT hleft = (n0 == bl) ? Hc[0] : (VT)ORC_NEG_INT, fleft = NEVSEL_V;                          \
+        for (int n = n0; n < n9; ++n) {                                                             \
+            const int j = n - bl + 1;                                                               \
+            const int inb = (n - m + 1 <= up);                                                      \
+            VT habove = inb ? Hp[j] : (VT)ORC_NEG_INT;                                              \
+            VT gabove = inb ? Gp[j] : NEVSEL_V;                                                     \
+            VT f = ORC_MAX(hleft - vv, fleft) - uu;              /* fwd2d1.cc:176 */                \
+            VT g = ORC_MAX(habove - vv, gabove) - uu;            /* :177 */                         \
+            VT h = Hp[j - 1] + (VT)srow[b->res[n]];              /* :178 */                         \
+            h = ORC_MAX(ORC_MAX(ORC_MAX(h, f), g), vzero);       /* :179 */                         \
+            maxh = ORC_MAX(maxh, h);                             /* :180 */                         \
+            Hc[j] = h; Gc[j] = g;                                                                   \
+            hleft = h; fleft = f;                                                                   \
+        }                                                                                           \
+        VT *t = Hp; Hp = Hc; Hc = t; t = Gp; Gp = Gc; Gc = t;                                       \
+    }                                                                                               \
+    free(bnd); free(buf);                                                                           \
+    return (double)maxh;                                                                            \
+}
+
+DEFINE_SCORE_SWG(float, f32, (-(FLT_MAX / 16 * 7)))
+DEFINE_SCORE_SWG(double, f64, (-(DBL_MAX / 16 * 7)))
+
+/* ---- semi-global score with end points: Fwd2d_vd ctor + forwardD(ends) + lastD(ends)
+ *      (fwd2d1.cc:212-322).  Every value carries the diagonal on which its path left the boundary.
+ *      Quirks kept: the origin record is vclear'ed, so its r is 0 and not r0 (:226); a's exgl is
+ *      ignored while b's is honoured (:227,234); gg subtracts (uu + vv) in one step (:309). -------- */
+#define DEFINE_SCORE_VD(VT, SUFFIX)                                                                 \
+typedef struct { VT val; int r; } o_vd_##SUFFIX;                                                    \
+static double aln_score_vd_##SUFFIX(const orc_seq *a, const orc_seq *b, const double *mtx, int dim, \
+                                    const orc_params *p, int *ends)                                 \
+{                                                                                                   \
+    typedef o_vd_##SUFFIX VD;                                                                       \
+    const VT uu = (VT)((float)p->u * (float)p->scale);                                              \
+    const VT vv = (VT)((float)p->v * (float)p->scale);                                              \
+    const float tgapf = (float)p->tgapf;                                                            \
+    orc_window w;                                                                                   \
+    orc_stripe(a, b, p->sh, &w);                                                                    \
+    const int lw = w.lw, up = w.up, W = w.width;                                                    \
+    const int al = a->left, ar = a->right, bl = b->left, br = b->right;                             \
+    const int r0 = bl - al;                                                                         \
+    const VD black = {(VT)ORC_NEG_INT, 0};                                                          \
+    VD *fin = (VD *)malloc(sizeof(VD) * (size_t)W);                                                 \
+    VD *FIN = fin - lw + 1;                                                                         \
+    for (int r = lw - 1; r <= up + 1; ++r) FIN[r] = black;                                          \
+    FIN[r0].val = 0; FIN[r0].r = 0;                                                                 \
+    {                                                                                               \
+        float ltg = al ? 1.f : tgapf;                                                               \
+        VT gp = (VT)(-vv * ltg), ge = (VT)(-uu * ltg);                                              \
+        for (int r = r0 + 1; r <= up; ++r) { FIN[r].val = gp += ge; FIN[r].r = r; }                 \
+        ltg = bl ? 1.f : (b->exgl ? 0.f : tgapf);                                                   \
+        gp = (VT)(-vv * ltg); ge = (VT)(-uu * ltg);                                                 \
+        for (int r = r0 - 1; r >= lw; --r) { FIN[r].val = gp += ge; FIN[r].r = r; }                 \
+    }                                                                                               \
+    VD *bnd = (VD *)malloc(sizeof(VD) * (size_t)W);                                                 \
+    memcpy(bnd, fin, sizeof(VD) * (size_t)W);                                                       \
+    VD *BND = bnd - lw + 1;                                                                         \
+    const int NB = br - bl + 2;                                                                     \
+    VD *buf = (VD *)malloc(sizeof(VD) * 4 * (size_t)NB);                                            \
+    VD *Hp = buf, *Gp = buf + NB, *Hc = buf + 2 * NB, *Gc = buf + 3 * NB;                           \
+    for (int n = bl - 1; n < br; ++n) {                                                             \
+        int r = n - (al - 1);                                                                       \
+        Hp[n - bl + 1] = (r >= lw && r <= up) ? BND[r] : black;                                     \
+        Gp[n - bl + 1] = black;                                                                     \
+    }                                                                                               \
+    for (int m = al; m < ar; ++m) {                                                                 \
+        const int n0 = ORC_MAX(m + lw, bl), n9 = ORC_MIN(m + up + 1, br);                           \
+        const double *srow = mtx + (size_t)a->res[m] * dim;                                         \
+        { int r = bl - 1 - m; Hc[0] = (r >= lw && r <= up) ? BND[r] : black; }                      \
+        VD hleft = (n0 == bl) ? Hc[0] : black, fleft = black;                                       \
+        for (int n = n0; n < n9; ++n) {                                                             \
+            const int j = n - bl + 1;                                                               \
+            const int inb = (n - m + 1 <= up);                                                      \
+            VD habove = inb ? Hp[j] : black, gabove = inb ? Gp[j] : black;                          \
+            VD ng, eg, f, g, h;                                                                     \
+            ng.val = hleft.val - vv - uu; ng.r = hleft.r;        /* fwd2d1.cc:305 */                \
+            eg.val = fleft.val - uu; eg.r = fleft.r;             /* :306 */                         \
+            f = ng.val > eg.val ? ng : eg;                       /* :307 */                         \
+            ng = habove; ng.val -= (uu + vv);                    /* :308 */                         \
+            eg = gabove; eg.val -= uu;                           /* :309 */                         \
+            g = ng.val > eg.val ? ng : eg;                       /* :310 */                         \
+            h = Hp[j - 1]; h.val += (VT)srow[b->res[n]];         /* :311 */                         \
+            ng = f.val > g.val ? f : g;                          /* :312 */                         \
+            h = h.val > ng.val ? h : ng;                         /* :313 */                         \
+            Hc[j] = h; Gc[j] = g;                                                                   \
+            hleft = h; fleft = f;                                                                   \
+            FIN[n - m] = h;                                                                         \
+        }                                                                                           \
+        VD *t = Hp; Hp = Hc; Hc = t; t = Gp; Gp = Gc; Gc = t;                                       \
+    }                                                                                               \
+    free(bnd); free(buf);                                                                           \
+    /* lastD(ends), fwd2d1.cc:271-312 */                                                            \
+    const int r9 = br - ar;                                                                         \
+    float rtg = b->exgr ? 0.f : tgapf;                                                              \
+    int dm = 0, dn = 0;                                                                             \
+    if (br == b->len && rtg < 1) {                                                                  \
+        int rw = up + 1, rf = br - al;                                                              \
+        if (rf < rw) rw = rf;                                                                       \
+        for (int r = rw - 1; r >= r9; --r) {                                                        \
+            ++dm;                                                                                   \
+            VT gpn = dm == 1 ? vv + uu : uu;                                                        \
+            FIN[r + 1].val += (VT)(gpn * rtg);                                                      \
+            if (FIN[r].val < FIN[r + 1].val) FIN[r] = FIN[r + 1]; else dm = 0;                      \
+        }                                                                                           \
+    }                                                                                               \
+    rtg = a->exgr ? 0.f : tgapf;                                                                    \
+    if (ar == a->len && rtg < 1) {                                                                  \
+        int rw = lw, rf = bl - ar + 1;                                                              \
+        if (rf > rw) rw = rf;                                                                       \
+        for (int r = rw + 1; r <= r9; ++r) {                                                        \
+            ++dn;                                                                                   \
+            VT gpn = dn == 1 ? vv + uu : uu;                                                        \
+            FIN[r - 1].val += (VT)(gpn * rtg);                                                      \
+            if (FIN[r].val < FIN[r - 1].val) FIN[r] = FIN[r - 1]; else dn = 0;                      \
+        }                                                                                           \
+    }                                                                                               \
+    ends[0] = FIN[r9].r - r0;                                                                       \
+    ends[1] = dn ? dn : -dm;                                                                        \
+    double res = (double)FIN[r9].val;                                                               \
+    free(fin);                                                                                      \
+    return res;                                                                                     \
+}
+
+DEFINE_SCORE_VD(float, f32)
+DEFINE_SCORE_VD(double, f64)
+
 double orc_aln_score_d(const orc_seq *a, const orc_seq *b, const double *mtx, int dim,
                        const orc_params *p)
 {
     return p->vtype ? aln_score_d_f64(a, b, mtx, dim, p) : aln_score_d_f32(a, b, mtx, dim, p);
+}
+
+double orc_aln_score_full(const orc_seq *a, const orc_seq *b, const double *mtx, int dim,
+                          const orc_params *p, int *ends)
+{   /* alnScoreD dispatch, fwd2d1.cc:324-337 */
+    if (p->lcl & 16) return p->vtype ? aln_score_swg_f64(a, b, mtx, dim, p) : aln_score_swg_f32(a, b, mtx, dim, p);
+    if (ends) return p->vtype ? aln_score_vd_f64(a, b, mtx, dim, p, ends) : aln_score_vd_f32(a, b, mtx, dim, p, ends);
+    return orc_aln_score_d(a, b, mtx, dim, p);
 }
 
 double orc_self_score(const orc_seq *a, const double *mtx, int dim, const orc_params *p)
@@ -187,6 +362,38 @@ double orc_score2dist(double scr, int la, int lb, double self_a, double self_b, 
     }
 }
 
+/* alnscore2dist(), algmode.lcl branch (aln2.cc:296-320): semi-global score with end points, the
+ * denominator from the self scores of the aligned sub-windows, dlen from the trimmed lengths. */
+double orc_score2dist_lcl(const orc_seq *a0, const orc_seq *b0, const double *mtx, int dim,
+                          const orc_params *p, double *raw, int *ends_out)
+{
+    orc_seq a = *a0, b = *b0;
+    a.exgl = (p->lcl & 1) != 0; a.exgr = (p->lcl & 2) != 0;      /* exg_seq, seq.cc:858-863 */
+    b.exgl = (p->lcl & 4) != 0; b.exgr = (p->lcl & 8) != 0;
+    int ends[2] = {0, 0};
+    double scr = orc_aln_score_full(&a, &b, mtx, dim, p, ends);
+    if (raw) *raw = scr;
+    if (ends_out) { ends_out[0] = ends[0]; ends_out[1] = ends[1]; }
+    int al = a.left, bl = b.left, ar = a.right, br = b.right;
+    if (ends[0] > 0) bl += ends[0]; else if (ends[0] < 0) al -= ends[0];
+    if (ends[1] > 0) br -= ends[1]; else if (ends[1] < 0) ar += ends[1];
+    orc_seq at = a, bt = b;
+    at.left = al; at.right = ar; bt.left = bl; bt.right = br;
+    const double sa = orc_self_score(&at, mtx, dim, p), sb = orc_self_score(&bt, mtx, dim, p);
+    const int dlen = abs(ar - al - br + bl);
+    if (p->vtype) {
+        double denome = sqrt(sa * sb);
+        double s = scr + (float)p->u * dlen / 2;
+        return 100. * (1. - s / denome);
+    } else {
+        float denome = (float)sqrt((float)sa * (float)sb);
+        float s = (float)scr;
+        s += (float)p->u * dlen / 2;
+        float dst = (float)(1. - s / denome);
+        return (float)(100. * dst);
+    }
+}
+
 void orc_calcdist(const orc_seq *seqs, int nn, const double *mtx, int dim, const orc_params *p,
                   double *dist, double *raw_scores)
 {   /* phyl.cc:318-342 (DynScr): selfscr per sequence, dpscore per pair in elem(i,j) order */
@@ -195,6 +402,12 @@ void orc_calcdist(const orc_seq *seqs, int nn, const double *mtx, int dim, const
     for (int j = 1; j < nn; ++j)
         for (int i = 0; i < j; ++i) {
             size_t k = (size_t)j * (j - 1) / 2 + i;
+            if (p->lcl) {
+                double scr;
+                dist[k] = orc_score2dist_lcl(seqs + i, seqs + j, mtx, dim, p, &scr, 0);
+                if (raw_scores) raw_scores[k] = scr;
+                continue;
+            }
             double scr = orc_aln_score_d(seqs + i, seqs + j, mtx, dim, p);
             if (raw_scores) raw_scores[k] = scr;
             dist[k] = orc_score2dist(scr, seqs[i].right - seqs[i].left, seqs[j].right - seqs[j].left,

@@ -52,6 +52,12 @@ int64_t orc_band_cells(const orc_seq *a, const orc_seq *b, int sh);
 double orc_aln_score_d(const orc_seq *a, const orc_seq *b, const double *mtx, int dim,
                        const orc_params *p);
 
+/* alnScoreD() with its full dispatch (fwd2d1.cc:324-337): algmode.lcl & 16 -> swgforwardD
+ * (:162-189); ends != NULL -> Fwd2d_vd (:212-322), ends[0] = diagonal offset of the path's start,
+ * ends[1] = trailing overhang (dn or -dm); else the plain (semi-)global score above. */
+double orc_aln_score_full(const orc_seq *a, const orc_seq *b, const double *mtx, int dim,
+                          const orc_params *p, int *ends);
+
 /* selfAlnScr(): reference src/aln2.cc:54-64 (many == 1) */
 double orc_self_score(const orc_seq *a, const double *mtx, int dim, const orc_params *p);
 
@@ -59,6 +65,12 @@ double orc_self_score(const orc_seq *a, const double *mtx, int dim, const orc_pa
  * reference src/aln2.cc:289-334 (else-branch :321-333), src/phyl.cc:221-251.
  * self_a/self_b are selfscr() values (phyl.cc:253-261, sumwt == 1 for single sequences). */
 double orc_score2dist(double scr, int la, int lb, double self_a, double self_b, const orc_params *p);
+
+/* alnscore2dist(), algmode.lcl != 0 branch (aln2.cc:296-320) x 100 (phyl.cc:249): exg_seq flags from
+ * lcl bits, alnScoreD with ends, denominator from the trimmed windows' self scores.  Undefined in the
+ * reference for lcl & 16 (ends is read uninitialised); do not call it so. */
+double orc_score2dist_lcl(const orc_seq *a, const orc_seq *b, const double *mtx, int dim,
+                          const orc_params *p, double *raw, int *ends_out);
 
 /* calcdist(seqs, nn, DynScr) for single sequences: reference src/phyl.cc:318-342.
  * dist[elem(i,j)], elem(i,j) = j(j-1)/2 + i for i < j (cmn.h:115); a = seq i, b = seq j.

@@ -78,6 +78,18 @@ def aln_score_d(a, b, mtx, p):
     return lib().orc_aln_score_d(C.byref(a), C.byref(b), mp, dim, C.byref(p))
 
 
+def aln_score_full(a, b, mtx, p, want_ends=False):
+    """alnScoreD with its dispatch (SWG when p.lcl & 16; Fwd2d_vd when want_ends): (score, ends|None)."""
+    L = lib()
+    L.orc_aln_score_full.restype = C.c_double
+    L.orc_aln_score_full.argtypes = [C.POINTER(OrcSeq), C.POINTER(OrcSeq), C.POINTER(C.c_double), C.c_int,
+                                     C.POINTER(OrcParams), C.POINTER(C.c_int)]
+    m, mp, dim = _mtx(mtx)
+    e = (C.c_int * 2)(0, 0)
+    s = L.orc_aln_score_full(C.byref(a), C.byref(b), mp, dim, C.byref(p), e if want_ends else None)
+    return s, ((e[0], e[1]) if want_ends else None)
+
+
 def band_cells(a, b, sh):
     return lib().orc_band_cells(C.byref(a), C.byref(b), sh)
 

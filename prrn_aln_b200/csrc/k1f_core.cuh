@@ -1,0 +1,262 @@
+// k1f_core.cuh -- floating-point form of the K1 recurrence (score-only banded affine fill): the
+// general path of alnScoreD for everything the exact-integer kernels do not take -- non-integral
+// scoring (the reference's default PAM matrices, src/simmtx.cc:282-334), discounted / free terminal
+// gaps (tgapf < 1, inex.exgl / exgr: the Fwd2d ctor src/fwd2d1.cc:57-90 and lastD :97-134) and the
+// Smith-Waterman-Gotoh score (algmode.lcl & 16: swgforwardD :162-189).
+//
+// Every value is produced by the same IEEE operation, in the same order, as Fwd2d::forwardD
+// (src/fwd2d1.cc:147-150):   ff = max(h_left - vv, ff_left) - uu ;  gg = max(h_up - vv, gg_up) - uu ;
+// h = h_diag + S ;  h = max(max(h, ff), gg)   -- only add/sub/max appear (no FMA, no re-association),
+// so float and double results are bit-identical to the reference's VTYPE arithmetic.
+// T = float (aln build) or double (prrn build, -DDVAL=1).
+//
+// Shared between the CUDA kernel (k1f_score.cu) and the host emulation (tests/host_emul/k1f_emul.cc).
+#pragma once
+#include "k1_core.cuh"
+
+template <typename T> PG_HD T k1f_neg() { return (T)-1.0e30; }     // the "-infinity" of this kernel
+
+template <typename T> PG_HD T k1f_max(T a, T b) { return a > b ? a : b; }
+
+// Per-pair description in KERNEL orientation: Q = rows, S = columns, r = n - m.
+template <typename T>
+struct K1FPair {
+    int LQ, LS, lw, up;
+    const T* topTab;    // boundary row:    H(-1, n) = topTab[n + 1]   (columns consumed before any row)
+    const T* leftTab;   // boundary column: H(m, -1) = leftTab[m + 1]
+    // lastD (fwd2d1.cc:97-134): which end-gap relaxations run, with which factor, in which order
+    int doQ, doS;       // Q exhausted (scan of the last row) / S exhausted (scan of the last column)
+    T rtgQ, rtgS;       // (VTYPE)-exact factors  rtgapf  of the two blocks
+    int qFirst;         // 1: the Q block is the reference's first block (Q is the reference's b)
+};
+
+// boundary values with the band applied
+template <typename T> PG_HD T k1f_top(const K1FPair<T>& g, int n)
+{
+    const int k = n + 1;
+    return k <= g.up ? g.topTab[k] : k1f_neg<T>();
+}
+template <typename T> PG_HD T k1f_left(const K1FPair<T>& g, int m)
+{
+    const int k = m + 1;
+    return -k >= g.lw ? g.leftTab[k] : k1f_neg<T>();
+}
+
+template <typename T, int R>
+struct K1FLane {
+    T H[R];     // H(mbase+k, n-1)
+    T E[R];     // ff of the coming column (eager): max(H(m,n-1) - vv, ff(m,n-1)) - uu
+    T hdiag;    // H(mbase-1, n-1)
+};
+
+template <typename T, int R>
+PG_HD void k1f_lane_init(K1FLane<T, R>& L, const K1FPair<T>& g, int mbase, T vv, T uu)
+{
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const T h = k1f_left(g, mbase + k);
+        L.H[k] = h;
+        L.E[k] = k1f_max(h - vv, k1f_neg<T>()) - uu;       // ff[r-1] = NEVSEL on the boundary column
+    }
+    L.hdiag = k1f_left(g, mbase - 1);
+}
+
+// One column for one lane.  sc[k] = S(q[mbase+k], s[n]);  (h_up, g_up) = H(mbase-1, n), gg(mbase-1, n).
+// Hands (H, gg) of its last row to the lane below.
+// SWG (swgforwardD, fwd2d1.cc:162-189): cells are clamped at 0 and the maximum over the in-band cells
+// is tracked; out-of-band cells are masked to -inf (rel = n - mbase - lw, span = up - lw).
+template <typename T, int R, bool SWG>
+PG_HD void k1f_lane_step(K1FLane<T, R>& L, T* sc, T vv, T uu, T h_up, T g_up, T* h_dn, T* g_dn, int rel,
+                         unsigned span, T* maxh)
+{
+    // phase 1 (independent per row): h_diag + S, consumed old H[k-1]
+    sc[0] = L.hdiag + sc[0];                                     // fwd2d1.cc:149
+#pragma unroll
+    for (int k = 1; k < R; ++k) sc[k] = L.H[k - 1] + sc[k];
+    // phase 2: the vertical chain
+    T habove = h_up, gabove = g_up;
+    T h = h_up, g = g_up;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        g = k1f_max(habove - vv, gabove) - uu;                   // :148
+        const T f = L.E[k];                                      // :147 (computed one column early)
+        h = k1f_max(k1f_max(sc[k], f), g);                       // :150
+        if (SWG) {
+            h = k1f_max(h, (T)0);                                // :179
+            h = (unsigned)(rel - k) <= span ? h : k1f_neg<T>();
+            *maxh = k1f_max(*maxh, h);                           // :180
+        }
+        L.E[k] = k1f_max(h - vv, f) - uu;
+        L.H[k] = h;
+        habove = h;
+        gabove = g;
+    }
+    L.hdiag = h_up;
+    *h_dn = h;
+    *g_dn = g;
+}
+
+// ---- lastD (fwd2d1.cc:97-134) ------------------------------------------------------------------
+// A "line" holds the values the reference's in-place hh[] has on one side of the end corner when
+// forwardD returns: line[0] = the boundary value in front of the line, line[i] = the i-th cell
+// (last column: H(i-1, LS-1), i = 1..LQ; last row: H(LQ-1, i-1), i = 1..LS); the last entry is the
+// end corner H(LQ-1, LS-1), shared by both lines (its current value travels as `corner`).
+//   ext    band extent towards this line (up for the last column, -lw for the last row)
+//   nline  number of cells on the line, nother = length of the other sequence
+//   first_block: the reference's first loop (`while (--h >= h9)`, may start from the boundary value
+//   or the hh[up+1] sentinel) or its second loop (`while (++h <= h9)`, starts from an in-band cell).
+template <typename T>
+PG_HD T k1f_lastd_scan(const T* line, int ext, int nline, int nother, bool first_block, T corner, T vv, T uu, T rtg)
+{
+    int first;
+    T run;
+    if (first_block) {
+        int s = nother - 1 - ext;
+        if (s < 0) s = 0;
+        run = ext == nother ? line[0] : k1f_neg<T>();
+        first = s + 1;
+    } else {
+        int e = ext < nother - 1 ? ext : nother - 1;
+        int s = nother - 1 - e;
+        if (s + 1 > nline) return corner;
+        run = s + 1 == nline ? corner : line[s + 1];
+        first = s + 2;
+    }
+    int cnt = 0;
+    const T open = vv + uu;
+    for (int i = first; i <= nline; ++i) {
+        T hv = i == nline ? corner : line[i];
+        ++cnt;
+        const T gpn = cnt == 1 ? open : uu;
+        run = run + (T)(gpn * rtg);
+        if (hv < run) hv = run;
+        else cnt = 0;
+        run = hv;
+    }
+    return first <= nline ? run : corner;
+}
+
+// both blocks in the reference's order; colLine / rowLine as described above
+template <typename T>
+PG_HD T k1f_lastd(const K1FPair<T>& g, const T* colLine, const T* rowLine, T corner, T vv, T uu)
+{
+    if (g.qFirst) {
+        if (g.doQ) corner = k1f_lastd_scan(rowLine, -g.lw, g.LS, g.LQ, true, corner, vv, uu, g.rtgQ);
+        if (g.doS) corner = k1f_lastd_scan(colLine, g.up, g.LQ, g.LS, false, corner, vv, uu, g.rtgS);
+    } else {
+        if (g.doS) corner = k1f_lastd_scan(colLine, g.up, g.LQ, g.LS, true, corner, vv, uu, g.rtgS);
+        if (g.doQ) corner = k1f_lastd_scan(rowLine, -g.lw, g.LS, g.LQ, false, corner, vv, uu, g.rtgQ);
+    }
+    return corner;
+}
+
+// Per-pair setup from the two sequences' flags (bit0 exgl, bit1 exgr, bit2 left != 0, bit3 right != len)
+// bnd = T[3][stride]: table 0 zeros (exgl), 1 factor 1, 2 factor tgapf (fwd2d1.cc:67-87).
+template <typename T>
+PG_HD void k1f_pair_setup(K1FPair<T>& g, int LQ, int LS, int sh, uint8_t qflags, uint8_t sflags, const T* bnd,
+                          int stride, float tgapf, bool swap)
+{
+    g.LQ = LQ; g.LS = LS;
+    k1_band(LQ, LS, sh, &g.lw, &g.up);
+    // boundary row (columns consumed first) follows the ROW sequence's left end, and vice versa
+    g.topTab = bnd + (size_t)((qflags & 1) ? 0 : (qflags & 4) ? 1 : 2) * stride;
+    g.leftTab = bnd + (size_t)((sflags & 1) ? 0 : (sflags & 4) ? 1 : 2) * stride;
+    const float rq = (qflags & 2) ? 0.f : tgapf, rs = (sflags & 2) ? 0.f : tgapf;
+    g.doQ = !(qflags & 8) && rq < 1.f;
+    g.doS = !(sflags & 8) && rs < 1.f;
+    g.rtgQ = (T)rq; g.rtgS = (T)rs;
+    g.qFirst = swap ? 1 : 0;
+}
+
+// Boundary tables (host): bnd[t * stride + k] = value of k leading residues against gaps with factor
+// t = 0: free (exgl), 1: full penalty, 2: tgapf -- accumulated exactly as the reference does
+// (gp = -vv*f; ge = -uu*f; hh[r] = gp += ge, fwd2d1.cc:70-74,80-84).
+#if !defined(__CUDA_ARCH__)
+template <typename T>
+static inline void k1f_build_tables(T* bnd, int stride, T uu, T vv, float tgapf)
+{
+    for (int t = 0; t < 3; ++t) {
+        T* tab = bnd + (size_t)t * stride;
+        const float f = t == 2 ? tgapf : 1.f;
+        T gp = (T)(-vv * f);
+        const T ge = (T)(-uu * f);
+        tab[0] = 0;
+        for (int k = 1; k < stride; ++k) tab[k] = t == 0 ? (T)0 : (gp += ge);
+    }
+}
+#endif
+
+// Host-side emulation of one warp (32 lanes x R rows, multi-pass over Q): the control flow of the
+// CUDA kernel with shuffles replaced by arrays.  mtx[q * dim + s] = score of (row residue, column residue).
+#if !defined(__CUDA_ARCH__)
+template <typename T, int R, bool SWG>
+static inline T k1f_emulate_pair(const uint8_t* q, const uint8_t* s, const K1FPair<T>& g, const T* mtx, int dim,
+                                 T vv, T uu)
+{
+    const int NT = 32;
+    const int rows_per_pass = NT * R;
+    const int LQ = g.LQ, LS = g.LS;
+    T* colLine = new T[LQ + 2];
+    T* rowLine = new T[LS + 2];
+    T* rowH = new T[LS + 1];
+    T* rowG = new T[LS + 1];
+    T result = 0, maxh = k1f_neg<T>();
+    if (LQ == 0 || LS == 0) {
+        // no cell: hh[] holds the boundary; the lines are the boundary column / row themselves
+        for (int i = 0; i <= LQ; ++i) colLine[i] = LS == 0 ? k1f_left(g, i - 1) : (i == 0 ? k1f_top(g, LS - 1) : k1f_neg<T>());
+        for (int j = 0; j <= LS; ++j) rowLine[j] = LQ == 0 ? k1f_top(g, j - 1) : (j == 0 ? k1f_left(g, LQ - 1) : k1f_neg<T>());
+        T corner = LQ == 0 ? k1f_top(g, LS - 1) : k1f_left(g, LQ - 1);
+        result = SWG ? maxh : k1f_lastd(g, colLine, rowLine, corner, vv, uu);
+        delete[] colLine; delete[] rowLine; delete[] rowH; delete[] rowG;
+        return result;
+    }
+    colLine[0] = k1f_top(g, LS - 1);
+    rowLine[0] = k1f_left(g, LQ - 1);
+    for (int pass = 0; pass * rows_per_pass < LQ; ++pass) {
+        const int pbase = pass * rows_per_pass;
+        K1FLane<T, R> L[NT];
+        T send_h[2][NT], send_g[2][NT];
+        for (int t = 0; t < NT; ++t) k1f_lane_init(L[t], g, pbase + t * R, vv, uu);
+        const int rows_here = LQ - pbase < rows_per_pass ? LQ - pbase : rows_per_pass;
+        const int lanes = (rows_here + R - 1) / R;
+        const bool last_pass = pbase + rows_here == LQ;
+        for (int step = 0; step < LS + lanes - 1; ++step) {
+            const int cur = step & 1, prv = cur ^ 1;
+            for (int t = 0; t < lanes; ++t) {
+                const int n = step - t;
+                if (n < 0 || n >= LS) continue;
+                const int mbase = pbase + t * R;
+                T h_up, g_up;
+                if (t == 0) {
+                    if (pass == 0) { h_up = k1f_top(g, n); g_up = k1f_neg<T>(); }
+                    else { h_up = rowH[n]; g_up = rowG[n]; }
+                } else { h_up = send_h[prv][t - 1]; g_up = send_g[prv][t - 1]; }
+                if (!SWG) {
+                    const int kL = n - g.lw - mbase, kU = n - g.up - 1 - mbase;
+                    if (kL >= 0 && kL < R) L[t].E[kL] = k1f_neg<T>();
+                    if (kU >= 0 && kU < R) L[t].E[kU] = k1f_neg<T>();
+                }
+                T sc[R];
+                for (int k = 0; k < R; ++k) {
+                    const int m = mbase + k;
+                    sc[k] = m < LQ ? mtx[q[m] * dim + s[n]] : (T)0;
+                }
+                T h_dn, g_dn;
+                k1f_lane_step<T, R, SWG>(L[t], sc, vv, uu, h_up, g_up, &h_dn, &g_dn, n - mbase - g.lw,
+                                         (unsigned)(g.up - g.lw), &maxh);
+                send_h[cur][t] = h_dn; send_g[cur][t] = g_dn;
+                if (t == NT - 1) { rowH[n] = h_dn; rowG[n] = g_dn; }
+                if (last_pass && t == (rows_here - 1) / R) rowLine[n + 1] = L[t].H[(rows_here - 1) % R];
+            }
+        }
+        for (int t = 0; t < lanes; ++t)
+            for (int k = 0; k < R; ++k)
+                if (pbase + t * R + k < LQ) colLine[pbase + t * R + k + 1] = L[t].H[k];
+        if (last_pass) result = L[(rows_here - 1) / R].H[(rows_here - 1) % R];
+    }
+    if (SWG) result = maxh;
+    else result = k1f_lastd(g, colLine, rowLine, result, vv, uu);
+    delete[] colLine; delete[] rowLine; delete[] rowH; delete[] rowG;
+    return result;
+}
+#endif

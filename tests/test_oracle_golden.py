@@ -14,12 +14,38 @@ def _oracle_params(O, g):
                     lcl=int(h["lcl"]), vtype=1 if h["vtype"] == "f64" else 0)
 
 
+def _exg_seq(O, e, gl, gr):
+    """Seq::exg_seq (src/seq.cc:858-863) for a single ungapped sequence: only the inex flags change."""
+    return O.seq(e, exgl=1 if gl else 0, exgr=1 if gr else 0)
+
+
 @pytest.mark.parametrize("name", golden_names("score_"))
 def test_scores_and_dist_bit_exact(oracle, name):
     g = golden(name)
     enc = [seqcode.encode_dna(s) if g["dna"] else seqcode.encode_protein(s) for s in g["seqs"]]
     p = _oracle_params(oracle, g)
-    dist, raw = oracle.calcdist([oracle.seq(e) for e in enc], np.array(g["matrix"]), p)
+    M = np.array(g["matrix"])
+    lcl = p.lcl
+    if lcl:
+        # alnScoreD's other branches: swgforwardD (lcl & 16) and Fwd2d_vd with `ends` (the driver ran
+        # exg_seq(lcl&1, lcl&2) on a and exg_seq(lcl&4, lcl&8) on b, as alnscore2dist does)
+        k = 0
+        for j in range(1, len(enc)):
+            for i in range(j):
+                if lcl & 16:
+                    a, b = oracle.seq(enc[i]), oracle.seq(enc[j])
+                else:
+                    a, b = _exg_seq(oracle, enc[i], lcl & 1, lcl & 2), _exg_seq(oracle, enc[j], lcl & 4, lcl & 8)
+                s, e = oracle.aln_score_full(a, b, M, p, want_ends="ends" in g)
+                assert s == g["scores"][k], (i, j)
+                if "ends" in g:
+                    assert list(e) == g["ends"][k], (i, j)
+                k += 1
+        if "dist" in g:
+            dist, _ = oracle.calcdist([oracle.seq(e) for e in enc], M, p)
+            assert np.array_equal(dist, np.array(g["dist"])), "calcdist (lcl) vector differs from the reference"
+        return
+    dist, raw = oracle.calcdist([oracle.seq(e) for e in enc], M, p)
     assert np.array_equal(raw, np.array(g["scores"])), "alnScoreD scores differ from the reference"
     assert np.array_equal(dist, np.array(g["dist"])), "calcdist vector differs from the reference"
 

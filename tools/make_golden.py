@@ -32,11 +32,15 @@ def score_case(name, seqs, flavour="f", dna=False, **kv):
         extra["molc"] = "n"
     sc = refio.run("scores", fa, flavour=flavour, **extra)
     mt = refio.run("matrix", fa, flavour=flavour, **extra)
-    ds = refio.run("dist", fa, flavour=flavour, **extra)
     n = len(seqs)
     scores = [sc["scores"][(i, j)] for j in range(1, n) for i in range(j)]
     rec = dict(name=name, kind="score", flavour=flavour, dna=dna, params=sc["header"], args=kv,
-               seqs=seqs, matrix=mt["matrix"].tolist(), scores=scores, dist=ds["dist"].tolist())
+               seqs=seqs, matrix=mt["matrix"].tolist(), scores=scores)
+    lcl = int(kv.get("lcl", 0))
+    if sc["ends"]:      # semi-global with end points (Fwd2d_vd): ends[2] per pair
+        rec["ends"] = [list(sc["ends"][(i, j)]) for j in range(1, n) for i in range(j)]
+    if not (lcl & 16):  # calcdist with lcl & 16 reads uninitialised `ends` in the reference (aln2.cc:296-305)
+        rec["dist"] = refio.run("dist", fa, flavour=flavour, **extra)["dist"].tolist()
     with open(os.path.join(GOLD, name + ".json"), "w") as f:
         json.dump(rec, f)
     print("wrote", name, "pairs", len(scores))
@@ -61,6 +65,19 @@ def align_case(name, seqs, flavour="f", **kv):
     with open(os.path.join(GOLD, name + ".json"), "w") as f:
         json.dump(rec, f)
     print("wrote", name, "pairs", len(pairs))
+
+
+def lcl_cases(p24, rag):
+    """algmode.lcl variants of alnScoreD: SWG score (lcl & 16) and semi-global with `ends` (Fwd2d_vd)."""
+    score_case("score_p24_lcl16", p24, lcl=16)
+    score_case("score_p24_lcl16_pam_f64", p24, flavour="d", mtx="pam", lcl=16, sh=-30)
+    score_case("score_rag_lcl16", rag, lcl=16, sh=5)
+    score_case("score_p24_lcl15", p24, lcl=15)
+    score_case("score_p24_lcl5_tgapf05", p24, lcl=5, tgapf=0.5)
+    score_case("score_p24_lcl10_pam_f32", p24, mtx="pam", lcl=10)
+    score_case("score_p24_lcl15_pam_f64", p24, flavour="d", mtx="pam", lcl=15, sh=-30)
+    score_case("score_rag_lcl15", rag, lcl=15, sh=5)
+    score_case("score_p24_tgapf03_pam_f64", p24, flavour="d", mtx="pam", tgapf=0.3)
 
 
 def sample_pair():
@@ -99,6 +116,7 @@ def main():
     long_ = gen_synth.synth_set(6, 1300, 0.1, 0.5, 31)
     score_case("score_long1300", long_)
     score_case("score_c1_ce13a", sample_pair(), sh=-50)
+    lcl_cases(p24, rag)
     # alignments with path (align2 -> alignC<DPunit> -> stdskl)
     p16 = p24[:16]
     align_case("align_p16_blosum62", p16)
@@ -117,4 +135,10 @@ def main():
 if __name__ == "__main__":
     if not refio.available("f"):
         sys.exit("oracle/_ref is not built: run `make -C oracle ref` where /root/reference exists")
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "lcl":      # only the lcl cases
+        p24_ = gen_synth.synth_set(24, 120, 0.1, 0.6, 11)
+        rag_ = [s[:k] for s, k in zip(gen_synth.synth_set(20, 300, 0.1, 0.7, 21),
+                                      [1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 300, 17, 64, 65, 31, 32, 33, 250])]
+        lcl_cases(p24_, rag_)
+    else:
+        main()
