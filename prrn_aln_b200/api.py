@@ -172,15 +172,19 @@ class Context:
             raise PgError(rc, self.L.pg_last_error(self.h).decode())
 
     # -- per-call level: batch of alnScoreD -------------------------------------------------------
-    def score_pairs(self, seqs, a_idx, b_idx, prm, mtx):
+    def score_pairs(self, seqs, a_idx, b_idx, prm, mtx, want_ends=False):
+        """Batch of alnScoreD(seqs[a], seqs[b]).  want_ends: also return the `ends` output (n x 2) of the
+        semi-global variant (Fwd2d_vd, src/fwd2d1.cc:191-322)."""
         a = np.ascontiguousarray(a_idx, dtype=np.int32)
         b = np.ascontiguousarray(b_idx, dtype=np.int32)
         m = _mtx_for(prm, mtx)
         out = np.empty(len(a), dtype=prm.ftype)
+        ends = np.zeros((len(a), 2), dtype=np.int32) if want_ends else None
         cs = seqs.c_struct()
         self._check(self.L.pg_score_pairs(self.h, C.byref(cs), a.ctypes.data, b.ctypes.data, len(a),
-                                          C.byref(prm), m.ctypes.data, m.shape[0], out.ctypes.data, None))
-        return out
+                                          C.byref(prm), m.ctypes.data, m.shape[0], out.ctypes.data,
+                                          ends.ctypes.data if want_ends else None))
+        return (out, ends) if want_ends else out
 
     # -- per-call level: batch of alignC<DPunit> ------------------------------------------------
     def align_pairs(self, seqs, a_idx, b_idx, prm, mtx):
@@ -270,15 +274,16 @@ def _ctx(device=0):
     return _DEFAULT_CTX[device]
 
 
-def alnScoreD(seqs, sm, prm=None, pairs=None, device=0):
+def alnScoreD(seqs, sm, prm=None, pairs=None, device=0, ends=False):
     """VTYPE alnScoreD(const Seq* seqs[2], const Simmtx* sm, int* ends) -- reference
     src/fwd2d1.cc:324 -- for a batch.  `seqs` is a SeqSet; pairs = [(a, b), ...] (default: the two
-    first sequences).  Returns the scores in the VTYPE of prm."""
+    first sequences).  Returns the scores in the VTYPE of prm; with ends=True also the `ends` array
+    (the reference's dispatch: prm.lcl & 16 -> Smith-Waterman-Gotoh score, ends -> Fwd2d_vd)."""
     prm = prm or Params()
     pairs = [(0, 1)] if pairs is None else pairs
     a = [p[0] for p in pairs]
     b = [p[1] for p in pairs]
-    return _ctx(device).score_pairs(seqs, a, b, prm, sm)
+    return _ctx(device).score_pairs(seqs, a, b, prm, sm, want_ends=ends)
 
 
 def stdskl(corners):

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "k1f_core.cuh"
 #include "k1p_core.cuh"
 #include "k2_core.cuh"
 #include "pg_internal.h"
@@ -60,6 +61,8 @@ extern "C" int pg_create(int device, pg_context** out)
     c->sm_count = prop.multiProcessorCount;
     c->d_items = c->d_mtx = c->d_self = c->d_rowbuf = c->d_out = c->d_pairs = c->d_dirs = c->d_trace = c->d_seqblob = c->d_planbuf = nullptr;
     c->dirs_cap = c->trace_cap = c->seqblob_cap = c->planbuf_cap = 0;
+    c->d_bnd = c->d_scratch = c->d_ends = nullptr;
+    c->bnd_cap = c->scratch_cap = c->ends_cap = 0;
     c->items_cap = c->mtx_cap = c->self_cap = c->rowbuf_cap = c->out_cap = c->pairs_cap = 0;
     c->d_counter = nullptr;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -79,6 +82,7 @@ extern "C" void pg_destroy(pg_context* c)
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_items); cudaFree(c->d_mtx); cudaFree(c->d_self); cudaFree(c->d_rowbuf);
     cudaFree(c->d_out); cudaFree(c->d_pairs); cudaFree(c->d_counter); cudaFree(c->d_dirs); cudaFree(c->d_trace); cudaFree(c->d_seqblob); cudaFree(c->d_planbuf);
+    cudaFree(c->d_bnd); cudaFree(c->d_scratch); cudaFree(c->d_ends);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -130,6 +134,112 @@ static int make_int_scoring(pg_context* c, const pg_params* prm, const void* mtx
     return PG_OK;
 }
 
+// ---- which kernel takes an alnScoreD batch ------------------------------------------------------
+// The exact-integer DPX kernels (K1 / K1P) take the global score with integral matrix and penalties,
+// tgapf == 1 and no free ends; everything else of alnScoreD's dispatch (fwd2d1.cc:324-337) goes to the
+// floating-point kernel K1F in the caller's VTYPE.  mode: 0 forwardD, 1 forwardD + lastD,
+// 2 swgforwardD, 3 Fwd2d_vd.  No path leaves the GPU.
+struct ScorePlan {
+    bool integer;       // K1 / K1P
+    int mode;           // K1F mode otherwise
+};
+
+static int plan_scoring(pg_context* c, const pg_params* prm, const void* mtx, int dim, const pg_dev_seqs* d,
+                        bool want_ends, IntScoring* sc, ScorePlan* plan)
+{
+    if (!prm || !mtx) return fail(c, PG_ERR_ARG, "params / mtx is NULL");
+    if (dim < 1 || dim > 32) return fail(c, PG_ERR_ARG, "dim must be in [1, 32]");
+    plan->integer = false;
+    if (prm->lcl & 16) { plan->mode = 2; return PG_OK; }
+    if (want_ends) { plan->mode = 3; return PG_OK; }
+    const bool lastd = d->any_exg || !(prm->alprm.tgapf == 1.0f);
+    plan->mode = lastd ? 1 : 0;
+    if (!lastd) {
+        const char* force = getenv("PG_FORCE_FLOAT");
+        if (!(force && force[0] == '1')) {
+            pg_params p0 = *prm;
+            p0.lcl = 0;
+            std::string keep = c->err;
+            if (make_int_scoring(c, &p0, mtx, dim, d->present, sc) == PG_OK) plan->integer = true;
+            else c->err = keep;     // not integral: K1F takes it
+        }
+    }
+    return PG_OK;
+}
+
+// ---- K1F staging: matrix in VTYPE, boundary tables, per-warp scratch, launch ----------------------
+static int k1f_run(pg_context* c, cudaStream_t st, pg_dev_seqs* d, const pg_params* prm, const void* mtx, int dim,
+                   int mode, int epilogue, const std::vector<PgItem>& items, bool multipass, const int32_t* d_pair_s,
+                   const int64_t* d_pair_out, int64_t k0, int64_t k1, int exg_override, void* d_out, int32_t* d_out_ends,
+                   int32_t* n_launches)
+{
+    int rc;
+    const int vt = prm->vtype ? 1 : 0;
+    const size_t esz = vt ? sizeof(double) : sizeof(float);
+    K1FArgs a;
+    memset(&a, 0, sizeof(a));
+    a.seqs = d->v;
+    // fwd2d1.cc:62-63: uu = (VTYPE)(alprm.u * alprm.scale) -- float products
+    const float fu = prm->alprm.u * prm->alprm.scale, fv = prm->alprm.v * prm->alprm.scale;
+    a.uu = (double)fu;
+    a.vv = (double)fv;
+    a.tgapf = prm->alprm.tgapf;
+    // score matrix as the caller's VTYPE
+    if ((rc = ensure_cap(c, &c->d_mtx, &c->mtx_cap, esz * (size_t)dim * dim))) return rc;
+    PG_CUDA(c, cudaMemcpyAsync(c->d_mtx, mtx, esz * (size_t)dim * dim, cudaMemcpyHostToDevice, st));
+    // boundary tables (fwd2d1.cc:67-87), accumulated in VTYPE as the reference does
+    const int stride = d->max_wlen + 2;
+    std::vector<unsigned char> bnd(3 * (size_t)stride * esz);
+    if (vt) k1f_build_tables<double>((double*)bnd.data(), stride, (double)fu, (double)fv, prm->alprm.tgapf);
+    else k1f_build_tables<float>((float*)bnd.data(), stride, fu, fv, prm->alprm.tgapf);
+    if ((rc = ensure_cap(c, &c->d_bnd, &c->bnd_cap, bnd.size()))) return rc;
+    PG_CUDA(c, cudaMemcpyAsync(c->d_bnd, bnd.data(), bnd.size(), cudaMemcpyHostToDevice, st));
+    if ((rc = ensure_cap(c, &c->d_items, &c->items_cap, sizeof(PgItem) * std::max<size_t>(items.size(), 1)))) return rc;
+    if (!items.empty())
+        PG_CUDA(c, cudaMemcpyAsync(c->d_items, items.data(), sizeof(PgItem) * items.size(), cudaMemcpyHostToDevice, st));
+    // per-warp scratch
+    const bool lines = mode == 1 || mode == 3, vd = mode == 3;
+    auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t n = (size_t)d->max_wlen + 4;
+    size_t off = 0;
+    a.off_rowv = (int32_t)off; off += multipass ? al16(2 * n * esz) : 0;
+    a.off_rowr = (int32_t)off; off += (multipass && vd) ? al16(2 * n * 4) : 0;
+    a.off_col = (int32_t)off; off += lines ? al16(n * esz) : 0;
+    a.off_row = (int32_t)off; off += lines ? al16(n * esz) : 0;
+    a.off_colr = (int32_t)off; off += vd ? al16(n * 4) : 0;
+    a.off_rowr2 = (int32_t)off; off += vd ? al16(n * 4) : 0;
+    a.off_misc = (int32_t)off; off += 16;
+    if (off > 0x7fffffff) return fail(c, PG_ERR_RANGE, "sequence too long for the score kernel's scratch layout");
+    const int grid = k1f_grid_blocks(c->sm_count, vt, mode);
+    a.scratch_stride = (int64_t)al16(off);
+    if ((rc = ensure_cap(c, &c->d_scratch, &c->scratch_cap, (size_t)a.scratch_stride * grid * k1f_warps_per_block()))) return rc;
+    a.scratch = c->d_scratch;
+    int launches = 1;
+    if (epilogue == 1) {
+        if ((rc = ensure_cap(c, &c->d_self, &c->self_cap, esz * std::max<size_t>(d->v.nseq, 1)))) return rc;
+        PG_CUDA(c, k1f_self_launch(d->v, c->d_mtx, dim, vt, c->d_self, st));
+        a.self = c->d_self;
+        ++launches;
+    }
+    PG_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int32_t), st));
+    a.items = (const PgItem*)c->d_items;
+    a.nitems = (int32_t)items.size();
+    a.counter = c->d_counter;
+    a.pair_s = d_pair_s;
+    a.pair_out = d_pair_out;
+    a.k_begin = k0; a.k_end = k1;
+    a.mtx = c->d_mtx; a.dim = dim;
+    a.bnd = c->d_bnd; a.bnd_stride = stride;
+    a.sh = prm->alprm.sh;
+    a.mode = mode; a.vtype = vt; a.epilogue = epilogue;
+    a.u_f32 = prm->alprm.u;
+    a.out = d_out; a.out_ends = d_out_ends;
+    a.exg_override = exg_override;
+    PG_CUDA(c, k1f_launch(a, c->sm_count, st));
+    if (n_launches) *n_launches = launches;
+    return PG_OK;
+}
+
 // ---- sequences --------------------------------------------------------------------------------
 static int seqs_upload_impl(pg_context* c, const pg_seqs* s, pg_dev_seqs** out, bool in_ctx);
 
@@ -159,7 +269,6 @@ static int seqs_upload_impl(pg_context* c, const pg_seqs* s, pg_dev_seqs** out, 
         int l = s->left ? s->left[i] : 0, r = s->right ? s->right[i] : s->lens[i];
         if (l < 0 || r > s->lens[i] || l > r) return fail(c, PG_ERR_ARG, "window outside the sequence");
         uint8_t ex = s->exg ? s->exg[i] : 0;
-        if (ex & 3) return fail(c, PG_ERR_UNSUPPORTED, "inex.exgl / exgr (free end gaps) is not built yet");
         left[i] = l;
         wlen[i] = r - l;
         flags[i] = (uint8_t)((ex & 3) | (l ? 4 : 0) | (r != s->lens[i] ? 8 : 0));
@@ -202,6 +311,8 @@ static int seqs_upload_impl(pg_context* c, const pg_seqs* s, pg_dev_seqs** out, 
     d->h_wlen = wlen;
     d->max_wlen = maxw;
     d->min_wlen = n ? *std::min_element(wlen.begin(), wlen.end()) : 0;
+    d->any_exg = false;
+    for (int i = 0; i < n; ++i) d->any_exg = d->any_exg || (flags[i] & 3);
     d->plan_k0 = d->plan_k1 = -1;
     d->d_plan = nullptr;
     d->plan_nitems = 0;
@@ -274,6 +385,38 @@ static void build_calcdist_items(const pg_dev_seqs* d, int64_t k0, int64_t k1, i
         int64_t ca = (int64_t)d->h_wlen[a.q] * (a.sub_end - a.sub_begin);
         int64_t cb = (int64_t)d->h_wlen[b.q] * (b.sub_end - b.sub_begin);
         return ca > cb;
+    });
+}
+
+// K1F orientation: rows = a = the smaller index i, subjects j > i restricted to the rows [jlo, jhi] of
+// the condensed range (partial first / last rows are trimmed by the kernel's slot test).
+static void build_calcdist_items_rows_a(const pg_dev_seqs* d, int64_t k0, int64_t k1, int grid_blocks, int rpp,
+                                        std::vector<PgItem>* items, bool* multipass)
+{
+    items->clear();
+    *multipass = false;
+    if (k1 <= k0) return;
+    const int NWv = k1f_warps_per_block();
+    const int jlo = row_of_k(k0), jhi = row_of_k(k1 - 1);
+    int64_t ch = ((k1 - k0) + (int64_t)16 * grid_blocks - 1) / ((int64_t)16 * grid_blocks);
+    ch = std::max<int64_t>(NWv, std::min<int64_t>(ch, 32 * NWv));
+    ch = (ch + NWv - 1) / NWv * NWv;
+    for (int i = 0; i < jhi; ++i) {
+        const int j0 = std::max(i + 1, jlo), j1 = jhi + 1;
+        const bool mp = d->h_wlen[i] > rpp;
+        if (mp) *multipass = true;
+        const int64_t c = mp ? NWv : ch;
+        for (int64_t j = j0; j < j1; j += c) {
+            PgItem it;
+            it.q = i;
+            it.sub_begin = (int32_t)j;
+            it.sub_end = (int32_t)std::min<int64_t>(j + c, j1);
+            it.pad = 0;
+            items->push_back(it);
+        }
+    }
+    std::stable_sort(items->begin(), items->end(), [&](const PgItem& a, const PgItem& b) {
+        return (int64_t)d->h_wlen[a.q] * (a.sub_end - a.sub_begin) > (int64_t)d->h_wlen[b.q] * (b.sub_end - b.sub_begin);
     });
 }
 
@@ -393,11 +536,24 @@ extern "C" int pg_calcdist_dev(pg_context* c, pg_dev_seqs* d, const pg_params* p
     if (!d_out_dist) return fail(c, PG_ERR_ARG, "pg_calcdist_dev: output is NULL");
     PG_CUDA(c, cudaSetDevice(c->device));
     if (d->max_code >= dim) return fail(c, PG_ERR_ARG, "residue code outside the substitution matrix");
+    if (prm->lcl & 16)
+        return fail(c, PG_ERR_UNSUPPORTED, "calcdist with algmode.lcl & 16: the reference reads `ends` uninitialised "
+                                           "there (aln2.cc:296-305), there is no defined result to reproduce");
     IntScoring sc;
-    int rc = make_int_scoring(c, prm, mtx, dim, d->present, &sc);
+    ScorePlan plan;
+    int rc = plan_scoring(c, prm, mtx, dim, d, prm->lcl != 0, &sc, &plan);
     if (rc) return rc;
     // everything (staging copies, self-score kernel, fill kernel) is ordered on one stream
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (!plan.integer) {
+        std::vector<PgItem> fitems;
+        bool fmp = false;
+        const int vt = prm->vtype ? 1 : 0;
+        build_calcdist_items_rows_a(d, k_begin, k_end, k1f_grid_blocks(c->sm_count, vt, plan.mode),
+                                    k1f_rows_per_pass(vt, plan.mode), &fitems, &fmp);
+        return k1f_run(c, st, d, prm, mtx, dim, plan.mode, prm->lcl ? 2 : 1, fitems, fmp, nullptr, nullptr, k_begin, k_end,
+                       prm->lcl ? (prm->lcl & 15) : -1, d_out_dist, nullptr, n_launches);
+    }
     const int grid = c->sm_count * k1_blocks_per_sm();
     // ---- packed int16x2 path when every value provably fits 16 bits (k1p_fits)
     {
@@ -524,7 +680,6 @@ extern "C" int pg_score_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
     if (!c) return PG_ERR_ARG;
     if (!s || !prm || !mtx || npairs < 0 || (npairs && (!a_idx || !b_idx || !out_scores)))
         return fail(c, PG_ERR_ARG, "pg_score_pairs: NULL / bad argument");
-    if (out_ends) return fail(c, PG_ERR_UNSUPPORTED, "`ends` output (Fwd2d_vd, fwd2d1.cc:191-322) is not built yet");
     if (npairs == 0) return PG_OK;
     if (npairs > 0x7fffffff) return fail(c, PG_ERR_ARG, "pg_score_pairs: too many pairs in one call");
     if (dim < 1 || dim > 32) return fail(c, PG_ERR_ARG, "dim must be in [1, 32]");
@@ -536,7 +691,8 @@ extern "C" int pg_score_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
     if ((rc = seqs_upload_impl(c, s, &d, true))) return rc;
     if (d->max_code >= dim) { pg_seqs_free(c, d); return fail(c, PG_ERR_ARG, "residue code outside the substitution matrix"); }
     IntScoring sc;
-    if ((rc = make_int_scoring(c, prm, mtx, dim, d->present, &sc))) { pg_seqs_free(c, d); return rc; }
+    ScorePlan plan;
+    if ((rc = plan_scoring(c, prm, mtx, dim, d, out_ends != nullptr, &sc, &plan))) { pg_seqs_free(c, d); return rc; }
     // rows = a (query of the work item), columns = b; sort pairs by a so that one CTA reuses the profile
     std::vector<int32_t> order(npairs);
     std::iota(order.begin(), order.end(), 0);
@@ -544,8 +700,9 @@ extern "C" int pg_score_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
     std::vector<int32_t> pair_s(npairs);
     std::vector<int64_t> pair_out(npairs);
     for (int64_t p = 0; p < npairs; ++p) { pair_s[p] = b_idx[order[p]]; pair_out[p] = order[p]; }
-    const int grid = c->sm_count * k1_blocks_per_sm();
-    const int NWv = k1_warps_per_block(), rpp = k1_rows_per_pass();
+    const int vt = prm->vtype ? 1 : 0;
+    const int grid = plan.integer ? c->sm_count * k1_blocks_per_sm() : k1f_grid_blocks(c->sm_count, vt, plan.mode);
+    const int NWv = k1_warps_per_block(), rpp = plan.integer ? k1_rows_per_pass() : k1f_rows_per_pass(vt, plan.mode);
     int64_t ch = (npairs + (int64_t)16 * grid - 1) / ((int64_t)16 * grid);
     ch = std::max<int64_t>(NWv, std::min<int64_t>(ch, 32 * NWv));
     ch = (ch + NWv - 1) / NWv * NWv;
@@ -568,11 +725,36 @@ extern "C" int pg_score_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
     std::stable_sort(items.begin(), items.end(), [&](const PgItem& x, const PgItem& y) {
         return (int64_t)d->h_wlen[x.q] * (x.sub_end - x.sub_begin) > (int64_t)d->h_wlen[y.q] * (y.sub_end - y.sub_begin);
     });
+    const size_t esz = prm->vtype ? sizeof(double) : sizeof(float);
+    if (!plan.integer) {
+        // floating-point / semi-global / local kernel, explicit pairs
+        cudaError_t e = cudaSuccess;
+        rc = ensure_cap(c, &c->d_pairs, &c->pairs_cap, (sizeof(int32_t) + sizeof(int64_t)) * (size_t)npairs + 64);
+        if (!rc) rc = ensure_cap(c, &c->d_out, &c->out_cap, esz * (size_t)npairs);
+        if (!rc && out_ends) rc = ensure_cap(c, &c->d_ends, &c->ends_cap, 2 * sizeof(int32_t) * (size_t)npairs);
+        if (!rc) {
+            int64_t* d_po = (int64_t*)c->d_pairs;
+            int32_t* d_ps = (int32_t*)((char*)c->d_pairs + sizeof(int64_t) * (size_t)npairs);
+            e = cudaMemcpyAsync(d_po, pair_out.data(), sizeof(int64_t) * npairs, cudaMemcpyHostToDevice, c->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_ps, pair_s.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, c->stream);
+            if (e != cudaSuccess) rc = fail(c, PG_ERR_CUDA, std::string("pg_score_pairs: ") + cudaGetErrorString(e));
+            if (!rc) rc = k1f_run(c, c->stream, d, prm, mtx, dim, plan.mode, 0, items, multipass, d_ps, d_po, 0, 0, -1,
+                                  c->d_out, out_ends ? (int32_t*)c->d_ends : nullptr, nullptr);
+            if (!rc) {
+                e = cudaMemcpyAsync(out_scores, c->d_out, esz * npairs, cudaMemcpyDeviceToHost, c->stream);
+                if (e == cudaSuccess && out_ends)
+                    e = cudaMemcpyAsync(out_ends, c->d_ends, 2 * sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, c->stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+                if (e != cudaSuccess) rc = fail(c, PG_ERR_CUDA, std::string("pg_score_pairs: ") + cudaGetErrorString(e));
+            }
+        }
+        pg_seqs_free(c, d);
+        return rc;
+    }
     K1Args a;
     memset(&a, 0, sizeof(a));
     a.seqs = d->v;
     cudaError_t e = cudaSuccess;
-    const size_t esz = prm->vtype ? sizeof(double) : sizeof(float);
     rc = stage_common(c, c->stream, sc, dim, items, multipass, grid, d->max_wlen, &a);
     if (!rc) rc = ensure_cap(c, &c->d_pairs, &c->pairs_cap, (sizeof(int32_t) + sizeof(int64_t)) * (size_t)npairs + 64);
     if (!rc) rc = ensure_cap(c, &c->d_out, &c->out_cap, esz * (size_t)npairs);

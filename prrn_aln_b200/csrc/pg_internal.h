@@ -83,6 +83,35 @@ struct K1PArgs {
     int64_t rowbuf_stride;
 };
 
+// floating-point / all-modes score kernel (k1f_score.cu); orientation rows = a, columns = b
+struct K1FArgs {
+    PgDevSeqs seqs;
+    const PgItem* items;        // q = a (rows); implicit mode: subjects are sequence indices j > q
+    int32_t nitems;
+    int32_t* counter;
+    const int32_t* pair_s;      // explicit mode: subject (b) per sorted pair; nullptr => implicit
+    const int64_t* pair_out;    // explicit mode: output slot per sorted pair
+    int64_t k_begin, k_end;     // implicit mode: slot = elem(q, j) - k_begin, written if inside the range
+    const void* mtx;            // VTYPE[dim * dim], mtx[a][b]
+    int32_t dim;
+    const void* bnd;            // VTYPE[3][bnd_stride] boundary tables (k1f_build_tables)
+    int32_t bnd_stride;
+    double uu, vv;              // (VTYPE)(alprm.u * scale), (VTYPE)(alprm.v * scale)  (fwd2d1.cc:62-63)
+    float tgapf;
+    int32_t sh;
+    int32_t mode;               // 0 forwardD, 1 forwardD + lastD, 2 swgforwardD, 3 Fwd2d_vd (ends)
+    int32_t vtype;              // 0 float, 1 double
+    int32_t epilogue;           // 0 score, 1 distance (global branch), 2 distance (lcl branch; mode 3)
+    float u_f32;
+    const void* self;           // VTYPE[nseq] self scores (epilogue 1)
+    void* out;                  // VTYPE / FTYPE per slot
+    int32_t* out_ends;          // mode 3: ends[2] per slot (nullable)
+    void* scratch;              // per-warp scratch: multi-pass rows, lastD lines
+    int64_t scratch_stride;     // bytes per warp
+    int32_t off_rowv, off_rowr, off_col, off_row, off_colr, off_rowr2, off_misc;
+    int32_t exg_override;       // -1: inex flags from the sequences; else bits 0-1 = a's exgl/exgr, 2-3 = b's
+};
+
 struct K2Rec;
 
 // arguments of the alignment-with-path kernels (k2_align.cu); pairs are sorted by query
@@ -116,6 +145,7 @@ struct pg_dev_seqs {
     int32_t max_code;           // largest residue code inside the windows
     uint8_t present[256];       // which residue codes occur inside the windows
     int32_t min_wlen;
+    bool any_exg;               // some sequence carries inex.exgl / exgr
     // cached packed plan of the last calcdist range (schedule only, no results)
     int64_t plan_k0, plan_k1;
     void* d_plan;               // PgItem2[nitems] | subs[nsubs]
@@ -142,6 +172,9 @@ struct pg_context {
     void* d_seqblob; size_t seqblob_cap;
     void* d_planbuf; size_t planbuf_cap;
     void* d_trace; size_t trace_cap;
+    void* d_bnd; size_t bnd_cap;
+    void* d_scratch; size_t scratch_cap;
+    void* d_ends; size_t ends_cap;
     int32_t* d_counter;
 };
 
@@ -157,6 +190,12 @@ int k1p_rows_per_pass();
 int k1p_pick_rows(int lq);
 int k1p_warps_per_block();
 int k1p_blocks_per_sm();
+// k1f_score.cu
+cudaError_t k1f_launch(const K1FArgs& a, int sm_count, cudaStream_t st);
+cudaError_t k1f_self_launch(const PgDevSeqs& s, const void* mtx, int dim, int vtype, void* self, cudaStream_t st);
+int k1f_warps_per_block();
+int k1f_rows_per_pass(int vtype, int mode);
+int k1f_grid_blocks(int sm_count, int vtype, int mode);
 // k2_align.cu
 cudaError_t k2_fill_launch(const K2Args& a, int grid_blocks, cudaStream_t st);
 cudaError_t k2_trace_launch(const K2Args& a, int npairs, cudaStream_t st);
