@@ -93,6 +93,38 @@ int orc_align_ngp(const orc_seq *a, const orc_seq *b, const double *mtx, int dim
 /* stdskl(): reference src/gaps.cc:139-175.  skl[0].n = count; normalises in place into out
  * (capacity 2*count+2); returns the new count. */
 int orc_stdskl(const orc_skl *skl, orc_skl *out);
+
+/* ---- group-to-group alignment with path (oracle_grp.c) ----------------------------------------- */
+typedef struct { int32_t glen; double freq; int32_t nres; } orc_gfreq;     /* GFREQ, gfreq.h:25 */
+
+/* One group (mSeq) as Fwd2c reads it through mSeqItr after PwdM's staging, for the columns
+ * left-1 .. right-1 (npos = right - left + 1 entries, entry x <-> sequence position left-1+x). */
+typedef struct {
+    int32_t many, len, left, right;
+    int32_t nelm, felm, hetero, nils;       /* mSeq::nelm / felm, Gfq::hetero, inex.nils */
+    const double *cfq, *dfq, *efq;          /* SeqThk per column (mseq.h:70-74) */
+    const uint8_t *res;                     /* [npos][many] residue codes */
+    const double *vss;                      /* [npos][nelm] frequency + profile vector, or NULL */
+    const double *weight;                   /* [many] sequence weights, or NULL */
+    const orc_gfreq *gpool;                 /* gap-profile lists, each terminated by glen < 0 */
+    const int32_t *sfq, *tfq, *rfq;         /* [npos] offsets into gpool (-1: none), or NULL */
+} orc_group;
+
+typedef struct {
+    int32_t alnmode;            /* ALN_MODE (aln.h:71-76): 6 NGP_ALB, 7 HLF_ALB, 8 RHF_ALB, 9 GPF_ALB */
+    int32_t a_mode, b_mode;     /* 0 single, 1 group of residues, 2 profile (maln2.cc:283-284) */
+    int32_t Noll, codonk1, sh;
+    int32_t vtype, dxd;         /* VTYPE flavour; DvsP == DxD (sim33_n) */
+    double u;                   /* alnprm.u */
+    double Weighted_GOP, Basic_GOP;                 /* PwdM::resetuab (maln2.cc:227-243) */
+    double BasicGOP, BasicGEP, LongGOP, LongGEP;    /* PwdB::PwdB (aln2.cc:97-117) */
+} orc_gparams;
+
+/* alignC<DPunit | DPunit_hf | DPunit_pf>(seqs, pwd, &scr): corner list in Vmf back-walk order
+ * (out[0].n = count), *score = DP score, *cells = cells visited.  Returns the count or -1. */
+int orc_align_groups(const orc_group *a, const orc_group *b, const double *mtx, int dim, const orc_gparams *p,
+                     double *score, orc_skl *out, int cap, int64_t *cells);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,3 +137,90 @@ def align_ngp(a, b, mtx, p, std=True):
         cnt = L.orc_stdskl(out, out2)
         out = out2
     return scr.value, [(out[i].m, out[i].n) for i in range(1, cnt + 1)]
+
+
+# ---- group-to-group alignment (oracle_grp.c) ----------------------------------------------------
+class OrcGfreq(C.Structure):
+    _fields_ = [("glen", C.c_int32), ("freq", C.c_double), ("nres", C.c_int32)]
+
+
+class OrcGroup(C.Structure):
+    _fields_ = [("many", C.c_int32), ("len", C.c_int32), ("left", C.c_int32), ("right", C.c_int32),
+                ("nelm", C.c_int32), ("felm", C.c_int32), ("hetero", C.c_int32), ("nils", C.c_int32),
+                ("cfq", C.c_void_p), ("dfq", C.c_void_p), ("efq", C.c_void_p), ("res", C.c_void_p),
+                ("vss", C.c_void_p), ("weight", C.c_void_p), ("gpool", C.c_void_p),
+                ("sfq", C.c_void_p), ("tfq", C.c_void_p), ("rfq", C.c_void_p)]
+
+
+class OrcGparams(C.Structure):
+    _fields_ = [("alnmode", C.c_int32), ("a_mode", C.c_int32), ("b_mode", C.c_int32), ("Noll", C.c_int32),
+                ("codonk1", C.c_int32), ("sh", C.c_int32), ("vtype", C.c_int32), ("dxd", C.c_int32),
+                ("u", C.c_double), ("Weighted_GOP", C.c_double), ("Basic_GOP", C.c_double),
+                ("BasicGOP", C.c_double), ("BasicGEP", C.c_double), ("LongGOP", C.c_double), ("LongGEP", C.c_double)]
+
+
+def group_arrays(g):
+    """Flatten one parsed `galign` group (tools/refio.parse_galign) into the arrays orc_group / pg_group take."""
+    npos = len(g["pos"])
+    out = dict(many=g["many"], len=g["len"], left=g["left"], right=g["right"], nelm=g["nelm"], felm=g["felm"],
+               hetero=g["hetero"], nils=g["nils"])
+    out["cfq"] = np.array(g["cfq"], np.float64)
+    out["dfq"] = np.array(g["dfq"], np.float64)
+    out["efq"] = np.array(g["efq"], np.float64)
+    out["res"] = np.ascontiguousarray(np.array(g["res"], np.uint8).reshape(npos, g["many"]))
+    out["vss"] = np.ascontiguousarray(np.array(g["vss"], np.float64)) if g["nelm"] and len(g["vss"][0]) else None
+    out["weight"] = np.array(g["weight"], np.float64) if g["weight"] else None
+    pool = []
+    offs = {}
+    for tag in ("sfq", "tfq", "rfq"):
+        o = np.full(npos, -1, np.int32)
+        for x, lst in enumerate(g[tag]):
+            if lst is None:
+                continue
+            o[x] = len(pool)
+            pool.extend(lst)
+            pool.append([-1, 0.0, 0])
+        offs[tag] = o
+    if not pool:
+        pool = [[-1, 0.0, 0]]
+    out["gpool"] = np.array([(int(a), float(b), int(c)) for a, b, c in pool],
+                            dtype=np.dtype([("glen", np.int32), ("freq", np.float64), ("nres", np.int32)], align=True))
+    out.update(offs)
+    return out
+
+
+def _orc_group(A):
+    def p(x):
+        return None if x is None else x.ctypes.data
+    g = OrcGroup(A["many"], A["len"], A["left"], A["right"], A["nelm"], A["felm"], A["hetero"], A["nils"],
+                 p(A["cfq"]), p(A["dfq"]), p(A["efq"]), p(A["res"]), p(A["vss"]), p(A["weight"]), p(A["gpool"]),
+                 p(A["sfq"]), p(A["tfq"]), p(A["rfq"]))
+    g._keep = A
+    return g
+
+
+def gparams_from_dump(d, sh=None):
+    h, pm, pc = d["header"], d["pwdm"], d["pwdc"]
+    return OrcGparams(pm["alnmode"], pm["a_mode"], pm["b_mode"], pm["Noll"], pm["codonk1"],
+                      int(h["sh"]) if sh is None else sh, 1 if h["vtype"] == "f64" else 0, 1 if pm["DvsP"] == 0 else 0,
+                      float(np.float32(float(h["u"]))), -float(np.float32(float(h["v"]))), pc["vgop1"],
+                      pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
+
+
+def align_groups(A, B, mtx, gp):
+    """alignC<recd_t> restatement on staged groups: (score, raw corner list, cells)."""
+    L = lib()
+    L.orc_align_groups.restype = C.c_int
+    L.orc_align_groups.argtypes = [C.POINTER(OrcGroup), C.POINTER(OrcGroup), C.POINTER(C.c_double), C.c_int,
+                                   C.POINTER(OrcGparams), C.POINTER(C.c_double), C.POINTER(OrcSkl), C.c_int,
+                                   C.POINTER(C.c_int64)]
+    m, mp, dim = _mtx(mtx)
+    ga, gb = _orc_group(A), _orc_group(B)
+    cap = 2 * (A["len"] + B["len"]) + 16
+    out = (OrcSkl * cap)()
+    scr = C.c_double(0)
+    cells = C.c_int64(0)
+    cnt = L.orc_align_groups(C.byref(ga), C.byref(gb), mp, dim, C.byref(gp), C.byref(scr), out, cap, C.byref(cells))
+    if cnt < 0:
+        raise RuntimeError("corner list overflow")
+    return scr.value, [(out[i].m, out[i].n) for i in range(1, cnt + 1)], cells.value

@@ -8,6 +8,9 @@
 //   dist     : calcdist(mSeq**, nn, DynScr)                             reference src/phyl.cc:318
 //   align    : align2(mSeq*[2], PwdM*, VTYPE*, Gsinfo*)                 reference src/maln2.cc:1875
 //   matrix   : dump of Simmtx::mtx as the reference built it            reference src/simmtx.cc:282-445
+//   galign   : two GROUPS (MSA files): PwdM staging + alignC<recd_t> + align2; dumps what the DP
+//              reads per column (thickness, profile vector, residues, gap-profile lists) so that the
+//              oracle restatement and the CUDA kernel can be fed the reference's own staged inputs
 //
 // It is used (a) to freeze golden vectors under tests/golden/ (tools/make_golden.py), (b) to pin the
 // C restatement in oracle/oracle.c, (c) as bench.py's cpu_baseline "reference" leg (dist/scores timing).
@@ -25,6 +28,7 @@
 #include "phyl.h"
 #include "consreg.h"
 #include "fspscore.h"
+#include "fwd2c.h"
 #include <sys/time.h>
 #include <string>
 #include <vector>
@@ -64,6 +68,42 @@ static std::vector<mSeq*> read_all(const char* fn)
 
 static void print_vt(double x) { printf("%.17g", x); }
 
+static void dump_gfq(const char* tag, GFREQ** pp)
+{
+	if (!pp || !*pp) { printf(" %s -1", tag); return; }
+	int	n = 0;
+	for (const GFREQ* g = *pp; neogfq(g); ++g) ++n;
+	printf(" %s %d", tag, n);
+	for (const GFREQ* g = *pp; neogfq(g); ++g) {
+	    printf(" %d ", g->glen); print_vt(g->freq); printf(" %d", g->nres);
+	}
+}
+
+// everything Fwd2c reads from one group through mSeqItr, position by position
+static void dump_group(int idx, mSeq* sd)
+{
+	printf("group %d many %d len %d left %d right %d nelm %d felm %d vect %d prof %d dels %d nils %d sngl %d exgl %d exgr %d hetero %d sumwt ",
+	    idx, sd->many, sd->len, sd->left, sd->right, sd->nelm, sd->felm, (int) sd->inex.vect, (int) sd->inex.prof,
+	    (int) sd->inex.dels, (int) sd->inex.nils, (int) sd->inex.sngl, (int) sd->inex.exgl, (int) sd->inex.exgr,
+	    sd->gfq? sd->gfq->hetero: -1);
+	print_vt(sd->sumwt); putchar('\n');
+	printf("weight %d", sd->weight? sd->many: 0);
+	if (sd->weight) for (int i = 0; i < sd->many; ++i) { putchar(' '); print_vt(sd->weight[i]); }
+	putchar('\n');
+	for (int p = sd->left - 1; p < sd->right; ++p) {
+	    mSeqItr	it(sd, p);
+	    printf("pos %d dns", p);
+	    if (it.dns) { putchar(' '); print_vt(it.dns->cfq); putchar(' '); print_vt(it.dns->dfq); putchar(' '); print_vt(it.dns->efq); }
+	    else printf(" nan nan nan");
+	    printf(" res");
+	    for (int i = 0; i < sd->many; ++i) printf(" %d", (p >= -1 && p <= sd->len)? it.res[i]: 0);
+	    printf(" vss %d", it.vss? sd->nelm: 0);
+	    if (it.vss) for (int i = 0; i < sd->nelm; ++i) { putchar(' '); print_vt(it.vss[i]); }
+	    dump_gfq("sfq", it.sfq); dump_gfq("tfq", it.tfq); dump_gfq("rfq", it.rfq);
+	    putchar('\n');
+	}
+}
+
 int main(int argc, const char** argv)
 {
 	if (argc < 3) {
@@ -95,6 +135,88 @@ int main(int argc, const char** argv)
 	thread_num = atoi(kv(argc, argv, "threads", "0"));
 	int	rep = atoi(kv(argc, argv, "rep", "1"));
 	if (strcmp(mtxname, "pam")) mdm_file[0] = mtxname;
+
+	if (cmd == "galign") {		// argv[2] = group A (MSA file), fb=<group B>
+	    const char* fb = kv(argc, argv, "fb", 0);
+	    if (!fb) fatal("galign needs fb=<file>\n");
+	    mSeq*	sq[2] = {new mSeq(), new mSeq()};
+	    FILE*	fd = fopen(argv[2], "r");
+	    if (!fd || !sq[0]->fgetseq(fd)) fatal("cannot read %s\n", argv[2]);
+	    fclose(fd);
+	    fd = fopen(fb, "r");
+	    if (!fd || !sq[1]->fgetseq(fd)) fatal("cannot read %s\n", fb);
+	    fclose(fd);
+	    if (atoi(kv(argc, argv, "wt", "0"))) {	// deterministic, unequal sequence weights (sum = many)
+		for (int g = 0; g < 2; ++g) {
+		    int	nn = sq[g]->many;
+		    if (nn < 2) continue;
+		    sq[g]->weight = new FTYPE[nn];
+		    FTYPE	tot = 0;
+		    for (int i = 0; i < nn; ++i) tot += sq[g]->weight[i] = 0.5 + ((i * 37 + 11 * g) % 10) / 8.;
+		    for (int i = 0; i < nn; ++i) sq[g]->weight[i] *= nn / tot;
+		}
+	    }
+	    prePwd(sq[0]->inex.molc);
+	    Simmtx*	sm = getSimmtx(0);
+	    printf("#ref_driver cmd=galign vtype=%s u=%g v=%g u0=%g u1=%g k1=%d ls=%d sh=%d tgapf=%g scale=%g gamma=%g lcl=%d\n",
+		sizeof(VTYPE) == 8? "f64": "f32", alprm.u, alprm.v, alprm.u0, alprm.u1, alprm.k1, alprm.ls, alprm.sh,
+		alprm.tgapf, alprm.scale, alprm.gamma, (int) algmode.lcl);
+	    PwdM*	pwd = new PwdM(sq);
+	    printf("pwdm alnmode %d swp %d a_mode %d b_mode %d an %d bn %d Noll %d codonk1 %d DvsP %d\n", pwd->alnmode,
+		(int) pwd->swp, (int) pwd->a_mode, (int) pwd->b_mode, pwd->an, pwd->bn, pwd->Noll, pwd->codonk1, pwd->DvsP);
+	    printf("pwdc Vab "); print_vt(pwd->Vab);
+	    printf(" BasicGOP "); print_vt(pwd->BasicGOP); printf(" BasicGEP "); print_vt(pwd->BasicGEP);
+	    printf(" LongGOP "); print_vt(pwd->LongGOP); printf(" LongGEP "); print_vt(pwd->LongGEP);
+	    printf(" vgop1 "); print_vt(pwd->vgop(1)); printf(" wgop1 "); print_vt(pwd->wgop(1));
+	    printf(" u "); print_vt(pwd->alnprm.u); printf(" v "); print_vt(pwd->alnprm.v); putchar('\n');
+	    printf("dim %d\n", sm->dim);
+	    for (int i = 0; i < sm->dim; ++i) {
+		for (int j = 0; j < sm->dim; ++j) { if (j) putchar(' '); print_vt(sm->mtx[i][j]); }
+		putchar('\n');
+	    }
+	    dump_group(0, sq[0]);
+	    dump_group(1, sq[1]);
+	    WINDOW	wdw;
+	    stripe((const Seq**) sq, &wdw, pwd->alnprm.sh);
+	    printf("window %d %d %d\n", wdw.lw, wdw.up, wdw.width);
+	    // the raw alignC result (Vmf back-walk order), as align2 dispatches it (maln2.cc:1899-1910)
+	    VTYPE	scr = 0;
+	    SKL*	skl = 0;
+	    double	t0 = now_s();
+	    int	rep = atoi(kv(argc, argv, "rep", "1"));
+	    for (int r = 0; r < rep; ++r) {
+		delete[] skl;
+		switch (pwd->alnmode) {
+		    case NGP_ALB: skl = alignC<DPunit>(sq, pwd, &scr); break;
+		    case HLF_ALB: case RHF_ALB: skl = alignC<DPunit_hf>(sq, pwd, &scr); break;
+		    case GPF_ALB: skl = alignC<DPunit_pf>(sq, pwd, &scr); break;
+		    case NTV_ALB: skl = alignC<DPunit_nv>(sq, pwd, &scr); break;
+		    default: fatal("galign: alnmode %d not handled by the driver\n", pwd->alnmode);
+		}
+	    }
+	    printf("time %.6f\n", (now_s() - t0) / rep);
+	    printf("alignc "); print_vt(scr);
+	    if (!skl) printf(" skl 0\n");
+	    else {
+		printf(" skl %d %d :", skl->n, skl->m);
+		for (int k = 1; k <= skl->n; ++k) printf(" %d %d", skl[k].m, skl[k].n);
+		putchar('\n');
+	    }
+	    delete[] skl;
+	    Gsinfo	gsi;
+	    scr = 0;
+	    skl = align2(sq, pwd, &scr, &gsi);
+	    printf("align2 sh %d ", pwd->alnprm.sh); print_vt(scr);
+	    if (!skl) printf(" skl 0\n");
+	    else {
+		printf(" skl %d %d :", skl->n, skl->m);
+		for (int k = 1; k <= skl->n; ++k) printf(" %d %d", skl[k].m, skl[k].n);
+		putchar('\n');
+	    }
+	    gsi.skl = 0;
+	    delete[] skl;
+	    return 0;
+	}
 
 	std::vector<mSeq*> seqs = read_all(argv[2]);
 	int	nn = (int) seqs.size();

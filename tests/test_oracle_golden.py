@@ -72,3 +72,19 @@ def test_alignment_scores_and_corner_lists_bit_exact(oracle, name):
         scr, pts = oracle.align_ngp(oracle.seq(enc[pr["i"]]), oracle.seq(enc[pr["j"]]), M, p)
         assert scr == pr["score"], (pr["i"], pr["j"])
         assert pts == [tuple(x) for x in pr["skl"]], (pr["i"], pr["j"])
+
+
+@pytest.mark.parametrize("name", golden_names("galign_"))
+def test_group_alignment_bit_exact(oracle, name):
+    """orc_align_groups (alignC<DPunit | DPunit_hf | DPunit_pf> restated) on the reference's own staged
+    inputs: DP score and raw corner list identical to the reference, float and double flavours."""
+    g = golden(name)
+    A, B = oracle.group_arrays(g["groups"][0]), oracle.group_arrays(g["groups"][1])
+    gp = oracle.gparams_from_dump(g)
+    scr, pts, cells = oracle.align_groups(A, B, np.array(g["matrix"]), gp)
+    assert scr == g["alignc"]["score"]
+    assert pts == [tuple(x) for x in g["alignc"]["skl"]]
+    lw, up, _ = g["window"]
+    a, b = g["groups"]
+    want_cells = sum(max(0, min(m + up + 1, b["right"]) - max(m + lw, b["left"])) for m in range(a["left"], a["right"]))
+    assert cells == want_cells

@@ -80,6 +80,52 @@ def lcl_cases(p24, rag):
     score_case("score_p24_tgapf03_pam_f64", p24, flavour="d", mtx="pam", tgapf=0.3)
 
 
+def galign_case(name, rows_a, rows_b, flavour="d", files=None, **kv):
+    """Group-to-group alignC: the reference's staged inputs (what Fwd2c reads through mSeqItr after
+    PwdM) + score + raw corner list (Vmf back-walk order) + align2's normalised list."""
+    import gen_msa
+    os.makedirs(TMP, exist_ok=True)
+    if files is None:
+        fa, fb = os.path.join(TMP, name + "_A"), os.path.join(TMP, name + "_B")
+        gen_msa.write_native(fa, rows_a, "A")
+        gen_msa.write_native(fb, rows_b, "B")
+    else:
+        fa, fb = files
+    d = refio.run_galign(fa, fb, flavour=flavour, **kv)
+    d.pop("time", None)
+    d.update(name=name, kind="galign", flavour=flavour, args=kv)
+    with open(os.path.join(GOLD, name + ".json"), "w") as f:
+        json.dump(d, f, separators=(",", ":"))
+    print("wrote", name, "alnmode", d["pwdm"]["alnmode"], "a/b mode", d["pwdm"]["a_mode"], d["pwdm"]["b_mode"],
+          "hetero", d["groups"][0]["hetero"], d["groups"][1]["hetero"], "score", d["alignc"]["score"])
+
+
+def galign_cases():
+    import gen_msa
+    sp = "/root/reference/sample/pas/"
+    galign_case("galign_c1_multi_ab_f32", None, None, flavour="f", files=(sp + "Multi_A", sp + "Multi_B"), mtx="blosum62", sh=-50)
+    galign_case("galign_c1_multi_ab_f64", None, None, flavour="d", files=(sp + "Multi_A", sp + "Multi_B"), mtx="blosum62", sh=-50)
+    fam = gen_msa.synth_msa(64, 90, 0.1, 0.5, 41)
+    A, B = gen_msa.split_family(fam, range(0, 3), range(3, 6))
+    galign_case("galign_gpf_raw3x3", A, B, mtx="blosum62")                       # GPF, sim22i
+    A, B = gen_msa.split_family(fam, range(0, 12), range(12, 17))
+    galign_case("galign_gpf_prof12_raw5", A, B)                                   # GPF, sim32, PAM
+    galign_case("galign_gpf_prof12_raw5_wt", A, B, wt=1)                          # GPF, sim32w (weights)
+    galign_case("galign_gpf_prof12_raw5_f32", A, B, flavour="f", wt=1)
+    A, B = gen_msa.split_family(fam, range(0, 34), range(34, 64))
+    galign_case("galign_gpf_prof34_prof30", A, B, wt=1, sh=-30)                   # GPF, sim33
+    A, B = gen_msa.split_family(fam, range(0, 10), [10])
+    galign_case("galign_hlf_prof10_single", A, B)                                 # HLF, sim31
+    galign_case("galign_rhf_single_prof10", B, A, wt=1)                           # RHF (swap)
+    A, B = gen_msa.split_family(fam, range(0, 8), range(8, 14))
+    galign_case("galign_gpf_twopiece", A, B, ls=3, wt=1)                          # Noll = 3
+    gl = gen_msa.synth_msa(7, 80, 0.2, 0.6, 43, gapless=True)
+    galign_case("galign_ngp_gapless4x3", gl[:4], gl[4:], mtx="blosum62")          # NGP with thickness
+    dn = gen_msa.synth_msa(12, 120, 0.05, 0.35, 44, dna=True)
+    A, B = gen_msa.split_family(dn, range(0, 7), range(7, 12))
+    galign_case("galign_dna_gpf_twopiece", A, B, molc="n", ls=3, wt=1)
+
+
 def sample_pair():
     """C1: the sample/pas ce13a1 x ce13a2 pair of sample/test.sh (annotation lines stripped)."""
     out = []
@@ -130,12 +176,15 @@ def main():
     align_case("align_c2_first12", gen_synth.config_set("c2", 12))
     align_case("align_long1300", long_[:4])
     align_case("align_c1_ce13a", sample_pair(), sh=-50)
+    galign_cases()
 
 
 if __name__ == "__main__":
     if not refio.available("f"):
         sys.exit("oracle/_ref is not built: run `make -C oracle ref` where /root/reference exists")
-    if len(sys.argv) > 1 and sys.argv[1] == "lcl":      # only the lcl cases
+    if len(sys.argv) > 1 and sys.argv[1] == "galign":
+        galign_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "lcl":      # only the lcl cases
         p24_ = gen_synth.synth_set(24, 120, 0.1, 0.6, 11)
         rag_ = [s[:k] for s, k in zip(gen_synth.synth_set(20, 300, 0.1, 0.7, 21),
                                       [1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 300, 17, 64, 65, 31, 32, 33, 250])]

@@ -70,3 +70,79 @@ def parse(text):
             r["fstat"][(int(t[1]), int(t[2]))] = [float(x) for x in t[3:]]
     r["dist"] = np.array(r["dist"])
     return r
+
+
+def parse_galign(text):
+    """Parse `ref_driver galign` output: the staged inputs Fwd2c reads per column + the alignC result."""
+    r = {"groups": [None, None]}
+    lines = text.splitlines()
+    i = 0
+    cur = None
+    while i < len(lines):
+        t = lines[i].split()
+        i += 1
+        if not t:
+            continue
+        if t[0].startswith("#ref_driver"):
+            r["header"] = dict(x.split("=", 1) for x in t[1:])
+        elif t[0] == "pwdm":
+            r["pwdm"] = {t[k]: int(t[k + 1]) for k in range(1, len(t), 2)}
+        elif t[0] == "pwdc":
+            r["pwdc"] = {t[k]: float(t[k + 1]) for k in range(1, len(t), 2)}
+        elif t[0] == "dim":
+            dim = int(t[1])
+            r["matrix"] = [[float(x) for x in lines[i + k].split()] for k in range(dim)]
+            i += dim
+        elif t[0] == "group":
+            cur = {t[k]: (float(t[k + 1]) if t[k] == "sumwt" else int(t[k + 1])) for k in range(2, len(t), 2)}
+            cur.update(pos=[], cfq=[], dfq=[], efq=[], res=[], vss=[], sfq=[], tfq=[], rfq=[], weight=None)
+            r["groups"][int(t[1])] = cur
+        elif t[0] == "weight":
+            n = int(t[1])
+            cur["weight"] = [float(x) for x in t[2:2 + n]] if n else None
+        elif t[0] == "pos":
+            cur["pos"].append(int(t[1]))
+            k = 3
+            cur["cfq"].append(float(t[k])); cur["dfq"].append(float(t[k + 1])); cur["efq"].append(float(t[k + 2]))
+            k += 3
+            assert t[k] == "res"
+            cur["res"].append([int(x) for x in t[k + 1:k + 1 + cur["many"]]])
+            k += 1 + cur["many"]
+            assert t[k] == "vss"
+            nv = int(t[k + 1])
+            cur["vss"].append([float(x) for x in t[k + 2:k + 2 + nv]])
+            k += 2 + nv
+            for tag in ("sfq", "tfq", "rfq"):
+                assert t[k] == tag, (t[k], tag)
+                n = int(t[k + 1])
+                k += 2
+                if n < 0:
+                    cur[tag].append(None)
+                else:
+                    cur[tag].append([[int(t[k + 3 * q]), float(t[k + 3 * q + 1]), int(t[k + 3 * q + 2])] for q in range(n)])
+                    k += 3 * n
+        elif t[0] == "window":
+            r["window"] = [int(x) for x in t[1:4]]
+        elif t[0] == "time":
+            r["time"] = float(t[1])
+        elif t[0] in ("alignc", "align2"):
+            off = 1 if t[0] == "alignc" else 3
+            scr = float(t[off])
+            pts = None
+            if t[off + 1] == "skl" and t[off + 2] != "0":
+                n = int(t[off + 2])
+                v = [int(x) for x in t[off + 5:off + 5 + 2 * n]]
+                pts = [list(x) for x in zip(v[0::2], v[1::2])]
+            r[t[0]] = dict(score=scr, skl=pts)
+            if t[0] == "align2":
+                r["align2"]["sh"] = int(t[2])
+    return r
+
+
+def run_galign(fa, fb, flavour="d", timeout=3600, **kv):
+    env = dict(os.environ, ALN_TAB=os.path.join(REFDIR, "table"))
+    args = [driver(flavour), "galign", fa, "fb=" + fb] + ["%s=%s" % (k, v) for k, v in kv.items()]
+    out = subprocess.run(args, env=env, capture_output=True, text=True, timeout=timeout)
+    if out.returncode != 0:
+        raise RuntimeError("ref_driver galign failed (%d): %s" % (out.returncode, out.stderr[-2000:]))
+    return parse_galign(out.stdout)
