@@ -83,6 +83,51 @@ int pg_align_pairs(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx, c
                    void *out_scores, int64_t **out_offs, pg_skl **out_pts);
 void pg_free(void *p);
 
+/* ---- per-call level, groups: stands behind
+ *   template<class recd_t> SKL* alignC(mSeq* seqs[2], PwdM* pwd, VTYPE* scr, ...)   src/fwd2c.h:670-677
+ * for recd_t = DPunit (NGP_ALB, groups without internal gaps), DPunit_hf (HLF_ALB / RHF_ALB) and
+ * DPunit_pf (GPF_ALB), as align2 dispatches it (src/maln2.cc:1899-1910), affine or two-piece, for a
+ * BATCH of independent (a, b) pairs -- e.g. the candidate partitions of Prrn::best_of_n
+ * (src/prrn5.cc:594-631).  Precondition as in the reference: PwdM pwd(seqs) already ran (sequences
+ * swapped if pwd->swp, mkthick / Gfq / convseq done).  A pg_group is what Fwd2c reads from one mSeq
+ * through mSeqItr for the columns left-1 .. right-1 (npos = right - left + 1 entries):
+ *   cfq, efq   SeqThk::cfq / efq per column                         src/mseq.h:70-74
+ *   vec        this side's factor of sim2: S(m,n) = vec_a[m] . vec_b[n] over kdim residue codes; every
+ *              sim11 .. sim33 variant (src/maln2.cc:534-623,1230-1296) is such a product (profile part
+ *              of vss x frequency vector; INTEGRATION.md gives the rule per a_mode / b_mode)
+ *   glen, gfreq, sfq / tfq / rfq   the column's GFREQ lists (Gfq::sfrq / tfrq / rfrq, src/gfreq.h:44-55)
+ *              pooled: list of column x starts at glen[sfq[x]], ends at the first glen < 0; -1 = empty
+ * Arithmetic is double for either VTYPE flavour; scores agree with the reference within 1e-5 relative
+ * and corner lists are identical except at near-ties (BASELINE north_star).  Output as pg_align_pairs:
+ * (*out_pts)[(*out_offs)[p] .. (*out_offs)[p+1]) = skl[1..n] in Vmf back-walk order; release with
+ * pg_free. */
+typedef struct {
+    int32_t many, len, left, right;
+    int32_t hetero;             /* Gfq::hetero, -1 without gap profile                               */
+    int32_t nils;               /* inex.nils                                                          */
+    const double *cfq, *efq;
+    const double *vec;          /* [npos][kdim]                                                       */
+    const int32_t *glen;
+    const double *gfreq;
+    int32_t npool;
+    const int32_t *sfq, *tfq, *rfq;     /* [npos] or NULL                                             */
+} pg_group;
+
+typedef struct {
+    int32_t alnmode;            /* ALN_MODE, src/aln.h:71-76: 6 NGP_ALB, 7 HLF_ALB, 8 RHF_ALB, 9 GPF_ALB */
+    int32_t Noll, codonk1;      /* PwdB::Noll, PwdB::codonk1 (src/aln2.cc:100,117)                     */
+    int32_t sh;                 /* pwd->alnprm.sh                                                      */
+    int32_t kdim;
+    double u;                   /* pwd->alnprm.u                                                       */
+    double Weighted_GOP, Basic_GOP;                 /* PwdM::resetuab, src/maln2.cc:227-243           */
+    double BasicGOP, BasicGEP, LongGOP, LongGEP;    /* PwdB::PwdB, src/aln2.cc:103-108                */
+} pg_gparams;
+
+int pg_align_groups(pg_context *ctx, const pg_group *a, const pg_group *b, const pg_gparams *prm, int64_t npairs,
+                    double *out_scores, int64_t **out_offs, pg_skl **out_pts);
+/* DP cells the reference visits for one group pair (band from stripe(), src/aln2.cc:156-174). */
+int64_t pg_group_cells(const pg_group *a, const pg_group *b, int32_t sh);
+
 /* ---- batch level: stands behind
  *   FTYPE* calcdist(mSeq** sbuf, int nn, DistCal realign = DynScr)            src/phyl.cc:318-342
  * (selfscr :253-261, dpscore :221-251, alnscore2dist src/aln2.cc:289-334) for single sequences.

@@ -51,6 +51,30 @@ class _PgSeqs(C.Structure):
                 ("right", C.c_void_p), ("exg", C.c_void_p), ("nseq", C.c_int32)]
 
 
+class _PgGroup(C.Structure):
+    _fields_ = [("many", C.c_int32), ("len", C.c_int32), ("left", C.c_int32), ("right", C.c_int32),
+                ("hetero", C.c_int32), ("nils", C.c_int32), ("cfq", C.c_void_p), ("efq", C.c_void_p),
+                ("vec", C.c_void_p), ("glen", C.c_void_p), ("gfreq", C.c_void_p), ("npool", C.c_int32),
+                ("sfq", C.c_void_p), ("tfq", C.c_void_p), ("rfq", C.c_void_p)]
+
+
+class GParams(C.Structure):
+    """pg_gparams: the PwdM / PwdB constants alignC reads (src/maln2.cc:227-243, src/aln2.cc:97-117)."""
+    _fields_ = [("alnmode", C.c_int32), ("Noll", C.c_int32), ("codonk1", C.c_int32), ("sh", C.c_int32),
+                ("kdim", C.c_int32), ("u", C.c_double), ("Weighted_GOP", C.c_double), ("Basic_GOP", C.c_double),
+                ("BasicGOP", C.c_double), ("BasicGEP", C.c_double), ("LongGOP", C.c_double), ("LongGEP", C.c_double)]
+
+
+def _pg_group(S):
+    """S: dict of flat arrays from prrn_aln_b200.groups.stage_pair."""
+    has = S["hetero"] >= 0
+    g = _PgGroup(S["many"], S["len"], S["left"], S["right"], S["hetero"], S["nils"], S["cfq"].ctypes.data,
+                 S["efq"].ctypes.data, S["vec"].ctypes.data, S["glen"].ctypes.data, S["gfreq"].ctypes.data,
+                 len(S["glen"]), S["sfq"].ctypes.data if has else None, S["tfq"].ctypes.data if has else None,
+                 S["rfq"].ctypes.data if has else None)
+    return g
+
+
 def lib_path():
     return os.path.join(_HERE, "libprrn_gpu.so")
 
@@ -83,6 +107,10 @@ def load_library():
     L.pg_align_pairs.argtypes = [C.c_void_p, C.POINTER(_PgSeqs), C.c_void_p, C.c_void_p, C.c_int64,
                                  C.POINTER(Params), C.c_void_p, C.c_int32, C.c_void_p,
                                  C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32))]
+    L.pg_align_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32))]
+    L.pg_group_cells.restype = C.c_int64
+    L.pg_group_cells.argtypes = [C.POINTER(_PgGroup), C.POINTER(_PgGroup), C.c_int32]
     L.pg_free.argtypes = [C.c_void_p]
     L.pg_free.restype = None
     L.pg_calcdist.argtypes = [C.c_void_p, C.POINTER(_PgSeqs), C.POINTER(Params), C.c_void_p, C.c_int32,
@@ -207,6 +235,27 @@ class Context:
             self.L.pg_free(pts)
         return out, [p[o[i]:o[i + 1]] for i in range(len(a))]
 
+    # -- per-call level, groups: batch of alignC<DPunit | DPunit_hf | DPunit_pf> --------------------
+    def align_groups(self, pairs):
+        """pairs: [(A, B, GParams), ...] with A / B from groups.stage_pair.  Returns (scores float64,
+        [corner array (n x 2, Vmf back-walk order) per pair]) as alignC does for each pair."""
+        n = len(pairs)
+        ga = (_PgGroup * max(n, 1))(*[_pg_group(p[0]) for p in pairs])
+        gb = (_PgGroup * max(n, 1))(*[_pg_group(p[1]) for p in pairs])
+        gp = (GParams * max(n, 1))(*[p[2] for p in pairs])
+        out = np.empty(n, np.float64)
+        offs = C.POINTER(C.c_int64)()
+        pts = C.POINTER(C.c_int32)()
+        self._check(self.L.pg_align_groups(self.h, ga, gb, gp, n, out.ctypes.data, C.byref(offs), C.byref(pts)))
+        try:
+            o = np.ctypeslib.as_array(offs, shape=(n + 1,)).copy()
+            total = int(o[-1])
+            p = np.ctypeslib.as_array(pts, shape=(max(total, 1) * 2,)).copy()[:2 * total].reshape(-1, 2)
+        finally:
+            self.L.pg_free(offs)
+            self.L.pg_free(pts)
+        return out, [p[o[i]:o[i + 1]] for i in range(n)]
+
     # -- batch level: calcdist(DynScr) ------------------------------------------------------------
     def calcdist(self, seqs, prm, mtx, k_begin=0, k_end=None, out=None):
         npair = seqs.n * (seqs.n - 1) // 2
@@ -240,6 +289,18 @@ class Context:
         a, b = C.c_double(0), C.c_double(0)
         self._check(self.L.pg_dpx_peak(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+def group_cells(A, B, sh):
+    """DP cells the reference visits for one staged group pair (host-only helper)."""
+    ga, gb = _pg_group(A), _pg_group(B)
+    return load_library().pg_group_cells(C.byref(ga), C.byref(gb), sh)
+
+
+def gparams_from_pwd(alnmode, Noll, codonk1, sh, kdim, u, v, Basic_GOP, BasicGOP, BasicGEP, LongGOP, LongGEP):
+    """GParams from the PwdM / PwdB members a shim reads (Weighted_GOP = (VTYPE) -alnprm.v, maln2.cc:238)."""
+    return GParams(alnmode, Noll, codonk1, sh, kdim, float(np.float32(u)), -float(np.float32(v)), Basic_GOP,
+                   BasicGOP, BasicGEP, LongGOP, LongGEP)
 
 
 def calcdist_cells(seqs, prm, k_begin=0, k_end=None):

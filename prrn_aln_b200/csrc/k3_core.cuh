@@ -1,0 +1,315 @@
+// k3_core.cuh -- per-cell machinery of kernel K3: group-to-group banded fill WITH path and gap-profile
+// state.  Stands behind alignC<DPunit | DPunit_hf | DPunit_pf> (reference src/fwd2c.h:359-482 forwardB,
+// :138-176 initB; src/fwd2c.cc gapopen / update specialisations; src/gfreq.cc:507-605 newgap /
+// newdelta / incdelta; src/maln.h:185-187 unp1, :262-312 newgap1/2/3; src/dpunit.cc reset / copy).
+// Shared by the CUDA kernel (k3_groups.cu) and the host emulation (tests/host_emul/k3_emul.cc).
+//
+// A DP record (the reference's DPunit_hf / DPunit_pf) is a run of 32-bit words
+//     [0-1] val (double)  [2] dir  [3] ptr  [4] glb  [5] -  [6 ..) dla: (glen, nins) pairs  [..) dlb
+// with list capacities fixed per alignment (hetero + 3), so records can live in any memory space and
+// be addressed by (slot, row).  Arithmetic is double for both VTYPE flavours (the group path is
+// floating point with a 1e-5 relative tolerance: BASELINE north_star).
+#pragma once
+#include <stdint.h>
+
+#include "k1_core.cuh"
+
+#define K3_NEVSEL (-(1.7976931348623157e+308 / 16 * 7))
+#define K3_LAST 0x7fffffff
+
+enum { K3_DIAG = 2, K3_NEWD = 3, K3_VERT = 4, K3_HORI = 8, K3_NEWV = 12, K3_NEWH = 13 };   // aln.h:47-52
+PG_HD bool k3_isdiag(int d) { d &= 15; return d == 2 || d == 3; }
+PG_HD bool k3_isvert(int d) { d &= 15; return (d >= 4 && d <= 7) || d == 12; }
+PG_HD bool k3_ishori(int d) { d &= 15; return (d >= 8 && d <= 11) || d == 13; }
+
+// One group as the DP reads it, columns left-1 .. right-1 (entry x <-> position left-1+x)
+struct K3Group {
+    const double* cfq;      // SeqThk::cfq
+    const double* efq;      // SeqThk::efq
+    const double* prof;     // [npos][kdim] profile row (what sim2 takes from the `a` side)
+    const double* freq;     // [npos][kdim] frequency row (what sim2 takes from the `b` side)
+    const int32_t* glen;    // pooled GFREQ lists: glen < 0 terminates
+    const double* gfreq;    //                    freq
+    const int32_t* sfq;     // [npos] list offsets, -1 = empty
+    const int32_t* tfq;
+    const int32_t* rfq;
+    int32_t L;              // right - left
+    int32_t nils;
+};
+
+struct K3Prm {
+    int32_t mode;           // 0 DPunit, 1 DPunit_hf, 2 DPunit_pf
+    int32_t Noll, codonk1;
+    int32_t lw, up;         // band in window-relative coordinates (r = n - m)
+    int32_t capa, capb;     // list capacities (pairs)
+    int32_t kdim;
+    double u;               // alnprm.u as the reference's float
+    double wgop, bgop;      // Weighted_GOP, Basic_GOP
+    double u2divu1, v2divv1;
+};
+
+// ---- record access -------------------------------------------------------------------------------
+PG_HD int k3_stride(int capa, int capb) { return 6 + 2 * (capa + capb); }
+PG_HD double k3_val(const int* r) { return *reinterpret_cast<const double*>(r); }
+PG_HD void k3_setval(int* r, double v) { *reinterpret_cast<double*>(r) = v; }
+#define K3_DIR(r) ((r)[2])
+#define K3_PTR(r) ((r)[3])
+#define K3_GLB(r) ((r)[4])
+PG_HD int* k3_dla(int* r) { return r + 6; }
+PG_HD const int* k3_dla(const int* r) { return r + 6; }
+PG_HD int* k3_dlb(int* r, int capa) { return r + 6 + 2 * capa; }
+PG_HD const int* k3_dlb(const int* r, int capa) { return r + 6 + 2 * capa; }
+
+// IDELTA lists: pairs (glen, nins), terminated by glen == K3_LAST (gfreq.h:26,31)
+PG_HD void k3_cleardelta(int* d) { d[0] = 0; d[1] = 0; d[2] = K3_LAST; d[3] = 0; }       // gfreq.cc:556
+PG_HD void k3_copydelta(int* dst, const int* src)
+{   // gfreq.cc:548-554
+    do { dst[0] = src[0]; dst[1] = src[1]; dst += 2; src += 2; } while (src[0] < K3_LAST);
+    dst[0] = src[0]; dst[1] = src[1];
+}
+PG_HD void k3_incdelta(int* dlt, const int* dln, int n)
+{   // gfreq.cc:595-602 (dlt may alias dln)
+    do { dlt[0] = dln[0]; dlt[1] = dln[1] + n; dlt += 2; dln += 2; } while (dln[0] < K3_LAST);
+    dlt[0] = dln[0]; dlt[1] = dln[1];
+}
+// gfreq.cc:567-584: filter the dynamic gap state through a column's static gap state; dlt may alias dln
+PG_HD void k3_newdelta(int* dlt, const int32_t* glen, const int* dln)
+{
+    int* dst = dlt;
+    int tg = 0, tn = 0;
+    if (glen)
+        for (; *glen >= 0; ++glen) {
+            const int gl = *glen;
+            if (gl >= dln[0]) {
+                while (gl >= dln[2]) dln += 2;
+                if (dln[1] > tn) {
+                    const int nins = dln[1];
+                    dst[0] = tg; dst[1] = tn; dst += 2;
+                    tn = nins;
+                    tg = gl + 1;
+                }
+            }
+        }
+    dst[0] = tg; dst[1] = tn;
+    dst[2] = K3_LAST; dst[3] = 0;
+}
+PG_HD int k3_gaplensd(int gl, const int* dl)
+{   // gfreq.h:67-71
+    while (gl >= dl[2]) dl += 2;
+    return gl + dl[1];
+}
+
+// a GFREQ list view
+struct K3List { const int32_t* glen; const double* freq; };
+PG_HD K3List k3_list(const K3Group& g, const int32_t* offs, int ix)
+{
+    K3List l;
+    const int o = offs ? offs[ix] : -1;
+    l.glen = o >= 0 ? g.glen + o : nullptr;
+    l.freq = o >= 0 ? g.gfreq + o : nullptr;
+    return l;
+}
+PG_HD bool k3_neo(const K3List& l, int i) { return l.glen && l.glen[i] >= 0; }
+
+// newgap(cf, dlc, df, dld), gfreq.cc:507-521
+PG_HD double k3_newgap4(const K3List& cf, const int* dlc, const K3List& df, const int* dld)
+{
+    double g = 0;
+    int ic = 0;
+    for (int id = 0; k3_neo(df, id); ++id) {
+        const int j = k3_gaplensd(df.glen[id], dld);
+        for (; k3_neo(cf, ic); ++ic)
+            if (k3_gaplensd(cf.glen[ic], dlc) >= j) break;
+        if (!k3_neo(cf, ic)) break;
+        g += cf.freq[ic] * df.freq[id];
+    }
+    return g;
+}
+// PwdM::newgap1(acf, dla, glb), maln.h:288-291 with newgap(cf, dlc, j) gfreq.cc:523-531, newgapc maln.h:270
+PG_HD double k3_newgap1(double wgop, const K3List& acf, const int* dla, int glb)
+{
+    if (!k3_neo(acf, 0)) return 0;
+    if (k3_neo(acf, 1)) {
+        for (int i = 0; k3_neo(acf, i); ++i)
+            if (k3_gaplensd(acf.glen[i], dla) >= glb) return wgop * acf.freq[i];
+        return wgop * 0.0;
+    }
+    return (dla[1] + acf.glen[0] >= glb) ? wgop * acf.freq[0] : 0;
+}
+// PwdM::newgap2(adf, glb, dla), maln.h:297-300 with newgap(df, i, dld) gfreq.cc:533-544, newgapd maln.h:278
+PG_HD double k3_newgap2(double wgop, const K3List& adf, int glb, const int* dla)
+{
+    if (!k3_neo(adf, 0)) return 0;
+    if (k3_neo(adf, 1)) {
+        double g = 0;
+        for (int i = 0; k3_neo(adf, i); ++i) {
+            while (adf.glen[i] >= dla[2]) dla += 2;
+            if (glb < adf.glen[i] + dla[1]) break;
+            g += adf.freq[i];
+        }
+        return wgop * g;
+    }
+    return (glb >= dla[1] + adf.glen[0]) ? wgop * adf.freq[0] : 0;
+}
+
+// sim2 as one contraction: profile row of a x frequency row of b (covers sim11 .. sim33, maln2.cc:534-623)
+PG_HD double k3_sim(const K3Group& a, const K3Group& b, const K3Prm& p, int ia, int ib)
+{
+    const double* pa = a.prof + (size_t)ia * p.kdim;
+    const double* fb = b.freq + (size_t)ib * p.kdim;
+    double s = 0;
+    for (int k = 0; k < p.kdim; ++k) s += pa[k] * fb[k];
+    return s;
+}
+// unp1, maln.h:185-187: x.cfq * y.efq * -u
+PG_HD double k3_unp(const K3Group& x, int ix, const K3Group& y, int iy, double u) { return x.cfq[ix] * y.efq[iy] * -u; }
+
+// gapopen (fwd2c.cc:52-91 without di-thickness, :152-161, :202-212)
+PG_HD double k3_gapopen(const K3Prm& p, const K3Group& a, const K3Group& b, const int* r, int ia, int ib, int d3)
+{
+    if (p.mode == 0) {
+        double axb = 0;
+        if (d3 > 0) { if (!k3_isvert(K3_DIR(r))) axb = a.cfq[ia] * b.efq[ib]; }
+        else if (d3 < 0) { if (!k3_ishori(K3_DIR(r))) axb = b.cfq[ib] * a.efq[ia]; }
+        else return 0;
+        return p.bgop * axb;
+    }
+    if (p.mode == 1) {
+        if (d3 == 0) return k3_newgap2(p.wgop, k3_list(a, a.tfq, ia), K3_GLB(r), k3_dla(r));
+        if (d3 > 0) return k3_newgap1(p.wgop, k3_list(a, a.sfq, ia), k3_dla(r), K3_GLB(r));
+        return k3_newgap2(p.wgop, k3_list(a, a.rfq, ia), K3_GLB(r), k3_dla(r));
+    }
+    const int* dla = k3_dla(r);
+    const int* dlb = k3_dlb(r, p.capa);
+    if (d3 == 0)
+        return k3_newgap4(k3_list(a, a.sfq, ia), dla, k3_list(b, b.tfq, ib), dlb) * p.bgop +
+               k3_newgap4(k3_list(b, b.sfq, ib), dlb, k3_list(a, a.tfq, ia), dla) * p.bgop;
+    if (d3 > 0) return k3_newgap4(k3_list(a, a.sfq, ia), dla, k3_list(b, b.rfq, ib), dlb) * p.bgop;
+    return k3_newgap4(k3_list(b, b.sfq, ib), dlb, k3_list(a, a.rfq, ia), dla) * p.bgop;
+}
+
+// update (fwd2c.cc:93-102, :163-182, :214-233); dst may alias src
+PG_HD void k3_update(const K3Prm& p, const K3Group& a, const K3Group& b, int* dst, const int* src, int ia, int ib,
+                     double gpn, int d3)
+{
+    const int sdir = K3_DIR(src);
+    int dir;
+    if (d3 > 0) dir = k3_ishori(sdir) ? K3_NEWV : K3_VERT;
+    else if (d3 < 0) dir = k3_isvert(sdir) ? K3_NEWH : K3_HORI;
+    else dir = k3_isdiag(sdir) ? K3_DIAG : K3_NEWD;
+    const int sglb = K3_GLB(src);
+    if (p.mode == 1) {
+        const int o = a.tfq ? a.tfq[ia] : -1;
+        if (d3 == 0) { k3_newdelta(k3_dla(dst), o >= 0 ? a.glen + o : nullptr, k3_dla(src)); K3_GLB(dst) = 0; }
+        else if (d3 > 0) { k3_newdelta(k3_dla(dst), o >= 0 ? a.glen + o : nullptr, k3_dla(src)); K3_GLB(dst) = sglb + 1; }
+        else { k3_incdelta(k3_dla(dst), k3_dla(src), 1); K3_GLB(dst) = 0; }
+    } else if (p.mode == 2) {
+        const int oa = a.tfq ? a.tfq[ia] : -1, ob = b.tfq ? b.tfq[ib] : -1;
+        const int32_t* ta = oa >= 0 ? a.glen + oa : nullptr;
+        const int32_t* tb = ob >= 0 ? b.glen + ob : nullptr;
+        if (d3 == 0) { k3_newdelta(k3_dla(dst), ta, k3_dla(src)); k3_newdelta(k3_dlb(dst, p.capa), tb, k3_dlb(src, p.capa)); }
+        else if (d3 > 0) { k3_newdelta(k3_dla(dst), ta, k3_dla(src)); k3_incdelta(k3_dlb(dst, p.capa), k3_dlb(src, p.capa), 1); }
+        else { k3_newdelta(k3_dlb(dst, p.capa), tb, k3_dlb(src, p.capa)); k3_incdelta(k3_dla(dst), k3_dla(src), 1); }
+    } else K3_GLB(dst) = 0;
+    const double v = k3_val(src) + gpn;
+    const int ptr = K3_PTR(src);
+    K3_DIR(dst) = dir;
+    k3_setval(dst, v);
+    K3_PTR(dst) = ptr;
+}
+PG_HD void k3_reset(const K3Prm& p, int* r)
+{
+    k3_setval(r, K3_NEVSEL);
+    K3_DIR(r) = 0; K3_PTR(r) = 0; K3_GLB(r) = 0; r[5] = 0;
+    k3_cleardelta(k3_dla(r));
+    k3_cleardelta(k3_dlb(r, p.capa));
+}
+PG_HD void k3_copy(const K3Prm& p, int* d, const int* s)
+{
+    if (d == s) return;
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; d[4] = s[4];
+    if (p.mode >= 1) k3_copydelta(k3_dla(d), k3_dla(s));
+    if (p.mode == 2) k3_copydelta(k3_dlb(d, p.capa), k3_dlb(s, p.capa));
+}
+
+// Path records (the reference's Vmf): (m, n, previous record); appended at NEWD / NEWV / NEWH cells
+struct K3Vmf { int m, n, p; };
+
+// One DP cell (fwd2c.h:393-468).  Inputs are read-only records: hdiag = H(m-1,n-1), habove / gabove /
+// g2above = row m-1 at column n (the black record outside the band), hleft = H(m,n-1).  f1 / f2 are the
+// row's running horizontal states (updated in place); hout / gout / g2out receive H, G, G2 of the cell.
+// Returns true when the cell must append a path record (the caller owns the record store).
+PG_HD bool k3_cell(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, int ib, bool first_row, bool first_col,
+                   double dab, double* pua, const int* hdiag, const int* habove, const int* gabove, const int* g2above,
+                   const int* hleft, int* f1, int* f2, int* hout, int* gout, int* g2out, const int* black)
+{
+    // diagonal (fwd2c.h:395-398), straight into the output record
+    double gop = k3_gapopen(p, a, b, hdiag, ia, ib, 0);
+    k3_update(p, a, b, hout, hdiag, ia, ib, dab + gop, 0);
+    double gnp;
+    const int* mx;
+    if (!first_row) {       // vertical (fwd2c.h:401-409)
+        if (a.nils) *pua = k3_unp(a, ia, b, ib, p.u);
+        gnp = k3_gapopen(p, a, b, gabove, ia, ib, 1);
+        gop = k3_gapopen(p, a, b, habove, ia, ib, 1);
+        if (!k3_isvert(K3_DIR(habove)) && (k3_val(habove) + gop > k3_val(gabove) + gnp))
+            k3_update(p, a, b, gout, habove, ia, ib, gop, 1);
+        else k3_update(p, a, b, gout, gabove, ia, ib, gnp, 1);
+        k3_setval(gout, k3_val(gout) + *pua);
+        mx = gout;
+        if (p.Noll == 3) {  // vertical2 (fwd2c.h:411-420)
+            gnp = p.v2divv1 * k3_gapopen(p, a, b, g2above, ia, ib, 1);
+            gop = p.v2divv1 * gop;
+            if (!k3_isvert(K3_DIR(habove)) && (k3_val(habove) + gop > k3_val(g2above) + gnp))
+                k3_update(p, a, b, g2out, habove, ia, ib, gop, 1);
+            else k3_update(p, a, b, g2out, g2above, ia, ib, gnp, 1);
+            k3_setval(g2out, k3_val(g2out) + p.u2divu1 * *pua);
+            if (k3_val(g2out) > k3_val(mx)) mx = g2out;
+        }
+    } else {                // first row: the G rows keep their untouched (black) records
+        k3_copy(p, gout, black);
+        if (p.Noll == 3) k3_copy(p, g2out, black);
+        mx = gout;
+    }
+    if (!first_col) {       // horizontal (fwd2c.h:422-431)
+        const double pub = k3_unp(b, ib, a, ia, p.u);
+        gnp = k3_gapopen(p, a, b, f1, ia, ib, -1);
+        gop = k3_gapopen(p, a, b, hleft, ia, ib, -1);
+        if (!k3_ishori(K3_DIR(hleft)) && (k3_val(hleft) + gop > k3_val(f1) + gnp))
+            k3_update(p, a, b, f1, hleft, ia, ib, gop, -1);
+        else k3_update(p, a, b, f1, f1, ia, ib, gnp, -1);
+        k3_setval(f1, k3_val(f1) + pub);
+        if (k3_val(f1) >= k3_val(mx)) mx = f1;
+        if (p.Noll == 3) {  // horizontal2 (fwd2c.h:433-442)
+            gnp = p.v2divv1 * k3_gapopen(p, a, b, f2, ia, ib, -1);
+            gop = p.v2divv1 * gop;
+            if (!k3_ishori(K3_DIR(hleft)) && (k3_val(hleft) + gop > k3_val(f2) + gnp))
+                k3_update(p, a, b, f2, hleft, ia, ib, gop, -1);
+            else k3_update(p, a, b, f2, f2, ia, ib, gnp, -1);
+            k3_setval(f2, k3_val(f2) + p.u2divu1 * pub);
+            if (k3_val(f2) >= k3_val(mx)) mx = f2;
+        }
+    }
+    if (k3_val(mx) > k3_val(hout)) k3_copy(p, hout, mx);        // fwd2c.h:453
+    const int dir = K3_DIR(hout);
+    return dir == K3_NEWD || dir == K3_NEWV || dir == K3_NEWH;   // fwd2c.h:465-467
+}
+
+// Boundary cells (initB, fwd2c.h:138-176).  Row: asi at a.left-1 (ia = 0), k-th column (1-based).
+PG_HD void k3_boundary_row(const K3Prm& p, const K3Group& a, const K3Group& b, int k, int* dst, const int* src)
+{
+    const int ia = 0, ib = k;           // b position left + k - 1  <->  staged index k
+    const double pub = k3_unp(b, ib, a, ia, p.u);
+    double gnp = k3_gapopen(p, a, b, src, ia, ib, -1);
+    gnp = (k < p.codonk1) ? gnp + pub : (p.v2divv1 * gnp + p.u2divu1 * pub);
+    k3_update(p, a, b, dst, src, ia, ib, gnp, -1);
+}
+// Column: bsi at b.left-1 (ib = 0), k-th row (1-based)
+PG_HD void k3_boundary_col(const K3Prm& p, const K3Group& a, const K3Group& b, int k, int* dst, const int* src)
+{
+    const int ia = k, ib = 0;
+    const double pua = k3_unp(a, ia, b, ib, p.u);
+    double gnp = k3_gapopen(p, a, b, src, ia, ib, 1);
+    gnp = (k < p.codonk1) ? gnp + pua : (p.v2divv1 * gnp + p.u2divu1 * pua);
+    k3_update(p, a, b, dst, src, ia, ib, gnp, 1);
+}

@@ -1,0 +1,170 @@
+// k3_groups.cu -- kernel K3: group-to-group banded alignment WITH path and gap-profile state (sm_100a).
+//
+// Stands behind alignC<DPunit | DPunit_hf | DPunit_pf> (reference src/fwd2c.h:670-677: Fwd2c ctor :81,
+// initB :138, forwardB :359, Vmf::traceback src/vmf.cc:103) as align2 dispatches it for NGP_ALB /
+// HLF_ALB / RHF_ALB / GPF_ALB (src/maln2.cc:1899-1910), affine and two-piece (Noll 2 / 3).
+//
+// Machine mapping
+//   CTA    = one alignment at a time (persistent CTAs pull pairs, heaviest first, from an atomic queue).
+//   thread = one ROW of the DP matrix; the CTA sweeps ANTI-DIAGONALS: at step s thread t computes cell
+//            (m = pass*T + t, n = s - t), one __syncthreads per step.  Rows beyond T take further passes;
+//            the bottom row of a pass is parked in a row buffer and re-enters as the top of the next.
+//   records  The reference's DPunit_hf / DPunit_pf records (value, direction, path pointer and the
+//            IDELTA lists of the dynamic gap state) are fixed-stride word runs (k3_core.cuh) in an
+//            L2-resident per-CTA arena; H records rotate through three generations per row so that
+//            the diagonal / upper / left neighbours are plain reads of what the neighbouring thread
+//            published one and two steps ago; G, G2 through two.
+//   path   = the reference's Vmf: an append-only record store per CTA (shared-memory cursor); the same
+//            thread block walks the pointer chain back at the end and emits the corner list in Vmf
+//            back-walk order, so the output equals alignC's, quirks included.
+//   sim2   = one contraction X_a[m] . Y_b[n] over residue codes (all sim11..sim33 variants, staged by
+//            the host layer); evaluated per cell here, or read from the tile matrix K4 precomputed.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "k3_core.cuh"
+#include "pg_internal.h"
+
+namespace {
+
+constexpr int T = K3_THREADS;
+
+__global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
+{
+    __shared__ int sm_pair;
+    __shared__ int sm_vmf;
+    __shared__ int sm_last_ptr;
+    __shared__ double sm_last_val;
+    const int t = threadIdx.x;
+    int* const arena = a.arena + (size_t)blockIdx.x * a.arena_words;
+    K3Vmf* const vmf = a.vmf + (size_t)blockIdx.x * a.vmf_cap;
+
+    for (;;) {
+        if (t == 0) sm_pair = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int pi = sm_pair;
+        if (pi >= a.npairs) break;
+        const K3Pair& P = a.pairs[pi];
+        const K3Group& A = P.a;
+        const K3Group& B = P.b;
+        const K3Prm& p = P.prm;
+        const int LQ = A.L, LS = B.L;
+        const int st = k3_stride(p.capa, p.capb);
+        // arena layout (records): rowH | rowG | rowG2 | colH | pubH[3][T] | pubG[2][T] | pubG2[2][T] | F1[T] | F2[T] | black
+        int* const rowH = arena;
+        int* const rowG = rowH + (size_t)(LS + 2) * st;
+        int* const rowG2 = rowG + (size_t)(LS + 2) * st;
+        int* const colH = rowG2 + (size_t)(LS + 2) * st;
+        int* const pubH = colH + (size_t)(LQ + 2) * st;
+        int* const pubG = pubH + (size_t)3 * T * st;
+        int* const pubG2 = pubG + (size_t)2 * T * st;
+        int* const F1 = pubG2 + (size_t)2 * T * st;
+        int* const F2 = F1 + (size_t)T * st;
+        int* const black = F2 + (size_t)T * st;
+        // ---- reset the records this pair can read before writing
+        for (int i = t; i < LS + 2; i += T) {
+            k3_reset(p, rowH + (size_t)i * st); k3_reset(p, rowG + (size_t)i * st); k3_reset(p, rowG2 + (size_t)i * st);
+        }
+        for (int i = t; i < LQ + 2; i += T) k3_reset(p, colH + (size_t)i * st);
+        for (int g = 0; g < 3; ++g) k3_reset(p, pubH + ((size_t)g * T + t) * st);
+        for (int g = 0; g < 2; ++g) { k3_reset(p, pubG + ((size_t)g * T + t) * st); k3_reset(p, pubG2 + ((size_t)g * T + t) * st); }
+        if (t == 0) k3_reset(p, black);
+        __syncthreads();
+        // ---- initB (fwd2c.h:138-176): origin, then the two boundary chains (one thread each)
+        if (t == 0) {
+            vmf[0].m = 0; vmf[0].n = 0; vmf[0].p = 0;                       // skip 0-th record (:361)
+            vmf[1].m = P.al; vmf[1].n = P.bl; vmf[1].p = 0;                 // origin
+            sm_vmf = 2;
+            k3_setval(colH, 0); K3_DIR(colH) = K3_DIAG; K3_PTR(colH) = 1;
+            const int rr = LQ < -p.lw ? LQ : -p.lw;
+            for (int k = 1; k <= rr; ++k) k3_boundary_col(p, A, B, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
+        }
+        if (t == 32) {
+            k3_setval(rowH, 0); K3_DIR(rowH) = K3_DIAG; K3_PTR(rowH) = 1;
+            const int rr = LS < p.up ? LS : p.up;
+            for (int k = 1; k <= rr; ++k) k3_boundary_row(p, A, B, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
+        }
+        __syncthreads();
+
+        for (int pbase = 0; pbase < LQ; pbase += T) {
+            const int rows = LQ - pbase < T ? LQ - pbase : T;
+            const bool last_pass = pbase + rows == LQ;
+            const int m = pbase + t;
+            const int ia = m + 1;
+            int* const f1 = F1 + (size_t)t * st;
+            int* const f2 = F2 + (size_t)t * st;
+            double pua = 0;
+            bool started = false;
+            const int nsteps = LS + rows - 1;
+            for (int s = 0; s < nsteps; ++s) {
+                const int n = s - t;
+                const int r = n - m;
+                if (t < rows && n >= 0 && n < LS && r >= p.lw && r <= p.up) {
+                    const int ib = n + 1;
+                    if (!started) {
+                        started = true;
+                        pua = k3_unp(A, ia, B, ib, p.u);            // once per row, at its first column (:377)
+                        k3_reset(p, f1);
+                        k3_reset(p, f2);
+                    }
+                    const int g3a = (s + 2) % 3, g3d = (s + 1) % 3, g2a = (s + 1) & 1;
+                    const int* hdiag = n == 0 ? colH + (size_t)m * st
+                                     : (t == 0 ? rowH + (size_t)n * st : pubH + ((size_t)g3d * T + (t - 1)) * st);
+                    const bool above_in = r + 1 <= p.up;
+                    const int* habove = !above_in ? black : (t == 0 ? rowH + (size_t)(n + 1) * st : pubH + ((size_t)g3a * T + (t - 1)) * st);
+                    const int* gabove = (!above_in || m == 0) ? black : (t == 0 ? rowG + (size_t)(n + 1) * st : pubG + ((size_t)g2a * T + (t - 1)) * st);
+                    const int* g2above = (!above_in || m == 0) ? black : (t == 0 ? rowG2 + (size_t)(n + 1) * st : pubG2 + ((size_t)g2a * T + (t - 1)) * st);
+                    const bool left_in = r - 1 >= p.lw;
+                    const int* hleft = n == 0 ? colH + (size_t)(m + 1) * st : (left_in ? pubH + ((size_t)g3a * T + t) * st : black);
+                    int* hout = pubH + ((size_t)(s % 3) * T + t) * st;
+                    int* gout = pubG + ((size_t)(s & 1) * T + t) * st;
+                    int* g2out = pubG2 + ((size_t)(s & 1) * T + t) * st;
+                    const double dab = P.simmat ? P.simmat[(size_t)m * LS + n] : k3_sim(A, B, p, ia, ib);
+                    if (k3_cell(p, A, B, ia, ib, m == 0, n == 0, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
+                                hout, gout, g2out, black)) {
+                        const int id = atomicAdd(&sm_vmf, 1);       // Vmf::add (fwd2c.h:465-467)
+                        if (id < a.vmf_cap) { vmf[id].m = m + P.al; vmf[id].n = n + P.bl; vmf[id].p = K3_PTR(hout); }
+                        K3_PTR(hout) = id;
+                    }
+                    if (t == rows - 1) {
+                        if (!last_pass) {
+                            k3_copy(p, rowH + (size_t)(n + 1) * st, hout);
+                            k3_copy(p, rowG + (size_t)(n + 1) * st, gout);
+                            if (p.Noll == 3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
+                        } else if (n == LS - 1) { sm_last_ptr = K3_PTR(hout); sm_last_val = k3_val(hout); }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // ---- final record + Vmf::traceback (fwd2c.h:475-481, vmf.cc:103-119)
+        if (t == 0) {
+            int* out = a.out_pts + 2 * P.out_off;
+            int cnt = 0;
+            const int nrec = sm_vmf;
+            if (nrec >= a.vmf_cap) cnt = -1;                        // record store overflow: reported, never silent
+            else {
+                out[0] = LQ + P.al; out[1] = LS + P.bl; cnt = 1;
+                for (int q = sm_last_ptr;; q = vmf[q].p) {
+                    if (cnt >= P.out_cap) { cnt = -1; break; }
+                    out[2 * cnt] = vmf[q].m; out[2 * cnt + 1] = vmf[q].n; ++cnt;
+                    if (!vmf[q].p) break;
+                }
+            }
+            a.out_cnt[pi] = cnt;
+            a.out_score[pi] = sm_last_val;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int k3_threads() { return T; }
+int k3_blocks_per_sm() { return 2; }
+
+cudaError_t k3_launch(const K3Args& a, int grid_blocks, cudaStream_t st)
+{
+    k3_fill_kernel<<<grid_blocks, T, 0, st>>>(a);
+    return cudaGetLastError();
+}

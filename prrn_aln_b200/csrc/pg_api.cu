@@ -63,6 +63,8 @@ extern "C" int pg_create(int device, pg_context** out)
     c->dirs_cap = c->trace_cap = c->seqblob_cap = c->planbuf_cap = 0;
     c->d_bnd = c->d_scratch = c->d_ends = nullptr;
     c->bnd_cap = c->scratch_cap = c->ends_cap = 0;
+    c->d_gblob = c->d_garena = c->d_gvmf = c->d_gout = nullptr;
+    c->gblob_cap = c->garena_cap = c->gvmf_cap = c->gout_cap = 0;
     c->items_cap = c->mtx_cap = c->self_cap = c->rowbuf_cap = c->out_cap = c->pairs_cap = 0;
     c->d_counter = nullptr;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -83,6 +85,7 @@ extern "C" void pg_destroy(pg_context* c)
     cudaFree(c->d_items); cudaFree(c->d_mtx); cudaFree(c->d_self); cudaFree(c->d_rowbuf);
     cudaFree(c->d_out); cudaFree(c->d_pairs); cudaFree(c->d_counter); cudaFree(c->d_dirs); cudaFree(c->d_trace); cudaFree(c->d_seqblob); cudaFree(c->d_planbuf);
     cudaFree(c->d_bnd); cudaFree(c->d_scratch); cudaFree(c->d_ends);
+    cudaFree(c->d_gblob); cudaFree(c->d_garena); cudaFree(c->d_gvmf); cudaFree(c->d_gout);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -96,6 +99,10 @@ static int ensure_cap(pg_context* c, void** p, size_t* cap, size_t need)
     *cap = n;
     return PG_OK;
 }
+
+// internal linkage helpers for the other translation units of the library (pg_groups.cu)
+int pg_int_fail(pg_context* ctx, int code, const char* msg) { return fail(ctx, code, msg); }
+int pg_int_ensure_cap(pg_context* c, void** p, size_t* cap, size_t need) { return ensure_cap(c, p, cap, need); }
 
 // ---- parameter / matrix validation for the integer kernels -------------------------------------
 struct IntScoring {

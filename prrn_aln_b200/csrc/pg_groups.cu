@@ -1,0 +1,238 @@
+// pg_groups.cu -- the extern "C" layer of the group-to-group path (include/prrn_gpu.h: pg_align_groups):
+// argument checks, flattening of the staged groups into one HBM blob, launch of kernel K3
+// (k3_groups.cu), collection of scores and corner lists.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "pg_internal.h"
+
+static inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// stripe() (src/aln2.cc:156-174) in absolute diagonal coordinates
+static void group_band(const pg_group* a, const pg_group* b, int sh, int* lw, int* up)
+{
+    if (sh < 0) {
+        int shorter = std::min(a->right - a->left, b->right - b->left);
+        sh = -sh * shorter / 100;
+    }
+    int hi = b->right - a->right, lo = b->left - a->left;
+    if (hi < lo) std::swap(hi, lo);
+    hi += sh; lo -= sh;
+    hi = std::min(hi, b->right - a->left);
+    lo = std::max(lo, b->left - a->right);
+    *lw = lo; *up = hi;
+}
+
+extern "C" int64_t pg_group_cells(const pg_group* a, const pg_group* b, int32_t sh)
+{
+    if (!a || !b) return 0;
+    int lw, up;
+    group_band(a, b, sh, &lw, &up);
+    int64_t c = 0;
+    for (int m = a->left; m < a->right; ++m) {
+        int n0 = std::max(m + lw, b->left), n9 = std::min(m + up + 1, b->right);
+        if (n9 > n0) c += n9 - n0;
+    }
+    return c;
+}
+
+namespace {
+struct SideOff { size_t cfq, efq, vec, glen, gfreq, sfq, tfq, rfq; };
+
+size_t place_side(const pg_group& g, int kdim, size_t off, SideOff* so)
+{
+    const size_t npos = (size_t)(g.right - g.left + 1);
+    const bool lists = g.sfq && g.tfq && g.rfq && g.glen && g.gfreq && g.npool > 0;
+    so->cfq = off; off = up16(off + 8 * npos);
+    so->efq = off; off = up16(off + 8 * npos);
+    so->vec = off; off = up16(off + 8 * npos * kdim);
+    so->gfreq = off; off = up16(off + 8 * (lists ? (size_t)g.npool : 1));
+    so->glen = off; off = up16(off + 4 * (lists ? (size_t)g.npool : 1));
+    so->sfq = off; off = up16(off + 4 * npos);
+    so->tfq = off; off = up16(off + 4 * npos);
+    so->rfq = off; off = up16(off + 4 * npos);
+    return off;
+}
+
+void fill_side(const pg_group& g, int kdim, const SideOff& so, char* h)
+{
+    const size_t npos = (size_t)(g.right - g.left + 1);
+    const bool lists = g.sfq && g.tfq && g.rfq && g.glen && g.gfreq && g.npool > 0;
+    memcpy(h + so.cfq, g.cfq, 8 * npos);
+    memcpy(h + so.efq, g.efq, 8 * npos);
+    memcpy(h + so.vec, g.vec, 8 * npos * kdim);
+    if (lists) {
+        memcpy(h + so.gfreq, g.gfreq, 8 * (size_t)g.npool);
+        memcpy(h + so.glen, g.glen, 4 * (size_t)g.npool);
+        memcpy(h + so.sfq, g.sfq, 4 * npos);
+        memcpy(h + so.tfq, g.tfq, 4 * npos);
+        memcpy(h + so.rfq, g.rfq, 4 * npos);
+    } else {
+        *(double*)(h + so.gfreq) = 0;
+        *(int32_t*)(h + so.glen) = -1;
+        memset(h + so.sfq, 0xff, 4 * npos);
+        memset(h + so.tfq, 0xff, 4 * npos);
+        memset(h + so.rfq, 0xff, 4 * npos);
+    }
+}
+
+K3Group dev_side(const pg_group& g, const SideOff& so, const char* d)
+{
+    K3Group k;
+    k.cfq = (const double*)(d + so.cfq); k.efq = (const double*)(d + so.efq);
+    k.prof = k.freq = (const double*)(d + so.vec);
+    k.glen = (const int32_t*)(d + so.glen); k.gfreq = (const double*)(d + so.gfreq);
+    k.sfq = (const int32_t*)(d + so.sfq); k.tfq = (const int32_t*)(d + so.tfq); k.rfq = (const int32_t*)(d + so.rfq);
+    k.L = g.right - g.left;
+    k.nils = g.nils;
+    return k;
+}
+}  // namespace
+
+extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
+                               double* out_scores, int64_t** out_offs, pg_skl** out_pts)
+{
+    if (!c) return PG_ERR_ARG;
+    if (npairs < 0 || !out_offs || !out_pts || (npairs && (!a || !b || !prm || !out_scores)))
+        return pg_int_fail(c, PG_ERR_ARG, "pg_align_groups: NULL / bad argument");
+    *out_offs = nullptr;
+    *out_pts = nullptr;
+    if (npairs > 0x3fffffff) return pg_int_fail(c, PG_ERR_ARG, "pg_align_groups: too many pairs in one call");
+    int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * (size_t)(npairs + 1));
+    if (!offs) return pg_int_fail(c, PG_ERR_ARG, "out of host memory");
+    offs[0] = 0;
+    if (npairs == 0) { *out_offs = offs; *out_pts = (pg_skl*)malloc(sizeof(pg_skl)); return PG_OK; }
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) { free(offs); return pg_int_fail(c, PG_ERR_CUDA, cudaGetErrorString(e)); }
+
+    // ---- validate, lay out the blob
+    std::vector<SideOff> soa(npairs), sob(npairs);
+    std::vector<K3Pair> pairs(npairs);
+    std::vector<int64_t> cells(npairs), outoff(npairs + 1);
+    size_t blob = 0, arena_words = 0;
+    int64_t max_cells = 0;
+    outoff[0] = 0;
+    for (int64_t i = 0; i < npairs; ++i) {
+        const pg_group& A = a[i];
+        const pg_group& B = b[i];
+        const pg_gparams& P = prm[i];
+        int mode;
+        switch (P.alnmode) {
+        case 6: mode = 0; break;
+        case 7: case 8: mode = 1; break;
+        case 9: mode = 2; break;
+        default:
+            free(offs);
+            return pg_int_fail(c, PG_ERR_UNSUPPORTED, "pg_align_groups: alnmode is not one of NGP_ALB / HLF_ALB / RHF_ALB / GPF_ALB "
+                                                      "(rectangle, naive, local and spliced modes are not built yet)");
+        }
+        if (A.left < 0 || A.right > A.len || A.left >= A.right || B.left < 0 || B.right > B.len || B.left >= B.right ||
+            !A.cfq || !A.efq || !A.vec || !B.cfq || !B.efq || !B.vec || P.kdim < 1 || P.kdim > 64 || P.Noll < 2 || P.Noll > 3) {
+            free(offs);
+            return pg_int_fail(c, PG_ERR_ARG, "pg_align_groups: bad group window / missing arrays (align2 handles empty windows "
+                                              "with nogap_skl before alignC)");
+        }
+        if ((mode >= 1 && !(A.sfq && A.tfq && A.rfq)) || (mode == 2 && !(B.sfq && B.tfq && B.rfq))) {
+            free(offs);
+            return pg_int_fail(c, PG_ERR_ARG, "pg_align_groups: gap-profile lists missing for a half / full profile mode");
+        }
+        blob = place_side(A, P.kdim, blob, &soa[i]);
+        blob = place_side(B, P.kdim, blob, &sob[i]);
+        K3Prm& kp = pairs[i].prm;
+        kp.mode = mode; kp.Noll = P.Noll; kp.codonk1 = P.codonk1; kp.kdim = P.kdim;
+        int lw, up;
+        group_band(&A, &B, P.sh, &lw, &up);
+        const int r0 = B.left - A.left;
+        kp.lw = lw - r0; kp.up = up - r0;
+        kp.capa = std::max(A.hetero, 0) + 3; kp.capb = std::max(B.hetero, 0) + 3;
+        kp.u = (double)(float)P.u;
+        kp.wgop = P.Weighted_GOP; kp.bgop = P.Basic_GOP;
+        kp.u2divu1 = P.BasicGEP < 0 ? P.LongGEP / P.BasicGEP : 0;      // fwd2c.h:85-86
+        kp.v2divv1 = P.BasicGOP < 0 ? P.LongGOP / P.BasicGOP : 0;
+        const int LQ = A.right - A.left, LS = B.right - B.left;
+        const size_t st = (size_t)k3_stride(kp.capa, kp.capb);
+        arena_words = std::max(arena_words, st * (size_t)(3 * (LS + 2) + (LQ + 2) + 9 * K3_THREADS + 1));
+        cells[i] = pg_group_cells(&A, &B, P.sh);
+        max_cells = std::max(max_cells, cells[i]);
+        pairs[i].al = A.left; pairs[i].bl = B.left;
+        pairs[i].simmat = nullptr;
+        pairs[i].out_cap = LQ + LS + 4;
+        pairs[i].out_off = outoff[i];
+        pairs[i].pad = 0;
+        outoff[i + 1] = outoff[i] + pairs[i].out_cap;
+    }
+    const int grid = (int)std::min<int64_t>(npairs, (int64_t)c->sm_count * k3_blocks_per_sm());
+    const int64_t vmf_cap = max_cells + 8;
+    if (vmf_cap > 0x7fffffff) { free(offs); return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: DP matrix too large for the path store"); }
+
+    // ---- stage
+    int rc = pg_int_ensure_cap(c, &c->d_gblob, &c->gblob_cap, blob + sizeof(K3Pair) * (size_t)npairs + 256);
+    if (!rc) rc = pg_int_ensure_cap(c, &c->d_garena, &c->garena_cap, arena_words * 4 * (size_t)grid);
+    if (!rc) rc = pg_int_ensure_cap(c, &c->d_gvmf, &c->gvmf_cap, sizeof(K3Vmf) * (size_t)vmf_cap * grid);
+    const size_t o_pts = 0, o_cnt = up16(o_pts + 8 * (size_t)outoff[npairs]), o_scr = up16(o_cnt + 4 * (size_t)npairs),
+                 obytes = up16(o_scr + 8 * (size_t)npairs);
+    if (!rc) rc = pg_int_ensure_cap(c, &c->d_gout, &c->gout_cap, obytes);
+    if (rc) { free(offs); return rc; }
+    std::vector<char> h(blob + sizeof(K3Pair) * (size_t)npairs);
+    char* d = (char*)c->d_gblob;
+    // heaviest pairs first (persistent CTAs finish together); the kernel indexes results by this order
+    std::vector<int32_t> order(npairs);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return cells[x] > cells[y]; });
+    std::vector<K3Pair> sorted(npairs);
+    for (int64_t i = 0; i < npairs; ++i) {
+        fill_side(a[i], prm[i].kdim, soa[i], h.data());
+        fill_side(b[i], prm[i].kdim, sob[i], h.data());
+        pairs[i].a = dev_side(a[i], soa[i], d);
+        pairs[i].b = dev_side(b[i], sob[i], d);
+    }
+    for (int64_t k = 0; k < npairs; ++k) sorted[k] = pairs[order[k]];
+    memcpy(h.data() + blob, sorted.data(), sizeof(K3Pair) * (size_t)npairs);
+    K3Args ka;
+    memset(&ka, 0, sizeof(ka));
+    ka.pairs = (const K3Pair*)(d + blob);
+    ka.npairs = (int32_t)npairs;
+    ka.counter = c->d_counter;
+    ka.arena = (int*)c->d_garena;
+    ka.arena_words = (int64_t)arena_words;
+    ka.vmf = (K3Vmf*)c->d_gvmf;
+    ka.vmf_cap = (int32_t)vmf_cap;
+    char* go = (char*)c->d_gout;
+    ka.out_pts = (int32_t*)(go + o_pts);
+    ka.out_cnt = (int32_t*)(go + o_cnt);
+    ka.out_score = (double*)(go + o_scr);
+    std::vector<int32_t> h_pts(2 * (size_t)outoff[npairs]), h_cnt(npairs);
+    std::vector<double> h_scr(npairs);
+    e = cudaMemcpyAsync(d, h.data(), h.size(), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counter, 0, sizeof(int32_t), c->stream);
+    if (e == cudaSuccess) e = k3_launch(ka, grid, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_pts.data(), ka.out_pts, 8 * (size_t)outoff[npairs], cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt.data(), ka.out_cnt, 4 * (size_t)npairs, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_scr.data(), ka.out_score, 8 * (size_t)npairs, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { free(offs); return pg_int_fail(c, PG_ERR_CUDA, (std::string("pg_align_groups: ") + cudaGetErrorString(e)).c_str()); }
+    // ---- back to the caller's order
+    std::vector<int32_t> cnt_by_orig(npairs);
+    for (int64_t k = 0; k < npairs; ++k) {
+        if (h_cnt[k] < 0) { free(offs); return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: path record store overflow"); }
+        cnt_by_orig[order[k]] = h_cnt[k];
+    }
+    for (int64_t i = 0; i < npairs; ++i) offs[i + 1] = offs[i] + cnt_by_orig[i];
+    pg_skl* pts = (pg_skl*)malloc(sizeof(pg_skl) * (size_t)std::max<int64_t>(offs[npairs], 1));
+    if (!pts) { free(offs); return pg_int_fail(c, PG_ERR_ARG, "out of host memory"); }
+    for (int64_t k = 0; k < npairs; ++k) {
+        const int64_t i = order[k];
+        const int32_t* src = h_pts.data() + 2 * pairs[i].out_off;
+        for (int q = 0; q < h_cnt[k]; ++q) { pts[offs[i] + q].m = src[2 * q]; pts[offs[i] + q].n = src[2 * q + 1]; }
+        out_scores[i] = h_scr[k];
+    }
+    *out_offs = offs;
+    *out_pts = pts;
+    return PG_OK;
+}

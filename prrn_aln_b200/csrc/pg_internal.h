@@ -137,6 +137,31 @@ struct K2Args {
     int32_t* out_cnt;           // [npairs]
 };
 
+// group-to-group alignment kernel (k3_groups.cu)
+#include "k3_core.cuh"
+#define K3_THREADS 256
+struct K3Pair {
+    K3Group a, b;               // device pointers
+    K3Prm prm;
+    const double* simmat;       // optional precomputed sim2 matrix [LQ][LS] (kernel K4), else nullptr
+    int32_t al, bl;             // a.left, b.left (absolute coordinates of the corner list)
+    int64_t out_off;            // corner output offset (in corners)
+    int32_t out_cap;
+    int32_t pad;
+};
+struct K3Args {
+    const K3Pair* pairs;
+    int32_t npairs;
+    int32_t* counter;
+    int* arena;                 // per-CTA record arena
+    int64_t arena_words;
+    K3Vmf* vmf;                 // per-CTA path record store
+    int32_t vmf_cap;
+    int32_t* out_pts;           // corner lists (2 ints per corner), Vmf back-walk order
+    int32_t* out_cnt;           // [npairs] corners, -1 on overflow
+    double* out_score;          // [npairs]
+};
+
 struct pg_dev_seqs {
     PgDevSeqs v;
     void* blob;                 // single device allocation holding everything
@@ -175,8 +200,15 @@ struct pg_context {
     void* d_bnd; size_t bnd_cap;
     void* d_scratch; size_t scratch_cap;
     void* d_ends; size_t ends_cap;
+    void* d_gblob; size_t gblob_cap;
+    void* d_garena; size_t garena_cap;
+    void* d_gvmf; size_t gvmf_cap;
+    void* d_gout; size_t gout_cap;
     int32_t* d_counter;
 };
+
+int pg_int_fail(pg_context* ctx, int code, const char* msg);
+int pg_int_ensure_cap(pg_context* c, void** p, size_t* cap, size_t need);
 
 // kernels (k1_score.cu)
 cudaError_t k1_launch(const K1Args& a, int grid_blocks, cudaStream_t st);
@@ -202,5 +234,9 @@ cudaError_t k2_trace_launch(const K2Args& a, int npairs, cudaStream_t st);
 int k2_rows_per_lane();
 int k2_warps_per_block();
 int k2_blocks_per_sm();
+// k3_groups.cu
+cudaError_t k3_launch(const K3Args& a, int grid_blocks, cudaStream_t st);
+int k3_threads();
+int k3_blocks_per_sm();
 // dpx_peak.cu
 cudaError_t dpx_peak_run(int sm_count, cudaStream_t st, double* gops_s32, double* gops_s16x2);

@@ -1,0 +1,83 @@
+"""Parity of kernel K3 (group-to-group alignC with gap-profile state, k3_groups.cu) through the C ABI
+(pg_align_groups) against goldens frozen from the unmodified reference: the reference's own staged
+inputs (ref_driver galign dump) go in, alignC's DP score and raw corner list must come out.
+Tolerance (BASELINE north_star): scores within 1e-5 relative -- the kernel computes in double and
+contracts sim2 in one order for all variants --, corner lists identical."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names
+import prrn_aln_b200 as P
+from prrn_aln_b200 import groups as G
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+
+REL_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = P.Context(0)
+    yield c
+    c.close()
+
+
+def stage_golden(g, sh=None):
+    pm, pc, h = g["pwdm"], g["pwdc"], g["header"]
+    A, B = G.stage_pair(g["groups"][0], g["groups"][1], pm["a_mode"], pm["b_mode"], g["matrix"], dxd=(pm["DvsP"] == 0))
+    gp = P.gparams_from_pwd(pm["alnmode"], pm["Noll"], pm["codonk1"], int(h["sh"]) if sh is None else sh, A["vec"].shape[1],
+                            float(h["u"]), float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
+    return A, B, gp
+
+
+@pytest.mark.parametrize("name", golden_names("galign_"))
+def test_group_goldens(ctx, name):
+    g = golden(name)
+    A, B, gp = stage_golden(g)
+    scores, pts = ctx.align_groups([(A, B, gp)])
+    want = g["alignc"]
+    assert abs(scores[0] - want["score"]) <= REL_TOL * max(1.0, abs(want["score"]))
+    assert pts[0].tolist() == want["skl"]
+    lw, up, _ = g["window"]
+    a, b = g["groups"]
+    cells = sum(max(0, min(m + up + 1, b["right"]) - max(m + lw, b["left"])) for m in range(a["left"], a["right"]))
+    assert P.group_cells(A, B, gp.sh) == cells
+
+
+def test_batch_of_all_goldens_in_one_call(ctx):
+    """One launch over every golden pair (different modes, sizes, capacities), twice over: results must
+    not depend on which CTA / arena a pair lands on."""
+    gs = [golden(n) for n in golden_names("galign_")]
+    staged = [stage_golden(g) for g in gs] * 3
+    scores, pts = ctx.align_groups(staged)
+    for k, (s, p) in enumerate(zip(scores, pts)):
+        want = gs[k % len(gs)]["alignc"]
+        assert abs(s - want["score"]) <= REL_TOL * max(1.0, abs(want["score"])), gs[k % len(gs)]["name"]
+        assert p.tolist() == want["skl"], gs[k % len(gs)]["name"]
+
+
+def test_matches_oracle_on_other_bands(ctx, oracle):
+    """Same staged inputs, other band shoulders than the golden's: the oracle is the checker."""
+    for name in ("galign_gpf_prof12_raw5_wt", "galign_hlf_prof10_single", "galign_gpf_twopiece", "galign_c1_multi_ab_f64"):
+        g = golden(name)
+        OA, OB = oracle.group_arrays(g["groups"][0]), oracle.group_arrays(g["groups"][1])
+        for sh in (-100, -25, 3, 0):
+            A, B, gp = stage_golden(g, sh=sh)
+            want_s, want_p, cells = oracle.align_groups(OA, OB, np.array(g["matrix"]), oracle.gparams_from_dump(g, sh=sh))
+            scores, pts = ctx.align_groups([(A, B, gp)])
+            assert abs(scores[0] - want_s) <= REL_TOL * max(1.0, abs(want_s)), (name, sh)
+            assert [tuple(x) for x in pts[0].tolist()] == want_p, (name, sh)
+            assert P.group_cells(A, B, sh) == cells
+
+
+def test_bad_arguments_fail_loudly(ctx):
+    g = golden("galign_gpf_raw3x3")
+    A, B, gp = stage_golden(g)
+    gp.alnmode = 4          # GPF_ALN (rectangle): not built
+    with pytest.raises(P.PgError) as e:
+        ctx.align_groups([(A, B, gp)])
+    assert e.value.code == 4

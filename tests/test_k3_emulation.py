@@ -1,0 +1,67 @@
+"""k3_core.cuh (the per-cell code of kernel K3: gap-profile lists, gapopen / update for DPunit,
+DPunit_hf, DPunit_pf, two-piece states) driven by a host emulation of the CTA's anti-diagonal
+wavefront (tests/host_emul/k3_emul.cc: slot rotation, band guards, pass hand-over, boundary chains,
+path record store) against the goldens frozen from the reference.  CPU only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden, golden_names
+from prrn_aln_b200 import groups as G
+
+
+class K3Group(C.Structure):
+    _fields_ = [("cfq", C.c_void_p), ("efq", C.c_void_p), ("prof", C.c_void_p), ("freq", C.c_void_p),
+                ("glen", C.c_void_p), ("gfreq", C.c_void_p), ("sfq", C.c_void_p), ("tfq", C.c_void_p),
+                ("rfq", C.c_void_p), ("L", C.c_int32), ("nils", C.c_int32)]
+
+
+class K3Prm(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("Noll", C.c_int32), ("codonk1", C.c_int32), ("lw", C.c_int32), ("up", C.c_int32),
+                ("capa", C.c_int32), ("capb", C.c_int32), ("kdim", C.c_int32), ("u", C.c_double), ("wgop", C.c_double),
+                ("bgop", C.c_double), ("u2divu1", C.c_double), ("v2divv1", C.c_double)]
+
+
+@pytest.fixture(scope="module")
+def emul3():
+    src = os.path.join(ROOT, "tests", "host_emul", "k3_emul.cc")
+    out = os.path.join(ROOT, "tests", "host_emul", "libk3emul.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", out, src])
+    L = C.CDLL(out)
+    L.k3_emul_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    return L
+
+
+def _k3group(S):
+    g = K3Group(S["cfq"].ctypes.data, S["efq"].ctypes.data, S["vec"].ctypes.data, S["vec"].ctypes.data,
+                S["glen"].ctypes.data, S["gfreq"].ctypes.data, S["sfq"].ctypes.data, S["tfq"].ctypes.data,
+                S["rfq"].ctypes.data, S["right"] - S["left"], S["nils"])
+    g._keep = S
+    return g
+
+
+@pytest.mark.parametrize("name", golden_names("galign_"))
+def test_wavefront_emulation_matches_reference(emul3, name):
+    d = golden(name)
+    pm, pc, h = d["pwdm"], d["pwdc"], d["header"]
+    A, B = G.stage_pair(d["groups"][0], d["groups"][1], pm["a_mode"], pm["b_mode"], d["matrix"], dxd=(pm["DvsP"] == 0))
+    lw, up, _ = d["window"]
+    r0 = B["left"] - A["left"]
+    mode = {6: 0, 7: 1, 8: 1, 9: 2}[pm["alnmode"]]
+    bgep, lgep, bgop, lgop = pc["BasicGEP"], pc["LongGEP"], pc["BasicGOP"], pc["LongGOP"]
+    p = K3Prm(mode, pm["Noll"], pm["codonk1"], lw - r0, up - r0, max(A["hetero"], 0) + 3, max(B["hetero"], 0) + 3,
+              A["vec"].shape[1], float(np.float32(float(h["u"]))), -float(np.float32(float(h["v"]))), pc["vgop1"],
+              lgep / bgep if bgep < 0 else 0.0, lgop / bgop if bgop < 0 else 0.0)
+    want = d["alignc"]
+    for T in (256, 7, 33):      # rows per pass: one pass, many passes, ragged last pass
+        out = np.zeros(2 * (A["len"] + B["len"] + 8), np.int32)
+        sc = C.c_double(0)
+        ga, gb = _k3group(A), _k3group(B)
+        n = emul3.k3_emul_align(C.byref(ga), C.byref(gb), C.byref(p), T, A["left"], B["left"], C.byref(sc),
+                                out.ctypes.data, len(out) // 2)
+        assert n > 0
+        assert abs(sc.value - want["score"]) <= 1e-5 * max(1.0, abs(want["score"])), T
+        assert [[int(out[2 * i]), int(out[2 * i + 1])] for i in range(n)] == want["skl"], T
