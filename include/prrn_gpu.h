@@ -155,6 +155,9 @@ int64_t pg_calcdist_cells(const pg_seqs *seqs, const pg_params *prm, int64_t k_b
  * number of (query pair, subject) slots, and per-k coverage counts (each must be 1).  Test aid. */
 int pg_debug_packed_plan(const pg_seqs *seqs, int64_t k_begin, int64_t k_end, int32_t grid_blocks,
                          int64_t *nitems, int64_t *nslots, uint8_t *cover);
+/* Device time (CUDA events on the library's stream) of the fill kernel(s) of the last pg_align_groups
+ * call, in milliseconds; -1 if none.  Measurement aid for bench scripts. */
+double pg_last_kernel_ms(pg_context *ctx);
 /* Register-only DPX micro-benchmark: measured issue rate of __viaddmax_s32 / __vimax3_s32 chains,
  * in 1e9 thread-instructions per second for the whole device; the roofline denominator. */
 int pg_dpx_peak(pg_context *ctx, double *gops_s32, double *gops_s16x2);

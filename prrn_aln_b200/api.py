@@ -111,6 +111,8 @@ def load_library():
                                   C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32))]
     L.pg_group_cells.restype = C.c_int64
     L.pg_group_cells.argtypes = [C.POINTER(_PgGroup), C.POINTER(_PgGroup), C.c_int32]
+    L.pg_last_kernel_ms.restype = C.c_double
+    L.pg_last_kernel_ms.argtypes = [C.c_void_p]
     L.pg_free.argtypes = [C.c_void_p]
     L.pg_free.restype = None
     L.pg_calcdist.argtypes = [C.c_void_p, C.POINTER(_PgSeqs), C.POINTER(Params), C.c_void_p, C.c_int32,
@@ -284,6 +286,9 @@ class Context:
         self._check(self.L.pg_calcdist_dev(self.h, dseqs, C.byref(prm), m.ctypes.data, m.shape[0], k_begin,
                                            k_end, C.c_void_p(d_out_ptr), C.c_void_p(stream or 0), C.byref(nl)))
         return nl.value
+
+    def last_kernel_ms(self):
+        return self.L.pg_last_kernel_ms(self.h)
 
     def dpx_peak(self):
         a, b = C.c_double(0), C.c_double(0)

@@ -5,17 +5,20 @@
 // Shared by the CUDA kernel (k3_groups.cu) and the host emulation (tests/host_emul/k3_emul.cc).
 //
 // A DP record (the reference's DPunit_hf / DPunit_pf) is a run of 32-bit words
-//     [0-1] val (double)  [2] dir  [3] ptr  [4] glb  [5] -  [6 ..) dla: (glen, nins) pairs  [..) dlb
-// with list capacities fixed per alignment (hetero + 3), so records can live in any memory space and
-// be addressed by (slot, row).  Arithmetic is double for both VTYPE flavours (the group path is
-// floating point with a 1e-5 relative tolerance: BASELINE north_star).
+//     [0-1] val (double)  [2] ptr  [3] dir | glb << 8  [4 ..) dla: (glen, nins) u16 pairs  [..) dlb
+// with list capacities fixed per alignment (hetero + 3), so records can live in any memory space
+// (shared memory for the wavefront, HBM/L2 for the parked rows) and be addressed by (slot, row).
+// Gap lengths / insertion counts are 16-bit: sequences up to 65,000 columns (checked by the host).
+// Arithmetic is double for both VTYPE flavours (the group path is floating point with a 1e-5 relative
+// tolerance: BASELINE north_star).
 #pragma once
 #include <stdint.h>
 
 #include "k1_core.cuh"
 
 #define K3_NEVSEL (-(1.7976931348623157e+308 / 16 * 7))
-#define K3_LAST 0x7fffffff
+#define K3_LAST 0xffff
+typedef unsigned short k3u16;
 
 enum { K3_DIAG = 2, K3_NEWD = 3, K3_VERT = 4, K3_HORI = 8, K3_NEWV = 12, K3_NEWH = 13 };   // aln.h:47-52
 PG_HD bool k3_isdiag(int d) { d &= 15; return d == 2 || d == 3; }
@@ -49,33 +52,34 @@ struct K3Prm {
 };
 
 // ---- record access -------------------------------------------------------------------------------
-PG_HD int k3_stride(int capa, int capb) { return 6 + 2 * (capa + capb); }
+PG_HD int k3_stride(int capa, int capb) { return (4 + capa + capb + 1) & ~1; }      // even: val stays 8-byte aligned
 PG_HD double k3_val(const int* r) { return *reinterpret_cast<const double*>(r); }
 PG_HD void k3_setval(int* r, double v) { *reinterpret_cast<double*>(r) = v; }
-#define K3_DIR(r) ((r)[2])
-#define K3_PTR(r) ((r)[3])
-#define K3_GLB(r) ((r)[4])
-PG_HD int* k3_dla(int* r) { return r + 6; }
-PG_HD const int* k3_dla(const int* r) { return r + 6; }
-PG_HD int* k3_dlb(int* r, int capa) { return r + 6 + 2 * capa; }
-PG_HD const int* k3_dlb(const int* r, int capa) { return r + 6 + 2 * capa; }
+#define K3_PTR(r) ((r)[2])
+PG_HD int k3_dir(const int* r) { return r[3] & 0xff; }
+PG_HD int k3_glb(const int* r) { return (int)((unsigned)r[3] >> 8); }
+PG_HD void k3_setdg(int* r, int dir, int glb) { r[3] = dir | (glb << 8); }
+PG_HD k3u16* k3_dla(int* r) { return reinterpret_cast<k3u16*>(r + 4); }
+PG_HD const k3u16* k3_dla(const int* r) { return reinterpret_cast<const k3u16*>(r + 4); }
+PG_HD k3u16* k3_dlb(int* r, int capa) { return reinterpret_cast<k3u16*>(r + 4 + capa); }
+PG_HD const k3u16* k3_dlb(const int* r, int capa) { return reinterpret_cast<const k3u16*>(r + 4 + capa); }
 
 // IDELTA lists: pairs (glen, nins), terminated by glen == K3_LAST (gfreq.h:26,31)
-PG_HD void k3_cleardelta(int* d) { d[0] = 0; d[1] = 0; d[2] = K3_LAST; d[3] = 0; }       // gfreq.cc:556
-PG_HD void k3_copydelta(int* dst, const int* src)
+PG_HD void k3_cleardelta(k3u16* d) { d[0] = 0; d[1] = 0; d[2] = K3_LAST; d[3] = 0; }       // gfreq.cc:556
+PG_HD void k3_copydelta(k3u16* dst, const k3u16* src)
 {   // gfreq.cc:548-554
     do { dst[0] = src[0]; dst[1] = src[1]; dst += 2; src += 2; } while (src[0] < K3_LAST);
     dst[0] = src[0]; dst[1] = src[1];
 }
-PG_HD void k3_incdelta(int* dlt, const int* dln, int n)
+PG_HD void k3_incdelta(k3u16* dlt, const k3u16* dln, int n)
 {   // gfreq.cc:595-602 (dlt may alias dln)
-    do { dlt[0] = dln[0]; dlt[1] = dln[1] + n; dlt += 2; dln += 2; } while (dln[0] < K3_LAST);
+    do { dlt[0] = dln[0]; dlt[1] = (k3u16)(dln[1] + n); dlt += 2; dln += 2; } while (dln[0] < K3_LAST);
     dlt[0] = dln[0]; dlt[1] = dln[1];
 }
 // gfreq.cc:567-584: filter the dynamic gap state through a column's static gap state; dlt may alias dln
-PG_HD void k3_newdelta(int* dlt, const int32_t* glen, const int* dln)
+PG_HD void k3_newdelta(k3u16* dlt, const int32_t* glen, const k3u16* dln)
 {
-    int* dst = dlt;
+    k3u16* dst = dlt;
     int tg = 0, tn = 0;
     if (glen)
         for (; *glen >= 0; ++glen) {
@@ -84,16 +88,16 @@ PG_HD void k3_newdelta(int* dlt, const int32_t* glen, const int* dln)
                 while (gl >= dln[2]) dln += 2;
                 if (dln[1] > tn) {
                     const int nins = dln[1];
-                    dst[0] = tg; dst[1] = tn; dst += 2;
+                    dst[0] = (k3u16)tg; dst[1] = (k3u16)tn; dst += 2;
                     tn = nins;
                     tg = gl + 1;
                 }
             }
         }
-    dst[0] = tg; dst[1] = tn;
+    dst[0] = (k3u16)tg; dst[1] = (k3u16)tn;
     dst[2] = K3_LAST; dst[3] = 0;
 }
-PG_HD int k3_gaplensd(int gl, const int* dl)
+PG_HD int k3_gaplensd(int gl, const k3u16* dl)
 {   // gfreq.h:67-71
     while (gl >= dl[2]) dl += 2;
     return gl + dl[1];
@@ -112,7 +116,7 @@ PG_HD K3List k3_list(const K3Group& g, const int32_t* offs, int ix)
 PG_HD bool k3_neo(const K3List& l, int i) { return l.glen && l.glen[i] >= 0; }
 
 // newgap(cf, dlc, df, dld), gfreq.cc:507-521
-PG_HD double k3_newgap4(const K3List& cf, const int* dlc, const K3List& df, const int* dld)
+PG_HD double k3_newgap4(const K3List& cf, const k3u16* dlc, const K3List& df, const k3u16* dld)
 {
     double g = 0;
     int ic = 0;
@@ -126,7 +130,7 @@ PG_HD double k3_newgap4(const K3List& cf, const int* dlc, const K3List& df, cons
     return g;
 }
 // PwdM::newgap1(acf, dla, glb), maln.h:288-291 with newgap(cf, dlc, j) gfreq.cc:523-531, newgapc maln.h:270
-PG_HD double k3_newgap1(double wgop, const K3List& acf, const int* dla, int glb)
+PG_HD double k3_newgap1(double wgop, const K3List& acf, const k3u16* dla, int glb)
 {
     if (!k3_neo(acf, 0)) return 0;
     if (k3_neo(acf, 1)) {
@@ -137,7 +141,7 @@ PG_HD double k3_newgap1(double wgop, const K3List& acf, const int* dla, int glb)
     return (dla[1] + acf.glen[0] >= glb) ? wgop * acf.freq[0] : 0;
 }
 // PwdM::newgap2(adf, glb, dla), maln.h:297-300 with newgap(df, i, dld) gfreq.cc:533-544, newgapd maln.h:278
-PG_HD double k3_newgap2(double wgop, const K3List& adf, int glb, const int* dla)
+PG_HD double k3_newgap2(double wgop, const K3List& adf, int glb, const k3u16* dla)
 {
     if (!k3_neo(adf, 0)) return 0;
     if (k3_neo(adf, 1)) {
@@ -169,18 +173,18 @@ PG_HD double k3_gapopen(const K3Prm& p, const K3Group& a, const K3Group& b, cons
 {
     if (p.mode == 0) {
         double axb = 0;
-        if (d3 > 0) { if (!k3_isvert(K3_DIR(r))) axb = a.cfq[ia] * b.efq[ib]; }
-        else if (d3 < 0) { if (!k3_ishori(K3_DIR(r))) axb = b.cfq[ib] * a.efq[ia]; }
+        if (d3 > 0) { if (!k3_isvert(k3_dir(r))) axb = a.cfq[ia] * b.efq[ib]; }
+        else if (d3 < 0) { if (!k3_ishori(k3_dir(r))) axb = b.cfq[ib] * a.efq[ia]; }
         else return 0;
         return p.bgop * axb;
     }
     if (p.mode == 1) {
-        if (d3 == 0) return k3_newgap2(p.wgop, k3_list(a, a.tfq, ia), K3_GLB(r), k3_dla(r));
-        if (d3 > 0) return k3_newgap1(p.wgop, k3_list(a, a.sfq, ia), k3_dla(r), K3_GLB(r));
-        return k3_newgap2(p.wgop, k3_list(a, a.rfq, ia), K3_GLB(r), k3_dla(r));
+        if (d3 == 0) return k3_newgap2(p.wgop, k3_list(a, a.tfq, ia), k3_glb(r), k3_dla(r));
+        if (d3 > 0) return k3_newgap1(p.wgop, k3_list(a, a.sfq, ia), k3_dla(r), k3_glb(r));
+        return k3_newgap2(p.wgop, k3_list(a, a.rfq, ia), k3_glb(r), k3_dla(r));
     }
-    const int* dla = k3_dla(r);
-    const int* dlb = k3_dlb(r, p.capa);
+    const k3u16* dla = k3_dla(r);
+    const k3u16* dlb = k3_dlb(r, p.capa);
     if (d3 == 0)
         return k3_newgap4(k3_list(a, a.sfq, ia), dla, k3_list(b, b.tfq, ib), dlb) * p.bgop +
                k3_newgap4(k3_list(b, b.sfq, ib), dlb, k3_list(a, a.tfq, ia), dla) * p.bgop;
@@ -192,17 +196,17 @@ PG_HD double k3_gapopen(const K3Prm& p, const K3Group& a, const K3Group& b, cons
 PG_HD void k3_update(const K3Prm& p, const K3Group& a, const K3Group& b, int* dst, const int* src, int ia, int ib,
                      double gpn, int d3)
 {
-    const int sdir = K3_DIR(src);
+    const int sdir = k3_dir(src);
     int dir;
     if (d3 > 0) dir = k3_ishori(sdir) ? K3_NEWV : K3_VERT;
     else if (d3 < 0) dir = k3_isvert(sdir) ? K3_NEWH : K3_HORI;
     else dir = k3_isdiag(sdir) ? K3_DIAG : K3_NEWD;
-    const int sglb = K3_GLB(src);
+    int glb = 0;
     if (p.mode == 1) {
         const int o = a.tfq ? a.tfq[ia] : -1;
-        if (d3 == 0) { k3_newdelta(k3_dla(dst), o >= 0 ? a.glen + o : nullptr, k3_dla(src)); K3_GLB(dst) = 0; }
-        else if (d3 > 0) { k3_newdelta(k3_dla(dst), o >= 0 ? a.glen + o : nullptr, k3_dla(src)); K3_GLB(dst) = sglb + 1; }
-        else { k3_incdelta(k3_dla(dst), k3_dla(src), 1); K3_GLB(dst) = 0; }
+        if (d3 == 0) k3_newdelta(k3_dla(dst), o >= 0 ? a.glen + o : nullptr, k3_dla(src));
+        else if (d3 > 0) { glb = k3_glb(src) + 1; k3_newdelta(k3_dla(dst), o >= 0 ? a.glen + o : nullptr, k3_dla(src)); }
+        else k3_incdelta(k3_dla(dst), k3_dla(src), 1);
     } else if (p.mode == 2) {
         const int oa = a.tfq ? a.tfq[ia] : -1, ob = b.tfq ? b.tfq[ib] : -1;
         const int32_t* ta = oa >= 0 ? a.glen + oa : nullptr;
@@ -210,24 +214,24 @@ PG_HD void k3_update(const K3Prm& p, const K3Group& a, const K3Group& b, int* ds
         if (d3 == 0) { k3_newdelta(k3_dla(dst), ta, k3_dla(src)); k3_newdelta(k3_dlb(dst, p.capa), tb, k3_dlb(src, p.capa)); }
         else if (d3 > 0) { k3_newdelta(k3_dla(dst), ta, k3_dla(src)); k3_incdelta(k3_dlb(dst, p.capa), k3_dlb(src, p.capa), 1); }
         else { k3_newdelta(k3_dlb(dst, p.capa), tb, k3_dlb(src, p.capa)); k3_incdelta(k3_dla(dst), k3_dla(src), 1); }
-    } else K3_GLB(dst) = 0;
+    }
     const double v = k3_val(src) + gpn;
     const int ptr = K3_PTR(src);
-    K3_DIR(dst) = dir;
+    k3_setdg(dst, dir, glb);
     k3_setval(dst, v);
     K3_PTR(dst) = ptr;
 }
 PG_HD void k3_reset(const K3Prm& p, int* r)
 {
     k3_setval(r, K3_NEVSEL);
-    K3_DIR(r) = 0; K3_PTR(r) = 0; K3_GLB(r) = 0; r[5] = 0;
+    K3_PTR(r) = 0; k3_setdg(r, 0, 0);
     k3_cleardelta(k3_dla(r));
     k3_cleardelta(k3_dlb(r, p.capa));
 }
 PG_HD void k3_copy(const K3Prm& p, int* d, const int* s)
 {
     if (d == s) return;
-    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; d[4] = s[4];
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
     if (p.mode >= 1) k3_copydelta(k3_dla(d), k3_dla(s));
     if (p.mode == 2) k3_copydelta(k3_dlb(d, p.capa), k3_dlb(s, p.capa));
 }
@@ -252,7 +256,7 @@ PG_HD bool k3_cell(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, i
         if (a.nils) *pua = k3_unp(a, ia, b, ib, p.u);
         gnp = k3_gapopen(p, a, b, gabove, ia, ib, 1);
         gop = k3_gapopen(p, a, b, habove, ia, ib, 1);
-        if (!k3_isvert(K3_DIR(habove)) && (k3_val(habove) + gop > k3_val(gabove) + gnp))
+        if (!k3_isvert(k3_dir(habove)) && (k3_val(habove) + gop > k3_val(gabove) + gnp))
             k3_update(p, a, b, gout, habove, ia, ib, gop, 1);
         else k3_update(p, a, b, gout, gabove, ia, ib, gnp, 1);
         k3_setval(gout, k3_val(gout) + *pua);
@@ -260,7 +264,7 @@ PG_HD bool k3_cell(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, i
         if (p.Noll == 3) {  // vertical2 (fwd2c.h:411-420)
             gnp = p.v2divv1 * k3_gapopen(p, a, b, g2above, ia, ib, 1);
             gop = p.v2divv1 * gop;
-            if (!k3_isvert(K3_DIR(habove)) && (k3_val(habove) + gop > k3_val(g2above) + gnp))
+            if (!k3_isvert(k3_dir(habove)) && (k3_val(habove) + gop > k3_val(g2above) + gnp))
                 k3_update(p, a, b, g2out, habove, ia, ib, gop, 1);
             else k3_update(p, a, b, g2out, g2above, ia, ib, gnp, 1);
             k3_setval(g2out, k3_val(g2out) + p.u2divu1 * *pua);
@@ -275,7 +279,7 @@ PG_HD bool k3_cell(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, i
         const double pub = k3_unp(b, ib, a, ia, p.u);
         gnp = k3_gapopen(p, a, b, f1, ia, ib, -1);
         gop = k3_gapopen(p, a, b, hleft, ia, ib, -1);
-        if (!k3_ishori(K3_DIR(hleft)) && (k3_val(hleft) + gop > k3_val(f1) + gnp))
+        if (!k3_ishori(k3_dir(hleft)) && (k3_val(hleft) + gop > k3_val(f1) + gnp))
             k3_update(p, a, b, f1, hleft, ia, ib, gop, -1);
         else k3_update(p, a, b, f1, f1, ia, ib, gnp, -1);
         k3_setval(f1, k3_val(f1) + pub);
@@ -283,7 +287,7 @@ PG_HD bool k3_cell(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, i
         if (p.Noll == 3) {  // horizontal2 (fwd2c.h:433-442)
             gnp = p.v2divv1 * k3_gapopen(p, a, b, f2, ia, ib, -1);
             gop = p.v2divv1 * gop;
-            if (!k3_ishori(K3_DIR(hleft)) && (k3_val(hleft) + gop > k3_val(f2) + gnp))
+            if (!k3_ishori(k3_dir(hleft)) && (k3_val(hleft) + gop > k3_val(f2) + gnp))
                 k3_update(p, a, b, f2, hleft, ia, ib, gop, -1);
             else k3_update(p, a, b, f2, f2, ia, ib, gnp, -1);
             k3_setval(f2, k3_val(f2) + p.u2divu1 * pub);
@@ -291,7 +295,7 @@ PG_HD bool k3_cell(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, i
         }
     }
     if (k3_val(mx) > k3_val(hout)) k3_copy(p, hout, mx);        // fwd2c.h:453
-    const int dir = K3_DIR(hout);
+    const int dir = k3_dir(hout);
     return dir == K3_NEWD || dir == K3_NEWV || dir == K3_NEWH;   // fwd2c.h:465-467
 }
 

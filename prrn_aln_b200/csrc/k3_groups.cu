@@ -21,6 +21,7 @@
 //            the host layer); evaluated per cell here, or read from the tile matrix K4 precomputed.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "k3_core.cuh"
 #include "pg_internal.h"
@@ -29,8 +30,17 @@ namespace {
 
 constexpr int T = K3_THREADS;
 
+constexpr int RING = 4;     // prefetch ring depth for the parked row (records n, n+1 are read at step n)
+
+// words of shared memory one pair needs for its wavefront records (0 = keep them in the global arena)
+__host__ __device__ inline size_t k3_smem_words(int st, int Noll)
+{
+    return (size_t)st * ((Noll == 3 ? 9 : 6) * T + 1 + 3 * RING);
+}
+
 __global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
 {
+    extern __shared__ __align__(16) int sm_dyn[];
     __shared__ int sm_pair;
     __shared__ int sm_vmf;
     __shared__ int sm_last_ptr;
@@ -45,29 +55,39 @@ __global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
         const int pi = sm_pair;
         if (pi >= a.npairs) break;
         const K3Pair& P = a.pairs[pi];
-        const K3Group& A = P.a;
-        const K3Group& B = P.b;
-        const K3Prm& p = P.prm;
+        const K3Group A = P.a;
+        const K3Group B = P.b;
+        const K3Prm p = P.prm;
         const int LQ = A.L, LS = B.L;
         const int st = k3_stride(p.capa, p.capb);
-        // arena layout (records): rowH | rowG | rowG2 | colH | pubH[3][T] | pubG[2][T] | pubG2[2][T] | F1[T] | F2[T] | black
+        const bool n3 = p.Noll == 3;
+        // parked rows / boundary column: global arena (L2).  rowH[k] = H(pbase-1, k-1), colH[k] = H(k-1, -1)
         int* const rowH = arena;
         int* const rowG = rowH + (size_t)(LS + 2) * st;
         int* const rowG2 = rowG + (size_t)(LS + 2) * st;
         int* const colH = rowG2 + (size_t)(LS + 2) * st;
-        int* const pubH = colH + (size_t)(LQ + 2) * st;
-        int* const pubG = pubH + (size_t)3 * T * st;
-        int* const pubG2 = pubG + (size_t)2 * T * st;
-        int* const F1 = pubG2 + (size_t)2 * T * st;
-        int* const F2 = F1 + (size_t)T * st;
-        int* const black = F2 + (size_t)T * st;
+        int* const gwave = colH + (size_t)(LQ + 2) * st;
+        // wavefront records: shared memory when they fit, else the arena
+        const bool in_smem = k3_smem_words(st, p.Noll) * 4 <= (size_t)a.smem_bytes;
+        int* const wave = in_smem ? sm_dyn : gwave;
+        int* const ringH = wave;                            // [RING] prefetched rowH records
+        int* const ringG = ringH + (size_t)RING * st;
+        int* const ringG2 = ringG + (size_t)RING * st;
+        int* const black = ringG2 + (size_t)RING * st;
+        int* const pubH = black + st;                       // [3][T]
+        int* const pubG = pubH + (size_t)3 * T * st;        // [2][T]
+        int* const F1 = pubG + (size_t)2 * T * st;          // [T]
+        int* const pubG2 = F1 + (size_t)T * st;             // [2][T]   (two-piece only)
+        int* const F2 = pubG2 + (size_t)2 * T * st;         // [T]
         // ---- reset the records this pair can read before writing
         for (int i = t; i < LS + 2; i += T) {
-            k3_reset(p, rowH + (size_t)i * st); k3_reset(p, rowG + (size_t)i * st); k3_reset(p, rowG2 + (size_t)i * st);
+            k3_reset(p, rowH + (size_t)i * st); k3_reset(p, rowG + (size_t)i * st);
+            if (n3) k3_reset(p, rowG2 + (size_t)i * st);
         }
         for (int i = t; i < LQ + 2; i += T) k3_reset(p, colH + (size_t)i * st);
         for (int g = 0; g < 3; ++g) k3_reset(p, pubH + ((size_t)g * T + t) * st);
-        for (int g = 0; g < 2; ++g) { k3_reset(p, pubG + ((size_t)g * T + t) * st); k3_reset(p, pubG2 + ((size_t)g * T + t) * st); }
+        for (int g = 0; g < 2; ++g) { k3_reset(p, pubG + ((size_t)g * T + t) * st); if (n3) k3_reset(p, pubG2 + ((size_t)g * T + t) * st); }
+        if (t < RING) { k3_reset(p, ringH + (size_t)t * st); k3_reset(p, ringG + (size_t)t * st); k3_reset(p, ringG2 + (size_t)t * st); }
         if (t == 0) k3_reset(p, black);
         __syncthreads();
         // ---- initB (fwd2c.h:138-176): origin, then the two boundary chains (one thread each)
@@ -75,16 +95,22 @@ __global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
             vmf[0].m = 0; vmf[0].n = 0; vmf[0].p = 0;                       // skip 0-th record (:361)
             vmf[1].m = P.al; vmf[1].n = P.bl; vmf[1].p = 0;                 // origin
             sm_vmf = 2;
-            k3_setval(colH, 0); K3_DIR(colH) = K3_DIAG; K3_PTR(colH) = 1;
+            k3_setval(colH, 0); k3_setdg(colH, K3_DIAG, 0); K3_PTR(colH) = 1;
             const int rr = LQ < -p.lw ? LQ : -p.lw;
             for (int k = 1; k <= rr; ++k) k3_boundary_col(p, A, B, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
         }
         if (t == 32) {
-            k3_setval(rowH, 0); K3_DIR(rowH) = K3_DIAG; K3_PTR(rowH) = 1;
+            k3_setval(rowH, 0); k3_setdg(rowH, K3_DIAG, 0); K3_PTR(rowH) = 1;
             const int rr = LS < p.up ? LS : p.up;
             for (int k = 1; k <= rr; ++k) k3_boundary_row(p, A, B, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
         }
         __syncthreads();
+
+        // prefetch role of this thread: word pw of record array pa (0 rowH, 1 rowG, 2 rowG2)
+        const int pa = t / st, pw = t - pa * st;
+        const bool pf_thread = pa < (n3 ? 3 : 2);
+        const int* const pf_src = pa == 0 ? rowH : (pa == 1 ? rowG : rowG2);
+        int* const pf_dst = pa == 0 ? ringH : (pa == 1 ? ringG : ringG2);
 
         for (int pbase = 0; pbase < LQ; pbase += T) {
             const int rows = LQ - pbase < T ? LQ - pbase : T;
@@ -96,30 +122,40 @@ __global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
             double pua = 0;
             bool started = false;
             const int nsteps = LS + rows - 1;
+            // ring: records 0 and 1 of the parked row before the first step
+            if (pf_thread) {
+                pf_dst[pw] = __ldcg(pf_src + pw);
+                if (LS + 1 >= 1) pf_dst[st + pw] = __ldcg(pf_src + st + pw);
+            }
+            __syncthreads();
             for (int s = 0; s < nsteps; ++s) {
                 const int n = s - t;
                 const int r = n - m;
+                // prefetch record s+2 of the parked row (read by thread 0 at steps s+1, s+2)
+                int pf_val = 0;
+                const bool pf_now = pf_thread && s + 2 <= LS + 1;
+                if (pf_now) pf_val = __ldcg(pf_src + (size_t)(s + 2) * st + pw);
                 if (t < rows && n >= 0 && n < LS && r >= p.lw && r <= p.up) {
                     const int ib = n + 1;
                     if (!started) {
                         started = true;
                         pua = k3_unp(A, ia, B, ib, p.u);            // once per row, at its first column (:377)
                         k3_reset(p, f1);
-                        k3_reset(p, f2);
+                        if (n3) k3_reset(p, f2);
                     }
                     const int g3a = (s + 2) % 3, g3d = (s + 1) % 3, g2a = (s + 1) & 1;
                     const int* hdiag = n == 0 ? colH + (size_t)m * st
-                                     : (t == 0 ? rowH + (size_t)n * st : pubH + ((size_t)g3d * T + (t - 1)) * st);
+                                     : (t == 0 ? ringH + (size_t)(n % RING) * st : pubH + ((size_t)g3d * T + (t - 1)) * st);
                     const bool above_in = r + 1 <= p.up;
-                    const int* habove = !above_in ? black : (t == 0 ? rowH + (size_t)(n + 1) * st : pubH + ((size_t)g3a * T + (t - 1)) * st);
-                    const int* gabove = (!above_in || m == 0) ? black : (t == 0 ? rowG + (size_t)(n + 1) * st : pubG + ((size_t)g2a * T + (t - 1)) * st);
-                    const int* g2above = (!above_in || m == 0) ? black : (t == 0 ? rowG2 + (size_t)(n + 1) * st : pubG2 + ((size_t)g2a * T + (t - 1)) * st);
+                    const int* habove = !above_in ? black : (t == 0 ? ringH + (size_t)((n + 1) % RING) * st : pubH + ((size_t)g3a * T + (t - 1)) * st);
+                    const int* gabove = (!above_in || m == 0) ? black : (t == 0 ? ringG + (size_t)((n + 1) % RING) * st : pubG + ((size_t)g2a * T + (t - 1)) * st);
+                    const int* g2above = (!above_in || m == 0) ? black : (t == 0 ? ringG2 + (size_t)((n + 1) % RING) * st : pubG2 + ((size_t)g2a * T + (t - 1)) * st);
                     const bool left_in = r - 1 >= p.lw;
                     const int* hleft = n == 0 ? colH + (size_t)(m + 1) * st : (left_in ? pubH + ((size_t)g3a * T + t) * st : black);
                     int* hout = pubH + ((size_t)(s % 3) * T + t) * st;
                     int* gout = pubG + ((size_t)(s & 1) * T + t) * st;
                     int* g2out = pubG2 + ((size_t)(s & 1) * T + t) * st;
-                    const double dab = P.simmat ? P.simmat[(size_t)m * LS + n] : k3_sim(A, B, p, ia, ib);
+                    const double dab = P.simmat ? __ldg(P.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
                     if (k3_cell(p, A, B, ia, ib, m == 0, n == 0, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
                                 hout, gout, g2out, black)) {
                         const int id = atomicAdd(&sm_vmf, 1);       // Vmf::add (fwd2c.h:465-467)
@@ -130,10 +166,11 @@ __global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
                         if (!last_pass) {
                             k3_copy(p, rowH + (size_t)(n + 1) * st, hout);
                             k3_copy(p, rowG + (size_t)(n + 1) * st, gout);
-                            if (p.Noll == 3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
+                            if (n3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
                         } else if (n == LS - 1) { sm_last_ptr = K3_PTR(hout); sm_last_val = k3_val(hout); }
                     }
                 }
+                if (pf_now) pf_dst[(size_t)((s + 2) % RING) * st + pw] = pf_val;
                 __syncthreads();
             }
         }
@@ -162,9 +199,22 @@ __global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
 
 int k3_threads() { return T; }
 int k3_blocks_per_sm() { return 2; }
+size_t k3_wave_words(int stride, int Noll) { return k3_smem_words(stride, Noll); }
 
+// smem_bytes: dynamic shared memory per CTA (the largest wavefront of the batch, capped by the caller)
 cudaError_t k3_launch(const K3Args& a, int grid_blocks, cudaStream_t st)
 {
-    k3_fill_kernel<<<grid_blocks, T, 0, st>>>(a);
+    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    if (e != cudaSuccess) return e;
+    // The gap-profile lists and score rows stream through L1.  Few pairs (latency: Prrn::best_of_n sized
+    // batches): one CTA per SM and the rest of the unified array as L1 (measured 28 vs 37 ms for 24
+    // pairs); more pairs than SMs (throughput): two CTAs per SM win (59 vs 68 ms for 384 pairs).
+    // PG_K3_CARVEOUT = percent of shared memory overrides.
+    int carve = grid_blocks > 148 ? 100 : (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
+    if (const char* cv = getenv("PG_K3_CARVEOUT")) carve = atoi(cv);
+    if (carve > 100) carve = 100;
+    e = cudaFuncSetAttribute(k3_fill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (e != cudaSuccess) return e;
+    k3_fill_kernel<<<grid_blocks, T, a.smem_bytes, st>>>(a);
     return cudaGetLastError();
 }

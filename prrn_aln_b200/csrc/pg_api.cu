@@ -63,11 +63,13 @@ extern "C" int pg_create(int device, pg_context** out)
     c->dirs_cap = c->trace_cap = c->seqblob_cap = c->planbuf_cap = 0;
     c->d_bnd = c->d_scratch = c->d_ends = nullptr;
     c->bnd_cap = c->scratch_cap = c->ends_cap = 0;
-    c->d_gblob = c->d_garena = c->d_gvmf = c->d_gout = nullptr;
-    c->gblob_cap = c->garena_cap = c->gvmf_cap = c->gout_cap = 0;
+    c->d_gblob = c->d_garena = c->d_gvmf = c->d_gout = c->d_gsim = nullptr;
+    c->gblob_cap = c->garena_cap = c->gvmf_cap = c->gout_cap = c->gsim_cap = 0;
     c->items_cap = c->mtx_cap = c->self_cap = c->rowbuf_cap = c->out_cap = c->pairs_cap = 0;
     c->d_counter = nullptr;
-    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+    c->ev_valid = false;
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_counter, sizeof(int32_t))) != cudaSuccess) {
         std::string m = std::string("pg_create: ") + cudaGetErrorString(e);
         delete c;
@@ -85,7 +87,8 @@ extern "C" void pg_destroy(pg_context* c)
     cudaFree(c->d_items); cudaFree(c->d_mtx); cudaFree(c->d_self); cudaFree(c->d_rowbuf);
     cudaFree(c->d_out); cudaFree(c->d_pairs); cudaFree(c->d_counter); cudaFree(c->d_dirs); cudaFree(c->d_trace); cudaFree(c->d_seqblob); cudaFree(c->d_planbuf);
     cudaFree(c->d_bnd); cudaFree(c->d_scratch); cudaFree(c->d_ends);
-    cudaFree(c->d_gblob); cudaFree(c->d_garena); cudaFree(c->d_gvmf); cudaFree(c->d_gout);
+    cudaFree(c->d_gblob); cudaFree(c->d_garena); cudaFree(c->d_gvmf); cudaFree(c->d_gout); cudaFree(c->d_gsim);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1017,6 +1020,14 @@ extern "C" int pg_debug_packed_plan(const pg_seqs* s, int64_t k_begin, int64_t k
             }
     }
     return PG_OK;
+}
+
+extern "C" double pg_last_kernel_ms(pg_context* c)
+{
+    if (!c || !c->ev_valid) return -1.0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) return -1.0;
+    return (double)ms;
 }
 
 extern "C" int pg_dpx_peak(pg_context* c, double* gops_s32, double* gops_s16x2)

@@ -115,7 +115,7 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     std::vector<SideOff> soa(npairs), sob(npairs);
     std::vector<K3Pair> pairs(npairs);
     std::vector<int64_t> cells(npairs), outoff(npairs + 1);
-    size_t blob = 0, arena_words = 0;
+    size_t blob = 0, arena_words = 0, wave_bytes = 0;
     int64_t max_cells = 0;
     outoff[0] = 0;
     for (int64_t i = 0; i < npairs; ++i) {
@@ -157,7 +157,12 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
         kp.v2divv1 = P.BasicGOP < 0 ? P.LongGOP / P.BasicGOP : 0;
         const int LQ = A.right - A.left, LS = B.right - B.left;
         const size_t st = (size_t)k3_stride(kp.capa, kp.capb);
-        arena_words = std::max(arena_words, st * (size_t)(3 * (LS + 2) + (LQ + 2) + 9 * K3_THREADS + 1));
+        arena_words = std::max(arena_words, st * (size_t)(3 * (LS + 2) + (LQ + 2)) + k3_wave_words((int)st, 3));
+        wave_bytes = std::max(wave_bytes, 4 * k3_wave_words((int)st, P.Noll));
+        if (A.len > 65000 || B.len > 65000) {
+            free(offs);
+            return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: groups longer than 65,000 columns exceed the 16-bit gap-state lists");
+        }
         cells[i] = pg_group_cells(&A, &B, P.sh);
         max_cells = std::max(max_cells, cells[i]);
         pairs[i].al = A.left; pairs[i].bl = B.left;
@@ -172,14 +177,36 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     if (vmf_cap > 0x7fffffff) { free(offs); return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: DP matrix too large for the path store"); }
 
     // ---- stage
-    int rc = pg_int_ensure_cap(c, &c->d_gblob, &c->gblob_cap, blob + sizeof(K3Pair) * (size_t)npairs + 256);
-    if (!rc) rc = pg_int_ensure_cap(c, &c->d_garena, &c->garena_cap, arena_words * 4 * (size_t)grid);
+    int rc = pg_int_ensure_cap(c, &c->d_garena, &c->garena_cap, arena_words * 4 * (size_t)grid);
     if (!rc) rc = pg_int_ensure_cap(c, &c->d_gvmf, &c->gvmf_cap, sizeof(K3Vmf) * (size_t)vmf_cap * grid);
     const size_t o_pts = 0, o_cnt = up16(o_pts + 8 * (size_t)outoff[npairs]), o_scr = up16(o_cnt + 4 * (size_t)npairs),
                  obytes = up16(o_scr + 8 * (size_t)npairs);
     if (!rc) rc = pg_int_ensure_cap(c, &c->d_gout, &c->gout_cap, obytes);
     if (rc) { free(offs); return rc; }
-    std::vector<char> h(blob + sizeof(K3Pair) * (size_t)npairs);
+    // ---- column score matrices S = X_a . Y_b^T (kernel K4, FP64 tensor cores) when they fit the budget;
+    //      otherwise (or with PG_K3_INLINE_SIM=1) K3 evaluates the contraction per cell
+    std::vector<size_t> sim_off(npairs, (size_t)-1);
+    size_t sim_bytes = 0;
+    {
+        const char* inl = getenv("PG_K3_INLINE_SIM");
+        const size_t SIM_BUDGET = (size_t)24 << 30;
+        if (!(inl && inl[0] == '1')) {
+            size_t tot = 0;
+            for (int64_t i = 0; i < npairs; ++i)
+                tot += up16(8 * (size_t)(a[i].right - a[i].left) * (size_t)(b[i].right - b[i].left));
+            if (tot <= SIM_BUDGET) {
+                for (int64_t i = 0; i < npairs; ++i) {
+                    sim_off[i] = sim_bytes;
+                    sim_bytes += up16(8 * (size_t)(a[i].right - a[i].left) * (size_t)(b[i].right - b[i].left));
+                }
+            }
+        }
+    }
+    if (sim_bytes) { rc = pg_int_ensure_cap(c, &c->d_gsim, &c->gsim_cap, sim_bytes); if (rc) { free(offs); return rc; } }
+    const size_t o_boff = up16(blob + sizeof(K3Pair) * (size_t)npairs);
+    rc = pg_int_ensure_cap(c, &c->d_gblob, &c->gblob_cap, o_boff + 4 * (size_t)(npairs + 1) + 256);
+    if (rc) { free(offs); return rc; }
+    std::vector<char> h(o_boff + 4 * (size_t)(npairs + 1));
     char* d = (char*)c->d_gblob;
     // heaviest pairs first (persistent CTAs finish together); the kernel indexes results by this order
     std::vector<int32_t> order(npairs);
@@ -191,9 +218,18 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
         fill_side(b[i], prm[i].kdim, sob[i], h.data());
         pairs[i].a = dev_side(a[i], soa[i], d);
         pairs[i].b = dev_side(b[i], sob[i], d);
+        pairs[i].simmat = sim_off[i] == (size_t)-1 ? nullptr : (const double*)((char*)c->d_gsim + sim_off[i]);
     }
     for (int64_t k = 0; k < npairs; ++k) sorted[k] = pairs[order[k]];
     memcpy(h.data() + blob, sorted.data(), sizeof(K3Pair) * (size_t)npairs);
+    int32_t* boff = (int32_t*)(h.data() + o_boff);
+    boff[0] = 0;
+    for (int64_t k = 0; k < npairs; ++k) boff[k + 1] = boff[k] + (sorted[k].simmat ? (sorted[k].a.L + 7) / 8 : 0);
+    K4Args k4;
+    k4.pairs = (const K3Pair*)(d + blob);
+    k4.npairs = (int32_t)npairs;
+    k4.block_off = (const int32_t*)(d + o_boff);
+    const int k4_blocks = boff[npairs];
     K3Args ka;
     memset(&ka, 0, sizeof(ka));
     ka.pairs = (const K3Pair*)(d + blob);
@@ -207,11 +243,18 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     ka.out_pts = (int32_t*)(go + o_pts);
     ka.out_cnt = (int32_t*)(go + o_cnt);
     ka.out_score = (double*)(go + o_scr);
+    // wavefront records live in shared memory when they fit (two CTAs per SM up to ~110 KB each, one up to
+    // 220 KB); pairs whose records are larger fall back to the L2-resident arena inside the kernel
+    ka.smem_bytes = (int32_t)std::min<size_t>(wave_bytes, (size_t)220 * 1024);
     std::vector<int32_t> h_pts(2 * (size_t)outoff[npairs]), h_cnt(npairs);
     std::vector<double> h_scr(npairs);
     e = cudaMemcpyAsync(d, h.data(), h.size(), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counter, 0, sizeof(int32_t), c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev0, c->stream);
+    if (e == cudaSuccess && sim_bytes) e = k4_launch(k4, k4_blocks, c->stream);
     if (e == cudaSuccess) e = k3_launch(ka, grid, c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev1, c->stream);
+    c->ev_valid = e == cudaSuccess;
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_pts.data(), ka.out_pts, 8 * (size_t)outoff[npairs], cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt.data(), ka.out_cnt, 4 * (size_t)npairs, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_scr.data(), ka.out_score, 8 * (size_t)npairs, cudaMemcpyDeviceToHost, c->stream);

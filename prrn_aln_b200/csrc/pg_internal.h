@@ -160,6 +160,14 @@ struct K3Args {
     int32_t* out_pts;           // corner lists (2 ints per corner), Vmf back-walk order
     int32_t* out_cnt;           // [npairs] corners, -1 on overflow
     double* out_score;          // [npairs]
+    int32_t smem_bytes;         // dynamic shared memory per CTA for the wavefront records
+};
+
+// profile contraction (k4_contract.cu): S = X_a . Y_b^T per pair, written to K3Pair::simmat
+struct K4Args {
+    const K3Pair* pairs;
+    int32_t npairs;
+    const int32_t* block_off;   // [npairs + 1] prefix sums of ceil(LQ / 8)
 };
 
 struct pg_dev_seqs {
@@ -204,7 +212,10 @@ struct pg_context {
     void* d_garena; size_t garena_cap;
     void* d_gvmf; size_t gvmf_cap;
     void* d_gout; size_t gout_cap;
+    void* d_gsim; size_t gsim_cap;
     int32_t* d_counter;
+    cudaEvent_t ev0, ev1;       // device time of the last fill launch (pg_last_kernel_ms)
+    bool ev_valid;
 };
 
 int pg_int_fail(pg_context* ctx, int code, const char* msg);
@@ -238,5 +249,8 @@ int k2_blocks_per_sm();
 cudaError_t k3_launch(const K3Args& a, int grid_blocks, cudaStream_t st);
 int k3_threads();
 int k3_blocks_per_sm();
+size_t k3_wave_words(int stride, int Noll);
+// k4_contract.cu
+cudaError_t k4_launch(const K4Args& a, int total_blocks, cudaStream_t st);
 // dpx_peak.cu
 cudaError_t dpx_peak_run(int sm_count, cudaStream_t st, double* gops_s32, double* gops_s16x2);

@@ -32,7 +32,7 @@ extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* 
     vmf.push_back({0, 0, 0});                       // skip 0-th record (fwd2c.h:361)
     vmf.push_back({al, bl, 0});                     // origin (initB)
     // origin + boundary chains
-    k3_setval(colH, 0); K3_DIR(colH) = K3_DIAG; K3_PTR(colH) = 1;
+    k3_setval(colH, 0); k3_setdg(colH, K3_DIAG, 0); K3_PTR(colH) = 1;
     k3_copy(p, rowH, colH);
     { int rr = LS < p.up ? LS : p.up; for (int k = 1; k <= rr; ++k) k3_boundary_row(p, a, b, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st); }
     { int rr = LQ < -p.lw ? LQ : -p.lw; for (int k = 1; k <= rr; ++k) k3_boundary_col(p, a, b, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st); }

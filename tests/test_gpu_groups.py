@@ -34,8 +34,12 @@ def stage_golden(g, sh=None):
     return A, B, gp
 
 
+@pytest.mark.parametrize("inline_sim", ["0", "1"])
 @pytest.mark.parametrize("name", golden_names("galign_"))
-def test_group_goldens(ctx, name):
+def test_group_goldens(ctx, name, inline_sim, monkeypatch):
+    """inline_sim 0: column score matrix precomputed by kernel K4 (FP64 tensor cores); 1: sim2 evaluated
+    inside the DP cell (PG_K3_INLINE_SIM=1).  Both must reproduce the reference."""
+    monkeypatch.setenv("PG_K3_INLINE_SIM", inline_sim)
     g = golden(name)
     A, B, gp = stage_golden(g)
     scores, pts = ctx.align_groups([(A, B, gp)])

@@ -12,50 +12,56 @@ PROT = "ARNDCQEGHILKMFPSTWYV"
 DNA = "ACGT"
 
 
-def synth_msa(nmem, root_len, d0, d1, seed, dna=False, gapless=False):
+def synth_msa(nmem, root_len, d0, d1, seed, dna=False, gapless=False, indel_events=3.0):
+    """Tree-structured family: member k descends from a random earlier member (member 0 from the root).
+    A child copies its parent's row, substitutes residues with its own divergence d ~ U(d0, d1), deletes a
+    few contiguous runs and inserts a few runs (new columns, gaps in every non-descendant), so gap runs
+    are shared along lineages and the column count grows slowly (a few columns per member)."""
     rng = random.Random(seed)
     alpha = DNA if dna else PROT
-    root = [rng.choice(alpha) for _ in range(root_len)]
-    cols = [[c] for c in root]          # each column: list of member characters so far
-    rows = []
-    # build member by member over a growing column list: columns = list of dicts
-    columns = [{"root": c} for c in root]
-    members = []
+    ncol = root_len
+    rows = []                       # each row: dict column-id -> char; columns kept in an ordered list
+    order = list(range(root_len))   # column ids in alignment order
+    next_id = root_len
+    root = {c: rng.choice(alpha) for c in order}
     for k in range(nmem):
+        parent = root if k == 0 else rows[rng.randrange(k)]
         d = rng.uniform(d0, d1)
-        out = {}                          # column object id -> char
-        newcols = []
-        i = 0
-        seq_cols = []
-        for col in columns:
-            r = rng.random()
-            base = col.get("root") or rng.choice(alpha)
-            if gapless:
-                ch = base if r > 0.7 * d else rng.choice(alpha)
-            elif r < 0.70 * d:
-                ch = rng.choice(alpha)
-            elif r < 0.85 * d:
-                ch = "-"
-            else:
-                ch = base
-            col.setdefault("chars", {})[k] = ch
-            newcols.append(col)
-            if not gapless and rng.random() < 0.15 * d * 0.5:
-                ins = {"root": None, "chars": {k: rng.choice(alpha)}}
-                newcols.append(ins)
-                # extend an insertion run sometimes
-                while rng.random() < 0.4:
-                    newcols.append({"root": None, "chars": {k: rng.choice(alpha)}})
-        columns = newcols
-    rows = []
-    for k in range(nmem):
-        rows.append("".join(col.get("chars", {}).get(k, "-") for col in columns))
-    # drop all-gap columns
-    keep = [j for j in range(len(columns)) if any(r[j] != "-" for r in rows)]
-    rows = ["".join(r[j] for j in keep) for r in rows]
-    # a member must not be empty
-    rows = [r if any(c != "-" for c in r) else alpha[0] + r[1:] for r in rows]
-    return rows
+        child = {}
+        for c in order:
+            ch = parent.get(c)
+            if ch is None:
+                continue
+            child[c] = rng.choice(alpha) if rng.random() < 0.7 * d else ch
+        if not gapless:
+            present = [c for c in order if c in child]
+            nev = 0
+            while rng.random() < indel_events * d / (1 + indel_events * d) and nev < 8:
+                nev += 1
+                if rng.random() < 0.5 and len(present) > 20:        # deletion of a contiguous run
+                    ln = 1
+                    while rng.random() < 0.6 and ln < 12:
+                        ln += 1
+                    st = rng.randrange(1, max(2, len(present) - ln - 1))
+                    for c in present[st:st + ln]:
+                        child.pop(c, None)
+                    present = [c for c in order if c in child]
+                else:                                               # insertion of a run of new columns
+                    ln = 1
+                    while rng.random() < 0.5 and ln < 8:
+                        ln += 1
+                    anchor = present[rng.randrange(len(present))]
+                    pos = order.index(anchor) + 1
+                    ids = list(range(next_id, next_id + ln))
+                    next_id += ln
+                    order[pos:pos] = ids
+                    for c in ids:
+                        child[c] = rng.choice(alpha)
+                    present = [c for c in order if c in child]
+        rows.append(child)
+    out = ["".join(r.get(c, "-") for c in order) for r in rows]
+    keep = [j for j in range(len(order)) if any(r[j] != "-" for r in out)]
+    return ["".join(r[j] for j in keep) for r in out]
 
 
 def split_family(rows, idx_a, idx_b):

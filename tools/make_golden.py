@@ -119,6 +119,11 @@ def galign_cases():
     galign_case("galign_rhf_single_prof10", B, A, wt=1)                           # RHF (swap)
     A, B = gen_msa.split_family(fam, range(0, 8), range(8, 14))
     galign_case("galign_gpf_twopiece", A, B, ls=3, wt=1)                          # Noll = 3
+    hh = gen_msa.synth_msa(40, 80, 0.3, 0.8, 45, indel_events=12.0)                # many distinct gap lengths per column
+    A, B = gen_msa.split_family(hh, range(0, 22), range(22, 40))
+    galign_case("galign_gpf_highhetero", A, B, wt=1, sh=-40)
+    A, B = gen_msa.split_family(hh, range(0, 3), range(3, 6))
+    galign_case("galign_gpf_raw3x3_gappy", A, B, mtx="blosum62")                 # GPF, sim22i
     gl = gen_msa.synth_msa(7, 80, 0.2, 0.6, 43, gapless=True)
     galign_case("galign_ngp_gapless4x3", gl[:4], gl[4:], mtx="blosum62")          # NGP with thickness
     dn = gen_msa.synth_msa(12, 120, 0.05, 0.35, 44, dna=True)
