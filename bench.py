@@ -120,6 +120,24 @@ def cpu_reference_run(seqs, threads, reps=1):
     return cells / dt / 1e9, "port", 1, dt, cells
 
 
+def group_side_measurement():
+    """The other half of BASELINE.json's metric: group-to-group DP (kernel K3 + K4) on partitions of a
+    200 x ~500 aa family (config 3 shape), with the reference's alignC timed beside it on one host core.
+    The inputs are staged by the reference itself (oracle/_ref/ref_driver_d: PwdM -> mkthick / Gfq /
+    convseq), which is test infrastructure; without it this object only says so."""
+    try:
+        import argparse as _ap
+        import bench_groups
+        import refio
+        if not refio.available("d"):
+            return {"unavailable": "oracle/_ref/ref_driver_d (the reference's staging of groups) is not built"}
+        a = _ap.Namespace(members=200, length=500, pairs=24, sh=-60, seed=7, cpu_rep=1)
+        dumps = bench_groups.build_pairs(a)
+        return bench_groups.measure(dumps, replicate=16, steps=3)
+    except Exception as e:      # the headline line must survive a failure of the side measurement
+        return {"error": repr(e)[:300]}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -155,6 +173,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-groups", action="store_true", help="skip the group-to-group (K3) side measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -285,10 +304,12 @@ def main():
         out["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": cores, "kind": kind,
                                "sample": "first %d of the 1000 sequences: %d pairs, %.3g cells, %.2f s" % (
                                    CPU_SAMPLE_N, CPU_SAMPLE_N * (CPU_SAMPLE_N - 1) // 2, cells, dtc)}
-    if rank == 0:
-        print(json.dumps(out))
     ctx.free_seqs(dseqs)
     ctx.close()
+    if rank == 0 and world == 1 and not args.no_groups:
+        out["group_to_group"] = group_side_measurement()
+    if rank == 0:
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

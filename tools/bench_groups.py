@@ -56,6 +56,52 @@ def build_pairs(args):
     return out
 
 
+def measure(dumps, replicate=16, steps=3, device=0, members=200, length=500, seed=7, sh=-60):
+    """Run the staged pairs through pg_align_groups; returns the result dict (see module docstring)."""
+    import prrn_aln_b200 as P
+    from prrn_aln_b200 import groups as G
+    staged = []
+    cells = 0
+    cpu_s = 0.0
+    for d in dumps:
+        pm, pc, h = d["pwdm"], d["pwdc"], d["header"]
+        A, B = G.stage_pair(d["groups"][0], d["groups"][1], pm["a_mode"], pm["b_mode"], d["matrix"], dxd=(pm["DvsP"] == 0))
+        gp = P.gparams_from_pwd(pm["alnmode"], pm["Noll"], pm["codonk1"], int(h["sh"]), A["vec"].shape[1], float(h["u"]),
+                                float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
+        staged.append((A, B, gp))
+        cells += P.group_cells(A, B, gp.sh)
+        cpu_s += d["time"]
+    batch = staged * replicate
+    ctx = P.Context(device)
+    scores, pts = ctx.align_groups(batch)           # warm-up + parity
+    bad = 0
+    for k, d in enumerate(dumps):
+        w = d["alignc"]
+        if abs(scores[k] - w["score"]) > 1e-5 * max(1.0, abs(w["score"])) or pts[k].tolist() != w["skl"]:
+            bad += 1
+    for _ in range(2):
+        ctx.align_groups(batch)
+    kms, wall = [], []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ctx.align_groups(batch)
+        wall.append(time.perf_counter() - t0)
+        kms.append(ctx.last_kernel_ms())
+    ctx.close()
+    tot_cells = cells * replicate
+    return {"metric": "group-to-group DP GCUPS (alignC with gap-profile state, band cells)",
+            "value": tot_cells / (np.median(kms) * 1e-3) / 1e9, "unit": "GCUPS",
+            "e2e": {"value": tot_cells / np.median(wall) / 1e9, "unit": "GCUPS"},
+            "kernel_ms": float(np.median(kms)), "call_ms": float(1e3 * np.median(wall)), "pairs": len(batch),
+            "cells": int(tot_cells), "parity_mismatches": bad,
+            "cpu_baseline": {"value": cells / cpu_s / 1e9, "unit": "GCUPS", "cores": 1, "kind": "reference",
+                             "sample": "the same %d distinct pairs, alignC only, %.2f s" % (len(dumps), cpu_s)},
+            "config": {"workload": "partitions of a synthetic %d x ~%d aa family (seed %d), sh=%d, PAM250 u=2 v=9, "
+                                   "sequence weights on; %d distinct pairs x %d" % (members, length, seed, sh, len(dumps), replicate),
+                       "modes": sorted(set(d["pwdm"]["alnmode"] for d in dumps)),
+                       "mean_hetero": float(np.mean([max(g["hetero"], 0) for d in dumps for g in d["groups"]]))}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--members", type=int, default=200)
@@ -77,47 +123,7 @@ def main():
             pickle.dump(dumps, open(args.cache, "wb"))
     if args.stage_only:
         return
-    import prrn_aln_b200 as P
-    from prrn_aln_b200 import groups as G
-    staged = []
-    cells = 0
-    cpu_s = 0.0
-    for d in dumps:
-        pm, pc, h = d["pwdm"], d["pwdc"], d["header"]
-        A, B = G.stage_pair(d["groups"][0], d["groups"][1], pm["a_mode"], pm["b_mode"], d["matrix"], dxd=(pm["DvsP"] == 0))
-        gp = P.gparams_from_pwd(pm["alnmode"], pm["Noll"], pm["codonk1"], int(h["sh"]), A["vec"].shape[1], float(h["u"]),
-                                float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
-        staged.append((A, B, gp))
-        cells += P.group_cells(A, B, gp.sh)
-        cpu_s += d["time"]
-    batch = staged * args.replicate
-    ctx = P.Context(0)
-    scores, pts = ctx.align_groups(batch)           # warm-up + parity
-    bad = 0
-    for k, d in enumerate(dumps):
-        w = d["alignc"]
-        if abs(scores[k] - w["score"]) > 1e-5 * max(1.0, abs(w["score"])) or pts[k].tolist() != w["skl"]:
-            bad += 1
-    kms, wall = [], []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        ctx.align_groups(batch)
-        wall.append(time.perf_counter() - t0)
-        kms.append(ctx.last_kernel_ms())
-    tot_cells = cells * args.replicate
-    out = {"metric": "group-to-group DP GCUPS (alignC with gap-profile state, band cells)",
-           "value": tot_cells / (np.median(kms) * 1e-3) / 1e9, "unit": "GCUPS",
-           "e2e": {"value": tot_cells / np.median(wall) / 1e9, "unit": "GCUPS"},
-           "kernel_ms": float(np.median(kms)), "call_ms": float(1e3 * np.median(wall)), "pairs": len(batch),
-           "cells": int(tot_cells), "parity_mismatches": bad,
-           "cpu_baseline": {"value": cells / cpu_s / 1e9, "unit": "GCUPS", "cores": 1, "kind": "reference",
-                            "sample": "the same %d pairs, alignC only, %.2f s" % (len(dumps), cpu_s)},
-           "config": {"workload": "partitions of a synthetic %d x ~%d aa family (seed %d), sh=%d, PAM250 u=2 v=9, "
-                                  "sequence weights on" % (args.members, args.length, args.seed, args.sh),
-                      "modes": sorted(set(d["pwdm"]["alnmode"] for d in dumps)),
-                      "mean_hetero": float(np.mean([max(g["hetero"], 0) for d in dumps for g in d["groups"]]))}}
-    print(json.dumps(out))
-    ctx.close()
+    print(json.dumps(measure(dumps, args.replicate, args.steps, 0, args.members, args.length, args.seed, args.sh)))
 
 
 if __name__ == "__main__":
