@@ -803,11 +803,32 @@ extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
     *out_pts = nullptr;
     if (npairs > 0x7fffffff) return fail(c, PG_ERR_ARG, "pg_align_pairs: too many pairs in one call");
     if (dim < 1 || dim > 32) return fail(c, PG_ERR_ARG, "dim must be in [1, 32]");
-    if (prm->alprm.ls >= 3)
-        return fail(c, PG_ERR_UNSUPPORTED, "two-piece gap penalty (ls == 3, fwd2c.h:411-442) is not built yet");
     for (int64_t p = 0; p < npairs; ++p)
         if (a_idx[p] < 0 || a_idx[p] >= s->nseq || b_idx[p] < 0 || b_idx[p] >= s->nseq)
             return fail(c, PG_ERR_ARG, "pg_align_pairs: sequence index out of range");
+    {   // the exact-integer bit kernel (K2) takes integral affine scoring; two-piece penalties and
+        // non-integral tables (default PAM) run as groups of one on the floating-point kernel K3
+        bool fp = prm->alprm.ls >= 3;
+        const char* force = getenv("PG_FORCE_FLOAT");
+        if (force && force[0] == '1') fp = true;
+        if (!fp) {
+            uint8_t present[256];
+            memset(present, 0, sizeof(present));
+            for (int64_t p = 0; p < npairs; ++p)
+                for (int side = 0; side < 2; ++side) {
+                    const int i = side ? b_idx[p] : a_idx[p];
+                    if (s->lens[i] < 0 || s->offs[i] < 0) return fail(c, PG_ERR_ARG, "negative length / offset");
+                    const int l = s->left ? s->left[i] : 0, r = s->right ? s->right[i] : s->lens[i];
+                    for (int k = l; k < r && k < s->lens[i]; ++k) present[s->res[s->offs[i] + k]] = 1;
+                }
+            IntScoring probe;
+            std::string keep = c->err;
+            pg_params p0 = *prm;
+            p0.lcl = 0; p0.alprm.tgapf = 1.0f;
+            if (make_int_scoring(c, &p0, mtx, dim, present, &probe) != PG_OK) { fp = true; c->err = keep; }
+        }
+        if (fp) return pg_int_align_pairs_fp(c, s, a_idx, b_idx, npairs, prm, mtx, dim, out_scores, out_offs, out_pts);
+    }
     int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * (size_t)(npairs + 1));
     if (!offs) return fail(c, PG_ERR_ARG, "out of host memory");
     offs[0] = 0;

@@ -279,3 +279,129 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     *out_pts = pts;
     return PG_OK;
 }
+
+
+// ---- alignC<DPunit> for two single sequences on the floating-point path --------------------------
+// pg_align_pairs sends here what the exact-integer bit kernel (K2) does not take: non-integral
+// matrices / penalties (the default PAM tables) and the two-piece gap function (alprm.ls == 3,
+// fwd2c.h:411-442).  A single sequence is a group of one: thickness 1 on every column (unit_dns,
+// mseq.h:89), no gap profile, sim2 = sim11 = mtx[a][b] -> X_a[m] = matrix row of a's residue,
+// Y_b[n] = one-hot of b's residue; constants as PwdB::PwdB / PwdM::resetuab derive them in the caller's
+// VTYPE (aln2.cc:97-117, maln2.cc:227-243).  Runs kernel K3 in its DPunit mode.
+namespace {
+template <typename VT>
+void single_gparams(const pg_params* prm, int dim, pg_gparams* gp)
+{
+    const float fu = prm->alprm.u, fv = prm->alprm.v, fu1 = prm->alprm.u1, fsc = prm->alprm.scale;
+    const VT Vab = (VT)(fsc * 1 * 1);
+    const VT BasicGOP = (VT)(-fv * Vab), BasicGEP = (VT)(-fu * Vab), LongGEP = (VT)(-fu1 * Vab);
+    const VT diffu = LongGEP - BasicGEP;
+    const VT LongGOP = BasicGOP - diffu * prm->alprm.k1;
+    gp->alnmode = 6;    // NGP_ALB
+    gp->Noll = prm->alprm.ls < 2 ? 2 : (prm->alprm.ls > 3 ? 3 : prm->alprm.ls);
+    gp->codonk1 = prm->alprm.ls == 3 ? prm->alprm.k1 : (0x7fffffff / 8 * 7);
+    gp->sh = prm->alprm.sh;
+    gp->kdim = dim;
+    gp->u = fu;
+    gp->Weighted_GOP = (double)(VT)-fv;
+    gp->Basic_GOP = (double)(VT)(-fsc * fv);
+    gp->BasicGOP = (double)BasicGOP; gp->BasicGEP = (double)BasicGEP;
+    gp->LongGOP = (double)LongGOP; gp->LongGEP = (double)LongGEP;
+}
+}  // namespace
+
+int pg_int_align_pairs_fp(pg_context* c, const pg_seqs* s, const int32_t* a_idx, const int32_t* b_idx, int64_t npairs,
+                          const pg_params* prm, const void* mtx, int32_t dim, void* out_scores, int64_t** out_offs,
+                          pg_skl** out_pts)
+{
+    if (prm->lcl != 0 || !(prm->alprm.tgapf == 1.0f))
+        return pg_int_fail(c, PG_ERR_UNSUPPORTED, "pg_align_pairs: semi-global / local alignment with path (nil-ended sequences, "
+                                                  "thickness at the ends) is not built yet");
+    pg_gparams gp;
+    if (prm->vtype) single_gparams<double>(prm, dim, &gp); else single_gparams<float>(prm, dim, &gp);
+    // per sequence and role: ones, matrix rows (as a), one-hot rows (as b)
+    const int n = s->nseq;
+    std::vector<std::vector<double>> rowv(n), onehot(n), ones(n);
+    std::vector<char> need_a(n, 0), need_b(n, 0);
+    for (int64_t p = 0; p < npairs; ++p) { need_a[a_idx[p]] = 1; need_b[b_idx[p]] = 1; }
+    auto wl = [&](int i) { return std::make_pair(s->left ? s->left[i] : 0, s->right ? s->right[i] : s->lens[i]); };
+    for (int i = 0; i < n; ++i) {
+        if (!need_a[i] && !need_b[i]) continue;
+        if (s->exg && (s->exg[i] & 3))
+            return pg_int_fail(c, PG_ERR_UNSUPPORTED, "pg_align_pairs: inex.exgl / exgr with path is not built yet");
+        const auto w = wl(i);
+        if (w.first < 0 || w.second > s->lens[i] || w.first > w.second) return pg_int_fail(c, PG_ERR_ARG, "window outside the sequence");
+        const size_t npos = (size_t)(w.second - w.first + 1);
+        ones[i].assign(npos, 1.0);
+        const uint8_t* r = s->res + s->offs[i] + w.first;
+        for (size_t x = 1; x < npos; ++x)
+            if (r[x - 1] >= dim) return pg_int_fail(c, PG_ERR_ARG, "residue code outside the substitution matrix");
+        if (need_a[i]) {
+            rowv[i].assign(npos * dim, 0.0);
+            for (size_t x = 1; x < npos; ++x)
+                for (int k = 0; k < dim; ++k) {
+                    const double v = prm->vtype ? ((const double*)mtx)[r[x - 1] * dim + k] : (double)((const float*)mtx)[r[x - 1] * dim + k];
+                    rowv[i][x * dim + k] = v == v ? v : 0.0;    // uninitialised (NaN) entries of unused codes
+                }
+        }
+        if (need_b[i]) {
+            onehot[i].assign(npos * dim, 0.0);
+            for (size_t x = 1; x < npos; ++x) onehot[i][x * dim + r[x - 1]] = 1.0;
+        }
+    }
+    int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * (size_t)(npairs + 1));
+    if (!offs) return pg_int_fail(c, PG_ERR_ARG, "out of host memory");
+    offs[0] = 0;
+    std::vector<pg_skl> all;
+    const int64_t CHUNK = 2048;
+    std::vector<pg_group> ga, gb;
+    std::vector<pg_gparams> gps;
+    std::vector<double> sc;
+    for (int64_t c0 = 0; c0 < npairs; c0 += CHUNK) {
+        const int64_t c1 = std::min(npairs, c0 + CHUNK);
+        ga.clear(); gb.clear(); gps.clear();
+        std::vector<int64_t> live;      // pairs with two non-empty windows (align2 answers the others with nogap_skl)
+        for (int64_t p = c0; p < c1; ++p) {
+            const int ia = a_idx[p], ib = b_idx[p];
+            const auto wa = wl(ia), wb = wl(ib);
+            if (wa.first == wa.second || wb.first == wb.second) continue;
+            pg_group A, B;
+            memset(&A, 0, sizeof(A)); memset(&B, 0, sizeof(B));
+            A.many = 1; A.len = s->lens[ia]; A.left = wa.first; A.right = wa.second; A.hetero = -1;
+            A.cfq = A.efq = ones[ia].data(); A.vec = rowv[ia].data();
+            B.many = 1; B.len = s->lens[ib]; B.left = wb.first; B.right = wb.second; B.hetero = -1;
+            B.cfq = B.efq = ones[ib].data(); B.vec = onehot[ib].data();
+            ga.push_back(A); gb.push_back(B); gps.push_back(gp);
+            live.push_back(p);
+        }
+        sc.assign(live.size(), 0.0);
+        int64_t* o2 = nullptr;
+        pg_skl* p2 = nullptr;
+        if (!live.empty()) {
+            int rc = pg_align_groups(c, ga.data(), gb.data(), gps.data(), (int64_t)live.size(), sc.data(), &o2, &p2);
+            if (rc) { free(offs); return rc; }
+        }
+        size_t li = 0;
+        for (int64_t p = c0; p < c1; ++p) {
+            double score = 0;
+            if (li < live.size() && live[li] == p) {
+                for (int64_t q = o2[li]; q < o2[li + 1]; ++q) all.push_back(p2[q]);
+                score = sc[li];
+                ++li;
+            } else {            // nogap_skl (aln2.cc:30-40) in back-walk order; score untouched (0)
+                const auto wa = wl(a_idx[p]), wb = wl(b_idx[p]);
+                pg_skl e1 = {wa.second, wb.second}, e0 = {wa.first, wb.first};
+                all.push_back(e1); all.push_back(e0);
+            }
+            offs[p + 1] = (int64_t)all.size();
+            if (prm->vtype) ((double*)out_scores)[p] = score; else ((float*)out_scores)[p] = (float)score;
+        }
+        pg_free(o2); pg_free(p2);
+    }
+    pg_skl* pts = (pg_skl*)malloc(sizeof(pg_skl) * std::max<size_t>(all.size(), 1));
+    if (!pts) { free(offs); return pg_int_fail(c, PG_ERR_ARG, "out of host memory"); }
+    memcpy(pts, all.data(), sizeof(pg_skl) * all.size());
+    *out_offs = offs;
+    *out_pts = pts;
+    return PG_OK;
+}

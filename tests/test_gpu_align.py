@@ -52,12 +52,36 @@ def test_golden_alignments_bit_exact(ctx, name):
 
 
 @pytest.mark.parametrize("name", OTHERS)
-def test_unsupported_alignment_modes_fail_loudly(ctx, name):
+def test_golden_alignments_float_path(ctx, name):
+    """Two-piece penalties (ls == 3) and non-integral matrices (PAM) run as groups of one on the
+    floating-point kernel K3: corner lists identical, scores exact for the double flavour and within
+    1e-5 relative for the float flavour (the kernel computes in double)."""
     g = golden(name)
     enc = [seqcode.encode_protein(s) for s in g["seqs"]]
-    with pytest.raises(P.PgError) as e:
-        ctx.align_pairs(P.SeqSet(enc), [0], [1], _params(g), np.array(g["matrix"]))
-    assert e.value.code == 4
+    ia = [p["i"] for p in g["pairs"]]
+    ib = [p["j"] for p in g["pairs"]]
+    prm = _params(g)
+    scores, raw = ctx.align_pairs(P.SeqSet(enc), ia, ib, prm, np.array(g["matrix"]))
+    for k, p in enumerate(g["pairs"]):
+        if prm.vtype:
+            assert float(scores[k]) == p["score"], (p["i"], p["j"])
+        else:
+            assert abs(float(scores[k]) - p["score"]) <= 1e-5 * max(1.0, abs(p["score"])), (p["i"], p["j"])
+        assert P.stdskl(raw[k]) == [tuple(x) for x in p["skl"]], (p["i"], p["j"])
+
+
+def test_integer_goldens_through_float_path(ctx, monkeypatch):
+    """PG_FORCE_FLOAT=1 sends integral affine cases to K3 too: both kernels must agree with the reference."""
+    monkeypatch.setenv("PG_FORCE_FLOAT", "1")
+    for name in ("align_p16_blosum62", "align_ragged", "align_long1300"):
+        g = golden(name)
+        enc = [seqcode.encode_protein(s) for s in g["seqs"]]
+        ia = [p["i"] for p in g["pairs"]]
+        ib = [p["j"] for p in g["pairs"]]
+        scores, raw = ctx.align_pairs(P.SeqSet(enc), ia, ib, _params(g), np.array(g["matrix"]))
+        for k, p in enumerate(g["pairs"]):
+            assert float(scores[k]) == p["score"], (name, p["i"], p["j"])
+            assert P.stdskl(raw[k]) == [tuple(x) for x in p["skl"]], (name, p["i"], p["j"])
 
 
 def test_raw_corner_lists_match_oracle_fuzz(ctx, oracle):
