@@ -61,13 +61,32 @@ def test_golden_alignments_float_path(ctx, name):
     ia = [p["i"] for p in g["pairs"]]
     ib = [p["j"] for p in g["pairs"]]
     prm = _params(g)
-    scores, raw = ctx.align_pairs(P.SeqSet(enc), ia, ib, prm, np.array(g["matrix"]))
+    M = np.array(g["matrix"])
+    scores, raw = ctx.align_pairs(P.SeqSet(enc), ia, ib, prm, M)
+    near_ties = 0
     for k, p in enumerate(g["pairs"]):
         if prm.vtype:
             assert float(scores[k]) == p["score"], (p["i"], p["j"])
         else:
             assert abs(float(scores[k]) - p["score"]) <= 1e-5 * max(1.0, abs(p["score"])), (p["i"], p["j"])
-        assert P.stdskl(raw[k]) == [tuple(x) for x in p["skl"]], (p["i"], p["j"])
+        pts = P.stdskl(raw[k])
+        if pts == [tuple(x) for x in p["skl"]]:
+            continue
+        # Documented near-tie (BASELINE north_star): the reference's float build and the kernel's double
+        # arithmetic may pick different co-optimal paths when two candidates differ by < 1e-5 relative.
+        # Only allowed for the float flavour with non-integral scores; the path we return must be a valid
+        # lattice path whose own score equals the reference's optimum within the tolerance.
+        assert not prm.vtype and prm.alprm.ls < 3, (p["i"], p["j"])
+        a, b = enc[p["i"]], enc[p["j"]]
+        assert pts[0] == (0, 0) and pts[-1] == (len(a), len(b))
+        sc = 0.0
+        for (m0, n0), (m1, n1) in zip(pts[:-1], pts[1:]):
+            dm, dn = m1 - m0, n1 - n0
+            assert dm >= 0 and dn >= 0 and (dm == dn or dm == 0 or dn == 0)
+            sc += sum(M[a[m0 + t], b[n0 + t]] for t in range(dm)) if dm == dn else -(prm.alprm.v + prm.alprm.u * (dm + dn))
+        assert abs(sc - p["score"]) <= 1e-5 * max(1.0, abs(p["score"])), (p["i"], p["j"], sc, p["score"])
+        near_ties += 1
+    assert near_ties <= 0.05 * len(g["pairs"]), near_ties
 
 
 def test_integer_goldens_through_float_path(ctx, monkeypatch):
