@@ -76,7 +76,8 @@ def _pg_group(S):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libprrn_gpu.so")
+    # PRRN_GPU_LIB: another build of the same library (A/B measurements); default: the in-tree build
+    return os.environ.get("PRRN_GPU_LIB") or os.path.join(_HERE, "libprrn_gpu.so")
 
 
 def declared_symbols():

@@ -28,31 +28,48 @@
 
 namespace {
 
-constexpr int T = K3_THREADS;
+constexpr int CTA = K3_THREADS;     // threads per CTA; an alignment gets TG of them (TG = 32 .. 256)
+constexpr int RING = 4;             // prefetch ring depth for the parked row (records n, n+1 are read at step n)
+constexpr int PFN = 4;              // prefetch words per thread (3 * stride <= PFN * TG, else no ring)
 
-constexpr int RING = 4;     // prefetch ring depth for the parked row (records n, n+1 are read at step n)
-
-// words of shared memory one pair needs for its wavefront records (0 = keep them in the global arena)
-__host__ __device__ inline size_t k3_smem_words(int st, int Noll)
+// words of shared memory one alignment needs for its wavefront records
+__host__ __device__ inline size_t k3_smem_words(int st, int Noll, int tg)
 {
-    return (size_t)st * ((Noll == 3 ? 9 : 6) * T + 1 + 3 * RING);
+    return (size_t)st * ((Noll == 3 ? 9 : 6) * tg + 1 + 3 * RING);
 }
 
-__global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
+// barrier over the TG threads that share one alignment (named barrier g + 1; a warp needs none)
+template <int TG>
+__device__ __forceinline__ void group_sync(int g)
 {
+    if (TG == 32) __syncwarp();
+    else if (TG == CTA) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(TG) : "memory");
+}
+
+// TG threads per alignment: the whole CTA for few pairs (latency), down to one warp per alignment for
+// large batches (no block barrier at all, 95 % of the lane-steps inside the matrix instead of 72 %).
+template <int TG>
+__global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
+{
+    constexpr int NG = CTA / TG;        // alignments in flight per CTA
     extern __shared__ __align__(16) int sm_dyn[];
-    __shared__ int sm_pair;
-    __shared__ int sm_vmf;
-    __shared__ int sm_last_ptr;
-    __shared__ double sm_last_val;
-    const int t = threadIdx.x;
-    int* const arena = a.arena + (size_t)blockIdx.x * a.arena_words;
-    K3Vmf* const vmf = a.vmf + (size_t)blockIdx.x * a.vmf_cap;
+    __shared__ int sm_pair[NG];
+    __shared__ int sm_vmf[NG];
+    __shared__ int sm_last_ptr[NG];
+    __shared__ double sm_last_val[NG];
+    const int g = threadIdx.x / TG;
+    const int t = threadIdx.x - g * TG;
+    const int slot = blockIdx.x * NG + g;
+    int* const arena = a.arena + (size_t)slot * a.arena_words;
+    K3Vmf* const vmf = a.vmf + (size_t)slot * a.vmf_cap;
+    int* const sm_grp = sm_dyn + (size_t)g * (a.smem_bytes / 4 / NG);
+    const size_t sm_grp_words = (size_t)(a.smem_bytes / 4 / NG);
 
     for (;;) {
-        if (t == 0) sm_pair = atomicAdd(a.counter, 1);
-        __syncthreads();
-        const int pi = sm_pair;
+        if (t == 0) sm_pair[g] = atomicAdd(a.counter, 1);
+        group_sync<TG>(g);
+        const int pi = sm_pair[g];
         if (pi >= a.npairs) break;
         const K3Pair& P = a.pairs[pi];
         const K3Group A = P.a;
@@ -68,52 +85,50 @@ __global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
         int* const colH = rowG2 + (size_t)(LS + 2) * st;
         int* const gwave = colH + (size_t)(LQ + 2) * st;
         // wavefront records: shared memory when they fit, else the arena
-        const bool in_smem = k3_smem_words(st, p.Noll) * 4 <= (size_t)a.smem_bytes;
-        int* const wave = in_smem ? sm_dyn : gwave;
+        const bool in_smem = k3_smem_words(st, p.Noll, TG) <= sm_grp_words;
+        int* const wave = in_smem ? sm_grp : gwave;
         int* const ringH = wave;                            // [RING] prefetched rowH records
         int* const ringG = ringH + (size_t)RING * st;
         int* const ringG2 = ringG + (size_t)RING * st;
         int* const black = ringG2 + (size_t)RING * st;
-        int* const pubH = black + st;                       // [3][T]
-        int* const pubG = pubH + (size_t)3 * T * st;        // [2][T]
-        int* const F1 = pubG + (size_t)2 * T * st;          // [T]
-        int* const pubG2 = F1 + (size_t)T * st;             // [2][T]   (two-piece only)
-        int* const F2 = pubG2 + (size_t)2 * T * st;         // [T]
+        int* const pubH = black + st;                       // [3][TG]
+        int* const pubG = pubH + (size_t)3 * TG * st;       // [2][TG]
+        int* const F1 = pubG + (size_t)2 * TG * st;         // [TG]
+        int* const pubG2 = F1 + (size_t)TG * st;            // [2][TG]   (two-piece only)
+        int* const F2 = pubG2 + (size_t)2 * TG * st;        // [TG]
         // ---- reset the records this pair can read before writing
-        for (int i = t; i < LS + 2; i += T) {
+        for (int i = t; i < LS + 2; i += TG) {
             k3_reset(p, rowH + (size_t)i * st); k3_reset(p, rowG + (size_t)i * st);
             if (n3) k3_reset(p, rowG2 + (size_t)i * st);
         }
-        for (int i = t; i < LQ + 2; i += T) k3_reset(p, colH + (size_t)i * st);
-        for (int g = 0; g < 3; ++g) k3_reset(p, pubH + ((size_t)g * T + t) * st);
-        for (int g = 0; g < 2; ++g) { k3_reset(p, pubG + ((size_t)g * T + t) * st); if (n3) k3_reset(p, pubG2 + ((size_t)g * T + t) * st); }
+        for (int i = t; i < LQ + 2; i += TG) k3_reset(p, colH + (size_t)i * st);
+        for (int k = 0; k < 3; ++k) k3_reset(p, pubH + ((size_t)k * TG + t) * st);
+        for (int k = 0; k < 2; ++k) { k3_reset(p, pubG + ((size_t)k * TG + t) * st); if (n3) k3_reset(p, pubG2 + ((size_t)k * TG + t) * st); }
         if (t < RING) { k3_reset(p, ringH + (size_t)t * st); k3_reset(p, ringG + (size_t)t * st); k3_reset(p, ringG2 + (size_t)t * st); }
         if (t == 0) k3_reset(p, black);
-        __syncthreads();
+        group_sync<TG>(g);
         // ---- initB (fwd2c.h:138-176): origin, then the two boundary chains (one thread each)
         if (t == 0) {
             vmf[0].m = 0; vmf[0].n = 0; vmf[0].p = 0;                       // skip 0-th record (:361)
             vmf[1].m = P.al; vmf[1].n = P.bl; vmf[1].p = 0;                 // origin
-            sm_vmf = 2;
+            sm_vmf[g] = 2;
             k3_setval(colH, 0); k3_setdg(colH, K3_DIAG, 0); K3_PTR(colH) = 1;
             const int rr = LQ < -p.lw ? LQ : -p.lw;
             for (int k = 1; k <= rr; ++k) k3_boundary_col(p, A, B, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
         }
-        if (t == 32) {
+        if (t == TG / 2) {
             k3_setval(rowH, 0); k3_setdg(rowH, K3_DIAG, 0); K3_PTR(rowH) = 1;
             const int rr = LS < p.up ? LS : p.up;
             for (int k = 1; k <= rr; ++k) k3_boundary_row(p, A, B, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
         }
-        __syncthreads();
+        group_sync<TG>(g);
 
-        // prefetch role of this thread: word pw of record array pa (0 rowH, 1 rowG, 2 rowG2)
-        const int pa = t / st, pw = t - pa * st;
-        const bool pf_thread = pa < (n3 ? 3 : 2);
-        const int* const pf_src = pa == 0 ? rowH : (pa == 1 ? rowG : rowG2);
-        int* const pf_dst = pa == 0 ? ringH : (pa == 1 ? ringG : ringG2);
+        // prefetch of the parked row: word w of the three records (rowH, rowG, rowG2) of one column
+        const int pf_words = (n3 ? 3 : 2) * st;
+        const bool ring_ok = pf_words <= PFN * TG;
 
-        for (int pbase = 0; pbase < LQ; pbase += T) {
-            const int rows = LQ - pbase < T ? LQ - pbase : T;
+        for (int pbase = 0; pbase < LQ; pbase += TG) {
+            const int rows = LQ - pbase < TG ? LQ - pbase : TG;
             const bool last_pass = pbase + rows == LQ;
             const int m = pbase + t;
             const int ia = m + 1;
@@ -123,18 +138,33 @@ __global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
             bool started = false;
             const int nsteps = LS + rows - 1;
             // ring: records 0 and 1 of the parked row before the first step
-            if (pf_thread) {
-                pf_dst[pw] = __ldcg(pf_src + pw);
-                if (LS + 1 >= 1) pf_dst[st + pw] = __ldcg(pf_src + st + pw);
+            if (ring_ok) {
+                for (int w = t; w < pf_words; w += TG) {
+                    const int pa = w / st, pw = w - pa * st;
+                    const int* src = pa == 0 ? rowH : (pa == 1 ? rowG : rowG2);
+                    int* dst = pa == 0 ? ringH : (pa == 1 ? ringG : ringG2);
+                    dst[pw] = __ldcg(src + pw);
+                    dst[st + pw] = __ldcg(src + st + pw);
+                }
             }
-            __syncthreads();
+            group_sync<TG>(g);
             for (int s = 0; s < nsteps; ++s) {
                 const int n = s - t;
                 const int r = n - m;
                 // prefetch record s+2 of the parked row (read by thread 0 at steps s+1, s+2)
-                int pf_val = 0;
-                const bool pf_now = pf_thread && s + 2 <= LS + 1;
-                if (pf_now) pf_val = __ldcg(pf_src + (size_t)(s + 2) * st + pw);
+                int pf_val[PFN];
+                const bool pf_now = ring_ok && s + 2 <= LS + 1;
+                if (pf_now) {
+#pragma unroll
+                    for (int q = 0; q < PFN; ++q) {
+                        const int w = t + q * TG;
+                        if (w < pf_words) {
+                            const int pa = w / st, pw = w - pa * st;
+                            const int* src = pa == 0 ? rowH : (pa == 1 ? rowG : rowG2);
+                            pf_val[q] = __ldcg(src + (size_t)(s + 2) * st + pw);
+                        }
+                    }
+                }
                 if (t < rows && n >= 0 && n < LS && r >= p.lw && r <= p.up) {
                     const int ib = n + 1;
                     if (!started) {
@@ -144,21 +174,24 @@ __global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
                         if (n3) k3_reset(p, f2);
                     }
                     const int g3a = (s + 2) % 3, g3d = (s + 1) % 3, g2a = (s + 1) & 1;
-                    const int* hdiag = n == 0 ? colH + (size_t)m * st
-                                     : (t == 0 ? ringH + (size_t)(n % RING) * st : pubH + ((size_t)g3d * T + (t - 1)) * st);
+                    const int* parkedH0 = ring_ok ? ringH + (size_t)(n % RING) * st : rowH + (size_t)n * st;
+                    const int* parkedH1 = ring_ok ? ringH + (size_t)((n + 1) % RING) * st : rowH + (size_t)(n + 1) * st;
+                    const int* parkedG1 = ring_ok ? ringG + (size_t)((n + 1) % RING) * st : rowG + (size_t)(n + 1) * st;
+                    const int* parkedG21 = ring_ok ? ringG2 + (size_t)((n + 1) % RING) * st : rowG2 + (size_t)(n + 1) * st;
+                    const int* hdiag = n == 0 ? colH + (size_t)m * st : (t == 0 ? parkedH0 : pubH + ((size_t)g3d * TG + (t - 1)) * st);
                     const bool above_in = r + 1 <= p.up;
-                    const int* habove = !above_in ? black : (t == 0 ? ringH + (size_t)((n + 1) % RING) * st : pubH + ((size_t)g3a * T + (t - 1)) * st);
-                    const int* gabove = (!above_in || m == 0) ? black : (t == 0 ? ringG + (size_t)((n + 1) % RING) * st : pubG + ((size_t)g2a * T + (t - 1)) * st);
-                    const int* g2above = (!above_in || m == 0) ? black : (t == 0 ? ringG2 + (size_t)((n + 1) % RING) * st : pubG2 + ((size_t)g2a * T + (t - 1)) * st);
+                    const int* habove = !above_in ? black : (t == 0 ? parkedH1 : pubH + ((size_t)g3a * TG + (t - 1)) * st);
+                    const int* gabove = (!above_in || m == 0) ? black : (t == 0 ? parkedG1 : pubG + ((size_t)g2a * TG + (t - 1)) * st);
+                    const int* g2above = (!above_in || m == 0) ? black : (t == 0 ? parkedG21 : pubG2 + ((size_t)g2a * TG + (t - 1)) * st);
                     const bool left_in = r - 1 >= p.lw;
-                    const int* hleft = n == 0 ? colH + (size_t)(m + 1) * st : (left_in ? pubH + ((size_t)g3a * T + t) * st : black);
-                    int* hout = pubH + ((size_t)(s % 3) * T + t) * st;
-                    int* gout = pubG + ((size_t)(s & 1) * T + t) * st;
-                    int* g2out = pubG2 + ((size_t)(s & 1) * T + t) * st;
+                    const int* hleft = n == 0 ? colH + (size_t)(m + 1) * st : (left_in ? pubH + ((size_t)g3a * TG + t) * st : black);
+                    int* hout = pubH + ((size_t)(s % 3) * TG + t) * st;
+                    int* gout = pubG + ((size_t)(s & 1) * TG + t) * st;
+                    int* g2out = pubG2 + ((size_t)(s & 1) * TG + t) * st;
                     const double dab = P.simmat ? __ldg(P.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
                     if (k3_cell(p, A, B, ia, ib, m == 0, n == 0, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
                                 hout, gout, g2out, black)) {
-                        const int id = atomicAdd(&sm_vmf, 1);       // Vmf::add (fwd2c.h:465-467)
+                        const int id = atomicAdd(&sm_vmf[g], 1);    // Vmf::add (fwd2c.h:465-467)
                         if (id < a.vmf_cap) { vmf[id].m = m + P.al; vmf[id].n = n + P.bl; vmf[id].p = K3_PTR(hout); }
                         K3_PTR(hout) = id;
                     }
@@ -167,54 +200,88 @@ __global__ void __launch_bounds__(T, 2) k3_fill_kernel(const K3Args a)
                             k3_copy(p, rowH + (size_t)(n + 1) * st, hout);
                             k3_copy(p, rowG + (size_t)(n + 1) * st, gout);
                             if (n3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
-                        } else if (n == LS - 1) { sm_last_ptr = K3_PTR(hout); sm_last_val = k3_val(hout); }
+                        } else if (n == LS - 1) { sm_last_ptr[g] = K3_PTR(hout); sm_last_val[g] = k3_val(hout); }
                     }
                 }
-                if (pf_now) pf_dst[(size_t)((s + 2) % RING) * st + pw] = pf_val;
-                __syncthreads();
+                if (pf_now) {
+#pragma unroll
+                    for (int q = 0; q < PFN; ++q) {
+                        const int w = t + q * TG;
+                        if (w < pf_words) {
+                            const int pa = w / st, pw = w - pa * st;
+                            int* dst = pa == 0 ? ringH : (pa == 1 ? ringG : ringG2);
+                            dst[(size_t)((s + 2) % RING) * st + pw] = pf_val[q];
+                        }
+                    }
+                }
+                group_sync<TG>(g);
             }
         }
         // ---- final record + Vmf::traceback (fwd2c.h:475-481, vmf.cc:103-119)
         if (t == 0) {
             int* out = a.out_pts + 2 * P.out_off;
             int cnt = 0;
-            const int nrec = sm_vmf;
+            const int nrec = sm_vmf[g];
             if (nrec >= a.vmf_cap) cnt = -1;                        // record store overflow: reported, never silent
             else {
                 out[0] = LQ + P.al; out[1] = LS + P.bl; cnt = 1;
-                for (int q = sm_last_ptr;; q = vmf[q].p) {
+                for (int q = sm_last_ptr[g];; q = vmf[q].p) {
                     if (cnt >= P.out_cap) { cnt = -1; break; }
                     out[2 * cnt] = vmf[q].m; out[2 * cnt + 1] = vmf[q].n; ++cnt;
                     if (!vmf[q].p) break;
                 }
             }
             a.out_cnt[pi] = cnt;
-            a.out_score[pi] = sm_last_val;
+            a.out_score[pi] = sm_last_val[g];
         }
-        __syncthreads();
+        group_sync<TG>(g);
     }
 }
 
-}  // namespace
-
-int k3_threads() { return T; }
-int k3_blocks_per_sm() { return 2; }
-size_t k3_wave_words(int stride, int Noll) { return k3_smem_words(stride, Noll); }
-
-// smem_bytes: dynamic shared memory per CTA (the largest wavefront of the batch, capped by the caller)
-cudaError_t k3_launch(const K3Args& a, int grid_blocks, cudaStream_t st)
+template <int TG>
+cudaError_t launch_tg(const K3Args& a, int grid_blocks, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel<TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     // The gap-profile lists and score rows stream through L1.  Few pairs (latency: Prrn::best_of_n sized
     // batches): one CTA per SM and the rest of the unified array as L1 (measured 28 vs 37 ms for 24
-    // pairs); more pairs than SMs (throughput): two CTAs per SM win (59 vs 68 ms for 384 pairs).
+    // pairs); more CTAs than SMs (throughput): two CTAs per SM win (59 vs 68 ms for 384 pairs).
     // PG_K3_CARVEOUT = percent of shared memory overrides.
     int carve = grid_blocks > 148 ? 100 : (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
     if (const char* cv = getenv("PG_K3_CARVEOUT")) carve = atoi(cv);
     if (carve > 100) carve = 100;
-    e = cudaFuncSetAttribute(k3_fill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    e = cudaFuncSetAttribute(k3_fill_kernel<TG>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return e;
-    k3_fill_kernel<<<grid_blocks, T, a.smem_bytes, st>>>(a);
+    k3_fill_kernel<TG><<<grid_blocks, CTA, a.smem_bytes, st>>>(a);
     return cudaGetLastError();
+}
+
+}  // namespace
+
+int k3_threads() { return CTA; }
+int k3_blocks_per_sm() { return 2; }
+size_t k3_wave_words(int stride, int Noll, int tg) { return k3_smem_words(stride, Noll, tg); }
+
+// Threads per alignment for a batch (PG_K3_TG overrides).  Measured on B200, partitions of a 200 x ~500
+// family: 384 pairs -> 256 threads 60 ms, 128: 72, 64: 81, 32: 155; 1,536 pairs -> 256: 193 ms, 128: 176,
+// 64: 189, 32: 314.  The whole CTA per alignment wins until the batch is several waves deep; a warp per
+// alignment loses (every 32 rows pass through the parked-row buffer in L2).
+int k3_pick_tg(int64_t npairs, int sm_count)
+{
+    if (const char* e = getenv("PG_K3_TG")) {
+        const int v = atoi(e);
+        if (v == 32 || v == 64 || v == 128 || v == 256) return v;
+    }
+    return npairs > (int64_t)8 * sm_count ? 128 : 256;
+}
+
+// a.smem_bytes: dynamic shared memory per CTA = (CTA / tg) x the largest wavefront of the batch (capped)
+cudaError_t k3_launch(const K3Args& a, int tg, int grid_blocks, cudaStream_t st)
+{
+    switch (tg) {
+    case 32: return launch_tg<32>(a, grid_blocks, st);
+    case 64: return launch_tg<64>(a, grid_blocks, st);
+    case 128: return launch_tg<128>(a, grid_blocks, st);
+    default: return launch_tg<256>(a, grid_blocks, st);
+    }
 }

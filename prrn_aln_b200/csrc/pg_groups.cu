@@ -116,6 +116,8 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     std::vector<K3Pair> pairs(npairs);
     std::vector<int64_t> cells(npairs), outoff(npairs + 1);
     size_t blob = 0, arena_words = 0, wave_bytes = 0;
+    const int tg = k3_pick_tg(npairs, c->sm_count);         // threads per alignment
+    const int ngrp = k3_threads() / tg;                     // alignments in flight per CTA
     int64_t max_cells = 0;
     outoff[0] = 0;
     for (int64_t i = 0; i < npairs; ++i) {
@@ -157,8 +159,8 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
         kp.v2divv1 = P.BasicGOP < 0 ? P.LongGOP / P.BasicGOP : 0;
         const int LQ = A.right - A.left, LS = B.right - B.left;
         const size_t st = (size_t)k3_stride(kp.capa, kp.capb);
-        arena_words = std::max(arena_words, st * (size_t)(3 * (LS + 2) + (LQ + 2)) + k3_wave_words((int)st, 3));
-        wave_bytes = std::max(wave_bytes, 4 * k3_wave_words((int)st, P.Noll));
+        arena_words = std::max(arena_words, st * (size_t)(3 * (LS + 2) + (LQ + 2)) + k3_wave_words((int)st, 3, tg));
+        wave_bytes = std::max(wave_bytes, 4 * k3_wave_words((int)st, P.Noll, tg));
         if (A.len > 65000 || B.len > 65000) {
             free(offs);
             return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: groups longer than 65,000 columns exceed the 16-bit gap-state lists");
@@ -172,13 +174,14 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
         pairs[i].pad = 0;
         outoff[i + 1] = outoff[i] + pairs[i].out_cap;
     }
-    const int grid = (int)std::min<int64_t>(npairs, (int64_t)c->sm_count * k3_blocks_per_sm());
+    const int grid = (int)std::min<int64_t>((npairs + ngrp - 1) / ngrp, (int64_t)c->sm_count * k3_blocks_per_sm());
+    const size_t slots = (size_t)grid * ngrp;               // arenas / path stores
     const int64_t vmf_cap = max_cells + 8;
     if (vmf_cap > 0x7fffffff) { free(offs); return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: DP matrix too large for the path store"); }
 
     // ---- stage
-    int rc = pg_int_ensure_cap(c, &c->d_garena, &c->garena_cap, arena_words * 4 * (size_t)grid);
-    if (!rc) rc = pg_int_ensure_cap(c, &c->d_gvmf, &c->gvmf_cap, sizeof(K3Vmf) * (size_t)vmf_cap * grid);
+    int rc = pg_int_ensure_cap(c, &c->d_garena, &c->garena_cap, arena_words * 4 * slots);
+    if (!rc) rc = pg_int_ensure_cap(c, &c->d_gvmf, &c->gvmf_cap, sizeof(K3Vmf) * (size_t)vmf_cap * slots);
     const size_t o_pts = 0, o_cnt = up16(o_pts + 8 * (size_t)outoff[npairs]), o_scr = up16(o_cnt + 4 * (size_t)npairs),
                  obytes = up16(o_scr + 8 * (size_t)npairs);
     if (!rc) rc = pg_int_ensure_cap(c, &c->d_gout, &c->gout_cap, obytes);
@@ -245,14 +248,17 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     ka.out_score = (double*)(go + o_scr);
     // wavefront records live in shared memory when they fit (two CTAs per SM up to ~110 KB each, one up to
     // 220 KB); pairs whose records are larger fall back to the L2-resident arena inside the kernel
-    ka.smem_bytes = (int32_t)std::min<size_t>(wave_bytes, (size_t)220 * 1024);
+    {
+        const size_t unit = 16 * (size_t)ngrp, cap = (size_t)220 * 1024 / unit * unit;
+        ka.smem_bytes = (int32_t)std::min((wave_bytes * ngrp + unit - 1) / unit * unit, cap);
+    }
     std::vector<int32_t> h_pts(2 * (size_t)outoff[npairs]), h_cnt(npairs);
     std::vector<double> h_scr(npairs);
     e = cudaMemcpyAsync(d, h.data(), h.size(), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counter, 0, sizeof(int32_t), c->stream);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev0, c->stream);
     if (e == cudaSuccess && sim_bytes) e = k4_launch(k4, k4_blocks, c->stream);
-    if (e == cudaSuccess) e = k3_launch(ka, grid, c->stream);
+    if (e == cudaSuccess) e = k3_launch(ka, tg, grid, c->stream);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev1, c->stream);
     c->ev_valid = e == cudaSuccess;
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_pts.data(), ka.out_pts, 8 * (size_t)outoff[npairs], cudaMemcpyDeviceToHost, c->stream);

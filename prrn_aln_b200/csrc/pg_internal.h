@@ -250,10 +250,11 @@ int k2_rows_per_lane();
 int k2_warps_per_block();
 int k2_blocks_per_sm();
 // k3_groups.cu
-cudaError_t k3_launch(const K3Args& a, int grid_blocks, cudaStream_t st);
+cudaError_t k3_launch(const K3Args& a, int tg, int grid_blocks, cudaStream_t st);
 int k3_threads();
 int k3_blocks_per_sm();
-size_t k3_wave_words(int stride, int Noll);
+int k3_pick_tg(int64_t npairs, int sm_count);
+size_t k3_wave_words(int stride, int Noll, int tg);
 // k4_contract.cu
 cudaError_t k4_launch(const K4Args& a, int total_blocks, cudaStream_t st);
 // dpx_peak.cu
