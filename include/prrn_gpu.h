@@ -83,6 +83,17 @@ int pg_align_pairs(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx, c
                    void *out_scores, int64_t **out_offs, pg_skl **out_pts);
 void pg_free(void *p);
 
+/* ---- per-call level: stands behind
+ *   SKL*  alignB_ng(const Seq* seqs[2], const PwdB* pwd, VTYPE* scr)                src/fwd2b1.cc:1347
+ *   VTYPE HomScoreB_ng(const Seq* seqs[2], const PwdB* pwd, long rr[])              src/fwd2b1.cc:1317
+ * (Aln2b1::initB_ng :64, forwardB_ng :145, lastB_ng :100, trcbkalignB_ng :1025, globalB_ng :1286) for a
+ * batch of pairs: prrn5's DynAln distances (src/adjmat.cc:84).  Global mode, tgapf == 1, DP matrices below
+ * MaxVmfSpace (no linear-space recursion), affine or two-piece.  Same outputs as pg_align_pairs: the score
+ * (== HomScoreB_ng's) and the corner records before stdskl, which the caller runs as globalB_ng does. */
+int pg_align_pairs_ng(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx, const int32_t *b_idx,
+                      int64_t npairs, const pg_params *prm, const void *mtx, int32_t dim,
+                      void *out_scores, int64_t **out_offs, pg_skl **out_pts);
+
 /* ---- per-call level, groups: stands behind
  *   template<class recd_t> SKL* alignC(mSeq* seqs[2], PwdM* pwd, VTYPE* scr, ...)   src/fwd2c.h:670-677
  * for recd_t = DPunit (NGP_ALB, groups without internal gaps), DPunit_hf (HLF_ALB / RHF_ALB) and
@@ -114,7 +125,8 @@ typedef struct {
 } pg_group;
 
 typedef struct {
-    int32_t alnmode;            /* ALN_MODE, src/aln.h:71-76: 6 NGP_ALB, 7 HLF_ALB, 8 RHF_ALB, 9 GPF_ALB */
+    int32_t alnmode;            /* ALN_MODE, src/aln.h:71-76: 6 NGP_ALB, 7 HLF_ALB, 8 RHF_ALB, 9 GPF_ALB
+                                   (100 is internal: the Aln2b1 recurrence behind pg_align_pairs_ng)   */
     int32_t Noll, codonk1;      /* PwdB::Noll, PwdB::codonk1 (src/aln2.cc:100,117)                     */
     int32_t sh;                 /* pwd->alnprm.sh                                                      */
     int32_t kdim;

@@ -125,6 +125,13 @@ typedef struct {
 int orc_align_groups(const orc_group *a, const orc_group *b, const double *mtx, int dim, const orc_gparams *p,
                      double *score, orc_skl *out, int cap, int64_t *cells);
 
+
+/* Aln2b1: trcbkalignB_ng inside globalB_ng (reference src/fwd2b1.cc:64-279,1025-1051,1286-1315) for two
+ * single sequences, global mode, tgapf == 1: the corner records before stdskl (out[0].n = count) and
+ * the forwardB_ng score (== HomScoreB_ng, :1317).  Returns the count, -1 overflow, -2 unsupported mode. */
+int orc_align_b1(const orc_seq *a, const orc_seq *b, const double *mtx, int dim, const orc_params *p,
+                 double *score, orc_skl *out, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -400,6 +400,134 @@ static long o_add(o_store *s, int m, int n, long p)
     return s->n++;
 }
 
+/* ================================================================================================
+ * Aln2b1: alignB_ng / HomScoreB_ng for two single sequences (reference src/fwd2b1.cc: initB_ng :64-98,
+ * forwardB_ng :145-279, lastB_ng :100-143, trcbkalignB_ng :1025-1051, globalB_ng :1286-1315), global
+ * mode with full terminal gap penalties (tgapf == 1, no exgr): the path prrn5's DynAln distances take
+ * (src/adjmat.cc:84).  Differs from Fwd2c<DPunit>: a gap opens on >= (:192,213), G displaces the
+ * diagonal on > and F on >= (:198,219), gap states keep the record of the cell they opened from and
+ * only cells where a diagonal run resumes (NEWD) append a path record.
+ * ================================================================================================ */
+#define DEFINE_ALIGN_B1(VT, SUFFIX, NEVSEL_V)                                                        \
+typedef struct { VT val; long ptr; int dir; } b1_unit_##SUFFIX;                                      \
+static int align_b1_##SUFFIX(const orc_seq *a, const orc_seq *b, const double *mtx, int dim,         \
+                             const orc_params *p, double *score, orc_skl *out, int cap)              \
+{                                                                                                    \
+    typedef b1_unit_##SUFFIX U;                                                                      \
+    const float fu = (float)p->u, fv = (float)p->v, fu1 = (float)p->u1, fsc = (float)p->scale;       \
+    const VT Vab = (VT)(fsc * 1 * 1);                      /* PwdB::PwdB, aln2.cc:97-117 */           \
+    const VT BasicGOP = (VT)(-fv * Vab), BasicGEP = (VT)(-fu * Vab), LongGEP = (VT)(-fu1 * Vab);     \
+    const VT diffu = LongGEP - BasicGEP;                                                             \
+    const VT LongGOP = BasicGOP - diffu * p->k1;                                                     \
+    const int Noll = p->ls < 2 ? 2 : (p->ls > 3 ? 3 : p->ls);                                        \
+    const int codonk1 = p->ls == 3 ? p->k1 : (INT_MAX / 8 * 7);                                      \
+    if (!((float)p->tgapf == 1.f) || a->exgr || b->exgr || p->lcl) return -2;                        \
+    orc_window w;                                                                                    \
+    orc_stripe(a, b, p->sh, &w);                                                                     \
+    const int lw = w.lw, up = w.up;                                                                  \
+    const int al = a->left, ar = a->right, bl = b->left, br = b->right;                              \
+    const U black = {NEVSEL_V, 0, 0};                                                                \
+    o_store st = {0, 0, 0};                                                                          \
+    o_add(&st, 0, 0, 0);                                                                             \
+    const long origin = o_add(&st, al, bl, 0);                                                       \
+    const int NB = br - bl + 2;                                                                      \
+    U *buf = (U *)malloc(sizeof(U) * 6 * (size_t)NB);                                                \
+    U *Hp = buf, *Gp = buf + NB, *G2p = buf + 2 * NB, *Hc = buf + 3 * NB, *Gc = buf + 4 * NB, *G2c = buf + 5 * NB;\
+    for (int j = 0; j < 6 * NB; ++j) buf[j] = black;                                                 \
+    /* initB_ng: origin, boundary row (:71-84) */                                                    \
+    Hp[0].val = 0; Hp[0].dir = G_NEWD; Hp[0].ptr = origin;                                           \
+    {                                                                                                \
+        const float ltg = al ? 1.f : (a->exgl ? 0.f : (float)p->tgapf);                              \
+        int rr = br - al; if (up < rr) rr = up;                                                      \
+        const int r0 = bl - al;                                                                      \
+        for (int r = r0 + 1, i = 1; r <= rr; ++r, ++i) {                                             \
+            VT gpn = (i == 1) ? ((1 > codonk1) ? LongGOP + 1 * LongGEP : BasicGOP + 1 * BasicGEP)    \
+                              : ((i > codonk1) ? LongGEP : BasicGEP);                                \
+            Hp[i].dir = G_HORI; Hp[i].ptr = origin;                                                  \
+            Hp[i].val = Hp[i - 1].val + (VT)(gpn * ltg);                                             \
+        }                                                                                            \
+    }                                                                                                \
+    U colprev = Hp[0];                                                                               \
+    int colk = 0;                                                                                    \
+    const float ltgb = bl ? 1.f : (b->exgl ? 0.f : (float)p->tgapf);                                 \
+    const int rr_col = (bl - ar > lw) ? bl - ar : lw;                                                \
+    for (int m = al; m < ar; ++m) {                                                                  \
+        const int n0 = G_MAX(m + lw, bl), n9 = G_MIN(m + up + 1, br);                                \
+        const double *srow = mtx + (size_t)a->res[m] * dim;                                          \
+        {   /* boundary column (:86-97) */                                                           \
+            int r = bl - 1 - m;                                                                      \
+            if (r >= rr_col) {                                                                       \
+                ++colk;                                                                              \
+                VT gpn = (colk == 1) ? ((1 > codonk1) ? LongGOP + 1 * LongGEP : BasicGOP + 1 * BasicGEP)\
+                                     : ((colk > codonk1) ? LongGEP : BasicGEP);                      \
+                U c; c.dir = G_VERT; c.ptr = origin; c.val = colprev.val + (VT)(gpn * ltgb);         \
+                colprev = c; Hc[0] = c;                                                              \
+            } else Hc[0] = black;                                                                    \
+        }                                                                                            \
+        U f1 = black, f2 = black;                                                                    \
+        for (int n = n0; n < n9; ++n) {                                                              \
+            const int j = n - bl + 1;                                                                \
+            const int above_inband = (n - m + 1 <= up);                                              \
+            const U habove = above_inband ? Hp[j] : black;                                           \
+            const U gabove = (above_inband && m > al) ? Gp[j] : black;                               \
+            const U g2above = (above_inband && m > al) ? G2p[j] : black;                             \
+            const U hleft = (n - 1 >= n0 || n - 1 == bl - 1) ? Hc[j - 1] : black;                    \
+            U h = Hp[j - 1], g, g2 = black;                                                          \
+            int which = 0;     /* 0 diag, 1 g, 2 g2, 3 f1, 4 f2 */                                   \
+            h.val += (VT)srow[b->res[n]];                      /* :181-183 */                        \
+            h.dir = g_isdiag(Hp[j - 1].dir) ? G_DIAG : G_NEWD;                                       \
+            VT mxv = h.val;                                                                          \
+            VT x = habove.val + BasicGOP;                       /* vertical :186-193 */              \
+            if (x >= gabove.val) { g.val = x; g.ptr = habove.ptr; g.dir = G_VERT; } else g = gabove; \
+            g.val += BasicGEP;                                                                       \
+            if (g.val > mxv) { which = 1; mxv = g.val; }                                             \
+            if (Noll == 3) {                                    /* vertical2 :196-205 */             \
+                x = habove.val + LongGOP;                                                            \
+                if (x >= g2above.val) { g2.val = x; g2.ptr = habove.ptr; g2.dir = G_VERT; } else g2 = g2above;\
+                g2.val += LongGEP;                                                                   \
+                if (g2.val > mxv) { which = 2; mxv = g2.val; }                                       \
+            }                                                                                        \
+            x = hleft.val + BasicGOP;                           /* horizontal :207-214 */            \
+            if (x >= f1.val) { f1.val = x; f1.ptr = hleft.ptr; f1.dir = G_HORI; }                    \
+            f1.val += BasicGEP;                                                                      \
+            if (f1.val >= mxv) { which = 3; mxv = f1.val; }                                          \
+            if (Noll == 3) {                                    /* horizontal2 :217-226 */           \
+                x = hleft.val + LongGOP;                                                             \
+                if (x >= f2.val) { f2.val = x; f2.ptr = hleft.ptr; f2.dir = 9 /* HORL */; }          \
+                f2.val += LongGEP;                                                                   \
+                if (f2.val >= mxv) { which = 4; mxv = f2.val; }                                      \
+            }                                                                                        \
+            if (which == 1) h = g; else if (which == 2) h = g2; else if (which == 3) h = f1; else if (which == 4) h = f2;\
+            if (h.dir == G_NEWD || h.dir == G_NEWV || h.dir == G_NEWH) h.ptr = o_add(&st, m, n, h.ptr);\
+            Hc[j] = h; Gc[j] = g; G2c[j] = g2;                                                       \
+        }                                                                                            \
+        U *t;                                                                                        \
+        t = Hp; Hp = Hc; Hc = t; t = Gp; Gp = Gc; Gc = t; t = G2p; G2p = G2c; G2c = t;               \
+    }                                                                                                \
+    const U last = Hp[br - 1 - bl + 1];                         /* lastB_ng with rtgapf == 1 (:141) */\
+    long pp = o_add(&st, ar, br, last.ptr);                                                          \
+    *score = (double)last.val;                                                                       \
+    int cnt = 0, ok = 1;                                                                             \
+    for (long q = pp;; q = st.v[q].p) {                         /* Vmf::traceback */                 \
+        if (cnt + 2 >= cap) { ok = 0; break; }                                                       \
+        out[++cnt].m = st.v[q].m; out[cnt].n = st.v[q].n;                                            \
+        if (!st.v[q].p) break;                                                                       \
+    }                                                                                                \
+    if (ok && (out[cnt].m != al || out[cnt].n != bl)) { out[++cnt].m = al; out[cnt].n = bl; }        /* :1040-1044 */\
+    out[0].m = 1; out[0].n = cnt;                                                                    \
+    free(buf); free(st.v);                                                                           \
+    return ok ? cnt : -1;                                                                            \
+}
+
+DEFINE_ALIGN_B1(float, f32, (-(FLT_MAX / 16 * 7)))
+DEFINE_ALIGN_B1(double, f64, (-(DBL_MAX / 16 * 7)))
+
+int orc_align_b1(const orc_seq *a, const orc_seq *b, const double *mtx, int dim, const orc_params *p,
+                 double *score, orc_skl *out, int cap)
+{
+    return p->vtype ? align_b1_f64(a, b, mtx, dim, p, score, out, cap) : align_b1_f32(a, b, mtx, dim, p, score, out, cap);
+}
+
 DEFINE_GROUP_ALIGN(float, f32, (-(FLT_MAX / 16 * 7)))
 DEFINE_GROUP_ALIGN(double, f64, (-(DBL_MAX / 16 * 7)))
 

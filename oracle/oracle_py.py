@@ -224,3 +224,25 @@ def align_groups(A, B, mtx, gp):
     if cnt < 0:
         raise RuntimeError("corner list overflow")
     return scr.value, [(out[i].m, out[i].n) for i in range(1, cnt + 1)], cells.value
+
+
+def align_b1(a, b, mtx, p, std=True):
+    """alignB_ng restatement (+ stdskl when std): (score, [(m, n), ...])."""
+    L = lib()
+    L.orc_align_b1.restype = C.c_int
+    L.orc_align_b1.argtypes = [C.POINTER(OrcSeq), C.POINTER(OrcSeq), C.POINTER(C.c_double), C.c_int,
+                               C.POINTER(OrcParams), C.POINTER(C.c_double), C.POINTER(OrcSkl), C.c_int]
+    L.orc_stdskl.restype = C.c_int
+    L.orc_stdskl.argtypes = [C.POINTER(OrcSkl), C.POINTER(OrcSkl)]
+    m, mp, dim = _mtx(mtx)
+    cap = 2 * (a.len + b.len) + 8
+    out = (OrcSkl * cap)()
+    scr = C.c_double(0)
+    cnt = L.orc_align_b1(C.byref(a), C.byref(b), mp, dim, C.byref(p), C.byref(scr), out, cap)
+    if cnt < 0:
+        raise RuntimeError("orc_align_b1 failed (%d)" % cnt)
+    if std:
+        out2 = (OrcSkl * (2 * cnt + 4))()
+        cnt = L.orc_stdskl(out, out2)
+        out = out2
+    return scr.value, [(out[i].m, out[i].n) for i in range(1, cnt + 1)]

@@ -33,6 +33,9 @@
 #include <string>
 #include <vector>
 
+// aln.h:334 declares HomScoreB_ng with two arguments; the definition (fwd2b1.cc:1317) takes three
+extern VTYPE HomScoreB_ng(const Seq* seqs[], const PwdB* pwd, long rr[]);
+
 void usage() {}
 template <class seq_t> void AlnServer<seq_t>::setparam(int) {}
 template <class seq_t> int AlnServer<seq_t>::localoption(int&, const char**&) { return 0; }
@@ -300,6 +303,29 @@ int main(int argc, const char** argv)
 		    print_vt(gsi.fstat.val); printf(" %g %g %g %g\n", (double) gsi.fstat.mch,
 			(double) gsi.fstat.mmc, (double) gsi.fstat.gap, (double) gsi.fstat.unp);
 		    gsi.skl = 0;
+		    delete[] skl;
+		    delete pwd;
+		}
+	    }
+	    printf("time %.6f\n", now_s() - t0);
+	} else if (cmd == "alignb") {		// Aln2b1: alignB_ng (stdskl-normalised) + HomScoreB_ng per pair (i<j)
+	    double	t0 = now_s();
+	    for (int j = 1; j < nn; ++j) {
+		for (int i = 0; i < j; ++i) {
+		    const Seq*	sq[2] = {seqs[i], seqs[j]};
+		    PwdB*	pwd = new PwdB(sq);
+		    VTYPE	scr = 0;
+		    SKL*	skl = alignB_ng(sq, pwd, &scr);
+		    long	rr[2] = {0, 0};
+		    VTYPE	hom = HomScoreB_ng(sq, pwd, rr);
+		    printf("alignb %d %d ", i, j);
+		    print_vt(scr); putchar(' '); print_vt(hom);
+		    if (!skl) printf(" skl 0\n");
+		    else {
+			printf(" skl %d %d :", skl->n, skl->m);
+			for (int k = 1; k <= skl->n; ++k) printf(" %d %d", skl[k].m, skl[k].n);
+			putchar('\n');
+		    }
 		    delete[] skl;
 		    delete pwd;
 		}

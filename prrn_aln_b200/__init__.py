@@ -7,5 +7,5 @@ fallback: calls raise PgError when the CUDA library or a device is missing.
 """
 from .api import (ALPRM, Context, PgError, Params, SeqSet, alnScoreD, calcdist, calcdist_cells,  # noqa: F401
                   elem, lib_path, load_library, declared_symbols, align2, stdskl, packed_plan_coverage,
-                  GParams, group_cells, gparams_from_pwd)
+                  GParams, group_cells, gparams_from_pwd, alignB_ng)
 from . import groups  # noqa: F401

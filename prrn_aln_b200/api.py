@@ -114,6 +114,7 @@ def load_library():
     L.pg_group_cells.argtypes = [C.POINTER(_PgGroup), C.POINTER(_PgGroup), C.c_int32]
     L.pg_last_kernel_ms.restype = C.c_double
     L.pg_last_kernel_ms.argtypes = [C.c_void_p]
+    L.pg_align_pairs_ng.argtypes = L.pg_align_pairs.argtypes
     L.pg_free.argtypes = [C.c_void_p]
     L.pg_free.restype = None
     L.pg_calcdist.argtypes = [C.c_void_p, C.POINTER(_PgSeqs), C.POINTER(Params), C.c_void_p, C.c_int32,
@@ -218,8 +219,9 @@ class Context:
         return (out, ends) if want_ends else out
 
     # -- per-call level: batch of alignC<DPunit> ------------------------------------------------
-    def align_pairs(self, seqs, a_idx, b_idx, prm, mtx):
-        """Returns (scores, [corner array (n x 2, Vmf back-walk order) per pair]) as alignC does."""
+    def align_pairs(self, seqs, a_idx, b_idx, prm, mtx, ng=False):
+        """Returns (scores, [corner array (n x 2, Vmf back-walk order) per pair]) as alignC does; ng=True:
+        the Aln2b1 recurrence of alignB_ng / HomScoreB_ng (src/fwd2b1.cc) instead of Fwd2c<DPunit>."""
         a = np.ascontiguousarray(a_idx, dtype=np.int32)
         b = np.ascontiguousarray(b_idx, dtype=np.int32)
         m = _mtx_for(prm, mtx)
@@ -227,8 +229,9 @@ class Context:
         offs = C.POINTER(C.c_int64)()
         pts = C.POINTER(C.c_int32)()
         cs = seqs.c_struct()
-        self._check(self.L.pg_align_pairs(self.h, C.byref(cs), a.ctypes.data, b.ctypes.data, len(a), C.byref(prm),
-                                          m.ctypes.data, m.shape[0], out.ctypes.data, C.byref(offs), C.byref(pts)))
+        fn = self.L.pg_align_pairs_ng if ng else self.L.pg_align_pairs
+        self._check(fn(self.h, C.byref(cs), a.ctypes.data, b.ctypes.data, len(a), C.byref(prm),
+                       m.ctypes.data, m.shape[0], out.ctypes.data, C.byref(offs), C.byref(pts)))
         try:
             o = np.ctypeslib.as_array(offs, shape=(len(a) + 1,)).copy()
             total = int(o[-1])
@@ -388,6 +391,15 @@ def align2(seqs, sm, prm=None, pairs=None, device=0):
     prm = prm or Params()
     pairs = [(0, 1)] if pairs is None else pairs
     scores, raw = _ctx(device).align_pairs(seqs, [p[0] for p in pairs], [p[1] for p in pairs], prm, sm)
+    return scores, [stdskl(r) for r in raw]
+
+
+def alignB_ng(seqs, sm, prm=None, pairs=None, device=0):
+    """SKL* alignB_ng(const Seq* seqs[2], const PwdB* pwd, VTYPE* scr) -- reference src/fwd2b1.cc:1347 --
+    for a batch: Aln2b1 fill + traceback on the GPU, stdskl on the host.  Returns (scores, [corner list])."""
+    prm = prm or Params()
+    pairs = [(0, 1)] if pairs is None else pairs
+    scores, raw = _ctx(device).align_pairs(seqs, [p[0] for p in pairs], [p[1] for p in pairs], prm, sm, ng=True)
     return scores, [stdskl(r) for r in raw]
 
 

@@ -41,7 +41,7 @@ struct K3Group {
 };
 
 struct K3Prm {
-    int32_t mode;           // 0 DPunit, 1 DPunit_hf, 2 DPunit_pf
+    int32_t mode;           // 0 DPunit, 1 DPunit_hf, 2 DPunit_pf, 3 Aln2b1 (RVPD records, fwd2b1.cc)
     int32_t Noll, codonk1;
     int32_t lw, up;         // band in window-relative coordinates (r = n - m)
     int32_t capa, capb;     // list capacities (pairs)
@@ -49,6 +49,9 @@ struct K3Prm {
     double u;               // alnprm.u as the reference's float
     double wgop, bgop;      // Weighted_GOP, Basic_GOP
     double u2divu1, v2divv1;
+    // mode 3 (Aln2b1, src/fwd2b1.cc): PwdB penalties and the leading-gap factors of initB_ng
+    double gop1, gep1, gop2, gep2;      // BasicGOP, BasicGEP, LongGOP, LongGEP
+    double ltg_a, ltg_b;                // a.left ? 1 : (a.exgl ? 0 : tgapf), same for b
 };
 
 // ---- record access -------------------------------------------------------------------------------
@@ -297,6 +300,51 @@ PG_HD bool k3_cell(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, i
     if (k3_val(mx) > k3_val(hout)) k3_copy(p, hout, mx);        // fwd2c.h:453
     const int dir = k3_dir(hout);
     return dir == K3_NEWD || dir == K3_NEWV || dir == K3_NEWH;   // fwd2c.h:465-467
+}
+
+// One DP cell of Aln2b1::forwardB_ng (src/fwd2b1.cc:176-249, global mode): a gap opens on >=, the
+// vertical state displaces the diagonal on >, the horizontal one on >=; a gap state keeps the path
+// pointer of the cell it opened from; only a resumed diagonal run (NEWD) appends a path record.
+PG_HD bool k3_cell_b1(const K3Prm& p, double dab, const int* hdiag, const int* habove, const int* gabove,
+                      const int* g2above, const int* hleft, int* f1, int* f2, int* hout, int* gout, int* g2out)
+{
+    k3_setval(hout, k3_val(hdiag) + dab);                               // :181-183
+    K3_PTR(hout) = K3_PTR(hdiag);
+    k3_setdg(hout, k3_isdiag(k3_dir(hdiag)) ? K3_DIAG : K3_NEWD, 0);
+    const int* mx = hout;
+    double x = k3_val(habove) + p.gop1;                                 // vertical :186-193
+    if (x >= k3_val(gabove)) { k3_setval(gout, x); K3_PTR(gout) = K3_PTR(habove); k3_setdg(gout, K3_VERT, 0); }
+    else { gout[0] = gabove[0]; gout[1] = gabove[1]; gout[2] = gabove[2]; gout[3] = gabove[3]; }
+    k3_setval(gout, k3_val(gout) + p.gep1);
+    if (k3_val(gout) > k3_val(mx)) mx = gout;
+    if (p.Noll == 3) {                                                  // vertical2 :196-205
+        x = k3_val(habove) + p.gop2;
+        if (x >= k3_val(g2above)) { k3_setval(g2out, x); K3_PTR(g2out) = K3_PTR(habove); k3_setdg(g2out, K3_VERT, 0); }
+        else { g2out[0] = g2above[0]; g2out[1] = g2above[1]; g2out[2] = g2above[2]; g2out[3] = g2above[3]; }
+        k3_setval(g2out, k3_val(g2out) + p.gep2);
+        if (k3_val(g2out) > k3_val(mx)) mx = g2out;
+    }
+    x = k3_val(hleft) + p.gop1;                                         // horizontal :207-214
+    if (x >= k3_val(f1)) { k3_setval(f1, x); K3_PTR(f1) = K3_PTR(hleft); k3_setdg(f1, K3_HORI, 0); }
+    k3_setval(f1, k3_val(f1) + p.gep1);
+    if (k3_val(f1) >= k3_val(mx)) mx = f1;
+    if (p.Noll == 3) {                                                  // horizontal2 :217-226
+        x = k3_val(hleft) + p.gop2;
+        if (x >= k3_val(f2)) { k3_setval(f2, x); K3_PTR(f2) = K3_PTR(hleft); k3_setdg(f2, 9 /* HORL */, 0); }
+        k3_setval(f2, k3_val(f2) + p.gep2);
+        if (k3_val(f2) >= k3_val(mx)) mx = f2;
+    }
+    if (mx != hout) { hout[0] = mx[0]; hout[1] = mx[1]; hout[2] = mx[2]; hout[3] = mx[3]; }      // :229
+    const int dir = k3_dir(hout);
+    return dir == K3_NEWD || dir == K3_NEWV || dir == K3_NEWH;          // :243-245
+}
+// boundary chains of initB_ng (src/fwd2b1.cc:64-98): k-th cell (1-based); records point at the origin
+PG_HD void k3_boundary_b1(const K3Prm& p, int k, int* dst, const int* src, bool row)
+{
+    const double gpn = k == 1 ? ((1 > p.codonk1) ? p.gop2 + p.gep2 : p.gop1 + p.gep1) : (k > p.codonk1 ? p.gep2 : p.gep1);
+    k3_setval(dst, k3_val(src) + gpn * (row ? p.ltg_a : p.ltg_b));
+    K3_PTR(dst) = 1;
+    k3_setdg(dst, row ? K3_HORI : K3_VERT, 0);
 }
 
 // Boundary cells (initB, fwd2c.h:138-176).  Row: asi at a.left-1 (ia = 0), k-th column (1-based).

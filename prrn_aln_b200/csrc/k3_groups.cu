@@ -112,14 +112,20 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
             vmf[0].m = 0; vmf[0].n = 0; vmf[0].p = 0;                       // skip 0-th record (:361)
             vmf[1].m = P.al; vmf[1].n = P.bl; vmf[1].p = 0;                 // origin
             sm_vmf[g] = 2;
-            k3_setval(colH, 0); k3_setdg(colH, K3_DIAG, 0); K3_PTR(colH) = 1;
+            k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(colH) = 1;
             const int rr = LQ < -p.lw ? LQ : -p.lw;
-            for (int k = 1; k <= rr; ++k) k3_boundary_col(p, A, B, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
+            for (int k = 1; k <= rr; ++k) {
+                if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false);
+                else k3_boundary_col(p, A, B, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
+            }
         }
         if (t == TG / 2) {
-            k3_setval(rowH, 0); k3_setdg(rowH, K3_DIAG, 0); K3_PTR(rowH) = 1;
+            k3_setval(rowH, 0); k3_setdg(rowH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(rowH) = 1;
             const int rr = LS < p.up ? LS : p.up;
-            for (int k = 1; k <= rr; ++k) k3_boundary_row(p, A, B, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
+            for (int k = 1; k <= rr; ++k) {
+                if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true);
+                else k3_boundary_row(p, A, B, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
+            }
         }
         group_sync<TG>(g);
 
@@ -189,8 +195,11 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
                     int* gout = pubG + ((size_t)(s & 1) * TG + t) * st;
                     int* g2out = pubG2 + ((size_t)(s & 1) * TG + t) * st;
                     const double dab = P.simmat ? __ldg(P.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
-                    if (k3_cell(p, A, B, ia, ib, m == 0, n == 0, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
-                                hout, gout, g2out, black)) {
+                    const bool rec = p.mode == 3
+                        ? k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, f1, f2, hout, gout, g2out)
+                        : k3_cell(p, A, B, ia, ib, m == 0, n == 0, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
+                                  hout, gout, g2out, black);
+                    if (rec) {
                         const int id = atomicAdd(&sm_vmf[g], 1);    // Vmf::add (fwd2c.h:465-467)
                         if (id < a.vmf_cap) { vmf[id].m = m + P.al; vmf[id].n = n + P.bl; vmf[id].p = K3_PTR(hout); }
                         K3_PTR(hout) = id;

@@ -827,7 +827,7 @@ extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
             p0.lcl = 0; p0.alprm.tgapf = 1.0f;
             if (make_int_scoring(c, &p0, mtx, dim, present, &probe) != PG_OK) { fp = true; c->err = keep; }
         }
-        if (fp) return pg_int_align_pairs_fp(c, s, a_idx, b_idx, npairs, prm, mtx, dim, out_scores, out_offs, out_pts);
+        if (fp) return pg_int_align_pairs_fp(c, s, a_idx, b_idx, npairs, prm, mtx, dim, out_scores, out_offs, out_pts, 0);
     }
     int64_t* offs = (int64_t*)malloc(sizeof(int64_t) * (size_t)(npairs + 1));
     if (!offs) return fail(c, PG_ERR_ARG, "out of host memory");

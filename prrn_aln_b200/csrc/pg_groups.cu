@@ -129,6 +129,7 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
         case 6: mode = 0; break;
         case 7: case 8: mode = 1; break;
         case 9: mode = 2; break;
+        case 100: mode = 3; break;      // PG_ALN_B1_NG: Aln2b1 (pg_align_pairs_ng), two single sequences
         default:
             free(offs);
             return pg_int_fail(c, PG_ERR_UNSUPPORTED, "pg_align_groups: alnmode is not one of NGP_ALB / HLF_ALB / RHF_ALB / GPF_ALB "
@@ -140,7 +141,7 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
             return pg_int_fail(c, PG_ERR_ARG, "pg_align_groups: bad group window / missing arrays (align2 handles empty windows "
                                               "with nogap_skl before alignC)");
         }
-        if ((mode >= 1 && !(A.sfq && A.tfq && A.rfq)) || (mode == 2 && !(B.sfq && B.tfq && B.rfq))) {
+        if (((mode == 1 || mode == 2) && !(A.sfq && A.tfq && A.rfq)) || (mode == 2 && !(B.sfq && B.tfq && B.rfq))) {
             free(offs);
             return pg_int_fail(c, PG_ERR_ARG, "pg_align_groups: gap-profile lists missing for a half / full profile mode");
         }
@@ -157,6 +158,8 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
         kp.wgop = P.Weighted_GOP; kp.bgop = P.Basic_GOP;
         kp.u2divu1 = P.BasicGEP < 0 ? P.LongGEP / P.BasicGEP : 0;      // fwd2c.h:85-86
         kp.v2divv1 = P.BasicGOP < 0 ? P.LongGOP / P.BasicGOP : 0;
+        kp.gop1 = P.BasicGOP; kp.gep1 = P.BasicGEP; kp.gop2 = P.LongGOP; kp.gep2 = P.LongGEP;
+        kp.ltg_a = kp.ltg_b = 1.0;
         const int LQ = A.right - A.left, LS = B.right - B.left;
         const size_t st = (size_t)k3_stride(kp.capa, kp.capb);
         arena_words = std::max(arena_words, st * (size_t)(3 * (LS + 2) + (LQ + 2)) + k3_wave_words((int)st, 3, tg));
@@ -318,13 +321,14 @@ void single_gparams(const pg_params* prm, int dim, pg_gparams* gp)
 
 int pg_int_align_pairs_fp(pg_context* c, const pg_seqs* s, const int32_t* a_idx, const int32_t* b_idx, int64_t npairs,
                           const pg_params* prm, const void* mtx, int32_t dim, void* out_scores, int64_t** out_offs,
-                          pg_skl** out_pts)
+                          pg_skl** out_pts, int b1)
 {
     if (prm->lcl != 0 || !(prm->alprm.tgapf == 1.0f))
         return pg_int_fail(c, PG_ERR_UNSUPPORTED, "pg_align_pairs: semi-global / local alignment with path (nil-ended sequences, "
                                                   "thickness at the ends) is not built yet");
     pg_gparams gp;
     if (prm->vtype) single_gparams<double>(prm, dim, &gp); else single_gparams<float>(prm, dim, &gp);
+    if (b1) gp.alnmode = 100;
     // per sequence and role: ones, matrix rows (as a), one-hot rows (as b)
     const int n = s->nseq;
     std::vector<std::vector<double>> rowv(n), onehot(n), ones(n);
@@ -410,4 +414,20 @@ int pg_int_align_pairs_fp(pg_context* c, const pg_seqs* s, const int32_t* a_idx,
     *out_offs = offs;
     *out_pts = pts;
     return PG_OK;
+}
+
+
+// ---- Aln2b1: alignB_ng / HomScoreB_ng ------------------------------------------------------------
+extern "C" int pg_align_pairs_ng(pg_context* c, const pg_seqs* s, const int32_t* a_idx, const int32_t* b_idx, int64_t npairs,
+                                 const pg_params* prm, const void* mtx, int32_t dim, void* out_scores, int64_t** out_offs,
+                                 pg_skl** out_pts)
+{
+    if (!c) return PG_ERR_ARG;
+    if (!s || !prm || !mtx || npairs < 0 || !out_offs || !out_pts || (npairs && (!a_idx || !b_idx || !out_scores)))
+        return pg_int_fail(c, PG_ERR_ARG, "pg_align_pairs_ng: NULL / bad argument");
+    if (dim < 1 || dim > 32) return pg_int_fail(c, PG_ERR_ARG, "dim must be in [1, 32]");
+    for (int64_t p = 0; p < npairs; ++p)
+        if (a_idx[p] < 0 || a_idx[p] >= s->nseq || b_idx[p] < 0 || b_idx[p] >= s->nseq)
+            return pg_int_fail(c, PG_ERR_ARG, "pg_align_pairs_ng: sequence index out of range");
+    return pg_int_align_pairs_fp(c, s, a_idx, b_idx, npairs, prm, mtx, dim, out_scores, out_offs, out_pts, 1);
 }

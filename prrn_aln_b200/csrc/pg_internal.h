@@ -223,7 +223,7 @@ int pg_int_ensure_cap(pg_context* c, void** p, size_t* cap, size_t need);
 
 int pg_int_align_pairs_fp(pg_context* c, const pg_seqs* s, const int32_t* a_idx, const int32_t* b_idx, int64_t npairs,
                           const pg_params* prm, const void* mtx, int32_t dim, void* out_scores, int64_t** out_offs,
-                          pg_skl** out_pts);
+                          pg_skl** out_pts, int b1);
 
 // kernels (k1_score.cu)
 cudaError_t k1_launch(const K1Args& a, int grid_blocks, cudaStream_t st);

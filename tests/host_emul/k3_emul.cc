@@ -32,10 +32,10 @@ extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* 
     vmf.push_back({0, 0, 0});                       // skip 0-th record (fwd2c.h:361)
     vmf.push_back({al, bl, 0});                     // origin (initB)
     // origin + boundary chains
-    k3_setval(colH, 0); k3_setdg(colH, K3_DIAG, 0); K3_PTR(colH) = 1;
+    k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(colH) = 1;
     k3_copy(p, rowH, colH);
-    { int rr = LS < p.up ? LS : p.up; for (int k = 1; k <= rr; ++k) k3_boundary_row(p, a, b, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st); }
-    { int rr = LQ < -p.lw ? LQ : -p.lw; for (int k = 1; k <= rr; ++k) k3_boundary_col(p, a, b, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st); }
+    { int rr = LS < p.up ? LS : p.up; for (int k = 1; k <= rr; ++k) { if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true); else k3_boundary_row(p, a, b, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st); } }
+    { int rr = LQ < -p.lw ? LQ : -p.lw; for (int k = 1; k <= rr; ++k) { if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false); else k3_boundary_col(p, a, b, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st); } }
     std::vector<double> pua(T, 0.0);
     std::vector<char> started(T, 0);
     int last_ptr = 0; double last_val = 0;
@@ -69,8 +69,11 @@ extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* 
                 int* gout = pubG + ((size_t)(s & 1) * T + t) * st;
                 int* g2out = pubG2 + ((size_t)(s & 1) * T + t) * st;
                 const double dab = k3_sim(a, b, p, ia, ib);
-                if (k3_cell(p, a, b, ia, ib, first_row, first_col, dab, &pua[t], hdiag, habove, gabove, g2above, hleft,
-                            F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out, black)) {
+                const bool rec = p.mode == 3
+                    ? k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out)
+                    : k3_cell(p, a, b, ia, ib, first_row, first_col, dab, &pua[t], hdiag, habove, gabove, g2above, hleft,
+                              F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out, black);
+                if (rec) {
                     vmf.push_back({m + al, n + bl, K3_PTR(hout)});
                     K3_PTR(hout) = (int)vmf.size() - 1;
                 }

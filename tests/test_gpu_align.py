@@ -165,3 +165,18 @@ def test_long_pair_multi_pass(ctx, oracle):
         osc, olist = oracle.align_ngp(oracle.seq(enc[i]), oracle.seq(enc[j]), M, oracle.params(), std=False)
         assert float(scores[k]) == osc
         assert [tuple(x) for x in raw[k].tolist()] == olist
+
+
+@pytest.mark.parametrize("name", golden_names("alignb_"))
+def test_aln2b1_goldens(ctx, name):
+    """pg_align_pairs_ng (Aln2b1: alignB_ng / HomScoreB_ng on the GPU, stdskl on the host).  Double
+    flavour and integral scoring: bit-exact; float flavour with non-integral values: 1e-5 / near-ties."""
+    g = golden(name)
+    enc = [seqcode.encode_protein(s) for s in g["seqs"]]
+    ia = [p["i"] for p in g["pairs"]]
+    ib = [p["j"] for p in g["pairs"]]
+    prm = _params(g)
+    scores, raw = ctx.align_pairs(P.SeqSet(enc), ia, ib, prm, np.array(g["matrix"]), ng=True)
+    for k, p in enumerate(g["pairs"]):
+        assert float(scores[k]) == p["score"] == p["hom"], (p["i"], p["j"])
+        assert P.stdskl(raw[k]) == [tuple(x) for x in p["skl"]], (p["i"], p["j"])

@@ -22,7 +22,8 @@ class K3Group(C.Structure):
 class K3Prm(C.Structure):
     _fields_ = [("mode", C.c_int32), ("Noll", C.c_int32), ("codonk1", C.c_int32), ("lw", C.c_int32), ("up", C.c_int32),
                 ("capa", C.c_int32), ("capb", C.c_int32), ("kdim", C.c_int32), ("u", C.c_double), ("wgop", C.c_double),
-                ("bgop", C.c_double), ("u2divu1", C.c_double), ("v2divv1", C.c_double)]
+                ("bgop", C.c_double), ("u2divu1", C.c_double), ("v2divv1", C.c_double), ("gop1", C.c_double),
+                ("gep1", C.c_double), ("gop2", C.c_double), ("gep2", C.c_double), ("ltg_a", C.c_double), ("ltg_b", C.c_double)]
 
 
 @pytest.fixture(scope="module")
@@ -54,7 +55,7 @@ def test_wavefront_emulation_matches_reference(emul3, name):
     bgep, lgep, bgop, lgop = pc["BasicGEP"], pc["LongGEP"], pc["BasicGOP"], pc["LongGOP"]
     p = K3Prm(mode, pm["Noll"], pm["codonk1"], lw - r0, up - r0, max(A["hetero"], 0) + 3, max(B["hetero"], 0) + 3,
               A["vec"].shape[1], float(np.float32(float(h["u"]))), -float(np.float32(float(h["v"]))), pc["vgop1"],
-              lgep / bgep if bgep < 0 else 0.0, lgop / bgop if bgop < 0 else 0.0)
+              lgep / bgep if bgep < 0 else 0.0, lgop / bgop if bgop < 0 else 0.0, bgop, bgep, lgop, lgep, 1.0, 1.0)
     want = d["alignc"]
     for T in (256, 7, 33):      # rows per pass: one pass, many passes, ragged last pass
         out = np.zeros(2 * (A["len"] + B["len"] + 8), np.int32)
@@ -65,3 +66,39 @@ def test_wavefront_emulation_matches_reference(emul3, name):
         assert n > 0
         assert abs(sc.value - want["score"]) <= 1e-5 * max(1.0, abs(want["score"])), T
         assert [[int(out[2 * i]), int(out[2 * i + 1])] for i in range(n)] == want["skl"], T
+
+
+def test_aln2b1_cell_emulation(emul3, oracle):
+    """Mode 3 of the K3 machinery (Aln2b1::forwardB_ng cell, initB_ng chains) on groups of one."""
+    from prrn_aln_b200 import seqcode
+    import prrn_aln_b200 as P
+    g = golden("alignb_p12_pam_f64")
+    enc = [seqcode.encode_protein(s) for s in g["seqs"]]
+    M = np.nan_to_num(np.array(g["matrix"]))
+    h = g["params"]
+    fu, fv, fu1, k1 = float(h["u"]), float(h["v"]), float(h["u1"]), int(h["k1"])
+    bgop, bgep, lgep = -fv, -fu, -float(np.float32(fu1))
+    lgop = bgop - (lgep - bgep) * k1
+    for pr in g["pairs"][:30]:
+        a, b = enc[pr["i"]], enc[pr["j"]]
+        la, lb = len(a), len(b)
+        sides = []
+        for e, asrow in ((a, True), (b, False)):
+            npos = len(e) + 1
+            vec = np.zeros((npos, 25))
+            for x in range(1, npos):
+                if asrow:
+                    vec[x] = M[e[x - 1]]
+                else:
+                    vec[x, e[x - 1]] = 1.0
+            sides.append(dict(cfq=np.ones(npos), efq=np.ones(npos), vec=np.ascontiguousarray(vec), glen=np.array([-1], np.int32),
+                              gfreq=np.zeros(1), sfq=np.full(npos, -1, np.int32), tfq=np.full(npos, -1, np.int32),
+                              rfq=np.full(npos, -1, np.int32), left=0, right=len(e), nils=0))
+        lw, up, _ = oracle.stripe(oracle.seq(a), oracle.seq(b), int(h["sh"]))
+        p = K3Prm(3, 2, 1 << 30, lw, up, 2, 2, 25, fu, -fv, -fv, 0.0, 0.0, bgop, bgep, lgop, lgep, 1.0, 1.0)
+        out = np.zeros(2 * (la + lb + 8), np.int32)
+        sc = C.c_double(0)
+        ga, gb = _k3group(sides[0]), _k3group(sides[1])
+        n = emul3.k3_emul_align(C.byref(ga), C.byref(gb), C.byref(p), 64, 0, 0, C.byref(sc), out.ctypes.data, len(out) // 2)
+        assert sc.value == pr["score"], (pr["i"], pr["j"])
+        assert P.stdskl([(int(out[2 * i]), int(out[2 * i + 1])) for i in range(n)]) == [tuple(x) for x in pr["skl"]]

@@ -88,3 +88,16 @@ def test_group_alignment_bit_exact(oracle, name):
     a, b = g["groups"]
     want_cells = sum(max(0, min(m + up + 1, b["right"]) - max(m + lw, b["left"])) for m in range(a["left"], a["right"]))
     assert cells == want_cells
+
+
+@pytest.mark.parametrize("name", golden_names("alignb_"))
+def test_aln2b1_bit_exact(oracle, name):
+    """orc_align_b1 (Aln2b1: alignB_ng + HomScoreB_ng restated) against the reference."""
+    g = golden(name)
+    enc = [seqcode.encode_protein(s) for s in g["seqs"]]
+    p = _oracle_params(oracle, g)
+    M = np.nan_to_num(np.array(g["matrix"]))
+    for pr in g["pairs"]:
+        scr, pts = oracle.align_b1(oracle.seq(enc[pr["i"]]), oracle.seq(enc[pr["j"]]), M, p)
+        assert scr == pr["score"] == pr["hom"], (pr["i"], pr["j"])
+        assert pts == [tuple(x) for x in pr["skl"]], (pr["i"], pr["j"])

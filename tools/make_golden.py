@@ -131,6 +131,32 @@ def galign_cases():
     galign_case("galign_dna_gpf_twopiece", A, B, molc="n", ls=3, wt=1)
 
 
+def alignb_case(name, seqs, flavour="f", **kv):
+    """Aln2b1: alignB_ng (stdskl-normalised corner list) + HomScoreB_ng per pair."""
+    os.makedirs(TMP, exist_ok=True)
+    fa = os.path.join(TMP, name + ".fa")
+    gen_synth.write_fasta(fa, seqs)
+    al = refio.run("alignb", fa, flavour=flavour, **kv)
+    mt = refio.run("matrix", fa, flavour=flavour, **kv)
+    n = len(seqs)
+    pairs = [dict(i=i, j=j, score=al["alignb"][(i, j)]["score"], hom=al["alignb"][(i, j)]["hom"],
+                  skl=al["alignb"][(i, j)]["skl"]) for j in range(1, n) for i in range(j)]
+    rec = dict(name=name, kind="alignb", flavour=flavour, params=al["header"], args=kv, seqs=seqs,
+               matrix=mt["matrix"].tolist(), pairs=pairs)
+    with open(os.path.join(GOLD, name + ".json"), "w") as f:
+        json.dump(rec, f)
+    print("wrote", name, "pairs", len(pairs))
+
+
+def alignb_cases():
+    p12 = gen_synth.synth_set(12, 120, 0.1, 0.7, 11)
+    alignb_case("alignb_p12_blosum62", p12)
+    alignb_case("alignb_p12_pam_f64", p12, flavour="d", mtx="pam")
+    alignb_case("alignb_p12_twopiece_f64", p12, flavour="d", ls=3)
+    alignb_case("alignb_p12_sh3_u3v11", gen_synth.synth_set(12, 150, 0.2, 0.9, 12), sh=3, u=3, v=11)
+    alignb_case("alignb_long700", gen_synth.synth_set(4, 700, 0.1, 0.5, 31))
+
+
 def sample_pair():
     """C1: the sample/pas ce13a1 x ce13a2 pair of sample/test.sh (annotation lines stripped)."""
     out = []
@@ -182,12 +208,15 @@ def main():
     align_case("align_long1300", long_[:4])
     align_case("align_c1_ce13a", sample_pair(), sh=-50)
     galign_cases()
+    alignb_cases()
 
 
 if __name__ == "__main__":
     if not refio.available("f"):
         sys.exit("oracle/_ref is not built: run `make -C oracle ref` where /root/reference exists")
-    if len(sys.argv) > 1 and sys.argv[1] == "galign":
+    if len(sys.argv) > 1 and sys.argv[1] == "alignb":
+        alignb_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "galign":
         galign_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == "lcl":      # only the lcl cases
         p24_ = gen_synth.synth_set(24, 120, 0.1, 0.6, 11)

@@ -66,6 +66,14 @@ def parse(text):
                 v = [int(x) for x in t[10:10 + 2 * n]]
                 skl = dict(n=n, flag=flag, pts=list(zip(v[0::2], v[1::2])))
             r["aligns"][key] = dict(swp=swp, mode=mode, score=scr, skl=skl)
+        elif t[0] == "alignb":
+            key = (int(t[1]), int(t[2]))
+            skl = None
+            if t[5] == "skl" and t[6] != "0":
+                n = int(t[6])
+                v = [int(x) for x in t[9:9 + 2 * n]]
+                skl = list(zip(v[0::2], v[1::2]))
+            r.setdefault("alignb", {})[key] = dict(score=float(t[3]), hom=float(t[4]), skl=skl)
         elif t[0] == "fstat":
             r["fstat"][(int(t[1]), int(t[2]))] = [float(x) for x in t[3:]]
     r["dist"] = np.array(r["dist"])
