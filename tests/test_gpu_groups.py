@@ -85,3 +85,56 @@ def test_bad_arguments_fail_loudly(ctx):
     with pytest.raises(P.PgError) as e:
         ctx.align_groups([(A, B, gp)])
     assert e.value.code == 4
+
+
+def test_edge_cases_groups(ctx):
+    """Empty batch, tiny windows, a window inside the groups, refusal of over-long groups."""
+    scores, pts = ctx.align_groups([])
+    assert len(scores) == 0 and pts == []
+    g = golden("galign_gpf_prof12_raw5_wt")
+    A, B, gp = stage_golden(g)
+    # one-column windows at the left end: the staged arrays keep their origin at left-1, so cut them
+    def cut(S, right):
+        T = dict(S)
+        n = right - S["left"] + 1
+        for k in ("cfq", "efq", "sfq", "tfq", "rfq"):
+            T[k] = np.ascontiguousarray(S[k][:n])
+        T["vec"] = np.ascontiguousarray(S["vec"][:n])
+        T["right"] = right
+        return T
+    for ra, rb in ((A["left"] + 1, B["left"] + 1), (A["left"] + 1, B["left"] + 7), (A["left"] + 9, B["left"] + 1),
+                   (A["left"] + 40, B["left"] + 33)):
+        s1, p1 = ctx.align_groups([(cut(A, ra), cut(B, rb), gp)])
+        assert np.isfinite(s1[0])
+        q = p1[0].tolist()
+        assert q[0] == [ra, rb] and q[-1] == [A["left"], B["left"]]          # back-walk order: end corner first
+        assert all(q[i][0] >= q[i + 1][0] and q[i][1] >= q[i + 1][1] for i in range(len(q) - 1))
+    A2 = dict(A)
+    A2["len"] = 70000
+    with pytest.raises(P.PgError) as e:
+        ctx.align_groups([(A2, B, gp)])
+    assert e.value.code == 5
+
+
+def test_tiny_windows_match_oracle(ctx, oracle):
+    """1..3-column windows of both groups against the oracle (boundary chains, first row / column rules)."""
+    g = golden("galign_gpf_highhetero")
+    base = oracle.gparams_from_dump(g)
+    for la in (1, 2, 3):
+        for lb in (1, 2, 3):
+            gg = {"groups": [dict(g["groups"][0]), dict(g["groups"][1])]}
+            for side, ln in ((0, la), (1, lb)):
+                d = gg["groups"][side]
+                n = ln + 1
+                for k in ("pos", "cfq", "dfq", "efq", "res", "vss", "sfq", "tfq", "rfq"):
+                    d[k] = d[k][:n]
+                d["right"] = d["left"] + ln
+            OA, OB = oracle.group_arrays(gg["groups"][0]), oracle.group_arrays(gg["groups"][1])
+            want_s, want_p, _ = oracle.align_groups(OA, OB, np.array(g["matrix"]), base)
+            pm, pc, h = g["pwdm"], g["pwdc"], g["header"]
+            A, B = G.stage_pair(gg["groups"][0], gg["groups"][1], pm["a_mode"], pm["b_mode"], g["matrix"])
+            gp = P.gparams_from_pwd(pm["alnmode"], pm["Noll"], pm["codonk1"], int(h["sh"]), A["vec"].shape[1], float(h["u"]),
+                                    float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
+            s1, p1 = ctx.align_groups([(A, B, gp)])
+            assert abs(s1[0] - want_s) <= REL_TOL * max(1.0, abs(want_s)), (la, lb)
+            assert [tuple(x) for x in p1[0].tolist()] == want_p, (la, lb)
