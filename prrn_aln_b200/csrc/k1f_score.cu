@@ -53,10 +53,6 @@ __device__ __forceinline__ void unpack16(double* v, double2 x) { v[0] = x.x; v[1
 template <typename T> __device__ __forceinline__ T shfl_up(T v) { return __shfl_up_sync(FULL, v, 1); }
 template <typename T> __device__ __forceinline__ T shfl_idx(T v, int src) { return __shfl_sync(FULL, v, src); }
 
-template <typename T> __device__ __forceinline__ T t_sqrt(T x);
-template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return __fsqrt_rn(x); }
-template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return __dsqrt_rn(x); }
-
 // alnscore2dist tail + dpscore's x100 (aln2.cc:332-333, phyl.cc:249) in FTYPE = T
 template <typename T>
 __device__ __forceinline__ T dist_value(T score, int dl, T self_a, T self_b, float u_f32)

@@ -150,6 +150,131 @@ __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k2_fill_kernel(const K
     }
 }
 
+// ---- one LONG pair: striped wavefront across warps ------------------------------------------------
+// A query of LQ rows is npass = ceil(LQ / 512) stripes.  k2_fill_kernel runs the stripes of a pair one
+// after the other in one warp (fine for proteins, 59 x 30,000 dependent steps for a 30 kb pair).  Here
+// every stripe is its own single-warp CTA with its own profile in shared memory, and stripe p+1 follows
+// stripe p a few columns behind: the bottom row of p goes through an L2-resident row buffer and a
+// progress counter (published every PUB columns with a fence) tells the stripe below how far it may
+// read.  Stripes take their index from a ticket, so a waiting stripe only ever waits for one that has
+// already started: no deadlock however many stripes are resident.  Same direction-word layout as
+// k2_fill_kernel, so the traceback kernel is shared.
+constexpr int PUB = 16;
+
+__global__ void __launch_bounds__(32) k2_fill_long_kernel(const K2Args a, int npass)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int4* const sm_prof = reinterpret_cast<int4*>(smem_raw);
+    int4* const sm_poke = sm_prof + a.dim * (R / 4) * 32;
+    const int lane = threadIdx.x;
+    const int negv = -a.v;
+    const int qi = a.pair_q[0], si = a.pair_s[0];
+    const uint8_t* q = a.seqs.res + a.seqs.offs[qi] + a.seqs.left[qi];
+    const uint8_t* s = a.seqs.res + a.seqs.offs[si] + a.seqs.left[si];
+    const int LQ = a.seqs.wlen[qi], LS = a.seqs.wlen[si];
+    K1Geom g;
+    g.LQ = LQ; g.LS = LS; g.u = a.u; g.v = a.v;
+    k1_band(LQ, LS, a.sh, &g.lw, &g.up);
+    g.topOpen = -a.v; g.topExt = -a.u; g.leftOpen = -a.v; g.leftExt = -a.u;
+
+    for (;;) {
+        int pass = 0;
+        if (lane == 0) pass = atomicAdd(a.ticket, 1);
+        pass = __shfl_sync(FULL, pass, 0);
+        if (pass >= npass) break;
+        const int pbase = pass * ROWS_PER_PASS;
+        {
+            int* p = reinterpret_cast<int*>(sm_prof);
+            const int total = a.dim * 32 * R;
+            for (int idx = lane; idx < total; idx += 32) {
+                int letter = idx / (32 * R);
+                int rem = idx - letter * (32 * R);
+                int j = rem >> 7, ln = (rem >> 2) & 31, c = rem & 3;
+                int row = pbase + ln * R + j * 4 + c;
+                p[idx] = row < LQ ? a.mtx[(int)q[row] * a.dim + letter] + 2 * a.u : 0;
+            }
+        }
+        __syncwarp();
+        const int rows_here = min(LQ - pbase, ROWS_PER_PASS);
+        const int lanes = (rows_here + R - 1) / R;
+        const int mbase = pbase + lane * R;
+        const bool last_pass = pass == npass - 1;
+        int2* const row_in = a.rowbuf + (int64_t)(pass - 1) * LS;      // bottom row of the stripe above
+        int2* const row_out = a.rowbuf + (int64_t)pass * LS;
+        volatile int* const prog_in = a.progress + (pass - 1);
+        unsigned long long* words = a.dirs + a.dir_off[0] + ((int64_t)pass * (LS + 31)) * 32 + lane;
+
+        K2Lane<R> L;
+        k2_lane_init(L, g, mbase);
+        const int lwm = g.lw + mbase;
+        const int upm = g.up + 1 + mbase;
+        int recv_h = K1_NEG, recv_g = K1_NEG;
+        const int4* pp = sm_prof + lane;
+        int4* pk = sm_poke + lane;
+        const int nsteps = LS + lanes - 1;
+        int avail = 0;          // columns of the stripe above known to be published
+
+        for (int step = 0; step < nsteps; ++step) {
+            const int n = step - lane;
+            int h_dn = K1_NEG, g_dn = K1_NEG;
+            if (n >= 0 && n < LS && lane < lanes) {
+                int h_up = recv_h, g_up = recv_g;
+                if (lane == 0) {
+                    if (pass == 0) { h_up = k1_top(g, n); g_up = K1_NEG; }
+                    else {
+                        while (avail <= n) avail = *prog_in;            // wait for the stripe above
+                        __threadfence();
+                        int2 v = __ldcg(row_in + n); h_up = v.x; g_up = v.y;
+                    }
+                }
+                const int kL = n - lwm, kU = n - upm;
+                if ((unsigned)kL < (unsigned)R || (unsigned)kU < (unsigned)R) {
+#pragma unroll
+                    for (int j = 0; j < R / 4; ++j)
+                        pk[j * 32] = make_int4(L.E[4 * j], L.E[4 * j + 1], L.E[4 * j + 2], L.E[4 * j + 3]);
+                    int* pki = reinterpret_cast<int*>(pk);
+                    if ((unsigned)kL < (unsigned)R) pki[(kL >> 2) * 128 + (kL & 3)] = K1_NEG;
+                    if ((unsigned)kU < (unsigned)R) pki[(kU >> 2) * 128 + (kU & 3)] = K1_NEG;
+#pragma unroll
+                    for (int j = 0; j < R / 4; ++j) {
+                        int4 v = pk[j * 32];
+                        L.E[4 * j] = v.x; L.E[4 * j + 1] = v.y; L.E[4 * j + 2] = v.z; L.E[4 * j + 3] = v.w;
+                    }
+                }
+                const int letter = __ldg(s + n);
+                const int4* pl = pp + letter * ((R / 4) * 32);
+                int sc[R];
+#pragma unroll
+                for (int j = 0; j < R / 4; ++j) {
+                    int4 v = pl[j * 32];
+                    sc[4 * j] = v.x; sc[4 * j + 1] = v.y; sc[4 * j + 2] = v.z; sc[4 * j + 3] = v.w;
+                }
+                const unsigned long long bits = k2_lane_step(L, sc, negv, h_up, g_up, mbase == 0, &h_dn, &g_dn);
+                __stcs(words + (int64_t)step * 32, bits);
+                if (lane == 31 && !last_pass) {
+                    __stcg(row_out + n, make_int2(h_dn, g_dn));
+                    if ((n % PUB) == PUB - 1 || n == LS - 1) {          // publish: data first, then the counter
+                        __threadfence();
+                        *(volatile int*)(a.progress + pass) = n + 1;
+                    }
+                }
+            }
+            recv_h = __shfl_up_sync(FULL, h_dn, 1);
+            recv_g = __shfl_up_sync(FULL, g_dn, 1);
+        }
+        if (last_pass) {
+            const int tl = (rows_here - 1) / R, kf = (rows_here - 1) % R;
+            int val = 0;
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+                if (k == kf) val = L.H[k];
+            val = __shfl_sync(FULL, val, tl);
+            if (lane == 0) a.score[0] = val - (LQ + LS) * a.u;
+        }
+        __syncwarp();
+    }
+}
+
 // one thread per alignment
 __global__ void __launch_bounds__(128) k2_trace_kernel(const K2Args a, int npairs)
 {
@@ -182,6 +307,18 @@ cudaError_t k2_fill_launch(const K2Args& a, int grid_blocks, cudaStream_t st)
                                          (int)smem_bytes(MAXDIM));
     if (e != cudaSuccess) return e;
     k2_fill_kernel<<<grid_blocks, NW * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st)
+{
+    if (a.dim < 1 || a.dim > MAXDIM) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)(a.dim + 1) * (R / 4) * 32 * sizeof(int4);
+    cudaError_t e = cudaFuncSetAttribute(k2_fill_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)(MAXDIM + 1) * (R / 4) * 32 * sizeof(int4)));
+    if (e != cudaSuccess) return e;
+    int blocks = npass < sm_count * 4 ? npass : sm_count * 4;
+    k2_fill_long_kernel<<<blocks, 32, smem, st>>>(a, npass);
     return cudaGetLastError();
 }
 

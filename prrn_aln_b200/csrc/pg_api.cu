@@ -867,9 +867,17 @@ extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
         int64_t c1 = c0;
         bool multipass = false;
         int max_ls = 0;
+        // a pair whose query spans LONG_PASSES stripes or more gets the striped multi-warp kernel, alone
+        const int LONG_PASSES = 6;
+        bool long_pair = false;
         while (c1 < npairs) {
             const int qa = a_idx[order[c1]], sb = b_idx[order[c1]];
             const size_t w = (size_t)k2_words_per_pair(d->h_wlen[qa], d->h_wlen[sb], Rr);
+            const bool is_long = d->h_wlen[qa] > (LONG_PASSES - 1) * rpp && d->h_wlen[sb] > 0;
+            if (is_long) {
+                if (c1 > c0) break;             // close the chunk before it
+                long_pair = true;
+            }
             if (c1 > c0 && words + w > DIR_BUDGET_WORDS) break;
             pq.push_back(qa); ps.push_back(sb);
             diroff.push_back((int64_t)words); lenoff.push_back(lens);
@@ -878,6 +886,7 @@ extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
             if (d->h_wlen[qa] > rpp) multipass = true;
             max_ls = std::max(max_ls, d->h_wlen[sb]);
             ++c1;
+            if (long_pair) break;
         }
         const int64_t np = c1 - c0;
         // ---- work items: runs of equal query, NW subjects per warp round
@@ -930,7 +939,23 @@ extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
         char* tb = (char*)c->d_trace;
         a.moves = (unsigned char*)(tb + o_mv); a.recs = (K2Rec*)(tb + o_rc); a.out_pts = (int32_t*)(tb + o_out);
         a.out_cnt = (int32_t*)(pb + o_cn);
-        if (e == cudaSuccess) e = k2_fill_launch(a, grid, c->stream);
+        int long_npass = 0;
+        if (long_pair) {
+            // row buffers of all stripes + progress counters + ticket, zeroed
+            long_npass = (d->h_wlen[pq[0]] + rpp - 1) / rpp;
+            const size_t rb = sizeof(int2) * (size_t)long_npass * (size_t)max_ls;
+            const size_t need = up256(rb) + sizeof(int32_t) * (size_t)(long_npass + 2);
+            if ((rc = ensure_cap(c, &c->d_rowbuf, &c->rowbuf_cap, need))) break;
+            a.rowbuf = (int2*)c->d_rowbuf;
+            a.progress = (int32_t*)((char*)c->d_rowbuf + up256(rb));
+            a.ticket = a.progress + long_npass;
+            if (e == cudaSuccess) e = cudaMemsetAsync(a.progress, 0, sizeof(int32_t) * (size_t)(long_npass + 2), c->stream);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev0, c->stream);
+        if (e == cudaSuccess) e = long_pair ? k2_fill_long_launch(a, long_npass, c->sm_count, c->stream)
+                                            : k2_fill_launch(a, grid, c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev1, c->stream);
+        c->ev_valid = e == cudaSuccess;
         if (e == cudaSuccess) e = k2_trace_launch(a, (int)np, c->stream);
         h_pts.resize(2 * (size_t)lens);
         if (e == cudaSuccess) e = cudaMemcpyAsync(h_score.data() + c0, pb + o_sc, 4 * np, cudaMemcpyDeviceToHost, c->stream);

@@ -135,6 +135,9 @@ struct K2Args {
     K2Rec* recs;                // trace scratch
     int32_t* out_pts;           // corner lists, 2 ints per corner, Vmf back-walk order
     int32_t* out_cnt;           // [npairs]
+    // striped long-pair kernel (k2_fill_long_kernel): one pair, one warp per 512-row stripe
+    int32_t* progress;          // [npass] columns whose bottom row a stripe has published
+    int32_t* ticket;            // stripe dispenser (scheduling order = dependency order)
 };
 
 // group-to-group alignment kernel (k3_groups.cu)
@@ -246,6 +249,7 @@ int k1f_grid_blocks(int sm_count, int vtype, int mode);
 // k2_align.cu
 cudaError_t k2_fill_launch(const K2Args& a, int grid_blocks, cudaStream_t st);
 cudaError_t k2_trace_launch(const K2Args& a, int npairs, cudaStream_t st);
+cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st);
 int k2_rows_per_lane();
 int k2_warps_per_block();
 int k2_blocks_per_sm();

@@ -67,6 +67,7 @@ def c5b(ctx, length=30000):
     t0 = time.perf_counter()
     sc, raw = ctx.align_pairs(ss, [0], [1], prm, Mn)
     dt = time.perf_counter() - t0
+    fill_ms = ctx.last_kernel_ms()
     pts = P.stdskl(raw[0])
     a, b = e2
     s = 0.0
@@ -79,7 +80,7 @@ def c5b(ctx, length=30000):
         else:
             s -= 6 + 2 * (dm + dn)
     print(json.dumps({"config": "c5b", "len": [len(a), len(b)], "cells": int(cells), "seconds_e2e": dt, "gcups_e2e": cells / dt / 1e9,
-                      "score": float(sc[0]), "path_rescored": s, "path_valid": bool(ok and s == float(sc[0])), "corners": len(pts)}))
+                      "fill_kernel_ms": fill_ms, "gcups_fill": cells / (fill_ms * 1e-3) / 1e9, "score": float(sc[0]), "path_rescored": s, "path_valid": bool(ok and s == float(sc[0])), "corners": len(pts)}))
 
 
 def c4(ctx, members=60, length=2000, pairs=6):
