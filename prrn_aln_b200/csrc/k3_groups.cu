@@ -71,10 +71,10 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
         group_sync<TG>(g);
         const int pi = sm_pair[g];
         if (pi >= a.npairs) break;
-        const K3Pair& P = a.pairs[pi];
-        const K3Group A = P.a;
-        const K3Group B = P.b;
-        const K3Prm p = P.prm;
+        const K3Pair& P_ = a.pairs[pi];
+        const K3Group A = P_.a;
+        const K3Group B = P_.b;
+        const K3Prm p = P_.prm;
         const int LQ = A.L, LS = B.L;
         const int st = k3_stride(p.capa, p.capb);
         const bool n3 = p.Noll == 3;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
         // ---- initB (fwd2c.h:138-176): origin, then the two boundary chains (one thread each)
         if (t == 0) {
             vmf[0].m = 0; vmf[0].n = 0; vmf[0].p = 0;                       // skip 0-th record (:361)
-            vmf[1].m = P.al; vmf[1].n = P.bl; vmf[1].p = 0;                 // origin
+            vmf[1].m = P_.al; vmf[1].n = P_.bl; vmf[1].p = 0;                 // origin
             sm_vmf[g] = 2;
             k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(colH) = 1;
             const int rr = LQ < -p.lw ? LQ : -p.lw;
@@ -133,57 +133,70 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
         const int pf_words = (n3 ? 3 : 2) * st;
         const bool ring_ok = pf_words <= PFN * TG;
 
-        for (int pbase = 0; pbase < LQ; pbase += TG) {
-            const int rows = LQ - pbase < TG ? LQ - pbase : TG;
-            const bool last_pass = pbase + rows == LQ;
-            const int m = pbase + t;
-            const int ia = m + 1;
+        // ---- continuous stripes: thread t takes rows t, t+TG, t+2TG, ...; its k-th row meets column n at
+        //      global step S = k*P + t + n with the period P = max(LS, TG + 4): a thread starts its next row the
+        //      step after it finished the previous one, so the wavefront never drains between stripes.  Ring
+        //      slot of the parked record (stripe k, index i) = (k*P + i) % RING: thread 0 reads slots S, S+1
+        //      at step S while slot S+3 is being filled.
+        {
+            const int P = LS > TG + 4 ? LS : TG + 4;
+            const int npass = (LQ + TG - 1) / TG;
+            const int rows_last = LQ - (npass - 1) * TG;
+            const int total_steps = (npass - 1) * P + (rows_last - 1) + LS;
             int* const f1 = F1 + (size_t)t * st;
             int* const f2 = F2 + (size_t)t * st;
             double pua = 0;
-            bool started = false;
-            const int nsteps = LS + rows - 1;
-            // ring: records 0 and 1 of the parked row before the first step
+            // ring: records 1 and 2 of the first parked row (the boundary row) before the first step
             if (ring_ok) {
                 for (int w = t; w < pf_words; w += TG) {
                     const int pa = w / st, pw = w - pa * st;
                     const int* src = pa == 0 ? rowH : (pa == 1 ? rowG : rowG2);
                     int* dst = pa == 0 ? ringH : (pa == 1 ? ringG : ringG2);
-                    dst[pw] = __ldcg(src + pw);
-                    dst[st + pw] = __ldcg(src + st + pw);
+                    dst[(size_t)(1 % RING) * st + pw] = __ldcg(src + st + pw);
+                    if (LS + 1 >= 2) dst[(size_t)(2 % RING) * st + pw] = __ldcg(src + 2 * st + pw);
                 }
             }
             group_sync<TG>(g);
-            for (int s = 0; s < nsteps; ++s) {
-                const int n = s - t;
-                const int r = n - m;
-                // prefetch record s+2 of the parked row (read by thread 0 at steps s+1, s+2)
+            // this thread's share of the ring prefetch: word pf_pw[q] of parked array pf_src[q]
+            const int* pf_src[PFN];
+            int* pf_dst[PFN];
+            bool pf_on[PFN];
+#pragma unroll
+            for (int q = 0; q < PFN; ++q) {
+                const int w = t + q * TG;
+                pf_on[q] = ring_ok && w < pf_words;
+                const int pa = w / st, pw = w - pa * st;
+                pf_src[q] = (pa == 0 ? rowH : (pa == 1 ? rowG : rowG2)) + pw;
+                pf_dst[q] = (pa == 0 ? ringH : (pa == 1 ? ringG : ringG2)) + pw;
+            }
+            // this thread's position: q = S - t = k*P + n
+            int k = 0, n = -t, m = t;
+            // thread 0's position two steps ahead (what the ring must hold by then)
+            int k2 = 0, n2 = 2;
+            if (n2 >= P) { n2 -= P; ++k2; }
+            for (int S = 0; S < total_steps; ++S) {
+                // prefetch the parked record thread 0 reads as "above" at step S + 2: index n2 + 1 of stripe k2 - 1
                 int pf_val[PFN];
-                const bool pf_now = ring_ok && s + 2 <= LS + 1;
+                const bool pf_now = ring_ok && n2 < LS && k2 * TG < LQ;
                 if (pf_now) {
 #pragma unroll
-                    for (int q = 0; q < PFN; ++q) {
-                        const int w = t + q * TG;
-                        if (w < pf_words) {
-                            const int pa = w / st, pw = w - pa * st;
-                            const int* src = pa == 0 ? rowH : (pa == 1 ? rowG : rowG2);
-                            pf_val[q] = __ldcg(src + (size_t)(s + 2) * st + pw);
-                        }
-                    }
+                    for (int q = 0; q < PFN; ++q)
+                        if (pf_on[q]) pf_val[q] = __ldcg(pf_src[q] + (size_t)(n2 + 1) * st);
                 }
-                if (t < rows && n >= 0 && n < LS && r >= p.lw && r <= p.up) {
-                    const int ib = n + 1;
-                    if (!started) {
-                        started = true;
-                        pua = k3_unp(A, ia, B, ib, p.u);            // once per row, at its first column (:377)
+                const int r = n - m;
+                if (n >= 0 && n < LS && m < LQ && r >= p.lw && r <= p.up) {
+                    const int ia = m + 1, ib = n + 1;
+                    if (n == 0 || r == p.lw) {                      // first in-band column of this row
+                        pua = k3_unp(A, ia, B, ib, p.u);            // once per row (:377)
                         k3_reset(p, f1);
                         if (n3) k3_reset(p, f2);
                     }
-                    const int g3a = (s + 2) % 3, g3d = (s + 1) % 3, g2a = (s + 1) & 1;
-                    const int* parkedH0 = ring_ok ? ringH + (size_t)(n % RING) * st : rowH + (size_t)n * st;
-                    const int* parkedH1 = ring_ok ? ringH + (size_t)((n + 1) % RING) * st : rowH + (size_t)(n + 1) * st;
-                    const int* parkedG1 = ring_ok ? ringG + (size_t)((n + 1) % RING) * st : rowG + (size_t)(n + 1) * st;
-                    const int* parkedG21 = ring_ok ? ringG2 + (size_t)((n + 1) % RING) * st : rowG2 + (size_t)(n + 1) * st;
+                    const int g3a = (S + 2) % 3, g3d = (S + 1) % 3, g2a = (S + 1) & 1;
+                    const int seq = k * P + n;                      // == S for thread 0
+                    const int* parkedH0 = ring_ok ? ringH + (size_t)(seq % RING) * st : rowH + (size_t)n * st;
+                    const int* parkedH1 = ring_ok ? ringH + (size_t)((seq + 1) % RING) * st : rowH + (size_t)(n + 1) * st;
+                    const int* parkedG1 = ring_ok ? ringG + (size_t)((seq + 1) % RING) * st : rowG + (size_t)(n + 1) * st;
+                    const int* parkedG21 = ring_ok ? ringG2 + (size_t)((seq + 1) % RING) * st : rowG2 + (size_t)(n + 1) * st;
                     const int* hdiag = n == 0 ? colH + (size_t)m * st : (t == 0 ? parkedH0 : pubH + ((size_t)g3d * TG + (t - 1)) * st);
                     const bool above_in = r + 1 <= p.up;
                     const int* habove = !above_in ? black : (t == 0 ? parkedH1 : pubH + ((size_t)g3a * TG + (t - 1)) * st);
@@ -191,51 +204,49 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
                     const int* g2above = (!above_in || m == 0) ? black : (t == 0 ? parkedG21 : pubG2 + ((size_t)g2a * TG + (t - 1)) * st);
                     const bool left_in = r - 1 >= p.lw;
                     const int* hleft = n == 0 ? colH + (size_t)(m + 1) * st : (left_in ? pubH + ((size_t)g3a * TG + t) * st : black);
-                    int* hout = pubH + ((size_t)(s % 3) * TG + t) * st;
-                    int* gout = pubG + ((size_t)(s & 1) * TG + t) * st;
-                    int* g2out = pubG2 + ((size_t)(s & 1) * TG + t) * st;
-                    const double dab = P.simmat ? __ldg(P.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
+                    int* hout = pubH + ((size_t)(S % 3) * TG + t) * st;
+                    int* gout = pubG + ((size_t)(S & 1) * TG + t) * st;
+                    int* g2out = pubG2 + ((size_t)(S & 1) * TG + t) * st;
+                    const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
                     const bool rec = p.mode == 3
                         ? k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, f1, f2, hout, gout, g2out)
                         : k3_cell(p, A, B, ia, ib, m == 0, n == 0, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
                                   hout, gout, g2out, black);
                     if (rec) {
                         const int id = atomicAdd(&sm_vmf[g], 1);    // Vmf::add (fwd2c.h:465-467)
-                        if (id < a.vmf_cap) { vmf[id].m = m + P.al; vmf[id].n = n + P.bl; vmf[id].p = K3_PTR(hout); }
+                        if (id < a.vmf_cap) { vmf[id].m = m + P_.al; vmf[id].n = n + P_.bl; vmf[id].p = K3_PTR(hout); }
                         K3_PTR(hout) = id;
                     }
-                    if (t == rows - 1) {
-                        if (!last_pass) {
-                            k3_copy(p, rowH + (size_t)(n + 1) * st, hout);
-                            k3_copy(p, rowG + (size_t)(n + 1) * st, gout);
-                            if (n3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
-                        } else if (n == LS - 1) { sm_last_ptr[g] = K3_PTR(hout); sm_last_val[g] = k3_val(hout); }
+                    if (m == LQ - 1) {
+                        if (n == LS - 1) { sm_last_ptr[g] = K3_PTR(hout); sm_last_val[g] = k3_val(hout); }
+                    } else if (t == TG - 1) {                       // bottom row of a stripe: park it
+                        k3_copy(p, rowH + (size_t)(n + 1) * st, hout);
+                        k3_copy(p, rowG + (size_t)(n + 1) * st, gout);
+                        if (n3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
                     }
                 }
                 if (pf_now) {
+                    const int slot = (k2 * P + n2 + 1) % RING;
 #pragma unroll
-                    for (int q = 0; q < PFN; ++q) {
-                        const int w = t + q * TG;
-                        if (w < pf_words) {
-                            const int pa = w / st, pw = w - pa * st;
-                            int* dst = pa == 0 ? ringH : (pa == 1 ? ringG : ringG2);
-                            dst[(size_t)((s + 2) % RING) * st + pw] = pf_val[q];
-                        }
-                    }
+                    for (int q = 0; q < PFN; ++q)
+                        if (pf_on[q]) pf_dst[q][(size_t)slot * st] = pf_val[q];
                 }
+                // advance the two positions
+                if (++n == P) { n = 0; ++k; m += TG; }
+                if (++n2 == P) { n2 = 0; ++k2; }
                 group_sync<TG>(g);
             }
         }
         // ---- final record + Vmf::traceback (fwd2c.h:475-481, vmf.cc:103-119)
         if (t == 0) {
-            int* out = a.out_pts + 2 * P.out_off;
+            int* out = a.out_pts + 2 * P_.out_off;
             int cnt = 0;
             const int nrec = sm_vmf[g];
             if (nrec >= a.vmf_cap) cnt = -1;                        // record store overflow: reported, never silent
             else {
-                out[0] = LQ + P.al; out[1] = LS + P.bl; cnt = 1;
+                out[0] = LQ + P_.al; out[1] = LS + P_.bl; cnt = 1;
                 for (int q = sm_last_ptr[g];; q = vmf[q].p) {
-                    if (cnt >= P.out_cap) { cnt = -1; break; }
+                    if (cnt >= P_.out_cap) { cnt = -1; break; }
                     out[2 * cnt] = vmf[q].m; out[2 * cnt + 1] = vmf[q].n; ++cnt;
                     if (!vmf[q].p) break;
                 }

@@ -7,9 +7,11 @@
 #include <vector>
 #include "../../prrn_aln_b200/csrc/k3_core.cuh"
 
-extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int T, int al, int bl,
+extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int Tsigned, int al, int bl,
                              double* score, int* out_pts, int cap)
 {
+    const int T = Tsigned < 0 ? -Tsigned : Tsigned;
+    const bool rev = Tsigned < 0;       // run the "threads" of a step in reverse order: results must not depend on it
     const K3Group& a = *ga; const K3Group& b = *gb; const K3Prm& p = *prm;
     const int LQ = a.L, LS = b.L;
     const int st = k3_stride(p.capa, p.capb);
@@ -37,53 +39,58 @@ extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* 
     { int rr = LS < p.up ? LS : p.up; for (int k = 1; k <= rr; ++k) { if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true); else k3_boundary_row(p, a, b, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st); } }
     { int rr = LQ < -p.lw ? LQ : -p.lw; for (int k = 1; k <= rr; ++k) { if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false); else k3_boundary_col(p, a, b, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st); } }
     std::vector<double> pua(T, 0.0);
-    std::vector<char> started(T, 0);
     int last_ptr = 0; double last_val = 0;
-    for (int pbase = 0; pbase < LQ; pbase += T) {
-        const int rows = LQ - pbase < T ? LQ - pbase : T;
-        const bool last_pass = pbase + rows == LQ;
-        std::fill(started.begin(), started.end(), 0);
-        for (int s = 0; s < LS + rows - 1; ++s) {
-            for (int t = 0; t < rows; ++t) {            // "threads"; no intra-step dependencies
-                const int m = pbase + t, n = s - t;
-                if (n < 0 || n >= LS) continue;
-                const int r = n - m;
-                if (r < p.lw || r > p.up) continue;
-                const int ia = m + 1, ib = n + 1;       // staged indices (entry 0 = position left-1)
-                if (!started[t]) {
-                    started[t] = 1;
-                    pua[t] = k3_unp(a, ia, b, ib, p.u); // once per row, at its first column (fwd2c.h:377)
-                    k3_reset(p, F1 + (size_t)t * st);
-                    k3_reset(p, F2 + (size_t)t * st);
-                }
-                const bool first_row = m == 0, first_col = n == 0;
-                const int* hdiag = n == 0 ? colH + (size_t)m * st
-                                 : (t == 0 ? rowH + (size_t)n * st : pubH + ((size_t)((s + 1) % 3) * T + (t - 1)) * st);
-                const bool above_in = r + 1 <= p.up;
-                const int* habove = !above_in ? black : (t == 0 ? rowH + (size_t)(n + 1) * st : pubH + ((size_t)((s + 2) % 3) * T + (t - 1)) * st);
-                const int* gabove = (!above_in || m == 0) ? black : (t == 0 ? rowG + (size_t)(n + 1) * st : pubG + ((size_t)((s + 1) & 1) * T + (t - 1)) * st);
-                const int* g2above = (!above_in || m == 0) ? black : (t == 0 ? rowG2 + (size_t)(n + 1) * st : pubG2 + ((size_t)((s + 1) & 1) * T + (t - 1)) * st);
-                const bool left_in = r - 1 >= p.lw;
-                const int* hleft = n == 0 ? colH + (size_t)(m + 1) * st : (left_in ? pubH + ((size_t)((s + 2) % 3) * T + t) * st : black);
-                int* hout = pubH + ((size_t)(s % 3) * T + t) * st;
-                int* gout = pubG + ((size_t)(s & 1) * T + t) * st;
-                int* g2out = pubG2 + ((size_t)(s & 1) * T + t) * st;
-                const double dab = k3_sim(a, b, p, ia, ib);
-                const bool rec = p.mode == 3
-                    ? k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out)
-                    : k3_cell(p, a, b, ia, ib, first_row, first_col, dab, &pua[t], hdiag, habove, gabove, g2above, hleft,
-                              F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out, black);
-                if (rec) {
-                    vmf.push_back({m + al, n + bl, K3_PTR(hout)});
-                    K3_PTR(hout) = (int)vmf.size() - 1;
-                }
-                if (t == rows - 1) {
-                    if (!last_pass) {
-                        k3_copy(p, rowH + (size_t)(n + 1) * st, hout);
-                        k3_copy(p, rowG + (size_t)(n + 1) * st, gout);
-                        if (p.Noll == 3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
-                    } else if (n == LS - 1) { last_ptr = K3_PTR(hout); last_val = k3_val(hout); }
-                }
+    // Continuous schedule (k3_groups.cu): thread t takes rows t, t+T, t+2T, ...; its k-th row meets column n
+    // at global step S = k*P + t + n with the period P = max(LS, T + 4), so a thread starts its next row
+    // the step after it finished the previous one and the wavefront never drains between passes.
+    const int P = LS > T + 4 ? LS : T + 4;
+    const int npass = (LQ + T - 1) / T;
+    const int rows_last = LQ - (npass - 1) * T;
+    const int total_steps = (npass - 1) * P + (rows_last - 1) + LS;
+    for (int S = 0; S < total_steps; ++S) {
+        for (int tt = 0; tt < T; ++tt) {                // "threads"; no intra-step dependencies
+            const int t = rev ? T - 1 - tt : tt;
+            const int q = S - t;
+            if (q < 0) continue;
+            const int k = q / P, n = q - k * P;
+            const int m = k * T + t;
+            if (m >= LQ || n >= LS) continue;
+            const int r = n - m;
+            if (r < p.lw || r > p.up) { continue; }
+            const int ia = m + 1, ib = n + 1;           // staged indices (entry 0 = position left-1)
+            const bool row_start = n == 0 || r == p.lw; // first in-band column of this row
+            if (row_start) {
+                pua[t] = k3_unp(a, ia, b, ib, p.u);     // once per row, at its first column (fwd2c.h:377)
+                k3_reset(p, F1 + (size_t)t * st);
+                k3_reset(p, F2 + (size_t)t * st);
+            }
+            const bool first_row = m == 0, first_col = n == 0;
+            const int* hdiag = n == 0 ? colH + (size_t)m * st
+                             : (t == 0 ? rowH + (size_t)n * st : pubH + ((size_t)((S + 1) % 3) * T + (t - 1)) * st);
+            const bool above_in = r + 1 <= p.up;
+            const int* habove = !above_in ? black : (t == 0 ? rowH + (size_t)(n + 1) * st : pubH + ((size_t)((S + 2) % 3) * T + (t - 1)) * st);
+            const int* gabove = (!above_in || m == 0) ? black : (t == 0 ? rowG + (size_t)(n + 1) * st : pubG + ((size_t)((S + 1) & 1) * T + (t - 1)) * st);
+            const int* g2above = (!above_in || m == 0) ? black : (t == 0 ? rowG2 + (size_t)(n + 1) * st : pubG2 + ((size_t)((S + 1) & 1) * T + (t - 1)) * st);
+            const bool left_in = r - 1 >= p.lw;
+            const int* hleft = n == 0 ? colH + (size_t)(m + 1) * st : (left_in ? pubH + ((size_t)((S + 2) % 3) * T + t) * st : black);
+            int* hout = pubH + ((size_t)(S % 3) * T + t) * st;
+            int* gout = pubG + ((size_t)(S & 1) * T + t) * st;
+            int* g2out = pubG2 + ((size_t)(S & 1) * T + t) * st;
+            const double dab = k3_sim(a, b, p, ia, ib);
+            const bool rec = p.mode == 3
+                ? k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out)
+                : k3_cell(p, a, b, ia, ib, first_row, first_col, dab, &pua[t], hdiag, habove, gabove, g2above, hleft,
+                          F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out, black);
+            if (rec) {
+                vmf.push_back({m + al, n + bl, K3_PTR(hout)});
+                K3_PTR(hout) = (int)vmf.size() - 1;
+            }
+            if (m == LQ - 1) {
+                if (n == LS - 1) { last_ptr = K3_PTR(hout); last_val = k3_val(hout); }
+            } else if (t == T - 1) {                    // bottom row of a stripe: park it for thread 0's next row
+                k3_copy(p, rowH + (size_t)(n + 1) * st, hout);
+                k3_copy(p, rowG + (size_t)(n + 1) * st, gout);
+                if (p.Noll == 3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
             }
         }
     }

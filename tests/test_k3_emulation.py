@@ -57,13 +57,13 @@ def test_wavefront_emulation_matches_reference(emul3, name):
               A["vec"].shape[1], float(np.float32(float(h["u"]))), -float(np.float32(float(h["v"]))), pc["vgop1"],
               lgep / bgep if bgep < 0 else 0.0, lgop / bgop if bgop < 0 else 0.0, bgop, bgep, lgop, lgep, 1.0, 1.0)
     want = d["alignc"]
-    for T in (256, 7, 33):      # rows per pass: one pass, many passes, ragged last pass
+    for T in (256, 7, 33, -33, -5):     # rows per stripe: one stripe, many, ragged last; negative: reversed thread order
         out = np.zeros(2 * (A["len"] + B["len"] + 8), np.int32)
         sc = C.c_double(0)
         ga, gb = _k3group(A), _k3group(B)
         n = emul3.k3_emul_align(C.byref(ga), C.byref(gb), C.byref(p), T, A["left"], B["left"], C.byref(sc),
                                 out.ctypes.data, len(out) // 2)
-        assert n > 0
+        assert n > 0, T
         assert abs(sc.value - want["score"]) <= 1e-5 * max(1.0, abs(want["score"])), T
         assert [[int(out[2 * i]), int(out[2 * i + 1])] for i in range(n)] == want["skl"], T
 
