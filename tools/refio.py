@@ -10,17 +10,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 
 
-def driver(flavour="f"):
-    return os.path.join(REFDIR, "ref_driver_" + flavour)
+def driver(flavour="f", gpu=False):
+    """gpu=True: the same driver with shim/shim_fwd2d1.cc linked in front of the reference's fwd2d1.o, i.e.
+    the unmodified reference calling libprrn_gpu.so for alnScoreD (oracle/Makefile: ref_gpu)."""
+    return os.path.join(REFDIR, "ref_driver_" + flavour + ("_gpu" if gpu else ""))
 
 
 def available(flavour="f"):
     return os.path.exists(driver(flavour)) and os.path.exists(os.path.join(REFDIR, "table", "blosum62"))
 
 
-def run(cmd, fasta, flavour="f", timeout=3600, **kv):
+def run(cmd, fasta, flavour="f", timeout=3600, gpu=False, **kv):
     env = dict(os.environ, ALN_TAB=os.path.join(REFDIR, "table"))
-    args = [driver(flavour), cmd, fasta] + ["%s=%s" % (k, v) for k, v in kv.items()]
+    args = [driver(flavour, gpu), cmd, fasta] + ["%s=%s" % (k, v) for k, v in kv.items()]
     out = subprocess.run(args, env=env, capture_output=True, text=True, timeout=timeout)
     if out.returncode != 0:
         raise RuntimeError("ref_driver failed (%d): %s" % (out.returncode, out.stderr[-2000:]))
