@@ -37,3 +37,72 @@ def test_reference_driver_on_gpu_library(name, tmp_path):
     if "dist" in g:
         ds = refio.run("dist", fa, flavour=fl, gpu=True, **g["args"])
         assert np.array_equal(ds["dist"], np.array(g["dist"])), "calcdist through the shim differs from the reference"
+
+
+ALIGN_CASES = ["align_p16_blosum62", "align_p16_pam_f32", "align_p16_twopiece_f64", "align_ragged", "align_c1_ce13a"]
+
+
+@pytest.mark.parametrize("name", ALIGN_CASES)
+def test_reference_align2_on_gpu_library(name, tmp_path):
+    """align2 of the unmodified reference (PwdM, alignC dispatch, stdskl, the sh = -100 retry) with
+    shim/shim_alignc.cc's alignC<DPunit> underneath: two single sequences."""
+    g = golden(name)
+    fl = g["flavour"]
+    if not os.path.exists(refio.driver(fl, gpu=True)):
+        pytest.skip("oracle/_ref/ref_driver_%s_gpu is not built" % fl)
+    fa = str(tmp_path / "in.fa")
+    gen_synth.write_fasta(fa, g["seqs"])
+    al = refio.run("align", fa, flavour=fl, gpu=True, **g["args"])
+    ties = 0
+    for p in g["pairs"]:
+        r = al["aligns"][(p["i"], p["j"])]
+        assert abs(r["score"] - p["score"]) <= 1e-5 * max(1.0, abs(p["score"])), (p["i"], p["j"])
+        if [list(x) for x in r["skl"]["pts"]] != [list(x) for x in p["skl"]]:
+            ties += 1       # float flavour, non-integral scores: co-optimal paths within the tolerance (test_gpu_align)
+            assert fl == "f"
+    assert ties <= 0.05 * len(g["pairs"])
+
+
+GALIGN_CASES = ["galign_c1_multi_ab_f64", "galign_gpf_prof12_raw5_wt", "galign_gpf_prof34_prof30", "galign_hlf_prof10_single",
+                "galign_rhf_single_prof10", "galign_gpf_twopiece", "galign_gpf_highhetero", "galign_ngp_gapless4x3"]
+
+
+@pytest.mark.parametrize("name", GALIGN_CASES)
+def test_reference_group_align2_on_gpu_library(name, tmp_path):
+    """Two GROUPS through the unmodified reference's PwdM staging + align2, with alignC<DPunit_hf /
+    DPunit_pf> from shim/shim_alignc.cc (C++ staging through mSeqItr -> pg_align_groups -> K4 + K3)."""
+    g = golden(name)
+    fl = g["flavour"]
+    if not os.path.exists(refio.driver(fl, gpu=True)):
+        pytest.skip("oracle/_ref/ref_driver_%s_gpu is not built" % fl)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_msa
+
+    # the goldens keep the staged view, not the MSA files: regenerate the inputs exactly as make_golden did
+    import make_golden as MG
+    captured = {}
+
+    def fake_case(nm, rows_a, rows_b, flavour="d", files=None, **kv):
+        captured[nm] = (rows_a, rows_b, flavour, files, kv)
+    real = MG.galign_case
+    MG.galign_case = fake_case
+    try:
+        MG.galign_cases()
+    finally:
+        MG.galign_case = real
+    rows_a, rows_b, flavour, files, kv = captured[name]
+    if files is None:
+        fa, fb = str(tmp_path / "A"), str(tmp_path / "B")
+        gen_msa.write_native(fa, rows_a, "A")
+        gen_msa.write_native(fb, rows_b, "B")
+    else:
+        pytest.skip("sample files live under /root/reference only")
+    env = dict(os.environ, ALN_TAB=os.path.join(refio.REFDIR, "table"))
+    import subprocess
+    out = subprocess.run([refio.driver(flavour, gpu=True), "galign", fa, "fb=" + fb] + ["%s=%s" % kvp for kvp in kv.items()],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    d = refio.parse_galign(out.stdout)
+    for key in ("alignc", "align2"):
+        assert abs(d[key]["score"] - g[key]["score"]) <= 1e-5 * max(1.0, abs(g[key]["score"])), key
+        assert d[key]["skl"] == g[key]["skl"], key
