@@ -44,3 +44,38 @@ def calcdist_sharded(ctx, seqs, prm, mtx, rank, world, dist=None, compute=None):
     if ctx is not None and torch.cuda.is_available():
         shard = shard.cuda()
     return gather_shards(shard, chunk, npair, world, dist)
+
+
+# ---- candidate partitions of the refinement step (Prrn::best_of_n, src/prrn5.cc:594-631) ---------
+def shard_candidates(costs, world, rank):
+    """The B candidate group pairs of one refinement step are independent: give rank r
+    the candidates of a greedy longest-processing-time split of `costs` (DP cells per candidate), so
+    every GPU gets about the same number of cells.  Deterministic; every candidate lands on one rank."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load = [0] * world
+    mine = []
+    for i in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        load[r] += costs[i]
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
+def best_of_n_sharded(scores_of, costs, rank, world, dist=None):
+    """Score the candidates of this rank with `scores_of(indices) -> list of float` (pg_align_groups on
+    the rank's GPU), combine the B scores over the ranks and return (best index, best score, all scores).
+    Ties go to the lowest index, as the reference's sequential arg-max does (prrn5.cc:618-626).  The only
+    collective is one all-reduce(MAX) of B doubles (every slot is written by exactly one rank, the others
+    hold -inf); the winner's corner list stays on the rank that owns it."""
+    import torch
+    mine = shard_candidates(costs, world, rank)
+    vals = scores_of(mine) if mine else []
+    n = len(costs)
+    buf = torch.full((n,), float("-inf"), dtype=torch.float64)
+    for i, v in zip(mine, vals):
+        buf[i] = float(v)
+    if world > 1 and dist is not None:
+        dist.all_reduce(buf, op=dist.ReduceOp.MAX)      # each slot is written by exactly one rank
+    best = int(torch.argmax(buf).item()) if n else -1
+    return best, (float(buf[best]) if n else float("-inf")), buf

@@ -66,3 +66,43 @@ def test_all_gather_assembles_condensed_vector(world, nseq):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert all(n == nseq * (nseq - 1) // 2 for _, _, n in res)
+
+
+def test_candidate_split_is_a_partition_and_balanced():
+    rng = np.random.default_rng(4)
+    for world in (1, 2, 3, 8):
+        costs = [int(x) for x in rng.integers(1000, 400000, size=37)]
+        parts = [sharding.shard_candidates(costs, world, r) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(len(costs)))
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(costs)
+
+
+def _bon_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    costs = [50, 400, 120, 400, 90, 300, 10]
+    truth = [3.5, 9.25, -1.0, 9.25, 4.0, 8.0, 0.5]          # two tied maxima: the lower index must win
+
+    def scores_of(idx):             # stand-in for pg_align_groups on this rank's GPU
+        return [truth[i] for i in idx]
+
+    best, val, allv = sharding.best_of_n_sharded(scores_of, costs, rank, world, dist)
+    q.put((rank, best, val, allv.tolist() == truth))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_best_of_n_over_ranks(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bon_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(b == 1 and v == 9.25 and ok for _, b, v, ok in res), res
