@@ -18,7 +18,9 @@
 
 static pg_context* pg_ctx()
 {
-	static pg_context* c = 0;
+	// one context (CUDA stream + workspace) per calling thread: the reference calls the DP concurrently from
+	// pthread workers (CalcServer, src/calcserv.h:436-457; Prrn::best_of_n, src/prrn5.cc:606-612)
+	static thread_local pg_context* c = 0;
 	if (!c && pg_create(0, &c) != PG_OK) fatal("prrn_gpu: %s\n", pg_last_error(0));
 	return (c);
 }

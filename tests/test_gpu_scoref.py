@@ -142,3 +142,26 @@ def test_fuzz_modes_windows_flags(ctx, oracle):
         assert np.array_equal(sc.astype(np.float64), np.array([w[0] for w in want])), (rep, mode, vt, sh, u, v, tg)
         if mode == 2:
             assert np.array_equal(r[1], np.array([w[1] for w in want])), (rep, vt, sh, u, v, tg)
+
+
+def test_full_size_c2_default_scoring(ctx, oracle):
+    """BASELINE config 2 at full size with the reference's DEFAULT scoring (PAM250, double VTYPE): 499,500
+    pairs on K1F; a seeded sample against the oracle, shard invariance, finite values."""
+    seqs = gen_synth.config_set("c2")
+    enc = [seqcode.encode_protein(s) for s in seqs]
+    M = np.array(golden("score_p24_pam_f64")["matrix"])
+    ss = P.SeqSet(enc)
+    prm = P.Params(P.ALPRM(sh=-60), vtype=1)
+    dist = ctx.calcdist(ss, prm, M)
+    n = len(enc)
+    assert len(dist) == n * (n - 1) // 2 and np.all(np.isfinite(dist))
+    rng = np.random.default_rng(21)
+    op = oracle.params(sh=-60, vtype=1)
+    for _ in range(150):
+        j = int(rng.integers(1, n))
+        i = int(rng.integers(0, j))
+        want, _ = oracle.calcdist([oracle.seq(enc[i]), oracle.seq(enc[j])], M, op)
+        assert float(dist[P.elem(i, j)]) == want[0], (i, j)
+    third = len(dist) // 3
+    part = ctx.calcdist(ss, prm, M, third, third + 50000)
+    assert np.array_equal(part, dist[third:third + 50000])

@@ -20,6 +20,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import gen_synth  # noqa: E402
 
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
+EXTRA = os.environ.get("PRRN_ARGS", "").split()     # e.g. PRRN_ARGS="-t16": pthread workers (best_of_n, CalcServer)
 
 
 def run(binary, fa, extra):
@@ -36,13 +37,13 @@ def main():
     for n, length, seed in cases:
         fa = "/tmp/prrn_in_%d_%d.fa" % (n, length)
         gen_synth.write_fasta(fa, gen_synth.synth_set(n, length, 0.1, 0.6, seed))
-        res = {"config": "prrn5 %d x ~%d aa (seed %d)" % (n, length, seed)}
+        res = {"config": "prrn5 %s %d x ~%d aa (seed %d)" % (" ".join(EXTRA), n, length, seed), "host_cores": os.cpu_count()}
         outs = {}
         for tag, binary in (("cpu", "prrn5_cpu"), ("gpu_shims", "prrn5_gpu")):
             if not os.path.exists(os.path.join(REFDIR, binary)):
                 res[tag] = "not built"
                 continue
-            dt, rc, md5, out, err = run(binary, fa, ["-m", "blosum62"])
+            dt, rc, md5, out, err = run(binary, fa, ["-m", "blosum62"] + EXTRA)
             res[tag] = {"wall_s": dt, "rc": rc, "msa_md5": md5, "lines": len(out.splitlines())}
             if rc:
                 res[tag]["stderr"] = err
