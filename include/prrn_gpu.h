@@ -96,8 +96,8 @@ int pg_align_pairs_ng(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx
 
 /* ---- per-call level, groups: stands behind
  *   template<class recd_t> SKL* alignC(mSeq* seqs[2], PwdM* pwd, VTYPE* scr, ...)   src/fwd2c.h:670-677
- * for recd_t = DPunit (NGP_ALB, groups without internal gaps), DPunit_hf (HLF_ALB / RHF_ALB) and
- * DPunit_pf (GPF_ALB), as align2 dispatches it (src/maln2.cc:1899-1910), affine or two-piece, for a
+ * for recd_t = DPunit (NGP_ALB, groups without internal gaps), DPunit_hf (HLF_ALB / RHF_ALB),
+ * DPunit_pf (GPF_ALB) and DPunit_nv (NTV_ALB), as align2 dispatches it (src/maln2.cc:1899-1910), affine or two-piece, for a
  * BATCH of independent (a, b) pairs -- e.g. the candidate partitions of Prrn::best_of_n
  * (src/prrn5.cc:594-631).  Precondition as in the reference: PwdM pwd(seqs) already ran (sequences
  * swapped if pwd->swp, mkthick / Gfq / convseq done).  A pg_group is what Fwd2c reads from one mSeq
@@ -122,10 +122,15 @@ typedef struct {
     const double *gfreq;
     int32_t npool;
     const int32_t *sfq, *tfq, *rfq;     /* [npos] or NULL                                             */
+    /* NTV_ALB only (DPunit_nv: small groups of raw residues, no profile; crg11 .. crg22w, src/maln2.cc:
+     * 881-1024,1454-1614): per column, bit i set = member i holds a gap (IsGap, src/seq.h:219); member
+     * weights (1.0 each when the mSeq has none).  many <= 32, no nil ends.  NULL otherwise.             */
+    const uint32_t *gapmask;            /* [npos]                                                     */
+    const double *weight;               /* [many]                                                     */
 } pg_group;
 
 typedef struct {
-    int32_t alnmode;            /* ALN_MODE, src/aln.h:71-76: 6 NGP_ALB, 7 HLF_ALB, 8 RHF_ALB, 9 GPF_ALB
+    int32_t alnmode;            /* ALN_MODE, src/aln.h:71-76: 6 NGP_ALB, 7 HLF_ALB, 8 RHF_ALB, 9 GPF_ALB, 10 NTV_ALB
                                    (100 is internal: the Aln2b1 recurrence behind pg_align_pairs_ng)   */
     int32_t Noll, codonk1;      /* PwdB::Noll, PwdB::codonk1 (src/aln2.cc:100,117)                     */
     int32_t sh;                 /* pwd->alnprm.sh                                                      */

@@ -77,7 +77,7 @@ static const orc_gfreq *g_list(const orc_group *g, const int32_t *offs, int ix)
 
 /* everything below is instantiated for float and double VTYPE */
 #define DEFINE_GROUP_ALIGN(VT, SUFFIX, NEVSEL_V)                                                     \
-typedef struct { VT val; int dir; long ptr; int glb; g_idelta *dla, *dlb; } g_unit_##SUFFIX;         \
+typedef struct { VT val; int dir; long ptr; int glb; g_idelta *dla, *dlb; int *gla, *glv; } g_unit_##SUFFIX;\
                                                                                                      \
 static VT g_newgap4_##SUFFIX(const orc_gfreq *cf, const g_idelta *dlc, const orc_gfreq *df, const g_idelta *dld)\
 {   /* gfreq.cc:507-521 */                                                                           \
@@ -186,6 +186,45 @@ static VT g_unp_##SUFFIX(const g_ctx_##SUFFIX *c, const orc_group *x, int ix, co
 static VT g_gapopen_##SUFFIX(const g_ctx_##SUFFIX *c, const g_unit_##SUFFIX *r, int ia, int ib, int d3)\
 {                                                                                                    \
     const orc_group *a = c->a, *b = c->b;                                                            \
+    if (c->mode == 3) {         /* DPunit_nv: crg2 = crg11 / crg12 / crg21 / crg22 (i and w forms are the\
+                                   many x many weighted form with unit weights; maln2.cc:881-1024,1454-1614);\
+                                   no nil ends: gapdensity = IsGap, postgapdensity = 1 (mseq.h:150-160) */\
+        const uint8_t *ra = a->res + (size_t)ia * a->many, *rb = b->res + (size_t)ib * b->many;      \
+        const int *gla = r->gla, *glb = r->glv;                                                      \
+        VT g = 0;                                                                                    \
+        if (d3 == 0) {                                                                               \
+            for (int i = 0; i < a->many; ++i) {                                                      \
+                VT s = 0;                                                                            \
+                if (ra[i] > 1) {                                                                     \
+                    for (int j = 0; j < b->many; ++j)                                                \
+                        if (rb[j] == 1 && gla[i] >= glb[j]) s += (VT)(b->weight ? b->weight[j] : 1) * (VT)1;\
+                } else if (ra[i] == 1) {                                                             \
+                    for (int j = 0; j < b->many; ++j)                                                \
+                        if (rb[j] > 1 && glb[j] >= gla[i]) s += (VT)(b->weight ? b->weight[j] : 1) * (VT)1;\
+                }                                                                                    \
+                g += s * (VT)(a->weight ? a->weight[i] : 1);                                         \
+            }                                                                                        \
+        } else if (d3 > 0) {                                                                         \
+            for (int i = 0; i < a->many; ++i) {                                                      \
+                if (ra[i] > 1) {                                                                     \
+                    VT s = 0;                                                                        \
+                    for (int j = 0; j < b->many; ++j)                                                \
+                        if (gla[i] >= glb[j]) s += (VT)(b->weight ? b->weight[j] : 1) * (VT)1;        \
+                    g += s * (VT)(a->weight ? a->weight[i] : 1);                                     \
+                }                                                                                    \
+            }                                                                                        \
+        } else {                                                                                     \
+            for (int j = 0; j < b->many; ++j) {                                                      \
+                if (rb[j] > 1) {                                                                     \
+                    VT s = 0;                                                                        \
+                    for (int i = 0; i < a->many; ++i)                                                \
+                        if (glb[j] >= gla[i]) s += (VT)(a->weight ? a->weight[i] : 1) * (VT)1;        \
+                    g += s * (VT)(b->weight ? b->weight[j] : 1);                                     \
+                }                                                                                    \
+            }                                                                                        \
+        }                                                                                            \
+        return (VT)(g * c->bgop);                                                                    \
+    }                                                                                                \
     if (c->mode == 0) {         /* no di-thickness (only under -Q): thickness products */            \
         VT axb = 0;                                                                                  \
         if (d3 > 0) { if (!g_isvert(r->dir)) axb = (VT)a->cfq[ia] * (VT)b->efq[ib]; }                \
@@ -222,6 +261,11 @@ static void g_update_##SUFFIX(const g_ctx_##SUFFIX *c, g_unit_##SUFFIX *dst, con
         else if (d3 > 0) { g_newdelta(dst->dla, g_list(a, a->tfq, ia), src->dla, 1); g_incdelta(dst->dlb, src->dlb, 1); }\
         else { g_newdelta(dst->dlb, g_list(b, b->tfq, ib), src->dlb, 1); g_incdelta(dst->dla, src->dla, 1); }\
     }                                                                                                \
+    if (c->mode == 3) {         /* elongap (mgaps.cc:442-451) on both run-length vectors */          \
+        const uint8_t *ra = a->res + (size_t)ia * a->many, *rb = b->res + (size_t)ib * b->many;      \
+        for (int i = 0; i < a->many; ++i) dst->gla[i] = (d3 >= 0) ? (ra[i] <= 1 ? src->gla[i] + 1 : 0) : src->gla[i] + 1;\
+        for (int j = 0; j < b->many; ++j) dst->glv[j] = (d3 <= 0) ? (rb[j] <= 1 ? src->glv[j] + 1 : 0) : src->glv[j] + 1;\
+    }                                                                                                \
     dst->dir = dir;                                                                                  \
     dst->val = src->val + gpn;                                                                       \
     dst->ptr = src->ptr;                                                                             \
@@ -229,15 +273,17 @@ static void g_update_##SUFFIX(const g_ctx_##SUFFIX *c, g_unit_##SUFFIX *dst, con
 static void g_reset_##SUFFIX(const g_ctx_##SUFFIX *c, g_unit_##SUFFIX *r)                            \
 {   /* reset<recd_t> (dpunit.cc) */                                                                  \
     r->val = NEVSEL_V; r->dir = 0; r->ptr = 0; r->glb = 0;                                           \
-    if (c->mode >= 1) g_cleardelta(r->dla);                                                          \
+    if (c->mode == 1 || c->mode == 2) g_cleardelta(r->dla);                                          \
     if (c->mode == 2) g_cleardelta(r->dlb);                                                          \
+    if (c->mode == 3) { memset(r->gla, 0, sizeof(int) * (size_t)c->a->many); memset(r->glv, 0, sizeof(int) * (size_t)c->b->many); }\
 }                                                                                                    \
 static void g_copy_##SUFFIX(const g_ctx_##SUFFIX *c, g_unit_##SUFFIX *d, const g_unit_##SUFFIX *s)   \
 {   /* copy<recd_t> (dpunit.cc) */                                                                   \
     if (d == s) return;                                                                              \
     d->val = s->val; d->dir = s->dir; d->ptr = s->ptr; d->glb = s->glb;                              \
-    if (c->mode >= 1) g_copydelta(d->dla, s->dla);                                                   \
+    if (c->mode == 1 || c->mode == 2) g_copydelta(d->dla, s->dla);                                   \
     if (c->mode == 2) g_copydelta(d->dlb, s->dlb);                                                   \
+    if (c->mode == 3) { memcpy(d->gla, s->gla, sizeof(int) * (size_t)c->a->many); memcpy(d->glv, s->glv, sizeof(int) * (size_t)c->b->many); }\
 }                                                                                                    \
                                                                                                      \
 static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double *mtx, int dim,      \
@@ -246,7 +292,7 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
     typedef g_unit_##SUFFIX U;                                                                       \
     g_ctx_##SUFFIX C;                                                                                \
     C.a = a; C.b = b; C.p = p; C.mtx = mtx; C.dim = dim;                                             \
-    C.mode = p->alnmode == 6 ? 0 : (p->alnmode == 9 ? 2 : 1);   /* NGP_ALB / HLF_ALB, RHF_ALB / GPF_ALB */\
+    C.mode = p->alnmode == 6 ? 0 : (p->alnmode == 9 ? 2 : (p->alnmode == 10 ? 3 : 1));   /* NGP / HLF, RHF / GPF / NTV _ALB */\
     C.wgop = (VT)p->Weighted_GOP; C.bgop = (VT)p->Basic_GOP;                                         \
     const VT BasicGOP = (VT)p->BasicGOP, BasicGEP = (VT)p->BasicGEP, LongGOP = (VT)p->LongGOP, LongGEP = (VT)p->LongGEP;\
     const VT u2divu1 = BasicGEP < 0 ? (VT)LongGEP / BasicGEP : 0;       /* fwd2c.h:85-86 */          \
@@ -264,7 +310,9 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
     const int nrec = 6 * NB + 8;                                                                     \
     U *buf = (U *)malloc(sizeof(U) * (size_t)nrec);                                                  \
     g_idelta *pool = (g_idelta *)malloc(sizeof(g_idelta) * (size_t)nrec * (size_t)(capa + capb));    \
+    int *glpool = (int *)calloc((size_t)nrec * (size_t)(a->many + b->many), sizeof(int));            \
     for (int i = 0; i < nrec; ++i) {                                                                 \
+        buf[i].gla = glpool + (size_t)i * (a->many + b->many); buf[i].glv = buf[i].gla + a->many;    \
         buf[i].dla = pool + (size_t)i * (capa + capb); buf[i].dlb = buf[i].dla + capa;               \
         g_cleardelta(buf[i].dla); g_cleardelta(buf[i].dlb);                                          \
         buf[i].val = NEVSEL_V; buf[i].dir = 0; buf[i].ptr = 0; buf[i].glb = 0;                       \
@@ -387,7 +435,7 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
         if (!st.v[q].p) break;                                                                       \
     }                                                                                                \
     out[0].m = 0; out[0].n = cnt;                                                                    \
-    free(buf); free(pool); free(st.v);                                                               \
+    free(buf); free(pool); free(glpool); free(st.v);                                                 \
     return ok ? cnt : -1;                                                                            \
 }
 

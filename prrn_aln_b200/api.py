@@ -55,7 +55,8 @@ class _PgGroup(C.Structure):
     _fields_ = [("many", C.c_int32), ("len", C.c_int32), ("left", C.c_int32), ("right", C.c_int32),
                 ("hetero", C.c_int32), ("nils", C.c_int32), ("cfq", C.c_void_p), ("efq", C.c_void_p),
                 ("vec", C.c_void_p), ("glen", C.c_void_p), ("gfreq", C.c_void_p), ("npool", C.c_int32),
-                ("sfq", C.c_void_p), ("tfq", C.c_void_p), ("rfq", C.c_void_p)]
+                ("sfq", C.c_void_p), ("tfq", C.c_void_p), ("rfq", C.c_void_p), ("gapmask", C.c_void_p),
+                ("weight", C.c_void_p)]
 
 
 class GParams(C.Structure):
@@ -71,7 +72,9 @@ def _pg_group(S):
     g = _PgGroup(S["many"], S["len"], S["left"], S["right"], S["hetero"], S["nils"], S["cfq"].ctypes.data,
                  S["efq"].ctypes.data, S["vec"].ctypes.data, S["glen"].ctypes.data, S["gfreq"].ctypes.data,
                  len(S["glen"]), S["sfq"].ctypes.data if has else None, S["tfq"].ctypes.data if has else None,
-                 S["rfq"].ctypes.data if has else None)
+                 S["rfq"].ctypes.data if has else None,
+                 S["gapmask"].ctypes.data if S.get("gapmask") is not None else None,
+                 S["weight"].ctypes.data if S.get("weight") is not None else None)
     return g
 
 

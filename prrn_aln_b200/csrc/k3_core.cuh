@@ -38,10 +38,15 @@ struct K3Group {
     const int32_t* rfq;
     int32_t L;              // right - left
     int32_t nils;
+    // mode 4 (DPunit_nv, groups of raw residues without profile): per column, bit i = member i holds a gap
+    const uint32_t* gapmask;
+    const double* weight;   // [many] member weights (1 when the reference has none)
+    int32_t many;
+    int32_t pad;
 };
 
 struct K3Prm {
-    int32_t mode;           // 0 DPunit, 1 DPunit_hf, 2 DPunit_pf, 3 Aln2b1 (RVPD records, fwd2b1.cc)
+    int32_t mode;           // 0 DPunit, 1 DPunit_hf, 2 DPunit_pf, 3 Aln2b1 (RVPD records, fwd2b1.cc), 4 DPunit_nv
     int32_t Noll, codonk1;
     int32_t lw, up;         // band in window-relative coordinates (r = n - m)
     int32_t capa, capb;     // list capacities (pairs)
@@ -172,8 +177,46 @@ PG_HD double k3_sim(const K3Group& a, const K3Group& b, const K3Prm& p, int ia, 
 PG_HD double k3_unp(const K3Group& x, int ix, const K3Group& y, int iy, double u) { return x.cfq[ix] * y.efq[iy] * -u; }
 
 // gapopen (fwd2c.cc:52-91 without di-thickness, :152-161, :202-212)
+// DPunit_nv: crg2 (src/maln2.cc:881-1024 crg11/12i/21i/22i, :1454-1614 the weighted forms) is, for every
+// variant, the many x many weighted form with unit weights where the reference has none.  The record's
+// two "lists" hold the members' current gap run lengths (gla / glb, 16 bit each).  No nil ends:
+// gapdensity = IsGap, postgapdensity = 1 (src/mseq.h:150-160).
+PG_HD double k3_crg(const K3Group& a, const K3Group& b, const k3u16* gla, const k3u16* glb, unsigned am, unsigned bm, int d3)
+{
+    double g = 0;
+    if (d3 == 0) {
+        for (int i = 0; i < a.many; ++i) {
+            double s = 0;
+            const bool agap = (am >> i) & 1u;
+            for (int j = 0; j < b.many; ++j) {
+                const bool bgap = (bm >> j) & 1u;
+                if (!agap ? (bgap && gla[i] >= glb[j]) : (!bgap && glb[j] >= gla[i])) s += b.weight[j];
+            }
+            g += s * a.weight[i];
+        }
+    } else if (d3 > 0) {
+        for (int i = 0; i < a.many; ++i)
+            if (!((am >> i) & 1u)) {
+                double s = 0;
+                for (int j = 0; j < b.many; ++j)
+                    if (gla[i] >= glb[j]) s += b.weight[j];
+                g += s * a.weight[i];
+            }
+    } else {
+        for (int j = 0; j < b.many; ++j)
+            if (!((bm >> j) & 1u)) {
+                double s = 0;
+                for (int i = 0; i < a.many; ++i)
+                    if (glb[j] >= gla[i]) s += a.weight[i];
+                g += s * b.weight[j];
+            }
+    }
+    return g;
+}
+
 PG_HD double k3_gapopen(const K3Prm& p, const K3Group& a, const K3Group& b, const int* r, int ia, int ib, int d3)
 {
+    if (p.mode == 4) return k3_crg(a, b, k3_dla(r), k3_dlb(r, p.capa), a.gapmask[ia], b.gapmask[ib], d3) * p.bgop;
     if (p.mode == 0) {
         double axb = 0;
         if (d3 > 0) { if (!k3_isvert(k3_dir(r))) axb = a.cfq[ia] * b.efq[ib]; }
@@ -205,7 +248,13 @@ PG_HD void k3_update(const K3Prm& p, const K3Group& a, const K3Group& b, int* ds
     else if (d3 < 0) dir = k3_isvert(sdir) ? K3_NEWH : K3_HORI;
     else dir = k3_isdiag(sdir) ? K3_DIAG : K3_NEWD;
     int glb = 0;
-    if (p.mode == 1) {
+    if (p.mode == 4) {          // elongap (src/mgaps.cc:442-451) on both run-length vectors
+        const unsigned am = a.gapmask[ia], bm = b.gapmask[ib];
+        k3u16* da = k3_dla(dst); const k3u16* sa = k3_dla(src);
+        k3u16* db = k3_dlb(dst, p.capa); const k3u16* sb = k3_dlb(src, p.capa);
+        for (int i = 0; i < a.many; ++i) da[i] = (k3u16)((d3 >= 0) ? (((am >> i) & 1u) ? sa[i] + 1 : 0) : sa[i] + 1);
+        for (int j = 0; j < b.many; ++j) db[j] = (k3u16)((d3 <= 0) ? (((bm >> j) & 1u) ? sb[j] + 1 : 0) : sb[j] + 1);
+    } else if (p.mode == 1) {
         const int o = a.tfq ? a.tfq[ia] : -1;
         if (d3 == 0) k3_newdelta(k3_dla(dst), o >= 0 ? a.glen + o : nullptr, k3_dla(src));
         else if (d3 > 0) { glb = k3_glb(src) + 1; k3_newdelta(k3_dla(dst), o >= 0 ? a.glen + o : nullptr, k3_dla(src)); }
@@ -228,6 +277,10 @@ PG_HD void k3_reset(const K3Prm& p, int* r)
 {
     k3_setval(r, K3_NEVSEL);
     K3_PTR(r) = 0; k3_setdg(r, 0, 0);
+    if (p.mode == 4) {          // reset<DPunit_nv>: vclear(gla, dtsize)
+        for (int w = 0; w < p.capa + p.capb; ++w) r[4 + w] = 0;
+        return;
+    }
     k3_cleardelta(k3_dla(r));
     k3_cleardelta(k3_dlb(r, p.capa));
 }
@@ -235,7 +288,8 @@ PG_HD void k3_copy(const K3Prm& p, int* d, const int* s)
 {
     if (d == s) return;
     d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
-    if (p.mode >= 1) k3_copydelta(k3_dla(d), k3_dla(s));
+    if (p.mode == 4) { for (int w = 0; w < p.capa + p.capb; ++w) d[4 + w] = s[4 + w]; return; }
+    if (p.mode == 1 || p.mode == 2) k3_copydelta(k3_dla(d), k3_dla(s));
     if (p.mode == 2) k3_copydelta(k3_dlb(d, p.capa), k3_dlb(s, p.capa));
 }
 

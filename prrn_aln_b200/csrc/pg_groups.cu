@@ -43,7 +43,7 @@ extern "C" int64_t pg_group_cells(const pg_group* a, const pg_group* b, int32_t 
 }
 
 namespace {
-struct SideOff { size_t cfq, efq, vec, glen, gfreq, sfq, tfq, rfq; };
+struct SideOff { size_t cfq, efq, vec, glen, gfreq, sfq, tfq, rfq, gapmask, weight; };
 
 size_t place_side(const pg_group& g, int kdim, size_t off, SideOff* so)
 {
@@ -57,6 +57,8 @@ size_t place_side(const pg_group& g, int kdim, size_t off, SideOff* so)
     so->sfq = off; off = up16(off + 4 * npos);
     so->tfq = off; off = up16(off + 4 * npos);
     so->rfq = off; off = up16(off + 4 * npos);
+    so->gapmask = off; off = up16(off + 4 * npos);
+    so->weight = off; off = up16(off + 8 * (size_t)std::max(g.many, 1));
     return off;
 }
 
@@ -80,6 +82,8 @@ void fill_side(const pg_group& g, int kdim, const SideOff& so, char* h)
         memset(h + so.tfq, 0xff, 4 * npos);
         memset(h + so.rfq, 0xff, 4 * npos);
     }
+    if (g.gapmask) memcpy(h + so.gapmask, g.gapmask, 4 * npos); else memset(h + so.gapmask, 0, 4 * npos);
+    for (int i = 0; i < std::max(g.many, 1); ++i) ((double*)(h + so.weight))[i] = (g.weight && i < g.many) ? g.weight[i] : 1.0;
 }
 
 K3Group dev_side(const pg_group& g, const SideOff& so, const char* d)
@@ -91,6 +95,10 @@ K3Group dev_side(const pg_group& g, const SideOff& so, const char* d)
     k.sfq = (const int32_t*)(d + so.sfq); k.tfq = (const int32_t*)(d + so.tfq); k.rfq = (const int32_t*)(d + so.rfq);
     k.L = g.right - g.left;
     k.nils = g.nils;
+    k.gapmask = (const uint32_t*)(d + so.gapmask);
+    k.weight = (const double*)(d + so.weight);
+    k.many = g.many;
+    k.pad = 0;
     return k;
 }
 }  // namespace
@@ -129,6 +137,7 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
         case 6: mode = 0; break;
         case 7: case 8: mode = 1; break;
         case 9: mode = 2; break;
+        case 10: mode = 4; break;       // NTV_ALB: DPunit_nv
         case 100: mode = 3; break;      // PG_ALN_B1_NG: Aln2b1 (pg_align_pairs_ng), two single sequences
         default:
             free(offs);
@@ -154,6 +163,15 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
         const int r0 = B.left - A.left;
         kp.lw = lw - r0; kp.up = up - r0;
         kp.capa = std::max(A.hetero, 0) + 3; kp.capb = std::max(B.hetero, 0) + 3;
+        if (mode == 4) {
+            if (!A.gapmask || !B.gapmask || A.many < 1 || B.many < 1 || A.many > 32 || B.many > 32 || A.nils || B.nils) {
+                free(offs);
+                return pg_int_fail(c, (A.nils || B.nils) ? PG_ERR_UNSUPPORTED : PG_ERR_ARG,
+                                   "pg_align_groups: NTV_ALB needs gap masks, 1..32 members per group and no nil ends "
+                                   "(semi-global naive mode is not built yet)");
+            }
+            kp.capa = (A.many + 1) / 2 + 1; kp.capb = (B.many + 1) / 2 + 1;     // 16-bit run lengths, two per word
+        }
         kp.u = (double)(float)P.u;
         kp.wgop = P.Weighted_GOP; kp.bgop = P.Basic_GOP;
         kp.u2divu1 = P.BasicGEP < 0 ? P.LongGEP / P.BasicGEP : 0;      // fwd2c.h:85-86

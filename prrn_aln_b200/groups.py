@@ -18,6 +18,7 @@ DECOMPACT = (0, 1, 2, 3, 5, 9)      # nil, gap, A, C, G, T (src/mseq.h:38) for s
 
 # ALN_MODE (src/aln.h:71-76)
 NGP_ALB, HLF_ALB, RHF_ALB, GPF_ALB, NTV_ALB = 6, 7, 8, 9, 10
+K3_MODE = {NGP_ALB: 0, HLF_ALB: 1, RHF_ALB: 1, GPF_ALB: 2, NTV_ALB: 4}
 
 
 def _onehot(g, dim):
@@ -85,8 +86,16 @@ def stage_pair(ga, gb, a_mode, b_mode, mtx, dxd=False):
     out = []
     for g, vec in ((ga, xa), (gb, yb)):
         glen, gfreq, offs = _lists(g)
+        res = np.asarray(g["res"], np.int64)
+        gapmask = weight = None
+        if res.ndim == 2 and res.shape[1] <= 32:     # NTV_ALB (DPunit_nv): IsGap bits per column + member weights
+            gapmask = np.zeros(res.shape[0], np.uint32)
+            for i in range(res.shape[1]):
+                gapmask |= (res[:, i] <= 1).astype(np.uint32) << np.uint32(i)
+            weight = (np.ones(res.shape[1]) if g.get("weight") is None else np.asarray(g["weight"], np.float64)).copy()
         out.append(dict(many=g["many"], len=g["len"], left=g["left"], right=g["right"], hetero=g["hetero"],
                         nils=g["nils"], cfq=np.ascontiguousarray(g["cfq"], np.float64),
                         efq=np.ascontiguousarray(g["efq"], np.float64), vec=np.ascontiguousarray(vec, np.float64),
-                        glen=glen, gfreq=gfreq, sfq=offs["sfq"], tfq=offs["tfq"], rfq=offs["rfq"]))
+                        glen=glen, gfreq=gfreq, sfq=offs["sfq"], tfq=offs["tfq"], rfq=offs["rfq"],
+                        gapmask=gapmask, weight=weight))
     return out[0], out[1]

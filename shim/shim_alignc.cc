@@ -3,7 +3,7 @@
 // The reference instantiates   template<class recd_t> SKL* alignC(mSeq* seqs[], PwdM*, VTYPE*, bool, WINDOW*)
 // (src/fwd2c.h:670-677) inside maln2.o as WEAK out-of-line functions; align2 (src/maln2.cc:1888-1910)
 // and prrn5's refinement reach the DP through them.  This file provides STRONG explicit specialisations
-// for recd_t = DPunit, DPunit_hf, DPunit_pf, so that once it is linked with the unmodified reference
+// for recd_t = DPunit, DPunit_hf, DPunit_pf, DPunit_nv, so that once it is linked with the unmodified reference
 // objects every one of those calls lands here: the groups are staged exactly as Fwd2c would read them
 // (mSeqItr over left-1 .. right-1 after PwdM's own convseq / mkthick / Gfq) and the banded fill with path
 // runs in libprrn_gpu.so (pg_align_groups: kernels K4 + K3).  Modes the library does not take yet
@@ -30,8 +30,9 @@ static pg_context* pg_ctx_groups()
 }
 
 struct PgSide {
-	std::vector<double>	cfq, efq, vec, gfreq;
+	std::vector<double>	cfq, efq, vec, gfreq, weight;
 	std::vector<int32_t>	glen, sfq, tfq, rfq;
+	std::vector<uint32_t>	gapmask;
 	int32_t	pool(GFREQ** pp) {
 	    if (!pp || !*pp) return (-1);
 	    int32_t	at = (int32_t) glen.size();
@@ -52,9 +53,16 @@ static void pg_stage(mSeq* sd, PgSide& S, const PwdM* pwd, bool is_a, const Simm
 	const bool	dxd = pwd->DvsP == 0;
 	S.cfq.resize(npos); S.efq.resize(npos); S.vec.assign((size_t) npos * K, 0.);
 	S.sfq.assign(npos, -1); S.tfq.assign(npos, -1); S.rfq.assign(npos, -1);
+	const bool	naive = pwd->alnmode == NTV_ALB && sd->many <= 32;	// DPunit_nv: IsGap bits + member weights
+	if (naive) {
+	    S.gapmask.assign(npos, 0);
+	    S.weight.assign(sd->many, 1.);
+	    if (sd->weight) for (int i = 0; i < sd->many; ++i) S.weight[i] = sd->weight[i];
+	}
 	for (int x = 0, p = sd->left - 1; x < npos; ++x, ++p) {
 	    mSeqItr	it(sd, p);
 	    S.cfq[x] = it.dns->cfq; S.efq[x] = it.dns->efq;
+	    if (naive) for (int i = 0; i < sd->many; ++i) if (IsGap(it.res[i])) S.gapmask[x] |= 1u << i;
 	    double*	v = &S.vec[(size_t) x * K];
 	    bool	profile_part = my_mode == 2 && (is_a || ot_mode != 2);
 	    bool	freq_part = my_mode == 2 && !profile_part;
@@ -88,6 +96,8 @@ static pg_group pg_view(mSeq* sd, PgSide& S)
 	g.glen = S.glen.data(); g.gfreq = S.gfreq.data(); g.npool = (int32_t) S.glen.size();
 	bool	lists = sd->gfq && sd->inex.dels;
 	g.sfq = lists? S.sfq.data(): 0; g.tfq = lists? S.tfq.data(): 0; g.rfq = lists? S.rfq.data(): 0;
+	g.gapmask = S.gapmask.empty()? 0: S.gapmask.data();
+	g.weight = S.weight.empty()? 0: S.weight.data();
 	return (g);
 }
 
@@ -95,7 +105,9 @@ template <class recd_t>
 static SKL* pg_alignC(mSeq* seqs[], PwdM* pwd, VTYPE* scr, bool rectangle, WINDOW* pwdw)
 {
 	bool	banded = pwd->alnmode == NGP_ALB || pwd->alnmode == HLF_ALB ||
-			 pwd->alnmode == RHF_ALB || pwd->alnmode == GPF_ALB;
+			 pwd->alnmode == RHF_ALB || pwd->alnmode == GPF_ALB ||
+			 (pwd->alnmode == NTV_ALB && !seqs[0]->inex.nils && !seqs[1]->inex.nils &&
+			  seqs[0]->many <= 32 && seqs[1]->many <= 32);
 	if (rectangle || pwdw || !banded || (algmode.lcl & 16)) {	// not built yet: the reference's own Fwd2c
 	    Fwd2c<recd_t>	pwa(seqs, pwd, true, rectangle, pwdw);
 	    *scr = rectangle? pwa.forwardA(0): pwa.forwardB(0);
@@ -131,3 +143,5 @@ template <> SKL* alignC<DPunit_hf>(mSeq* seqs[], PwdM* pwd, VTYPE* scr, bool rec
 	{return pg_alignC<DPunit_hf>(seqs, pwd, scr, rectangle, pwdw);}
 template <> SKL* alignC<DPunit_pf>(mSeq* seqs[], PwdM* pwd, VTYPE* scr, bool rectangle, WINDOW* pwdw)
 	{return pg_alignC<DPunit_pf>(seqs, pwd, scr, rectangle, pwdw);}
+template <> SKL* alignC<DPunit_nv>(mSeq* seqs[], PwdM* pwd, VTYPE* scr, bool rectangle, WINDOW* pwdw)
+	{return pg_alignC<DPunit_nv>(seqs, pwd, scr, rectangle, pwdw);}

@@ -64,7 +64,8 @@ def test_reference_align2_on_gpu_library(name, tmp_path):
 
 
 GALIGN_CASES = ["galign_c1_multi_ab_f64", "galign_gpf_prof12_raw5_wt", "galign_gpf_prof34_prof30", "galign_hlf_prof10_single",
-                "galign_rhf_single_prof10", "galign_gpf_twopiece", "galign_gpf_highhetero", "galign_ngp_gapless4x3"]
+                "galign_rhf_single_prof10", "galign_gpf_twopiece", "galign_gpf_highhetero", "galign_ngp_gapless4x3",
+                "galign_gpf_lcl15", "galign_hlf_lcl10", "galign_ntv_2x2", "galign_ntv_3x1_wt", "galign_ntv_1x3_twopiece"]
 
 
 @pytest.mark.parametrize("name", GALIGN_CASES)

@@ -16,7 +16,8 @@ from prrn_aln_b200 import groups as G
 class K3Group(C.Structure):
     _fields_ = [("cfq", C.c_void_p), ("efq", C.c_void_p), ("prof", C.c_void_p), ("freq", C.c_void_p),
                 ("glen", C.c_void_p), ("gfreq", C.c_void_p), ("sfq", C.c_void_p), ("tfq", C.c_void_p),
-                ("rfq", C.c_void_p), ("L", C.c_int32), ("nils", C.c_int32)]
+                ("rfq", C.c_void_p), ("L", C.c_int32), ("nils", C.c_int32), ("gapmask", C.c_void_p),
+                ("weight", C.c_void_p), ("many", C.c_int32), ("pad", C.c_int32)]
 
 
 class K3Prm(C.Structure):
@@ -39,7 +40,9 @@ def emul3():
 def _k3group(S):
     g = K3Group(S["cfq"].ctypes.data, S["efq"].ctypes.data, S["vec"].ctypes.data, S["vec"].ctypes.data,
                 S["glen"].ctypes.data, S["gfreq"].ctypes.data, S["sfq"].ctypes.data, S["tfq"].ctypes.data,
-                S["rfq"].ctypes.data, S["right"] - S["left"], S["nils"])
+                S["rfq"].ctypes.data, S["right"] - S["left"], S["nils"],
+                S["gapmask"].ctypes.data if S.get("gapmask") is not None else None,
+                S["weight"].ctypes.data if S.get("weight") is not None else None, S.get("many", 1), 0)
     g._keep = S
     return g
 
@@ -51,9 +54,12 @@ def test_wavefront_emulation_matches_reference(emul3, name):
     A, B = G.stage_pair(d["groups"][0], d["groups"][1], pm["a_mode"], pm["b_mode"], d["matrix"], dxd=(pm["DvsP"] == 0))
     lw, up, _ = d["window"]
     r0 = B["left"] - A["left"]
-    mode = {6: 0, 7: 1, 8: 1, 9: 2}[pm["alnmode"]]
+    mode = G.K3_MODE[pm["alnmode"]]
+    capa, capb = max(A["hetero"], 0) + 3, max(B["hetero"], 0) + 3
+    if mode == 4:
+        capa, capb = (A["many"] + 1) // 2 + 1, (B["many"] + 1) // 2 + 1
     bgep, lgep, bgop, lgop = pc["BasicGEP"], pc["LongGEP"], pc["BasicGOP"], pc["LongGOP"]
-    p = K3Prm(mode, pm["Noll"], pm["codonk1"], lw - r0, up - r0, max(A["hetero"], 0) + 3, max(B["hetero"], 0) + 3,
+    p = K3Prm(mode, pm["Noll"], pm["codonk1"], lw - r0, up - r0, capa, capb,
               A["vec"].shape[1], float(np.float32(float(h["u"]))), -float(np.float32(float(h["v"]))), pc["vgop1"],
               lgep / bgep if bgep < 0 else 0.0, lgop / bgop if bgop < 0 else 0.0, bgop, bgep, lgop, lgep, 1.0, 1.0)
     want = d["alignc"]

@@ -124,6 +124,37 @@ def galign_cases():
     galign_case("galign_gpf_highhetero", A, B, wt=1, sh=-40)
     A, B = gen_msa.split_family(hh, range(0, 3), range(3, 6))
     galign_case("galign_gpf_raw3x3_gappy", A, B, mtx="blosum62")                 # GPF, sim22i
+    # semi-global (free end gaps on some sides): exg_seq turns terminal gap runs into nil columns, the
+    # thickness / gap-profile staging carries the effect (inex.nils -> pua per cell in forwardB)
+    def ragged(rows, seed):
+        """members that start late / end early: terminal gap runs of 2..9 columns in a third of the rows"""
+        import random
+        rng = random.Random(seed)
+        out = []
+        for r in rows:
+            r = list(r)
+            if rng.random() < 0.35:
+                for k in range(rng.randint(2, 9)):
+                    r[k] = "-"
+            if rng.random() < 0.35:
+                for k in range(rng.randint(2, 9)):
+                    r[-1 - k] = "-"
+            out.append("".join(r))
+        return out
+    A, B = gen_msa.split_family(ragged(fam, 5), range(0, 12), range(12, 17))
+    galign_case("galign_gpf_lcl15", A, B, wt=1, lcl=15)
+    galign_case("galign_gpf_lcl5_tgapf05", A, B, wt=1, lcl=5, tgapf=0.5)
+    galign_case("galign_gpf_ragged_global", A, B, wt=1)
+    A, B = gen_msa.split_family(ragged(fam, 6), range(0, 10), [10])
+    galign_case("galign_hlf_lcl10", A, B, lcl=10)
+    # NTV_ALB (DPunit_nv): small groups of raw residues, no profile (2 nj + ni < 8)
+    A, B = gen_msa.split_family(hh, range(0, 2), range(2, 4))
+    galign_case("galign_ntv_2x2", A, B)
+    galign_case("galign_ntv_2x2_wt_f32", A, B, flavour="f", wt=1)
+    A, B = gen_msa.split_family(hh, range(0, 3), [3])
+    galign_case("galign_ntv_3x1_wt", A, B, wt=1)
+    A, B = gen_msa.split_family(hh, [4], range(5, 8))
+    galign_case("galign_ntv_1x3_twopiece", A, B, ls=3, mtx="blosum62")
     gl = gen_msa.synth_msa(7, 80, 0.2, 0.6, 43, gapless=True)
     galign_case("galign_ngp_gapless4x3", gl[:4], gl[4:], mtx="blosum62")          # NGP with thickness
     dn = gen_msa.synth_msa(12, 120, 0.05, 0.35, 44, dna=True)
