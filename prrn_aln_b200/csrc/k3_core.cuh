@@ -296,28 +296,26 @@ PG_HD void k3_copy(const K3Prm& p, int* d, const int* s)
 // Path records (the reference's Vmf): (m, n, previous record); appended at NEWD / NEWV / NEWH cells
 struct K3Vmf { int m, n, p; };
 
-// One DP cell (fwd2c.h:393-468).  Inputs are read-only records: hdiag = H(m-1,n-1), habove / gabove /
-// g2above = row m-1 at column n (the black record outside the band), hleft = H(m,n-1).  f1 / f2 are the
-// row's running horizontal states (updated in place); hout / gout / g2out receive H, G, G2 of the cell.
-// Returns true when the cell must append a path record (the caller owns the record store).
-PG_HD bool k3_cell(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, int ib, bool first_row, bool first_col,
-                   double dab, double* pua, const int* hdiag, const int* habove, const int* gabove, const int* g2above,
-                   const int* hleft, int* f1, int* f2, int* hout, int* gout, int* g2out, const int* black)
-{
-    // diagonal (fwd2c.h:395-398), straight into the output record
-    double gop = k3_gapopen(p, a, b, hdiag, ia, ib, 0);
+// The cell in four pieces.  The diagonal, vertical and horizontal candidates read disjoint inputs and
+// write disjoint records, so one thread may run them in turn (k3_cell) or three threads side by side
+// (the role-split latency kernel); k3_combine then applies the reference's selection order.
+PG_HD void k3_part_diag(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, int ib, double dab,
+                        const int* hdiag, int* hout)
+{   // diagonal (fwd2c.h:395-398), straight into the output record
+    const double gop = k3_gapopen(p, a, b, hdiag, ia, ib, 0);
     k3_update(p, a, b, hout, hdiag, ia, ib, dab + gop, 0);
-    double gnp;
-    const int* mx;
+}
+PG_HD void k3_part_vert(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, int ib, bool first_row, double* pua,
+                        const int* habove, const int* gabove, const int* g2above, int* gout, int* g2out, const int* black)
+{
     if (!first_row) {       // vertical (fwd2c.h:401-409)
         if (a.nils) *pua = k3_unp(a, ia, b, ib, p.u);
-        gnp = k3_gapopen(p, a, b, gabove, ia, ib, 1);
-        gop = k3_gapopen(p, a, b, habove, ia, ib, 1);
+        double gnp = k3_gapopen(p, a, b, gabove, ia, ib, 1);
+        double gop = k3_gapopen(p, a, b, habove, ia, ib, 1);
         if (!k3_isvert(k3_dir(habove)) && (k3_val(habove) + gop > k3_val(gabove) + gnp))
             k3_update(p, a, b, gout, habove, ia, ib, gop, 1);
         else k3_update(p, a, b, gout, gabove, ia, ib, gnp, 1);
         k3_setval(gout, k3_val(gout) + *pua);
-        mx = gout;
         if (p.Noll == 3) {  // vertical2 (fwd2c.h:411-420)
             gnp = p.v2divv1 * k3_gapopen(p, a, b, g2above, ia, ib, 1);
             gop = p.v2divv1 * gop;
@@ -325,35 +323,59 @@ PG_HD bool k3_cell(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, i
                 k3_update(p, a, b, g2out, habove, ia, ib, gop, 1);
             else k3_update(p, a, b, g2out, g2above, ia, ib, gnp, 1);
             k3_setval(g2out, k3_val(g2out) + p.u2divu1 * *pua);
-            if (k3_val(g2out) > k3_val(mx)) mx = g2out;
         }
     } else {                // first row: the G rows keep their untouched (black) records
         k3_copy(p, gout, black);
         if (p.Noll == 3) k3_copy(p, g2out, black);
-        mx = gout;
     }
-    if (!first_col) {       // horizontal (fwd2c.h:422-431)
-        const double pub = k3_unp(b, ib, a, ia, p.u);
-        gnp = k3_gapopen(p, a, b, f1, ia, ib, -1);
-        gop = k3_gapopen(p, a, b, hleft, ia, ib, -1);
-        if (!k3_ishori(k3_dir(hleft)) && (k3_val(hleft) + gop > k3_val(f1) + gnp))
-            k3_update(p, a, b, f1, hleft, ia, ib, gop, -1);
-        else k3_update(p, a, b, f1, f1, ia, ib, gnp, -1);
-        k3_setval(f1, k3_val(f1) + pub);
+}
+PG_HD void k3_part_hori(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, int ib, bool first_col,
+                        const int* hleft, int* f1, int* f2)
+{
+    if (first_col) return;  // horizontal (fwd2c.h:422-431)
+    const double pub = k3_unp(b, ib, a, ia, p.u);
+    double gnp = k3_gapopen(p, a, b, f1, ia, ib, -1);
+    double gop = k3_gapopen(p, a, b, hleft, ia, ib, -1);
+    if (!k3_ishori(k3_dir(hleft)) && (k3_val(hleft) + gop > k3_val(f1) + gnp))
+        k3_update(p, a, b, f1, hleft, ia, ib, gop, -1);
+    else k3_update(p, a, b, f1, f1, ia, ib, gnp, -1);
+    k3_setval(f1, k3_val(f1) + pub);
+    if (p.Noll == 3) {      // horizontal2 (fwd2c.h:433-442)
+        gnp = p.v2divv1 * k3_gapopen(p, a, b, f2, ia, ib, -1);
+        gop = p.v2divv1 * gop;
+        if (!k3_ishori(k3_dir(hleft)) && (k3_val(hleft) + gop > k3_val(f2) + gnp))
+            k3_update(p, a, b, f2, hleft, ia, ib, gop, -1);
+        else k3_update(p, a, b, f2, f2, ia, ib, gnp, -1);
+        k3_setval(f2, k3_val(f2) + p.u2divu1 * pub);
+    }
+}
+// selection (fwd2c.h:409-453): G first, G2 beats it on >, F1 and F2 on >=; the gap state replaces the diagonal
+// only if strictly better.  Returns true when the cell must append a path record (:465-467).
+PG_HD bool k3_combine(const K3Prm& p, bool first_row, bool first_col, int* hout, const int* gout, const int* g2out,
+                      const int* f1, const int* f2)
+{
+    const int* mx = gout;
+    if (!first_row && p.Noll == 3 && k3_val(g2out) > k3_val(mx)) mx = g2out;
+    if (!first_col) {
         if (k3_val(f1) >= k3_val(mx)) mx = f1;
-        if (p.Noll == 3) {  // horizontal2 (fwd2c.h:433-442)
-            gnp = p.v2divv1 * k3_gapopen(p, a, b, f2, ia, ib, -1);
-            gop = p.v2divv1 * gop;
-            if (!k3_ishori(k3_dir(hleft)) && (k3_val(hleft) + gop > k3_val(f2) + gnp))
-                k3_update(p, a, b, f2, hleft, ia, ib, gop, -1);
-            else k3_update(p, a, b, f2, f2, ia, ib, gnp, -1);
-            k3_setval(f2, k3_val(f2) + p.u2divu1 * pub);
-            if (k3_val(f2) >= k3_val(mx)) mx = f2;
-        }
+        if (p.Noll == 3 && k3_val(f2) >= k3_val(mx)) mx = f2;
     }
-    if (k3_val(mx) > k3_val(hout)) k3_copy(p, hout, mx);        // fwd2c.h:453
+    if (k3_val(mx) > k3_val(hout)) k3_copy(p, hout, mx);
     const int dir = k3_dir(hout);
-    return dir == K3_NEWD || dir == K3_NEWV || dir == K3_NEWH;   // fwd2c.h:465-467
+    return dir == K3_NEWD || dir == K3_NEWV || dir == K3_NEWH;
+}
+
+// One DP cell (fwd2c.h:393-468).  Inputs are read-only records: hdiag = H(m-1,n-1), habove / gabove /
+// g2above = row m-1 at column n (the black record outside the band), hleft = H(m,n-1).  f1 / f2 are the
+// row's running horizontal states (updated in place); hout / gout / g2out receive H, G, G2 of the cell.
+PG_HD bool k3_cell(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, int ib, bool first_row, bool first_col,
+                   double dab, double* pua, const int* hdiag, const int* habove, const int* gabove, const int* g2above,
+                   const int* hleft, int* f1, int* f2, int* hout, int* gout, int* g2out, const int* black)
+{
+    k3_part_diag(p, a, b, ia, ib, dab, hdiag, hout);
+    k3_part_vert(p, a, b, ia, ib, first_row, pua, habove, gabove, g2above, gout, g2out, black);
+    k3_part_hori(p, a, b, ia, ib, first_col, hleft, f1, f2);
+    return k3_combine(p, first_row, first_col, hout, gout, g2out, f1, f2);
 }
 
 // One DP cell of Aln2b1::forwardB_ng (src/fwd2b1.cc:176-249, global mode): a gap opens on >=, the

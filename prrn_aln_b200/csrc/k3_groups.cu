@@ -49,26 +49,31 @@ __device__ __forceinline__ void group_sync(int g)
 
 // TG threads per alignment: the whole CTA for few pairs (latency), down to one warp per alignment for
 // large batches (no block barrier at all, 95 % of the lane-steps inside the matrix instead of 72 %).
-template <int TG>
-__global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
+// SPLIT (latency mode, TG = 256 only): three threads per row -- the diagonal, vertical and horizontal
+// candidates of a cell are computed side by side by threads of three warp groups ("roles"), a second
+// barrier, then role 0 applies the selection.  Same records, same results, ~1/3 of the per-step chain.
+template <int TG, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_kernel(const K3Args a)
 {
-    constexpr int NG = CTA / TG;        // alignments in flight per CTA
+    constexpr int NG = SPLIT ? 1 : CTA / TG;        // alignments in flight per CTA
     extern __shared__ __align__(16) int sm_dyn[];
     __shared__ int sm_pair[NG];
     __shared__ int sm_vmf[NG];
     __shared__ int sm_last_ptr[NG];
     __shared__ double sm_last_val[NG];
-    const int g = threadIdx.x / TG;
-    const int t = threadIdx.x - g * TG;
+    const int role = SPLIT ? threadIdx.x / TG : 0;  // 0 diagonal (+ selection), 1 vertical, 2 horizontal
+    const int g = SPLIT ? 0 : threadIdx.x / TG;
+    const int t = threadIdx.x - (SPLIT ? role : g) * TG;
     const int slot = blockIdx.x * NG + g;
     int* const arena = a.arena + (size_t)slot * a.arena_words;
     K3Vmf* const vmf = a.vmf + (size_t)slot * a.vmf_cap;
     int* const sm_grp = sm_dyn + (size_t)g * (a.smem_bytes / 4 / NG);
     const size_t sm_grp_words = (size_t)(a.smem_bytes / 4 / NG);
 
+#define GSYNC() do { if (SPLIT) __syncthreads(); else group_sync<TG>(g); } while (0)
     for (;;) {
-        if (t == 0) sm_pair[g] = atomicAdd(a.counter, 1);
-        group_sync<TG>(g);
+        if (t == 0 && role == 0) sm_pair[g] = atomicAdd(a.counter, 1);
+        GSYNC();
         const int pi = sm_pair[g];
         if (pi >= a.npairs) break;
         const K3Pair& P_ = a.pairs[pi];
@@ -97,6 +102,7 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
         int* const pubG2 = F1 + (size_t)TG * st;            // [2][TG]   (two-piece only)
         int* const F2 = pubG2 + (size_t)2 * TG * st;        // [TG]
         // ---- reset the records this pair can read before writing
+        if (role == 0) {
         for (int i = t; i < LS + 2; i += TG) {
             k3_reset(p, rowH + (size_t)i * st); k3_reset(p, rowG + (size_t)i * st);
             if (n3) k3_reset(p, rowG2 + (size_t)i * st);
@@ -106,9 +112,10 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
         for (int k = 0; k < 2; ++k) { k3_reset(p, pubG + ((size_t)k * TG + t) * st); if (n3) k3_reset(p, pubG2 + ((size_t)k * TG + t) * st); }
         if (t < RING) { k3_reset(p, ringH + (size_t)t * st); k3_reset(p, ringG + (size_t)t * st); k3_reset(p, ringG2 + (size_t)t * st); }
         if (t == 0) k3_reset(p, black);
-        group_sync<TG>(g);
+        }
+        GSYNC();
         // ---- initB (fwd2c.h:138-176): origin, then the two boundary chains (one thread each)
-        if (t == 0) {
+        if (t == 0 && role == 0) {
             vmf[0].m = 0; vmf[0].n = 0; vmf[0].p = 0;                       // skip 0-th record (:361)
             vmf[1].m = P_.al; vmf[1].n = P_.bl; vmf[1].p = 0;                 // origin
             sm_vmf[g] = 2;
@@ -119,7 +126,7 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
                 else k3_boundary_col(p, A, B, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
             }
         }
-        if (t == TG / 2) {
+        if (t == TG / 2 && role == (SPLIT ? 1 : 0)) {
             k3_setval(rowH, 0); k3_setdg(rowH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(rowH) = 1;
             const int rr = LS < p.up ? LS : p.up;
             for (int k = 1; k <= rr; ++k) {
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
                 else k3_boundary_row(p, A, B, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
             }
         }
-        group_sync<TG>(g);
+        GSYNC();
 
         // prefetch of the parked row: word w of the three records (rowH, rowG, rowG2) of one column
         const int pf_words = (n3 ? 3 : 2) * st;
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
             int* const f2 = F2 + (size_t)t * st;
             double pua = 0;
             // ring: records 1 and 2 of the first parked row (the boundary row) before the first step
-            if (ring_ok) {
+            if (ring_ok && role == 0) {
                 for (int w = t; w < pf_words; w += TG) {
                     const int pa = w / st, pw = w - pa * st;
                     const int* src = pa == 0 ? rowH : (pa == 1 ? rowG : rowG2);
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
                     if (LS + 1 >= 2) dst[(size_t)(2 % RING) * st + pw] = __ldcg(src + 2 * st + pw);
                 }
             }
-            group_sync<TG>(g);
+            GSYNC();
             // this thread's share of the ring prefetch: word pf_pw[q] of parked array pf_src[q]
             const int* pf_src[PFN];
             int* pf_dst[PFN];
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
 #pragma unroll
             for (int q = 0; q < PFN; ++q) {
                 const int w = t + q * TG;
-                pf_on[q] = ring_ok && w < pf_words;
+                pf_on[q] = ring_ok && w < pf_words && role == (SPLIT ? 2 : 0);
                 const int pa = w / st, pw = w - pa * st;
                 pf_src[q] = (pa == 0 ? rowH : (pa == 1 ? rowG : rowG2)) + pw;
                 pf_dst[q] = (pa == 0 ? ringH : (pa == 1 ? ringG : ringG2)) + pw;
@@ -184,12 +191,16 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
                         if (pf_on[q]) pf_val[q] = __ldcg(pf_src[q] + (size_t)(n2 + 1) * st);
                 }
                 const int r = n - m;
-                if (n >= 0 && n < LS && m < LQ && r >= p.lw && r <= p.up) {
+                const bool active = n >= 0 && n < LS && m < LQ && r >= p.lw && r <= p.up;
+                bool rec = false;
+                int* hout = pubH + ((size_t)(S % 3) * TG + t) * st;
+                int* gout = pubG + ((size_t)(S & 1) * TG + t) * st;
+                int* g2out = pubG2 + ((size_t)(S & 1) * TG + t) * st;
+                if (active) {
                     const int ia = m + 1, ib = n + 1;
                     if (n == 0 || r == p.lw) {                      // first in-band column of this row
-                        pua = k3_unp(A, ia, B, ib, p.u);            // once per row (:377)
-                        k3_reset(p, f1);
-                        if (n3) k3_reset(p, f2);
+                        if (!SPLIT || role == 1) pua = k3_unp(A, ia, B, ib, p.u);   // once per row (:377)
+                        if (!SPLIT || role == 2) { k3_reset(p, f1); if (n3) k3_reset(p, f2); }
                     }
                     const int g3a = (S + 2) % 3, g3d = (S + 1) % 3, g2a = (S + 1) & 1;
                     const int seq = k * P + n;                      // == S for thread 0
@@ -204,14 +215,31 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
                     const int* g2above = (!above_in || m == 0) ? black : (t == 0 ? parkedG21 : pubG2 + ((size_t)g2a * TG + (t - 1)) * st);
                     const bool left_in = r - 1 >= p.lw;
                     const int* hleft = n == 0 ? colH + (size_t)(m + 1) * st : (left_in ? pubH + ((size_t)g3a * TG + t) * st : black);
-                    int* hout = pubH + ((size_t)(S % 3) * TG + t) * st;
-                    int* gout = pubG + ((size_t)(S & 1) * TG + t) * st;
-                    int* g2out = pubG2 + ((size_t)(S & 1) * TG + t) * st;
-                    const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
-                    const bool rec = p.mode == 3
-                        ? k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, f1, f2, hout, gout, g2out)
-                        : k3_cell(p, A, B, ia, ib, m == 0, n == 0, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
-                                  hout, gout, g2out, black);
+                    if (!SPLIT) {
+                        const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
+                        rec = p.mode == 3
+                            ? k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, f1, f2, hout, gout, g2out)
+                            : k3_cell(p, A, B, ia, ib, m == 0, n == 0, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
+                                      hout, gout, g2out, black);
+                    } else if (p.mode == 3) {
+                        if (role == 0) {
+                            const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
+                            rec = k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, f1, f2, hout, gout, g2out);
+                        }
+                    } else if (role == 0) {
+                        const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
+                        k3_part_diag(p, A, B, ia, ib, dab, hdiag, hout);
+                    } else if (role == 1) {
+                        k3_part_vert(p, A, B, ia, ib, m == 0, &pua, habove, gabove, g2above, gout, g2out, black);
+                    } else {
+                        k3_part_hori(p, A, B, ia, ib, n == 0, hleft, f1, f2);
+                    }
+                }
+                if (SPLIT) {
+                    __syncthreads();                                // the three candidates are in shared memory
+                    if (active && role == 0 && p.mode != 3) rec = k3_combine(p, m == 0, n == 0, hout, gout, g2out, f1, f2);
+                }
+                if (active && role == 0) {
                     if (rec) {
                         const int id = atomicAdd(&sm_vmf[g], 1);    // Vmf::add (fwd2c.h:465-467)
                         if (id < a.vmf_cap) { vmf[id].m = m + P_.al; vmf[id].n = n + P_.bl; vmf[id].p = K3_PTR(hout); }
@@ -234,11 +262,11 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
                 // advance the two positions
                 if (++n == P) { n = 0; ++k; m += TG; }
                 if (++n2 == P) { n2 = 0; ++k2; }
-                group_sync<TG>(g);
+                GSYNC();
             }
         }
         // ---- final record + Vmf::traceback (fwd2c.h:475-481, vmf.cc:103-119)
-        if (t == 0) {
+        if (t == 0 && role == 0) {
             int* out = a.out_pts + 2 * P_.out_off;
             int cnt = 0;
             const int nrec = sm_vmf[g];
@@ -254,14 +282,14 @@ __global__ void __launch_bounds__(CTA, 2) k3_fill_kernel(const K3Args a)
             a.out_cnt[pi] = cnt;
             a.out_score[pi] = sm_last_val[g];
         }
-        group_sync<TG>(g);
+        GSYNC();
     }
 }
 
-template <int TG>
+template <int TG, bool SPLIT>
 cudaError_t launch_tg(const K3Args& a, int grid_blocks, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel<TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     // The gap-profile lists and score rows stream through L1.  Few pairs (latency: Prrn::best_of_n sized
     // batches): one CTA per SM and the rest of the unified array as L1 (measured 28 vs 37 ms for 24
@@ -270,9 +298,9 @@ cudaError_t launch_tg(const K3Args& a, int grid_blocks, cudaStream_t st)
     int carve = grid_blocks > 148 ? 100 : (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
     if (const char* cv = getenv("PG_K3_CARVEOUT")) carve = atoi(cv);
     if (carve > 100) carve = 100;
-    e = cudaFuncSetAttribute(k3_fill_kernel<TG>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return e;
-    k3_fill_kernel<TG><<<grid_blocks, CTA, a.smem_bytes, st>>>(a);
+    k3_fill_kernel<TG, SPLIT><<<grid_blocks, SPLIT ? 3 * CTA : CTA, a.smem_bytes, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -290,8 +318,9 @@ int k3_pick_tg(int64_t npairs, int sm_count)
 {
     if (const char* e = getenv("PG_K3_TG")) {
         const int v = atoi(e);
-        if (v == 32 || v == 64 || v == 128 || v == 256) return v;
+        if (v == 32 || v == 64 || v == 128 || v == 256 || v == 768) return v;
     }
+    if (npairs <= sm_count) return 768;     // latency mode: at most one alignment per SM -> three threads per row
     return npairs > (int64_t)8 * sm_count ? 128 : 256;
 }
 
@@ -299,9 +328,10 @@ int k3_pick_tg(int64_t npairs, int sm_count)
 cudaError_t k3_launch(const K3Args& a, int tg, int grid_blocks, cudaStream_t st)
 {
     switch (tg) {
-    case 32: return launch_tg<32>(a, grid_blocks, st);
-    case 64: return launch_tg<64>(a, grid_blocks, st);
-    case 128: return launch_tg<128>(a, grid_blocks, st);
-    default: return launch_tg<256>(a, grid_blocks, st);
+    case 32: return launch_tg<32, false>(a, grid_blocks, st);
+    case 64: return launch_tg<64, false>(a, grid_blocks, st);
+    case 128: return launch_tg<128, false>(a, grid_blocks, st);
+    case 768: return launch_tg<256, true>(a, grid_blocks, st);     // role-split latency kernel
+    default: return launch_tg<256, false>(a, grid_blocks, st);
     }
 }

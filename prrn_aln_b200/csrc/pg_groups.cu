@@ -124,7 +124,8 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     std::vector<K3Pair> pairs(npairs);
     std::vector<int64_t> cells(npairs), outoff(npairs + 1);
     size_t blob = 0, arena_words = 0, wave_bytes = 0;
-    const int tg = k3_pick_tg(npairs, c->sm_count);         // threads per alignment
+    const int tg_sel = k3_pick_tg(npairs, c->sm_count);     // threads per alignment (768 = 3 roles x 256 rows)
+    const int tg = tg_sel == 768 ? 256 : tg_sel;            // rows per stripe
     const int ngrp = k3_threads() / tg;                     // alignments in flight per CTA
     int64_t max_cells = 0;
     outoff[0] = 0;
@@ -279,7 +280,7 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counter, 0, sizeof(int32_t), c->stream);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev0, c->stream);
     if (e == cudaSuccess && sim_bytes) e = k4_launch(k4, k4_blocks, c->stream);
-    if (e == cudaSuccess) e = k3_launch(ka, tg, grid, c->stream);
+    if (e == cudaSuccess) e = k3_launch(ka, tg_sel, grid, c->stream);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev1, c->stream);
     c->ev_valid = e == cudaSuccess;
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_pts.data(), ka.out_pts, 8 * (size_t)outoff[npairs], cudaMemcpyDeviceToHost, c->stream);
