@@ -52,7 +52,9 @@ __device__ __forceinline__ void group_sync(int g)
 // SPLIT (latency mode, TG = 256 only): three threads per row -- the diagonal, vertical and horizontal
 // candidates of a cell are computed side by side by threads of three warp groups ("roles"), a second
 // barrier, then role 0 applies the selection.  Same records, same results, ~1/3 of the per-step chain.
-template <int TG, bool SPLIT>
+// MODE (record type) is a template parameter: a batch is launched once per mode present, so every
+// `p.mode ==` test inside the per-cell code folds away (p.mode is overwritten with the constant below).
+template <int TG, bool SPLIT, int MODE>
 __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_kernel(const K3Args a)
 {
     constexpr int NG = SPLIT ? 1 : CTA / TG;        // alignments in flight per CTA
@@ -79,7 +81,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
         const K3Pair& P_ = a.pairs[pi];
         const K3Group A = P_.a;
         const K3Group B = P_.b;
-        const K3Prm p = P_.prm;
+        K3Prm p = P_.prm;
+        p.mode = MODE;
         const int LQ = A.L, LS = B.L;
         const int st = k3_stride(p.capa, p.capb);
         const bool n3 = p.Noll == 3;
@@ -219,8 +222,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                         const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
                         rec = p.mode == 3
                             ? k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, f1, f2, hout, gout, g2out)
-                            : k3_cell(p, A, B, ia, ib, m == 0, n == 0, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
-                                      hout, gout, g2out, black);
+                            : k3_cell_mono(p, A, B, ia, ib, m == 0, n == 0, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
+                                           hout, gout, g2out, black);
                     } else if (p.mode == 3) {
                         if (role == 0) {
                             const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
@@ -286,10 +289,10 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
     }
 }
 
-template <int TG, bool SPLIT>
-cudaError_t launch_tg(const K3Args& a, int grid_blocks, cudaStream_t st)
+template <int TG, bool SPLIT, int MODE>
+cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     // The gap-profile lists and score rows stream through L1.  Few pairs (latency: Prrn::best_of_n sized
     // batches): one CTA per SM and the rest of the unified array as L1 (measured 28 vs 37 ms for 24
@@ -298,10 +301,22 @@ cudaError_t launch_tg(const K3Args& a, int grid_blocks, cudaStream_t st)
     int carve = grid_blocks > 148 ? 100 : (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
     if (const char* cv = getenv("PG_K3_CARVEOUT")) carve = atoi(cv);
     if (carve > 100) carve = 100;
-    e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return e;
-    k3_fill_kernel<TG, SPLIT><<<grid_blocks, SPLIT ? 3 * CTA : CTA, a.smem_bytes, st>>>(a);
+    k3_fill_kernel<TG, SPLIT, MODE><<<grid_blocks, SPLIT ? 3 * CTA : CTA, a.smem_bytes, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int TG, bool SPLIT>
+cudaError_t launch_tg(const K3Args& a, int mode, int grid_blocks, cudaStream_t st)
+{
+    switch (mode) {
+    case 0: return launch_tgm<TG, SPLIT, 0>(a, grid_blocks, st);
+    case 1: return launch_tgm<TG, SPLIT, 1>(a, grid_blocks, st);
+    case 2: return launch_tgm<TG, SPLIT, 2>(a, grid_blocks, st);
+    case 3: return launch_tgm<TG, SPLIT, 3>(a, grid_blocks, st);
+    default: return launch_tgm<TG, SPLIT, 4>(a, grid_blocks, st);
+    }
 }
 
 }  // namespace
@@ -313,25 +328,25 @@ size_t k3_wave_words(int stride, int Noll, int tg) { return k3_smem_words(stride
 // Threads per alignment for a batch (PG_K3_TG overrides).  Measured on B200, partitions of a 200 x ~500
 // family: 384 pairs -> 256 threads 60 ms, 128: 72, 64: 81, 32: 155; 1,536 pairs -> 256: 193 ms, 128: 176,
 // 64: 189, 32: 314.  The whole CTA per alignment wins until the batch is several waves deep; a warp per
-// alignment loses (every 32 rows pass through the parked-row buffer in L2).
+// alignment loses (every 32 rows pass through the parked-row buffer in L2), so only 128 / 256 / 3x256 are
+// instantiated (x 5 record modes).
 int k3_pick_tg(int64_t npairs, int sm_count)
 {
     if (const char* e = getenv("PG_K3_TG")) {
         const int v = atoi(e);
-        if (v == 32 || v == 64 || v == 128 || v == 256 || v == 768) return v;
+        if (v == 128 || v == 256 || v == 768) return v;
     }
     if (npairs <= sm_count) return 768;     // latency mode: at most one alignment per SM -> three threads per row
     return npairs > (int64_t)8 * sm_count ? 128 : 256;
 }
 
 // a.smem_bytes: dynamic shared memory per CTA = (CTA / tg) x the largest wavefront of the batch (capped)
-cudaError_t k3_launch(const K3Args& a, int tg, int grid_blocks, cudaStream_t st)
+// One launch processes the pairs of ONE mode (a.pairs / a.npairs / a.counter / a.out_* are that mode's slice).
+cudaError_t k3_launch(const K3Args& a, int tg, int mode, int grid_blocks, cudaStream_t st)
 {
     switch (tg) {
-    case 32: return launch_tg<32, false>(a, grid_blocks, st);
-    case 64: return launch_tg<64, false>(a, grid_blocks, st);
-    case 128: return launch_tg<128, false>(a, grid_blocks, st);
-    case 768: return launch_tg<256, true>(a, grid_blocks, st);     // role-split latency kernel
-    default: return launch_tg<256, false>(a, grid_blocks, st);
+    case 128: return launch_tg<128, false>(a, mode, grid_blocks, st);
+    case 768: return launch_tg<256, true>(a, mode, grid_blocks, st);      // role-split latency kernel
+    default: return launch_tg<256, false>(a, mode, grid_blocks, st);
     }
 }

@@ -70,9 +70,18 @@ extern "C" int pg_create(int device, pg_context** out)
     c->ev_valid = false;
     if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMalloc(&c->d_counter, sizeof(int32_t))) != cudaSuccess) {
+        (e = cudaMalloc(&c->d_counter, 8 * sizeof(int32_t))) != cudaSuccess) {     // [0] work queue; [1..5] K3 per-mode queues
         std::string m = std::string("pg_create: ") + cudaGetErrorString(e);
         delete c;
+        return fail(nullptr, PG_ERR_CUDA, m);
+    }
+    for (int i = 0; i < 5 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        std::string m = std::string("pg_create: ") + cudaGetErrorString(e);
         return fail(nullptr, PG_ERR_CUDA, m);
     }
     *out = c;
@@ -88,7 +97,8 @@ extern "C" void pg_destroy(pg_context* c)
     cudaFree(c->d_out); cudaFree(c->d_pairs); cudaFree(c->d_counter); cudaFree(c->d_dirs); cudaFree(c->d_trace); cudaFree(c->d_seqblob); cudaFree(c->d_planbuf);
     cudaFree(c->d_bnd); cudaFree(c->d_scratch); cudaFree(c->d_ends);
     cudaFree(c->d_gblob); cudaFree(c->d_garena); cudaFree(c->d_gvmf); cudaFree(c->d_gout); cudaFree(c->d_gsim);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_fork);
+    for (int i = 0; i < 5; ++i) { cudaStreamDestroy(c->aux[i]); cudaEventDestroy(c->ev_join[i]); }
     cudaStreamDestroy(c->stream);
     delete c;
 }

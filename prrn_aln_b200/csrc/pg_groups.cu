@@ -197,7 +197,16 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
         outoff[i + 1] = outoff[i] + pairs[i].out_cap;
     }
     const int grid = (int)std::min<int64_t>((npairs + ngrp - 1) / ngrp, (int64_t)c->sm_count * k3_blocks_per_sm());
-    const size_t slots = (size_t)grid * ngrp;               // arenas / path stores
+    // arenas / path stores: the kernels of the record modes present run side by side, each on its own slots
+    int64_t n_mode[5] = {0, 0, 0, 0, 0};
+    int g_mode[5], slot0_mode[5];
+    for (int64_t i = 0; i < npairs; ++i) ++n_mode[pairs[i].prm.mode];
+    size_t slots = 0;
+    for (int m5 = 0; m5 < 5; ++m5) {
+        g_mode[m5] = (int)std::min<int64_t>((n_mode[m5] + ngrp - 1) / ngrp, grid);
+        slot0_mode[m5] = (int)slots;
+        slots += (size_t)g_mode[m5] * ngrp;
+    }
     const int64_t vmf_cap = max_cells + 8;
     if (vmf_cap > 0x7fffffff) { free(offs); return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: DP matrix too large for the path store"); }
 
@@ -236,7 +245,10 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     // heaviest pairs first (persistent CTAs finish together); the kernel indexes results by this order
     std::vector<int32_t> order(npairs);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return cells[x] > cells[y]; });
+    // ... grouped by record mode: one launch per mode present, each with its own queue
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        return pairs[x].prm.mode != pairs[y].prm.mode ? pairs[x].prm.mode < pairs[y].prm.mode : cells[x] > cells[y];
+    });
     std::vector<K3Pair> sorted(npairs);
     for (int64_t i = 0; i < npairs; ++i) {
         fill_side(a[i], prm[i].kdim, soa[i], h.data());
@@ -277,10 +289,33 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     std::vector<int32_t> h_pts(2 * (size_t)outoff[npairs]), h_cnt(npairs);
     std::vector<double> h_scr(npairs);
     e = cudaMemcpyAsync(d, h.data(), h.size(), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counter, 0, sizeof(int32_t), c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counter, 0, 8 * sizeof(int32_t), c->stream);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev0, c->stream);
     if (e == cudaSuccess && sim_bytes) e = k4_launch(k4, k4_blocks, c->stream);
-    if (e == cudaSuccess) e = k3_launch(ka, tg_sel, grid, c->stream);
+    // one kernel per record mode present, side by side on auxiliary streams (fork / join around them)
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_fork, c->stream);
+    int used[5] = {0, 0, 0, 0, 0};
+    for (int64_t k0 = 0; k0 < npairs && e == cudaSuccess;) {
+        const int mode = sorted[k0].prm.mode;
+        int64_t k1 = k0;
+        while (k1 < npairs && sorted[k1].prm.mode == mode) ++k1;
+        K3Args km = ka;
+        km.pairs = ka.pairs + k0;
+        km.npairs = (int32_t)(k1 - k0);
+        km.counter = c->d_counter + 1 + mode;
+        km.out_cnt = ka.out_cnt + k0;
+        km.out_score = ka.out_score + k0;
+        const int gm = g_mode[mode];
+        km.arena = ka.arena + (size_t)slot0_mode[mode] * arena_words;
+        km.vmf = ka.vmf + (size_t)slot0_mode[mode] * (size_t)vmf_cap;
+        e = cudaStreamWaitEvent(c->aux[mode], c->ev_fork, 0);
+        if (e == cudaSuccess) e = k3_launch(km, tg_sel, mode, gm, c->aux[mode]);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev_join[mode], c->aux[mode]);
+        used[mode] = 1;
+        k0 = k1;
+    }
+    for (int m5 = 0; m5 < 5 && e == cudaSuccess; ++m5)
+        if (used[m5]) e = cudaStreamWaitEvent(c->stream, c->ev_join[m5], 0);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev1, c->stream);
     c->ev_valid = e == cudaSuccess;
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_pts.data(), ka.out_pts, 8 * (size_t)outoff[npairs], cudaMemcpyDeviceToHost, c->stream);

@@ -217,6 +217,8 @@ struct pg_context {
     void* d_gout; size_t gout_cap;
     void* d_gsim; size_t gsim_cap;
     int32_t* d_counter;
+    cudaStream_t aux[5];        // K3 launches one kernel per record mode: they run side by side
+    cudaEvent_t ev_fork, ev_join[5];
     cudaEvent_t ev0, ev1;       // device time of the last fill launch (pg_last_kernel_ms)
     bool ev_valid;
 };
@@ -254,7 +256,7 @@ int k2_rows_per_lane();
 int k2_warps_per_block();
 int k2_blocks_per_sm();
 // k3_groups.cu
-cudaError_t k3_launch(const K3Args& a, int tg, int grid_blocks, cudaStream_t st);
+cudaError_t k3_launch(const K3Args& a, int tg, int mode, int grid_blocks, cudaStream_t st);
 int k3_threads();
 int k3_blocks_per_sm();
 int k3_pick_tg(int64_t npairs, int sm_count);
