@@ -26,9 +26,11 @@ constexpr int BLOCKS_PER_SM = 3;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int QMAX = RMAX / 4;
 
+constexpr int POKE_WORDS = RMAX + 8;     // band-cut scratch words per lane (poke_stride(RMAX) at most)
+
 __host__ __device__ inline size_t smem_bytes(int dim)
 {
-    return (size_t)(dim + NW) * QMAX * 32 * sizeof(uint4) + 16;
+    return (size_t)dim * QMAX * 32 * sizeof(uint4) + (size_t)NW * 32 * POKE_WORDS * 4 + 16;
 }
 
 __device__ __forceinline__ void store_result(const K1PArgs& a, int score, int qi, int si, int LQ, int LS)
@@ -56,14 +58,47 @@ __device__ __forceinline__ void store_result(const K1PArgs& a, int score, int qi
     }
 }
 
+// shared-memory accesses by 32-bit address (keeps the per-lane base in one register, no generic-pointer math)
+__device__ __forceinline__ uint4 lds128(unsigned addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts16(unsigned addr, unsigned short v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+// base + i for a byte pointer as one wide multiply-add (FMA pipe) instead of an add-with-carry pair (ALU pipe)
+__device__ __forceinline__ const uint8_t* byte_at(const uint8_t* base, int i)
+{
+    unsigned long long r;
+    asm("mad.wide.s32 %0, %1, 1, %2;" : "=l"(r) : "r"(i), "l"((unsigned long long)base));
+    return reinterpret_cast<const uint8_t*>(r);
+}
+
+// words of band-cut scratch per lane: RP rows + padding that makes the lane stride an odd number of 16-byte
+// chunks (conflict-free 128-bit accesses with rows contiguous per lane, so a row's address is linear in n)
+__host__ __device__ constexpr int poke_stride(int rp) { return ((rp / 4 + 1) % 2 ? rp + 4 : rp + 8); }
+
 // One work item with R rows per lane (R in {8,10,12,14,16}: the host picks the smallest variant whose
 // 32*R rows hold the longer query, so that 400-residue queries fill 29 of 32 lanes instead of 25).
 // The profile keeps the [letter][quad][lane][4] layout with Q = ceil(R/4) quads per lane.
-template <int R>
-__device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& item, uint4* sm_prof, uint4* sm_poke)
+// MP = the longer query needs more than one pass (bottom row parked in a.rowbuf between passes).
+//
+// The ALU pipe (DPX instructions included) issues at half the rate of the scheduler, so everything that is
+// not DPX is kept off it: addresses are IMADs on a per-lane shared-memory base, the top boundary is a
+// register that changes at two columns per alignment, one unsigned compare tests "lane inside the matrix".
+template <int R, bool MP>
+__device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& item, uint4* sm_prof, unsigned* sm_poke)
 {
     constexpr int Q = (R + 3) / 4;
     constexpr int RP = 4 * Q;
+    constexpr int PS = poke_stride(RP);
     constexpr int ROWS_PER_PASS = 32 * R;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -76,7 +111,11 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
     const uint8_t* q1 = a.seqs.res + a.seqs.offs[qi1] + a.seqs.left[qi1];
     const int LQ0 = a.seqs.wlen[qi0], LQ1 = a.seqs.wlen[qi1];
     const int LQ = max(LQ0, LQ1);
-    const int npass = LQ > 0 ? (LQ + ROWS_PER_PASS - 1) / ROWS_PER_PASS : 1;
+    const int npass = MP ? (LQ + ROWS_PER_PASS - 1) / ROWS_PER_PASS : 1;
+    unsigned prof_sh = (unsigned)__cvta_generic_to_shared(sm_prof + lane);
+    unsigned pk_sh = (unsigned)__cvta_generic_to_shared(sm_poke + (warp * 32 + lane) * PS);
+    asm volatile("" : "+r"(prof_sh), "+r"(pk_sh));      // opaque: keep both bases in registers, never recomputed per step
+    const bool lane0 = lane == 0;
 
     for (int pass = 0; pass < npass; ++pass) {
         const int pbase = pass * ROWS_PER_PASS;
@@ -104,6 +143,7 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
         const bool fin0 = LQ0 > pbase && LQ0 <= pbase + ROWS_PER_PASS;
         const bool fin1 = LQ1 > pbase && LQ1 <= pbase + ROWS_PER_PASS;
         const int r0 = LQ0 - 1 - pbase, r1 = LQ1 - 1 - pbase;
+        const bool top_lane = lane0 && pass == 0;
 
         for (int sub = item.sub_begin + warp, ord = 0; sub < item.sub_end; sub += NW, ++ord) {
             const unsigned ent = a.subs[sub];
@@ -127,68 +167,78 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
                 }
                 continue;
             }
-            uint2* rowbuf = a.rowbuf ? a.rowbuf + ((int64_t)gwarp * a.rowbuf_stride + (int64_t)ord * LS) : nullptr;
+            uint2* rowbuf = MP && a.rowbuf ? a.rowbuf + ((int64_t)gwarp * a.rowbuf_stride + (int64_t)ord * LS) : nullptr;
 
             K1PLane<R> L;
             k1p_lane_init(L, g0, g1, mbase, negv2);
+            // band cut: row k of this lane loses its horizontal input at column n when k == n - lwm (diagonal
+            // lw) or k == n - upm (diagonal up + 1), per packed half
             const int lwm0 = g0.lw + mbase, upm0 = g0.up + 1 + mbase;
             const int lwm1 = g1.lw + mbase, upm1 = g1.up + 1 + mbase;
-            // top boundary of pass 0 as seen by lane 0 (n == step): base + (n+1)*slope while inside
-            // the band, then -inf; warp-uniform, so it costs two selects per step instead of a branch
+            // top boundary of pass 0 as seen by lane 0 (n == step): the drifted value is the constant
+            // topOpen while n + 1 <= up, then -inf; it changes at columns up0 and up1 only
             const int tslope = g0.topExt + g0.u;
+            unsigned topv = neg2, topf = neg2;
+            int tev = -1;                               // next column at which topv changes (lane 0, pass 0)
+            if (top_lane) {
+                topv = k1p_pack(1 <= g0.up ? g0.topOpen + tslope : K1P_NEG, 1 <= g1.up ? g1.topOpen + tslope : K1P_NEG);
+                topf = K1P_ADDMAX(topv, negv2, neg2);
+                tev = tslope != 0 ? 1 : min(g0.up >= 1 ? g0.up : 0x7fffffff, g1.up >= 1 ? g1.up : 0x7fffffff);
+            }
             unsigned recv_h = neg2, recv_f = neg2;
-            const uint4* pp = sm_prof + lane;
-            uint4* pk = sm_poke + warp * (QMAX * 32) + lane;
             const int nsteps = LS + lanes - 1;
-            const bool lane0 = lane == 0;
+            const unsigned LSa = lane < lanes ? (unsigned)LS : 0u;      // lane works at column n iff (unsigned)n < LSa
+            const uint8_t* sl = s - lane;                               // letter of this lane at `step` = sl[step]
 
             for (int step = 0; step < nsteps; ++step) {
                 const int n = step - lane;
                 unsigned h_dn = neg2, f_dn = neg2;
-                if (n >= 0 && n < LS && lane < lanes) {
+                if ((unsigned)n < LSa) {
                     unsigned h_up = recv_h, f_up = recv_f;
-                    if (pass == 0) {
-                        const int kk = step + 1;
-                        const int t0 = kk <= g0.up ? g0.topOpen + kk * tslope : K1P_NEG;
-                        const int t1 = kk <= g1.up ? g1.topOpen + kk * tslope : K1P_NEG;
-                        const unsigned topv = k1p_pack(t0, t1);
-                        const unsigned topf = K1P_ADDMAX(topv, negv2, neg2);
-                        h_up = lane0 ? topv : h_up;
-                        f_up = lane0 ? topf : f_up;
-                    } else if (lane0) {
-                        uint2 v = __ldcg(rowbuf + n); h_up = v.x; f_up = v.y;
+                    if (n == tev) {                                     // rare: lane 0, a few times per alignment
+                        const int kk = n + 1;
+                        topv = k1p_pack(kk <= g0.up ? g0.topOpen + kk * tslope : K1P_NEG,
+                                        kk <= g1.up ? g1.topOpen + kk * tslope : K1P_NEG);
+                        topf = K1P_ADDMAX(topv, negv2, neg2);
+                        tev = tslope != 0 ? n + 1
+                                          : min(g0.up > n ? g0.up : 0x7fffffff, g1.up > n ? g1.up : 0x7fffffff);
                     }
-                    const int kL0 = n - lwm0, kU0 = n - upm0, kL1 = n - lwm1, kU1 = n - upm1;
-                    if ((unsigned)kL0 < (unsigned)R || (unsigned)kU0 < (unsigned)R ||
-                        (unsigned)kL1 < (unsigned)R || (unsigned)kU1 < (unsigned)R) {
+                    if (top_lane) { h_up = topv; f_up = topf; }
+                    if (MP) {
+                        if (pass > 0 && lane0) { uint2 v = __ldcg(rowbuf + n); h_up = v.x; f_up = v.y; }
+                    }
+                    const unsigned kL0 = (unsigned)(n - lwm0), kU0 = (unsigned)(n - upm0);
+                    const unsigned kL1 = (unsigned)(n - lwm1), kU1 = (unsigned)(n - upm1);
+                    if (min(min(kL0, kU0), min(kL1, kU1)) < (unsigned)R) {
 #pragma unroll
                         for (int j = 0; j < Q; ++j)
-                            pk[j * 32] = make_uint4(L.E[4 * j], 4 * j + 1 < R ? L.E[4 * j + 1] : 0u,
-                                                    4 * j + 2 < R ? L.E[4 * j + 2] : 0u, 4 * j + 3 < R ? L.E[4 * j + 3] : 0u);
-                        short* pks = reinterpret_cast<short*>(pk);
-                        if ((unsigned)kL0 < (unsigned)R) pks[(kL0 >> 2) * 256 + (kL0 & 3) * 2] = (short)K1P_NEG;
-                        if ((unsigned)kU0 < (unsigned)R) pks[(kU0 >> 2) * 256 + (kU0 & 3) * 2] = (short)K1P_NEG;
-                        if ((unsigned)kL1 < (unsigned)R) pks[(kL1 >> 2) * 256 + (kL1 & 3) * 2 + 1] = (short)K1P_NEG;
-                        if ((unsigned)kU1 < (unsigned)R) pks[(kU1 >> 2) * 256 + (kU1 & 3) * 2 + 1] = (short)K1P_NEG;
+                            sts128(pk_sh + 16 * j, make_uint4(L.E[4 * j], 4 * j + 1 < R ? L.E[4 * j + 1] : 0u,
+                                                              4 * j + 2 < R ? L.E[4 * j + 2] : 0u, 4 * j + 3 < R ? L.E[4 * j + 3] : 0u));
+                        if (kL0 < (unsigned)R) sts16(pk_sh + 4 * kL0, (unsigned short)K1P_NEG);
+                        if (kU0 < (unsigned)R) sts16(pk_sh + 4 * kU0, (unsigned short)K1P_NEG);
+                        if (kL1 < (unsigned)R) sts16(pk_sh + 4 * kL1 + 2, (unsigned short)K1P_NEG);
+                        if (kU1 < (unsigned)R) sts16(pk_sh + 4 * kU1 + 2, (unsigned short)K1P_NEG);
 #pragma unroll
                         for (int j = 0; j < Q; ++j) {
-                            uint4 v = pk[j * 32];
+                            uint4 v = lds128(pk_sh + 16 * j);
                             L.E[4 * j] = v.x;
                             if (4 * j + 1 < R) L.E[4 * j + 1] = v.y;
                             if (4 * j + 2 < R) L.E[4 * j + 2] = v.z;
                             if (4 * j + 3 < R) L.E[4 * j + 3] = v.w;
                         }
                     }
-                    const int letter = __ldg(s + n);
-                    const uint4* pl = pp + letter * (Q * 32);
+                    const unsigned letter = __ldg(byte_at(sl, step));
+                    const unsigned pa = prof_sh + letter * (unsigned)(Q * 32 * sizeof(uint4));
                     unsigned sc[RP];
 #pragma unroll
                     for (int j = 0; j < Q; ++j) {
-                        uint4 v = pl[j * 32];
+                        uint4 v = lds128(pa + j * (unsigned)(32 * sizeof(uint4)));
                         sc[4 * j] = v.x; sc[4 * j + 1] = v.y; sc[4 * j + 2] = v.z; sc[4 * j + 3] = v.w;
                     }
                     k1p_lane_step(L, sc, negv2, h_up, f_up, &h_dn, &f_dn);
-                    if (lane == 31 && !last_pass) __stcg(rowbuf + n, make_uint2(h_dn, f_dn));
+                    if (MP) {
+                        if (lane == 31 && !last_pass) __stcg(rowbuf + n, make_uint2(h_dn, f_dn));
+                    }
                 }
                 recv_h = __shfl_up_sync(FULL, h_dn, 1);
                 recv_f = __shfl_up_sync(FULL, f_dn, 1);
@@ -214,12 +264,20 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
     }
 }
 
+template <int R>
+__device__ __forceinline__ void process_item_r(const K1PArgs& a, const PgItem2& item, uint4* sm_prof, unsigned* sm_poke)
+{
+    const int LQ = max(a.seqs.wlen[item.q0], a.seqs.wlen[item.q1]);
+    if (LQ <= 32 * R) process_item<R, false>(a, item, sm_prof, sm_poke);
+    else process_item<R, true>(a, item, sm_prof, sm_poke);
+}
+
 __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k1p_score_kernel(const K1PArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* const sm_prof = reinterpret_cast<uint4*>(smem_raw);
-    uint4* const sm_poke = sm_prof + a.dim * QMAX * 32;
-    int* const sm_item = reinterpret_cast<int*>(sm_poke + NW * QMAX * 32);
+    unsigned* const sm_poke = reinterpret_cast<unsigned*>(sm_prof + a.dim * QMAX * 32);
+    int* const sm_item = reinterpret_cast<int*>(sm_poke + NW * 32 * POKE_WORDS);
     for (;;) {
         if (threadIdx.x == 0) *sm_item = atomicAdd(a.counter, 1);
         __syncthreads();
@@ -227,11 +285,11 @@ __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k1p_score_kernel(const
         if (it >= a.nitems) break;
         const PgItem2 item = a.items[it];
         switch (item.rows) {
-        case 8:  process_item<8>(a, item, sm_prof, sm_poke); break;
-        case 10: process_item<10>(a, item, sm_prof, sm_poke); break;
-        case 12: process_item<12>(a, item, sm_prof, sm_poke); break;
-        case 14: process_item<14>(a, item, sm_prof, sm_poke); break;
-        default: process_item<16>(a, item, sm_prof, sm_poke); break;
+        case 8:  process_item_r<8>(a, item, sm_prof, sm_poke); break;
+        case 10: process_item_r<10>(a, item, sm_prof, sm_poke); break;
+        case 12: process_item_r<12>(a, item, sm_prof, sm_poke); break;
+        case 14: process_item_r<14>(a, item, sm_prof, sm_poke); break;
+        default: process_item_r<16>(a, item, sm_prof, sm_poke); break;
         }
     }
 }
