@@ -8,7 +8,7 @@
 //   CTA  = one work item = a PAIR of queries (q0, q1) x a run of subjects; the packed profile
 //          P[letter][row] = (S'(q0_row, letter), S'(q1_row, letter)) lives in shared memory in the
 //          conflict-free [letter][R/4][lane][4] layout (one LDS.128 = 4 rows x 2 alignments).
-//   warp = one subject at a time; lane t owns rows [16t, 16t+16) of both queries.
+//   half-warp (16 lanes) = one subject at a time; lane t of it owns rows [R t, R t + R) of both queries.
 // The host (pg_api.cu) chooses query pairs of similar length and gives every unordered pair {x, y}
 // to exactly one (query, subject) slot (round-robin tournament), with two "valid" bits per subject.
 #include <cuda_runtime.h>
@@ -19,10 +19,12 @@
 
 namespace {
 
-constexpr int RMAX = 16;        // largest rows-per-lane variant
+constexpr int RMAX = 28;        // largest rows-per-lane variant
 constexpr int NW = 8;
+constexpr int HL = 16;          // lanes of one systolic array (half a warp)
+constexpr int NHW = NW * 32 / HL;
 constexpr int MAXDIM = 32;
-constexpr int BLOCKS_PER_SM = 3;
+constexpr int BLOCKS_PER_SM = 2;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int QMAX = RMAX / 4;
 
@@ -30,7 +32,7 @@ constexpr int POKE_WORDS = RMAX + 8;     // band-cut scratch words per lane (pok
 
 __host__ __device__ inline size_t smem_bytes(int dim)
 {
-    return (size_t)dim * QMAX * 32 * sizeof(uint4) + (size_t)NW * 32 * POKE_WORDS * 4 + 16;
+    return (size_t)dim * QMAX * HL * sizeof(uint4) + (size_t)NW * 32 * POKE_WORDS * 4 + 16;
 }
 
 __device__ __forceinline__ void store_result(const K1PArgs& a, int score, int qi, int si, int LQ, int LS)
@@ -73,21 +75,16 @@ __device__ __forceinline__ void sts16(unsigned addr, unsigned short v)
 {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
-// base + i for a byte pointer as one wide multiply-add (FMA pipe) instead of an add-with-carry pair (ALU pipe)
-__device__ __forceinline__ const uint8_t* byte_at(const uint8_t* base, int i)
-{
-    unsigned long long r;
-    asm("mad.wide.s32 %0, %1, 1, %2;" : "=l"(r) : "r"(i), "l"((unsigned long long)base));
-    return reinterpret_cast<const uint8_t*>(r);
-}
-
 // words of band-cut scratch per lane: RP rows + padding that makes the lane stride an odd number of 16-byte
 // chunks (conflict-free 128-bit accesses with rows contiguous per lane, so a row's address is linear in n)
 __host__ __device__ constexpr int poke_stride(int rp) { return ((rp / 4 + 1) % 2 ? rp + 4 : rp + 8); }
 
-// One work item with R rows per lane (R in {8,10,12,14,16}: the host picks the smallest variant whose
-// 32*R rows hold the longer query, so that 400-residue queries fill 29 of 32 lanes instead of 25).
-// The profile keeps the [letter][quad][lane][4] layout with Q = ceil(R/4) quads per lane.
+// One work item with R rows per lane.  A HALF-WARP (16 lanes) is one systolic array: the two halves of a warp
+// run two different subjects of the item against the same pair of queries (same profile), so every per-step
+// instruction that is not a DPX instruction -- profile fetch, band cut, shuffles, loop control -- is paid once
+// per 2 x R x 2 cells.  R in {16..28}: the host picks the smallest variant whose 16*R rows hold the longer query.
+// The profile layout is [letter][quad][half-lane][4] with Q = ceil(R/4) quads per lane (a quarter-warp reads
+// 128 contiguous bytes: conflict-free LDS.128).
 // MP = the longer query needs more than one pass (bottom row parked in a.rowbuf between passes).
 //
 // The ALU pipe (DPX instructions included) issues at half the rate of the scheduler, so everything that is
@@ -99,11 +96,12 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
     constexpr int Q = (R + 3) / 4;
     constexpr int RP = 4 * Q;
     constexpr int PS = poke_stride(RP);
-    constexpr int ROWS_PER_PASS = 32 * R;
+    constexpr int ROWS_PER_PASS = HL * R;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int gwarp = blockIdx.x * NW + warp;
+    const int hl = lane & (HL - 1);                     // lane inside the half-warp
+    const int hw = tid / HL;                            // half-warp of the CTA
+    const int ghw = blockIdx.x * NHW + hw;
     const unsigned negv2 = k1p_pack(-a.v, -a.v);
     const unsigned neg2 = k1p_pack(K1P_NEG, K1P_NEG);
     const int qi0 = item.q0, qi1 = item.q1;
@@ -112,20 +110,20 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
     const int LQ0 = a.seqs.wlen[qi0], LQ1 = a.seqs.wlen[qi1];
     const int LQ = max(LQ0, LQ1);
     const int npass = MP ? (LQ + ROWS_PER_PASS - 1) / ROWS_PER_PASS : 1;
-    unsigned prof_sh = (unsigned)__cvta_generic_to_shared(sm_prof + lane);
-    unsigned pk_sh = (unsigned)__cvta_generic_to_shared(sm_poke + (warp * 32 + lane) * PS);
+    unsigned prof_sh = (unsigned)__cvta_generic_to_shared(sm_prof + hl);
+    unsigned pk_sh = (unsigned)__cvta_generic_to_shared(sm_poke + tid * PS);
     asm volatile("" : "+r"(prof_sh), "+r"(pk_sh));      // opaque: keep both bases in registers, never recomputed per step
-    const bool lane0 = lane == 0;
+    const bool lane0 = hl == 0;
 
     for (int pass = 0; pass < npass; ++pass) {
         const int pbase = pass * ROWS_PER_PASS;
         {
             unsigned* p = reinterpret_cast<unsigned*>(sm_prof);
-            const int total = a.dim * 32 * RP;
+            const int total = a.dim * HL * RP;
             for (int idx = tid; idx < total; idx += NW * 32) {
-                int letter = idx / (32 * RP);
-                int rem = idx - letter * (32 * RP);
-                int j = rem >> 7, ln = (rem >> 2) & 31, c = rem & 3;
+                int letter = idx / (HL * RP);
+                int rem = idx - letter * (HL * RP);
+                int j = rem / (HL * 4), ln = (rem >> 2) & (HL - 1), c = rem & 3;
                 int kk = j * 4 + c;
                 int row = pbase + ln * R + kk;
                 bool ok = kk < R;
@@ -138,19 +136,22 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
 
         const int rows_here = min(LQ - pbase, ROWS_PER_PASS);
         const int lanes = (rows_here + R - 1) / R;
-        const int mbase = pbase + lane * R;
+        const int mbase = pbase + hl * R;
         const bool last_pass = pass == npass - 1;
         const bool fin0 = LQ0 > pbase && LQ0 <= pbase + ROWS_PER_PASS;
         const bool fin1 = LQ1 > pbase && LQ1 <= pbase + ROWS_PER_PASS;
         const int r0 = LQ0 - 1 - pbase, r1 = LQ1 - 1 - pbase;
         const bool top_lane = lane0 && pass == 0;
 
-        for (int sub = item.sub_begin + warp, ord = 0; sub < item.sub_end; sub += NW, ++ord) {
-            const unsigned ent = a.subs[sub];
+        // both halves of a warp walk the subject list together; a half without a subject idles
+        for (int sub0 = item.sub_begin + (hw & ~1), ord = 0; sub0 < item.sub_end; sub0 += NHW, ++ord) {
+            const int sub = sub0 + (hw & 1);
+            const bool have = sub < item.sub_end;
+            const unsigned ent = have ? a.subs[sub] : 0u;
             const int si = (int)(ent & 0x3fffffffu);
             const bool v0 = (ent >> 30) & 1u, v1 = (ent >> 31) & 1u;
-            const uint8_t* s = a.seqs.res + a.seqs.offs[si] + a.seqs.left[si];
-            const int LS = a.seqs.wlen[si];
+            const unsigned soff = (unsigned)(a.seqs.offs[si] + a.seqs.left[si]);    // < 2^31: checked by the host
+            const int LS = have ? a.seqs.wlen[si] : 0;
             K1Geom g0, g1;
             g0.LQ = LQ0; g0.LS = LS; g0.u = a.u; g0.v = a.v;
             g1.LQ = LQ1; g1.LS = LS; g1.u = a.u; g1.v = a.v;
@@ -158,16 +159,9 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
             k1_band(LQ1, LS, a.sh, &g1.lw, &g1.up);
             g0.topOpen = g1.topOpen = g0.leftOpen = g1.leftOpen = -a.v;
             g0.topExt = g1.topExt = g0.leftExt = g1.leftExt = -a.u;
-            if (LS == 0 || LQ0 == 0 || LQ1 == 0) {
-                // empty sequences never reach this kernel (the host routes such batches to the
-                // int32 kernel); kept for safety: the score is a boundary value
-                if (lane == 0 && pass == 0) {
-                    if (v0) store_result(a, (LQ0 == 0 ? k1_top(g0, LS - 1) : k1_left(g0, LQ0 - 1)) - (LQ0 + LS) * a.u, qi0, si, LQ0, LS);
-                    if (v1) store_result(a, (LQ1 == 0 ? k1_top(g1, LS - 1) : k1_left(g1, LQ1 - 1)) - (LQ1 + LS) * a.u, qi1, si, LQ1, LS);
-                }
-                continue;
-            }
-            uint2* rowbuf = MP && a.rowbuf ? a.rowbuf + ((int64_t)gwarp * a.rowbuf_stride + (int64_t)ord * LS) : nullptr;
+            // empty sequences never reach this kernel (the host routes such batches to the int32 kernel)
+            const bool live = have && LS > 0 && LQ0 > 0 && LQ1 > 0;
+            uint2* rowbuf = MP && a.rowbuf ? a.rowbuf + ((int64_t)ghw * a.rowbuf_stride + (int64_t)ord * LS) : nullptr;
 
             K1PLane<R> L;
             k1p_lane_init(L, g0, g1, mbase, negv2);
@@ -186,12 +180,13 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
                 tev = tslope != 0 ? 1 : min(g0.up >= 1 ? g0.up : 0x7fffffff, g1.up >= 1 ? g1.up : 0x7fffffff);
             }
             unsigned recv_h = neg2, recv_f = neg2;
-            const int nsteps = LS + lanes - 1;
-            const unsigned LSa = lane < lanes ? (unsigned)LS : 0u;      // lane works at column n iff (unsigned)n < LSa
-            const uint8_t* sl = s - lane;                               // letter of this lane at `step` = sl[step]
+            int nsteps = live ? LS + lanes - 1 : 0;
+            nsteps = max(nsteps, __shfl_xor_sync(FULL, nsteps, HL));
+            const unsigned LSa = live && hl < lanes ? (unsigned)LS : 0u;    // lane works at column n iff (unsigned)n < LSa
+            const unsigned sl = soff - (unsigned)hl;                        // letter of this lane at `step` = res[sl + step]
 
             for (int step = 0; step < nsteps; ++step) {
-                const int n = step - lane;
+                const int n = step - hl;
                 unsigned h_dn = neg2, f_dn = neg2;
                 if ((unsigned)n < LSa) {
                     unsigned h_up = recv_h, f_up = recv_f;
@@ -227,21 +222,21 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
                             if (4 * j + 3 < R) L.E[4 * j + 3] = v.w;
                         }
                     }
-                    const unsigned letter = __ldg(byte_at(sl, step));
-                    const unsigned pa = prof_sh + letter * (unsigned)(Q * 32 * sizeof(uint4));
+                    const unsigned letter = __ldg(a.seqs.res + (sl + (unsigned)step));
+                    const unsigned pa = prof_sh + letter * (unsigned)(Q * HL * sizeof(uint4));
                     unsigned sc[RP];
 #pragma unroll
                     for (int j = 0; j < Q; ++j) {
-                        uint4 v = lds128(pa + j * (unsigned)(32 * sizeof(uint4)));
+                        uint4 v = lds128(pa + j * (unsigned)(HL * sizeof(uint4)));
                         sc[4 * j] = v.x; sc[4 * j + 1] = v.y; sc[4 * j + 2] = v.z; sc[4 * j + 3] = v.w;
                     }
                     k1p_lane_step(L, sc, negv2, h_up, f_up, &h_dn, &f_dn);
                     if (MP) {
-                        if (lane == 31 && !last_pass) __stcg(rowbuf + n, make_uint2(h_dn, f_dn));
+                        if (hl == HL - 1 && !last_pass) __stcg(rowbuf + n, make_uint2(h_dn, f_dn));
                     }
                 }
-                recv_h = __shfl_up_sync(FULL, h_dn, 1);
-                recv_f = __shfl_up_sync(FULL, f_dn, 1);
+                recv_h = __shfl_up_sync(FULL, h_dn, 1, HL);
+                recv_f = __shfl_up_sync(FULL, f_dn, 1, HL);
             }
 
             if (fin0 || fin1) {
@@ -252,9 +247,9 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
                     if (k == k0f) val0 = L.H[k];
                     if (k == k1f) val1 = L.H[k];
                 }
-                val0 = __shfl_sync(FULL, val0, (r0 >= 0 ? r0 / R : 0) & 31);
-                val1 = __shfl_sync(FULL, val1, (r1 >= 0 ? r1 / R : 0) & 31);
-                if (lane == 0) {
+                val0 = __shfl_sync(FULL, val0, (r0 >= 0 ? r0 / R : 0) & (HL - 1), HL);
+                val1 = __shfl_sync(FULL, val1, (r1 >= 0 ? r1 / R : 0) & (HL - 1), HL);
+                if (lane0 && live) {
                     if (fin0 && v0) store_result(a, k1p_lo(val0) - (LQ0 + LS) * a.u, qi0, si, LQ0, LS);
                     if (fin1 && v1) store_result(a, k1p_hi(val1) - (LQ1 + LS) * a.u, qi1, si, LQ1, LS);
                 }
@@ -268,7 +263,7 @@ template <int R>
 __device__ __forceinline__ void process_item_r(const K1PArgs& a, const PgItem2& item, uint4* sm_prof, unsigned* sm_poke)
 {
     const int LQ = max(a.seqs.wlen[item.q0], a.seqs.wlen[item.q1]);
-    if (LQ <= 32 * R) process_item<R, false>(a, item, sm_prof, sm_poke);
+    if (LQ <= HL * R) process_item<R, false>(a, item, sm_prof, sm_poke);
     else process_item<R, true>(a, item, sm_prof, sm_poke);
 }
 
@@ -276,7 +271,7 @@ __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k1p_score_kernel(const
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* const sm_prof = reinterpret_cast<uint4*>(smem_raw);
-    unsigned* const sm_poke = reinterpret_cast<unsigned*>(sm_prof + a.dim * QMAX * 32);
+    unsigned* const sm_poke = reinterpret_cast<unsigned*>(sm_prof + a.dim * QMAX * HL);
     int* const sm_item = reinterpret_cast<int*>(sm_poke + NW * 32 * POKE_WORDS);
     for (;;) {
         if (threadIdx.x == 0) *sm_item = atomicAdd(a.counter, 1);
@@ -285,26 +280,26 @@ __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k1p_score_kernel(const
         if (it >= a.nitems) break;
         const PgItem2 item = a.items[it];
         switch (item.rows) {
-        case 8:  process_item_r<8>(a, item, sm_prof, sm_poke); break;
-        case 10: process_item_r<10>(a, item, sm_prof, sm_poke); break;
-        case 12: process_item_r<12>(a, item, sm_prof, sm_poke); break;
-        case 14: process_item_r<14>(a, item, sm_prof, sm_poke); break;
-        default: process_item_r<16>(a, item, sm_prof, sm_poke); break;
+        case 16: process_item_r<16>(a, item, sm_prof, sm_poke); break;
+        case 20: process_item_r<20>(a, item, sm_prof, sm_poke); break;
+        case 24: process_item_r<24>(a, item, sm_prof, sm_poke); break;
+        case 26: process_item_r<26>(a, item, sm_prof, sm_poke); break;
+        default: process_item_r<28>(a, item, sm_prof, sm_poke); break;
         }
     }
 }
 
 }  // namespace
 
-int k1p_rows_per_pass() { return 32 * RMAX; }
+int k1p_rows_per_pass() { return HL * RMAX; }
 int k1p_pick_rows(int lq)
 {
-    const int opts[5] = {8, 10, 12, 14, 16};
+    const int opts[5] = {16, 20, 24, 26, 28};
     for (int i = 0; i < 5; ++i)
-        if (lq <= 32 * opts[i]) return opts[i];
-    return 16;
+        if (lq <= HL * opts[i]) return opts[i];
+    return RMAX;
 }
-int k1p_warps_per_block() { return NW; }
+int k1p_warps_per_block() { return NHW; }      // systolic arrays (half-warps) per CTA: the host's unit of subjects
 int k1p_blocks_per_sm() { return BLOCKS_PER_SM; }
 
 cudaError_t k1p_launch(const K1PArgs& a, int grid_blocks, cudaStream_t st)

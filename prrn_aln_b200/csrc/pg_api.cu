@@ -331,6 +331,7 @@ static int seqs_upload_impl(pg_context* c, const pg_seqs* s, pg_dev_seqs** out, 
     d->h_wlen = wlen;
     d->max_wlen = maxw;
     d->min_wlen = n ? *std::min_element(wlen.begin(), wlen.end()) : 0;
+    d->res_bytes = (int64_t)total;
     d->any_exg = false;
     for (int i = 0; i < n; ++i) d->any_exg = d->any_exg || (flags[i] & 3);
     d->plan_k0 = d->plan_k1 = -1;
@@ -586,6 +587,7 @@ extern "C" int pg_calcdist_dev(pg_context* c, pg_dev_seqs* d, const pg_params* p
                 }
         const char* force = getenv("PG_FORCE_INT32");
         const bool packed = !(force && force[0] == '1') && d->min_wlen >= 1 && n >= 2 &&
+                            d->res_bytes < ((int64_t)1 << 31) &&       // K1P addresses residues by 32-bit offsets
                             k1p_fits(smax, smin, sc.v, d->max_wlen);
         if (packed) {
             if (d->plan_k0 != k_begin || d->plan_k1 != k_end || !d->d_plan) {

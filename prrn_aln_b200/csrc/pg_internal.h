@@ -181,6 +181,7 @@ struct pg_dev_seqs {
     int32_t max_code;           // largest residue code inside the windows
     uint8_t present[256];       // which residue codes occur inside the windows
     int32_t min_wlen;
+    int64_t res_bytes;              // bytes of concatenated residues
     bool any_exg;               // some sequence carries inex.exgl / exgr
     // cached packed plan of the last calcdist range (schedule only, no results)
     int64_t plan_k0, plan_k1;
