@@ -142,6 +142,7 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
         const bool fin1 = LQ1 > pbase && LQ1 <= pbase + ROWS_PER_PASS;
         const int r0 = LQ0 - 1 - pbase, r1 = LQ1 - 1 - pbase;
         const bool top_lane = lane0 && pass == 0;
+        const unsigned tmask = top_lane ? 0xffffffffu : 0u;
 
         // both halves of a warp walk the subject list together; a half without a subject idles
         for (int sub0 = item.sub_begin + (hw & ~1), ord = 0; sub0 < item.sub_end; sub0 += NHW, ++ord) {
@@ -184,6 +185,7 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
             nsteps = max(nsteps, __shfl_xor_sync(FULL, nsteps, HL));
             const unsigned LSa = live && hl < lanes ? (unsigned)LS : 0u;    // lane works at column n iff (unsigned)n < LSa
             const unsigned sl = soff - (unsigned)hl;                        // letter of this lane at `step` = res[sl + step]
+            unsigned nxt = __ldg(a.seqs.res + soff);                        // every lane starts at column 0
 
             for (int step = 0; step < nsteps; ++step) {
                 const int n = step - hl;
@@ -198,7 +200,8 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
                         tev = tslope != 0 ? n + 1
                                           : min(g0.up > n ? g0.up : 0x7fffffff, g1.up > n ? g1.up : 0x7fffffff);
                     }
-                    if (top_lane) { h_up = topv; f_up = topf; }
+                    h_up = (h_up & ~tmask) | (topv & tmask);           // lane 0 of pass 0 takes the top boundary
+                    f_up = (f_up & ~tmask) | (topf & tmask);
                     if (MP) {
                         if (pass > 0 && lane0) { uint2 v = __ldcg(rowbuf + n); h_up = v.x; f_up = v.y; }
                     }
@@ -222,7 +225,10 @@ __device__ __forceinline__ void process_item(const K1PArgs& a, const PgItem2& it
                             if (4 * j + 3 < R) L.E[4 * j + 3] = v.w;
                         }
                     }
-                    const unsigned letter = __ldg(a.seqs.res + (sl + (unsigned)step));
+                    // the letter of the next column is fetched one step ahead (s[LS] at the last column is padding
+                    // or the next sequence: never used), so no global-load latency sits in front of the profile rows
+                    const unsigned letter = nxt;
+                    nxt = __ldg(a.seqs.res + (sl + (unsigned)step + 1u));
                     const unsigned pa = prof_sh + letter * (unsigned)(Q * HL * sizeof(uint4));
                     unsigned sc[RP];
 #pragma unroll

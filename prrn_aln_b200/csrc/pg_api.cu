@@ -477,25 +477,36 @@ static void build_packed_plan(const pg_dev_seqs* d, int64_t k0, int64_t k1, int 
     int64_t ch = (total / 2 + (int64_t)16 * grid_blocks - 1) / ((int64_t)16 * grid_blocks);
     ch = std::max<int64_t>(NWv, std::min<int64_t>(ch, 32 * NWv));
     ch = (ch + NWv - 1) / NWv * NWv;
+    // subjects are visited longest first, so that every item holds subjects of similar length: the two halves of
+    // a warp (and the systolic arrays of a CTA) then run the same number of steps
+    const int nseq = (int)d->h_wlen.size();
+    std::vector<int> by_len(jhi + 1), posJ(nseq, -1);
+    std::iota(by_len.begin(), by_len.end(), 0);
+    std::stable_sort(by_len.begin(), by_len.end(), [&](int x, int y) { return d->h_wlen[x] > d->h_wlen[y]; });
+    for (int p = 0; p < nJ; ++p) posJ[J[p]] = p;
     std::vector<uint32_t> list;
     for (int p = 0; p < nJ; p += 2) {
         const int qa = J[p], qb = p + 1 < nJ ? J[p + 1] : J[p];
         const bool has_b = p + 1 < nJ;
         list.clear();
-        for (int s = 0; s < jlo; ++s) {                      // (a) rectangle part
-            const uint32_t va = in_range(qa, s), vb = has_b && in_range(qb, s);
+        for (int s : by_len) {
+            uint32_t va, vb;
+            if (s < jlo) {                                   // (a) rectangle part
+                va = in_range(qa, s); vb = has_b && in_range(qb, s);
+            } else {                                         // (b) tournament part
+                const int py = posJ[s];
+                if (py == p) continue;
+                va = assigned(p, py) && in_range(qa, s);
+                vb = has_b && py != p + 1 && assigned(p + 1, py) && in_range(qb, s);
+            }
             if (va | vb) list.push_back((uint32_t)s | (va << 30) | (vb << 31));
-        }
-        const int span = h + 2 + (nJ % 2 == 0 ? 1 : 0);     // (b) tournament part
-        for (int t = 1; t <= nJ - 1 && t <= span + nJ / 2; ++t) {
-            const int py = (p + t) % nJ;
-            uint32_t va = py != p && assigned(p, py) && in_range(qa, J[py]);
-            uint32_t vb = has_b && py != p + 1 && assigned(p + 1, py) && in_range(qb, J[py]);
-            if (va | vb) list.push_back((uint32_t)J[py] | (va << 30) | (vb << 31));
         }
         const bool mp = std::max(d->h_wlen[qa], d->h_wlen[qb]) > rpp;
         if (mp) *multipass = true;
-        const int64_t cc = mp ? NWv : ch;
+        // the shortest quarter of the queries is cut into items of a quarter of the size: they sort to the end of
+        // the queue and level the tail of the persistent CTAs
+        const int64_t cs = p >= nJ / 4 ? ch : std::max<int64_t>(NWv, (ch / 4 + NWv - 1) / NWv * NWv);
+        const int64_t cc = mp ? NWv : cs;
         for (size_t i = 0; i < list.size(); i += cc) {
             PgItem2 it;
             it.q0 = qa; it.q1 = qb;

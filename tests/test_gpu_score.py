@@ -100,6 +100,20 @@ def test_int32_and_packed_kernels_agree(ctx, oracle, monkeypatch):
         assert np.array_equal(plain, want), sh
 
 
+def test_packed_kernel_every_rows_variant(ctx, oracle):
+    """Mixed lengths 20..700 in one calcdist: the packed kernel picks 16 / 20 / 24 / 26 / 28 rows per lane per
+    query pair and runs queries beyond 448 residues in several passes; every distance equals the oracle's."""
+    rng = np.random.default_rng(11)
+    lens = [int(x) for x in rng.integers(20, 700, size=56)] + [255, 256, 257, 320, 321, 384, 385, 416, 417, 448, 449, 450]
+    enc = [rng.integers(3, 23, size=n).astype(np.uint8) for n in lens]
+    M = np.array(golden("score_p24_blosum62")["matrix"])
+    for sh in (-60, 12):
+        prm = P.Params(P.ALPRM(sh=sh), vtype=1)
+        want, _ = oracle.calcdist([oracle.seq(e) for e in enc], M, oracle.params(sh=sh, vtype=1))
+        got = ctx.calcdist(P.SeqSet(enc), prm, M)
+        assert np.array_equal(got, want), sh
+
+
 def test_sharded_ranges_concatenate(ctx):
     seqs = gen_synth.config_set("c5a", 60)
     enc = [seqcode.encode_protein(s) for s in seqs]
