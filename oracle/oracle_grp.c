@@ -469,7 +469,7 @@ static int align_b1_##SUFFIX(const orc_seq *a, const orc_seq *b, const double *m
     const VT LongGOP = BasicGOP - diffu * p->k1;                                                     \
     const int Noll = p->ls < 2 ? 2 : (p->ls > 3 ? 3 : p->ls);                                        \
     const int codonk1 = p->ls == 3 ? p->k1 : (INT_MAX / 8 * 7);                                      \
-    if (!((float)p->tgapf == 1.f) || a->exgr || b->exgr || p->lcl) return -2;                        \
+    if (p->lcl & 16) return -2;                               /* fwdswgB_ng is another function */   \
     orc_window w;                                                                                    \
     orc_stripe(a, b, p->sh, &w);                                                                     \
     const int lw = w.lw, up = w.up;                                                                  \
@@ -495,6 +495,10 @@ static int align_b1_##SUFFIX(const orc_seq *a, const orc_seq *b, const double *m
             Hp[i].val = Hp[i - 1].val + (VT)(gpn * ltg);                                             \
         }                                                                                            \
     }                                                                                                \
+    const U topb = Hp[NB - 2];                                  /* boundary cell above the last column */\
+    U leftb = black;                                            /* boundary cell left of the last row */\
+    U *lastC = (U *)malloc(sizeof(U) * (size_t)(ar - al + 1));  /* cells of the last column, per row */  \
+    for (int m = 0; m <= ar - al; ++m) lastC[m] = black;                                             \
     U colprev = Hp[0];                                                                               \
     int colk = 0;                                                                                    \
     const float ltgb = bl ? 1.f : (b->exgl ? 0.f : (float)p->tgapf);                                 \
@@ -548,11 +552,52 @@ static int align_b1_##SUFFIX(const orc_seq *a, const orc_seq *b, const double *m
             if (which == 1) h = g; else if (which == 2) h = g2; else if (which == 3) h = f1; else if (which == 4) h = f2;\
             if (h.dir == G_NEWD || h.dir == G_NEWV || h.dir == G_NEWH) h.ptr = o_add(&st, m, n, h.ptr);\
             Hc[j] = h; Gc[j] = g; G2c[j] = g2;                                                       \
+            if (n == br - 1) lastC[m - al] = h;                                                      \
         }                                                                                            \
+        if (m == ar - 1) leftb = Hc[0];                                                              \
         U *t;                                                                                        \
         t = Hp; Hp = Hc; Hc = t; t = Gp; Gp = Gc; Gc = t; t = G2p; G2p = G2c; G2c = t;               \
     }                                                                                                \
-    const U last = Hp[br - 1 - bl + 1];                         /* lastB_ng with rtgapf == 1 (:141) */\
+    /* lastB_ng (:100-143): trailing gaps at true sequence ends cost rtgapf times the penalty; the last       \
+       column is relaxed downwards, then the last row rightwards, in place as the reference does */   \
+    U *lastR = Hp + 1;                                          /* lastR[n - bl] = cell (ar-1, n) */  \
+    int dm = 0, dn = 0;                                                                              \
+    {                                                                                                \
+        const float rtg = b->exgr ? 0.f : (float)p->tgapf;                                           \
+        if (br == b->len && rtg < 1) {                                                               \
+            const int rw = G_MIN(up, br - al);                                                       \
+            U top = topb;                                                                            \
+            for (int m = br - rw; m <= ar - 1; ++m) {            /* diagonals rw-1 .. br-ar */         \
+                U *gq = (m == al) ? &top : &lastC[m - 1 - al];                                       \
+                U *hq = &lastC[m - al];                                                              \
+                ++dm;                                                                                \
+                const VT gpn = !g_isvert(gq->dir) ? ((1 > codonk1) ? LongGOP + 1 * LongGEP : BasicGOP + 1 * BasicGEP)\
+                                                  : ((dm > codonk1) ? LongGEP : BasicGEP);           \
+                gq->val += (VT)(gpn * rtg);                                                          \
+                if (gq->val > hq->val) { *hq = *gq; hq->dir = G_VERT; } else dm = 0;                 \
+            }                                                                                        \
+            lastR[br - 1 - bl] = lastC[ar - 1 - al];            /* the corner cell is shared */       \
+        }                                                                                            \
+    }                                                                                                \
+    {                                                                                                \
+        const float rtg = a->exgr ? 0.f : (float)p->tgapf;                                           \
+        if (ar == a->len && rtg < 1) {                                                               \
+            const int rw = G_MAX(lw, bl - ar);                                                       \
+            U lft = leftb;                                                                           \
+            for (int n = rw + ar; n <= br - 1; ++n) {            /* diagonals rw+1 .. br-ar */         \
+                U *fq = (n == bl) ? &lft : &lastR[n - 1 - bl];                                       \
+                U *hq = &lastR[n - bl];                                                              \
+                ++dn;                                                                                \
+                const VT gpn = !g_ishori(fq->dir) ? ((1 > codonk1) ? LongGOP + 1 * LongGEP : BasicGOP + 1 * BasicGEP)\
+                                                  : ((dn > codonk1) ? LongGEP : BasicGEP);           \
+                fq->val += (VT)(gpn * rtg);                                                          \
+                if (fq->val > hq->val) { *hq = *fq; hq->dir = G_VERT; } else dn = 0;                 \
+            }                                                                                        \
+        }                                                                                            \
+    }                                                                                                \
+    U last = lastR[br - 1 - bl];                                                                     \
+    if (dn || dm) { if (dn) dm = 0; last.ptr = o_add(&st, ar - dm, br - dn, last.ptr); }             \
+    free(lastC);                                                                                     \
     long pp = o_add(&st, ar, br, last.ptr);                                                          \
     *score = (double)last.val;                                                                       \
     int cnt = 0, ok = 1;                                                                             \

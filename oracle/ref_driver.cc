@@ -313,6 +313,10 @@ int main(int argc, const char** argv)
 	    for (int j = 1; j < nn; ++j) {
 		for (int i = 0; i < j; ++i) {
 		    const Seq*	sq[2] = {seqs[i], seqs[j]};
+		    if (algmode.lcl && !(algmode.lcl & 16)) {	// semi-global: free end gaps per side (as aln does)
+			seqs[i]->exg_seq(algmode.lcl & 1, algmode.lcl & 2);
+			seqs[j]->exg_seq(algmode.lcl & 4, algmode.lcl & 8);
+		    }
 		    PwdB*	pwd = new PwdB(sq);
 		    VTYPE	scr = 0;
 		    SKL*	skl = alignB_ng(sq, pwd, &scr);

@@ -57,6 +57,10 @@ struct K3Prm {
     // mode 3 (Aln2b1, src/fwd2b1.cc): PwdB penalties and the leading-gap factors of initB_ng
     double gop1, gep1, gop2, gep2;      // BasicGOP, BasicGEP, LongGOP, LongGEP
     double ltg_a, ltg_b;                // a.left ? 1 : (a.exgl ? 0 : tgapf), same for b
+    // lastB_ng: trailing-gap factors (exgr ? 0 : tgapf) and whether the relaxation of the last column (gaps after
+    // the end of b) / last row (after the end of a) runs at all (true sequence end and factor < 1)
+    double rtg_a, rtg_b;
+    int32_t last_c, last_r;
 };
 
 // ---- record access -------------------------------------------------------------------------------

@@ -91,7 +91,12 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
         int* const rowG = rowH + (size_t)(LS + 2) * st;
         int* const rowG2 = rowG + (size_t)(LS + 2) * st;
         int* const colH = rowG2 + (size_t)(LS + 2) * st;
-        int* const gwave = colH + (size_t)(LQ + 2) * st;
+        // mode 3 with relaxed trailing gaps (lastB_ng): lastC[m+1] = H(m, LS-1), lastC[0] = boundary above the last
+        // column; lastR[n+1] = H(LQ-1, n), lastR[0] = boundary left of the last row
+        int* const lastC = colH + (size_t)(LQ + 2) * st;
+        int* const lastR = lastC + (size_t)(LQ + 2) * st;
+        int* const gwave = lastR + (size_t)(LS + 2) * st;
+        const bool want_last = MODE == 3 && (p.last_c || p.last_r);
         // wavefront records: shared memory when they fit, else the arena
         const bool in_smem = k3_smem_words(st, p.Noll, TG) <= sm_grp_words;
         int* const wave = in_smem ? sm_grp : gwave;
@@ -138,6 +143,10 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
             }
         }
         GSYNC();
+        if (want_last && t == 0 && role == 0) {
+            k3_copy(p, lastC, rowH + (size_t)LS * st);              // black unless the band reaches it
+            k3_copy(p, lastR, colH + (size_t)LQ * st);
+        }
 
         // prefetch of the parked row: word w of the three records (rowH, rowG, rowG2) of one column
         const int pf_words = (n3 ? 3 : 2) * st;
@@ -248,6 +257,10 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                         if (id < a.vmf_cap) { vmf[id].m = m + P_.al; vmf[id].n = n + P_.bl; vmf[id].p = K3_PTR(hout); }
                         K3_PTR(hout) = id;
                     }
+                    if (want_last) {
+                        if (n == LS - 1) k3_copy(p, lastC + (size_t)(m + 1) * st, hout);
+                        if (m == LQ - 1) k3_copy(p, lastR + (size_t)(n + 1) * st, hout);
+                    }
                     if (m == LQ - 1) {
                         if (n == LS - 1) { sm_last_ptr[g] = K3_PTR(hout); sm_last_val[g] = k3_val(hout); }
                     } else if (t == TG - 1) {                       // bottom row of a stripe: park it
@@ -267,6 +280,47 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                 if (++n2 == P) { n2 = 0; ++k2; }
                 GSYNC();
             }
+        }
+        // ---- Aln2b1::lastB_ng (fwd2b1.cc:100-143): trailing gaps at true sequence ends cost rtgapf times the
+        //      penalty: the last column is relaxed downwards, then the last row rightwards, in place
+        if (want_last && t == 0 && role == 0) {
+            __threadfence();
+            int dm = 0, dn = 0;
+            if (p.last_c) {
+                const int rw = p.up < LS ? p.up : LS;
+                for (int m = LS - rw; m <= LQ - 1; ++m) {
+                    int* gq = lastC + (size_t)m * st;
+                    int* hq = lastC + (size_t)(m + 1) * st;
+                    ++dm;
+                    const double gpn = !k3_isvert(k3_dir(gq)) ? ((1 > p.codonk1) ? p.gop2 + p.gep2 : p.gop1 + p.gep1)
+                                                              : (dm > p.codonk1 ? p.gep2 : p.gep1);
+                    k3_setval(gq, k3_val(gq) + gpn * p.rtg_b);
+                    if (k3_val(gq) > k3_val(hq)) { k3_copy(p, hq, gq); k3_setdg(hq, K3_VERT, 0); } else dm = 0;
+                }
+                k3_copy(p, lastR + (size_t)LS * st, lastC + (size_t)LQ * st);       // the corner cell is shared
+            }
+            if (p.last_r) {
+                const int rw = p.lw > -LQ ? p.lw : -LQ;
+                for (int n = rw + LQ; n <= LS - 1; ++n) {
+                    int* fq = lastR + (size_t)n * st;
+                    int* hq = lastR + (size_t)(n + 1) * st;
+                    ++dn;
+                    const double gpn = !k3_ishori(k3_dir(fq)) ? ((1 > p.codonk1) ? p.gop2 + p.gep2 : p.gop1 + p.gep1)
+                                                              : (dn > p.codonk1 ? p.gep2 : p.gep1);
+                    k3_setval(fq, k3_val(fq) + gpn * p.rtg_a);
+                    if (k3_val(fq) > k3_val(hq)) { k3_copy(p, hq, fq); k3_setdg(hq, K3_VERT, 0); } else dn = 0;
+                }
+            }
+            int* const h9 = lastR + (size_t)LS * st;
+            int ptr = K3_PTR(h9);
+            if (dn || dm) {
+                if (dn) dm = 0;
+                const int id = sm_vmf[g]++;
+                if (id < a.vmf_cap) { vmf[id].m = LQ - dm + P_.al; vmf[id].n = LS - dn + P_.bl; vmf[id].p = ptr; }
+                ptr = id;
+            }
+            sm_last_ptr[g] = ptr;
+            sm_last_val[g] = k3_val(h9);
         }
         // ---- final record + Vmf::traceback (fwd2c.h:475-481, vmf.cc:103-119)
         if (t == 0 && role == 0) {

@@ -65,6 +65,7 @@ extern "C" int pg_create(int device, pg_context** out)
     c->bnd_cap = c->scratch_cap = c->ends_cap = 0;
     c->d_gblob = c->d_garena = c->d_gvmf = c->d_gout = c->d_gsim = nullptr;
     c->gblob_cap = c->garena_cap = c->gvmf_cap = c->gout_cap = c->gsim_cap = 0;
+    c->h_gstage = nullptr; c->gstage_cap = 0;
     c->items_cap = c->mtx_cap = c->self_cap = c->rowbuf_cap = c->out_cap = c->pairs_cap = 0;
     c->d_counter = nullptr;
     c->ev_valid = false;
@@ -96,6 +97,7 @@ extern "C" void pg_destroy(pg_context* c)
     cudaFree(c->d_items); cudaFree(c->d_mtx); cudaFree(c->d_self); cudaFree(c->d_rowbuf);
     cudaFree(c->d_out); cudaFree(c->d_pairs); cudaFree(c->d_counter); cudaFree(c->d_dirs); cudaFree(c->d_trace); cudaFree(c->d_seqblob); cudaFree(c->d_planbuf);
     cudaFree(c->d_bnd); cudaFree(c->d_scratch); cudaFree(c->d_ends);
+    if (c->h_gstage) cudaFreeHost(c->h_gstage);
     cudaFree(c->d_gblob); cudaFree(c->d_garena); cudaFree(c->d_gvmf); cudaFree(c->d_gout); cudaFree(c->d_gsim);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_fork);
     for (int i = 0; i < 5; ++i) { cudaStreamDestroy(c->aux[i]); cudaEventDestroy(c->ev_join[i]); }
@@ -461,10 +463,16 @@ static void build_packed_plan(const pg_dev_seqs* d, int64_t k0, int64_t k1, int 
     std::vector<int> J(nJ);
     std::iota(J.begin(), J.end(), jlo);
     std::stable_sort(J.begin(), J.end(), [&](int x, int y) { return d->h_wlen[x] < d->h_wlen[y]; });
+    // pair {x, y} is inside [k0, k1) iff min(x, y) lies in [rlo, rhi) of the row max(x, y) of the triangle
+    std::vector<int32_t> rlo(jhi + 1), rhi(jhi + 1);
+    for (int64_t j = 0; j <= jhi; ++j) {
+        const int64_t t = j * (j - 1) / 2;
+        rlo[j] = (int32_t)std::min<int64_t>(std::max<int64_t>(k0 - t, 0), j);
+        rhi[j] = (int32_t)std::min<int64_t>(std::max<int64_t>(k1 - t, 0), j);
+    }
     auto in_range = [&](int x, int y) {
-        const int64_t hi = x > y ? x : y, lo = x > y ? y : x;
-        const int64_t k = hi * (hi - 1) / 2 + lo;
-        return k >= k0 && k < k1;
+        const int hi = x > y ? x : y, lo = x > y ? y : x;
+        return lo >= rlo[hi] && lo < rhi[hi];
     };
     const int h = (nJ - 1) / 2;
     auto assigned = [&](int px, int py) {       // does the pair of positions (px, py) belong to px ?

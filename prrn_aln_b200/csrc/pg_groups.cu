@@ -103,8 +103,23 @@ K3Group dev_side(const pg_group& g, const SideOff& so, const char* d)
 }
 }  // namespace
 
+// Terminal-gap factors of one Aln2b1 pair (initB_ng / lastB_ng, src/fwd2b1.cc:64-143); nullptr = all 1, no relaxation
+struct PgTerm {
+    double ltg_a, ltg_b, rtg_a, rtg_b;
+    int32_t last_c, last_r;
+};
+
+static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
+                               double* out_scores, int64_t** out_offs, pg_skl** out_pts, const PgTerm* term);
+
 extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
                                double* out_scores, int64_t** out_offs, pg_skl** out_pts)
+{
+    return pg_int_align_groups(c, a, b, prm, npairs, out_scores, out_offs, out_pts, nullptr);
+}
+
+static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
+                               double* out_scores, int64_t** out_offs, pg_skl** out_pts, const PgTerm* term)
 {
     if (!c) return PG_ERR_ARG;
     if (npairs < 0 || !out_offs || !out_pts || (npairs && (!a || !b || !prm || !out_scores)))
@@ -178,10 +193,15 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
         kp.u2divu1 = P.BasicGEP < 0 ? P.LongGEP / P.BasicGEP : 0;      // fwd2c.h:85-86
         kp.v2divv1 = P.BasicGOP < 0 ? P.LongGOP / P.BasicGOP : 0;
         kp.gop1 = P.BasicGOP; kp.gep1 = P.BasicGEP; kp.gop2 = P.LongGOP; kp.gep2 = P.LongGEP;
-        kp.ltg_a = kp.ltg_b = 1.0;
+        kp.ltg_a = kp.ltg_b = kp.rtg_a = kp.rtg_b = 1.0;
+        kp.last_c = kp.last_r = 0;
+        if (term && mode == 3) {
+            kp.ltg_a = term[i].ltg_a; kp.ltg_b = term[i].ltg_b; kp.rtg_a = term[i].rtg_a; kp.rtg_b = term[i].rtg_b;
+            kp.last_c = term[i].last_c; kp.last_r = term[i].last_r;
+        }
         const int LQ = A.right - A.left, LS = B.right - B.left;
         const size_t st = (size_t)k3_stride(kp.capa, kp.capb);
-        arena_words = std::max(arena_words, st * (size_t)(3 * (LS + 2) + (LQ + 2)) + k3_wave_words((int)st, 3, tg));
+        arena_words = std::max(arena_words, st * (size_t)(4 * (LS + 2) + 2 * (LQ + 2)) + k3_wave_words((int)st, 3, tg));
         wave_bytes = std::max(wave_bytes, 4 * k3_wave_words((int)st, P.Noll, tg));
         if (A.len > 65000 || B.len > 65000) {
             free(offs);
@@ -240,7 +260,19 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     const size_t o_boff = up16(blob + sizeof(K3Pair) * (size_t)npairs);
     rc = pg_int_ensure_cap(c, &c->d_gblob, &c->gblob_cap, o_boff + 4 * (size_t)(npairs + 1) + 256);
     if (rc) { free(offs); return rc; }
-    std::vector<char> h(o_boff + 4 * (size_t)(npairs + 1));
+    // host staging in pinned memory owned by the context: one async copy at PCIe rate, no zero fill
+    const size_t h_bytes = o_boff + 4 * (size_t)(npairs + 1);
+    if (c->gstage_cap < h_bytes) {
+        if (c->h_gstage) cudaFreeHost(c->h_gstage);
+        c->h_gstage = nullptr; c->gstage_cap = 0;
+        const size_t want = h_bytes + h_bytes / 4 + 4096;
+        if (cudaHostAlloc(&c->h_gstage, want, cudaHostAllocDefault) != cudaSuccess) {
+            free(offs);
+            return pg_int_fail(c, PG_ERR_CUDA, "pg_align_groups: cudaHostAlloc(staging) failed");
+        }
+        c->gstage_cap = want;
+    }
+    struct { char* p; size_t n; char* data() const { return p; } size_t size() const { return n; } } h = {(char*)c->h_gstage, h_bytes};
     char* d = (char*)c->d_gblob;
     // heaviest pairs first (persistent CTAs finish together); the kernel indexes results by this order
     std::vector<int32_t> order(npairs);
@@ -377,7 +409,9 @@ int pg_int_align_pairs_fp(pg_context* c, const pg_seqs* s, const int32_t* a_idx,
                           const pg_params* prm, const void* mtx, int32_t dim, void* out_scores, int64_t** out_offs,
                           pg_skl** out_pts, int b1)
 {
-    if (prm->lcl != 0 || !(prm->alprm.tgapf == 1.0f))
+    // Fwd2c<DPunit> on nil-ended sequences is not built; Aln2b1 (b1) takes tgapf < 1 and free ends (initB_ng /
+    // lastB_ng), but not the Smith-Waterman branch (lcl & 16: fwdswgB_ng is another function)
+    if (b1 ? (prm->lcl & 16) != 0 : (prm->lcl != 0 || !(prm->alprm.tgapf == 1.0f)))
         return pg_int_fail(c, PG_ERR_UNSUPPORTED, "pg_align_pairs: semi-global / local alignment with path (nil-ended sequences, "
                                                   "thickness at the ends) is not built yet");
     pg_gparams gp;
@@ -391,7 +425,7 @@ int pg_int_align_pairs_fp(pg_context* c, const pg_seqs* s, const int32_t* a_idx,
     auto wl = [&](int i) { return std::make_pair(s->left ? s->left[i] : 0, s->right ? s->right[i] : s->lens[i]); };
     for (int i = 0; i < n; ++i) {
         if (!need_a[i] && !need_b[i]) continue;
-        if (s->exg && (s->exg[i] & 3))
+        if (!b1 && s->exg && (s->exg[i] & 3))
             return pg_int_fail(c, PG_ERR_UNSUPPORTED, "pg_align_pairs: inex.exgl / exgr with path is not built yet");
         const auto w = wl(i);
         if (w.first < 0 || w.second > s->lens[i] || w.first > w.second) return pg_int_fail(c, PG_ERR_ARG, "window outside the sequence");
@@ -420,10 +454,11 @@ int pg_int_align_pairs_fp(pg_context* c, const pg_seqs* s, const int32_t* a_idx,
     const int64_t CHUNK = 2048;
     std::vector<pg_group> ga, gb;
     std::vector<pg_gparams> gps;
+    std::vector<PgTerm> terms;
     std::vector<double> sc;
     for (int64_t c0 = 0; c0 < npairs; c0 += CHUNK) {
         const int64_t c1 = std::min(npairs, c0 + CHUNK);
-        ga.clear(); gb.clear(); gps.clear();
+        ga.clear(); gb.clear(); gps.clear(); terms.clear();
         std::vector<int64_t> live;      // pairs with two non-empty windows (align2 answers the others with nogap_skl)
         for (int64_t p = c0; p < c1; ++p) {
             const int ia = a_idx[p], ib = b_idx[p];
@@ -436,13 +471,29 @@ int pg_int_align_pairs_fp(pg_context* c, const pg_seqs* s, const int32_t* a_idx,
             B.many = 1; B.len = s->lens[ib]; B.left = wb.first; B.right = wb.second; B.hetero = -1;
             B.cfq = B.efq = ones[ib].data(); B.vec = onehot[ib].data();
             ga.push_back(A); gb.push_back(B); gps.push_back(gp);
+            if (b1) {
+                // inex flags of the two roles: the caller's per-sequence flags, or algmode.lcl as aln applies it
+                // (exg_seq(lcl&1, lcl&2) on a, exg_seq(lcl&4, lcl&8) on b)
+                const int ea = (s->exg ? s->exg[ia] & 3 : 0) | (prm->lcl & 3);
+                const int eb = (s->exg ? s->exg[ib] & 3 : 0) | ((prm->lcl >> 2) & 3);
+                const double tg = (double)prm->alprm.tgapf;
+                PgTerm t;
+                t.ltg_a = wa.first ? 1.0 : ((ea & 1) ? 0.0 : tg);
+                t.ltg_b = wb.first ? 1.0 : ((eb & 1) ? 0.0 : tg);
+                t.rtg_a = (ea & 2) ? 0.0 : tg;
+                t.rtg_b = (eb & 2) ? 0.0 : tg;
+                t.last_c = wb.second == s->lens[ib] && t.rtg_b < 1.0;
+                t.last_r = wa.second == s->lens[ia] && t.rtg_a < 1.0;
+                terms.push_back(t);
+            }
             live.push_back(p);
         }
         sc.assign(live.size(), 0.0);
         int64_t* o2 = nullptr;
         pg_skl* p2 = nullptr;
         if (!live.empty()) {
-            int rc = pg_align_groups(c, ga.data(), gb.data(), gps.data(), (int64_t)live.size(), sc.data(), &o2, &p2);
+            int rc = pg_int_align_groups(c, ga.data(), gb.data(), gps.data(), (int64_t)live.size(), sc.data(), &o2, &p2,
+                                         b1 ? terms.data() : nullptr);
             if (rc) { free(offs); return rc; }
         }
         size_t li = 0;

@@ -213,6 +213,7 @@ struct pg_context {
     void* d_scratch; size_t scratch_cap;
     void* d_ends; size_t ends_cap;
     void* d_gblob; size_t gblob_cap;
+    void* h_gstage; size_t gstage_cap;      // pinned host staging of the group blob (grow-only)
     void* d_garena; size_t garena_cap;
     void* d_gvmf; size_t gvmf_cap;
     void* d_gout; size_t gout_cap;

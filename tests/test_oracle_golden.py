@@ -97,7 +97,9 @@ def test_aln2b1_bit_exact(oracle, name):
     enc = [seqcode.encode_protein(s) for s in g["seqs"]]
     p = _oracle_params(oracle, g)
     M = np.nan_to_num(np.array(g["matrix"]))
+    lcl = p.lcl                 # semi-global goldens: the driver ran exg_seq(lcl&1, lcl&2) on a, (lcl&4, lcl&8) on b
     for pr in g["pairs"]:
-        scr, pts = oracle.align_b1(oracle.seq(enc[pr["i"]]), oracle.seq(enc[pr["j"]]), M, p)
+        scr, pts = oracle.align_b1(_exg_seq(oracle, enc[pr["i"]], lcl & 1, lcl & 2),
+                                   _exg_seq(oracle, enc[pr["j"]], lcl & 4, lcl & 8), M, p)
         assert scr == pr["score"] == pr["hom"], (pr["i"], pr["j"])
         assert pts == [tuple(x) for x in pr["skl"]], (pr["i"], pr["j"])

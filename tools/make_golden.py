@@ -186,6 +186,14 @@ def alignb_cases():
     alignb_case("alignb_p12_twopiece_f64", p12, flavour="d", ls=3)
     alignb_case("alignb_p12_sh3_u3v11", gen_synth.synth_set(12, 150, 0.2, 0.9, 12), sh=3, u=3, v=11)
     alignb_case("alignb_long700", gen_synth.synth_set(4, 700, 0.1, 0.5, 31))
+    # terminal gaps: reduced penalty at true ends (initB_ng / lastB_ng with tgapf < 1), free ends per side
+    rag = [s[a:len(s) - b] for s, a, b in zip(gen_synth.synth_set(10, 160, 0.1, 0.6, 41),
+                                             [0, 30, 0, 45, 10, 0, 60, 5, 0, 25], [0, 0, 40, 20, 0, 55, 0, 35, 15, 0])]
+    alignb_case("alignb_rag10_tgapf05_f64", rag, flavour="d", tgapf=0.5)
+    alignb_case("alignb_rag10_tgapf0", rag, tgapf=0)
+    alignb_case("alignb_rag10_lcl15_f64", rag, flavour="d", lcl=15)
+    alignb_case("alignb_rag10_lcl6", rag, lcl=6)
+    alignb_case("alignb_rag10_lcl9_twopiece_f64", rag, flavour="d", lcl=9, ls=3)
 
 
 def sample_pair():
