@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "k1f_core.cuh"
@@ -492,23 +493,46 @@ static void build_packed_plan(const pg_dev_seqs* d, int64_t k0, int64_t k1, int 
     std::iota(by_len.begin(), by_len.end(), 0);
     std::stable_sort(by_len.begin(), by_len.end(), [&](int x, int y) { return d->h_wlen[x] > d->h_wlen[y]; });
     for (int p = 0; p < nJ; ++p) posJ[J[p]] = p;
-    std::vector<uint32_t> list;
+    // the subject lists of the query pairs are independent: host threads build them side by side
+    const int npq = (nJ + 1) / 2;
+    std::vector<std::vector<uint32_t>> lists(npq);
+    auto build_lists = [&](int p_begin, int p_end) {
+        for (int pq = p_begin; pq < p_end; ++pq) {
+            const int p = 2 * pq;
+            const int qa = J[p], qb = p + 1 < nJ ? J[p + 1] : J[p];
+            const bool has_b = p + 1 < nJ;
+            std::vector<uint32_t>& list = lists[pq];
+            list.reserve((size_t)jhi / 2 + 16);
+            for (int s : by_len) {
+                uint32_t va, vb;
+                if (s < jlo) {                                   // (a) rectangle part
+                    va = in_range(qa, s); vb = has_b && in_range(qb, s);
+                } else {                                         // (b) tournament part
+                    const int py = posJ[s];
+                    if (py == p) continue;
+                    va = assigned(p, py) && in_range(qa, s);
+                    vb = has_b && py != p + 1 && assigned(p + 1, py) && in_range(qb, s);
+                }
+                if (va | vb) list.push_back((uint32_t)s | (va << 30) | (vb << 31));
+            }
+        }
+    };
+    {
+        const int64_t work = (int64_t)npq * (jhi + 1);
+        int nth = work < 200000 ? 1 : (int)std::min<int64_t>(4, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char* ev = getenv("PG_PLAN_THREADS")) nth = std::max(1, atoi(ev));
+        nth = std::min(nth, npq);
+        if (nth <= 1) build_lists(0, npq);
+        else {
+            std::vector<std::thread> th;
+            for (int k = 0; k < nth; ++k)
+                th.emplace_back(build_lists, (int)((int64_t)npq * k / nth), (int)((int64_t)npq * (k + 1) / nth));
+            for (auto& t : th) t.join();
+        }
+    }
     for (int p = 0; p < nJ; p += 2) {
         const int qa = J[p], qb = p + 1 < nJ ? J[p + 1] : J[p];
-        const bool has_b = p + 1 < nJ;
-        list.clear();
-        for (int s : by_len) {
-            uint32_t va, vb;
-            if (s < jlo) {                                   // (a) rectangle part
-                va = in_range(qa, s); vb = has_b && in_range(qb, s);
-            } else {                                         // (b) tournament part
-                const int py = posJ[s];
-                if (py == p) continue;
-                va = assigned(p, py) && in_range(qa, s);
-                vb = has_b && py != p + 1 && assigned(p + 1, py) && in_range(qb, s);
-            }
-            if (va | vb) list.push_back((uint32_t)s | (va << 30) | (vb << 31));
-        }
+        const std::vector<uint32_t>& list = lists[p / 2];
         const bool mp = std::max(d->h_wlen[qa], d->h_wlen[qb]) > rpp;
         if (mp) *multipass = true;
         // the shortest quarter of the queries is cut into items of a quarter of the size: they sort to the end of
