@@ -52,17 +52,66 @@ def workload(n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    """SM clock / throttle-reason sampler running during the timed region: NVML (what nvidia-smi reads) polled
+    every few ms from a thread, so that a timed region of tens of ms still gets samples; falls back to
+    `nvidia-smi -lms` when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index=0):
         self.index = index
-        self.rows = []
+        self.rows = []          # nvidia-smi fallback
+        self.sm, self.mx, self.reasons = [], [], set()
         self.proc = None
+        self.nv = None
+        self.h = None
+        self.stop_flag = False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
+
+    def sample_now(self):
+        if not self.nv:
+            return
+        nv, h = self.nv, self.h
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in self.BITS:
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self.stop_flag:
+            self.sample_now()
+            time.sleep(0.004)
 
     def start(self):
+        try:
+            self.nv, self.h = self._nvml_handle()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -77,6 +126,11 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nv:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -95,7 +149,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def cpu_reference_run(seqs, threads, reps=1):
@@ -227,16 +281,18 @@ def main():
         step_dev()
     sync_all()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
+    if rank == 0:
+        sampler.start()                  # polls while the timed steps below execute
     for i in range(args.steps):
         flush.fill_(i & 0xff)            # evict L2 between timed iterations (outside the events)
         ev[i][0].record(stream)
         launches += step_dev()
         ev[i][1].record(stream)
+    if rank == 0:
+        sampler.sample_now()             # the steps are queued and running: at least one sample under load
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
