@@ -87,9 +87,12 @@ void pg_free(void *p);
  *   SKL*  alignB_ng(const Seq* seqs[2], const PwdB* pwd, VTYPE* scr)                src/fwd2b1.cc:1347
  *   VTYPE HomScoreB_ng(const Seq* seqs[2], const PwdB* pwd, long rr[])              src/fwd2b1.cc:1317
  * (Aln2b1::initB_ng :64, forwardB_ng :145, lastB_ng :100, trcbkalignB_ng :1025, globalB_ng :1286) for a
- * batch of pairs: prrn5's DynAln distances (src/adjmat.cc:84).  Global mode, tgapf == 1, DP matrices below
- * MaxVmfSpace (no linear-space recursion), affine or two-piece.  Same outputs as pg_align_pairs: the score
- * (== HomScoreB_ng's) and the corner records before stdskl, which the caller runs as globalB_ng does. */
+ * batch of pairs: prrn5's DynAln distances (src/adjmat.cc:84).  Global and semi-global: alprm.tgapf and the
+ * inex.exgl / exgr flags of each sequence (seqs->exg, or prm->lcl & 15 applied as aln does: bits 1, 2 to a,
+ * 4, 8 to b) scale the leading gaps in initB_ng and drive the relaxation of lastB_ng.  prm->lcl & 16
+ * (fwdswgB_ng) returns PG_ERR_UNSUPPORTED.  DP matrices of any size are traced directly (no linear-space
+ * recursion), affine or two-piece.  Same outputs as pg_align_pairs: the score (== HomScoreB_ng's) and the
+ * corner records before stdskl, which the caller runs as globalB_ng does. */
 int pg_align_pairs_ng(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx, const int32_t *b_idx,
                       int64_t npairs, const pg_params *prm, const void *mtx, int32_t dim,
                       void *out_scores, int64_t **out_offs, pg_skl **out_pts);
