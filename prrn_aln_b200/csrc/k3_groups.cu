@@ -35,7 +35,14 @@ constexpr int PFN = 4;              // prefetch words per thread (3 * stride <= 
 // words of shared memory one alignment needs for its wavefront records
 __host__ __device__ inline size_t k3_smem_words(int st, int Noll, int tg)
 {
-    return (size_t)st * ((Noll == 3 ? 9 : 6) * tg + 1 + 3 * RING);
+    return (size_t)st * ((Noll == 3 ? 9 : 6) * tg + 1 + 3 * RING + 4);
+}
+// SM variant of the kernel (every record operand of a cell lives in shared memory, so the compiler emits
+// LDS / STS with 32-bit addresses instead of generic loads): needs the wavefront records in shared memory
+// and the prefetch ring of the parked row
+__host__ __device__ inline bool k3_sm_ok(int st, int Noll, int tg, size_t smem_words_per_group)
+{
+    return k3_smem_words(st, Noll, tg) <= smem_words_per_group && (Noll == 3 ? 3 : 2) * st <= PFN * tg;
 }
 
 // barrier over the TG threads that share one alignment (named barrier g + 1; a warp needs none)
@@ -54,7 +61,8 @@ __device__ __forceinline__ void group_sync(int g)
 // barrier, then role 0 applies the selection.  Same records, same results, ~1/3 of the per-step chain.
 // MODE (record type) is a template parameter: a batch is launched once per mode present, so every
 // `p.mode ==` test inside the per-cell code folds away (p.mode is overwritten with the constant below).
-template <int TG, bool SPLIT, int MODE>
+// SM: all record operands in shared memory (see k3_sm_ok; the host picks the variant per launch).
+template <int TG, bool SPLIT, int MODE, bool SM>
 __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_kernel(const K3Args a)
 {
     constexpr int NG = SPLIT ? 1 : CTA / TG;        // alignments in flight per CTA
@@ -83,6 +91,14 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
         const K3Group B = P_.b;
         K3Prm p = P_.prm;
         p.mode = MODE;
+        // the per-column data of both groups sit in the staged blob (global memory; never null, pg_groups.cu
+        // dev_side): telling the compiler turns the generic loads through these struct members into LDG
+#define K3_GLOBAL(ptr) __builtin_assume(__isGlobal(ptr))
+        K3_GLOBAL(A.cfq); K3_GLOBAL(A.efq); K3_GLOBAL(A.prof); K3_GLOBAL(A.freq); K3_GLOBAL(A.glen); K3_GLOBAL(A.gfreq);
+        K3_GLOBAL(A.sfq); K3_GLOBAL(A.tfq); K3_GLOBAL(A.rfq); K3_GLOBAL(A.gapmask); K3_GLOBAL(A.weight);
+        K3_GLOBAL(B.cfq); K3_GLOBAL(B.efq); K3_GLOBAL(B.prof); K3_GLOBAL(B.freq); K3_GLOBAL(B.glen); K3_GLOBAL(B.gfreq);
+        K3_GLOBAL(B.sfq); K3_GLOBAL(B.tfq); K3_GLOBAL(B.rfq); K3_GLOBAL(B.gapmask); K3_GLOBAL(B.weight);
+#undef K3_GLOBAL
         const int LQ = A.L, LS = B.L;
         const int st = k3_stride(p.capa, p.capb);
         const bool n3 = p.Noll == 3;
@@ -98,13 +114,14 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
         int* const gwave = lastR + (size_t)(LS + 2) * st;
         const bool want_last = MODE == 3 && (p.last_c || p.last_r);
         // wavefront records: shared memory when they fit, else the arena
-        const bool in_smem = k3_smem_words(st, p.Noll, TG) <= sm_grp_words;
-        int* const wave = in_smem ? sm_grp : gwave;
+        const bool in_smem = SM || k3_smem_words(st, p.Noll, TG) <= sm_grp_words;
+        int* const wave = SM ? sm_grp : (in_smem ? sm_grp : gwave);
         int* const ringH = wave;                            // [RING] prefetched rowH records
         int* const ringG = ringH + (size_t)RING * st;
         int* const ringG2 = ringG + (size_t)RING * st;
         int* const black = ringG2 + (size_t)RING * st;
-        int* const pubH = black + st;                       // [3][TG]
+        int* const colbuf = black + st;                     // [2][2] boundary-column records of the row that starts (SM)
+        int* const pubH = colbuf + (size_t)4 * st;          // [3][TG]
         int* const pubG = pubH + (size_t)3 * TG * st;       // [2][TG]
         int* const F1 = pubG + (size_t)2 * TG * st;         // [TG]
         int* const pubG2 = F1 + (size_t)TG * st;            // [2][TG]   (two-piece only)
@@ -150,7 +167,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
 
         // prefetch of the parked row: word w of the three records (rowH, rowG, rowG2) of one column
         const int pf_words = (n3 ? 3 : 2) * st;
-        const bool ring_ok = pf_words <= PFN * TG;
+        const bool ring_ok = SM || pf_words <= PFN * TG;
 
         // ---- continuous stripes: thread t takes rows t, t+TG, t+2TG, ...; its k-th row meets column n at
         //      global step S = k*P + t + n with the period P = max(LS, TG + 4): a thread starts its next row the
@@ -220,13 +237,24 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                     const int* parkedH1 = ring_ok ? ringH + (size_t)((seq + 1) % RING) * st : rowH + (size_t)(n + 1) * st;
                     const int* parkedG1 = ring_ok ? ringG + (size_t)((seq + 1) % RING) * st : rowG + (size_t)(n + 1) * st;
                     const int* parkedG21 = ring_ok ? ringG2 + (size_t)((seq + 1) % RING) * st : rowG2 + (size_t)(n + 1) * st;
-                    const int* hdiag = n == 0 ? colH + (size_t)m * st : (t == 0 ? parkedH0 : pubH + ((size_t)g3d * TG + (t - 1)) * st);
+                    // boundary column: H(m-1, -1) and H(m, -1).  SM: one row starts per step; its two boundary records
+                    // come to shared memory first, so that every operand of the cell is a shared-memory record
+                    int* const cb = colbuf + (size_t)(S & 1) * 2 * st;
+                    const int* const colD = SM ? cb : colH + (size_t)m * st;
+                    const int* const colL = SM ? cb + st : colH + (size_t)(m + 1) * st;
+                    if (SM && n == 0) {
+                        const int* gD = colH + (size_t)m * st;
+                        const int* gL = colH + (size_t)(m + 1) * st;
+                        if (!SPLIT || role == 0) for (int w = 0; w < st; w += 2) *reinterpret_cast<int2*>(cb + w) = __ldcg(reinterpret_cast<const int2*>(gD + w));
+                        if (!SPLIT || role == 2) for (int w = 0; w < st; w += 2) *reinterpret_cast<int2*>(cb + st + w) = __ldcg(reinterpret_cast<const int2*>(gL + w));
+                    }
+                    const int* hdiag = n == 0 ? colD : (t == 0 ? parkedH0 : pubH + ((size_t)g3d * TG + (t - 1)) * st);
                     const bool above_in = r + 1 <= p.up;
                     const int* habove = !above_in ? black : (t == 0 ? parkedH1 : pubH + ((size_t)g3a * TG + (t - 1)) * st);
                     const int* gabove = (!above_in || m == 0) ? black : (t == 0 ? parkedG1 : pubG + ((size_t)g2a * TG + (t - 1)) * st);
                     const int* g2above = (!above_in || m == 0) ? black : (t == 0 ? parkedG21 : pubG2 + ((size_t)g2a * TG + (t - 1)) * st);
                     const bool left_in = r - 1 >= p.lw;
-                    const int* hleft = n == 0 ? colH + (size_t)(m + 1) * st : (left_in ? pubH + ((size_t)g3a * TG + t) * st : black);
+                    const int* hleft = n == 0 ? colL : (left_in ? pubH + ((size_t)g3a * TG + t) * st : black);
                     if (!SPLIT) {
                         const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
                         rec = p.mode == 3
@@ -343,10 +371,10 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
     }
 }
 
-template <int TG, bool SPLIT, int MODE>
+template <int TG, bool SPLIT, int MODE, bool SM>
 cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     // The gap-profile lists and score rows stream through L1.  Few pairs (latency: Prrn::best_of_n sized
     // batches): one CTA per SM and the rest of the unified array as L1 (measured 28 vs 37 ms for 24
@@ -355,21 +383,21 @@ cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
     int carve = grid_blocks > 148 ? 100 : (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
     if (const char* cv = getenv("PG_K3_CARVEOUT")) carve = atoi(cv);
     if (carve > 100) carve = 100;
-    e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return e;
-    k3_fill_kernel<TG, SPLIT, MODE><<<grid_blocks, SPLIT ? 3 * CTA : CTA, a.smem_bytes, st>>>(a);
+    k3_fill_kernel<TG, SPLIT, MODE, SM><<<grid_blocks, SPLIT ? 3 * CTA : CTA, a.smem_bytes, st>>>(a);
     return cudaGetLastError();
 }
 
-template <int TG, bool SPLIT>
+template <int TG, bool SPLIT, bool SM>
 cudaError_t launch_tg(const K3Args& a, int mode, int grid_blocks, cudaStream_t st)
 {
     switch (mode) {
-    case 0: return launch_tgm<TG, SPLIT, 0>(a, grid_blocks, st);
-    case 1: return launch_tgm<TG, SPLIT, 1>(a, grid_blocks, st);
-    case 2: return launch_tgm<TG, SPLIT, 2>(a, grid_blocks, st);
-    case 3: return launch_tgm<TG, SPLIT, 3>(a, grid_blocks, st);
-    default: return launch_tgm<TG, SPLIT, 4>(a, grid_blocks, st);
+    case 0: return launch_tgm<TG, SPLIT, 0, SM>(a, grid_blocks, st);
+    case 1: return launch_tgm<TG, SPLIT, 1, SM>(a, grid_blocks, st);
+    case 2: return launch_tgm<TG, SPLIT, 2, SM>(a, grid_blocks, st);
+    case 3: return launch_tgm<TG, SPLIT, 3, SM>(a, grid_blocks, st);
+    default: return launch_tgm<TG, SPLIT, 4, SM>(a, grid_blocks, st);
     }
 }
 
@@ -398,9 +426,20 @@ int k3_pick_tg(int64_t npairs, int sm_count)
 // One launch processes the pairs of ONE mode (a.pairs / a.npairs / a.counter / a.out_* are that mode's slice).
 cudaError_t k3_launch(const K3Args& a, int tg, int mode, int grid_blocks, cudaStream_t st)
 {
+    // a.all_sm: every pair of the launch keeps its wavefront records and prefetch ring in shared memory for this
+    // tg (k3_all_sm): the variant whose cell operands are all shared-memory records.  Otherwise (very long
+    // gap-state lists) the generic-address variant, one thread per row, 256 rows per stripe.
+    if (!a.all_sm) return launch_tg<256, false, false>(a, mode, grid_blocks, st);
+    if (getenv("PG_K3_GENERIC") && tg != 768 && tg != 128) return launch_tg<256, false, false>(a, mode, grid_blocks, st);
     switch (tg) {
-    case 128: return launch_tg<128, false>(a, mode, grid_blocks, st);
-    case 768: return launch_tg<256, true>(a, mode, grid_blocks, st);      // role-split latency kernel
-    default: return launch_tg<256, false>(a, mode, grid_blocks, st);
+    case 128: return launch_tg<128, false, true>(a, mode, grid_blocks, st);
+    case 768: return launch_tg<256, true, true>(a, mode, grid_blocks, st);      // role-split latency kernel
+    default: return launch_tg<256, false, true>(a, mode, grid_blocks, st);
     }
+}
+
+bool k3_sm_fits(int stride, int Noll, int tg, size_t smem_bytes)
+{
+    const int ngrp = tg == 768 ? 1 : K3_THREADS / tg;
+    return k3_sm_ok(stride, Noll, tg == 768 ? 256 : tg, smem_bytes / 4 / ngrp);
 }

@@ -338,6 +338,10 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         km.out_cnt = ka.out_cnt + k0;
         km.out_score = ka.out_score + k0;
         const int gm = g_mode[mode];
+        km.all_sm = 1;
+        for (int64_t k = k0; k < k1 && km.all_sm; ++k)
+            km.all_sm = k3_sm_fits(k3_stride(sorted[k].prm.capa, sorted[k].prm.capb), sorted[k].prm.Noll, tg_sel,
+                                   (size_t)ka.smem_bytes) ? 1 : 0;
         km.arena = ka.arena + (size_t)slot0_mode[mode] * arena_words;
         km.vmf = ka.vmf + (size_t)slot0_mode[mode] * (size_t)vmf_cap;
         e = cudaStreamWaitEvent(c->aux[mode], c->ev_fork, 0);

@@ -164,6 +164,7 @@ struct K3Args {
     int32_t* out_cnt;           // [npairs] corners, -1 on overflow
     double* out_score;          // [npairs]
     int32_t smem_bytes;         // dynamic shared memory per CTA for the wavefront records
+    int32_t all_sm;             // every pair fits the all-shared-memory variant (k3_sm_fits)
 };
 
 // profile contraction (k4_contract.cu): S = X_a . Y_b^T per pair, written to K3Pair::simmat
@@ -262,6 +263,7 @@ cudaError_t k3_launch(const K3Args& a, int tg, int mode, int grid_blocks, cudaSt
 int k3_threads();
 int k3_blocks_per_sm();
 int k3_pick_tg(int64_t npairs, int sm_count);
+bool k3_sm_fits(int stride, int Noll, int tg, size_t smem_bytes);
 size_t k3_wave_words(int stride, int Noll, int tg);
 // k4_contract.cu
 cudaError_t k4_launch(const K4Args& a, int total_blocks, cudaStream_t st);
