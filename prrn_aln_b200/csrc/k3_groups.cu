@@ -19,9 +19,11 @@
 //            back-walk order, so the output equals alignC's, quirks included.
 //   sim2   = one contraction X_a[m] . Y_b[n] over residue codes (all sim11..sim33 variants, staged by
 //            the host layer); evaluated per cell here, or read from the tile matrix K4 precomputed.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "k3_core.cuh"
 #include "pg_internal.h"
@@ -35,7 +37,7 @@ constexpr int PFN = 4;              // prefetch words per thread (3 * stride <= 
 // words of shared memory one alignment needs for its wavefront records
 __host__ __device__ inline size_t k3_smem_words(int st, int Noll, int tg)
 {
-    return (size_t)st * ((Noll == 3 ? 9 : 6) * tg + 1 + 3 * RING + 4);
+    return (size_t)st * ((Noll == 3 ? 9 : 6) * tg + 1 + 3 * RING + 4 + 4);
 }
 // SM variant of the kernel (every record operand of a cell lives in shared memory, so the compiler emits
 // LDS / STS with 32-bit addresses instead of generic loads): needs the wavefront records in shared memory
@@ -54,6 +56,18 @@ __device__ __forceinline__ void group_sync(int g)
     else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(TG) : "memory");
 }
 
+// Cluster barrier of the per-step hand-off.  cg::cluster_group::sync() is arrive.release + wait.acquire at cluster
+// scope, for which ptxas emits an L1 invalidate (CCTL.IVALL) -- every step would throw away the gap-profile lists
+// the latency mode keeps in L1.  What crosses CTAs here is (a) shared-memory records read through DSMEM one
+// barrier after they were written and (b) parked rows in global memory read with ld.global.cg (L2) hundreds of
+// steps later, so the barrier is used relaxed with a CTA-scope fence in front (PG_K3_CLUSTER_FENCE=1 selects
+// the fully fenced form; results are identical in both, see tests).
+__device__ __forceinline__ void cluster_step_sync()
+{
+    __threadfence_block();
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+
 // TG threads per alignment: the whole CTA for few pairs (latency), down to one warp per alignment for
 // large batches (no block barrier at all, 95 % of the lane-steps inside the matrix instead of 72 %).
 // SPLIT (latency mode, TG = 256 only): three threads per row -- the diagonal, vertical and horizontal
@@ -62,10 +76,21 @@ __device__ __forceinline__ void group_sync(int g)
 // MODE (record type) is a template parameter: a batch is launched once per mode present, so every
 // `p.mode ==` test inside the per-cell code folds away (p.mode is overwritten with the constant below).
 // SM: all record operands in shared memory (see k3_sm_ok; the host picks the variant per launch).
-template <int TG, bool SPLIT, int MODE, bool SM>
+// CL (latency mode only: SPLIT, SM): a THREAD-BLOCK CLUSTER of NC CTAs works on one alignment -- CTA c holds the
+// rows c*256 .. c*256+255 (+ k*NC*256), so NC*256 rows are in flight and a 1,100-row alignment needs
+// LQ + LS steps instead of five stripes one after the other.  The first thread of CTA c > 0 reads what the last
+// thread of CTA c-1 published one and two steps ago through distributed shared memory (copied to a local
+// slot, so the cell code still sees shared-memory records); every step ends in a cluster barrier; the path
+// records of CTA c live in its own part of the store (id = c * vmf_cap + local id).
+template <int TG, bool SPLIT, int MODE, bool SM, bool CL>
 __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_kernel(const K3Args a)
 {
+    static_assert(!CL || (SPLIT && SM && TG == CTA), "the cluster variant is the role-split shared-memory kernel");
+    namespace cg = cooperative_groups;
     constexpr int NG = SPLIT ? 1 : CTA / TG;        // alignments in flight per CTA
+    const int NC = CL ? (int)cg::this_cluster().num_blocks() : 1;       // CTAs per alignment
+    const int crank = CL ? (int)cg::this_cluster().block_rank() : 0;
+    const int TGC = NC * TG;                        // rows in flight per alignment
     extern __shared__ __align__(16) int sm_dyn[];
     __shared__ int sm_pair[NG];
     __shared__ int sm_vmf[NG];
@@ -74,17 +99,18 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
     const int role = SPLIT ? threadIdx.x / TG : 0;  // 0 diagonal (+ selection), 1 vertical, 2 horizontal
     const int g = SPLIT ? 0 : threadIdx.x / TG;
     const int t = threadIdx.x - (SPLIT ? role : g) * TG;
-    const int slot = blockIdx.x * NG + g;
+    const int slot = CL ? (int)blockIdx.x / NC : blockIdx.x * NG + g;
     int* const arena = a.arena + (size_t)slot * a.arena_words;
-    K3Vmf* const vmf = a.vmf + (size_t)slot * a.vmf_cap;
+    K3Vmf* const vmf = a.vmf + (size_t)slot * (CL ? NC : 1) * a.vmf_cap;       // CL: NC consecutive parts
     int* const sm_grp = sm_dyn + (size_t)g * (a.smem_bytes / 4 / NG);
     const size_t sm_grp_words = (size_t)(a.smem_bytes / 4 / NG);
 
-#define GSYNC() do { if (SPLIT) __syncthreads(); else group_sync<TG>(g); } while (0)
+#define GSYNC() do { if (CL) cluster_step_sync(); else if (SPLIT) __syncthreads(); else group_sync<TG>(g); } while (0)
     for (;;) {
-        if (t == 0 && role == 0) sm_pair[g] = atomicAdd(a.counter, 1);
+        if (t == 0 && role == 0 && crank == 0) sm_pair[g] = atomicAdd(a.counter, 1);
         GSYNC();
-        const int pi = sm_pair[g];
+        const int pi = CL ? *cg::this_cluster().map_shared_rank(&sm_pair[0], 0) : sm_pair[g];
+        if (CL) cg::this_cluster().sync();     // nobody leaves (or rewrites sm_pair) before every CTA has read it
         if (pi >= a.npairs) break;
         const K3Pair& P_ = a.pairs[pi];
         const K3Group A = P_.a;
@@ -112,6 +138,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
         int* const lastC = colH + (size_t)(LQ + 2) * st;
         int* const lastR = lastC + (size_t)(LQ + 2) * st;
         int* const gwave = lastR + (size_t)(LS + 2) * st;
+        int* const ghdr = gwave;                            // CL: {last ptr, overflow flag, last val (double)} of the cluster
         const bool want_last = MODE == 3 && (p.last_c || p.last_r);
         // wavefront records: shared memory when they fit, else the arena
         const bool in_smem = SM || k3_smem_words(st, p.Noll, TG) <= sm_grp_words;
@@ -121,18 +148,22 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
         int* const ringG2 = ringG + (size_t)RING * st;
         int* const black = ringG2 + (size_t)RING * st;
         int* const colbuf = black + st;                     // [2][2] boundary-column records of the row that starts (SM)
-        int* const pubH = colbuf + (size_t)4 * st;          // [3][TG]
+        int* const xbuf = colbuf + (size_t)4 * st;          // [4] records of the neighbour CTA's last thread (CL)
+        int* const pubH = xbuf + (size_t)4 * st;            // [3][TG]
         int* const pubG = pubH + (size_t)3 * TG * st;       // [2][TG]
         int* const F1 = pubG + (size_t)2 * TG * st;         // [TG]
         int* const pubG2 = F1 + (size_t)TG * st;            // [2][TG]   (two-piece only)
         int* const F2 = pubG2 + (size_t)2 * TG * st;        // [TG]
         // ---- reset the records this pair can read before writing
         if (role == 0) {
+        if (crank == 0) {
         for (int i = t; i < LS + 2; i += TG) {
             k3_reset(p, rowH + (size_t)i * st); k3_reset(p, rowG + (size_t)i * st);
             if (n3) k3_reset(p, rowG2 + (size_t)i * st);
         }
         for (int i = t; i < LQ + 2; i += TG) k3_reset(p, colH + (size_t)i * st);
+        if (CL && t == 0) { ghdr[0] = 0; ghdr[1] = 0; }
+        }
         for (int k = 0; k < 3; ++k) k3_reset(p, pubH + ((size_t)k * TG + t) * st);
         for (int k = 0; k < 2; ++k) { k3_reset(p, pubG + ((size_t)k * TG + t) * st); if (n3) k3_reset(p, pubG2 + ((size_t)k * TG + t) * st); }
         if (t < RING) { k3_reset(p, ringH + (size_t)t * st); k3_reset(p, ringG + (size_t)t * st); k3_reset(p, ringG2 + (size_t)t * st); }
@@ -140,7 +171,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
         }
         GSYNC();
         // ---- initB (fwd2c.h:138-176): origin, then the two boundary chains (one thread each)
-        if (t == 0 && role == 0) {
+        if (CL && crank != 0 && t == 0 && role == 0) sm_vmf[g] = 0;
+        if (t == 0 && role == 0 && crank == 0) {
             vmf[0].m = 0; vmf[0].n = 0; vmf[0].p = 0;                       // skip 0-th record (:361)
             vmf[1].m = P_.al; vmf[1].n = P_.bl; vmf[1].p = 0;                 // origin
             sm_vmf[g] = 2;
@@ -151,7 +183,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                 else k3_boundary_col(p, A, B, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
             }
         }
-        if (t == TG / 2 && role == (SPLIT ? 1 : 0)) {
+        if (t == TG / 2 && role == (SPLIT ? 1 : 0) && crank == 0) {
             k3_setval(rowH, 0); k3_setdg(rowH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(rowH) = 1;
             const int rr = LS < p.up ? LS : p.up;
             for (int k = 1; k <= rr; ++k) {
@@ -160,7 +192,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
             }
         }
         GSYNC();
-        if (want_last && t == 0 && role == 0) {
+        if (want_last && t == 0 && role == 0 && crank == 0) {
             k3_copy(p, lastC, rowH + (size_t)LS * st);              // black unless the band reaches it
             k3_copy(p, lastR, colH + (size_t)LQ * st);
         }
@@ -175,15 +207,15 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
         //      slot of the parked record (stripe k, index i) = (k*P + i) % RING: thread 0 reads slots S, S+1
         //      at step S while slot S+3 is being filled.
         {
-            const int P = LS > TG + 4 ? LS : TG + 4;
-            const int npass = (LQ + TG - 1) / TG;
-            const int rows_last = LQ - (npass - 1) * TG;
+            const int P = LS > TGC + 4 ? LS : TGC + 4;
+            const int npass = (LQ + TGC - 1) / TGC;
+            const int rows_last = LQ - (npass - 1) * TGC;
             const int total_steps = (npass - 1) * P + (rows_last - 1) + LS;
             int* const f1 = F1 + (size_t)t * st;
             int* const f2 = F2 + (size_t)t * st;
             double pua = 0;
             // ring: records 1 and 2 of the first parked row (the boundary row) before the first step
-            if (ring_ok && role == 0) {
+            if (ring_ok && role == 0 && crank == 0) {
                 for (int w = t; w < pf_words; w += TG) {
                     const int pa = w / st, pw = w - pa * st;
                     const int* src = pa == 0 ? rowH : (pa == 1 ? rowG : rowG2);
@@ -200,20 +232,25 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
 #pragma unroll
             for (int q = 0; q < PFN; ++q) {
                 const int w = t + q * TG;
-                pf_on[q] = ring_ok && w < pf_words && role == (SPLIT ? 2 : 0);
+                pf_on[q] = ring_ok && w < pf_words && role == (SPLIT ? 2 : 0) && crank == 0;
                 const int pa = w / st, pw = w - pa * st;
                 pf_src[q] = (pa == 0 ? rowH : (pa == 1 ? rowG : rowG2)) + pw;
                 pf_dst[q] = (pa == 0 ? ringH : (pa == 1 ? ringG : ringG2)) + pw;
             }
             // this thread's position: q = S - t = k*P + n
-            int k = 0, n = -t, m = t;
+            const int gt = crank * TG + t;                  // row slot of this thread inside the alignment
+            int k = 0, n = -gt, m = gt;
+            // CL: the same records in the previous CTA of the cluster (its last thread is the row above)
+            const int* const nbH = CL && crank > 0 ? cg::this_cluster().map_shared_rank(pubH, crank - 1) : pubH;
+            const int* const nbG = CL && crank > 0 ? cg::this_cluster().map_shared_rank(pubG, crank - 1) : pubG;
+            const int* const nbG2 = CL && crank > 0 ? cg::this_cluster().map_shared_rank(pubG2, crank - 1) : pubG2;
             // thread 0's position two steps ahead (what the ring must hold by then)
             int k2 = 0, n2 = 2;
             if (n2 >= P) { n2 -= P; ++k2; }
             for (int S = 0; S < total_steps; ++S) {
                 // prefetch the parked record thread 0 reads as "above" at step S + 2: index n2 + 1 of stripe k2 - 1
                 int pf_val[PFN];
-                const bool pf_now = ring_ok && n2 < LS && k2 * TG < LQ;
+                const bool pf_now = ring_ok && n2 < LS && k2 * TGC < LQ;
                 if (pf_now) {
 #pragma unroll
                     for (int q = 0; q < PFN; ++q)
@@ -237,6 +274,22 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                     const int* parkedH1 = ring_ok ? ringH + (size_t)((seq + 1) % RING) * st : rowH + (size_t)(n + 1) * st;
                     const int* parkedG1 = ring_ok ? ringG + (size_t)((seq + 1) % RING) * st : rowG + (size_t)(n + 1) * st;
                     const int* parkedG21 = ring_ok ? ringG2 + (size_t)((seq + 1) % RING) * st : rowG2 + (size_t)(n + 1) * st;
+                    if (CL && crank > 0) {
+                        // the row above lives in the previous CTA: copy what its last thread published one (above) and
+                        // two (diagonal) steps ago into local records
+                        parkedH0 = xbuf; parkedH1 = xbuf + st; parkedG1 = xbuf + 2 * st; parkedG21 = xbuf + 3 * st;
+                        if (t == 0) {
+                            const size_t last = (size_t)(TG - 1) * st;
+                            const bool all4 = MODE == 3;            // the Aln2b1 cell is not split over roles
+                            if (role == 0 && n > 0)
+                                for (int w = 0; w < st; w += 2) *reinterpret_cast<int2*>(xbuf + w) = *reinterpret_cast<const int2*>(nbH + (size_t)g3d * TG * st + last + w);
+                            if (role == (all4 ? 0 : 1)) {
+                                for (int w = 0; w < st; w += 2) *reinterpret_cast<int2*>(xbuf + st + w) = *reinterpret_cast<const int2*>(nbH + (size_t)g3a * TG * st + last + w);
+                                for (int w = 0; w < st; w += 2) *reinterpret_cast<int2*>(xbuf + 2 * st + w) = *reinterpret_cast<const int2*>(nbG + (size_t)g2a * TG * st + last + w);
+                                if (n3) for (int w = 0; w < st; w += 2) *reinterpret_cast<int2*>(xbuf + 3 * st + w) = *reinterpret_cast<const int2*>(nbG2 + (size_t)g2a * TG * st + last + w);
+                            }
+                        }
+                    }
                     // boundary column: H(m-1, -1) and H(m, -1).  SM: one row starts per step; its two boundary records
                     // come to shared memory first, so that every operand of the cell is a shared-memory record
                     int* const cb = colbuf + (size_t)(S & 1) * 2 * st;
@@ -281,8 +334,10 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                 }
                 if (active && role == 0) {
                     if (rec) {
-                        const int id = atomicAdd(&sm_vmf[g], 1);    // Vmf::add (fwd2c.h:465-467)
-                        if (id < a.vmf_cap) { vmf[id].m = m + P_.al; vmf[id].n = n + P_.bl; vmf[id].p = K3_PTR(hout); }
+                        int id = atomicAdd(&sm_vmf[g], 1);          // Vmf::add (fwd2c.h:465-467)
+                        const bool fits = id < a.vmf_cap;
+                        if (CL) { if (!fits) ghdr[1] = 1; id += crank * a.vmf_cap; }
+                        if (fits) { vmf[id].m = m + P_.al; vmf[id].n = n + P_.bl; vmf[id].p = K3_PTR(hout); }
                         K3_PTR(hout) = id;
                     }
                     if (want_last) {
@@ -290,8 +345,11 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                         if (m == LQ - 1) k3_copy(p, lastR + (size_t)(n + 1) * st, hout);
                     }
                     if (m == LQ - 1) {
-                        if (n == LS - 1) { sm_last_ptr[g] = K3_PTR(hout); sm_last_val[g] = k3_val(hout); }
-                    } else if (t == TG - 1) {                       // bottom row of a stripe: park it
+                        if (n == LS - 1) {
+                            if (CL) { ghdr[0] = K3_PTR(hout); *reinterpret_cast<double*>(ghdr + 2) = k3_val(hout); }
+                            else { sm_last_ptr[g] = K3_PTR(hout); sm_last_val[g] = k3_val(hout); }
+                        }
+                    } else if (t == TG - 1 && crank == NC - 1) {    // bottom row of a stripe: park it
                         k3_copy(p, rowH + (size_t)(n + 1) * st, hout);
                         k3_copy(p, rowG + (size_t)(n + 1) * st, gout);
                         if (n3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
@@ -304,14 +362,18 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                         if (pf_on[q]) pf_dst[q][(size_t)slot * st] = pf_val[q];
                 }
                 // advance the two positions
-                if (++n == P) { n = 0; ++k; m += TG; }
+                if (++n == P) { n = 0; ++k; m += TGC; }
                 if (++n2 == P) { n2 = 0; ++k2; }
                 GSYNC();
             }
         }
         // ---- Aln2b1::lastB_ng (fwd2b1.cc:100-143): trailing gaps at true sequence ends cost rtgapf times the
         //      penalty: the last column is relaxed downwards, then the last row rightwards, in place
-        if (want_last && t == 0 && role == 0) {
+        if (CL && t == 0 && role == 0 && crank == 0) {            // the last cell was written by some CTA of the cluster
+            sm_last_ptr[g] = __ldcg(ghdr);
+            sm_last_val[g] = __ldcg(reinterpret_cast<const double*>(ghdr + 2));
+        }
+        if (want_last && t == 0 && role == 0 && crank == 0) {
             __threadfence();
             int dm = 0, dn = 0;
             if (p.last_c) {
@@ -351,11 +413,11 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
             sm_last_val[g] = k3_val(h9);
         }
         // ---- final record + Vmf::traceback (fwd2c.h:475-481, vmf.cc:103-119)
-        if (t == 0 && role == 0) {
+        if (t == 0 && role == 0 && crank == 0) {
             int* out = a.out_pts + 2 * P_.out_off;
             int cnt = 0;
             const int nrec = sm_vmf[g];
-            if (nrec >= a.vmf_cap) cnt = -1;                        // record store overflow: reported, never silent
+            if (nrec >= a.vmf_cap || (CL && __ldcg(ghdr + 1))) cnt = -1;    // record store overflow: reported, never silent
             else {
                 out[0] = LQ + P_.al; out[1] = LS + P_.bl; cnt = 1;
                 for (int q = sm_last_ptr[g];; q = vmf[q].p) {
@@ -374,7 +436,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
 template <int TG, bool SPLIT, int MODE, bool SM>
 cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     // The gap-profile lists and score rows stream through L1.  Few pairs (latency: Prrn::best_of_n sized
     // batches): one CTA per SM and the rest of the unified array as L1 (measured 28 vs 37 ms for 24
@@ -383,15 +445,49 @@ cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
     int carve = grid_blocks > 148 ? 100 : (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
     if (const char* cv = getenv("PG_K3_CARVEOUT")) carve = atoi(cv);
     if (carve > 100) carve = 100;
-    e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return e;
-    k3_fill_kernel<TG, SPLIT, MODE, SM><<<grid_blocks, SPLIT ? 3 * CTA : CTA, a.smem_bytes, st>>>(a);
+    k3_fill_kernel<TG, SPLIT, MODE, SM, false><<<grid_blocks, SPLIT ? 3 * CTA : CTA, a.smem_bytes, st>>>(a);
     return cudaGetLastError();
+}
+
+// cluster variant: `clusters` alignments in flight, a.cluster CTAs each
+template <int MODE>
+cudaError_t launch_cluster(const K3Args& a, int clusters, cudaStream_t st)
+{
+    auto kern = k3_fill_kernel<CTA, true, MODE, true, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    if (e != cudaSuccess) return e;
+    int carve = (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
+    if (const char* cv = getenv("PG_K3_CARVEOUT")) carve = atoi(cv);
+    if (carve > 100) carve = 100;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(clusters * a.cluster));
+    cfg.blockDim = dim3(3 * CTA);
+    cfg.dynamicSmemBytes = (size_t)a.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)a.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 template <int TG, bool SPLIT, bool SM>
 cudaError_t launch_tg(const K3Args& a, int mode, int grid_blocks, cudaStream_t st)
 {
+    if (SPLIT && SM && a.cluster > 1) {
+        switch (mode) {
+        case 0: return launch_cluster<0>(a, grid_blocks, st);
+        case 1: return launch_cluster<1>(a, grid_blocks, st);
+        case 2: return launch_cluster<2>(a, grid_blocks, st);
+        case 3: return launch_cluster<3>(a, grid_blocks, st);
+        default: return launch_cluster<4>(a, grid_blocks, st);
+        }
+    }
     switch (mode) {
     case 0: return launch_tgm<TG, SPLIT, 0, SM>(a, grid_blocks, st);
     case 1: return launch_tgm<TG, SPLIT, 1, SM>(a, grid_blocks, st);

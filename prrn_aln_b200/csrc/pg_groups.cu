@@ -219,20 +219,45 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
     const int grid = (int)std::min<int64_t>((npairs + ngrp - 1) / ngrp, (int64_t)c->sm_count * k3_blocks_per_sm());
     // arenas / path stores: the kernels of the record modes present run side by side, each on its own slots
     int64_t n_mode[5] = {0, 0, 0, 0, 0};
-    int g_mode[5], slot0_mode[5];
-    for (int64_t i = 0; i < npairs; ++i) ++n_mode[pairs[i].prm.mode];
-    size_t slots = 0;
+    int g_mode[5], slot0_mode[5], nc_mode[5], vslot0_mode[5], maxlq_mode[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = 0; i < npairs; ++i) {
+        ++n_mode[pairs[i].prm.mode];
+        maxlq_mode[pairs[i].prm.mode] = std::max(maxlq_mode[pairs[i].prm.mode], a[i].right - a[i].left);
+    }
+    // latency mode: a thread-block cluster of 2 / 4 / 8 CTAs per alignment (256 rows each), as many as the longest
+    // group of the mode needs and the SMs can hold at once (PG_K3_CLUSTER=1 turns it off)
+    {
+        const char* ce = getenv("PG_K3_CLUSTER");
+        const int cmax = tg_sel == 768 ? (ce ? atoi(ce) : 8) : 1;
+        int64_t ctas = 0;
+        for (int m5 = 0; m5 < 5; ++m5) {
+            int nc = 1;
+            while (nc < cmax && nc < 8 && maxlq_mode[m5] > nc * 256) nc *= 2;
+            nc_mode[m5] = n_mode[m5] ? nc : 1;
+            ctas += n_mode[m5] * nc_mode[m5];
+        }
+        while (ctas > c->sm_count) {            // more clusters than SMs: halve the widest ones
+            int w = 0;
+            for (int m5 = 1; m5 < 5; ++m5) if (nc_mode[m5] > nc_mode[w]) w = m5;
+            if (nc_mode[w] == 1) break;
+            ctas -= n_mode[w] * (nc_mode[w] / 2);
+            nc_mode[w] /= 2;
+        }
+    }
+    size_t slots = 0, vslots = 0;
     for (int m5 = 0; m5 < 5; ++m5) {
         g_mode[m5] = (int)std::min<int64_t>((n_mode[m5] + ngrp - 1) / ngrp, grid);
         slot0_mode[m5] = (int)slots;
+        vslot0_mode[m5] = (int)vslots;
         slots += (size_t)g_mode[m5] * ngrp;
+        vslots += (size_t)g_mode[m5] * ngrp * nc_mode[m5];      // path store: one part per CTA of a cluster
     }
     const int64_t vmf_cap = max_cells + 8;
-    if (vmf_cap > 0x7fffffff) { free(offs); return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: DP matrix too large for the path store"); }
+    if (vmf_cap * 8 > 0x7fffffff) { free(offs); return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: DP matrix too large for the path store"); }
 
     // ---- stage
     int rc = pg_int_ensure_cap(c, &c->d_garena, &c->garena_cap, arena_words * 4 * slots);
-    if (!rc) rc = pg_int_ensure_cap(c, &c->d_gvmf, &c->gvmf_cap, sizeof(K3Vmf) * (size_t)vmf_cap * slots);
+    if (!rc) rc = pg_int_ensure_cap(c, &c->d_gvmf, &c->gvmf_cap, sizeof(K3Vmf) * (size_t)vmf_cap * vslots);
     const size_t o_pts = 0, o_cnt = up16(o_pts + 8 * (size_t)outoff[npairs]), o_scr = up16(o_cnt + 4 * (size_t)npairs),
                  obytes = up16(o_scr + 8 * (size_t)npairs);
     if (!rc) rc = pg_int_ensure_cap(c, &c->d_gout, &c->gout_cap, obytes);
@@ -343,7 +368,8 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
             km.all_sm = k3_sm_fits(k3_stride(sorted[k].prm.capa, sorted[k].prm.capb), sorted[k].prm.Noll, tg_sel,
                                    (size_t)ka.smem_bytes) ? 1 : 0;
         km.arena = ka.arena + (size_t)slot0_mode[mode] * arena_words;
-        km.vmf = ka.vmf + (size_t)slot0_mode[mode] * (size_t)vmf_cap;
+        km.vmf = ka.vmf + (size_t)vslot0_mode[mode] * (size_t)vmf_cap;
+        km.cluster = nc_mode[mode];
         e = cudaStreamWaitEvent(c->aux[mode], c->ev_fork, 0);
         if (e == cudaSuccess) e = k3_launch(km, tg_sel, mode, gm, c->aux[mode]);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev_join[mode], c->aux[mode]);

@@ -18,7 +18,23 @@
 #include "fwd2c.h"
 #include "prrn_gpu.h"
 
+#include <chrono>
+#include <cstdlib>
 #include <vector>
+
+// PRRN_GPU_STATS=1: calls / seconds per route, printed to stderr at exit (where does a prrn run spend its time?)
+struct PgStats {
+	long	n_gpu, n_ref; double t_stage, t_gpu, t_ref, kernel_ms; long cells;
+	bool	on;
+	PgStats() : n_gpu(0), n_ref(0), t_stage(0), t_gpu(0), t_ref(0), kernel_ms(0), cells(0), on(getenv("PRRN_GPU_STATS") != 0) {}
+	~PgStats() {
+	    if (on) fprintf(stderr, "prrn_gpu alignC: %ld calls on the GPU (staging %.2f s, pg_align_groups %.2f s of which "
+		"kernels %.2f s, %.3g cells), %ld calls left on the reference's Fwd2c (%.2f s)\n",
+		n_gpu, t_stage, t_gpu, kernel_ms * 1e-3, (double) cells, n_ref, t_ref);
+	}
+};
+static PgStats	pg_stats;
+static double	pg_now() {return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();}
 
 static pg_context* pg_ctx_groups()
 {
@@ -108,10 +124,13 @@ static SKL* pg_alignC(mSeq* seqs[], PwdM* pwd, VTYPE* scr, bool rectangle, WINDO
 			 pwd->alnmode == RHF_ALB || pwd->alnmode == GPF_ALB ||
 			 (pwd->alnmode == NTV_ALB && !seqs[0]->inex.nils && !seqs[1]->inex.nils &&
 			  seqs[0]->many <= 32 && seqs[1]->many <= 32);
+	const double	t0 = pg_stats.on? pg_now(): 0;
 	if (rectangle || pwdw || !banded || (algmode.lcl & 16)) {	// not built yet: the reference's own Fwd2c
 	    Fwd2c<recd_t>	pwa(seqs, pwd, true, rectangle, pwdw);
 	    *scr = rectangle? pwa.forwardA(0): pwa.forwardB(0);
-	    return pwa.traceback();
+	    SKL*	r = pwa.traceback();
+	    if (pg_stats.on) {++pg_stats.n_ref; pg_stats.t_ref += pg_now() - t0;}
+	    return r;
 	}
 	PgSide	A, B;
 	pg_stage(seqs[0], A, pwd, true, pwd->simmtx);
@@ -126,8 +145,14 @@ static SKL* pg_alignC(mSeq* seqs[], PwdM* pwd, VTYPE* scr, bool rectangle, WINDO
 	double	s = 0;
 	int64_t*	offs = 0;
 	pg_skl*	pts = 0;
+	const double	t1 = pg_stats.on? pg_now(): 0;
 	if (pg_align_groups(pg_ctx_groups(), &ga, &gb, &gp, 1, &s, &offs, &pts) != PG_OK)
 	    fatal("prrn_gpu alignC: %s\n", pg_last_error(pg_ctx_groups()));
+	if (pg_stats.on) {
+	    ++pg_stats.n_gpu; pg_stats.t_stage += t1 - t0; pg_stats.t_gpu += pg_now() - t1;
+	    pg_stats.kernel_ms += pg_last_kernel_ms(pg_ctx_groups());
+	    pg_stats.cells += (long) pg_group_cells(&ga, &gb, gp.sh);
+	}
 	*scr = (VTYPE) s;
 	int	n = (int) offs[1];
 	SKL*	skl = new SKL[n + 1];		// callers delete[] it (src/maln2.cc:1923,1948)
