@@ -56,16 +56,31 @@ __device__ __forceinline__ void group_sync(int g)
     else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(TG) : "memory");
 }
 
-// Cluster barrier of the per-step hand-off.  cg::cluster_group::sync() is arrive.release + wait.acquire at cluster
-// scope, for which ptxas emits an L1 invalidate (CCTL.IVALL) -- every step would throw away the gap-profile lists
-// the latency mode keeps in L1.  What crosses CTAs here is (a) shared-memory records read through DSMEM one
-// barrier after they were written and (b) parked rows in global memory read with ld.global.cg (L2) hundreds of
-// steps later, so the barrier is used relaxed with a CTA-scope fence in front (PG_K3_CLUSTER_FENCE=1 selects
-// the fully fenced form; results are identical in both, see tests).
-__device__ __forceinline__ void cluster_step_sync()
+// Per-step hand-shake of the cluster variant.  A cluster-wide barrier per anti-diagonal is too expensive here
+// (measured: steps fall 2.6x with 8 CTAs, time only 1.3x; its acquire also invalidates L1, CCTL.IVALL, where the
+// latency mode keeps the gap-profile lists).  Only NEIGHBOURS exchange data, so each CTA owns two mbarriers:
+// [0] counts the arrival of the CTA above, [1] of the CTA below (two sets, used by alternate steps, so that an
+// arrival for step S + 2 can never be mistaken for step S); after its own __syncthreads ONE thread arrives
+// (release, cluster scope) on the neighbours' barriers through DSMEM and waits for both neighbours of the same
+// step, then a second __syncthreads releases the CTA.  Neighbours therefore never differ by more than the step in progress, which is what the
+// three H generations need; CTAs further apart may be up to NC - 1 steps apart (the period P allows for it).
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count)
 {
-    __threadfence_block();
-    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_remote_arrive(unsigned local_addr, unsigned rank)
+{
+    asm volatile("{ .reg .b32 ra; mapa.shared::cluster.u32 ra, %0, %1; "
+                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra]; }" ::"r"(local_addr), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
 }
 
 // TG threads per alignment: the whole CTA for few pairs (latency), down to one warp per alignment for
@@ -105,7 +120,31 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
     int* const sm_grp = sm_dyn + (size_t)g * (a.smem_bytes / 4 / NG);
     const size_t sm_grp_words = (size_t)(a.smem_bytes / 4 / NG);
 
-#define GSYNC() do { if (CL) cluster_step_sync(); else if (SPLIT) __syncthreads(); else group_sync<TG>(g); } while (0)
+#define GSYNC() do { if (CL) cg::this_cluster().sync(); else if (SPLIT) __syncthreads(); else group_sync<TG>(g); } while (0)
+    // CL: neighbour hand-shake of one step (see mbar_* above)
+    __shared__ __align__(8) unsigned long long sm_mb[4];       // [set][0 from above, 1 from below]
+    unsigned mb_step = 0;                                       // steps synchronised so far (all pairs)
+    if (CL) {
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < 4; ++i) mbar_init(smem_addr(&sm_mb[i]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cg::this_cluster().sync();
+    }
+#define STEP_SYNC() do { \
+        if (CL) { \
+            __syncthreads(); \
+            if (threadIdx.x == 0) { \
+                const unsigned set = (mb_step & 1u) * 2u, par = (mb_step >> 1) & 1u; \
+                if (crank > 0) mbar_remote_arrive(smem_addr(&sm_mb[set + 1]), (unsigned)(crank - 1)); \
+                if (crank < NC - 1) mbar_remote_arrive(smem_addr(&sm_mb[set]), (unsigned)(crank + 1)); \
+                if (crank > 0) mbar_wait(smem_addr(&sm_mb[set]), par); \
+                if (crank < NC - 1) mbar_wait(smem_addr(&sm_mb[set + 1]), par); \
+            } \
+            ++mb_step; \
+            __syncthreads(); \
+        } else GSYNC(); \
+    } while (0)
     for (;;) {
         if (t == 0 && role == 0 && crank == 0) sm_pair[g] = atomicAdd(a.counter, 1);
         GSYNC();
@@ -207,7 +246,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
         //      slot of the parked record (stripe k, index i) = (k*P + i) % RING: thread 0 reads slots S, S+1
         //      at step S while slot S+3 is being filled.
         {
-            const int P = LS > TGC + 4 ? LS : TGC + 4;
+            const int PMIN = TGC + 4 + (CL ? NC : 0);      // CL: CTA 0 may run up to NC - 1 steps ahead of the last CTA
+            const int P = LS > PMIN ? LS : PMIN;
             const int npass = (LQ + TGC - 1) / TGC;
             const int rows_last = LQ - (npass - 1) * TGC;
             const int total_steps = (npass - 1) * P + (rows_last - 1) + LS;
@@ -262,6 +302,27 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                 int* hout = pubH + ((size_t)(S % 3) * TG + t) * st;
                 int* gout = pubG + ((size_t)(S & 1) * TG + t) * st;
                 int* g2out = pubG2 + ((size_t)(S & 1) * TG + t) * st;
+                if (CL && crank > 0 && t < 32) {
+                    // the row above the first row of this CTA lives in the previous CTA: the first warp of a role copies
+                    // what that CTA's last thread published one (above) and two (diagonal) steps ago into local records,
+                    // one 8-byte word per lane (a single remote round trip instead of st / 2 dependent ones)
+                    const int n0 = n + t, m0 = m - t, r0 = n0 - m0;                // position of thread 0 of this CTA
+                    if (n0 >= 0 && n0 < LS && m0 < LQ && r0 >= p.lw && r0 <= p.up) {
+                        const int g3a_ = (S + 2) % 3, g3d_ = (S + 1) % 3, g2a_ = (S + 1) & 1;
+                        const size_t last = (size_t)(TG - 1) * st;
+                        const bool all4 = MODE == 3;                            // the Aln2b1 cell is not split over roles
+                        for (int w = 2 * t; w < st; w += 64) {
+                            if (role == 0 && n0 > 0)
+                                *reinterpret_cast<int2*>(xbuf + w) = *reinterpret_cast<const int2*>(nbH + (size_t)g3d_ * TG * st + last + w);
+                            if (role == (all4 ? 0 : 1)) {
+                                *reinterpret_cast<int2*>(xbuf + st + w) = *reinterpret_cast<const int2*>(nbH + (size_t)g3a_ * TG * st + last + w);
+                                *reinterpret_cast<int2*>(xbuf + 2 * st + w) = *reinterpret_cast<const int2*>(nbG + (size_t)g2a_ * TG * st + last + w);
+                                if (n3) *reinterpret_cast<int2*>(xbuf + 3 * st + w) = *reinterpret_cast<const int2*>(nbG2 + (size_t)g2a_ * TG * st + last + w);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
                 if (active) {
                     const int ia = m + 1, ib = n + 1;
                     if (n == 0 || r == p.lw) {                      // first in-band column of this row
@@ -274,22 +335,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                     const int* parkedH1 = ring_ok ? ringH + (size_t)((seq + 1) % RING) * st : rowH + (size_t)(n + 1) * st;
                     const int* parkedG1 = ring_ok ? ringG + (size_t)((seq + 1) % RING) * st : rowG + (size_t)(n + 1) * st;
                     const int* parkedG21 = ring_ok ? ringG2 + (size_t)((seq + 1) % RING) * st : rowG2 + (size_t)(n + 1) * st;
-                    if (CL && crank > 0) {
-                        // the row above lives in the previous CTA: copy what its last thread published one (above) and
-                        // two (diagonal) steps ago into local records
-                        parkedH0 = xbuf; parkedH1 = xbuf + st; parkedG1 = xbuf + 2 * st; parkedG21 = xbuf + 3 * st;
-                        if (t == 0) {
-                            const size_t last = (size_t)(TG - 1) * st;
-                            const bool all4 = MODE == 3;            // the Aln2b1 cell is not split over roles
-                            if (role == 0 && n > 0)
-                                for (int w = 0; w < st; w += 2) *reinterpret_cast<int2*>(xbuf + w) = *reinterpret_cast<const int2*>(nbH + (size_t)g3d * TG * st + last + w);
-                            if (role == (all4 ? 0 : 1)) {
-                                for (int w = 0; w < st; w += 2) *reinterpret_cast<int2*>(xbuf + st + w) = *reinterpret_cast<const int2*>(nbH + (size_t)g3a * TG * st + last + w);
-                                for (int w = 0; w < st; w += 2) *reinterpret_cast<int2*>(xbuf + 2 * st + w) = *reinterpret_cast<const int2*>(nbG + (size_t)g2a * TG * st + last + w);
-                                if (n3) for (int w = 0; w < st; w += 2) *reinterpret_cast<int2*>(xbuf + 3 * st + w) = *reinterpret_cast<const int2*>(nbG2 + (size_t)g2a * TG * st + last + w);
-                            }
-                        }
-                    }
+                    if (CL && crank > 0) { parkedH0 = xbuf; parkedH1 = xbuf + st; parkedG1 = xbuf + 2 * st; parkedG21 = xbuf + 3 * st; }
                     // boundary column: H(m-1, -1) and H(m, -1).  SM: one row starts per step; its two boundary records
                     // come to shared memory first, so that every operand of the cell is a shared-memory record
                     int* const cb = colbuf + (size_t)(S & 1) * 2 * st;
@@ -364,8 +410,9 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                 // advance the two positions
                 if (++n == P) { n = 0; ++k; m += TGC; }
                 if (++n2 == P) { n2 = 0; ++k2; }
-                GSYNC();
+                STEP_SYNC();
             }
+            if (CL) cg::this_cluster().sync();      // the last cell, the path parts and the parked rows of every CTA
         }
         // ---- Aln2b1::lastB_ng (fwd2b1.cc:100-143): trailing gaps at true sequence ends cost rtgapf times the
         //      penalty: the last column is relaxed downwards, then the last row rightwards, in place
