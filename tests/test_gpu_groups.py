@@ -138,3 +138,37 @@ def test_tiny_windows_match_oracle(ctx, oracle):
             s1, p1 = ctx.align_groups([(A, B, gp)])
             assert abs(s1[0] - want_s) <= REL_TOL * max(1.0, abs(want_s)), (la, lb)
             assert [tuple(x) for x in p1[0].tolist()] == want_p, (la, lb)
+
+
+def test_cluster_latency_kernel_matches_reference(ctx, monkeypatch):
+    """Groups of ~1,100 columns in a latency-sized batch: K3 runs them on thread-block clusters (2 / 4 / 8 CTAs per
+    alignment, rows handed from CTA to CTA through distributed shared memory).  Every score and corner list must
+    equal the reference's own alignC (oracle/_ref/ref_driver_d, test infrastructure), with the cluster variant,
+    with clusters capped at 2 CTAs and with the single-CTA kernel (PG_K3_CLUSTER=1)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import argparse
+    import bench_groups
+    import refio
+    if not refio.available("d"):
+        pytest.skip("oracle/_ref is not built")
+    args = argparse.Namespace(members=30, length=1050, pairs=4, seed=5, sh=-60, cpu_rep=1)
+    dumps = bench_groups.build_pairs(args)
+    staged = []
+    for d in dumps:
+        pm, pc, h = d["pwdm"], d["pwdc"], d["header"]
+        A, B = G.stage_pair(d["groups"][0], d["groups"][1], pm["a_mode"], pm["b_mode"], d["matrix"], dxd=(pm["DvsP"] == 0))
+        gp = P.gparams_from_pwd(pm["alnmode"], pm["Noll"], pm["codonk1"], int(h["sh"]), A["vec"].shape[1], float(h["u"]),
+                                float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
+        staged.append((A, B, gp))
+    assert max(int(s[0]["right"] - s[0]["left"]) for s in staged) > 256      # more rows than one CTA holds
+    for cap in (None, "2", "1"):
+        if cap is None:
+            monkeypatch.delenv("PG_K3_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("PG_K3_CLUSTER", cap)
+        for batch in (staged, staged[:1]):
+            scores, pts = ctx.align_groups(batch)
+            for k in range(len(batch)):
+                w = dumps[k]["alignc"]
+                assert abs(scores[k] - w["score"]) <= 1e-5 * max(1.0, abs(w["score"])), (cap, k)
+                assert pts[k].tolist() == w["skl"], (cap, k)
