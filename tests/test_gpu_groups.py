@@ -161,7 +161,7 @@ def test_cluster_latency_kernel_matches_reference(ctx, monkeypatch):
                                 float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
         staged.append((A, B, gp))
     assert max(int(s[0]["right"] - s[0]["left"]) for s in staged) > 256      # more rows than one CTA holds
-    for cap in (None, "2", "1"):
+    for cap in (None, "8", "2", "1"):
         if cap is None:
             monkeypatch.delenv("PG_K3_CLUSTER", raising=False)
         else:
