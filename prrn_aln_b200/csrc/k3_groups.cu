@@ -74,13 +74,25 @@ __device__ __forceinline__ void mbar_remote_arrive(unsigned local_addr, unsigned
     asm volatile("{ .reg .b32 ra; mapa.shared::cluster.u32 ra, %0, %1; "
                  "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra]; }" ::"r"(local_addr), "r"(rank) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity)
+// The wait acquires at CTA scope by default: what a neighbour hands over per step are shared-memory records, read
+// through DSMEM (never cached in L1) after this wait and a __syncthreads, and parked rows in global memory that are
+// read with ld.global.cg hundreds of steps later; a cluster-scope acquire makes ptxas invalidate L1 (CCTL.IVALL)
+// on every step, where the latency mode keeps the gap-profile lists (measured: prrn5 C3 kernels 22.8 s against
+// 25.1 s).  fenced = true (PG_K3_CLUSTER_FENCE=1) selects the cluster-scope form; the tests run both.
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity, bool fenced)
 {
     unsigned ok;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
+    if (fenced) {
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        } while (!ok);
+    } else {
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        } while (!ok);
+    }
 }
 
 // TG threads per alignment: the whole CTA for few pairs (latency), down to one warp per alignment for
@@ -138,8 +150,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                 const unsigned set = (mb_step & 1u) * 2u, par = (mb_step >> 1) & 1u; \
                 if (crank > 0) mbar_remote_arrive(smem_addr(&sm_mb[set + 1]), (unsigned)(crank - 1)); \
                 if (crank < NC - 1) mbar_remote_arrive(smem_addr(&sm_mb[set]), (unsigned)(crank + 1)); \
-                if (crank > 0) mbar_wait(smem_addr(&sm_mb[set]), par); \
-                if (crank < NC - 1) mbar_wait(smem_addr(&sm_mb[set + 1]), par); \
+                if (crank > 0) mbar_wait(smem_addr(&sm_mb[set]), par, a.cluster_fence != 0); \
+                if (crank < NC - 1) mbar_wait(smem_addr(&sm_mb[set + 1]), par, a.cluster_fence != 0); \
             } \
             ++mb_step; \
             __syncthreads(); \
@@ -503,6 +515,8 @@ template <int MODE>
 cudaError_t launch_cluster(const K3Args& a, int clusters, cudaStream_t st)
 {
     auto kern = k3_fill_kernel<CTA, true, MODE, true, true>;
+    K3Args ac = a;
+    { const char* f = getenv("PG_K3_CLUSTER_FENCE"); ac.cluster_fence = f && f[0] == '1'; }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     int carve = (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
@@ -520,7 +534,7 @@ cudaError_t launch_cluster(const K3Args& a, int clusters, cudaStream_t st)
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)a.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, a);
+    return cudaLaunchKernelEx(&cfg, kern, ac);
 }
 
 template <int TG, bool SPLIT, bool SM>

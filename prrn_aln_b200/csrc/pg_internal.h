@@ -166,6 +166,7 @@ struct K3Args {
     int32_t smem_bytes;         // dynamic shared memory per CTA for the wavefront records
     int32_t all_sm;             // every pair fits the all-shared-memory variant (k3_sm_fits)
     int32_t cluster;            // latency mode: CTAs (thread-block cluster size) per alignment, 1 = none
+    int32_t cluster_fence;      // cluster variant: cluster-scope acquire in the per-step hand-shake (PG_K3_CLUSTER_FENCE)
 };
 
 // profile contraction (k4_contract.cu): S = X_a . Y_b^T per pair, written to K3Pair::simmat
