@@ -541,13 +541,16 @@ template <int TG, bool SPLIT, bool SM>
 cudaError_t launch_tg(const K3Args& a, int mode, int grid_blocks, cudaStream_t st)
 {
     if (SPLIT && SM && a.cluster > 1) {
+        cudaError_t e;
         switch (mode) {
-        case 0: return launch_cluster<0>(a, grid_blocks, st);
-        case 1: return launch_cluster<1>(a, grid_blocks, st);
-        case 2: return launch_cluster<2>(a, grid_blocks, st);
-        case 3: return launch_cluster<3>(a, grid_blocks, st);
-        default: return launch_cluster<4>(a, grid_blocks, st);
+        case 0: e = launch_cluster<0>(a, grid_blocks, st); break;
+        case 1: e = launch_cluster<1>(a, grid_blocks, st); break;
+        case 2: e = launch_cluster<2>(a, grid_blocks, st); break;
+        case 3: e = launch_cluster<3>(a, grid_blocks, st); break;
+        default: e = launch_cluster<4>(a, grid_blocks, st); break;
         }
+        if (e == cudaSuccess) return e;
+        (void)cudaGetLastError();       // a cluster of this size cannot be co-scheduled here: the single-CTA kernel below
     }
     switch (mode) {
     case 0: return launch_tgm<TG, SPLIT, 0, SM>(a, grid_blocks, st);
