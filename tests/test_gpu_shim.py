@@ -39,6 +39,28 @@ def test_reference_driver_on_gpu_library(name, tmp_path):
         assert np.array_equal(ds["dist"], np.array(g["dist"])), "calcdist through the shim differs from the reference"
 
 
+def test_calcdist_batch_shim_is_one_library_call(tmp_path):
+    """shim/shim_calcdist.cc: the reference's calcdist(mSeq**, nn, DynScr) symbol itself is bound to the library, so
+    the driver's all-vs-all step is ONE pg_calcdist call (not nn(nn-1)/2 alnScoreD calls) and still returns the
+    reference's distance vector bit for bit; a mode the library refuses (lcl & 16) runs the reference's own
+    calcdist (calcdist_ref) and matches its golden too."""
+    import subprocess
+    g = golden("score_p24_blosum62")
+    fl = g["flavour"]
+    drv = refio.driver(fl, gpu=True)
+    if not os.path.exists(drv):
+        pytest.skip("oracle/_ref/ref_driver_%s_gpu is not built" % fl)
+    fa = str(tmp_path / "in.fa")
+    gen_synth.write_fasta(fa, g["seqs"])
+    env = dict(os.environ, ALN_TAB=os.path.join(refio.REFDIR, "table"), PRRN_GPU_STATS="1")
+    out = subprocess.run([drv, "dist", fa] + ["%s=%s" % kv for kv in g["args"].items()], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    n = len(g["seqs"])
+    assert "prrn_gpu calcdist: %d sequences, %d pairs in one pg_calcdist call" % (n, n * (n - 1) // 2) in out.stderr
+    assert np.array_equal(refio.parse(out.stdout)["dist"], np.array(g["dist"]))
+
+
 ALIGN_CASES = ["align_p16_blosum62", "align_p16_pam_f32", "align_p16_twopiece_f64", "align_ragged", "align_c1_ce13a"]
 
 
