@@ -33,11 +33,14 @@ namespace {
 constexpr int CTA = K3_THREADS;     // threads per CTA; an alignment gets TG of them (TG = 32 .. 256)
 constexpr int RING = 4;             // prefetch ring depth for the parked row (records n, n+1 are read at step n)
 constexpr int PFN = 4;              // prefetch words per thread (3 * stride <= PFN * TG, else no ring)
+constexpr int XD = 8;               // cluster variant: depth of the ring of neighbour records (steps a CTA may lead)
+constexpr int TGCL = 192;           // cluster variant: rows per CTA (3 x 192 = 576 threads leave 112 registers per thread;
+                                    // with 3 x 256 the extra hand-over state spilled into local memory: +2.4 us per step)
 
 // words of shared memory one alignment needs for its wavefront records
 __host__ __device__ inline size_t k3_smem_words(int st, int Noll, int tg)
 {
-    return (size_t)st * ((Noll == 3 ? 9 : 6) * tg + 1 + 3 * RING + 4 + 4);
+    return (size_t)st * ((Noll == 3 ? 9 : 6) * tg + 1 + 3 * RING + 4 + 3 * XD);
 }
 // SM variant of the kernel (every record operand of a cell lives in shared memory, so the compiler emits
 // LDS / STS with 32-bit addresses instead of generic loads): needs the wavefront records in shared memory
@@ -56,15 +59,25 @@ __device__ __forceinline__ void group_sync(int g)
     else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(TG) : "memory");
 }
 
-// Per-step hand-shake of the cluster variant.  A cluster-wide barrier per anti-diagonal is too expensive here
-// (measured: steps fall 2.6x with 8 CTAs, time only 1.3x; its acquire also invalidates L1, CCTL.IVALL, where the
-// latency mode keeps the gap-profile lists).  Only NEIGHBOURS exchange data, so each CTA owns two mbarriers:
-// [0] counts the arrival of the CTA above, [1] of the CTA below (two sets, used by alternate steps, so that an
-// arrival for step S + 2 can never be mistaken for step S); after its own __syncthreads ONE thread arrives
-// (release, cluster scope) on the neighbours' barriers through DSMEM and waits for both neighbours of the same
-// step, then a second __syncthreads releases the CTA.  Neighbours therefore never differ by more than the step in progress, which is what the
-// three H generations need; CTAs further apart may be up to NC - 1 steps apart (the period P allows for it).
+// Hand-over between the CTAs of a cluster.  A cluster-wide barrier (or a neighbour hand-shake) per anti-diagonal
+// keeps all NC x 256 rows in lock step, and a step then lasts as long as the slowest of ~1,000 cells (measured:
+// 6-7 us against 3.5 us of one CTA).  The CTAs are therefore decoupled: CTA c PUSHES the records of its last row
+// into a ring of XD slots in the shared memory of CTA c+1 (plain DSMEM stores by one warp, then
+// mbarrier.arrive.release.cluster on that CTA's full[slot]); CTA c+1 waits for full[(S-1) % XD] when its first
+// row needs step S-1 of the row above, and returns the slot with a remote arrive on empty[] once it has used it
+// as "above" (step +1) and "diagonal" (step +2).  A CTA may lead its successor by XD - 2 steps; inside a CTA
+// the usual two block barriers per step remain.
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// rank / size of the cluster straight from the special registers (pure: the compiler re-reads them instead of
+// keeping -- and spilling -- loop-invariant copies; the cluster kernel runs at the 80-register limit)
+__device__ __forceinline__ int cl_rank() { unsigned r; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return (int)r; }
+__device__ __forceinline__ int cl_size() { unsigned r; asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return (int)r; }
+// 8-byte store into the shared memory of another CTA of the cluster (address of the same variable here + rank)
+__device__ __forceinline__ void st_remote_v2(unsigned local_addr, unsigned rank, int2 v)
+{
+    asm volatile("{ .reg .b32 ra; mapa.shared::cluster.u32 ra, %0, %1; st.shared::cluster.v2.u32 [ra], {%2, %3}; }"
+                 ::"r"(local_addr), "r"(rank), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ void mbar_init(unsigned addr, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
@@ -95,6 +108,34 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity, bool f
     }
 }
 
+// CL, end of step S, last warp of role 0: push the last row (H, G, G2 records of thread 255) into slot S % XD of the
+// CTA below once that slot is free again, then signal it.  Not inlined: its temporaries must not lengthen live
+// ranges inside the per-cell code (the kernel sits at the 80-register limit).
+__device__ __noinline__ void cl_push(const int* srcH, const int* srcG, const int* srcG2, unsigned ring_addr, unsigned full_addr,
+                                     unsigned empty_addr, int S, int st, int lane, bool fenced)
+{
+    const int xs = S % XD;
+    if (S >= XD && lane == 0) mbar_wait(empty_addr + 8u * xs, (unsigned)(S / XD - 1) & 1u, fenced);
+    __syncwarp();
+    const unsigned below = (unsigned)(cl_rank() + 1);
+    const unsigned dst = ring_addr + 4u * (unsigned)(xs * 3 * st);
+    for (int w = 2 * lane; w < st; w += 64) {
+        st_remote_v2(dst + 4 * w, below, *reinterpret_cast<const int2*>(srcH + w));
+        st_remote_v2(dst + 4 * (st + w), below, *reinterpret_cast<const int2*>(srcG + w));
+        if (srcG2) st_remote_v2(dst + 4 * (2 * st + w), below, *reinterpret_cast<const int2*>(srcG2 + w));
+    }
+    __syncwarp();
+    if (lane == 0) mbar_remote_arrive(full_addr + 8u * xs, below);
+}
+__device__ __noinline__ void cl_wait_above(unsigned full_addr, int S, bool fenced)
+{
+    mbar_wait(full_addr + 8u * (unsigned)((S - 1) % XD), (unsigned)((S - 1) / XD) & 1u, fenced);
+}
+__device__ __noinline__ void cl_release(unsigned empty_addr, int S)
+{
+    mbar_remote_arrive(empty_addr + 8u * (unsigned)((S - 2) % XD), (unsigned)(cl_rank() - 1));
+}
+
 // TG threads per alignment: the whole CTA for few pairs (latency), down to one warp per alignment for
 // large batches (no block barrier at all, 95 % of the lane-steps inside the matrix instead of 72 %).
 // SPLIT (latency mode, TG = 256 only): three threads per row -- the diagonal, vertical and horizontal
@@ -110,14 +151,15 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity, bool f
 // slot, so the cell code still sees shared-memory records); every step ends in a cluster barrier; the path
 // records of CTA c live in its own part of the store (id = c * vmf_cap + local id).
 template <int TG, bool SPLIT, int MODE, bool SM, bool CL>
-__global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_kernel(const K3Args a)
+__global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_kernel(const K3Args a)
 {
-    static_assert(!CL || (SPLIT && SM && TG == CTA), "the cluster variant is the role-split shared-memory kernel");
+    static_assert(!CL || (SPLIT && SM), "the cluster variant is the role-split shared-memory kernel");
+    static_assert(!SPLIT || CL || TG == CTA, "role-split without clusters runs 3 x 256 threads");
     namespace cg = cooperative_groups;
     constexpr int NG = SPLIT ? 1 : CTA / TG;        // alignments in flight per CTA
-    const int NC = CL ? (int)cg::this_cluster().num_blocks() : 1;       // CTAs per alignment
-    const int crank = CL ? (int)cg::this_cluster().block_rank() : 0;
-    const int TGC = NC * TG;                        // rows in flight per alignment
+#define NC (CL ? cl_size() : 1)                     /* CTAs per alignment */
+#define crank (CL ? cl_rank() : 0)
+#define TGC (NC * TG)                               /* rows in flight per alignment */
     extern __shared__ __align__(16) int sm_dyn[];
     __shared__ int sm_pair[NG];
     __shared__ int sm_vmf[NG];
@@ -133,35 +175,20 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
     const size_t sm_grp_words = (size_t)(a.smem_bytes / 4 / NG);
 
 #define GSYNC() do { if (CL) cg::this_cluster().sync(); else if (SPLIT) __syncthreads(); else group_sync<TG>(g); } while (0)
-    // CL: neighbour hand-shake of one step (see mbar_* above)
-    __shared__ __align__(8) unsigned long long sm_mb[4];       // [set][0 from above, 1 from below]
-    unsigned mb_step = 0;                                       // steps synchronised so far (all pairs)
-    if (CL) {
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < 4; ++i) mbar_init(smem_addr(&sm_mb[i]), 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        cg::this_cluster().sync();
-    }
-#define STEP_SYNC() do { \
-        if (CL) { \
-            __syncthreads(); \
-            if (threadIdx.x == 0) { \
-                const unsigned set = (mb_step & 1u) * 2u, par = (mb_step >> 1) & 1u; \
-                if (crank > 0) mbar_remote_arrive(smem_addr(&sm_mb[set + 1]), (unsigned)(crank - 1)); \
-                if (crank < NC - 1) mbar_remote_arrive(smem_addr(&sm_mb[set]), (unsigned)(crank + 1)); \
-                if (crank > 0) mbar_wait(smem_addr(&sm_mb[set]), par, a.cluster_fence != 0); \
-                if (crank < NC - 1) mbar_wait(smem_addr(&sm_mb[set + 1]), par, a.cluster_fence != 0); \
-            } \
-            ++mb_step; \
-            __syncthreads(); \
-        } else GSYNC(); \
-    } while (0)
+#define GSTEP() do { if (SPLIT) __syncthreads(); else group_sync<TG>(g); } while (0)       /* end of one step */
+    // CL: ring hand-over (see above): full[slot] counts the push of the CTA above, empty[slot] the release by the CTA below
+    __shared__ __align__(8) unsigned long long sm_full[XD], sm_empty[XD];
     for (;;) {
         if (t == 0 && role == 0 && crank == 0) sm_pair[g] = atomicAdd(a.counter, 1);
         GSYNC();
         const int pi = CL ? *cg::this_cluster().map_shared_rank(&sm_pair[0], 0) : sm_pair[g];
-        if (CL) cg::this_cluster().sync();     // nobody leaves (or rewrites sm_pair) before every CTA has read it
+        if (CL) {
+            if (threadIdx.x == 0) {             // fresh barriers per alignment (every CTA runs the same number of steps)
+                for (int i = 0; i < XD; ++i) { mbar_init(smem_addr(&sm_full[i]), 1); mbar_init(smem_addr(&sm_empty[i]), 1); }
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            cg::this_cluster().sync();          // nobody leaves (or rewrites sm_pair) before every CTA has read it
+        }
         if (pi >= a.npairs) break;
         const K3Pair& P_ = a.pairs[pi];
         const K3Group A = P_.a;
@@ -199,8 +226,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
         int* const ringG2 = ringG + (size_t)RING * st;
         int* const black = ringG2 + (size_t)RING * st;
         int* const colbuf = black + st;                     // [2][2] boundary-column records of the row that starts (SM)
-        int* const xbuf = colbuf + (size_t)4 * st;          // [4] records of the neighbour CTA's last thread (CL)
-        int* const pubH = xbuf + (size_t)4 * st;            // [3][TG]
+        int* const xring = colbuf + (size_t)4 * st;         // [XD][3] H, G, G2 of the last row of the CTA above (CL)
+        int* const pubH = xring + (size_t)3 * XD * st;      // [3][TG]
         int* const pubG = pubH + (size_t)3 * TG * st;       // [2][TG]
         int* const F1 = pubG + (size_t)2 * TG * st;         // [TG]
         int* const pubG2 = F1 + (size_t)TG * st;            // [2][TG]   (two-piece only)
@@ -258,7 +285,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
         //      slot of the parked record (stripe k, index i) = (k*P + i) % RING: thread 0 reads slots S, S+1
         //      at step S while slot S+3 is being filled.
         {
-            const int PMIN = TGC + 4 + (CL ? NC : 0);      // CL: CTA 0 may run up to NC - 1 steps ahead of the last CTA
+            const int PMIN = TGC + 4 + (CL ? 4 + NC * XD : 0);     // CL: CTA 0 may lead the last CTA by (NC - 1) * (XD - 1) steps
             const int P = LS > PMIN ? LS : PMIN;
             const int npass = (LQ + TGC - 1) / TGC;
             const int rows_last = LQ - (npass - 1) * TGC;
@@ -293,9 +320,6 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
             const int gt = crank * TG + t;                  // row slot of this thread inside the alignment
             int k = 0, n = -gt, m = gt;
             // CL: the same records in the previous CTA of the cluster (its last thread is the row above)
-            const int* const nbH = CL && crank > 0 ? cg::this_cluster().map_shared_rank(pubH, crank - 1) : pubH;
-            const int* const nbG = CL && crank > 0 ? cg::this_cluster().map_shared_rank(pubG, crank - 1) : pubG;
-            const int* const nbG2 = CL && crank > 0 ? cg::this_cluster().map_shared_rank(pubG2, crank - 1) : pubG2;
             // thread 0's position two steps ahead (what the ring must hold by then)
             int k2 = 0, n2 = 2;
             if (n2 >= P) { n2 -= P; ++k2; }
@@ -314,27 +338,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                 int* hout = pubH + ((size_t)(S % 3) * TG + t) * st;
                 int* gout = pubG + ((size_t)(S & 1) * TG + t) * st;
                 int* g2out = pubG2 + ((size_t)(S & 1) * TG + t) * st;
-                if (CL && crank > 0 && t < 32) {
-                    // the row above the first row of this CTA lives in the previous CTA: the first warp of a role copies
-                    // what that CTA's last thread published one (above) and two (diagonal) steps ago into local records,
-                    // one 8-byte word per lane (a single remote round trip instead of st / 2 dependent ones)
-                    const int n0 = n + t, m0 = m - t, r0 = n0 - m0;                // position of thread 0 of this CTA
-                    if (n0 >= 0 && n0 < LS && m0 < LQ && r0 >= p.lw && r0 <= p.up) {
-                        const int g3a_ = (S + 2) % 3, g3d_ = (S + 1) % 3, g2a_ = (S + 1) & 1;
-                        const size_t last = (size_t)(TG - 1) * st;
-                        const bool all4 = MODE == 3;                            // the Aln2b1 cell is not split over roles
-                        for (int w = 2 * t; w < st; w += 64) {
-                            if (role == 0 && n0 > 0)
-                                *reinterpret_cast<int2*>(xbuf + w) = *reinterpret_cast<const int2*>(nbH + (size_t)g3d_ * TG * st + last + w);
-                            if (role == (all4 ? 0 : 1)) {
-                                *reinterpret_cast<int2*>(xbuf + st + w) = *reinterpret_cast<const int2*>(nbH + (size_t)g3a_ * TG * st + last + w);
-                                *reinterpret_cast<int2*>(xbuf + 2 * st + w) = *reinterpret_cast<const int2*>(nbG + (size_t)g2a_ * TG * st + last + w);
-                                if (n3) *reinterpret_cast<int2*>(xbuf + 3 * st + w) = *reinterpret_cast<const int2*>(nbG2 + (size_t)g2a_ * TG * st + last + w);
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
+                if (CL && crank > 0 && t == 0 && role <= 1 && S >= 1)     // the row above has finished step S - 1 (pushed into our ring)
+                    cl_wait_above(smem_addr(sm_full), S, a.cluster_fence != 0);
                 if (active) {
                     const int ia = m + 1, ib = n + 1;
                     if (n == 0 || r == p.lw) {                      // first in-band column of this row
@@ -347,7 +352,11 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                     const int* parkedH1 = ring_ok ? ringH + (size_t)((seq + 1) % RING) * st : rowH + (size_t)(n + 1) * st;
                     const int* parkedG1 = ring_ok ? ringG + (size_t)((seq + 1) % RING) * st : rowG + (size_t)(n + 1) * st;
                     const int* parkedG21 = ring_ok ? ringG2 + (size_t)((seq + 1) % RING) * st : rowG2 + (size_t)(n + 1) * st;
-                    if (CL && crank > 0) { parkedH0 = xbuf; parkedH1 = xbuf + st; parkedG1 = xbuf + 2 * st; parkedG21 = xbuf + 3 * st; }
+                    if (CL && crank > 0) {          // the row above lives in the CTA above: its records of steps S - 2 and S - 1
+                        const int sd = (S + XD - 2) % XD, sa = (S + XD - 1) % XD;
+                        parkedH0 = xring + (size_t)(sd * 3) * st; parkedH1 = xring + (size_t)(sa * 3) * st;
+                        parkedG1 = xring + (size_t)(sa * 3 + 1) * st; parkedG21 = xring + (size_t)(sa * 3 + 2) * st;
+                    }
                     // boundary column: H(m-1, -1) and H(m, -1).  SM: one row starts per step; its two boundary records
                     // come to shared memory first, so that every operand of the cell is a shared-memory record
                     int* const cb = colbuf + (size_t)(S & 1) * 2 * st;
@@ -422,7 +431,15 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
                 // advance the two positions
                 if (++n == P) { n = 0; ++k; m += TGC; }
                 if (++n2 == P) { n2 = 0; ++k2; }
-                STEP_SYNC();
+                if (CL && role == 0) {
+                    if (crank < NC - 1 && t >= TG - 32)
+                        cl_push(pubH + ((size_t)(S % 3) * TG + (TG - 1)) * st, pubG + ((size_t)(S & 1) * TG + (TG - 1)) * st,
+                                n3 ? pubG2 + ((size_t)(S & 1) * TG + (TG - 1)) * st : nullptr, smem_addr(xring), smem_addr(sm_full),
+                                smem_addr(sm_empty), S, st, t - (TG - 32), a.cluster_fence != 0);
+                    // the slot of step S - 2 has now served as "above" (S - 1) and "diagonal" (S): give it back
+                    if (crank > 0 && t == 0 && S >= 2) cl_release(smem_addr(sm_empty), S);
+                }
+                GSTEP();
             }
             if (CL) cg::this_cluster().sync();      // the last cell, the path parts and the parked rows of every CTA
         }
@@ -492,6 +509,10 @@ __global__ void __launch_bounds__(SPLIT ? 3 * CTA : CTA, SPLIT ? 1 : 2) k3_fill_
     }
 }
 
+#undef NC
+#undef crank
+#undef TGC
+
 template <int TG, bool SPLIT, int MODE, bool SM>
 cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
 {
@@ -506,7 +527,7 @@ cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
     if (carve > 100) carve = 100;
     e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return e;
-    k3_fill_kernel<TG, SPLIT, MODE, SM, false><<<grid_blocks, SPLIT ? 3 * CTA : CTA, a.smem_bytes, st>>>(a);
+    k3_fill_kernel<TG, SPLIT, MODE, SM, false><<<grid_blocks, SPLIT ? 3 * TG : CTA, a.smem_bytes, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -514,7 +535,7 @@ cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
 template <int MODE>
 cudaError_t launch_cluster(const K3Args& a, int clusters, cudaStream_t st)
 {
-    auto kern = k3_fill_kernel<CTA, true, MODE, true, true>;
+    auto kern = k3_fill_kernel<TGCL, true, MODE, true, true>;
     K3Args ac = a;
     { const char* f = getenv("PG_K3_CLUSTER_FENCE"); ac.cluster_fence = f && f[0] == '1'; }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
@@ -527,7 +548,7 @@ cudaError_t launch_cluster(const K3Args& a, int clusters, cudaStream_t st)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(clusters * a.cluster));
-    cfg.blockDim = dim3(3 * CTA);
+    cfg.blockDim = dim3(3 * TGCL);
     cfg.dynamicSmemBytes = (size_t)a.smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -564,6 +585,7 @@ cudaError_t launch_tg(const K3Args& a, int mode, int grid_blocks, cudaStream_t s
 }  // namespace
 
 int k3_threads() { return CTA; }
+int k3_cluster_rows() { return TGCL; }
 int k3_blocks_per_sm() { return 2; }
 size_t k3_wave_words(int stride, int Noll, int tg) { return k3_smem_words(stride, Noll, tg); }
 

@@ -236,7 +236,7 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         for (int m5 = 0; m5 < 5; ++m5) {
             int nc = 1;
             if (ce || maxlq_mode[m5] > 768)
-                while (nc < cmax && nc < 8 && maxlq_mode[m5] > nc * 256) nc *= 2;
+                while (nc < cmax && nc < 8 && maxlq_mode[m5] > nc * k3_cluster_rows()) nc *= 2;
             nc_mode[m5] = n_mode[m5] ? nc : 1;
             ctas += n_mode[m5] * nc_mode[m5];
         }

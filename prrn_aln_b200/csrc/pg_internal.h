@@ -263,6 +263,7 @@ int k2_blocks_per_sm();
 // k3_groups.cu
 cudaError_t k3_launch(const K3Args& a, int tg, int mode, int grid_blocks, cudaStream_t st);
 int k3_threads();
+int k3_cluster_rows();        // rows per CTA of the cluster latency kernel
 int k3_blocks_per_sm();
 int k3_pick_tg(int64_t npairs, int sm_count);
 bool k3_sm_fits(int stride, int Noll, int tg, size_t smem_bytes);
