@@ -22,6 +22,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -323,7 +324,16 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             // thread 0's position two steps ahead (what the ring must hold by then)
             int k2 = 0, n2 = 2;
             if (n2 >= P) { n2 -= P; ++k2; }
+#ifdef K3_TIMERS
+            long long tm_wait = 0, tm_c1 = 0, tm_b1 = 0, tm_c2 = 0, tm_b2 = 0, tm_push = 0, tm_t;
+#define TM_START() (tm_t = clock64())
+#define TM_ADD(acc) do { const long long now_ = clock64(); acc += now_ - tm_t; tm_t = now_; } while (0)
+#else
+#define TM_START() do {} while (0)
+#define TM_ADD(acc) do {} while (0)
+#endif
             for (int S = 0; S < total_steps; ++S) {
+                TM_START();
                 // prefetch the parked record thread 0 reads as "above" at step S + 2: index n2 + 1 of stripe k2 - 1
                 int pf_val[PFN];
                 const bool pf_now = ring_ok && n2 < LS && k2 * TGC < LQ;
@@ -340,6 +350,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                 int* g2out = pubG2 + ((size_t)(S & 1) * TG + t) * st;
                 if (CL && crank > 0 && t == 0 && role <= 1 && S >= 1)     // the row above has finished step S - 1 (pushed into our ring)
                     cl_wait_above(smem_addr(sm_full), S, a.cluster_fence != 0);
+                TM_ADD(tm_wait);
                 if (active) {
                     const int ia = m + 1, ib = n + 1;
                     if (n == 0 || r == p.lw) {                      // first in-band column of this row
@@ -395,8 +406,10 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                         k3_part_hori(p, A, B, ia, ib, n == 0, hleft, f1, f2);
                     }
                 }
+                TM_ADD(tm_c1);
                 if (SPLIT) {
                     __syncthreads();                                // the three candidates are in shared memory
+                    TM_ADD(tm_b1);
                     if (active && role == 0 && p.mode != 3) rec = k3_combine(p, m == 0, n == 0, hout, gout, g2out, f1, f2);
                 }
                 if (active && role == 0) {
@@ -431,6 +444,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                 // advance the two positions
                 if (++n == P) { n = 0; ++k; m += TGC; }
                 if (++n2 == P) { n2 = 0; ++k2; }
+                TM_ADD(tm_c2);
                 if (CL && role == 0) {
                     if (crank < NC - 1 && t >= TG - 32)
                         cl_push(pubH + ((size_t)(S % 3) * TG + (TG - 1)) * st, pubG + ((size_t)(S & 1) * TG + (TG - 1)) * st,
@@ -439,8 +453,15 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                     // the slot of step S - 2 has now served as "above" (S - 1) and "diagonal" (S): give it back
                     if (crank > 0 && t == 0 && S >= 2) cl_release(smem_addr(sm_empty), S);
                 }
+                TM_ADD(tm_push);
                 GSTEP();
+                TM_ADD(tm_b2);
             }
+#ifdef K3_TIMERS
+            if (role == 0 && (t == 0 || t == TG - 1))
+                printf("k3 timers pair %d cta %d/%d t %d steps %d LQ %d LS %d us: wait %.0f c1 %.0f b1 %.0f c2 %.0f push %.0f b2 %.0f\n", pi, crank, NC, t,
+                       total_steps, LQ, LS, tm_wait / 1965., tm_c1 / 1965., tm_b1 / 1965., tm_c2 / 1965., tm_push / 1965., tm_b2 / 1965.);
+#endif
             if (CL) cg::this_cluster().sync();      // the last cell, the path parts and the parked rows of every CTA
         }
         // ---- Aln2b1::lastB_ng (fwd2b1.cc:100-143): trailing gaps at true sequence ends cost rtgapf times the
