@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             int k2 = 0, n2 = 2;
             if (n2 >= P) { n2 -= P; ++k2; }
 #ifdef K3_TIMERS
-            long long tm_wait = 0, tm_c1 = 0, tm_b1 = 0, tm_c2 = 0, tm_b2 = 0, tm_push = 0, tm_t;
+            long long tm_wait = 0, tm_c1 = 0, tm_b1 = 0, tm_c2 = 0, tm_b2 = 0, tm_push = 0, tm_cmb = 0, tm_vmf = 0, tm_pre = 0, tm_t;
 #define TM_START() (tm_t = clock64())
 #define TM_ADD(acc) do { const long long now_ = clock64(); acc += now_ - tm_t; tm_t = now_; } while (0)
 #else
@@ -411,6 +411,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                     __syncthreads();                                // the three candidates are in shared memory
                     TM_ADD(tm_b1);
                     if (active && role == 0 && p.mode != 3) rec = k3_combine(p, m == 0, n == 0, hout, gout, g2out, f1, f2);
+                    TM_ADD(tm_cmb);
                 }
                 if (active && role == 0) {
                     if (rec) {
@@ -435,6 +436,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                         if (n3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
                     }
                 }
+                TM_ADD(tm_vmf);
                 if (pf_now) {
                     const int slot = (k2 * P + n2 + 1) % RING;
 #pragma unroll
@@ -459,8 +461,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             }
 #ifdef K3_TIMERS
             if (role == 0 && (t == 0 || t == TG - 1))
-                printf("k3 timers pair %d cta %d/%d t %d steps %d LQ %d LS %d us: wait %.0f c1 %.0f b1 %.0f c2 %.0f push %.0f b2 %.0f\n", pi, crank, NC, t,
-                       total_steps, LQ, LS, tm_wait / 1965., tm_c1 / 1965., tm_b1 / 1965., tm_c2 / 1965., tm_push / 1965., tm_b2 / 1965.);
+                printf("k3 timers pair %d cta %d/%d t %d steps %d LQ %d LS %d us: wait %.0f c1 %.0f b1 %.0f combine %.0f records %.0f rest %.0f push %.0f b2 %.0f\n", pi, crank, NC, t,
+                       total_steps, LQ, LS, tm_wait / 1965., tm_c1 / 1965., tm_b1 / 1965., tm_cmb / 1965., tm_vmf / 1965., tm_c2 / 1965., tm_push / 1965., tm_b2 / 1965.);
 #endif
             if (CL) cg::this_cluster().sync();      // the last cell, the path parts and the parked rows of every CTA
         }
