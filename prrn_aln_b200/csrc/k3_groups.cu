@@ -460,8 +460,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                 TM_ADD(tm_b2);
             }
 #ifdef K3_TIMERS
-            if (role == 0 && (t == 0 || t == TG - 1))
-                printf("k3 timers pair %d cta %d/%d t %d steps %d LQ %d LS %d us: wait %.0f c1 %.0f b1 %.0f combine %.0f records %.0f rest %.0f push %.0f b2 %.0f\n", pi, crank, NC, t,
+            if (t == 0 || t == TG - 1)
+                printf("k3 timers role %d pair %d cta %d/%d t %d steps %d LQ %d LS %d us: wait %.0f c1 %.0f b1 %.0f combine %.0f records %.0f rest %.0f push %.0f b2 %.0f\n", role, pi, crank, NC, t,
                        total_steps, LQ, LS, tm_wait / 1965., tm_c1 / 1965., tm_b1 / 1965., tm_cmb / 1965., tm_vmf / 1965., tm_c2 / 1965., tm_push / 1965., tm_b2 / 1965.);
 #endif
             if (CL) cg::this_cluster().sync();      // the last cell, the path parts and the parked rows of every CTA
