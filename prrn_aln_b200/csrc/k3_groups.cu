@@ -545,7 +545,7 @@ cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
     // batches): one CTA per SM and the rest of the unified array as L1 (measured 28 vs 37 ms for 24
     // pairs); more CTAs than SMs (throughput): two CTAs per SM win (59 vs 68 ms for 384 pairs).
     // PG_K3_CARVEOUT = percent of shared memory overrides.
-    int carve = grid_blocks > 148 ? 100 : (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
+    int carve = (!SPLIT && grid_blocks > 148) ? 100 : (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
     if (const char* cv = getenv("PG_K3_CARVEOUT")) carve = atoi(cv);
     if (carve > 100) carve = 100;
     e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
@@ -612,19 +612,19 @@ int k3_cluster_rows() { return TGCL; }
 int k3_blocks_per_sm() { return 2; }
 size_t k3_wave_words(int stride, int Noll, int tg) { return k3_smem_words(stride, Noll, tg); }
 
-// Threads per alignment for a batch (PG_K3_TG overrides).  Measured on B200, partitions of a 200 x ~500
-// family: 384 pairs -> 256 threads 60 ms, 128: 72, 64: 81, 32: 155; 1,536 pairs -> 256: 193 ms, 128: 176,
-// 64: 189, 32: 314.  The whole CTA per alignment wins until the batch is several waves deep; a warp per
-// alignment loses (every 32 rows pass through the parked-row buffer in L2), so only 128 / 256 / 3x256 are
-// instantiated (x 5 record modes).
+// Threads per alignment for a batch (PG_K3_TG overrides).  Measured on B200, partitions of a 200 x ~500 family:
+// the role-split kernel (768 = 3 threads per row, one CTA per SM, the rest of the unified array as L1 for the
+// gap-profile lists) wins at every batch size -- 24 pairs 8.7 ms, 384 pairs 30.4 ms against 46.4 ms (one thread
+// per row, 256 rows, two CTAs per SM, no L1 left), 1,536 pairs 111 ms against 147 ms (128 rows per alignment).
+// The one-thread-per-row variants stay for PG_K3_TG = 128 / 256 and for records too long for shared memory.
 int k3_pick_tg(int64_t npairs, int sm_count)
 {
+    (void)npairs; (void)sm_count;
     if (const char* e = getenv("PG_K3_TG")) {
         const int v = atoi(e);
         if (v == 128 || v == 256 || v == 768) return v;
     }
-    if (npairs <= sm_count) return 768;     // latency mode: at most one alignment per SM -> three threads per row
-    return npairs > (int64_t)8 * sm_count ? 128 : 256;
+    return 768;
 }
 
 // a.smem_bytes: dynamic shared memory per CTA = (CTA / tg) x the largest wavefront of the batch (capped)

@@ -216,7 +216,8 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         pairs[i].pad = 0;
         outoff[i + 1] = outoff[i] + pairs[i].out_cap;
     }
-    const int grid = (int)std::min<int64_t>((npairs + ngrp - 1) / ngrp, (int64_t)c->sm_count * k3_blocks_per_sm());
+    const int grid = (int)std::min<int64_t>((npairs + ngrp - 1) / ngrp,
+                                            (int64_t)c->sm_count * (tg_sel == 768 ? 1 : k3_blocks_per_sm()));
     // arenas / path stores: the kernels of the record modes present run side by side, each on its own slots
     int64_t n_mode[5] = {0, 0, 0, 0, 0};
     int g_mode[5], slot0_mode[5], nc_mode[5], vslot0_mode[5], maxlq_mode[5] = {0, 0, 0, 0, 0};

@@ -52,9 +52,15 @@ def test_group_goldens(ctx, name, inline_sim, monkeypatch):
     assert P.group_cells(A, B, gp.sh) == cells
 
 
-def test_batch_of_all_goldens_in_one_call(ctx):
-    """One launch over every golden pair (different modes, sizes, capacities), twice over: results must
-    not depend on which CTA / arena a pair lands on."""
+@pytest.mark.parametrize("tg", [None, "256", "128"])
+def test_batch_of_all_goldens_in_one_call(ctx, tg, monkeypatch):
+    """One launch over every golden pair (different modes, sizes, capacities), three times over: results must
+    not depend on which CTA / arena a pair lands on -- with the default kernel (three threads per row) and with
+    the one-thread-per-row variants (PG_K3_TG = 256 / 128 rows per alignment)."""
+    if tg is None:
+        monkeypatch.delenv("PG_K3_TG", raising=False)
+    else:
+        monkeypatch.setenv("PG_K3_TG", tg)
     gs = [golden(n) for n in golden_names("galign_")]
     staged = [stage_golden(g) for g in gs] * 3
     scores, pts = ctx.align_groups(staged)
