@@ -225,18 +225,18 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         ++n_mode[pairs[i].prm.mode];
         maxlq_mode[pairs[i].prm.mode] = std::max(maxlq_mode[pairs[i].prm.mode], a[i].right - a[i].left);
     }
-    // latency mode: a thread-block cluster of 4 / 8 CTAs per alignment (256 rows each) when the longest group of
-    // the mode needs four stripes or more -- a cluster step costs ~6 us against ~3.5 us of the single CTA (neighbour
-    // hand-shake through DSMEM), so it only pays once it replaces 4+ stripes by one (measured: prrn5 on 80 x 300
-    // aa loses 25 % with 2-CTA clusters, 200 x 500 aa gains 1.5x with 8) -- and as many as the SMs hold at once.
-    // PG_K3_CLUSTER = 1 turns it off, 2 / 4 / 8 force that size wherever a group exceeds one CTA (tests).
+    // a thread-block cluster of 2 / 4 / 8 CTAs per alignment (192 rows each) when the longest group of the mode
+    // needs more than one 256-row stripe and the SMs can hold all clusters of the batch at once (otherwise
+    // alignments side by side use the SMs better).  Measured with the decoupled ring hand-over: ~650-row groups
+    // 12.0 -> 8.8 ms (24 pairs), ~1,100 rows 32 -> 14.5 ms, 300-450 rows unchanged (prrn5 on 80 x 300 aa).
+    // PG_K3_CLUSTER = 1 turns it off, 2 / 4 / 8 cap the size.
     {
         const char* ce = getenv("PG_K3_CLUSTER");
         const int cmax = tg_sel == 768 ? (ce ? atoi(ce) : 8) : 1;
         int64_t ctas = 0;
         for (int m5 = 0; m5 < 5; ++m5) {
             int nc = 1;
-            if (ce || maxlq_mode[m5] > 768)
+            if (maxlq_mode[m5] > k3_threads())
                 while (nc < cmax && nc < 8 && maxlq_mode[m5] > nc * k3_cluster_rows()) nc *= 2;
             nc_mode[m5] = n_mode[m5] ? nc : 1;
             ctas += n_mode[m5] * nc_mode[m5];
