@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pg_internal.h"
@@ -312,9 +313,23 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         return pairs[x].prm.mode != pairs[y].prm.mode ? pairs[x].prm.mode < pairs[y].prm.mode : cells[x] > cells[y];
     });
     std::vector<K3Pair> sorted(npairs);
+    {   // staging copies of the pairs are independent: large batches are filled by up to 4 host threads
+        auto fill_range = [&](int64_t i0, int64_t i1) {
+            for (int64_t i = i0; i < i1; ++i) {
+                fill_side(a[i], prm[i].kdim, soa[i], h.data());
+                fill_side(b[i], prm[i].kdim, sob[i], h.data());
+            }
+        };
+        int nth = h_bytes < ((size_t)8 << 20) ? 1 : (int)std::min<int64_t>(4, std::max(1u, std::thread::hardware_concurrency()));
+        nth = (int)std::min<int64_t>(nth, npairs);
+        if (nth <= 1) fill_range(0, npairs);
+        else {
+            std::vector<std::thread> th;
+            for (int k = 0; k < nth; ++k) th.emplace_back(fill_range, npairs * k / nth, npairs * (k + 1) / nth);
+            for (auto& t : th) t.join();
+        }
+    }
     for (int64_t i = 0; i < npairs; ++i) {
-        fill_side(a[i], prm[i].kdim, soa[i], h.data());
-        fill_side(b[i], prm[i].kdim, sob[i], h.data());
         pairs[i].a = dev_side(a[i], soa[i], d);
         pairs[i].b = dev_side(b[i], sob[i], d);
         pairs[i].simmat = sim_off[i] == (size_t)-1 ? nullptr : (const double*)((char*)c->d_gsim + sim_off[i]);
