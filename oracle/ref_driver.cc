@@ -120,6 +120,7 @@ int main(int argc, const char** argv)
 
 	optimize(GLOBAL, MAXIMUM);
 	if (isprot) setdefPprm(250, 2., 9.);
+	else setdefmolc(DNA);		// plain FASTA of ACGT is otherwise guessed per file (seq.cc:85)
 	alprm.sh = atoi(kv(argc, argv, "sh", "-60"));
 	const char* s;
 	if ((s = kv(argc, argv, "u", 0)))  alprm.u = atof(s);
@@ -224,7 +225,10 @@ int main(int argc, const char** argv)
 	std::vector<mSeq*> seqs = read_all(argv[2]);
 	int	nn = (int) seqs.size();
 	if (!nn) fatal("no sequence\n");
-	prePwd(seqs[0]->inex.molc);
+	if (!isprot && nn >= 2) {	// as aln does (aln.cc:368): prePwd(int) would pick the protein defaults for DNA (aln2.cc:66-77)
+	    const Seq*	two[2] = {seqs[0], seqs[1]};
+	    prePwd(two);
+	} else prePwd(seqs[0]->inex.molc);
 	Simmtx*	sm = getSimmtx(0);
 	printf("#ref_driver cmd=%s n=%d vtype=%s u=%g v=%g u1=%g k1=%d ls=%d sh=%d tgapf=%g scale=%g lcl=%d threads=%d\n",
 	    cmd.c_str(), nn, sizeof(VTYPE) == 8? "f64": "f32",

@@ -41,8 +41,11 @@ OTHERS = [n for n in golden_names("align_") if not _supported(golden(n))]
 
 @pytest.mark.parametrize("name", AFFINE_INT)
 def test_golden_alignments_bit_exact(ctx, name):
+    """Includes the long DNA pairs frozen from the reference's aln set-up (align_dna6k: 12 stripes, align_c5b_30k:
+    BASELINE config 5b, 59 stripes): the striped multi-warp wavefront kernel against the reference's own corner list."""
     g = golden(name)
-    enc = [seqcode.encode_protein(s) for s in g["seqs"]]
+    dna = g.get("args", {}).get("molc") == "n"
+    enc = [seqcode.encode_dna(s) if dna else seqcode.encode_protein(s) for s in g["seqs"]]
     ia = [p["i"] for p in g["pairs"]]
     ib = [p["j"] for p in g["pairs"]]
     scores, raw = ctx.align_pairs(P.SeqSet(enc), ia, ib, _params(g), np.array(g["matrix"]))

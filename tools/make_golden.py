@@ -67,6 +67,13 @@ def align_case(name, seqs, flavour="f", **kv):
     print("wrote", name, "pairs", len(pairs))
 
 
+def dna_pair_cases():
+    """Long DNA pairs through aln's own set-up (prePwd(Seq**), algmode.crs = 1: s[=] 2, s[#] -4, u 2, v 6; sh -50):
+    C5b (30 kb x 30 kb, 55 s of the reference's alignC<DPunit>) and a 6 kb pair -- the striped long-pair kernel."""
+    align_case("align_dna6k", gen_synth.synth_set(2, 6000, 0.2, 0.2, 7, gen_synth.NT), molc="n", crs=1, sh=-50, mtx="pam")
+    align_case("align_c5b_30k", gen_synth.synth_set(2, 30000, 0.2, 0.2, 5, gen_synth.NT), molc="n", crs=1, sh=-50, mtx="pam")
+
+
 def lcl_cases(p24, rag):
     """algmode.lcl variants of alnScoreD: SWG score (lcl & 16) and semi-global with `ends` (Fwd2d_vd)."""
     score_case("score_p24_lcl16", p24, lcl=16)
@@ -248,6 +255,7 @@ def main():
     align_case("align_c1_ce13a", sample_pair(), sh=-50)
     galign_cases()
     alignb_cases()
+    dna_pair_cases()
 
 
 if __name__ == "__main__":
@@ -255,6 +263,8 @@ if __name__ == "__main__":
         sys.exit("oracle/_ref is not built: run `make -C oracle ref` where /root/reference exists")
     if len(sys.argv) > 1 and sys.argv[1] == "alignb":
         alignb_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "dna":
+        dna_pair_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == "galign":
         galign_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == "lcl":      # only the lcl cases
