@@ -6,11 +6,14 @@ protein set: score-only banded affine Gotoh fill for every pair + the distance e
 
   python bench.py --gpus 1 --steps 5 --warmup 3            # our arm (CUDA, sm_100a)
   python bench.py --impl reference --steps 2 --warmup 1    # the reference's own CPU code on host cores
-  torchrun --nproc-per-node N bench.py --gpus N ...        # pairs sharded over N GPUs + NCCL all-gather
+  torchrun --nproc-per-node N bench.py --gpus N ...        # the same pairs sharded over N GPUs + NCCL all-gather
 
 Prints ONE JSON line (rank 0).  `value` = GCUPS over the cells the reference's loops visit
 (SURVEY.md 8(d)), inputs resident in HBM; `e2e` = the same through the host-buffer C-ABI call
-(H2D of sequences + matrix, D2H of the distance vector inside the timed region).
+(H2D of sequences + matrix, D2H of the distance vector inside the timed region).  Further objects on the
+same line: `scale_out` (config 5a, 10,000 x 300 aa, strong-scaled at the same N), `group_to_group` (kernel
+K3/K4 throughput with the reference's alignC beside it), `prrn_msa` (config 3 end to end: the reference's own
+prrn5, plain on the host and linked with the shims, wall seconds and MSA identity) -- the last two at N = 1.
 """
 import argparse
 import json
@@ -44,11 +47,9 @@ def blosum62_matrix():
         return np.array(json.load(f)["matrix"])
 
 
-def workload(n_gpus):
-    """Weak scaling: M sequences with M(M-1)/2 ~= n_gpus * C(1000,2); same generator, seed 1."""
-    m = BASE_N if n_gpus == 1 else int(round((1 + math.sqrt(1 + 8.0 * n_gpus * BASE_N * (BASE_N - 1) / 2)) / 2))
-    seqs = gen_synth.synth_set(m, 400, 0.1, 0.6, 1)
-    return seqs
+def workload_c2():
+    """BASELINE config 2: 1,000 proteins of ~400 aa (seed 1) -- the same set at every N (strong scaling)."""
+    return gen_synth.synth_set(BASE_N, 400, 0.1, 0.6, 1)
 
 
 class ClockSampler:
@@ -155,10 +156,11 @@ class ClockSampler:
 def cpu_reference_run(seqs, threads, reps=1):
     """Time the reference's own calcdist (oracle/_ref/ref_driver_d, unmodified reference objects) --
     or the oracle port when the reference build is absent -- on the host cores.  Returns
-    (gcups, kind, cores, seconds, cells)."""
-    import prrn_aln_b200 as P
-    enc = [seqcode.encode_protein(s) for s in seqs]
-    cells = P.calcdist_cells(P.SeqSet(enc), P.Params(P.ALPRM(sh=SH)))
+    (gcups, kind, cores, seconds, cells).  Cells are counted in numpy (prrn_aln_b200/sharding.py: no CUDA
+    library is loaded by this leg)."""
+    from prrn_aln_b200 import sharding
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    cells = int(sharding.row_costs(lens, SH)[0].sum())
     import refio
     if refio.available("d"):
         fa = "/tmp/prrn_bench_cpu_%d.fa" % os.getpid()
@@ -167,6 +169,7 @@ def cpu_reference_run(seqs, threads, reps=1):
         os.unlink(fa)
         return cells / r["time"] / 1e9, "reference", max(threads, 1), r["time"], cells
     import oracle_py as O
+    enc = [seqcode.encode_protein(s) for s in seqs]
     M = blosum62_matrix()
     t0 = time.time()
     O.calcdist([O.seq(e) for e in enc], M, O.params(sh=SH, vtype=1), want_scores=False)
@@ -192,11 +195,46 @@ def group_side_measurement():
         return {"error": repr(e)[:300]}
 
 
+def prrn_msa_measurement():
+    """The third part of BASELINE.json's metric: `prrn` MSA wall seconds on config 3 (200 x ~500 aa, prrn5 -m blosum62):
+    the reference's own prrn5 program as it is (every DP on ONE host core: upstream's threaded mode crashes on
+    unaligned protein input) and the same objects linked with shim/*.cc (every alnScoreD / calcdist /
+    alignC in libprrn_gpu.so), side by side in the same run; the two MSAs must be identical."""
+    try:
+        import run_prrn
+        if not all(os.path.exists(os.path.join(run_prrn.REFDIR, run_prrn.BIN[a])) for a in ("cpu", "gpu")):
+            return {"unavailable": "oracle/_ref/prrn5_cpu / prrn5_gpu (the reference's prrn5, plain and shimmed) are not built"}
+        c = run_prrn.CONFIGS["c3"]
+        path = run_prrn.input_path("c3")
+        res = {}
+
+        def leg(arm):
+            res[arm] = run_prrn.run(arm, path, c["args"], {"PRRN_GPU_STATS": "1"} if arm == "gpu" else {})[0]
+        th = [threading.Thread(target=leg, args=(a,)) for a in ("cpu", "gpu")]      # side by side: different resources
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        out = {"metric": "prrn MSA wall seconds", "unit": "s", "higher_is_better": False,
+               "config": {"workload": "C3: prrn5 -m blosum62 on 200 x ~500 aa synthetic proteins (seed 1), double VTYPE, -t0"},
+               "value": res["gpu"]["wall_s"], "cpu_baseline": {"value": res["cpu"]["wall_s"], "unit": "s", "cores": 1,
+                                                               "kind": "reference", "sample": "the whole run"},
+               "identical_msa": res["cpu"]["rc"] == 0 and res["gpu"]["rc"] == 0 and res["cpu"]["msa_md5"] == res["gpu"]["msa_md5"],
+               "msa_md5": res["gpu"]["msa_md5"], "rc": [res["cpu"]["rc"], res["gpu"]["rc"]],
+               "library_stats": res["gpu"].get("stats")}
+        frozen = json.load(open(run_prrn.FROZEN)) if os.path.exists(run_prrn.FROZEN) else {}
+        if "c3" in frozen:
+            out["equals_frozen_reference_msa"] = frozen["c3"]["msa_md5"] == res["gpu"]["msa_md5"]
+        return out
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    seqs = workload(1)[:CPU_SAMPLE_N]
+    seqs = workload_c2()[:CPU_SAMPLE_N]
     threads = os.cpu_count() or 1
     for _ in range(args.warmup):
         cpu_reference_run(seqs[:100], threads)
@@ -211,13 +249,98 @@ def run_reference_arm(args):
     print(json.dumps({
         "impl": "reference", "metric": "DP GCUPS (all-pairs calcdist, band cells)", "value": val, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C2 all-vs-all calcdist(DynScr): 1000 x ~400 aa synthetic proteins (seed 1), "
                                "BLOSUM62 u=2 v=9 sh=-60; CPU arm runs a bounded sample", "sample": sample},
         "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+class AllPairs:
+    """One all-vs-all calcdist workload, STRONG-scaled: the condensed index range of the same sequence set is cut
+    into `world` contiguous, cost-balanced shards (equal DP cells, prrn_aln_b200/sharding.py); every rank fills its
+    shard with pg_calcdist_dev and the shards are exchanged by NCCL all-gather.  With chunks > 1 a rank's shard is cut
+    again and the all-gather of piece c runs (asynchronously, on NCCL's stream) while piece c + 1 is being filled."""
+
+    def __init__(self, P, torch, dist, ctx, seqs, rank, world, chunks, stream):
+        from prrn_aln_b200 import sharding
+        self.P, self.torch, self.dist, self.ctx, self.rank, self.world, self.stream = P, torch, dist, ctx, rank, world, stream
+        self.enc = [seqcode.encode_protein(s) for s in seqs]
+        self.ss = P.SeqSet(self.enc)
+        self.M = blosum62_matrix()
+        self.prm = P.Params(P.ALPRM(sh=SH), vtype=1)     # prrn build: FTYPE = double
+        self.npair = self.ss.n * (self.ss.n - 1) // 2
+        lens = np.array([len(e) for e in self.enc], dtype=np.int64)
+        self.cells_total = int(sharding.row_costs(lens, SH)[0].sum())
+        # world * chunks cost-balanced pieces; rank r owns pieces r, r + world, ... (piece c of every rank is
+        # exchanged in one all-gather)
+        pieces = sharding.cost_balanced_ranges(lens, SH, world * chunks)
+        self.mine = [pieces[c * world + rank] for c in range(chunks)]
+        self.slot = [max(b - a for a, b in pieces[c * world:(c + 1) * world]) for c in range(chunks)]
+        # one device handle per piece: each caches the host-built schedule of its own k range
+        self.dseqs = [ctx.upload(self.ss) for _ in range(chunks)]
+        self.d_shard = [torch.empty(max(n, 1), dtype=torch.float64, device="cuda") for n in self.slot]
+        self.d_all = [torch.empty(max(n, 1) * world, dtype=torch.float64, device="cuda") if world > 1 else self.d_shard[c]
+                      for c, n in enumerate(self.slot)]
+        self.pieces = pieces
+        self.chunks = chunks
+
+    def step(self):
+        nl = 0
+        handles = []
+        for c, (k0, k1) in enumerate(self.mine):
+            nl += self.ctx.calcdist_dev(self.dseqs[c], self.prm, self.M, k0, k1, self.d_shard[c].data_ptr(), self.stream.cuda_stream)
+            if self.world > 1:
+                handles.append(self.dist.all_gather_into_tensor(self.d_all[c], self.d_shard[c], async_op=True))
+        for h in handles:
+            h.wait()
+        return nl
+
+    def assembled(self):
+        """The full condensed distance vector on this rank (device), pieces put back in k order."""
+        torch = self.torch
+        parts = []
+        for idx, (a, b) in enumerate(self.pieces):
+            c, r = divmod(idx, self.world)
+            parts.append((a, self.d_all[c][r * max(self.slot[c], 1): r * max(self.slot[c], 1) + (b - a)] if self.world > 1
+                          else self.d_shard[c][:b - a]))
+        parts.sort(key=lambda t: t[0])
+        return torch.cat([p for _, p in parts])
+
+    def close(self):
+        for d in self.dseqs:
+            self.ctx.free_seqs(d)
+
+
+def time_steps(torch, dist, world, rank, stream, step, steps, warmup, flush, sampler=None):
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(warmup, 3)):
+        step()
+    sync_all()
+    launches = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sync_all()
+    if sampler is not None:
+        sampler.start()                  # polls while the timed steps below execute
+    for i in range(steps):
+        flush.fill_(i & 0xff)            # evict L2 between timed iterations (outside the events)
+        ev[i][0].record(stream)
+        launches += step()
+        ev[i][1].record(stream)
+    if sampler is not None:
+        sampler.sample_now()             # the steps are queued and running: at least one sample under load
+    sync_all()
+    clocks = sampler.stop() if sampler is not None else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), launches, clocks
 
 
 def main():
@@ -228,6 +351,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-groups", action="store_true", help="skip the group-to-group (K3) side measurement")
+    ap.add_argument("--no-scaleout", action="store_true", help="skip the C5a (10,000 x 300 aa) strong-scaling object")
+    ap.add_argument("--no-prrn", action="store_true", help="skip the prrn MSA wall-time object (C3, ~80 s of host time)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -243,87 +368,45 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    seqs = workload(world)
-    enc = [seqcode.encode_protein(s) for s in seqs]
-    ss = P.SeqSet(enc)
-    M = blosum62_matrix()
-    prm = P.Params(P.ALPRM(sh=SH), vtype=1)     # prrn build: FTYPE = double
-    npair = ss.n * (ss.n - 1) // 2
-    from prrn_aln_b200 import sharding
-    k0, k1, chunk = sharding.shard_range(npair, world, rank)
-    cells_total = P.calcdist_cells(ss, prm)
-    cells_mine = P.calcdist_cells(ss, prm, k0, k1)
-
     ctx = P.Context(local)
-    dseqs = ctx.upload(ss)
     stream = torch.cuda.Stream()         # a real (non-default) stream: kernels, NCCL and timing events share it
     torch.cuda.set_stream(stream)
-    d_shard = torch.empty(chunk, dtype=torch.float64, device="cuda")
-    d_all = torch.empty(chunk * world, dtype=torch.float64, device="cuda") if world > 1 else d_shard
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
-    def step_dev():
-        nl = ctx.calcdist_dev(dseqs, prm, M, k0, k1, d_shard.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.all_gather_into_tensor(d_all, d_shard)
-        return nl
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step_dev()
-    sync_all()
-    sampler = ClockSampler(local)
-    launches = 0
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync_all()
-    if rank == 0:
-        sampler.start()                  # polls while the timed steps below execute
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)            # evict L2 between timed iterations (outside the events)
-        ev[i][0].record(stream)
-        launches += step_dev()
-        ev[i][1].record(stream)
-    if rank == 0:
-        sampler.sample_now()             # the steps are queued and running: at least one sample under load
-    sync_all()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    gcups = cells_total * args.steps / (ms_total * 1e-3) / 1e9
+    # ---- headline: C2 (1,000 x ~400 aa), the same set at every N: strong scaling
+    c2 = AllPairs(P, torch, dist, ctx, workload_c2(), rank, world, 1, stream)
+    ms_total, launches, clocks = time_steps(torch, dist, world, rank, stream, c2.step, args.steps, args.warmup, flush,
+                                            ClockSampler(local) if rank == 0 else None)
+    gcups = c2.cells_total * args.steps / (ms_total * 1e-3) / 1e9
+    ss, npair, M, prm = c2.ss, c2.npair, c2.M, c2.prm
+    k0, k1 = c2.mine[0]
 
     # ---- end to end through the host-buffer C-ABI call: H2D (sequences, matrix) + D2H (distances)
     pin_out = torch.empty(max(k1 - k0, 1), dtype=torch.float64).pin_memory()
     out_np = pin_out.numpy()
     res_pin = torch.from_numpy(ss.res.copy()).pin_memory()
-    ss_pin = P.SeqSet(enc)
+    ss_pin = P.SeqSet(c2.enc)
     ss_pin.res = res_pin.numpy()
-    for _ in range(2):
+    for _ in range(3):
         ctx.calcdist(ss_pin, prm, M, k0, k1, out=out_np)
-    sync_all()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        t1 = time.perf_counter()
         ctx.calcdist(ss_pin, prm, M, k0, k1, out=out_np)
-        checksum = float(out_np[:8].sum())
-        if os.environ.get("BENCH_DEBUG"):
-            print("e2e step %.2f ms" % ((time.perf_counter() - t1) * 1e3), file=sys.stderr)
+        checksum = float(out_np[:8].sum())  # noqa: F841
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_gcups = cells_total * args.steps / float(t.item()) / 1e9
+    e2e_gcups = c2.cells_total * args.steps / float(t.item()) / 1e9
     h2d = int(ss.res.nbytes + ss.offs.nbytes + 2 * ss.lens.nbytes + ss.n + M.size * 4)
     d2h = int((k1 - k0) * 8)
 
@@ -344,26 +427,62 @@ def main():
     out = {
         "metric": "DP GCUPS (all-pairs calcdist, band cells)", "value": gcups, "unit": "GCUPS", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
         "config": {"workload": "C2 all-vs-all calcdist(DynScr): %d x ~400 aa synthetic proteins (seed 1), %d pairs, "
-                               "BLOSUM62 u=2 v=9 sh=-60, prrn (double) build semantics; pairs sharded over %d GPU(s)"
-                               % (ss.n, npair, world),
-                   "pairs": npair, "cells": cells_total, "full_matrix_cells": int(sum(
+                               "BLOSUM62 u=2 v=9 sh=-60, prrn (double) build semantics; the same set at every N, "
+                               "condensed index cut into %d cost-balanced shard(s) (equal DP cells)" % (ss.n, npair, world),
+                   "pairs": npair, "cells": c2.cells_total, "full_matrix_cells": int(sum(
                        int(ss.lens[j]) * int(ss.lens[:j].sum()) for j in range(1, ss.n))),
-                   "l2": "256 MB buffer written between timed iterations", "collective": "nccl all_gather" if world > 1 else None},
+                   "l2": "256 MB buffer written between timed iterations", "collective": "nccl all_gather" if world > 1 else None,
+                   "schedule": "value: the host-built work schedule of the shard is cached on the device-sequence handle "
+                               "(built once, in the warm-up); e2e: every call uploads the sequences and rebuilds it"},
         "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
+    c2.close()
+
+    # ---- scale-out config C5a: 10,000 x ~300 aa (49,995,000 pairs), strong scaling, all-gather overlapped
+    if not args.no_scaleout:
+        try:
+            chunks = 1 if world == 1 else 4
+            c5 = AllPairs(P, torch, dist, ctx, gen_synth.config_set("c5a"), rank, world, chunks, stream)
+            st5 = 3
+            ms5, nl5, _ = time_steps(torch, dist, world, rank, stream, c5.step, st5, 3, flush)
+            ag_ms = None
+            if world > 1:               # the exchange alone (all pieces back to back), for the record
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); dist.barrier()
+                e0.record(stream)
+                for c in range(c5.chunks):
+                    dist.all_gather_into_tensor(c5.d_all[c], c5.d_shard[c])
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ag_ms = e0.elapsed_time(e1)
+            full = c5.assembled()
+            out["scale_out"] = {
+                "metric": "DP GCUPS (all-pairs calcdist, band cells)", "value": c5.cells_total * st5 / (ms5 * 1e-3) / 1e9,
+                "unit": "GCUPS", "n_gpus": world, "steps": st5, "warmup": 3, "ms_per_step": ms5 / st5, "scaling": "strong",
+                "gpu_launches": nl5, "all_gather_ms_alone": ag_ms, "all_gather_bytes": int(c5.npair * 8),
+                "checksum": float(full.sum().item()), "pairs": c5.npair, "cells": c5.cells_total,
+                "config": {"workload": "C5a all-vs-all calcdist(DynScr): 10,000 x ~300 aa synthetic proteins (seed 5), "
+                                       "49,995,000 pairs, BLOSUM62 u=2 v=9 sh=-60; the same set at every N, %d cost-balanced "
+                                       "piece(s) per rank, the all-gather of a piece overlaps the fill of the next" % chunks}}
+            c5.close()
+            del c5, full
+        except Exception as e:
+            out["scale_out"] = {"error": repr(e)[:300]}
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = workload(1)[:CPU_SAMPLE_N]
+        sample = workload_c2()[:CPU_SAMPLE_N]
         g, kind, cores, dtc, cells = cpu_reference_run(sample, os.cpu_count() or 1)
         out["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": cores, "kind": kind,
                                "sample": "first %d of the 1000 sequences: %d pairs, %.3g cells, %.2f s" % (
                                    CPU_SAMPLE_N, CPU_SAMPLE_N * (CPU_SAMPLE_N - 1) // 2, cells, dtc)}
-    ctx.free_seqs(dseqs)
     ctx.close()
     if rank == 0 and world == 1 and not args.no_groups:
         out["group_to_group"] = group_side_measurement()
+    if rank == 0 and world == 1 and not args.no_prrn:
+        out["prrn_msa"] = prrn_msa_measurement()
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -145,6 +145,14 @@ typedef struct {
 
 int pg_align_groups(pg_context *ctx, const pg_group *a, const pg_group *b, const pg_gparams *prm, int64_t npairs,
                     double *out_scores, int64_t **out_offs, pg_skl **out_pts);
+/* ---- per-call level, groups, score only: stands behind
+ *   template<class recd_t> VTYPE HomScoreC(mSeq* seqs[2], PwdM* pwd, long rr[2], ...)   src/fwd2c.h:663-668
+ * as HomScore dispatches it (src/maln2.cc:1853-1857), i.e. Fwd2c without Vmf + forwardB(rr).  Same inputs as
+ * pg_align_groups.  out_rr (nullable, 2 per pair) receives pp[] of forwardB (src/fwd2c.h:476-479): rr[0] = the
+ * diagonal n - m of the last first-row cell on the optimal path (b.left - a.left if it never enters the first
+ * row; :468-469), rr[1] = the end diagonal. */
+int pg_score_groups(pg_context *ctx, const pg_group *a, const pg_group *b, const pg_gparams *prm, int64_t npairs,
+                    double *out_scores, int64_t *out_rr);
 /* DP cells the reference visits for one group pair (band from stripe(), src/aln2.cc:156-174). */
 int64_t pg_group_cells(const pg_group *a, const pg_group *b, int32_t sh);
 
@@ -162,7 +170,9 @@ typedef struct pg_dev_seqs pg_dev_seqs;
 int  pg_seqs_upload(pg_context *ctx, const pg_seqs *seqs, pg_dev_seqs **out);
 void pg_seqs_free(pg_context *ctx, pg_dev_seqs *d);
 /* d_out_dist: DEVICE pointer to (k_end - k_begin) FTYPE values; stream: cudaStream_t or NULL.
- * Asynchronous with respect to the host; *n_launches (nullable) receives the number of kernels. */
+ * Asynchronous with respect to the host; *n_launches (nullable) receives the number of kernels.  The context's
+ * workspace is shared by all calls: the next call on this context -- on any stream -- is ordered on the device after
+ * the work queued here, so calls never overlap; keep `stream` alive until it has been synchronized. */
 int pg_calcdist_dev(pg_context *ctx, pg_dev_seqs *seqs, const pg_params *prm, const void *mtx,
                     int32_t dim, int64_t k_begin, int64_t k_end, void *d_out_dist, void *stream,
                     int32_t *n_launches);

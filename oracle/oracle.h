@@ -124,6 +124,10 @@ typedef struct {
  * (out[0].n = count), *score = DP score, *cells = cells visited.  Returns the count or -1. */
 int orc_align_groups(const orc_group *a, const orc_group *b, const double *mtx, int dim, const orc_gparams *p,
                      double *score, orc_skl *out, int cap, int64_t *cells);
+/* HomScoreC<recd_t>(seqs, pwd, rr) (reference src/fwd2c.h:663-668): the same fill without Vmf; rr = pp[] of forwardB
+ * (:468-469, :476-479). */
+int orc_homscore_groups(const orc_group *a, const orc_group *b, const double *mtx, int dim, const orc_gparams *p,
+                        double *score, long rr[2]);
 
 
 /* Aln2b1: trcbkalignB_ng inside globalB_ng (reference src/fwd2b1.cc:64-279,1025-1051,1286-1315) for two

@@ -287,7 +287,8 @@ static void g_copy_##SUFFIX(const g_ctx_##SUFFIX *c, g_unit_##SUFFIX *d, const g
 }                                                                                                    \
                                                                                                      \
 static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double *mtx, int dim,      \
-                            const orc_gparams *p, double *score, orc_skl *out, int cap, int64_t *cells)\
+                            const orc_gparams *p, double *score, orc_skl *out, int cap, int64_t *cells,\
+                            long *rr /* HomScoreC: Fwd2c without Vmf, fwd2c.h:663-668 */)           \
 {                                                                                                    \
     typedef g_unit_##SUFFIX U;                                                                       \
     g_ctx_##SUFFIX C;                                                                                \
@@ -324,7 +325,7 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
     o_add(&st, 0, 0, 0);                           /* skip 0-th record (fwd2c.h:361) */              \
     int64_t ncell = 0;                                                                               \
     /* initB (fwd2c.h:138-176): origin, then the boundary row with asi at a.left - 1 */              \
-    Hp[0].val = 0; Hp[0].dir = G_DIAG; Hp[0].ptr = o_add(&st, al, bl, 0);                            \
+    Hp[0].val = 0; Hp[0].dir = G_DIAG; Hp[0].ptr = rr ? (long)(bl - al) : o_add(&st, al, bl, 0);  /* fwd2c.h:144 */\
     {                                                                                                \
         int rr = br - al; if (up < rr) rr = up;                                                      \
         const int r0 = bl - al;                                                                      \
@@ -415,7 +416,8 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
             }                                                                                        \
             if (mx->val > dg->val) g_copy_##SUFFIX(&C, &Hc[j], mx);     /* fwd2c.h:453 */            \
             else g_copy_##SUFFIX(&C, &Hc[j], dg);                                                    \
-            if (Hc[j].dir == G_NEWD || Hc[j].dir == G_NEWV || Hc[j].dir == G_NEWH)                   \
+            if (rr) { if (m == al) Hc[j].ptr = n - m; }                 /* fwd2c.h:468-469 */        \
+            else if (Hc[j].dir == G_NEWD || Hc[j].dir == G_NEWV || Hc[j].dir == G_NEWH)              \
                 Hc[j].ptr = o_add(&st, m, n, Hc[j].ptr);                /* fwd2c.h:465-467 */        \
             g_copy_##SUFFIX(&C, &Gc[j], g);                                                          \
             g_copy_##SUFFIX(&C, &G2c[j], g2);                                                        \
@@ -425,9 +427,14 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
     }                                                                                                \
     /* result cell H[b.right - a.right] (fwd2c.h:475-481) */                                         \
     const U *last = &Hp[br - 1 - bl + 1];                                                            \
-    long pp = o_add(&st, ar, br, last->ptr);                                                         \
     *score = (double)last->val;                                                                      \
     if (cells) *cells = ncell;                                                                       \
+    if (rr) {                                      /* pp[] of forwardB (fwd2c.h:476-479) */          \
+        rr[0] = last->ptr; rr[1] = (long)(bl - al) + (br - ar);                                      \
+        free(buf); free(pool); free(glpool); free(st.v);                                             \
+        return 0;                                                                                    \
+    }                                                                                                \
+    long pp = o_add(&st, ar, br, last->ptr);                                                         \
     int cnt = 0, ok = 1;                                                                             \
     for (long q = pp;; q = st.v[q].p) {            /* Vmf::traceback (vmf.cc:103-119) */             \
         if (cnt + 1 >= cap) { ok = 0; break; }                                                       \
@@ -627,6 +634,13 @@ DEFINE_GROUP_ALIGN(double, f64, (-(DBL_MAX / 16 * 7)))
 int orc_align_groups(const orc_group *a, const orc_group *b, const double *mtx, int dim, const orc_gparams *p,
                      double *score, orc_skl *out, int cap, int64_t *cells)
 {
-    return p->vtype ? g_align_f64(a, b, mtx, dim, p, score, out, cap, cells)
-                    : g_align_f32(a, b, mtx, dim, p, score, out, cap, cells);
+    return p->vtype ? g_align_f64(a, b, mtx, dim, p, score, out, cap, cells, 0)
+                    : g_align_f32(a, b, mtx, dim, p, score, out, cap, cells, 0);
+}
+
+int orc_homscore_groups(const orc_group *a, const orc_group *b, const double *mtx, int dim, const orc_gparams *p,
+                        double *score, long rr[2])
+{
+    return p->vtype ? g_align_f64(a, b, mtx, dim, p, score, 0, 0, 0, rr)
+                    : g_align_f32(a, b, mtx, dim, p, score, 0, 0, 0, rr);
 }

@@ -226,6 +226,20 @@ def align_groups(A, B, mtx, gp):
     return scr.value, [(out[i].m, out[i].n) for i in range(1, cnt + 1)], cells.value
 
 
+def homscore_groups(A, B, mtx, gp):
+    """HomScoreC<recd_t>(seqs, pwd, rr) restatement: (score, [rr0, rr1])."""
+    L = lib()
+    L.orc_homscore_groups.restype = C.c_int
+    L.orc_homscore_groups.argtypes = [C.POINTER(OrcGroup), C.POINTER(OrcGroup), C.POINTER(C.c_double), C.c_int,
+                                      C.POINTER(OrcGparams), C.POINTER(C.c_double), C.POINTER(C.c_long)]
+    m, mp, dim = _mtx(mtx)
+    ga, gb = _orc_group(A), _orc_group(B)
+    scr = C.c_double(0)
+    rr = (C.c_long * 2)()
+    L.orc_homscore_groups(C.byref(ga), C.byref(gb), mp, dim, C.byref(gp), C.byref(scr), rr)
+    return scr.value, [rr[0], rr[1]]
+
+
 def align_b1(a, b, mtx, p, std=True):
     """alignB_ng restatement (+ stdskl when std): (score, [(m, n), ...])."""
     L = lib()

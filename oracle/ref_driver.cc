@@ -40,6 +40,17 @@ void usage() {}
 template <class seq_t> void AlnServer<seq_t>::setparam(int) {}
 template <class seq_t> int AlnServer<seq_t>::localoption(int&, const char**&) { return 0; }
 
+// galign mt=N: N workers call align2 at the same time, as the workers of Prrn::best_of_n do (src/prrn5.cc:565-612)
+struct MtArg { mSeq* sq[2]; PwdM* pwd; VTYPE scr; SKL* skl; };
+static void* mt_align2(void* p)
+{
+	MtArg*	a = (MtArg*) p;
+	Gsinfo	gsi;
+	a->skl = align2(a->sq, a->pwd, &a->scr, &gsi);
+	gsi.skl = 0;
+	return 0;
+}
+
 static double now_s()
 {
 	struct timeval tv; gettimeofday(&tv, 0);
@@ -195,6 +206,10 @@ int main(int argc, const char** argv)
 		    case HLF_ALB: case RHF_ALB: skl = alignC<DPunit_hf>(sq, pwd, &scr); break;
 		    case GPF_ALB: skl = alignC<DPunit_pf>(sq, pwd, &scr); break;
 		    case NTV_ALB: skl = alignC<DPunit_nv>(sq, pwd, &scr); break;
+		    case NGP_ALN: skl = alignC<DPunit>(sq, pwd, &scr, true); break;		// rectangle (bnd=0), maln2.cc:1911-1915
+		    case NTV_ALN: skl = alignC<DPunit_nv>(sq, pwd, &scr, true); break;
+		    case HLF_ALN: case RHF_ALN: skl = alignC<DPunit_hf>(sq, pwd, &scr, true); break;
+		    case GPF_ALN: skl = alignC<DPunit_pf>(sq, pwd, &scr, true); break;
 		    default: fatal("galign: alnmode %d not handled by the driver\n", pwd->alnmode);
 		}
 	    }
@@ -207,6 +222,11 @@ int main(int argc, const char** argv)
 		putchar('\n');
 	    }
 	    delete[] skl;
+	    {	// HomScore -> HomScoreC<recd_t>(seqs, pwd, rr): the score-only fill (maln2.cc:1837-1862, fwd2c.h:663-668)
+		long	rr[2] = {0, 0};
+		VTYPE	hs = HomScore(sq, pwd, rr);
+		printf("homscore "); print_vt(hs); printf(" %ld %ld\n", rr[0], rr[1]);
+	    }
 	    Gsinfo	gsi;
 	    scr = 0;
 	    skl = align2(sq, pwd, &scr, &gsi);
@@ -219,6 +239,36 @@ int main(int argc, const char** argv)
 	    }
 	    gsi.skl = 0;
 	    delete[] skl;
+	    int	mt = atoi(kv(argc, argv, "mt", "0"));
+	    if (mt > 0) {
+		std::vector<MtArg>	args(mt);
+		std::vector<pthread_t>	th(mt);
+		for (int k = 0; k < mt; ++k) {		// own sequences and PwdM per worker, built one after the other
+		    for (int g = 0; g < 2; ++g) {
+			args[k].sq[g] = new mSeq();
+			FILE*	f = fopen(g? fb: argv[2], "r");
+			if (!f || !args[k].sq[g]->fgetseq(f)) fatal("cannot read group %d\n", g);
+			fclose(f);
+			if (sq[g]->weight) {
+			    args[k].sq[g]->weight = new FTYPE[sq[g]->many];
+			    for (int i = 0; i < sq[g]->many; ++i) args[k].sq[g]->weight[i] = sq[g]->weight[i];
+			}
+		    }
+		    args[k].pwd = new PwdM(args[k].sq);
+		    args[k].scr = 0; args[k].skl = 0;
+		}
+		for (int k = 0; k < mt; ++k) pthread_create(&th[k], 0, mt_align2, &args[k]);
+		for (int k = 0; k < mt; ++k) pthread_join(th[k], 0);
+		for (int k = 0; k < mt; ++k) {
+		    printf("mt %d ", k); print_vt(args[k].scr);
+		    if (!args[k].skl) printf(" skl 0\n");
+		    else {
+			printf(" skl %d %d :", args[k].skl->n, args[k].skl->m);
+			for (int q = 1; q <= args[k].skl->n; ++q) printf(" %d %d", args[k].skl[q].m, args[k].skl[q].n);
+			putchar('\n');
+		    }
+		}
+	    }
 	    return 0;
 	}
 

@@ -113,6 +113,7 @@ def load_library():
                                  C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32))]
     L.pg_align_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32))]
+    L.pg_score_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.pg_group_cells.restype = C.c_int64
     L.pg_group_cells.argtypes = [C.POINTER(_PgGroup), C.POINTER(_PgGroup), C.c_int32]
     L.pg_last_kernel_ms.restype = C.c_double
@@ -264,6 +265,18 @@ class Context:
             self.L.pg_free(offs)
             self.L.pg_free(pts)
         return out, [p[o[i]:o[i + 1]] for i in range(n)]
+
+    def score_groups(self, pairs):
+        """HomScoreC<recd_t>(seqs, pwd, rr) for a batch (reference src/fwd2c.h:663-668, dispatched by HomScore,
+        src/maln2.cc:1837-1862): the same fill without the path store.  Returns (scores float64, rr int64 (n x 2))."""
+        n = len(pairs)
+        ga = (_PgGroup * max(n, 1))(*[_pg_group(p[0]) for p in pairs])
+        gb = (_PgGroup * max(n, 1))(*[_pg_group(p[1]) for p in pairs])
+        gp = (GParams * max(n, 1))(*[p[2] for p in pairs])
+        out = np.empty(n, np.float64)
+        rr = np.zeros((n, 2), np.int64)
+        self._check(self.L.pg_score_groups(self.h, ga, gb, gp, n, out.ctypes.data, rr.ctypes.data))
+        return out, rr
 
     # -- batch level: calcdist(DynScr) ------------------------------------------------------------
     def calcdist(self, seqs, prm, mtx, k_begin=0, k_end=None, out=None):

@@ -61,6 +61,9 @@ struct K3Prm {
     // the end of b) / last row (after the end of a) runs at all (true sequence end and factor < 1)
     double rtg_a, rtg_b;
     int32_t last_c, last_r;
+    // score only (HomScoreC, src/fwd2c.h:663-668: Fwd2c without Vmf): no path records; ptr carries the diagonal
+    // n - m of the path's last first-row cell instead (fwd2c.h:468-469), the origin's b.left - a.left otherwise
+    int32_t novmf, origin_r;
 };
 
 // ---- record access -------------------------------------------------------------------------------

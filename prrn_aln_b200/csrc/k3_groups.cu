@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             vmf[0].m = 0; vmf[0].n = 0; vmf[0].p = 0;                       // skip 0-th record (:361)
             vmf[1].m = P_.al; vmf[1].n = P_.bl; vmf[1].p = 0;                 // origin
             sm_vmf[g] = 2;
-            k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(colH) = 1;
+            k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(colH) = p.novmf ? p.origin_r : 1;
             const int rr = LQ < -p.lw ? LQ : -p.lw;
             for (int k = 1; k <= rr; ++k) {
                 if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false);
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             }
         }
         if (t == TG / 2 && role == (SPLIT ? 1 : 0) && crank == 0) {
-            k3_setval(rowH, 0); k3_setdg(rowH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(rowH) = 1;
+            k3_setval(rowH, 0); k3_setdg(rowH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(rowH) = p.novmf ? p.origin_r : 1;
             const int rr = LS < p.up ? LS : p.up;
             for (int k = 1; k <= rr; ++k) {
                 if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true);
@@ -414,7 +414,9 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                     TM_ADD(tm_cmb);
                 }
                 if (active && role == 0) {
-                    if (rec) {
+                    if (p.novmf) {                                  // HomScoreC: no Vmf; first-row cells remember their diagonal
+                        if (m == 0) K3_PTR(hout) = n + p.origin_r;
+                    } else if (rec) {
                         int id = atomicAdd(&sm_vmf[g], 1);          // Vmf::add (fwd2c.h:465-467)
                         const bool fits = id < a.vmf_cap;
                         if (CL) { if (!fits) ghdr[1] = 1; id += crank * a.vmf_cap; }
@@ -516,7 +518,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             int* out = a.out_pts + 2 * P_.out_off;
             int cnt = 0;
             const int nrec = sm_vmf[g];
-            if (nrec >= a.vmf_cap || (CL && __ldcg(ghdr + 1))) cnt = -1;    // record store overflow: reported, never silent
+            if (p.novmf) out[0] = sm_last_ptr[g];                             // pp[0] of forwardB (fwd2c.h:476-479); no corners
+            else if (nrec >= a.vmf_cap || (CL && __ldcg(ghdr + 1))) cnt = -1;   // record store overflow: reported, never silent
             else {
                 out[0] = LQ + P_.al; out[1] = LS + P_.bl; cnt = 1;
                 for (int q = sm_last_ptr[g];; q = vmf[q].p) {

@@ -82,6 +82,8 @@ extern "C" int pg_create(int device, pg_context** out)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_ws, cudaEventDisableTiming);
+    c->ws_stream = c->stream;
     if (e != cudaSuccess) {
         std::string m = std::string("pg_create: ") + cudaGetErrorString(e);
         return fail(nullptr, PG_ERR_CUDA, m);
@@ -100,7 +102,8 @@ extern "C" void pg_destroy(pg_context* c)
     cudaFree(c->d_bnd); cudaFree(c->d_scratch); cudaFree(c->d_ends);
     if (c->h_gstage) cudaFreeHost(c->h_gstage);
     cudaFree(c->d_gblob); cudaFree(c->d_garena); cudaFree(c->d_gvmf); cudaFree(c->d_gout); cudaFree(c->d_gsim);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_fork);
+    if (c->ws_stream != c->stream) cudaStreamSynchronize(c->ws_stream);     // a caller's stream may still use the workspace
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_ws);
     for (int i = 0; i < 5; ++i) { cudaStreamDestroy(c->aux[i]); cudaEventDestroy(c->ev_join[i]); }
     cudaStreamDestroy(c->stream);
     delete c;
@@ -114,6 +117,15 @@ static int ensure_cap(pg_context* c, void** p, size_t* cap, size_t need)
     PG_CUDA(c, cudaMalloc(p, n));
     *cap = n;
     return PG_OK;
+}
+
+cudaError_t pg_int_order_stream(pg_context* c, cudaStream_t st)
+{
+    if (c->ws_stream == st) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(c->ev_ws, c->ws_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, c->ev_ws, 0);
+    if (e == cudaSuccess) c->ws_stream = st;
+    return e;
 }
 
 // internal linkage helpers for the other translation units of the library (pg_groups.cu)
@@ -185,6 +197,12 @@ static int plan_scoring(pg_context* c, const pg_params* prm, const void* mtx, in
             std::string keep = c->err;
             if (make_int_scoring(c, &p0, mtx, dim, d->present, sc) == PG_OK) plan->integer = true;
             else c->err = keep;     // not integral: K1F takes it
+            // K1 / K1P pick rows and columns freely (rows = the longer list's query, tournament halves); that equals
+            // the reference's mtx[a][b] (fwd2d1.cc:149) only for a matrix symmetric over the codes present.  K1F
+            // keeps the orientation rows = a.
+            for (int i = 0; plan->integer && i < dim; ++i)
+                for (int j = 0; j < i; ++j)
+                    if (d->present[i] && d->present[j] && sc->mtx[i * dim + j] != sc->mtx[j * dim + i]) { plan->integer = false; break; }
         }
     }
     return PG_OK;
@@ -279,6 +297,7 @@ static int seqs_upload_impl(pg_context* c, const pg_seqs* s, pg_dev_seqs** out, 
     if (!s || !out || s->nseq < 0 || (s->nseq > 0 && (!s->res || !s->offs || !s->lens)))
         return fail(c, PG_ERR_ARG, "pg_seqs_upload: bad sequence set");
     PG_CUDA(c, cudaSetDevice(c->device));
+    PG_CUDA(c, pg_int_order_stream(c, c->stream));
     const int n = s->nseq;
     int64_t total = 0;
     for (int i = 0; i < n; ++i) {
@@ -607,8 +626,10 @@ extern "C" int pg_calcdist_dev(pg_context* c, pg_dev_seqs* d, const pg_params* p
     ScorePlan plan;
     int rc = plan_scoring(c, prm, mtx, dim, d, prm->lcl != 0, &sc, &plan);
     if (rc) return rc;
-    // everything (staging copies, self-score kernel, fill kernel) is ordered on one stream
+    // everything (staging copies, self-score kernel, fill kernel) is ordered on one stream; the context's workspace
+    // (work-queue counter, matrix, items, self scores, scratch) passes from the stream that used it last to this one
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    PG_CUDA(c, pg_int_order_stream(c, st));
     if (!plan.integer) {
         std::vector<PgItem> fitems;
         bool fmp = false;
@@ -874,7 +895,8 @@ extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
                     const int i = side ? b_idx[p] : a_idx[p];
                     if (s->lens[i] < 0 || s->offs[i] < 0) return fail(c, PG_ERR_ARG, "negative length / offset");
                     const int l = s->left ? s->left[i] : 0, r = s->right ? s->right[i] : s->lens[i];
-                    for (int k = l; k < r && k < s->lens[i]; ++k) present[s->res[s->offs[i] + k]] = 1;
+                    if (l < 0 || r > s->lens[i] || l > r) return fail(c, PG_ERR_ARG, "window outside the sequence");
+                    for (int k = l; k < r; ++k) present[s->res[s->offs[i] + k]] = 1;
                 }
             IntScoring probe;
             std::string keep = c->err;

@@ -111,7 +111,8 @@ struct PgTerm {
 };
 
 static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
-                               double* out_scores, int64_t** out_offs, pg_skl** out_pts, const PgTerm* term);
+                               double* out_scores, int64_t** out_offs, pg_skl** out_pts, const PgTerm* term,
+                               int64_t* out_rr = nullptr, bool score_only = false);
 
 extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
                                double* out_scores, int64_t** out_offs, pg_skl** out_pts)
@@ -119,8 +120,20 @@ extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group*
     return pg_int_align_groups(c, a, b, prm, npairs, out_scores, out_offs, out_pts, nullptr);
 }
 
+// HomScoreC (src/fwd2c.h:663-668): the same fill without the path store
+extern "C" int pg_score_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
+                               double* out_scores, int64_t* out_rr)
+{
+    int64_t* offs = nullptr;
+    pg_skl* pts = nullptr;
+    const int rc = pg_int_align_groups(c, a, b, prm, npairs, out_scores, &offs, &pts, nullptr, out_rr, true);
+    free(offs); free(pts);
+    return rc;
+}
+
 static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
-                               double* out_scores, int64_t** out_offs, pg_skl** out_pts, const PgTerm* term)
+                               double* out_scores, int64_t** out_offs, pg_skl** out_pts, const PgTerm* term,
+                               int64_t* out_rr, bool score_only)
 {
     if (!c) return PG_ERR_ARG;
     if (npairs < 0 || !out_offs || !out_pts || (npairs && (!a || !b || !prm || !out_scores)))
@@ -133,6 +146,7 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
     offs[0] = 0;
     if (npairs == 0) { *out_offs = offs; *out_pts = (pg_skl*)malloc(sizeof(pg_skl)); return PG_OK; }
     cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) e = pg_int_order_stream(c, c->stream);
     if (e != cudaSuccess) { free(offs); return pg_int_fail(c, PG_ERR_CUDA, cudaGetErrorString(e)); }
 
     // ---- validate, lay out the blob
@@ -196,6 +210,12 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         kp.gop1 = P.BasicGOP; kp.gep1 = P.BasicGEP; kp.gop2 = P.LongGOP; kp.gep2 = P.LongGEP;
         kp.ltg_a = kp.ltg_b = kp.rtg_a = kp.rtg_b = 1.0;
         kp.last_c = kp.last_r = 0;
+        kp.novmf = score_only ? 1 : 0;
+        kp.origin_r = B.left - A.left;
+        if (score_only && mode == 3) {
+            free(offs);
+            return pg_int_fail(c, PG_ERR_ARG, "pg_score_groups: the Aln2b1 recurrence has its own entry (pg_align_pairs_ng)");
+        }
         if (term && mode == 3) {
             kp.ltg_a = term[i].ltg_a; kp.ltg_b = term[i].ltg_b; kp.rtg_a = term[i].rtg_a; kp.rtg_b = term[i].rtg_b;
             kp.last_c = term[i].last_c; kp.last_r = term[i].last_r;
@@ -258,7 +278,7 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         slots += (size_t)g_mode[m5] * ngrp;
         vslots += (size_t)g_mode[m5] * ngrp * nc_mode[m5];      // path store: one part per CTA of a cluster
     }
-    const int64_t vmf_cap = max_cells + 8;
+    const int64_t vmf_cap = score_only ? 8 : max_cells + 8;
     if (vmf_cap * 8 > 0x7fffffff) { free(offs); return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: DP matrix too large for the path store"); }
 
     // ---- stage
@@ -419,6 +439,10 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         const int32_t* src = h_pts.data() + 2 * pairs[i].out_off;
         for (int q = 0; q < h_cnt[k]; ++q) { pts[offs[i] + q].m = src[2 * q]; pts[offs[i] + q].n = src[2 * q + 1]; }
         out_scores[i] = h_scr[k];
+        if (score_only && out_rr) {         // pp[2] of forwardB (fwd2c.h:476-479)
+            out_rr[2 * i] = src[0];
+            out_rr[2 * i + 1] = (int64_t)(b[i].left - a[i].left) + (b[i].right - a[i].right);
+        }
     }
     *out_offs = offs;
     *out_pts = pts;

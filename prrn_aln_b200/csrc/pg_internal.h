@@ -226,9 +226,17 @@ struct pg_context {
     cudaEvent_t ev_fork, ev_join[5];
     cudaEvent_t ev0, ev1;       // device time of the last fill launch (pg_last_kernel_ms)
     bool ev_valid;
+    // The workspace above is shared by every call on this context.  Calls are ordered on c->stream, except
+    // pg_calcdist_dev on a caller's stream: whoever touches the workspace next first waits (on the device) for the
+    // last stream that used it (pg_int_order_stream).
+    cudaStream_t ws_stream;     // stream of the last call that used the workspace
+    cudaEvent_t ev_ws;
 };
 
 int pg_int_fail(pg_context* ctx, int code, const char* msg);
+// Make `st` the stream that owns the context's workspace: if another stream used it last, `st` waits for the work
+// queued there.  Called at the top of every entry point before the workspace is written.
+cudaError_t pg_int_order_stream(pg_context* c, cudaStream_t st);
 int pg_int_ensure_cap(pg_context* c, void** p, size_t* cap, size_t need);
 
 int pg_int_align_pairs_fp(pg_context* c, const pg_seqs* s, const int32_t* a_idx, const int32_t* b_idx, int64_t npairs,

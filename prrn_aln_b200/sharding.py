@@ -17,6 +17,78 @@ def shard_range(npair, world, rank):
     return k0, k1, chunk
 
 
+# ---- cost model: DP cells the reference visits per pair -----------------------------
+def band(lq, ls, sh):
+    """stripe() (reference src/aln2.cc:156-174) for two full windows of lq rows and ls columns, numpy-vectorised:
+    returns (lw, up) in diagonal coordinates r = n - m."""
+    lq = np.asarray(lq, dtype=np.int64)
+    ls = np.asarray(ls, dtype=np.int64)
+    shv = np.full(np.broadcast(lq, ls).shape, sh, dtype=np.int64)
+    if sh < 0:
+        shv = -sh * np.minimum(lq, ls) // 100
+    hi = np.maximum(ls - lq, 0) + shv
+    lo = np.minimum(ls - lq, 0) - shv
+    return np.maximum(lo, -lq), np.minimum(hi, ls)
+
+
+def _sum_clamped(a0, n, hi):
+    """sum_{m=0}^{n-1} clamp(a0 + m, 0, hi), vectorised."""
+    m0 = np.clip(-a0, 0, n)
+    m1 = np.clip(hi - a0, m0, n)
+    cnt = m1 - m0
+    lin = cnt * a0 + (m0 + m1 - 1) * cnt // 2
+    return lin + (n - m1) * hi
+
+
+def band_cells(lq, ls, sh):
+    """Cells (m, n) the reference's loops visit for a pair of lq x ls residues: rows 0..lq-1, columns
+    max(m + lw, 0) .. min(m + up + 1, ls) - 1 (loop bounds src/fwd2d1.cc:136-146, src/fwd2c.h:364-374)."""
+    lq = np.asarray(lq, dtype=np.int64)
+    ls = np.asarray(ls, dtype=np.int64)
+    lw, up = band(lq, ls, sh)
+    c = _sum_clamped(up + 1, lq, ls) - _sum_clamped(lw, lq, ls)
+    return np.where((lq > 0) & (ls > 0), c, 0)
+
+
+def row_costs(lens, sh):
+    """cost[j] = cells of the pairs (i, j), i < j -- row j of the condensed triangle (a = i, b = j).  Lengths
+    have few distinct values, so the cost is a table over (length of i, length of j) times running counts."""
+    lens = np.asarray(lens, dtype=np.int64)
+    n = len(lens)
+    if n == 0:
+        return np.zeros(0, np.int64), None, None
+    uniq, inv = np.unique(lens, return_inverse=True)
+    table = band_cells(uniq[:, None], uniq[None, :], sh)            # [length of a][length of b]
+    counts = np.zeros((n + 1, len(uniq)), dtype=np.int64)
+    np.add.at(counts, (np.arange(1, n + 1), inv), 1)
+    counts = np.cumsum(counts, axis=0)                              # counts[j] = histogram of lens[:j]
+    cost = np.einsum("ju,uj->j", counts[:n], table[:, inv])
+    return cost, table, inv
+
+
+def cost_balanced_ranges(lens, sh, world):
+    """Contiguous ranges [k0, k1) of the condensed index k = j(j-1)/2 + i, one per rank, with about the same number
+    of DP cells each (cost-balanced, not count-balanced: ragged sets put the long sequences'
+    rows where they fall).  Returns [(k0, k1)] * world covering [0, n(n-1)/2)."""
+    n = len(lens)
+    npair = n * (n - 1) // 2
+    if world <= 1 or npair == 0:
+        return [(0, npair)] + [(npair, npair)] * (max(world, 1) - 1)
+    cost, table, inv = row_costs(lens, sh)
+    cum = np.concatenate([[0], np.cumsum(cost)])                    # cum[j] = cells of rows < j
+    total = int(cum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r // world
+        j = int(np.searchsorted(cum, target, side="right")) - 1     # row holding the target
+        j = min(max(j, 1), n - 1)
+        within = np.cumsum(table[inv[:j], inv[j]])                  # cells of (0..i, j)
+        i = int(np.searchsorted(within, target - int(cum[j]), side="left"))
+        cuts.append(max(cuts[-1], min(j * (j - 1) // 2 + min(i, j), npair)))
+    cuts.append(npair)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def gather_shards(shard, chunk, npair, world, dist=None):
     """all-gather equal-size (padded) shards and trim the result to npair entries.
     `shard` is a torch tensor of length `chunk` on the rank's device (padding beyond k1-k0 ignored)."""
@@ -68,14 +140,21 @@ def best_of_n_sharded(scores_of, costs, rank, world, dist=None):
     Ties go to the lowest index, as the reference's sequential arg-max does (prrn5.cc:618-626).  The only
     collective is one all-reduce(MAX) of B doubles (every slot is written by exactly one rank, the others
     hold -inf); the winner's corner list stays on the rank that owns it."""
+    import math
     import torch
     mine = shard_candidates(costs, world, rank)
     vals = scores_of(mine) if mine else []
     n = len(costs)
+    # NCCL reduces device tensors only: the buffer lives on this rank's GPU there, on the host under gloo
+    on_gpu = world > 1 and dist is not None and dist.get_backend() == "nccl"
     buf = torch.full((n,), float("-inf"), dtype=torch.float64)
     for i, v in zip(mine, vals):
-        buf[i] = float(v)
+        v = float(v)
+        buf[i] = v if not math.isnan(v) else float("-inf")     # the reference's strict `>` never picks a NaN (prrn5.cc:620)
+    if on_gpu:
+        buf = buf.cuda()
     if world > 1 and dist is not None:
         dist.all_reduce(buf, op=dist.ReduceOp.MAX)      # each slot is written by exactly one rank
+    buf = buf.cpu()
     best = int(torch.argmax(buf).item()) if n else -1
     return best, (float(buf[best]) if n else float("-inf")), buf

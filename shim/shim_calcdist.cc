@@ -15,6 +15,7 @@
 #include "maln.h"
 #include "phyl.h"
 #include "prrn_gpu.h"
+#include "shim_ctx.h"
 
 #include <stdlib.h>
 #include <string.h>
@@ -22,21 +23,20 @@
 
 extern FTYPE*	calcdist_ref(mSeq** sbuf, int nn, DistCal realign);	// src/phyl.cc:318 compiled as calcdist_ref
 
-static pg_context* pg_ctx_dist()
-{
-	static thread_local pg_context* c = 0;
-	if (!c && pg_create(0, &c) != PG_OK) fatal("prrn_gpu: %s\n", pg_last_error(0));
-	return (c);
-}
-
 FTYPE* calcdist(mSeq** sbuf, int nn, DistCal realign)
 {
 	Simmtx*	sm = getSimmtx(0);
 	convertseqs(sbuf, nn, sm);			// as the reference does first (src/phyl.cc:320): sets thickness / sumwt
 	// single unweighted sequences only (groups and weighted members go through PwdM in dpscore, src/phyl.cc:233-237)
-	bool	take = realign == DynScr && nn >= 2 && !(algmode.lcl & 16);
+	// (groups and weighted members: the reference's dpscore builds a PwdM per pair and calls HomScore / align2, which
+	// land in shim_alignc.cc -- still the GPU; realign != DynScr is not a DP job at all)
+	bool	take = realign == DynScr && nn >= 2;
 	for (int i = 0; take && i < nn; ++i)
 	    take = sbuf[i]->many == 1 && !sbuf[i]->weight;
+	if (take && (algmode.lcl & 16)) {		// a DP mode the library refuses: fatal() unless PRRN_GPU_ALLOW_REF=1
+	    pg_refused("calcdist", "Smith-Waterman distances (algmode.lcl & 16)");
+	    take = false;
+	}
 	if (!take) {
 	    if (getenv("PRRN_GPU_STATS"))
 		fprintf(stderr, "prrn_gpu calcdist: %d sequences left on the reference's calcdist (realign %d, lcl %d, many %d, sumwt %g)\n",
@@ -68,12 +68,14 @@ FTYPE* calcdist(mSeq** sbuf, int nn, DistCal realign)
 	for (int i = 0; i < sm->dim; ++i)
 	    for (int j = 0; j < sm->dim; ++j) flat[(size_t) i * sm->dim + j] = sm->mtx[i][j];
 	FTYPE*	dist = new FTYPE[ncomb(nn)];		// the caller delete[]s it, as with the reference's own
-	int	rc = pg_calcdist(pg_ctx_dist(), &S, &P, flat.data(), sm->dim, 0, (int64_t) ncomb(nn), dist);
-	if (rc == PG_ERR_UNSUPPORTED) {			// a mode the library refuses: the reference's own code
+	PgLease	ctx;
+	int	rc = pg_calcdist(ctx, &S, &P, flat.data(), sm->dim, 0, (int64_t) ncomb(nn), dist);
+	if (rc == PG_ERR_UNSUPPORTED) {			// a mode the library refuses: fatal() unless PRRN_GPU_ALLOW_REF=1
+	    pg_refused("calcdist", pg_last_error(ctx));
 	    delete[] dist;
 	    return calcdist_ref(sbuf, nn, realign);
 	}
-	if (rc != PG_OK) fatal("prrn_gpu calcdist: %s\n", pg_last_error(pg_ctx_dist()));
+	if (rc != PG_OK) fatal("prrn_gpu calcdist: %s\n", pg_last_error(ctx));
 	if (getenv("PRRN_GPU_STATS"))
 	    fprintf(stderr, "prrn_gpu calcdist: %d sequences, %d pairs in one pg_calcdist call\n", nn, ncomb(nn));
 	return (dist);

@@ -13,17 +13,19 @@
 #include "seq.h"
 #include "aln.h"
 #include "prrn_gpu.h"
+#include "shim_ctx.h"
 
 #include <string.h>
+#include <chrono>
 
-static pg_context* pg_ctx()
-{
-	// one context (CUDA stream + workspace) per calling thread: the reference calls the DP concurrently from
-	// pthread workers (CalcServer, src/calcserv.h:436-457; Prrn::best_of_n, src/prrn5.cc:606-612)
-	static thread_local pg_context* c = 0;
-	if (!c && pg_create(0, &c) != PG_OK) fatal("prrn_gpu: %s\n", pg_last_error(0));
-	return (c);
-}
+// PRRN_GPU_STATS=1: calls and seconds, printed to stderr at exit
+struct PgScoreStats {
+	long	n; double t; bool on; std::mutex mu;
+	PgScoreStats() : n(0), t(0), on(getenv("PRRN_GPU_STATS") != 0) {}
+	~PgScoreStats() {if (on) fprintf(stderr, "prrn_gpu alnScoreD: %ld calls, %.2f s in the library (%.1f us per call)\n", n, t, n? 1e6 * t / n: 0.);}
+};
+static PgScoreStats	pg_sstats;
+static double	pg_snow() {return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();}
 
 static void pg_fill_params(pg_params* p)
 {
@@ -60,10 +62,13 @@ const	Seq*	b = seqs[1];
 	VTYPE*	flat = new VTYPE[sm->dim * sm->dim];
 	for (int i = 0; i < sm->dim; ++i)
 	    for (int j = 0; j < sm->dim; ++j) flat[i * sm->dim + j] = sm->mtx[i][j];
-	int	rc = pg_score_pairs(pg_ctx(), &S, &ia, &ib, 1, &P, flat, sm->dim, &scr,
+	const double	t0 = pg_sstats.on? pg_snow(): 0;
+	PgLease	ctx;		// the reference calls this concurrently from pthread workers: one pooled context per call in flight
+	int	rc = pg_score_pairs(ctx, &S, &ia, &ib, 1, &P, flat, sm->dim, &scr,
 		    (algmode.lcl & 16)? 0: ends);
 	delete[] flat;
 	delete[] res;
-	if (rc != PG_OK) fatal("prrn_gpu alnScoreD: %s\n", pg_last_error(pg_ctx()));
+	if (rc != PG_OK) fatal("prrn_gpu alnScoreD: %s\n", pg_last_error(ctx));
+	if (pg_sstats.on) {std::lock_guard<std::mutex> lk(pg_sstats.mu); ++pg_sstats.n; pg_sstats.t += pg_snow() - t0;}
 	return (scr);
 }

@@ -52,6 +52,26 @@ def test_group_goldens(ctx, name, inline_sim, monkeypatch):
     assert P.group_cells(A, B, gp.sh) == cells
 
 
+def test_homscore_goldens_in_one_call(ctx, oracle):
+    """pg_score_groups = HomScoreC<recd_t>(seqs, pwd, rr) (src/fwd2c.h:663-668): the fill without the path store.
+    Score and rr[2] against the reference's own HomScore for every golden pair (one batch), and against the oracle
+    on other band shoulders."""
+    gs = [golden(n) for n in golden_names("galign_")]
+    scores, rr = ctx.score_groups([stage_golden(g) for g in gs])
+    for k, g in enumerate(gs):
+        want = g["homscore"]
+        assert abs(scores[k] - want["score"]) <= REL_TOL * max(1.0, abs(want["score"])), g["name"]
+        assert rr[k].tolist() == want["rr"], g["name"]
+    for name in ("galign_ntv_3x1_wt", "galign_gpf_prof12_raw5_wt", "galign_gpf_highhetero"):
+        g = golden(name)
+        OA, OB = oracle.group_arrays(g["groups"][0]), oracle.group_arrays(g["groups"][1])
+        for sh in (-100, -25, 3):
+            A, B, gp = stage_golden(g, sh=sh)
+            ws, wrr = oracle.homscore_groups(OA, OB, np.array(g["matrix"]), oracle.gparams_from_dump(g, sh=sh))
+            s1, r1 = ctx.score_groups([(A, B, gp)])
+            assert abs(s1[0] - ws) <= REL_TOL * max(1.0, abs(ws)) and r1[0].tolist() == wrr, (name, sh)
+
+
 @pytest.mark.parametrize("tg", [None, "256", "128"])
 def test_batch_of_all_goldens_in_one_call(ctx, tg, monkeypatch):
     """One launch over every golden pair (different modes, sizes, capacities), three times over: results must

@@ -129,3 +129,99 @@ def test_reference_group_align2_on_gpu_library(name, tmp_path):
     for key in ("alignc", "align2"):
         assert abs(d[key]["score"] - g[key]["score"]) <= 1e-5 * max(1.0, abs(g[key]["score"])), key
         assert d[key]["skl"] == g[key]["skl"], key
+    # HomScore -> HomScoreC<recd_t> (shim_alignc.cc -> pg_score_groups): score and rr[2] of the reference
+    assert abs(d["homscore"]["score"] - g["homscore"]["score"]) <= 1e-5 * max(1.0, abs(g["homscore"]["score"]))
+    assert d["homscore"]["rr"] == g["homscore"]["rr"]
+
+
+def _galign_inputs(name, tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_msa
+    import make_golden as MG
+    captured = {}
+    real = MG.galign_case
+    MG.galign_case = lambda nm, a, b, flavour="d", files=None, **kv: captured.__setitem__(nm, (a, b, flavour, files, kv))
+    try:
+        MG.galign_cases()
+    finally:
+        MG.galign_case = real
+    rows_a, rows_b, flavour, files, kv = captured[name]
+    fa, fb = str(tmp_path / "A"), str(tmp_path / "B")
+    gen_msa.write_native(fa, rows_a, "A")
+    gen_msa.write_native(fb, rows_b, "B")
+    return fa, fb, flavour, kv
+
+
+def test_concurrent_workers_become_one_batch(tmp_path):
+    """The rendezvous of shim_alignc.cc: B pthread workers of the reference reach alignC at the same time (as the
+    workers of Prrn::best_of_n do, src/prrn5.cc:565-612) and leave with their own results from ONE pg_align_groups
+    call; contexts come from the pool (no context per thread)."""
+    import subprocess
+    name = "galign_gpf_prof12_raw5_wt"
+    g = golden(name)
+    fa, fb, flavour, kv = _galign_inputs(name, tmp_path)
+    drv = refio.driver(flavour, gpu=True)
+    if not os.path.exists(drv):
+        pytest.skip("oracle/_ref/ref_driver_%s_gpu is not built" % flavour)
+    env = dict(os.environ, ALN_TAB=os.path.join(refio.REFDIR, "table"), PRRN_GPU_STATS="1", PRRN_GPU_BATCH_WAIT_US="2000000")
+    out = subprocess.run([drv, "galign", fa, "fb=" + fb, "mt=6"] + ["%s=%s" % kvp for kvp in kv.items()],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    d = refio.parse_galign(out.stdout)
+    assert len(d["mt"]) == 6
+    for m in d["mt"]:
+        assert abs(m["score"] - g["align2"]["score"]) <= 1e-5 * max(1.0, abs(g["align2"]["score"]))
+        assert m["skl"] == g["align2"]["skl"]
+    assert "largest 6" in out.stderr, out.stderr[-400:]
+    import re
+    assert int(re.search(r"(\d+) contexts", out.stderr).group(1)) <= 2, out.stderr[-400:]
+    # and with the rendezvous off: six library calls, same results
+    env["PRRN_GPU_BATCH"] = "0"
+    out = subprocess.run([drv, "galign", fa, "fb=" + fb, "mt=6"] + ["%s=%s" % kvp for kvp in kv.items()],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    assert "largest 1" in out.stderr
+    assert [m["skl"] for m in refio.parse_galign(out.stdout)["mt"]] == [g["align2"]["skl"]] * 6
+
+
+def test_refused_calls_are_fatal_unless_allowed(tmp_path):
+    """No silent CPU fallback in the shims: a rectangle (-A) alignment is refused with the reference's fatal()
+    unless PRRN_GPU_ALLOW_REF=1, and then it is announced."""
+    import subprocess
+    fa, fb, flavour, kv = _galign_inputs("galign_gpf_raw3x3", tmp_path)
+    drv = refio.driver(flavour, gpu=True)
+    if not os.path.exists(drv):
+        pytest.skip("oracle/_ref/ref_driver_%s_gpu is not built" % flavour)
+    env = dict(os.environ, ALN_TAB=os.path.join(refio.REFDIR, "table"))
+    env.pop("PRRN_GPU_ALLOW_REF", None)
+    cmd = [drv, "galign", fa, "fb=" + fb, "bnd=0"] + ["%s=%s" % kvp for kvp in kv.items()]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0 and "no CPU fallback" in out.stderr
+    env["PRRN_GPU_ALLOW_REF"] = "1"
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "left on the reference's own code" in out.stderr
+
+
+ALIGNB_CASES = ["alignb_p12_blosum62", "alignb_p12_pam_f64", "alignb_p12_twopiece_f64", "alignb_rag10_tgapf05_f64",
+                "alignb_rag10_lcl15_f64", "alignb_rag10_lcl6", "alignb_rag10_lcl9_twopiece_f64", "alignb_long700"]
+
+
+@pytest.mark.parametrize("name", ALIGNB_CASES)
+def test_reference_alignB_ng_on_gpu_library(name, tmp_path):
+    """shim/shim_fwd2b1.cc: the reference's alignB_ng / HomScoreB_ng symbols (Aln2b1, what prrn5's DynAln distances
+    call, src/adjmat.cc:78-88) bound to pg_align_pairs_ng; stdskl stays the reference's own."""
+    g = golden(name)
+    fl = g["flavour"]
+    if not os.path.exists(refio.driver(fl, gpu=True)):
+        pytest.skip("oracle/_ref/ref_driver_%s_gpu is not built" % fl)
+    fa = str(tmp_path / "in.fa")
+    gen_synth.write_fasta(fa, g["seqs"])
+    al = refio.run("alignb", fa, flavour=fl, gpu=True, **g["args"])
+    exact = fl == "d" or np.all(np.nan_to_num(np.array(g["matrix"])) == np.rint(np.nan_to_num(np.array(g["matrix"]))))
+    for p in g["pairs"]:
+        r = al["alignb"][(p["i"], p["j"])]
+        if exact:
+            assert r["score"] == p["score"] and r["hom"] == p["hom"], (p["i"], p["j"])
+            assert [list(x) for x in r["skl"]] == [list(x) for x in p["skl"]], (p["i"], p["j"])
+        else:
+            assert abs(r["score"] - p["score"]) <= 1e-5 * max(1.0, abs(p["score"]))

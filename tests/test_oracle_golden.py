@@ -89,6 +89,9 @@ def test_group_alignment_bit_exact(oracle, name):
     a, b = g["groups"]
     want_cells = sum(max(0, min(m + up + 1, b["right"]) - max(m + lw, b["left"])) for m in range(a["left"], a["right"]))
     assert cells == want_cells
+    # HomScore -> HomScoreC<recd_t>(seqs, pwd, rr): Fwd2c without Vmf, ptr = diagonal of the last first-row cell
+    hs, rr = oracle.homscore_groups(A, B, np.array(g["matrix"]), gp)
+    assert hs == g["homscore"]["score"] and rr == g["homscore"]["rr"]
 
 
 @pytest.mark.parametrize("name", golden_names("alignb_"))

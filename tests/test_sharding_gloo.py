@@ -26,6 +26,27 @@ def test_shard_ranges_cover_everything():
             assert all(cov[i][1] == cov[i + 1][0] for i in range(world - 1))
 
 
+def test_cost_model_equals_the_library_cell_count_and_ranges_balance():
+    """sharding.band_cells / row_costs (numpy) against pg_calcdist_cells (C, host-only) on ragged lengths and several
+    band shoulders; cost-balanced shard ranges cover the condensed index and carry equal numbers of DP cells."""
+    rng = np.random.default_rng(3)
+    lens = np.concatenate([rng.integers(1, 40, size=30), rng.integers(300, 420, size=60), [0, 1, 2]])
+    rng.shuffle(lens)
+    enc = [rng.integers(3, 23, size=int(n)).astype(np.uint8) for n in lens]
+    ss = P.SeqSet(enc)
+    npair = len(lens) * (len(lens) - 1) // 2
+    for sh in (-60, -20, 0, 3, 1000):
+        prm = P.Params(P.ALPRM(sh=sh))
+        cost, _, _ = sharding.row_costs(lens, sh)
+        assert int(cost.sum()) == P.calcdist_cells(ss, prm), sh
+        for world in (1, 2, 3, 8):
+            rg = sharding.cost_balanced_ranges(lens, sh, world)
+            assert rg[0][0] == 0 and rg[-1][1] == npair and all(rg[i][1] == rg[i + 1][0] for i in range(world - 1))
+            cells = [P.calcdist_cells(ss, prm, a, b) for a, b in rg]
+            assert sum(cells) == int(cost.sum())
+            assert max(cells) - min(cells) <= 2 * int(sharding.band_cells(lens[:, None], lens[None, :], sh).max()) + 1, (sh, world, cells)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

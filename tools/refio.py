@@ -135,6 +135,15 @@ def parse_galign(text):
             r["window"] = [int(x) for x in t[1:4]]
         elif t[0] == "time":
             r["time"] = float(t[1])
+        elif t[0] == "mt":
+            pts = None
+            if t[3] == "skl" and t[4] != "0":
+                n = int(t[4])
+                v = [int(x) for x in t[7:7 + 2 * n]]
+                pts = [list(x) for x in zip(v[0::2], v[1::2])]
+            r.setdefault("mt", []).append(dict(score=float(t[2]), skl=pts))
+        elif t[0] == "homscore":
+            r["homscore"] = dict(score=float(t[1]), rr=[int(t[2]), int(t[3])])
         elif t[0] in ("alignc", "align2"):
             off = 1 if t[0] == "alignc" else 3
             scr = float(t[off])

@@ -1,13 +1,23 @@
 #!/usr/bin/env python
-"""End-to-end `prrn` MSA runs (the "prrn MSA wall-s" part of BASELINE.json's metric): the reference's own
-prrn5 program, unmodified, (a) as it is -- every DP on the host CPU -- and (b) linked with shim/*.cc so
-that alnScoreD and alignC<DPunit | DPunit_hf | DPunit_pf> run in libprrn_gpu.so (oracle/Makefile: prrn).
-Prints one JSON line per input: wall seconds of both, and whether the two MSAs are identical.
+"""End-to-end `prrn` MSA runs (the "prrn MSA wall-s" part of BASELINE.json's metric): the reference's own prrn5
+program, unmodified, (a) as it is -- every DP on the host CPU (oracle/_ref/prrn5_cpu) -- and (b) linked with shim/*.cc
+so that alnScoreD, calcdist, alignC / HomScoreC and alignB_ng run in libprrn_gpu.so (oracle/_ref/prrn5_gpu).
 
-Note what (b) is and is not: the shims are PER-CALL bindings.  prrn5's refinement is a chain of dependent
-align2 calls, so each group alignment is a batch of ONE on the GPU (K3's latency mode); the batch entry
-points (pg_calcdist, pg_align_groups over best_of_n candidates) need the two small source patches of
-INTEGRATION.md and are not exercised here."""
+    python tools/run_prrn.py [--arm cpu|gpu|both] [--freeze] CONFIG ...
+
+CONFIG:
+    small      40 x ~200 aa                      prrn5 -m blosum62
+    mid        80 x ~300 aa                      prrn5 -m blosum62
+    c3         200 x ~500 aa (BASELINE config 3) prrn5 -m blosum62
+    c3t4       the MSA of c3 as a pre-aligned start, refined with B = 4 candidate partitions per cycle
+               (Prrn::best_of_n, src/prrn5.cc:594): prrn5 -m blosum62 -t4 -r4   (needs c3's CPU output first)
+    c4n50 / c4n60 / c4n100   the first 50 / 60 / 100 of the 100 DNA sequences of ~2 kb of BASELINE config 4, two-piece
+               gap penalties: prrn5 -yl3  (the stock reference crashes above 60 DNA members, SURVEY.md N4: n100 is
+               GPU-timed only)
+Prints one JSON line per config: wall seconds per arm, md5 of the MSA body, and whether the arms agree with each other
+and with the frozen result of the CPU arm (tests/golden/prrn_msa.json; --freeze writes it, in the container where
+/root/reference was built)."""
+import argparse
 import hashlib
 import json
 import os
@@ -20,37 +30,94 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import gen_synth  # noqa: E402
 
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
-EXTRA = os.environ.get("PRRN_ARGS", "").split()     # e.g. PRRN_ARGS="-t16": pthread workers (best_of_n, CalcServer)
+FROZEN = os.path.join(ROOT, "tests", "golden", "prrn_msa.json")
+BIN = {"cpu": "prrn5_cpu", "gpu": "prrn5_gpu"}
+
+CONFIGS = {
+    "small": dict(seqs=lambda: gen_synth.synth_set(40, 200, 0.1, 0.6, 3), args=["-m", "blosum62"]),
+    "mid": dict(seqs=lambda: gen_synth.synth_set(80, 300, 0.1, 0.6, 2), args=["-m", "blosum62"]),
+    "c3": dict(seqs=lambda: gen_synth.config_set("c3"), args=["-m", "blosum62"]),
+    "c3t4": dict(start="c3", args=["-m", "blosum62", "-t4", "-r4"]),
+    "c4n20": dict(seqs=lambda: gen_synth.config_set("c4", 20), args=["-yl3"]),
+    "c4n50": dict(seqs=lambda: gen_synth.config_set("c4", 50), args=["-yl3"]),
+    "c4n60": dict(seqs=lambda: gen_synth.config_set("c4", 60), args=["-yl3"]),
+    "c4n100": dict(seqs=lambda: gen_synth.config_set("c4", 100), args=["-yl3"], gpu_only=True),
+}
 
 
-def run(binary, fa, extra):
+def msa_body(stdout):
+    return "\n".join(l for l in stdout.splitlines() if not l.startswith(">") and "sec" not in l)
+
+
+def run(arm, path, args, env_extra=None, timeout=3000):
     env = dict(os.environ, ALN_TAB=os.path.join(REFDIR, "table"))
+    env.update(env_extra or {})
     t0 = time.perf_counter()
-    out = subprocess.run([os.path.join(REFDIR, binary)] + extra + [fa], env=env, capture_output=True, text=True, timeout=3000)
+    out = subprocess.run([os.path.join(REFDIR, BIN[arm])] + args + [path], env=env, capture_output=True, text=True,
+                         timeout=timeout)
     dt = time.perf_counter() - t0
-    body = "\n".join(l for l in out.stdout.splitlines() if not l.startswith(">") and "sec" not in l)
-    return dt, out.returncode, hashlib.md5(body.encode()).hexdigest(), out.stdout, out.stderr[-300:]
+    r = {"wall_s": dt, "rc": out.returncode, "msa_md5": hashlib.md5(msa_body(out.stdout).encode()).hexdigest(),
+         "lines": len(out.stdout.splitlines())}
+    if out.returncode:
+        r["stderr"] = out.stderr[-400:]
+    stats = [l for l in out.stderr.splitlines() if l.startswith("prrn_gpu")]
+    if stats:
+        r["stats"] = stats
+    return r, out.stdout
+
+
+def input_path(name):
+    c = CONFIGS[name]
+    path = "/tmp/prrn_in_%s.fa" % name
+    if "start" in c:        # pre-aligned start = the frozen MSA of another config (the CPU arm's own output)
+        src = os.path.join(ROOT, "tests", "golden", "prrn_%s_cpu.msa" % c["start"])
+        if not os.path.exists(src):
+            return None
+        return src
+    gen_synth.write_fasta(path, c["seqs"]())
+    return path
 
 
 def main():
-    cases = [(40, 200, 3), (200, 500, 1)] if len(sys.argv) < 2 else [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
-    for n, length, seed in cases:
-        fa = "/tmp/prrn_in_%d_%d.fa" % (n, length)
-        gen_synth.write_fasta(fa, gen_synth.synth_set(n, length, 0.1, 0.6, seed))
-        res = {"config": "prrn5 %s %d x ~%d aa (seed %d)" % (" ".join(EXTRA), n, length, seed), "host_cores": os.cpu_count()}
-        outs = {}
-        for tag, binary in (("cpu", "prrn5_cpu"), ("gpu_shims", "prrn5_gpu")):
-            if not os.path.exists(os.path.join(REFDIR, binary)):
-                res[tag] = "not built"
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--arm", default="both", choices=["cpu", "gpu", "both"])
+    ap.add_argument("--freeze", action="store_true", help="record the CPU arm's md5 (and keep c3's MSA as the start of c3t4)")
+    ap.add_argument("configs", nargs="+")
+    a = ap.parse_args()
+    frozen = json.load(open(FROZEN)) if os.path.exists(FROZEN) else {}
+    for name in a.configs:
+        c = CONFIGS[name]
+        path = input_path(name)
+        res = {"config": name, "command": "prrn5 " + " ".join(c["args"]), "host_cores": os.cpu_count()}
+        if path is None:
+            res["unavailable"] = "pre-aligned start missing: run --freeze %s first" % c["start"]
+            print(json.dumps(res), flush=True)
+            continue
+        arms = ["cpu", "gpu"] if a.arm == "both" else [a.arm]
+        if c.get("gpu_only") and "cpu" in arms:
+            arms.remove("cpu")
+        for arm in arms:
+            if not os.path.exists(os.path.join(REFDIR, BIN[arm])):
+                res[arm] = "not built"
                 continue
-            dt, rc, md5, out, err = run(binary, fa, ["-m", "blosum62"] + EXTRA)
-            res[tag] = {"wall_s": dt, "rc": rc, "msa_md5": md5, "lines": len(out.splitlines())}
-            if rc:
-                res[tag]["stderr"] = err
-            outs[tag] = out
-        if len(outs) == 2:
-            res["identical_msa"] = res["cpu"]["msa_md5"] == res["gpu_shims"]["msa_md5"]
-        print(json.dumps(res))
+            env = {"PRRN_GPU_STATS": "1"} if arm == "gpu" else {}
+            r, stdout = run(arm, path, c["args"], env)
+            res[arm] = r
+            if arm == "cpu" and a.freeze and r["rc"] == 0:
+                frozen[name] = {"msa_md5": r["msa_md5"], "lines": r["lines"], "cpu_wall_s_here": round(r["wall_s"], 2),
+                                "command": res["command"]}
+                if name == "c3":
+                    with open(os.path.join(ROOT, "tests", "golden", "prrn_c3_cpu.msa"), "w") as f:
+                        f.write(stdout)
+        if isinstance(res.get("cpu"), dict) and isinstance(res.get("gpu"), dict):
+            res["identical_msa"] = res["cpu"]["msa_md5"] == res["gpu"]["msa_md5"]
+        if name in frozen and isinstance(res.get("gpu"), dict):
+            res["gpu_equals_frozen_cpu_msa"] = res["gpu"]["msa_md5"] == frozen[name]["msa_md5"]
+            res["frozen_cpu_wall_s_container"] = frozen[name]["cpu_wall_s_here"]
+        print(json.dumps(res), flush=True)
+    if a.freeze:
+        with open(FROZEN, "w") as f:
+            json.dump(frozen, f, indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
