@@ -587,7 +587,7 @@ cudaError_t launch_cluster(const K3Args& a, int clusters, cudaStream_t st)
 template <int TG, bool SPLIT, bool SM>
 cudaError_t launch_tg(const K3Args& a, int mode, int grid_blocks, cudaStream_t st)
 {
-    if (SPLIT && SM && a.cluster > 1) {
+    if (SPLIT && SM && (a.cluster > 1 || a.rows192)) {
         cudaError_t e;
         switch (mode) {
         case 0: e = launch_cluster<0>(a, grid_blocks, st); break;
@@ -598,6 +598,7 @@ cudaError_t launch_tg(const K3Args& a, int mode, int grid_blocks, cudaStream_t s
         }
         if (e == cudaSuccess) return e;
         (void)cudaGetLastError();       // a cluster of this size cannot be co-scheduled here: the single-CTA kernel below
+        if (a.rows192) return launch_tg<256, false, false>(a, mode, grid_blocks, st);   // (256 rows do not fit shared memory)
     }
     switch (mode) {
     case 0: return launch_tgm<TG, SPLIT, 0, SM>(a, grid_blocks, st);
@@ -645,6 +646,8 @@ cudaError_t k3_launch(const K3Args& a, int tg, int mode, int grid_blocks, cudaSt
     default: return launch_tg<256, false, true>(a, mode, grid_blocks, st);
     }
 }
+
+bool k3_sm_fits_rows(int stride, int Noll, int rows, size_t smem_bytes) { return k3_sm_ok(stride, Noll, rows, smem_bytes / 4); }
 
 bool k3_sm_fits(int stride, int Noll, int tg, size_t smem_bytes)
 {

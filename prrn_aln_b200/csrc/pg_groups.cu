@@ -407,9 +407,16 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         for (int64_t k = k0; k < k1 && km.all_sm; ++k)
             km.all_sm = k3_sm_fits(k3_stride(sorted[k].prm.capa, sorted[k].prm.capb), sorted[k].prm.Noll, tg_sel,
                                    (size_t)ka.smem_bytes) ? 1 : 0;
+        km.cluster = nc_mode[mode];
+        if (!km.all_sm && tg_sel == 768) {      // long records (high hetero, two-piece): 192 rows per CTA may still fit
+            km.rows192 = 1;
+            for (int64_t k = k0; k < k1 && km.rows192; ++k)
+                km.rows192 = k3_sm_fits_rows(k3_stride(sorted[k].prm.capa, sorted[k].prm.capb), sorted[k].prm.Noll,
+                                             k3_cluster_rows(), (size_t)ka.smem_bytes) ? 1 : 0;
+            km.all_sm = km.rows192;
+        }
         km.arena = ka.arena + (size_t)slot0_mode[mode] * arena_words;
         km.vmf = ka.vmf + (size_t)vslot0_mode[mode] * (size_t)vmf_cap;
-        km.cluster = nc_mode[mode];
         e = cudaStreamWaitEvent(c->aux[mode], c->ev_fork, 0);
         if (e == cudaSuccess) e = k3_launch(km, tg_sel, mode, gm, c->aux[mode]);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev_join[mode], c->aux[mode]);

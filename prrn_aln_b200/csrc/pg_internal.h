@@ -167,6 +167,8 @@ struct K3Args {
     int32_t all_sm;             // every pair fits the all-shared-memory variant (k3_sm_fits)
     int32_t cluster;            // latency mode: CTAs (thread-block cluster size) per alignment, 1 = none
     int32_t cluster_fence;      // cluster variant: cluster-scope acquire in the per-step hand-shake (PG_K3_CLUSTER_FENCE)
+    int32_t rows192;            // the records fit shared memory only with 192 rows per CTA: the cluster kernel's geometry,
+                                // also for a "cluster" of one CTA (long gap-state lists: high hetero, two-piece)
 };
 
 // profile contraction (k4_contract.cu): S = X_a . Y_b^T per pair, written to K3Pair::simmat
@@ -275,6 +277,7 @@ int k3_cluster_rows();        // rows per CTA of the cluster latency kernel
 int k3_blocks_per_sm();
 int k3_pick_tg(int64_t npairs, int sm_count);
 bool k3_sm_fits(int stride, int Noll, int tg, size_t smem_bytes);
+bool k3_sm_fits_rows(int stride, int Noll, int rows, size_t smem_bytes);
 size_t k3_wave_words(int stride, int Noll, int tg);
 // k4_contract.cu
 cudaError_t k4_launch(const K4Args& a, int total_blocks, cudaStream_t st);

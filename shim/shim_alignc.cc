@@ -41,6 +41,8 @@
 #include <dlfcn.h>
 #include <pthread.h>
 
+#include <math.h>
+
 #include <chrono>
 #include <condition_variable>
 #include <cstdlib>
@@ -117,6 +119,10 @@ static void pg_stage(mSeq* sd, PgSide& S, const PwdM* pwd, bool is_a, const Simm
 	    } else {					// residue counts (weights) per code
 		for (int i = 0; i < sd->many; ++i) v[it.res[i]] += sd->weight? sd->weight[i]: 1.;
 	    }
+	    // Entries of residue codes that never occur may be uninitialised in Simmtx (and in the profiles convseq derives
+	    // from it): the reference indexes by residue and never reads them, the contraction meets them with weight 0,
+	    // and 0 x NaN is NaN.  Non-finite entries therefore count as 0.
+	    for (int k = 0; k < K; ++k) if (!(fabs(v[k]) <= 1.7e308)) v[k] = 0;
 	    if (it.sfq) {S.sfq[x] = S.pool(it.sfq); S.tfq[x] = S.pool(it.tfq); S.rfq[x] = S.pool(it.rfq);}
 	}
 	if (S.glen.empty()) {S.glen.push_back(-1); S.gfreq.push_back(0);}
@@ -376,6 +382,50 @@ static void pg_stage_job(mSeq* seqs[], PwdM* pwd, PgJob* job, bool score_only)
 	}
 }
 
+// PRRN_GPU_TRACE=1: one line per call on stderr (what reaches the DP, how long the kernels took).
+// PRRN_GPU_VERIFY=1: after every call, the reference's own Fwd2c runs on the same inputs and the two results are
+// compared (score within 1e-5 relative, corner lists identical); differences are reported on stderr and counted.
+// PRRN_GPU_VERIFY=2 additionally continues with the reference's result, so that one divergent call does not change
+// the inputs of all later ones.  Debugging aids for end-to-end parity runs (off by default; the reference's own code).
+static const int	pg_verify = getenv("PRRN_GPU_VERIFY")? atoi(getenv("PRRN_GPU_VERIFY")): 0;
+static const bool	pg_trace = getenv("PRRN_GPU_TRACE") != 0;
+static long	pg_vcalls = 0, pg_vbad = 0;
+struct PgVerifyReport {~PgVerifyReport() {if (pg_verify) fprintf(stderr, "prrn_gpu verify: %ld calls compared with the reference's Fwd2c, %ld differ\n", pg_vcalls, pg_vbad);}};
+static PgVerifyReport	pg_vreport;
+
+template <class recd_t>
+static SKL* pg_check(mSeq* seqs[], PwdM* pwd, VTYPE* scr, SKL* skl, const char* route)
+{
+	if (pg_trace)
+	    fprintf(stderr, "prrn_gpu trace: %s alnmode %d Noll %d members %d x %d columns %d x %d hetero %d / %d nils %d %d sh %d score %.10g corners %d\n",
+		route, pwd->alnmode, pwd->Noll, seqs[0]->many, seqs[1]->many, seqs[0]->right - seqs[0]->left, seqs[1]->right - seqs[1]->left,
+		seqs[0]->gfq? seqs[0]->gfq->hetero: -1, seqs[1]->gfq? seqs[1]->gfq->hetero: -1, (int) seqs[0]->inex.nils, (int) seqs[1]->inex.nils,
+		pwd->alnprm.sh, (double) *scr, skl? skl->n: -1);
+	if (!pg_verify) return skl;
+	Fwd2c<recd_t>	pwa(seqs, pwd, true, false, 0);
+	VTYPE	rs = pwa.forwardB(0);
+	SKL*	rk = pwa.traceback();
+	bool	same = fabs((double) rs - (double) *scr) <= 1e-5 * (fabs((double) rs) > 1? fabs((double) rs): 1.) && rk && skl && rk->n == skl->n;
+	int	first = -1;
+	if (same) for (int k = 1; k <= rk->n; ++k) if (rk[k].m != skl[k].m || rk[k].n != skl[k].n) {same = false; first = k; break;}
+	static std::mutex	mu;
+	std::lock_guard<std::mutex>	lk(mu);
+	++pg_vcalls;
+	if (!same) {
+	    ++pg_vbad;
+	    fprintf(stderr, "prrn_gpu verify: call %ld (%s) DIFFERS: alnmode %d Noll %d members %d x %d window [%d,%d) x [%d,%d) hetero %d / %d nils %d %d "
+		"sh %d: score gpu %.12g ref %.12g, corners gpu %d ref %d, first differing corner %d", pg_vcalls, route, pwd->alnmode, pwd->Noll,
+		seqs[0]->many, seqs[1]->many, seqs[0]->left, seqs[0]->right, seqs[1]->left, seqs[1]->right,
+		seqs[0]->gfq? seqs[0]->gfq->hetero: -1, seqs[1]->gfq? seqs[1]->gfq->hetero: -1, (int) seqs[0]->inex.nils, (int) seqs[1]->inex.nils,
+		pwd->alnprm.sh, (double) *scr, (double) rs, skl? skl->n: -1, rk? rk->n: -1, first);
+	    if (first > 0) fprintf(stderr, " (gpu %d,%d ref %d,%d)", skl[first].m, skl[first].n, rk[first].m, rk[first].n);
+	    fputc('\n', stderr);
+	}
+	if (pg_verify >= 2) {delete[] skl; *scr = rs; return rk;}
+	delete[] rk;
+	return skl;
+}
+
 template <class recd_t>
 static SKL* pg_alignC(mSeq* seqs[], PwdM* pwd, VTYPE* scr, bool rectangle, WINDOW* pwdw)
 {
@@ -388,12 +438,12 @@ static SKL* pg_alignC(mSeq* seqs[], PwdM* pwd, VTYPE* scr, bool rectangle, WINDO
 	    if (pg_stats.on) {std::lock_guard<std::mutex> lk(pg_stats.mu); ++pg_stats.n_ref; pg_stats.t_ref += pg_now() - t0;}
 	    return r;
 	}
-	if (pg_plain_pair(seqs, pwd)) return pg_align_plain_pair(seqs, pwd, scr);
+	if (pg_plain_pair(seqs, pwd)) return pg_check<recd_t>(seqs, pwd, scr, pg_align_plain_pair(seqs, pwd, scr), "pair");
 	PgJob	job;
 	pg_stage_job(seqs, pwd, &job, false);
 	pg_submit(&job);
 	*scr = (VTYPE) job.score;
-	return pg_skl_from(job.pts.data(), (int) job.pts.size());
+	return pg_check<recd_t>(seqs, pwd, scr, pg_skl_from(job.pts.data(), (int) job.pts.size()), "groups");
 }
 
 template <class recd_t>
