@@ -195,6 +195,58 @@ def group_side_measurement():
         return {"error": repr(e)[:300]}
 
 
+def group_candidates_measurement(P, torch, dist, rank, world, local):
+    """SURVEY.md 8(e), row 4: the B candidate partitions of one refinement step (Prrn::best_of_n, src/prrn5.cc:594) are
+    independent -- B / N per GPU by a longest-processing-time split of their DP cells (sharding.shard_candidates), every
+    rank aligns its share with pg_align_groups, ONE all-reduce(MAX) of B doubles over NCCL picks the winner."""
+    try:
+        import argparse as _ap
+        import bench_groups
+        import refio
+        from prrn_aln_b200 import groups as G
+        from prrn_aln_b200 import sharding
+        if not refio.available("d"):
+            return {"unavailable": "oracle/_ref/ref_driver_d (the reference's staging of groups) is not built"}
+        a = _ap.Namespace(members=200, length=500, pairs=24, sh=-60, seed=7, cpu_rep=1)
+        dumps = bench_groups.build_pairs(a)             # every rank stages the same candidates (replicated MSA state)
+        rep = 8
+        staged, costs = [], []
+        for d in dumps:
+            pm, pc, h = d["pwdm"], d["pwdc"], d["header"]
+            A, B = G.stage_pair(d["groups"][0], d["groups"][1], pm["a_mode"], pm["b_mode"], d["matrix"], dxd=(pm["DvsP"] == 0))
+            gp = P.gparams_from_pwd(pm["alnmode"], pm["Noll"], pm["codonk1"], int(h["sh"]), A["vec"].shape[1], float(h["u"]),
+                                    float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
+            staged.append((A, B, gp))
+            costs.append(int(P.group_cells(A, B, gp.sh)))
+        staged, costs = staged * rep, costs * rep
+        ctx = P.Context(local)
+
+        def scores_of(idx):
+            return list(ctx.align_groups([staged[i] for i in idx])[0])
+        for _ in range(3):
+            sharding.best_of_n_sharded(scores_of, costs, rank, world, dist)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        steps = 3
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            best, val, allv = sharding.best_of_n_sharded(scores_of, costs, rank, world, dist)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        ctx.close()
+        want = [d["alignc"]["score"] for d in dumps] * rep
+        bad = sum(1 for x, w in zip(allv.tolist(), want) if abs(x - w) > 1e-5 * max(1.0, abs(w)))
+        return {"metric": "group-to-group DP GCUPS (candidate partitions sharded over GPUs, host-buffer calls)",
+                "value": sum(costs) * steps / float(dt.item()) / 1e9, "unit": "GCUPS", "n_gpus": world, "ms_per_step": 1e3 * float(dt.item()) / steps,
+                "candidates": len(costs), "cells": int(sum(costs)), "best": best, "best_score": val, "score_mismatches_vs_reference": bad,
+                "collective": "nccl all_reduce(max) of %d doubles" % len(costs) if world > 1 else None, "scaling": "strong"}
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
 def prrn_msa_measurement():
     """The third part of BASELINE.json's metric: `prrn` MSA wall seconds on config 3 (200 x ~500 aa, prrn5 -m blosum62):
     the reference's own prrn5 program as it is (every DP on ONE host core: upstream's threaded mode crashes on
@@ -479,6 +531,10 @@ def main():
                                "sample": "first %d of the 1000 sequences: %d pairs, %.3g cells, %.2f s" % (
                                    CPU_SAMPLE_N, CPU_SAMPLE_N * (CPU_SAMPLE_N - 1) // 2, cells, dtc)}
     ctx.close()
+    if world > 1 and not args.no_groups:
+        gc = group_candidates_measurement(P, torch, dist, rank, world, local)
+        if rank == 0:
+            out["group_candidates"] = gc
     if rank == 0 and world == 1 and not args.no_groups:
         out["group_to_group"] = group_side_measurement()
     if rank == 0 and world == 1 and not args.no_prrn:

@@ -43,6 +43,8 @@ struct K3Group {
     const double* weight;   // [many] member weights (1 when the reference has none)
     int32_t many;
     int32_t pad;
+    // register-list form (k3r_core.cuh): fixed-stride column blocks {cfq, efq, freq[3][CS], glen[3][CS]}, or null
+    const int* blk;
 };
 
 struct K3Prm {
@@ -64,6 +66,9 @@ struct K3Prm {
     // score only (HomScoreC, src/fwd2c.h:663-668: Fwd2c without Vmf): no path records; ptr carries the diagonal
     // n - m of the path's last first-row cell instead (fwd2c.h:468-469), the origin's b.left - a.left otherwise
     int32_t novmf, origin_r;
+    // register-list form (k3r_core.cuh): words per dynamic list (4, 6 or 8; capa / capb then describe the same
+    // records), 0 = the list-walking form of this file
+    int32_t rl, pad2;
 };
 
 // ---- record access -------------------------------------------------------------------------------

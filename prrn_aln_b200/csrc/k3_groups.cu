@@ -27,6 +27,7 @@
 #include <string.h>
 
 #include "k3_core.cuh"
+#include "k3r_core.cuh"
 #include "pg_internal.h"
 
 namespace {
@@ -37,6 +38,8 @@ constexpr int PFN = 4;              // prefetch words per thread (3 * stride <= 
 constexpr int XD = 8;               // cluster variant: depth of the ring of neighbour records (steps a CTA may lead)
 constexpr int TGCL = 192;           // cluster variant: rows per CTA (3 x 192 = 576 threads leave 112 registers per thread;
                                     // with 3 x 256 the extra hand-over state spilled into local memory: +2.4 us per step)
+constexpr int TGRL = 128;           // register-list form (k3r_core.cuh): rows per CTA; 3 x 128 threads, two CTAs per SM,
+                                    // 168 registers per thread (the records and lists of a cell live in registers)
 
 // words of shared memory one alignment needs for its wavefront records
 __host__ __device__ inline size_t k3_smem_words(int st, int Noll, int tg)
@@ -151,11 +154,15 @@ __device__ __noinline__ void cl_release(unsigned empty_addr, int S)
 // thread of CTA c-1 published one and two steps ago through distributed shared memory (copied to a local
 // slot, so the cell code still sees shared-memory records); every step ends in a cluster barrier; the path
 // records of CTA c live in its own part of the store (id = c * vmf_cap + local id).
-template <int TG, bool SPLIT, int MODE, bool SM, bool CL>
+// RL (register lists, k3r_core.cuh): 0 = the list-walking cell of k3_core.cuh; 4 / 6 / 8 = words per dynamic list of the
+// branch-free register form (record modes 1 and 2, role-split shared-memory kernels, TGRL rows per CTA).
+template <int TG, bool SPLIT, int MODE, bool SM, bool CL, int RL>
 __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_kernel(const K3Args a)
 {
     static_assert(!CL || (SPLIT && SM), "the cluster variant is the role-split shared-memory kernel");
-    static_assert(!SPLIT || CL || TG == CTA, "role-split without clusters runs 3 x 256 threads");
+    static_assert(!SPLIT || CL || TG == CTA || RL, "role-split without clusters runs 3 x 256 threads");
+    static_assert(!RL || (SPLIT && SM && (MODE == 1 || MODE == 2) && TG == TGRL), "register lists: modes 1 / 2, role-split, shared memory");
+    constexpr int RCAP = RL ? RL : 4, RCS = RCAP - 2, RMODE = MODE == 2 ? 2 : 1;      // (valid template arguments also when RL == 0)
     namespace cg = cooperative_groups;
     constexpr int NG = SPLIT ? 1 : CTA / TG;        // alignments in flight per CTA
 #define NC (CL ? cl_size() : 1)                     /* CTAs per alignment */
@@ -177,6 +184,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
 
 #define GSYNC() do { if (CL) cg::this_cluster().sync(); else if (SPLIT) __syncthreads(); else group_sync<TG>(g); } while (0)
 #define GSTEP() do { if (SPLIT) __syncthreads(); else group_sync<TG>(g); } while (0)       /* end of one step */
+#define RESET(ptr) do { if (RL) k3r_reset<RCAP, RMODE>(ptr); else k3_reset(p, ptr); } while (0)
+#define RCOPY(d, s) do { if (RL) k3r_copy_words(d, s, st); else k3_copy(p, d, s); } while (0)
     // CL: ring hand-over (see above): full[slot] counts the push of the CTA above, empty[slot] the release by the CTA below
     __shared__ __align__(8) unsigned long long sm_full[XD], sm_empty[XD];
     for (;;) {
@@ -206,6 +215,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
 #undef K3_GLOBAL
         const int LQ = A.L, LS = B.L;
         const int st = k3_stride(p.capa, p.capb);
+        constexpr int BW = k3r_block_words(RCS);              // words per static column block (register-list form)
+        if (RL) { __builtin_assume(__isGlobal(A.blk)); __builtin_assume(__isGlobal(B.blk)); }
         const bool n3 = p.Noll == 3;
         // parked rows / boundary column: global arena (L2).  rowH[k] = H(pbase-1, k-1), colH[k] = H(k-1, -1)
         int* const rowH = arena;
@@ -237,16 +248,16 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
         if (role == 0) {
         if (crank == 0) {
         for (int i = t; i < LS + 2; i += TG) {
-            k3_reset(p, rowH + (size_t)i * st); k3_reset(p, rowG + (size_t)i * st);
-            if (n3) k3_reset(p, rowG2 + (size_t)i * st);
+            RESET(rowH + (size_t)i * st); RESET(rowG + (size_t)i * st);
+            if (n3) RESET(rowG2 + (size_t)i * st);
         }
-        for (int i = t; i < LQ + 2; i += TG) k3_reset(p, colH + (size_t)i * st);
+        for (int i = t; i < LQ + 2; i += TG) RESET(colH + (size_t)i * st);
         if (CL && t == 0) { ghdr[0] = 0; ghdr[1] = 0; }
         }
-        for (int k = 0; k < 3; ++k) k3_reset(p, pubH + ((size_t)k * TG + t) * st);
-        for (int k = 0; k < 2; ++k) { k3_reset(p, pubG + ((size_t)k * TG + t) * st); if (n3) k3_reset(p, pubG2 + ((size_t)k * TG + t) * st); }
-        if (t < RING) { k3_reset(p, ringH + (size_t)t * st); k3_reset(p, ringG + (size_t)t * st); k3_reset(p, ringG2 + (size_t)t * st); }
-        if (t == 0) k3_reset(p, black);
+        for (int k = 0; k < 3; ++k) RESET(pubH + ((size_t)k * TG + t) * st);
+        for (int k = 0; k < 2; ++k) { RESET(pubG + ((size_t)k * TG + t) * st); if (n3) RESET(pubG2 + ((size_t)k * TG + t) * st); }
+        if (t < RING) { RESET(ringH + (size_t)t * st); RESET(ringG + (size_t)t * st); RESET(ringG2 + (size_t)t * st); }
+        if (t == 0) RESET(black);
         }
         GSYNC();
         // ---- initB (fwd2c.h:138-176): origin, then the two boundary chains (one thread each)
@@ -259,6 +270,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             const int rr = LQ < -p.lw ? LQ : -p.lw;
             for (int k = 1; k <= rr; ++k) {
                 if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false);
+                else if (RL) k3r_boundary_col<RCAP, RCS, RMODE>(p, A.blk + (size_t)k * BW, B.blk, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
                 else k3_boundary_col(p, A, B, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
             }
         }
@@ -267,13 +279,14 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             const int rr = LS < p.up ? LS : p.up;
             for (int k = 1; k <= rr; ++k) {
                 if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true);
+                else if (RL) k3r_boundary_row<RCAP, RCS, RMODE>(p, A.blk, B.blk + (size_t)k * BW, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
                 else k3_boundary_row(p, A, B, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
             }
         }
         GSYNC();
         if (want_last && t == 0 && role == 0 && crank == 0) {
-            k3_copy(p, lastC, rowH + (size_t)LS * st);              // black unless the band reaches it
-            k3_copy(p, lastR, colH + (size_t)LQ * st);
+            RCOPY(lastC, rowH + (size_t)LS * st);                   // black unless the band reaches it
+            RCOPY(lastR, colH + (size_t)LQ * st);
         }
 
         // prefetch of the parked row: word w of the three records (rowH, rowG, rowG2) of one column
@@ -355,7 +368,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                     const int ia = m + 1, ib = n + 1;
                     if (n == 0 || r == p.lw) {                      // first in-band column of this row
                         if (!SPLIT || role == 1) pua = k3_unp(A, ia, B, ib, p.u);   // once per row (:377)
-                        if (!SPLIT || role == 2) { k3_reset(p, f1); if (n3) k3_reset(p, f2); }
+                        if (!SPLIT || role == 2) { RESET(f1); if (n3) RESET(f2); }
                     }
                     const int g3a = (S + 2) % 3, g3d = (S + 1) % 3, g2a = (S + 1) & 1;
                     const int seq = k * P + n;                      // == S for thread 0
@@ -397,6 +410,17 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                             const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
                             rec = k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, f1, f2, hout, gout, g2out);
                         }
+                    } else if (RL) {
+                        const int* const ablk = A.blk + (size_t)ia * BW;
+                        const int* const bblk = B.blk + (size_t)ib * BW;
+                        if (role == 0) {
+                            const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
+                            k3r_part_diag<RCAP, RCS, RMODE>(p, ablk, bblk, dab, hdiag, hout);
+                        } else if (role == 1) {
+                            k3r_part_vert<RCAP, RCS, RMODE>(p, ablk, bblk, A.nils != 0, m == 0, &pua, habove, gabove, g2above, gout, g2out, black, st);
+                        } else {
+                            k3r_part_hori<RCAP, RCS, RMODE>(p, ablk, bblk, n == 0, hleft, f1, f2);
+                        }
                     } else if (role == 0) {
                         const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
                         k3_part_diag(p, A, B, ia, ib, dab, hdiag, hout);
@@ -410,7 +434,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                 if (SPLIT) {
                     __syncthreads();                                // the three candidates are in shared memory
                     TM_ADD(tm_b1);
-                    if (active && role == 0 && p.mode != 3) rec = k3_combine(p, m == 0, n == 0, hout, gout, g2out, f1, f2);
+                    if (active && role == 0 && p.mode != 3)
+                        rec = RL ? k3r_combine(p, m == 0, n == 0, hout, gout, g2out, f1, f2, st) : k3_combine(p, m == 0, n == 0, hout, gout, g2out, f1, f2);
                     TM_ADD(tm_cmb);
                 }
                 if (active && role == 0) {
@@ -424,8 +449,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                         K3_PTR(hout) = id;
                     }
                     if (want_last) {
-                        if (n == LS - 1) k3_copy(p, lastC + (size_t)(m + 1) * st, hout);
-                        if (m == LQ - 1) k3_copy(p, lastR + (size_t)(n + 1) * st, hout);
+                        if (n == LS - 1) RCOPY(lastC + (size_t)(m + 1) * st, hout);
+                        if (m == LQ - 1) RCOPY(lastR + (size_t)(n + 1) * st, hout);
                     }
                     if (m == LQ - 1) {
                         if (n == LS - 1) {
@@ -433,9 +458,9 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                             else { sm_last_ptr[g] = K3_PTR(hout); sm_last_val[g] = k3_val(hout); }
                         }
                     } else if (t == TG - 1 && crank == NC - 1) {    // bottom row of a stripe: park it
-                        k3_copy(p, rowH + (size_t)(n + 1) * st, hout);
-                        k3_copy(p, rowG + (size_t)(n + 1) * st, gout);
-                        if (n3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
+                        RCOPY(rowH + (size_t)(n + 1) * st, hout);
+                        RCOPY(rowG + (size_t)(n + 1) * st, gout);
+                        if (n3) RCOPY(rowG2 + (size_t)(n + 1) * st, g2out);
                     }
                 }
                 TM_ADD(tm_vmf);
@@ -542,7 +567,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
 template <int TG, bool SPLIT, int MODE, bool SM>
 cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     // The gap-profile lists and score rows stream through L1.  Few pairs (latency: Prrn::best_of_n sized
     // batches): one CTA per SM and the rest of the unified array as L1 (measured 28 vs 37 ms for 24
@@ -551,9 +576,9 @@ cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
     int carve = (!SPLIT && grid_blocks > 148) ? 100 : (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
     if (const char* cv = getenv("PG_K3_CARVEOUT")) carve = atoi(cv);
     if (carve > 100) carve = 100;
-    e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    e = cudaFuncSetAttribute(k3_fill_kernel<TG, SPLIT, MODE, SM, false, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (e != cudaSuccess) return e;
-    k3_fill_kernel<TG, SPLIT, MODE, SM, false><<<grid_blocks, SPLIT ? 3 * TG : CTA, a.smem_bytes, st>>>(a);
+    k3_fill_kernel<TG, SPLIT, MODE, SM, false, 0><<<grid_blocks, SPLIT ? 3 * TG : CTA, a.smem_bytes, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -561,7 +586,7 @@ cudaError_t launch_tgm(const K3Args& a, int grid_blocks, cudaStream_t st)
 template <int MODE>
 cudaError_t launch_cluster(const K3Args& a, int clusters, cudaStream_t st)
 {
-    auto kern = k3_fill_kernel<TGCL, true, MODE, true, true>;
+    auto kern = k3_fill_kernel<TGCL, true, MODE, true, true, 0>;
     K3Args ac = a;
     { const char* f = getenv("PG_K3_CLUSTER_FENCE"); ac.cluster_fence = f && f[0] == '1'; }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
@@ -582,6 +607,45 @@ cudaError_t launch_cluster(const K3Args& a, int clusters, cudaStream_t st)
     at[0].val.clusterDim.x = (unsigned)a.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, ac);
+}
+
+// register-list form: TGRL rows x 3 roles per CTA, two CTAs per SM; `units` CTAs, or clusters of a.cluster CTAs
+template <int MODE, int RL>
+cudaError_t launch_rl(const K3Args& a, int units, cudaStream_t st)
+{
+    const bool cl = a.cluster > 1;
+    K3Args ac = a;
+    { const char* f = getenv("PG_K3_CLUSTER_FENCE"); ac.cluster_fence = f && f[0] == '1'; }
+    const void* kern = cl ? (const void*)k3_fill_kernel<TGRL, true, MODE, true, true, RL>
+                          : (const void*)k3_fill_kernel<TGRL, true, MODE, true, false, RL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+    if (e != cudaSuccess) return e;
+    int carve = (int)(2 * (a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;       // room for two CTAs per SM
+    if (const char* cv = getenv("PG_K3_CARVEOUT")) carve = atoi(cv);
+    if (carve > 100) carve = 100;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(units * (cl ? a.cluster : 1)));
+    cfg.blockDim = dim3(3 * TGRL);
+    cfg.dynamicSmemBytes = (size_t)a.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)(cl ? a.cluster : 1); at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = cl ? 1 : 0;
+    void* args[1] = {(void*)&ac};
+    return cudaLaunchKernelExC(&cfg, kern, args);
+}
+template <int MODE>
+cudaError_t launch_rl_cap(const K3Args& a, int units, cudaStream_t st)
+{
+    switch (a.rl) {
+    case 4: return launch_rl<MODE, 4>(a, units, st);
+    case 6: return launch_rl<MODE, 6>(a, units, st);
+    default: return launch_rl<MODE, 8>(a, units, st);
+    }
 }
 
 template <int TG, bool SPLIT, bool SM>
@@ -613,6 +677,7 @@ cudaError_t launch_tg(const K3Args& a, int mode, int grid_blocks, cudaStream_t s
 
 int k3_threads() { return CTA; }
 int k3_cluster_rows() { return TGCL; }
+int k3_rl_rows() { return TGRL; }
 int k3_blocks_per_sm() { return 2; }
 size_t k3_wave_words(int stride, int Noll, int tg) { return k3_smem_words(stride, Noll, tg); }
 
@@ -638,6 +703,7 @@ cudaError_t k3_launch(const K3Args& a, int tg, int mode, int grid_blocks, cudaSt
     // a.all_sm: every pair of the launch keeps its wavefront records and prefetch ring in shared memory for this
     // tg (k3_all_sm): the variant whose cell operands are all shared-memory records.  Otherwise (very long
     // gap-state lists) the generic-address variant, one thread per row, 256 rows per stripe.
+    if (a.rl) return mode == 1 ? launch_rl_cap<1>(a, grid_blocks, st) : launch_rl_cap<2>(a, grid_blocks, st);
     if (!a.all_sm) return launch_tg<256, false, false>(a, mode, grid_blocks, st);
     if (getenv("PG_K3_GENERIC") && tg != 768 && tg != 128) return launch_tg<256, false, false>(a, mode, grid_blocks, st);
     switch (tg) {

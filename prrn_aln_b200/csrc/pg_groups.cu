@@ -2,6 +2,7 @@
 // argument checks, flattening of the staged groups into one HBM blob, launch of kernel K3
 // (k3_groups.cu), collection of scores and corner lists.  No CPU fallback.
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -12,6 +13,7 @@
 #include <vector>
 
 #include "pg_internal.h"
+#include "k3r_core.cuh"
 
 static inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -44,9 +46,10 @@ extern "C" int64_t pg_group_cells(const pg_group* a, const pg_group* b, int32_t 
 }
 
 namespace {
-struct SideOff { size_t cfq, efq, vec, glen, gfreq, sfq, tfq, rfq, gapmask, weight; };
+struct SideOff { size_t cfq, efq, vec, glen, gfreq, sfq, tfq, rfq, gapmask, weight, blk; int cs; };
 
-size_t place_side(const pg_group& g, int kdim, size_t off, SideOff* so)
+// cs > 0: also the fixed-stride column blocks of the register-list kernels (k3r_core.cuh), cs entries per list
+size_t place_side(const pg_group& g, int kdim, size_t off, SideOff* so, int cs)
 {
     const size_t npos = (size_t)(g.right - g.left + 1);
     const bool lists = g.sfq && g.tfq && g.rfq && g.glen && g.gfreq && g.npool > 0;
@@ -60,6 +63,9 @@ size_t place_side(const pg_group& g, int kdim, size_t off, SideOff* so)
     so->rfq = off; off = up16(off + 4 * npos);
     so->gapmask = off; off = up16(off + 4 * npos);
     so->weight = off; off = up16(off + 8 * (size_t)std::max(g.many, 1));
+    so->cs = cs;
+    so->blk = off;
+    if (cs > 0) off = up16(off + 4 * npos * (size_t)k3r_block_words(cs));
     return off;
 }
 
@@ -85,6 +91,9 @@ void fill_side(const pg_group& g, int kdim, const SideOff& so, char* h)
     }
     if (g.gapmask) memcpy(h + so.gapmask, g.gapmask, 4 * npos); else memset(h + so.gapmask, 0, 4 * npos);
     for (int i = 0; i < std::max(g.many, 1); ++i) ((double*)(h + so.weight))[i] = (g.weight && i < g.many) ? g.weight[i] : 1.0;
+    if (so.cs > 0)
+        k3r_build_blocks((int*)(h + so.blk), so.cs, (int)npos, g.cfq, g.efq, lists ? g.glen : nullptr, lists ? g.gfreq : nullptr,
+                         lists ? g.sfq : nullptr, lists ? g.tfq : nullptr, lists ? g.rfq : nullptr);
 }
 
 K3Group dev_side(const pg_group& g, const SideOff& so, const char* d)
@@ -100,6 +109,7 @@ K3Group dev_side(const pg_group& g, const SideOff& so, const char* d)
     k.weight = (const double*)(d + so.weight);
     k.many = g.many;
     k.pad = 0;
+    k.blk = so.cs > 0 ? (const int*)(d + so.blk) : nullptr;
     return k;
 }
 }  // namespace
@@ -159,6 +169,36 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
     const int ngrp = k3_threads() / tg;                     // alignments in flight per CTA
     int64_t max_cells = 0;
     outoff[0] = 0;
+    // ---- register-list kernels (k3r_core.cuh) for the gap-profile record modes, on request (PG_K3_RL=1): one list
+    //      capacity per mode and call, the smallest of 4 / 6 / 8 words that holds every dynamic list (hetero + 1 entries
+    //      and the terminator) and every static list (CAP - 2 entries) of the mode's pairs; longer lists or sequences
+    //      run the list-walking form.  Measured on B200: bit-identical results, warps 27 of 32
+    //      lanes wide instead of 19 and barrier stalls halved, but the capacity-wide unrolled merges execute as many
+    //      warp instructions per cell as the list walk (~100) -- 384 pairs 29.6 ms against 30.9 ms, 24 pairs 10.2 ms
+    //      against 8.8 ms -- so the list-walking kernels stay the default.
+    int rl_cap[5] = {0, 0, 0, 0, 0};
+    {
+        const char* ev = getenv("PG_K3_RL");
+        const bool rl_on = tg_sel == 768 && ev && ev[0] == '1';
+        int need[5] = {0, 0, 0, 0, 0};
+        bool ok[5] = {false, rl_on, rl_on, false, false};
+        for (int64_t i = 0; i < npairs && rl_on; ++i) {
+            const int m5 = (prm[i].alnmode == 7 || prm[i].alnmode == 8) ? 1 : (prm[i].alnmode == 9 ? 2 : -1);
+            if (m5 < 0 || !ok[m5]) continue;
+            const pg_group* gs[2] = {&a[i], &b[i]};
+            for (int sd = 0; sd < 2 && ok[m5]; ++sd) {
+                const pg_group& G = *gs[sd];
+                if (G.len > 30000 || G.left < 0 || G.right > G.len || G.left >= G.right) { ok[m5] = false; break; }
+                int longest = 0, max_glen = 0;
+                if (G.sfq && G.tfq && G.rfq && G.glen && G.gfreq && G.npool > 0)
+                    k3r_scan_lists(G.right - G.left + 1, G.glen, G.sfq, G.tfq, G.rfq, &longest, &max_glen);
+                if (max_glen > 30000) { ok[m5] = false; break; }
+                need[m5] = std::max(need[m5], std::max(std::max(G.hetero, 0), longest));
+            }
+        }
+        for (int m5 = 1; m5 <= 2; ++m5)
+            if (ok[m5] && need[m5] <= 6) rl_cap[m5] = need[m5] <= 2 ? 4 : (need[m5] <= 4 ? 6 : 8);
+    }
     for (int64_t i = 0; i < npairs; ++i) {
         const pg_group& A = a[i];
         const pg_group& B = b[i];
@@ -185,8 +225,9 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
             free(offs);
             return pg_int_fail(c, PG_ERR_ARG, "pg_align_groups: gap-profile lists missing for a half / full profile mode");
         }
-        blob = place_side(A, P.kdim, blob, &soa[i]);
-        blob = place_side(B, P.kdim, blob, &sob[i]);
+        const int rl = rl_cap[mode];
+        blob = place_side(A, P.kdim, blob, &soa[i], rl ? rl - 2 : 0);
+        blob = place_side(B, P.kdim, blob, &sob[i], rl ? rl - 2 : 0);
         K3Prm& kp = pairs[i].prm;
         kp.mode = mode; kp.Noll = P.Noll; kp.codonk1 = P.codonk1; kp.kdim = P.kdim;
         int lw, up;
@@ -202,6 +243,11 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
                                    "(semi-global naive mode is not built yet)");
             }
             kp.capa = (A.many + 1) / 2 + 1; kp.capb = (B.many + 1) / 2 + 1;     // 16-bit run lengths, two per word
+        }
+        kp.rl = rl; kp.pad2 = 0;
+        if (rl) {               // the records of the register-list form: 4 header words + rl words per list, a multiple of 4
+            kp.capa = rl;
+            kp.capb = mode == 2 ? rl : k3r_rec_words(rl, 1) - 4 - rl;
         }
         kp.u = (double)(float)P.u;
         kp.wgop = P.Weighted_GOP; kp.bgop = P.Basic_GOP;
@@ -222,7 +268,7 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         }
         const int LQ = A.right - A.left, LS = B.right - B.left;
         const size_t st = (size_t)k3_stride(kp.capa, kp.capb);
-        arena_words = std::max(arena_words, st * (size_t)(4 * (LS + 2) + 2 * (LQ + 2)) + k3_wave_words((int)st, 3, tg));
+        arena_words = std::max(arena_words, (st * (size_t)(4 * (LS + 2) + 2 * (LQ + 2)) + k3_wave_words((int)st, 3, tg) + 3) & ~(size_t)3);
         wave_bytes = std::max(wave_bytes, 4 * k3_wave_words((int)st, P.Noll, tg));
         if (A.len > 65000 || B.len > 65000) {
             free(offs);
@@ -257,22 +303,25 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         int64_t ctas = 0;
         for (int m5 = 0; m5 < 5; ++m5) {
             int nc = 1;
-            if (maxlq_mode[m5] > k3_threads())
-                while (nc < cmax && nc < 8 && maxlq_mode[m5] > nc * k3_cluster_rows()) nc *= 2;
+            const int rows1 = rl_cap[m5] ? k3_rl_rows() : k3_threads();         // rows of a single CTA / of a cluster CTA
+            const int rowsc = rl_cap[m5] ? k3_rl_rows() : k3_cluster_rows();
+            if (maxlq_mode[m5] > rows1)
+                while (nc < cmax && nc < 8 && maxlq_mode[m5] > nc * rowsc) nc *= 2;
             nc_mode[m5] = n_mode[m5] ? nc : 1;
-            ctas += n_mode[m5] * nc_mode[m5];
+            ctas += n_mode[m5] * nc_mode[m5] * (rl_cap[m5] ? 1 : 2);            // in half SMs: the register-list CTAs pair up
         }
-        while (ctas > c->sm_count) {            // more clusters than SMs: halve the widest ones
+        while (ctas > 2 * c->sm_count) {        // more clusters than SMs: halve the widest ones
             int w = 0;
             for (int m5 = 1; m5 < 5; ++m5) if (nc_mode[m5] > nc_mode[w]) w = m5;
             if (nc_mode[w] == 1) break;
-            ctas -= n_mode[w] * (nc_mode[w] / 2);
+            ctas -= n_mode[w] * (nc_mode[w] / 2) * (rl_cap[w] ? 1 : 2);
             nc_mode[w] /= 2;
         }
     }
     size_t slots = 0, vslots = 0;
     for (int m5 = 0; m5 < 5; ++m5) {
-        g_mode[m5] = (int)std::min<int64_t>((n_mode[m5] + ngrp - 1) / ngrp, grid);
+        g_mode[m5] = rl_cap[m5] ? (int)std::min<int64_t>(n_mode[m5], (int64_t)2 * c->sm_count / nc_mode[m5] > 0 ? (int64_t)2 * c->sm_count / nc_mode[m5] : 1)
+                                : (int)std::min<int64_t>((n_mode[m5] + ngrp - 1) / ngrp, grid);
         slot0_mode[m5] = (int)slots;
         vslot0_mode[m5] = (int)vslots;
         slots += (size_t)g_mode[m5] * ngrp;
@@ -408,6 +457,14 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
             km.all_sm = k3_sm_fits(k3_stride(sorted[k].prm.capa, sorted[k].prm.capb), sorted[k].prm.Noll, tg_sel,
                                    (size_t)ka.smem_bytes) ? 1 : 0;
         km.cluster = nc_mode[mode];
+        km.rl = rl_cap[mode];
+        if (km.rl) {                            // register-list kernels: 128 rows per CTA, their own shared-memory size
+            size_t wb = 0;
+            for (int64_t k = k0; k < k1; ++k)
+                wb = std::max(wb, 4 * k3_wave_words(k3_stride(sorted[k].prm.capa, sorted[k].prm.capb), sorted[k].prm.Noll, k3_rl_rows()));
+            km.smem_bytes = (int32_t)((wb + 15) / 16 * 16);
+            km.all_sm = 1;
+        }
         if (!km.all_sm && tg_sel == 768) {      // long records (high hetero, two-piece): 192 rows per CTA may still fit
             km.rows192 = 1;
             for (int64_t k = k0; k < k1 && km.rows192; ++k)
@@ -417,6 +474,9 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         }
         km.arena = ka.arena + (size_t)slot0_mode[mode] * arena_words;
         km.vmf = ka.vmf + (size_t)vslot0_mode[mode] * (size_t)vmf_cap;
+        if (getenv("PG_K3_DEBUG"))
+            fprintf(stderr, "pg_align_groups: mode %d pairs %d rl %d cluster %d units %d smem %d all_sm %d rows192 %d\n", mode, km.npairs,
+                    km.rl, km.cluster, gm, km.smem_bytes, km.all_sm, km.rows192);
         e = cudaStreamWaitEvent(c->aux[mode], c->ev_fork, 0);
         if (e == cudaSuccess) e = k3_launch(km, tg_sel, mode, gm, c->aux[mode]);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev_join[mode], c->aux[mode]);

@@ -167,6 +167,7 @@ struct K3Args {
     int32_t all_sm;             // every pair fits the all-shared-memory variant (k3_sm_fits)
     int32_t cluster;            // latency mode: CTAs (thread-block cluster size) per alignment, 1 = none
     int32_t cluster_fence;      // cluster variant: cluster-scope acquire in the per-step hand-shake (PG_K3_CLUSTER_FENCE)
+    int32_t rl;                 // register-list form (k3r_core.cuh): words per dynamic list (4 / 6 / 8) of this launch, 0 = classic
     int32_t rows192;            // the records fit shared memory only with 192 rows per CTA: the cluster kernel's geometry,
                                 // also for a "cluster" of one CTA (long gap-state lists: high hetero, two-piece)
 };
@@ -274,6 +275,7 @@ int k2_blocks_per_sm();
 cudaError_t k3_launch(const K3Args& a, int tg, int mode, int grid_blocks, cudaStream_t st);
 int k3_threads();
 int k3_cluster_rows();        // rows per CTA of the cluster latency kernel
+int k3_rl_rows();             // rows per CTA of the register-list kernels
 int k3_blocks_per_sm();
 int k3_pick_tg(int64_t npairs, int sm_count);
 bool k3_sm_fits(int stride, int Noll, int tg, size_t smem_bytes);

@@ -6,17 +6,39 @@
 #include <string.h>
 #include <vector>
 #include "../../prrn_aln_b200/csrc/k3_core.cuh"
+#include "../../prrn_aln_b200/csrc/k3r_core.cuh"
 
-extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int Tsigned, int al, int bl,
-                             double* score, int* out_pts, int cap)
+// RL = 0: the list-walking cell (k3_core.cuh); 4 / 6 / 8: the register-list form (k3r_core.cuh) with that many words
+// per dynamic list, column blocks built here from the pooled lists
+template <int RL, int RMODE>
+static int emul(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int Tsigned, int al, int bl,
+                double* score, int* out_pts, int cap)
 {
+    constexpr int RCAP = RL ? RL : 4, RCS = RCAP - 2;
+    constexpr int BW = k3r_block_words(RCS);
     const int T = Tsigned < 0 ? -Tsigned : Tsigned;
     const bool rev = Tsigned < 0;       // run the "threads" of a step in reverse order: results must not depend on it
-    const K3Group& a = *ga; const K3Group& b = *gb; const K3Prm& p = *prm;
+    const K3Group& a = *ga; const K3Group& b = *gb;
+    K3Prm p = *prm;
     const int LQ = a.L, LS = b.L;
+    std::vector<int> ablk, bblk;
+    int *ablk_p = nullptr, *bblk_p = nullptr;
+    if (RL) {
+        p.rl = RL; p.capa = RL; p.capb = RMODE == 2 ? RL : k3r_rec_words(RL, 1) - 4 - RL;
+        ablk.resize((size_t)(LQ + 1) * BW + 4); bblk.resize((size_t)(LS + 1) * BW + 4);
+        ablk_p = ablk.data(); bblk_p = bblk.data();
+        while (((uintptr_t)ablk_p & 15) != 0) ++ablk_p;     // blocks are read 16 bytes at a time
+        while (((uintptr_t)bblk_p & 15) != 0) ++bblk_p;
+        const int la = k3r_build_blocks(ablk_p, RCS, LQ + 1, a.cfq, a.efq, a.glen, a.gfreq, a.sfq, a.tfq, a.rfq);
+        const int lb = k3r_build_blocks(bblk_p, RCS, LS + 1, b.cfq, b.efq, b.glen, b.gfreq, b.sfq, b.tfq, b.rfq);
+        if (la > RCS || lb > RCS) return -2;
+    }
     const int st = k3_stride(p.capa, p.capb);
-    std::vector<int> mem((size_t)st * (3 * (LS + 2) + (LQ + 2) + 9 * T + 2));
+#define RESET(ptr) do { if (RL) k3r_reset<RCAP, RMODE>(ptr); else k3_reset(p, ptr); } while (0)
+#define RCOPY(d, s) do { if (RL) k3r_copy_words(d, s, st); else k3_copy(p, d, s); } while (0)
+    std::vector<int> mem((size_t)st * (3 * (LS + 2) + (LQ + 2) + 9 * T + 2) + 4);
     int* base = mem.data();
+    while (((uintptr_t)base & 15) != 0) ++base;     // records are read and written 16 bytes at a time in the RL form
     auto rec = [&](size_t i) { return base + i * st; };
     size_t o = 0;
     int* rowH = rec(o); o += LS + 2;
@@ -29,15 +51,21 @@ extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* 
     int* F1 = rec(o); o += T;
     int* F2 = rec(o); o += T;
     int* black = rec(o); o += 1;
-    for (size_t i = 0; i < o; ++i) k3_reset(p, rec(i));
+    for (size_t i = 0; i < o; ++i) RESET(rec(i));
     std::vector<K3Vmf> vmf;
     vmf.push_back({0, 0, 0});                       // skip 0-th record (fwd2c.h:361)
     vmf.push_back({al, bl, 0});                     // origin (initB)
     // origin + boundary chains
     k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(colH) = 1;
-    k3_copy(p, rowH, colH);
-    { int rr = LS < p.up ? LS : p.up; for (int k = 1; k <= rr; ++k) { if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true); else k3_boundary_row(p, a, b, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st); } }
-    { int rr = LQ < -p.lw ? LQ : -p.lw; for (int k = 1; k <= rr; ++k) { if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false); else k3_boundary_col(p, a, b, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st); } }
+    RCOPY(rowH, colH);
+    { int rr = LS < p.up ? LS : p.up; for (int k = 1; k <= rr; ++k) {
+        if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true);
+        else if (RL) k3r_boundary_row<RCAP, RCS, RMODE>(p, ablk_p, bblk_p + (size_t)k * BW, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
+        else k3_boundary_row(p, a, b, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st); } }
+    { int rr = LQ < -p.lw ? LQ : -p.lw; for (int k = 1; k <= rr; ++k) {
+        if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false);
+        else if (RL) k3r_boundary_col<RCAP, RCS, RMODE>(p, ablk_p + (size_t)k * BW, bblk_p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
+        else k3_boundary_col(p, a, b, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st); } }
     std::vector<double> pua(T, 0.0);
     int last_ptr = 0; double last_val = 0;
     // Continuous schedule (k3_groups.cu): thread t takes rows t, t+T, t+2T, ...; its k-th row meets column n
@@ -61,8 +89,8 @@ extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* 
             const bool row_start = n == 0 || r == p.lw; // first in-band column of this row
             if (row_start) {
                 pua[t] = k3_unp(a, ia, b, ib, p.u);     // once per row, at its first column (fwd2c.h:377)
-                k3_reset(p, F1 + (size_t)t * st);
-                k3_reset(p, F2 + (size_t)t * st);
+                RESET(F1 + (size_t)t * st);
+                RESET(F2 + (size_t)t * st);
             }
             const bool first_row = m == 0, first_col = n == 0;
             const int* hdiag = n == 0 ? colH + (size_t)m * st
@@ -77,10 +105,13 @@ extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* 
             int* gout = pubG + ((size_t)(S & 1) * T + t) * st;
             int* g2out = pubG2 + ((size_t)(S & 1) * T + t) * st;
             const double dab = k3_sim(a, b, p, ia, ib);
-            const bool rec = p.mode == 3
-                ? k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out)
-                : k3_cell(p, a, b, ia, ib, first_row, first_col, dab, &pua[t], hdiag, habove, gabove, g2above, hleft,
-                          F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out, black);
+            bool rec;
+            if (p.mode == 3) rec = k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out);
+            else if (RL) rec = k3r_cell<RCAP, RCS, RMODE>(p, ablk_p + (size_t)ia * BW, bblk_p + (size_t)ib * BW, a.nils != 0, first_row, first_col,
+                                                          dab, &pua[t], hdiag, habove, gabove, g2above, hleft, F1 + (size_t)t * st,
+                                                          F2 + (size_t)t * st, hout, gout, g2out, black, st);
+            else rec = k3_cell(p, a, b, ia, ib, first_row, first_col, dab, &pua[t], hdiag, habove, gabove, g2above, hleft,
+                               F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out, black);
             if (rec) {
                 vmf.push_back({m + al, n + bl, K3_PTR(hout)});
                 K3_PTR(hout) = (int)vmf.size() - 1;
@@ -88,9 +119,9 @@ extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* 
             if (m == LQ - 1) {
                 if (n == LS - 1) { last_ptr = K3_PTR(hout); last_val = k3_val(hout); }
             } else if (t == T - 1) {                    // bottom row of a stripe: park it for thread 0's next row
-                k3_copy(p, rowH + (size_t)(n + 1) * st, hout);
-                k3_copy(p, rowG + (size_t)(n + 1) * st, gout);
-                if (p.Noll == 3) k3_copy(p, rowG2 + (size_t)(n + 1) * st, g2out);
+                RCOPY(rowH + (size_t)(n + 1) * st, hout);
+                RCOPY(rowG + (size_t)(n + 1) * st, gout);
+                if (p.Noll == 3) RCOPY(rowG2 + (size_t)(n + 1) * st, g2out);
             }
         }
     }
@@ -103,4 +134,27 @@ extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* 
         if (!vmf[q].p) break;
     }
     return cnt;
+}
+#undef RESET
+#undef RCOPY
+
+extern "C" int k3_emul_align(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int Tsigned, int al, int bl,
+                             double* score, int* out_pts, int cap)
+{
+    return emul<0, 1>(ga, gb, prm, Tsigned, al, bl, score, out_pts, cap);
+}
+
+// register-list form; rl = 4 / 6 / 8 words per dynamic list; record modes 1 (DPunit_hf) and 2 (DPunit_pf) only.
+// Returns -2 when a static list is longer than rl - 2 entries.
+extern "C" int k3_emul_align_rl(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int Tsigned, int al, int bl,
+                                double* score, int* out_pts, int cap, int rl)
+{
+    const int m = prm->mode;
+    if (m != 1 && m != 2) return -3;
+    switch (rl) {
+    case 4: return m == 1 ? emul<4, 1>(ga, gb, prm, Tsigned, al, bl, score, out_pts, cap) : emul<4, 2>(ga, gb, prm, Tsigned, al, bl, score, out_pts, cap);
+    case 6: return m == 1 ? emul<6, 1>(ga, gb, prm, Tsigned, al, bl, score, out_pts, cap) : emul<6, 2>(ga, gb, prm, Tsigned, al, bl, score, out_pts, cap);
+    case 8: return m == 1 ? emul<8, 1>(ga, gb, prm, Tsigned, al, bl, score, out_pts, cap) : emul<8, 2>(ga, gb, prm, Tsigned, al, bl, score, out_pts, cap);
+    default: return -3;
+    }
 }

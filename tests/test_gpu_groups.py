@@ -34,12 +34,15 @@ def stage_golden(g, sh=None):
     return A, B, gp
 
 
-@pytest.mark.parametrize("inline_sim", ["0", "1"])
+@pytest.mark.parametrize("inline_sim", ["0", "1", "rl"])
 @pytest.mark.parametrize("name", golden_names("galign_"))
 def test_group_goldens(ctx, name, inline_sim, monkeypatch):
     """inline_sim 0: column score matrix precomputed by kernel K4 (FP64 tensor cores); 1: sim2 evaluated
-    inside the DP cell (PG_K3_INLINE_SIM=1).  Both must reproduce the reference."""
-    monkeypatch.setenv("PG_K3_INLINE_SIM", inline_sim)
+    inside the DP cell (PG_K3_INLINE_SIM=1); rl: the register-list form of the cell (k3r_core.cuh, PG_K3_RL=1:
+    fixed-capacity lists in registers, branch-free merges) for the gap-profile record modes.  All must reproduce
+    the reference."""
+    monkeypatch.setenv("PG_K3_INLINE_SIM", "1" if inline_sim == "1" else "0")
+    monkeypatch.setenv("PG_K3_RL", "1" if inline_sim == "rl" else "0")
     g = golden(name)
     A, B, gp = stage_golden(g)
     scores, pts = ctx.align_groups([(A, B, gp)])
@@ -72,12 +75,13 @@ def test_homscore_goldens_in_one_call(ctx, oracle):
             assert abs(s1[0] - ws) <= REL_TOL * max(1.0, abs(ws)) and r1[0].tolist() == wrr, (name, sh)
 
 
-@pytest.mark.parametrize("tg", [None, "256", "128"])
+@pytest.mark.parametrize("tg", [None, "256", "128", "rl"])
 def test_batch_of_all_goldens_in_one_call(ctx, tg, monkeypatch):
     """One launch over every golden pair (different modes, sizes, capacities), three times over: results must
     not depend on which CTA / arena a pair lands on -- with the default kernel (three threads per row) and with
     the one-thread-per-row variants (PG_K3_TG = 256 / 128 rows per alignment)."""
-    if tg is None:
+    monkeypatch.setenv("PG_K3_RL", "1" if tg == "rl" else "0")
+    if tg is None or tg == "rl":
         monkeypatch.delenv("PG_K3_TG", raising=False)
     else:
         monkeypatch.setenv("PG_K3_TG", tg)

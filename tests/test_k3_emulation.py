@@ -17,23 +17,26 @@ class K3Group(C.Structure):
     _fields_ = [("cfq", C.c_void_p), ("efq", C.c_void_p), ("prof", C.c_void_p), ("freq", C.c_void_p),
                 ("glen", C.c_void_p), ("gfreq", C.c_void_p), ("sfq", C.c_void_p), ("tfq", C.c_void_p),
                 ("rfq", C.c_void_p), ("L", C.c_int32), ("nils", C.c_int32), ("gapmask", C.c_void_p),
-                ("weight", C.c_void_p), ("many", C.c_int32), ("pad", C.c_int32)]
+                ("weight", C.c_void_p), ("many", C.c_int32), ("pad", C.c_int32), ("blk", C.c_void_p)]
 
 
 class K3Prm(C.Structure):
     _fields_ = [("mode", C.c_int32), ("Noll", C.c_int32), ("codonk1", C.c_int32), ("lw", C.c_int32), ("up", C.c_int32),
                 ("capa", C.c_int32), ("capb", C.c_int32), ("kdim", C.c_int32), ("u", C.c_double), ("wgop", C.c_double),
                 ("bgop", C.c_double), ("u2divu1", C.c_double), ("v2divv1", C.c_double), ("gop1", C.c_double),
-                ("gep1", C.c_double), ("gop2", C.c_double), ("gep2", C.c_double), ("ltg_a", C.c_double), ("ltg_b", C.c_double)]
+                ("gep1", C.c_double), ("gop2", C.c_double), ("gep2", C.c_double), ("ltg_a", C.c_double), ("ltg_b", C.c_double),
+                ("rtg_a", C.c_double), ("rtg_b", C.c_double), ("last_c", C.c_int32), ("last_r", C.c_int32),
+                ("novmf", C.c_int32), ("origin_r", C.c_int32), ("rl", C.c_int32), ("pad2", C.c_int32)]
 
 
 @pytest.fixture(scope="module")
 def emul3():
     src = os.path.join(ROOT, "tests", "host_emul", "k3_emul.cc")
     out = os.path.join(ROOT, "tests", "host_emul", "libk3emul.so")
-    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", out, src])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
     L = C.CDLL(out)
     L.k3_emul_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.k3_emul_align_rl.argtypes = L.k3_emul_align.argtypes + [C.c_int]
     return L
 
 
@@ -72,6 +75,29 @@ def test_wavefront_emulation_matches_reference(emul3, name):
         assert n > 0, T
         assert abs(sc.value - want["score"]) <= 1e-5 * max(1.0, abs(want["score"])), T
         assert [[int(out[2 * i]), int(out[2 * i + 1])] for i in range(n)] == want["skl"], T
+    if mode not in (1, 2):
+        return
+    # the register-list form of the cell (k3r_core.cuh): every capacity that holds this pair's lists must give the
+    # very same score (bit for bit against the list-walking form) and corner list
+    sc0 = C.c_double(0)
+    out0 = np.zeros(2 * (A["len"] + B["len"] + 8), np.int32)
+    ga, gb = _k3group(A), _k3group(B)
+    emul3.k3_emul_align(C.byref(ga), C.byref(gb), C.byref(p), 33, A["left"], B["left"], C.byref(sc0), out0.ctypes.data, len(out0) // 2)
+    need = max(A["hetero"], B["hetero"], 0)
+    ran = 0
+    for rl in (4, 6, 8):
+        for T in (33, -7, 128):
+            out = np.zeros(2 * (A["len"] + B["len"] + 8), np.int32)
+            sc = C.c_double(0)
+            n = emul3.k3_emul_align_rl(C.byref(ga), C.byref(gb), C.byref(p), T, A["left"], B["left"], C.byref(sc),
+                                       out.ctypes.data, len(out) // 2, rl)
+            if rl - 2 < need or n == -2:
+                continue        # capacity below hetero or below the longest static list: the host never picks it
+            assert n > 0, (rl, T, n)
+            assert sc.value == sc0.value, (rl, T)
+            assert [[int(out[2 * i]), int(out[2 * i + 1])] for i in range(n)] == want["skl"], (rl, T)
+            ran += 1
+    assert ran or need > 6
 
 
 def test_aln2b1_cell_emulation(emul3, oracle):
