@@ -10,6 +10,7 @@
 //                    the reference's record rules and emits the corner list in Vmf back-walk order.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "k2_core.cuh"
 #include "pg_internal.h"
@@ -161,11 +162,18 @@ __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k2_fill_kernel(const K
 // k2_fill_kernel, so the traceback kernel is shared.
 constexpr int PUB = 16;
 
+// RR rows per lane: a stripe is 32 * RR rows.  One warp alone on its scheduler runs a lane-step as one dependent
+// chain (about 30 cycles per row + 150 of fixed work), so narrow stripes (RR = 4: 128 rows, 235 warps for a 30 kb
+// query) finish the matrix in LS + stripes * skew steps of a quarter of the length.  The bottom row of the stripe
+// above is read in coalesced chunks of 32 columns (one 256-byte load per 32 steps, handed to lane 0 by shuffle)
+// instead of one L2 round trip on the critical path of every step.
+template <int RR>
 __global__ void __launch_bounds__(32) k2_fill_long_kernel(const K2Args a, int npass)
 {
+    constexpr int RPP = 32 * RR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int4* const sm_prof = reinterpret_cast<int4*>(smem_raw);
-    int4* const sm_poke = sm_prof + a.dim * (R / 4) * 32;
+    int4* const sm_poke = sm_prof + a.dim * (RR / 4) * 32;
     const int lane = threadIdx.x;
     const int negv = -a.v;
     const int qi = a.pair_q[0], si = a.pair_s[0];
@@ -176,35 +184,37 @@ __global__ void __launch_bounds__(32) k2_fill_long_kernel(const K2Args a, int np
     g.LQ = LQ; g.LS = LS; g.u = a.u; g.v = a.v;
     k1_band(LQ, LS, a.sh, &g.lw, &g.up);
     g.topOpen = -a.v; g.topExt = -a.u; g.leftOpen = -a.v; g.leftExt = -a.u;
+    unsigned char* const dir_base = reinterpret_cast<unsigned char*>(a.dirs + a.dir_off[0]);
 
     for (;;) {
         int pass = 0;
         if (lane == 0) pass = atomicAdd(a.ticket, 1);
         pass = __shfl_sync(FULL, pass, 0);
         if (pass >= npass) break;
-        const int pbase = pass * ROWS_PER_PASS;
+        const int pbase = pass * RPP;
         {
             int* p = reinterpret_cast<int*>(sm_prof);
-            const int total = a.dim * 32 * R;
+            const int total = a.dim * 32 * RR;
             for (int idx = lane; idx < total; idx += 32) {
-                int letter = idx / (32 * R);
-                int rem = idx - letter * (32 * R);
+                int letter = idx / (32 * RR);
+                int rem = idx - letter * (32 * RR);
                 int j = rem >> 7, ln = (rem >> 2) & 31, c = rem & 3;
-                int row = pbase + ln * R + j * 4 + c;
+                int row = pbase + ln * RR + j * 4 + c;
                 p[idx] = row < LQ ? a.mtx[(int)q[row] * a.dim + letter] + 2 * a.u : 0;
             }
         }
         __syncwarp();
-        const int rows_here = min(LQ - pbase, ROWS_PER_PASS);
-        const int lanes = (rows_here + R - 1) / R;
-        const int mbase = pbase + lane * R;
+        const int rows_here = min(LQ - pbase, RPP);
+        const int lanes = (rows_here + RR - 1) / RR;
+        const int mbase = pbase + lane * RR;
         const bool last_pass = pass == npass - 1;
-        int2* const row_in = a.rowbuf + (int64_t)(pass - 1) * LS;      // bottom row of the stripe above
+        const int2* const row_in = a.rowbuf + (int64_t)(pass - 1) * LS;      // bottom row of the stripe above
         int2* const row_out = a.rowbuf + (int64_t)pass * LS;
         volatile int* const prog_in = a.progress + (pass - 1);
-        unsigned long long* words = a.dirs + a.dir_off[0] + ((int64_t)pass * (LS + 31)) * 32 + lane;
+        // direction bits: RR / 2 bytes per lane-step, slot (pass * (LS + 31) + step) * 32 + lane (k2_core.cuh)
+        unsigned char* const words = dir_base + ((int64_t)pass * (LS + 31) * 32 + lane) * (RR / 2);
 
-        K2Lane<R> L;
+        K2Lane<RR> L;
         k2_lane_init(L, g, mbase);
         const int lwm = g.lw + mbase;
         const int upm = g.up + 1 + mbase;
@@ -213,45 +223,56 @@ __global__ void __launch_bounds__(32) k2_fill_long_kernel(const K2Args a, int np
         int4* pk = sm_poke + lane;
         const int nsteps = LS + lanes - 1;
         int avail = 0;          // columns of the stripe above known to be published
+        int2 chunk = make_int2(K1_NEG, K1_NEG);         // lane i: row_in[32 * (step / 32) + i]
 
         for (int step = 0; step < nsteps; ++step) {
             const int n = step - lane;
+            if (pass > 0 && (step & 31) == 0 && step < LS) {        // lane 0 enters a new chunk of 32 columns
+                const int need = min(step + 32, LS);
+                if (lane == 0) {
+                    while (avail < need) avail = *prog_in;          // wait for the stripe above
+                    __threadfence();
+                }
+                __syncwarp();
+                if (step + lane < LS) chunk = __ldcg(row_in + step + lane);
+            }
+            const int in_h = __shfl_sync(FULL, chunk.x, step & 31);
+            const int in_g = __shfl_sync(FULL, chunk.y, step & 31);
             int h_dn = K1_NEG, g_dn = K1_NEG;
             if (n >= 0 && n < LS && lane < lanes) {
                 int h_up = recv_h, g_up = recv_g;
                 if (lane == 0) {
                     if (pass == 0) { h_up = k1_top(g, n); g_up = K1_NEG; }
-                    else {
-                        while (avail <= n) avail = *prog_in;            // wait for the stripe above
-                        __threadfence();
-                        int2 v = __ldcg(row_in + n); h_up = v.x; g_up = v.y;
-                    }
+                    else { h_up = in_h; g_up = in_g; }
                 }
                 const int kL = n - lwm, kU = n - upm;
-                if ((unsigned)kL < (unsigned)R || (unsigned)kU < (unsigned)R) {
+                if ((unsigned)kL < (unsigned)RR || (unsigned)kU < (unsigned)RR) {
 #pragma unroll
-                    for (int j = 0; j < R / 4; ++j)
+                    for (int j = 0; j < RR / 4; ++j)
                         pk[j * 32] = make_int4(L.E[4 * j], L.E[4 * j + 1], L.E[4 * j + 2], L.E[4 * j + 3]);
                     int* pki = reinterpret_cast<int*>(pk);
-                    if ((unsigned)kL < (unsigned)R) pki[(kL >> 2) * 128 + (kL & 3)] = K1_NEG;
-                    if ((unsigned)kU < (unsigned)R) pki[(kU >> 2) * 128 + (kU & 3)] = K1_NEG;
+                    if ((unsigned)kL < (unsigned)RR) pki[(kL >> 2) * 128 + (kL & 3)] = K1_NEG;
+                    if ((unsigned)kU < (unsigned)RR) pki[(kU >> 2) * 128 + (kU & 3)] = K1_NEG;
 #pragma unroll
-                    for (int j = 0; j < R / 4; ++j) {
+                    for (int j = 0; j < RR / 4; ++j) {
                         int4 v = pk[j * 32];
                         L.E[4 * j] = v.x; L.E[4 * j + 1] = v.y; L.E[4 * j + 2] = v.z; L.E[4 * j + 3] = v.w;
                     }
                 }
                 const int letter = __ldg(s + n);
-                const int4* pl = pp + letter * ((R / 4) * 32);
-                int sc[R];
+                const int4* pl = pp + letter * ((RR / 4) * 32);
+                int sc[RR];
 #pragma unroll
-                for (int j = 0; j < R / 4; ++j) {
+                for (int j = 0; j < RR / 4; ++j) {
                     int4 v = pl[j * 32];
                     sc[4 * j] = v.x; sc[4 * j + 1] = v.y; sc[4 * j + 2] = v.z; sc[4 * j + 3] = v.w;
                 }
                 const unsigned long long bits = k2_lane_step(L, sc, negv, h_up, g_up, mbase == 0, &h_dn, &g_dn);
-                __stcs(words + (int64_t)step * 32, bits);
-                if (lane == 31 && !last_pass) {
+                unsigned char* const w = words + (int64_t)step * 32 * (RR / 2);
+                if (RR == 16) __stcs(reinterpret_cast<unsigned long long*>(w), bits);
+                else if (RR == 8) __stcs(reinterpret_cast<unsigned*>(w), (unsigned)bits);
+                else __stcs(reinterpret_cast<unsigned short*>(w), (unsigned short)bits);
+                if (lane == lanes - 1 && !last_pass) {
                     __stcg(row_out + n, make_int2(h_dn, g_dn));
                     if ((n % PUB) == PUB - 1 || n == LS - 1) {          // publish: data first, then the counter
                         __threadfence();
@@ -263,10 +284,10 @@ __global__ void __launch_bounds__(32) k2_fill_long_kernel(const K2Args a, int np
             recv_g = __shfl_up_sync(FULL, g_dn, 1);
         }
         if (last_pass) {
-            const int tl = (rows_here - 1) / R, kf = (rows_here - 1) % R;
+            const int tl = (rows_here - 1) / RR, kf = (rows_here - 1) % RR;
             int val = 0;
 #pragma unroll
-            for (int k = 0; k < R; ++k)
+            for (int k = 0; k < RR; ++k)
                 if (k == kf) val = L.H[k];
             val = __shfl_sync(FULL, val, tl);
             if (lane == 0) a.score[0] = val - (LQ + LS) * a.u;
@@ -289,7 +310,7 @@ __global__ void __launch_bounds__(128) k2_trace_kernel(const K2Args a, int npair
             a.out_cnt[p] = 2;
             continue;
         }
-        a.out_cnt[p] = k2_trace(a.dirs + a.dir_off[p], LQ, LS, R, ql, sl, a.moves + off, a.recs + off, out);
+        a.out_cnt[p] = k2_trace(a.dirs + a.dir_off[p], LQ, LS, a.rows_per_lane ? a.rows_per_lane : R, ql, sl, a.moves + off, a.recs + off, out);
     }
 }
 
@@ -310,16 +331,40 @@ cudaError_t k2_fill_launch(const K2Args& a, int grid_blocks, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// rows per lane of the striped kernel for a query of LQ rows (PG_K2_LONG_ROWS = 4 / 8 / 16 overrides).  A step costs
+// about 650 + 43 R cycles on a warp that has its scheduler to itself, and the matrix takes LS + LQ / R + 64 stripes
+// steps: measured on the 30 kb pair of config 5b, R = 16 / 8 / 4: 23.1 / 17.0 / 18.3 ms (38 ms before the chunked input).
+int k2_long_rows(int LQ, int LS)
+{
+    if (const char* e = getenv("PG_K2_LONG_ROWS")) {
+        const int v = atoi(e);
+        if (v == 4 || v == 8 || v == 16) return v;
+    }
+    (void)LS;
+    return LQ >= 4096 ? 8 : 16;
+}
+
+template <int RR>
+static cudaError_t long_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st)
+{
+    const size_t smem = (size_t)(a.dim + 1) * (RR / 4) * 32 * sizeof(int4);
+    cudaError_t e = cudaFuncSetAttribute(k2_fill_long_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)(MAXDIM + 1) * (RR / 4) * 32 * sizeof(int4)));
+    if (e != cudaSuccess) return e;
+    // every stripe in flight must be resident (a stripe waits for the one above): up to 16 single-warp CTAs per SM
+    int blocks = npass < sm_count * 16 ? npass : sm_count * 16;
+    k2_fill_long_kernel<RR><<<blocks, 32, smem, st>>>(a, npass);
+    return cudaGetLastError();
+}
+
 cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st)
 {
     if (a.dim < 1 || a.dim > MAXDIM) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)(a.dim + 1) * (R / 4) * 32 * sizeof(int4);
-    cudaError_t e = cudaFuncSetAttribute(k2_fill_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((size_t)(MAXDIM + 1) * (R / 4) * 32 * sizeof(int4)));
-    if (e != cudaSuccess) return e;
-    int blocks = npass < sm_count * 4 ? npass : sm_count * 4;
-    k2_fill_long_kernel<<<blocks, 32, smem, st>>>(a, npass);
-    return cudaGetLastError();
+    switch (a.rows_per_lane) {
+    case 4: return long_launch<4>(a, npass, sm_count, st);
+    case 8: return long_launch<8>(a, npass, sm_count, st);
+    default: return long_launch<16>(a, npass, sm_count, st);
+    }
 }
 
 cudaError_t k2_trace_launch(const K2Args& a, int npairs, cudaStream_t st)

@@ -92,6 +92,7 @@ PG_HD unsigned long long k2_lane_step(K2Lane<R>& L, const int* sc, int negv, int
 }
 
 // ---- direction-bit addressing -------------------------------------------------------------------
+// One lane-step owns R / 2 bytes (4 bits per row); with R = 16 that is the 64-bit word above.  Sizes in 64-bit words.
 PG_HD long long k2_words_per_pair(int LQ, int LS, int R)
 {
     if (LQ <= 0 || LS <= 0) return 0;
@@ -99,7 +100,8 @@ PG_HD long long k2_words_per_pair(int LQ, int LS, int R)
     const int npass = (LQ + rpp - 1) / rpp;
     const int last_rows = LQ - (npass - 1) * rpp;
     const int last_lanes = (last_rows + R - 1) / R;
-    return ((long long)(npass - 1) * (LS + 31) + (LS + last_lanes - 1)) * 32;
+    const long long slots = ((long long)(npass - 1) * (LS + 31) + (LS + last_lanes - 1)) * 32;
+    return (slots * (R / 2) + 7) / 8;
 }
 
 PG_HD unsigned k2_nibble(const unsigned long long* words, int LS, int R, int m, int n)
@@ -107,8 +109,9 @@ PG_HD unsigned k2_nibble(const unsigned long long* words, int LS, int R, int m, 
     const int rpp = 32 * R;
     const int pass = m / rpp, rm = m - pass * rpp;
     const int lane = rm / R, k = rm - lane * R;
-    const long long idx = ((long long)pass * (LS + 31) + (n + lane)) * 32 + lane;
-    return (unsigned)(words[idx] >> (4 * k)) & 15u;
+    const long long slot = ((long long)pass * (LS + 31) + (n + lane)) * 32 + lane;
+    const unsigned char b = reinterpret_cast<const unsigned char*>(words)[slot * (R / 2) + (k >> 1)];
+    return (unsigned)(b >> (4 * (k & 1))) & 15u;
 }
 
 struct K2Rec { int m, n, p; };

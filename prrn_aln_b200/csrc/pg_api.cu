@@ -949,8 +949,10 @@ extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
         bool long_pair = false;
         while (c1 < npairs) {
             const int qa = a_idx[order[c1]], sb = b_idx[order[c1]];
-            const size_t w = (size_t)k2_words_per_pair(d->h_wlen[qa], d->h_wlen[sb], Rr);
             const bool is_long = d->h_wlen[qa] > (LONG_PASSES - 1) * rpp && d->h_wlen[sb] > 0;
+            // (the striped kernel chooses its own rows per lane, and with them the size of a lane-step's direction bits)
+            const size_t w = (size_t)k2_words_per_pair(d->h_wlen[qa], d->h_wlen[sb],
+                                                        is_long ? k2_long_rows(d->h_wlen[qa], d->h_wlen[sb]) : Rr);
             if (is_long) {
                 if (c1 > c0) break;             // close the chunk before it
                 long_pair = true;
@@ -1019,7 +1021,8 @@ extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
         int long_npass = 0;
         if (long_pair) {
             // row buffers of all stripes + progress counters + ticket, zeroed
-            long_npass = (d->h_wlen[pq[0]] + rpp - 1) / rpp;
+            a.rows_per_lane = k2_long_rows(d->h_wlen[pq[0]], max_ls);
+            long_npass = (d->h_wlen[pq[0]] + 32 * a.rows_per_lane - 1) / (32 * a.rows_per_lane);
             const size_t rb = sizeof(int2) * (size_t)long_npass * (size_t)max_ls;
             const size_t need = up256(rb) + sizeof(int32_t) * (size_t)(long_npass + 2);
             if ((rc = ensure_cap(c, &c->d_rowbuf, &c->rowbuf_cap, need))) break;

@@ -138,6 +138,7 @@ struct K2Args {
     // striped long-pair kernel (k2_fill_long_kernel): one pair, one warp per 512-row stripe
     int32_t* progress;          // [npass] columns whose bottom row a stripe has published
     int32_t* ticket;            // stripe dispenser (scheduling order = dependency order)
+    int32_t rows_per_lane;      // rows per lane of the fill that wrote `dirs` (0 = k2_rows_per_lane(); the striped kernel: 4 / 8 / 16)
 };
 
 // group-to-group alignment kernel (k3_groups.cu)
@@ -269,6 +270,7 @@ cudaError_t k2_fill_launch(const K2Args& a, int grid_blocks, cudaStream_t st);
 cudaError_t k2_trace_launch(const K2Args& a, int npairs, cudaStream_t st);
 cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st);
 int k2_rows_per_lane();
+int k2_long_rows(int LQ, int LS);     // rows per lane of the striped long-pair kernel
 int k2_warps_per_block();
 int k2_blocks_per_sm();
 // k3_groups.cu

@@ -39,7 +39,10 @@ static int emulate(const uint8_t* q, const uint8_t* s, const K1Geom& g, const in
                 }
                 int h_dn, g_dn;
                 unsigned long long bits = k2_lane_step(L[t], sc, negv, h_up, g_up, mbase == 0, &h_dn, &g_dn);
-                words[((size_t)pass * (g.LS + 31) + step) * 32 + t] = bits;
+                {   // R / 2 bytes per lane-step, slot (pass * (LS + 31) + step) * 32 + lane (k2_core.cuh)
+                    unsigned char* w = reinterpret_cast<unsigned char*>(words.data()) + (((size_t)pass * (g.LS + 31) + step) * 32 + t) * (R / 2);
+                    for (int b = 0; b < R / 2; ++b) w[b] = (unsigned char)(bits >> (8 * b));
+                }
                 send_h[cur][t] = h_dn; send_g[cur][t] = g_dn;
                 if (t == T - 1) { rowH[n] = h_dn; rowG[n] = g_dn; }
             }
