@@ -56,30 +56,35 @@ PG_HD unsigned long long k2_lane_step(K2Lane<R>& L, const int* sc, int negv, int
 {
     int diag = L.hdiag;
     // vertical state entering row mbase: open from H(mbase-1,n) only if strictly better
-    int x0 = h_up + negv;
+    const int x0 = h_up + negv;
     bool gopen = x0 > g_up;
-    int g = gopen ? x0 : g_up;
+    int g = x0 > g_up ? x0 : g_up;
     if (first_row) { g = K1_NEG; gopen = false; }
     unsigned long long bits = 0;
     unsigned eopen_next = 0;
     int h = h_up, gcur = g_up;
+    // The VALUES go through max() only, so that the chain from one row to the next is two operations
+    // (h = max(t, g); g' = max(h - v, g)) and everything else -- t = max(diagonal, horizontal), the tie-rule
+    // predicates that become direction bits, the horizontal state of the next column -- hangs off that chain
+    // (a single warp per scheduler runs these kernels' long pairs: the dependent chain is the step time).
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         const int d = diag + sc[k];
         const int e = L.E[k];
+        const int t = d > e ? d : e;
+        const bool e_gt_d = e > d;
         const bool fge = e >= g;                 // F beats G on ties (fwd2c.h:431)
-        const int mxv = fge ? e : g;
-        const bool nd = mxv > d;                 // a gap state wins only if strictly better (:453)
-        h = nd ? mxv : d;
+        const bool nd = e_gt_d || g > d;         // a gap state wins only if strictly better (:453)
+        h = t > g ? t : g;
         const unsigned src = nd ? (fge ? 2u : 1u) : 0u;
         const unsigned nib = src | (gopen ? 4u : 0u) | (((L.eopen >> k) & 1u) << 3);
         bits |= (unsigned long long)nib << (4 * k);
         const int x = h + negv;
         gcur = g;
         gopen = x > g;                           // next row's vertical state (fwd2c.h:405-408)
-        g = gopen ? x : g;
+        g = x > g ? x : g;
         const bool eo = x > e;                   // next column's horizontal state (:426-429)
-        L.E[k] = eo ? x : e;
+        L.E[k] = x > e ? x : e;
         eopen_next |= (eo ? 1u : 0u) << k;
         diag = L.H[k];
         L.H[k] = h;

@@ -52,8 +52,26 @@ def c5a(ctx, n=10000):
     h = npair // 3
     part = ctx.calcdist(ss, prm, M, h, h + 100000)
     bad += not np.array_equal(part, d[h:h + 100000])
-    print(json.dumps({"config": "c5a", "sequences": len(enc), "pairs": npair, "cells": int(cells), "seconds_e2e": dt,
-                      "gcups_e2e": cells / dt / 1e9, "oracle_sample_mismatches": int(bad), "checksum": float(d.sum())}))
+    out = {"config": "c5a", "sequences": len(enc), "pairs": npair, "cells": int(cells), "seconds_e2e": dt,
+           "gcups_e2e": cells / dt / 1e9, "oracle_sample_mismatches": int(bad), "checksum": float(d.sum())}
+    # CPU beside it: the reference's own calcdist on a 1 % sample of the pairs (every 10th sequence: 1,000 sequences,
+    # 499,500 pairs of the same length distribution) on all host cores, compared value by value, extrapolated by cells
+    import refio
+    if refio.available("d"):
+        from prrn_aln_b200 import sharding
+        sub = list(range(0, len(seqs), 10))
+        fa = "/tmp/prrn_c5a_sample_%d.fa" % os.getpid()
+        gen_synth.write_fasta(fa, [seqs[i] for i in sub])
+        th = os.cpu_count() or 1
+        r = refio.run("dist", fa, flavour="d", threads=th, sh=-60)
+        os.unlink(fa)
+        want = np.array(r["dist"])
+        got = np.array([d[P.elem(sub[i], sub[j])] for j in range(1, len(sub)) for i in range(j)])
+        scells = int(sharding.row_costs(np.array([len(seqs[i]) for i in sub]), -60)[0].sum())
+        out["cpu_sample"] = {"kind": "reference", "cores": th, "pairs": len(want), "cells": scells, "seconds": r["time"],
+                             "gcups": scells / r["time"] / 1e9, "mismatches_vs_gpu": int(np.sum(want != got)),
+                             "extrapolated_seconds_all_pairs": r["time"] * cells / scells}
+    print(json.dumps(out))
 
 
 def c5b(ctx, length=30000):
@@ -79,8 +97,21 @@ def c5b(ctx, length=30000):
             s += float(np.sum(Mn[a[m0:m1], b[n0:n1]]))
         else:
             s -= 6 + 2 * (dm + dn)
-    print(json.dumps({"config": "c5b", "len": [len(a), len(b)], "cells": int(cells), "seconds_e2e": dt, "gcups_e2e": cells / dt / 1e9,
-                      "fill_kernel_ms": fill_ms, "gcups_fill": cells / (fill_ms * 1e-3) / 1e9, "score": float(sc[0]), "path_rescored": s, "path_valid": bool(ok and s == float(sc[0])), "corners": len(pts)}))
+    out = {"config": "c5b", "len": [len(a), len(b)], "cells": int(cells), "seconds_e2e": dt, "gcups_e2e": cells / dt / 1e9,
+           "fill_kernel_ms": fill_ms, "gcups_fill": cells / (fill_ms * 1e-3) / 1e9, "score": float(sc[0]), "path_rescored": s,
+           "path_valid": bool(ok and s == float(sc[0])), "corners": len(pts)}
+    gpath = os.path.join(ROOT, "tests", "golden", "align_c5b_30k.json")
+    if length == 30000 and os.path.exists(gpath):       # the reference's own corner list for this pair (tools/make_golden.py dna)
+        g = json.load(open(gpath))["pairs"][0]
+        out["equals_reference_alignment"] = bool(float(sc[0]) == g["score"] and pts == [tuple(x) for x in g["skl"]])
+    import refio
+    if os.environ.get("C5B_CPU") == "1" and refio.available("f"):     # the reference itself on one host core (about a minute)
+        fa = "/tmp/prrn_c5b_%d.fa" % os.getpid()
+        gen_synth.write_fasta(fa, dna)
+        r = refio.run("align", fa, flavour="f", molc="n", crs=1, sh=-50, mtx="pam")
+        os.unlink(fa)
+        out["cpu_reference"] = {"cores": 1, "seconds": r["time"], "gcups": cells / r["time"] / 1e9, "score": r["aligns"][(0, 1)]["score"]}
+    print(json.dumps(out))
 
 
 def c4(ctx, members=60, length=2000, pairs=6):
