@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <numeric>
@@ -512,6 +513,10 @@ static void build_packed_plan(const pg_dev_seqs* d, int64_t k0, int64_t k1, int 
     std::iota(by_len.begin(), by_len.end(), 0);
     std::stable_sort(by_len.begin(), by_len.end(), [&](int x, int y) { return d->h_wlen[x] > d->h_wlen[y]; });
     for (int p = 0; p < nJ; ++p) posJ[J[p]] = p;
+    // the whole triangle of the whole set (what calcdist asks for on one GPU): no range tests needed
+    const bool full = k0 == 0 && k1 == tri((int64_t)nseq) && jhi == nseq - 1;
+    std::vector<int> by_len_lo;                                  // sequences below jlo, longest first
+    for (int x : by_len) if (x < jlo) by_len_lo.push_back(x);
     // the subject lists of the query pairs are independent: host threads build them side by side
     const int npq = (nJ + 1) / 2;
     std::vector<std::vector<uint32_t>> lists(npq);
@@ -522,6 +527,35 @@ static void build_packed_plan(const pg_dev_seqs* d, int64_t k0, int64_t k1, int 
             const bool has_b = p + 1 < nJ;
             std::vector<uint32_t>& list = lists[pq];
             list.reserve((size_t)jhi / 2 + 16);
+            if (full) {
+                // Whole triangle: every pair is in range, so the subjects of (p, p + 1) are known without scanning all
+                // sequences -- the positions p + 1 .. p + h + 2 (mod |J|) of the tournament, longest first (J is sorted
+                // by length: descending position, the wrapped positions last), and the sequences below jlo (sequence 0)
+                // merged in by length.
+                int r = 0;                                       // next rectangle-part subject (by_len_lo: longest first)
+                auto emit_lo = [&](int upto_len) {               // rectangle subjects at least as long as upto_len
+                    while (r < (int)by_len_lo.size() && d->h_wlen[by_len_lo[r]] >= upto_len) {
+                        list.push_back((uint32_t)by_len_lo[r] | (1u << 30) | ((has_b ? 1u : 0u) << 31));
+                        ++r;
+                    }
+                };
+                const int last = p + h + 2;                      // dd_a in [1, h + 2] covers both queries, antipodal ties included
+                auto visit = [&](int py) {
+                    if (py == p || py < 0 || py >= nJ) return;
+                    const uint32_t va = assigned(p, py);
+                    const uint32_t vb = has_b && py != p + 1 && assigned(p + 1, py);
+                    if (!(va | vb)) return;
+                    emit_lo(d->h_wlen[J[py]]);
+                    list.push_back((uint32_t)J[py] | (va << 30) | (vb << 31));
+                };
+                if (nJ <= h + 3) { for (int py = nJ - 1; py >= 0; --py) visit(py); }
+                else {
+                    for (int q = std::min(last, nJ - 1); q >= p + 1; --q) visit(q);
+                    for (int q = last - nJ; q >= 0; --q) visit(q);              // wrapped around: the short end of J
+                }
+                emit_lo(-1);
+                continue;
+            }
             for (int s : by_len) {
                 uint32_t va, vb;
                 if (s < jlo) {                                   // (a) rectangle part
@@ -736,25 +770,39 @@ extern "C" int pg_calcdist_dev(pg_context* c, pg_dev_seqs* d, const pg_params* p
     return PG_OK;
 }
 
+static double now_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 extern "C" int pg_calcdist(pg_context* c, const pg_seqs* s, const pg_params* prm, const void* mtx, int32_t dim,
                            int64_t k_begin, int64_t k_end, void* out_dist)
 {
     if (!c) return PG_ERR_ARG;
     if (!s || !prm) return fail(c, PG_ERR_ARG, "pg_calcdist: NULL argument");
+    static const bool timing = getenv("PG_TIMING") != nullptr;     // PG_TIMING=1: host-side breakdown of this call on stderr
+    const double t0 = timing ? now_ms() : 0;
     pg_dev_seqs* d = nullptr;
     int rc = seqs_upload_impl(c, s, &d, true);
+    const double t1 = timing ? now_ms() : 0;
     if (rc) return rc;
     const size_t esz = prm->vtype ? sizeof(double) : sizeof(float);
     const size_t cnt = k_end > k_begin ? (size_t)(k_end - k_begin) : 0;
     if (cnt && !out_dist) { pg_seqs_free(c, d); return fail(c, PG_ERR_ARG, "pg_calcdist: output is NULL"); }
     rc = ensure_cap(c, &c->d_out, &c->out_cap, std::max<size_t>(cnt * esz, 16));
     if (!rc) rc = pg_calcdist_dev(c, d, prm, mtx, dim, k_begin, k_end, c->d_out, nullptr, nullptr);
+    const double t2 = timing ? now_ms() : 0;
     if (!rc && cnt) {
         cudaError_t e = cudaMemcpyAsync(out_dist, c->d_out, cnt * esz, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail(c, PG_ERR_CUDA, std::string("pg_calcdist D2H: ") + cudaGetErrorString(e));
     }
     pg_seqs_free(c, d);
+    if (timing)
+        fprintf(stderr, "pg_calcdist: upload %.3f ms, schedule + launches %.3f ms, kernels + D2H + sync %.3f ms\n", t1 - t0, t2 - t1,
+                now_ms() - t2);
     return rc;
 }
 

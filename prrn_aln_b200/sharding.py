@@ -100,12 +100,20 @@ def gather_shards(shard, chunk, npair, world, dist=None):
     return full[:npair]
 
 
-def calcdist_sharded(ctx, seqs, prm, mtx, rank, world, dist=None, compute=None):
-    """calcdist over `world` ranks.  `compute(k0, k1) -> numpy/torch vector` defaults to the CUDA
-    path of `ctx`; the CPU tests inject a stand-in to exercise the sharding/gather logic only."""
+def calcdist_sharded(ctx, seqs, prm, mtx, rank, world, dist=None, compute=None, sh=None):
+    """calcdist over `world` ranks.  Rank r computes a contiguous range of the condensed index -- with `sh` given
+    (the band shoulder, alprm.sh) the ranges carry equal numbers of DP cells (cost_balanced_ranges), else equal
+    numbers of pairs -- and ONE all-gather of equal-size (padded) shards assembles the vector on every rank.
+    `compute(k0, k1) -> numpy/torch vector` defaults to the CUDA path of `ctx`; the CPU tests inject a stand-in to
+    exercise the sharding / gather logic only."""
     import torch
     npair = seqs.n * (seqs.n - 1) // 2
-    k0, k1, chunk = shard_range(npair, world, rank)
+    if sh is None:
+        ranges = [shard_range(npair, world, r)[:2] for r in range(world)]
+    else:
+        ranges = cost_balanced_ranges(np.asarray(seqs.lens), sh, world)
+    chunk = max(max(b - a for a, b in ranges), 1)
+    k0, k1 = ranges[rank]
     if compute is None:
         def compute(a, b):
             return ctx.calcdist(seqs, prm, mtx, a, b)
@@ -115,7 +123,11 @@ def calcdist_sharded(ctx, seqs, prm, mtx, rank, world, dist=None, compute=None):
     shard[:k1 - k0] = part
     if ctx is not None and torch.cuda.is_available():
         shard = shard.cuda()
-    return gather_shards(shard, chunk, npair, world, dist)
+    if world == 1 or dist is None:
+        return shard[:npair]
+    full = torch.empty(chunk * world, dtype=shard.dtype, device=shard.device)
+    dist.all_gather_into_tensor(full, shard)
+    return torch.cat([full[r * chunk: r * chunk + (b - a)] for r, (a, b) in enumerate(ranges)])
 
 
 # ---- candidate partitions of the refinement step (Prrn::best_of_n, src/prrn5.cc:594-631) ---------

@@ -55,7 +55,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, nseq, q):
+def _worker(rank, world, port, nseq, q, sh=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -66,7 +66,7 @@ def _worker(rank, world, port, nseq, q):
     def compute(k0, k1):            # stand-in "distance": a function of k only
         return np.arange(k0, k1, dtype=np.float64) * 0.5 + 1.0
 
-    full = sharding.calcdist_sharded(None, seqs, None, None, rank, world, dist, compute)
+    full = sharding.calcdist_sharded(None, seqs, None, None, rank, world, dist, compute, sh=sh)
     npair = nseq * (nseq - 1) // 2
     ok = bool(torch.equal(full, torch.arange(npair, dtype=torch.float64) * 0.5 + 1.0))
     q.put((rank, ok, int(full.numel())))
@@ -74,12 +74,13 @@ def _worker(rank, world, port, nseq, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nseq", [(2, 11), (3, 7), (2, 2)])
-def test_all_gather_assembles_condensed_vector(world, nseq):
+@pytest.mark.parametrize("world,nseq,sh", [(2, 11, None), (3, 7, None), (2, 2, None), (2, 23, -60), (3, 17, 3)])
+def test_all_gather_assembles_condensed_vector(world, nseq, sh):
+    """sh None: equal-count shards; sh given: cost-balanced shards of unequal length, padded for the all-gather."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, nseq, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nseq, q, sh)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
