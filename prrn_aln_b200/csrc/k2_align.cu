@@ -10,6 +10,7 @@
 //                    the reference's record rules and emits the corner list in Vmf back-walk order.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "k2_core.cuh"
@@ -162,6 +163,19 @@ __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k2_fill_kernel(const K
 // k2_fill_kernel, so the traceback kernel is shared.
 constexpr int PUB = 16;
 
+// progress counters between stripes: release store / acquire load at GPU scope (a __threadfence() compiles to
+// MEMBAR.SC.GPU and, on the reading side, an L1 invalidation that also throws away the subject's residues)
+__device__ __forceinline__ void st_release(int* p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // RR rows per lane: a stripe is 32 * RR rows.  One warp alone on its scheduler runs a lane-step as one dependent
 // chain (about 30 cycles per row + 150 of fixed work), so narrow stripes (RR = 4: 128 rows, 235 warps for a 30 kb
 // query) finish the matrix in LS + stripes * skew steps of a quarter of the length.  The bottom row of the stripe
@@ -210,10 +224,14 @@ __global__ void __launch_bounds__(32) k2_fill_long_kernel(const K2Args a, int np
         const bool last_pass = pass == npass - 1;
         const int2* const row_in = a.rowbuf + (int64_t)(pass - 1) * LS;      // bottom row of the stripe above
         int2* const row_out = a.rowbuf + (int64_t)pass * LS;
-        volatile int* const prog_in = a.progress + (pass - 1);
+        const int* const prog_in = a.progress + (pass - 1);
         // direction bits: RR / 2 bytes per lane-step, slot (pass * (LS + 31) + step) * 32 + lane (k2_core.cuh)
         unsigned char* const words = dir_base + ((int64_t)pass * (LS + 31) * 32 + lane) * (RR / 2);
 
+#ifdef K2_TIMERS
+        unsigned long long tm0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm0));
+        long long tm_wait = 0;
+#endif
         K2Lane<RR> L;
         k2_lane_init(L, g, mbase);
         const int lwm = g.lw + mbase;
@@ -224,16 +242,24 @@ __global__ void __launch_bounds__(32) k2_fill_long_kernel(const K2Args a, int np
         const int nsteps = LS + lanes - 1;
         int avail = 0;          // columns of the stripe above known to be published
         int2 chunk = make_int2(K1_NEG, K1_NEG);         // lane i: row_in[32 * (step / 32) + i]
+        // the residue of the column a lane works on next is fetched one step ahead (off the step's critical path;
+        // s[LS] behind the last column is padding or the next sequence and never used)
+        int nxt = (lane < lanes && LS > 0) ? (int)__ldg(s) : 0;
 
         for (int step = 0; step < nsteps; ++step) {
             const int n = step - lane;
             if (pass > 0 && (step & 31) == 0 && step < LS) {        // lane 0 enters a new chunk of 32 columns
                 const int need = min(step + 32, LS);
+#ifdef K2_TIMERS
+                const long long tw0 = clock64();
+#endif
                 if (lane == 0) {
-                    while (avail < need) avail = *prog_in;          // wait for the stripe above
-                    __threadfence();
+                    while (avail < need) avail = ld_acquire(prog_in);       // wait for the stripe above
                 }
                 __syncwarp();
+#ifdef K2_TIMERS
+                tm_wait += clock64() - tw0;
+#endif
                 if (step + lane < LS) chunk = __ldcg(row_in + step + lane);
             }
             const int in_h = __shfl_sync(FULL, chunk.x, step & 31);
@@ -259,7 +285,8 @@ __global__ void __launch_bounds__(32) k2_fill_long_kernel(const K2Args a, int np
                         L.E[4 * j] = v.x; L.E[4 * j + 1] = v.y; L.E[4 * j + 2] = v.z; L.E[4 * j + 3] = v.w;
                     }
                 }
-                const int letter = __ldg(s + n);
+                const int letter = nxt;
+                nxt = (int)__ldg(s + n + 1);
                 const int4* pl = pp + letter * ((RR / 4) * 32);
                 int sc[RR];
 #pragma unroll
@@ -274,10 +301,8 @@ __global__ void __launch_bounds__(32) k2_fill_long_kernel(const K2Args a, int np
                 else __stcs(reinterpret_cast<unsigned short*>(w), (unsigned short)bits);
                 if (lane == lanes - 1 && !last_pass) {
                     __stcg(row_out + n, make_int2(h_dn, g_dn));
-                    if ((n % PUB) == PUB - 1 || n == LS - 1) {          // publish: data first, then the counter
-                        __threadfence();
-                        *(volatile int*)(a.progress + pass) = n + 1;
-                    }
+                    if ((n % PUB) == PUB - 1 || n == LS - 1)            // publish: data first, then the counter
+                        st_release(a.progress + pass, n + 1);
                 }
             }
             recv_h = __shfl_up_sync(FULL, h_dn, 1);
@@ -292,6 +317,12 @@ __global__ void __launch_bounds__(32) k2_fill_long_kernel(const K2Args a, int np
             val = __shfl_sync(FULL, val, tl);
             if (lane == 0) a.score[0] = val - (LQ + LS) * a.u;
         }
+#ifdef K2_TIMERS
+        { unsigned long long tm1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm1));
+          if (lane == 0 && (pass < 4 || pass % 16 == 0 || pass == npass - 1))
+              printf("k2 stripe %d of %d: start %.1f us, ran %.1f us, waited %.1f us, %d steps\n", pass, npass, (double)(tm0 % 100000000000ull) * 1e-3,
+                     (double)(tm1 - tm0) * 1e-3, tm_wait / 1965., nsteps); }
+#endif
         __syncwarp();
     }
 }
@@ -331,9 +362,11 @@ cudaError_t k2_fill_launch(const K2Args& a, int grid_blocks, cudaStream_t st)
     return cudaGetLastError();
 }
 
-// rows per lane of the striped kernel for a query of LQ rows (PG_K2_LONG_ROWS = 4 / 8 / 16 overrides).  A step costs
-// about 650 + 43 R cycles on a warp that has its scheduler to itself, and the matrix takes LS + LQ / R + 64 stripes
-// steps: measured on the 30 kb pair of config 5b, R = 16 / 8 / 4: 23.1 / 17.0 / 18.3 ms (38 ms before the chunked input).
+// rows per lane of the striped kernel for a query of LQ rows (PG_K2_LONG_ROWS = 4 / 8 / 16 overrides).  Measured on the
+// 30 kb pair of config 5b (-DK2_TIMERS prints per-stripe times): with R = 8 the first stripe alone walks its 30,048
+// steps in 14.1 ms (923 cycles per step: ~340 instructions of a warp that has its scheduler to itself, at its own
+// instruction-level parallelism), the other 117 stripes finish 4.8 ms later (87 steps of skew each): R = 16 / 8 / 4:
+// 23.1 / 17.0 / 18.3 ms (38 ms before the chunked input).  The per-step instruction count, not the hand-over, is the limit.
 int k2_long_rows(int LQ, int LS)
 {
     if (const char* e = getenv("PG_K2_LONG_ROWS")) {
