@@ -102,7 +102,12 @@ int pg_align_pairs_ng(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx
  * for recd_t = DPunit (NGP_ALB, groups without internal gaps), DPunit_hf (HLF_ALB / RHF_ALB),
  * DPunit_pf (GPF_ALB) and DPunit_nv (NTV_ALB), as align2 dispatches it (src/maln2.cc:1899-1910), affine or two-piece, for a
  * BATCH of independent (a, b) pairs -- e.g. the candidate partitions of Prrn::best_of_n
- * (src/prrn5.cc:594-631).  Precondition as in the reference: PwdM pwd(seqs) already ran (sequences
+ * (src/prrn5.cc:594-631).  alnmode NGP_ALN (algmode.bnd = 0 on groups without gap profile: align2 calls
+ * alignC<DPunit>(seqs, pwd, scr, true), src/maln2.cc:1906) runs the rectangle form, forwardA + initA (src/fwd2c.h:
+ * 111-135,231-356): every cell of the window, no band; it needs b.left = 0 and b's per-column arrays ONE COLUMN
+ * LONGER (npos + 1 entries: forwardA reads b's thickness at position b.right, :240-249).  The rectangle forms with
+ * gap profiles (HLF_ALN / RHF_ALN / GPF_ALN / NTV_ALN) and the rectangle HomScoreC return PG_ERR_UNSUPPORTED.
+ * Precondition as in the reference: PwdM pwd(seqs) already ran (sequences
  * swapped if pwd->swp, mkthick / Gfq / convseq done).  A pg_group is what Fwd2c reads from one mSeq
  * through mSeqItr for the columns left-1 .. right-1 (npos = right - left + 1 entries):
  *   cfq, efq   SeqThk::cfq / efq per column                         src/mseq.h:70-74
@@ -133,7 +138,7 @@ typedef struct {
 } pg_group;
 
 typedef struct {
-    int32_t alnmode;            /* ALN_MODE, src/aln.h:71-76: 6 NGP_ALB, 7 HLF_ALB, 8 RHF_ALB, 9 GPF_ALB, 10 NTV_ALB
+    int32_t alnmode;            /* ALN_MODE, src/aln.h:71-76: 1 NGP_ALN, 6 NGP_ALB, 7 HLF_ALB, 8 RHF_ALB, 9 GPF_ALB, 10 NTV_ALB
                                    (100 is internal: the Aln2b1 recurrence behind pg_align_pairs_ng)   */
     int32_t Noll, codonk1;      /* PwdB::Noll, PwdB::codonk1 (src/aln2.cc:100,117)                     */
     int32_t sh;                 /* pwd->alnprm.sh                                                      */

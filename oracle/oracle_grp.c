@@ -293,7 +293,10 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
     typedef g_unit_##SUFFIX U;                                                                       \
     g_ctx_##SUFFIX C;                                                                                \
     C.a = a; C.b = b; C.p = p; C.mtx = mtx; C.dim = dim;                                             \
-    C.mode = p->alnmode == 6 ? 0 : (p->alnmode == 9 ? 2 : (p->alnmode == 10 ? 3 : 1));   /* NGP / HLF, RHF / GPF / NTV _ALB */\
+    /* alnmode 1 (NGP_ALN): the rectangle variant forwardA + initA (fwd2c.h:111-135,231-356), groups without gap profile */\
+    const int rect = p->alnmode == 1;                                                               \
+    const int am = rect ? 6 : p->alnmode;                                                           \
+    C.mode = am == 6 ? 0 : (am == 9 ? 2 : (am == 10 ? 3 : 1));           /* NGP / HLF, RHF / GPF / NTV */\
     C.wgop = (VT)p->Weighted_GOP; C.bgop = (VT)p->Basic_GOP;                                         \
     const VT BasicGOP = (VT)p->BasicGOP, BasicGEP = (VT)p->BasicGEP, LongGOP = (VT)p->LongGOP, LongGEP = (VT)p->LongGEP;\
     const VT u2divu1 = BasicGEP < 0 ? (VT)LongGEP / BasicGEP : 0;       /* fwd2c.h:85-86 */          \
@@ -303,7 +306,7 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
     orc_seq sa = {0, a->len, al, ar, 0, 0}, sb = {0, b->len, bl, br, 0, 0};                          \
     orc_window w;                                                                                    \
     orc_stripe(&sa, &sb, p->sh, &w);                                                                 \
-    const int lw = w.lw, up = w.up;                                                                  \
+    const int lw = rect ? bl - ar : w.lw, up = rect ? br - al : w.up;    /* rectangle: every cell */  \
     const int capa = (a->hetero > 0 ? a->hetero : 0) + 3, capb = (b->hetero > 0 ? b->hetero : 0) + 3;\
     /* staged column index of sequence position x: x - (left - 1) */                                 \
     const int A0 = al - 1, B0 = bl - 1;                                                              \
@@ -325,7 +328,7 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
     o_add(&st, 0, 0, 0);                           /* skip 0-th record (fwd2c.h:361) */              \
     int64_t ncell = 0;                                                                               \
     /* initB (fwd2c.h:138-176): origin, then the boundary row with asi at a.left - 1 */              \
-    Hp[0].val = 0; Hp[0].dir = G_DIAG; Hp[0].ptr = rr ? (long)(bl - al) : o_add(&st, al, bl, 0);  /* fwd2c.h:144 */\
+    Hp[0].val = 0; Hp[0].dir = rect ? 0 : G_DIAG /* initA only clears the origin (:116) */; Hp[0].ptr = rr ? (long)(bl - al) : o_add(&st, al, bl, 0);  /* fwd2c.h:144 */\
     {                                                                                                \
         int rr = br - al; if (up < rr) rr = up;                                                      \
         const int r0 = bl - al;                                                                      \
@@ -333,7 +336,8 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
             const int ia = al - 1 - A0, ib = (bl + k - 1) - B0;                                      \
             VT pub = g_unp_##SUFFIX(&C, b, ib, a, ia);                                               \
             VT gnp = g_gapopen_##SUFFIX(&C, &Hp[k - 1], ia, ib, -1);                                 \
-            gnp = (k < codonk1) ? gnp + pub : (VT)(v2divv1 * gnp + u2divu1 * pub);                   \
+            /* initB tests the column count after its increment (:156-160), initA before (:125-131) */ \
+            gnp = ((rect ? k - 1 : k) < codonk1) ? gnp + pub : (VT)(v2divv1 * gnp + u2divu1 * pub);  \
             g_update_##SUFFIX(&C, &Hp[k], &Hp[k - 1], ia, ib, gnp, -1);                              \
         }                                                                                            \
     }                                                                                                \
@@ -346,7 +350,15 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
         /* boundary column cell of this row (initB second loop), bsi at b.left - 1 */                \
         {                                                                                            \
             int r = bl - 1 - m;                                                                      \
-            if (r >= rr_col) {                                                                       \
+            if (rect) {                                                                              \
+                /* forwardA computes the boundary cell of a row in place (:245-249): no long-gap switch, and bsi    \
+                   is where the previous row left it -- position 0 before the first row (`mSeqItr bsi(b, 0)`,     \
+                   :240), position b.right afterwards */                                             \
+                const int ib = (m == al ? 0 : br) - B0;                                              \
+                VT gnp = g_gapopen_##SUFFIX(&C, colprev, ia, ib, 1) + g_unp_##SUFFIX(&C, a, ia, b, ib);\
+                g_update_##SUFFIX(&C, &Hc[0], colprev, ia, ib, gnp, 1);                              \
+                g_copy_##SUFFIX(&C, colprev, &Hc[0]);                                                \
+            } else if (r >= rr_col) {                                                                \
                 ++colk;                                                                              \
                 const int ib = bl - 1 - B0;                                                          \
                 VT pua = g_unp_##SUFFIX(&C, a, ia, b, ib);                                           \
@@ -373,8 +385,8 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
             g_update_##SUFFIX(&C, dg, &Hp[j - 1], ia, ib, dab + gop, 0);                             \
             VT gnp;                                                                                  \
             const U *mx;                                                                             \
-            if (m > al) {       /* vertical (fwd2c.h:401-409) */                                     \
-                if (a->nils) pua = g_unp_##SUFFIX(&C, a, ia, b, ib);                                 \
+            if (m > al || rect) {   /* vertical (fwd2c.h:401-409; forwardA has no first-row skip, :263-271) */\
+                if (a->nils || rect) pua = g_unp_##SUFFIX(&C, a, ia, b, ib);                         \
                 gnp = g_gapopen_##SUFFIX(&C, gabove, ia, ib, 1);                                     \
                 gop = g_gapopen_##SUFFIX(&C, habove, ia, ib, 1);                                     \
                 if (!g_isvert(habove->dir) && (habove->val + gop > gabove->val + gnp))               \
@@ -384,7 +396,7 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
                 mx = g;                                                                              \
                 if (Noll == 3) {    /* vertical2 (fwd2c.h:411-420) */                                \
                     gnp = (VT)(v2divv1 * g_gapopen_##SUFFIX(&C, g2above, ia, ib, 1));                \
-                    gop = (VT)(v2divv1 * gop);                                                       \
+                    gop = rect ? (VT)(v2divv1 + gop) : (VT)(v2divv1 * gop);     /* forwardA: `+`, fwd2c.h:276 */\
                     if (!g_isvert(habove->dir) && (habove->val + gop > g2above->val + gnp))          \
                         g_update_##SUFFIX(&C, g2, habove, ia, ib, gop, 1);                           \
                     else g_update_##SUFFIX(&C, g2, g2above, ia, ib, gnp, 1);                         \
@@ -395,7 +407,7 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
                 g_copy_##SUFFIX(&C, g, black); g_copy_##SUFFIX(&C, g2, black);                       \
                 mx = g;                                                                              \
             }                                                                                        \
-            if (n > bl) {       /* horizontal (fwd2c.h:422-431) */                                   \
+            if (n > bl || rect) {   /* horizontal (fwd2c.h:422-431; forwardA: no first-column skip, :286-294) */\
                 VT pub = g_unp_##SUFFIX(&C, b, ib, a, ia);                                           \
                 gnp = g_gapopen_##SUFFIX(&C, f1, ia, ib, -1);                                        \
                 gop = g_gapopen_##SUFFIX(&C, hleft, ia, ib, -1);                                     \

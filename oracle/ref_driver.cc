@@ -94,7 +94,7 @@ static void dump_gfq(const char* tag, GFREQ** pp)
 }
 
 // everything Fwd2c reads from one group through mSeqItr, position by position
-static void dump_group(int idx, mSeq* sd)
+static void dump_group(int idx, mSeq* sd, bool one_more = false)
 {
 	printf("group %d many %d len %d left %d right %d nelm %d felm %d vect %d prof %d dels %d nils %d sngl %d exgl %d exgr %d hetero %d sumwt ",
 	    idx, sd->many, sd->len, sd->left, sd->right, sd->nelm, sd->felm, (int) sd->inex.vect, (int) sd->inex.prof,
@@ -104,7 +104,9 @@ static void dump_group(int idx, mSeq* sd)
 	printf("weight %d", sd->weight? sd->many: 0);
 	if (sd->weight) for (int i = 0; i < sd->many; ++i) { putchar(' '); print_vt(sd->weight[i]); }
 	putchar('\n');
-	for (int p = sd->left - 1; p < sd->right; ++p) {
+	// rectangle mode (forwardA, fwd2c.h:231-356) also reads b's column at position `right`: dumped for groups without
+	// gap profile only (NGP: thickness is all the boundary reads; the list pointers there are not always valid)
+	for (int p = sd->left - 1; p < sd->right + (one_more && !sd->gfq? 1: 0); ++p) {
 	    mSeqItr	it(sd, p);
 	    printf("pos %d dns", p);
 	    if (it.dns) { putchar(' '); print_vt(it.dns->cfq); putchar(' '); print_vt(it.dns->dfq); putchar(' '); print_vt(it.dns->efq); }
@@ -189,8 +191,8 @@ int main(int argc, const char** argv)
 		for (int j = 0; j < sm->dim; ++j) { if (j) putchar(' '); print_vt(sm->mtx[i][j]); }
 		putchar('\n');
 	    }
-	    dump_group(0, sq[0]);
-	    dump_group(1, sq[1]);
+	    dump_group(0, sq[0], algmode.bnd == 0);
+	    dump_group(1, sq[1], algmode.bnd == 0);
 	    WINDOW	wdw;
 	    stripe((const Seq**) sq, &wdw, pwd->alnprm.sh);
 	    printf("window %d %d %d\n", wdw.lw, wdw.up, wdw.width);

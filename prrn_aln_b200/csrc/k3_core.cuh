@@ -68,7 +68,11 @@ struct K3Prm {
     int32_t novmf, origin_r;
     // register-list form (k3r_core.cuh): words per dynamic list (4, 6 or 8; capa / capb then describe the same
     // records), 0 = the list-walking form of this file
-    int32_t rl, pad2;
+    int32_t rl;
+    // rectangle (alnmode NGP_ALN: forwardA + initA, src/fwd2c.h:111-135,231-356; record mode 0 only): every cell of
+    // the window, no first-row / first-column skips, the boundary column without the long-gap switch; staged b holds
+    // one more column (position b.right)
+    int32_t rect;
 };
 
 // ---- record access -------------------------------------------------------------------------------
@@ -324,7 +328,7 @@ PG_HD void k3_part_vert(const K3Prm& p, const K3Group& a, const K3Group& b, int 
                         const int* habove, const int* gabove, const int* g2above, int* gout, int* g2out, const int* black)
 {
     if (!first_row) {       // vertical (fwd2c.h:401-409)
-        if (a.nils) *pua = k3_unp(a, ia, b, ib, p.u);
+        if (a.nils || p.rect) *pua = k3_unp(a, ia, b, ib, p.u);      // forwardA: per cell (:272)
         double gnp = k3_gapopen(p, a, b, gabove, ia, ib, 1);
         double gop = k3_gapopen(p, a, b, habove, ia, ib, 1);
         if (!k3_isvert(k3_dir(habove)) && (k3_val(habove) + gop > k3_val(gabove) + gnp))
@@ -333,7 +337,7 @@ PG_HD void k3_part_vert(const K3Prm& p, const K3Group& a, const K3Group& b, int 
         k3_setval(gout, k3_val(gout) + *pua);
         if (p.Noll == 3) {  // vertical2 (fwd2c.h:411-420)
             gnp = p.v2divv1 * k3_gapopen(p, a, b, g2above, ia, ib, 1);
-            gop = p.v2divv1 * gop;
+            gop = p.rect ? p.v2divv1 + gop : p.v2divv1 * gop;           // forwardA adds (:276)
             if (!k3_isvert(k3_dir(habove)) && (k3_val(habove) + gop > k3_val(g2above) + gnp))
                 k3_update(p, a, b, g2out, habove, ia, ib, gop, 1);
             else k3_update(p, a, b, g2out, g2above, ia, ib, gnp, 1);
@@ -405,7 +409,7 @@ PG_HD bool k3_cell_mono(const K3Prm& p, const K3Group& a, const K3Group& b, int 
     double gnp;
     const int* mx;
     if (!first_row) {       // vertical (fwd2c.h:401-409)
-        if (a.nils) *pua = k3_unp(a, ia, b, ib, p.u);
+        if (a.nils || p.rect) *pua = k3_unp(a, ia, b, ib, p.u);      // forwardA: per cell (:272)
         gnp = k3_gapopen(p, a, b, gabove, ia, ib, 1);
         gop = k3_gapopen(p, a, b, habove, ia, ib, 1);
         if (!k3_isvert(k3_dir(habove)) && (k3_val(habove) + gop > k3_val(gabove) + gnp))
@@ -415,7 +419,7 @@ PG_HD bool k3_cell_mono(const K3Prm& p, const K3Group& a, const K3Group& b, int 
         mx = gout;
         if (p.Noll == 3) {  // vertical2 (fwd2c.h:411-420)
             gnp = p.v2divv1 * k3_gapopen(p, a, b, g2above, ia, ib, 1);
-            gop = p.v2divv1 * gop;
+            gop = p.rect ? p.v2divv1 + gop : p.v2divv1 * gop;           // forwardA adds (:276)
             if (!k3_isvert(k3_dir(habove)) && (k3_val(habove) + gop > k3_val(g2above) + gnp))
                 k3_update(p, a, b, g2out, habove, ia, ib, gop, 1);
             else k3_update(p, a, b, g2out, g2above, ia, ib, gnp, 1);
@@ -502,15 +506,19 @@ PG_HD void k3_boundary_row(const K3Prm& p, const K3Group& a, const K3Group& b, i
     const int ia = 0, ib = k;           // b position left + k - 1  <->  staged index k
     const double pub = k3_unp(b, ib, a, ia, p.u);
     double gnp = k3_gapopen(p, a, b, src, ia, ib, -1);
-    gnp = (k < p.codonk1) ? gnp + pub : (p.v2divv1 * gnp + p.u2divu1 * pub);
+    // initB tests the column count after its increment (:156-160), initA before (:125-131)
+    gnp = (k - (p.rect ? 1 : 0) < p.codonk1) ? gnp + pub : (p.v2divv1 * gnp + p.u2divu1 * pub);
     k3_update(p, a, b, dst, src, ia, ib, gnp, -1);
 }
 // Column: bsi at b.left-1 (ib = 0), k-th row (1-based)
 PG_HD void k3_boundary_col(const K3Prm& p, const K3Group& a, const K3Group& b, int k, int* dst, const int* src)
 {
-    const int ia = k, ib = 0;
+    // forwardA computes the boundary cell of a row in place (:245-249): no long-gap switch, and bsi is where the
+    // previous row left it -- position 0 before the first row (`mSeqItr bsi(b, 0)`, :240; b.left = 0: staged index
+    // 1), position b.right afterwards (staged index L + 1)
+    const int ia = k, ib = p.rect ? (k == 1 ? 1 : b.L + 1) : 0;
     const double pua = k3_unp(a, ia, b, ib, p.u);
     double gnp = k3_gapopen(p, a, b, src, ia, ib, 1);
-    gnp = (k < p.codonk1) ? gnp + pua : (p.v2divv1 * gnp + p.u2divu1 * pua);
+    gnp = (p.rect || k < p.codonk1) ? gnp + pua : (p.v2divv1 * gnp + p.u2divu1 * pua);
     k3_update(p, a, b, dst, src, ia, ib, gnp, 1);
 }

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             vmf[0].m = 0; vmf[0].n = 0; vmf[0].p = 0;                       // skip 0-th record (:361)
             vmf[1].m = P_.al; vmf[1].n = P_.bl; vmf[1].p = 0;                 // origin
             sm_vmf[g] = 2;
-            k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(colH) = p.novmf ? p.origin_r : 1;
+            k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : (p.rect ? 0 : K3_DIAG), 0); K3_PTR(colH) = p.novmf ? p.origin_r : 1;
             const int rr = LQ < -p.lw ? LQ : -p.lw;
             for (int k = 1; k <= rr; ++k) {
                 if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false);
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             }
         }
         if (t == TG / 2 && role == (SPLIT ? 1 : 0) && crank == 0) {
-            k3_setval(rowH, 0); k3_setdg(rowH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(rowH) = p.novmf ? p.origin_r : 1;
+            k3_setval(rowH, 0); k3_setdg(rowH, p.mode == 3 ? K3_NEWD : (p.rect ? 0 : K3_DIAG), 0); K3_PTR(rowH) = p.novmf ? p.origin_r : 1;
             const int rr = LS < p.up ? LS : p.up;
             for (int k = 1; k <= rr; ++k) {
                 if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true);
@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                 TM_ADD(tm_wait);
                 if (active) {
                     const int ia = m + 1, ib = n + 1;
+                    const bool fr = m == 0 && !p.rect, fc = n == 0 && !p.rect;      // initA: no first-row / -column skips
                     if (n == 0 || r == p.lw) {                      // first in-band column of this row
                         if (!SPLIT || role == 1) pua = k3_unp(A, ia, B, ib, p.u);   // once per row (:377)
                         if (!SPLIT || role == 2) { RESET(f1); if (n3) RESET(f2); }
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                         const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
                         rec = p.mode == 3
                             ? k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, f1, f2, hout, gout, g2out)
-                            : k3_cell_mono(p, A, B, ia, ib, m == 0, n == 0, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
+                            : k3_cell_mono(p, A, B, ia, ib, fr, fc, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
                                            hout, gout, g2out, black);
                     } else if (p.mode == 3) {
                         if (role == 0) {
@@ -425,9 +426,9 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                         const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
                         k3_part_diag(p, A, B, ia, ib, dab, hdiag, hout);
                     } else if (role == 1) {
-                        k3_part_vert(p, A, B, ia, ib, m == 0, &pua, habove, gabove, g2above, gout, g2out, black);
+                        k3_part_vert(p, A, B, ia, ib, fr, &pua, habove, gabove, g2above, gout, g2out, black);
                     } else {
-                        k3_part_hori(p, A, B, ia, ib, n == 0, hleft, f1, f2);
+                        k3_part_hori(p, A, B, ia, ib, fc, hleft, f1, f2);
                     }
                 }
                 TM_ADD(tm_c1);
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                     __syncthreads();                                // the three candidates are in shared memory
                     TM_ADD(tm_b1);
                     if (active && role == 0 && p.mode != 3)
-                        rec = RL ? k3r_combine(p, m == 0, n == 0, hout, gout, g2out, f1, f2, st) : k3_combine(p, m == 0, n == 0, hout, gout, g2out, f1, f2);
+                        rec = RL ? k3r_combine(p, m == 0, n == 0, hout, gout, g2out, f1, f2, st) : k3_combine(p, m == 0 && !p.rect, n == 0 && !p.rect, hout, gout, g2out, f1, f2);
                     TM_ADD(tm_cmb);
                 }
                 if (active && role == 0) {

@@ -46,12 +46,14 @@ extern "C" int64_t pg_group_cells(const pg_group* a, const pg_group* b, int32_t 
 }
 
 namespace {
-struct SideOff { size_t cfq, efq, vec, glen, gfreq, sfq, tfq, rfq, gapmask, weight, blk; int cs; };
+struct SideOff { size_t cfq, efq, vec, glen, gfreq, sfq, tfq, rfq, gapmask, weight, blk; int cs, extra; };
 
 // cs > 0: also the fixed-stride column blocks of the register-list kernels (k3r_core.cuh), cs entries per list
-size_t place_side(const pg_group& g, int kdim, size_t off, SideOff* so, int cs)
+// extra: columns staged beyond right - 1 (1 for side b of a rectangle pair: forwardA reads position b.right)
+size_t place_side(const pg_group& g, int kdim, size_t off, SideOff* so, int cs, int extra = 0)
 {
-    const size_t npos = (size_t)(g.right - g.left + 1);
+    const size_t npos = (size_t)(g.right - g.left + 1 + extra);
+    so->extra = extra;
     const bool lists = g.sfq && g.tfq && g.rfq && g.glen && g.gfreq && g.npool > 0;
     so->cfq = off; off = up16(off + 8 * npos);
     so->efq = off; off = up16(off + 8 * npos);
@@ -71,7 +73,7 @@ size_t place_side(const pg_group& g, int kdim, size_t off, SideOff* so, int cs)
 
 void fill_side(const pg_group& g, int kdim, const SideOff& so, char* h)
 {
-    const size_t npos = (size_t)(g.right - g.left + 1);
+    const size_t npos = (size_t)(g.right - g.left + 1 + so.extra);
     const bool lists = g.sfq && g.tfq && g.rfq && g.glen && g.gfreq && g.npool > 0;
     memcpy(h + so.cfq, g.cfq, 8 * npos);
     memcpy(h + so.efq, g.efq, 8 * npos);
@@ -204,7 +206,9 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         const pg_group& B = b[i];
         const pg_gparams& P = prm[i];
         int mode;
+        bool rect = false;
         switch (P.alnmode) {
+        case 1: mode = 0; rect = true; break;   // NGP_ALN: forwardA over the whole rectangle
         case 6: mode = 0; break;
         case 7: case 8: mode = 1; break;
         case 9: mode = 2; break;
@@ -212,8 +216,16 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         case 100: mode = 3; break;      // PG_ALN_B1_NG: Aln2b1 (pg_align_pairs_ng), two single sequences
         default:
             free(offs);
-            return pg_int_fail(c, PG_ERR_UNSUPPORTED, "pg_align_groups: alnmode is not one of NGP_ALB / HLF_ALB / RHF_ALB / GPF_ALB "
-                                                      "(rectangle, naive, local and spliced modes are not built yet)");
+            return pg_int_fail(c, PG_ERR_UNSUPPORTED, "pg_align_groups: alnmode is not one of NGP_ALN / NGP_ALB / HLF_ALB / RHF_ALB / "
+                                                      "GPF_ALB / NTV_ALB (the rectangle modes with gap profiles, local and spliced "
+                                                      "modes are not built yet)");
+        }
+        if (rect && (score_only || B.left != 0)) {
+            free(offs);
+            return pg_int_fail(c, score_only ? PG_ERR_UNSUPPORTED : PG_ERR_ARG,
+                               score_only ? "pg_score_groups: the rectangle form of HomScoreC (forwardA with island reports) is not built"
+                                          : "pg_align_groups: NGP_ALN needs b.left = 0 (forwardA starts its b iterator at position 0, "
+                                            "src/fwd2c.h:240) and b's arrays one column longer (position b.right)");
         }
         if (A.left < 0 || A.right > A.len || A.left >= A.right || B.left < 0 || B.right > B.len || B.left >= B.right ||
             !A.cfq || !A.efq || !A.vec || !B.cfq || !B.efq || !B.vec || P.kdim < 1 || P.kdim > 64 || P.Noll < 2 || P.Noll > 3) {
@@ -227,13 +239,14 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         }
         const int rl = rl_cap[mode];
         blob = place_side(A, P.kdim, blob, &soa[i], rl ? rl - 2 : 0);
-        blob = place_side(B, P.kdim, blob, &sob[i], rl ? rl - 2 : 0);
+        blob = place_side(B, P.kdim, blob, &sob[i], rl ? rl - 2 : 0, rect ? 1 : 0);
         K3Prm& kp = pairs[i].prm;
         kp.mode = mode; kp.Noll = P.Noll; kp.codonk1 = P.codonk1; kp.kdim = P.kdim;
         int lw, up;
         group_band(&A, &B, P.sh, &lw, &up);
         const int r0 = B.left - A.left;
         kp.lw = lw - r0; kp.up = up - r0;
+        if (rect) { kp.lw = -(A.right - A.left); kp.up = B.right - B.left; }
         kp.capa = std::max(A.hetero, 0) + 3; kp.capb = std::max(B.hetero, 0) + 3;
         if (mode == 4) {
             if (!A.gapmask || !B.gapmask || A.many < 1 || B.many < 1 || A.many > 32 || B.many > 32 || A.nils || B.nils) {
@@ -244,7 +257,7 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
             }
             kp.capa = (A.many + 1) / 2 + 1; kp.capb = (B.many + 1) / 2 + 1;     // 16-bit run lengths, two per word
         }
-        kp.rl = rl; kp.pad2 = 0;
+        kp.rl = rl; kp.rect = rect ? 1 : 0;
         if (rl) {               // the records of the register-list form: 4 header words + rl words per list, a multiple of 4
             kp.capa = rl;
             kp.capb = mode == 2 ? rl : k3r_rec_words(rl, 1) - 4 - rl;
@@ -274,7 +287,7 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
             free(offs);
             return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: groups longer than 65,000 columns exceed the 16-bit gap-state lists");
         }
-        cells[i] = pg_group_cells(&A, &B, P.sh);
+        cells[i] = rect ? (int64_t)(A.right - A.left) * (B.right - B.left) : pg_group_cells(&A, &B, P.sh);
         max_cells = std::max(max_cells, cells[i]);
         pairs[i].al = A.left; pairs[i].bl = B.left;
         pairs[i].simmat = nullptr;

@@ -17,8 +17,9 @@ import numpy as np
 DECOMPACT = (0, 1, 2, 3, 5, 9)      # nil, gap, A, C, G, T (src/mseq.h:38) for sim33_n
 
 # ALN_MODE (src/aln.h:71-76)
+NGP_ALN = 1                         # the rectangle form (forwardA) of NGP_ALB; b's arrays hold one more column
 NGP_ALB, HLF_ALB, RHF_ALB, GPF_ALB, NTV_ALB = 6, 7, 8, 9, 10
-K3_MODE = {NGP_ALB: 0, HLF_ALB: 1, RHF_ALB: 1, GPF_ALB: 2, NTV_ALB: 4}
+K3_MODE = {NGP_ALN: 0, NGP_ALB: 0, HLF_ALB: 1, RHF_ALB: 1, GPF_ALB: 2, NTV_ALB: 4}
 
 
 def _onehot(g, dim):

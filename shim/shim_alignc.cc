@@ -22,7 +22,8 @@
 // 2,000) covers worker pools whose idle members block elsewhere (CalcServer).  PRRN_GPU_BATCH=0 turns it off.
 // Results do not depend on how calls were grouped: every alignment of a batch is computed independently.
 //
-// Calls the CUDA path does not take (rectangle -A, caller-supplied window, Smith-Waterman, naive groups with nil
+// The rectangle form (algmode.bnd = 0) is taken for NGP_ALN: alignC<DPunit>(seqs, pwd, scr, true), forwardA + initA.
+// Calls the CUDA path does not take (rectangle with gap profiles, caller-supplied window, Smith-Waterman, naive groups with nil
 // ends or more than 32 members) are fatal() unless PRRN_GPU_ALLOW_REF=1 (shim_ctx.h); then they run the reference's
 // own Fwd2c -- the reference's code, not a port; nothing here re-implements the DP on the CPU.
 #ifndef _GNU_SOURCE
@@ -35,6 +36,8 @@
 #include "gfreq.h"
 #include "vmf.h"
 #include "fwd2c.h"
+#include "fwd2h.h"
+#include "fwd2s.h"
 #include "prrn_gpu.h"
 #include "shim_ctx.h"
 
@@ -83,9 +86,10 @@ struct PgSide {
 static const int pg_decompact[6] = {nil_code, gap_code, A, C, G, T};	// src/mseq.h:38
 
 // one vector per column such that sim2(m, n) = vec_a[m] . vec_b[n]	(src/maln2.cc:534-623, 1230-1296)
-static void pg_stage(mSeq* sd, PgSide& S, const PwdM* pwd, bool is_a, const Simmtx* sm)
+// extra: columns staged beyond right - 1 (the rectangle form reads b at position right, src/fwd2c.h:240-249)
+static void pg_stage(mSeq* sd, PgSide& S, const PwdM* pwd, bool is_a, const Simmtx* sm, int extra = 0)
 {
-	const int	npos = sd->right - sd->left + 1, K = sm->dim;
+	const int	npos = sd->right - sd->left + 1 + extra, K = sm->dim;
 	const int	my_mode = is_a? pwd->a_mode: pwd->b_mode;
 	const int	ot_mode = is_a? pwd->b_mode: pwd->a_mode;
 	const bool	dxd = pwd->DvsP == 0;
@@ -279,11 +283,17 @@ extern "C" int pthread_create(pthread_t* th, const pthread_attr_t* attr, void* (
 }
 
 // ---- what the library takes ---------------------------------------------------------------------------------------
-static const char* pg_untaken(mSeq* seqs[], PwdM* pwd, bool rectangle, WINDOW* pwdw)
+static const char* pg_untaken(mSeq* seqs[], PwdM* pwd, bool rectangle, WINDOW* pwdw, bool score_only = false)
 {
-	if (rectangle) return "rectangle (-A, forwardA)";
 	if (pwdw) return "caller-supplied window";
 	if (algmode.lcl & 16) return "Smith-Waterman local mode (forwardC)";
+	if (rectangle) {		// forwardA + initA: taken for the groups without gap profile (NGP_ALN)
+	    if (score_only) return "rectangle (forwardA) without path, with its island reports";
+	    if (pwd->alnmode != NGP_ALN) return "rectangle (forwardA) with gap profiles or naive groups";
+	    if (seqs[0]->inex.exgr || seqs[1]->inex.exgr) return "rectangle (forwardA) with free right ends (store_ild)";
+	    if (seqs[1]->left != 0) return "rectangle (forwardA) on a sub-window of b";
+	    return 0;
+	}
 	switch (pwd->alnmode) {
 	    case NGP_ALB: case HLF_ALB: case RHF_ALB: case GPF_ALB: return 0;
 	    case NTV_ALB:
@@ -372,7 +382,7 @@ static void pg_stage_job(mSeq* seqs[], PwdM* pwd, PgJob* job, bool score_only)
 {
 	const double	t0 = pg_stats.on? pg_now(): 0;
 	pg_stage(seqs[0], job->A, pwd, true, pwd->simmtx);
-	pg_stage(seqs[1], job->B, pwd, false, pwd->simmtx);
+	pg_stage(seqs[1], job->B, pwd, false, pwd->simmtx, pwd->alnmode == NGP_ALN? 1: 0);
 	job->ga = pg_view(seqs[0], job->A); job->gb = pg_view(seqs[1], job->B);
 	pg_fill_gparams(pwd, &job->gp);
 	job->score_only = score_only;
@@ -402,8 +412,9 @@ static SKL* pg_check(mSeq* seqs[], PwdM* pwd, VTYPE* scr, SKL* skl, const char* 
 		seqs[0]->gfq? seqs[0]->gfq->hetero: -1, seqs[1]->gfq? seqs[1]->gfq->hetero: -1, (int) seqs[0]->inex.nils, (int) seqs[1]->inex.nils,
 		pwd->alnprm.sh, (double) *scr, skl? skl->n: -1);
 	if (!pg_verify) return skl;
-	Fwd2c<recd_t>	pwa(seqs, pwd, true, false, 0);
-	VTYPE	rs = pwa.forwardB(0);
+	const bool	rect = pwd->alnmode == NGP_ALN;
+	Fwd2c<recd_t>	pwa(seqs, pwd, true, rect, 0);
+	VTYPE	rs = rect? pwa.forwardA(0): pwa.forwardB(0);
 	SKL*	rk = pwa.traceback();
 	bool	same = fabs((double) rs - (double) *scr) <= 1e-5 * (fabs((double) rs) > 1? fabs((double) rs): 1.) && rk && skl && rk->n == skl->n;
 	int	first = -1;
@@ -449,7 +460,7 @@ static SKL* pg_alignC(mSeq* seqs[], PwdM* pwd, VTYPE* scr, bool rectangle, WINDO
 template <class recd_t>
 static VTYPE pg_HomScoreC(mSeq* seqs[], PwdM* pwd, long rr[], bool rectangle, WINDOW* pwdw)
 {
-	if (const char* why = pg_untaken(seqs, pwd, rectangle, pwdw)) {
+	if (const char* why = pg_untaken(seqs, pwd, rectangle, pwdw, true)) {
 	    pg_refused("HomScoreC", why);
 	    const double	t0 = pg_stats.on? pg_now(): 0;
 	    Fwd2c<recd_t>	pwa(seqs, pwd, false, rectangle, pwdw);
@@ -481,3 +492,38 @@ template <> VTYPE HomScoreC<DPunit_pf>(mSeq* seqs[], PwdM* pwd, long rr[], bool 
 	{return pg_HomScoreC<DPunit_pf>(seqs, pwd, rr, rectangle, pwdw);}
 template <> VTYPE HomScoreC<DPunit_nv>(mSeq* seqs[], PwdM* pwd, long rr[], bool rectangle, WINDOW* pwdw)
 	{return pg_HomScoreC<DPunit_nv>(seqs, pwd, rr, rectangle, pwdw);}
+
+// HomScore (src/maln2.cc:1837-1872).  align2 reaches alignC<recd_t> through the out-of-line instantiations above,
+// but the compiler folds HomScoreC<recd_t> into HomScore inside maln2.o, so there is no call left to interpose:
+// the shim therefore carries HomScore's own dispatch (the same switch), and the link takes this definition.
+VTYPE HomScore(mSeq* seqs[], PwdM* pwdm, long rr[])
+{
+	mSeq*&	a = seqs[0];
+	mSeq*&	b = seqs[1];
+	if (a->left == a->right || b->left == b->right) {
+	    if (rr) {rr[0] = b->left - a->left; rr[1] = b->right - a->right;}
+	    return (0);
+	}
+	switch (pwdm->alnmode) {
+	    case NGP_ALB: return HomScoreC<DPunit>(seqs, pwdm, rr, false, 0);
+	    case HLF_ALB:
+	    case RHF_ALB: return HomScoreC<DPunit_hf>(seqs, pwdm, rr, false, 0);
+	    case GPF_ALB: return HomScoreC<DPunit_pf>(seqs, pwdm, rr, false, 0);
+	    case NTV_ALB: return HomScoreC<DPunit_nv>(seqs, pwdm, rr, false, 0);
+	    case NGP_ALN: return HomScoreC<DPunit>(seqs, pwdm, rr, true, 0);
+	    case NTV_ALN: return HomScoreC<DPunit_nv>(seqs, pwdm, rr, true, 0);
+	    case HLF_ALN:
+	    case RHF_ALN: return HomScoreC<DPunit_hf>(seqs, pwdm, rr, true, 0);
+	    case GPF_ALN: return HomScoreC<DPunit_pf>(seqs, pwdm, rr, true, 0);
+	    // spliced modes (fwd2h.h / fwd2s.h): SURVEY section 8 keeps them out of scope -- the reference's own templates
+	    case NGP_ALH: pg_refused("HomScore", "spliced mode (HomScoreH)"); return HomScoreH<RVPDJ_nv>(seqs, pwdm);
+	    case HLF_ALH:
+	    case RHF_ALH: pg_refused("HomScore", "spliced mode (HomScoreH)"); return HomScoreH<RVPDJ_hf>(seqs, pwdm);
+	    case NGP_ALS: pg_refused("HomScore", "spliced mode (HomScoreS)"); return HomScoreS<RVPDJ_nv>(seqs, pwdm);
+	    case HLF_ALS:
+	    case RHF_ALS: pg_refused("HomScore", "spliced mode (HomScoreH)"); return HomScoreH<RVPDJ_hf>(seqs, pwdm);
+	    default:
+		fatal("Mode %d is not supported !\n", pwdm->alnmode);
+	}
+	return (0);
+}

@@ -56,7 +56,7 @@ static int emul(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int Tsig
     vmf.push_back({0, 0, 0});                       // skip 0-th record (fwd2c.h:361)
     vmf.push_back({al, bl, 0});                     // origin (initB)
     // origin + boundary chains
-    k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : K3_DIAG, 0); K3_PTR(colH) = 1;
+    k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : (p.rect ? 0 : K3_DIAG), 0); K3_PTR(colH) = 1;
     RCOPY(rowH, colH);
     { int rr = LS < p.up ? LS : p.up; for (int k = 1; k <= rr; ++k) {
         if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true);
@@ -92,7 +92,7 @@ static int emul(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int Tsig
                 RESET(F1 + (size_t)t * st);
                 RESET(F2 + (size_t)t * st);
             }
-            const bool first_row = m == 0, first_col = n == 0;
+            const bool first_row = m == 0 && !p.rect, first_col = n == 0 && !p.rect;
             const int* hdiag = n == 0 ? colH + (size_t)m * st
                              : (t == 0 ? rowH + (size_t)n * st : pubH + ((size_t)((S + 1) % 3) * T + (t - 1)) * st);
             const bool above_in = r + 1 <= p.up;

@@ -51,6 +51,8 @@ def test_group_goldens(ctx, name, inline_sim, monkeypatch):
     assert pts[0].tolist() == want["skl"]
     lw, up, _ = g["window"]
     a, b = g["groups"]
+    if g["pwdm"]["alnmode"] == G.NGP_ALN:       # the rectangle form (forwardA): no band
+        return
     cells = sum(max(0, min(m + up + 1, b["right"]) - max(m + lw, b["left"])) for m in range(a["left"], a["right"]))
     assert P.group_cells(A, B, gp.sh) == cells
 
@@ -59,7 +61,7 @@ def test_homscore_goldens_in_one_call(ctx, oracle):
     """pg_score_groups = HomScoreC<recd_t>(seqs, pwd, rr) (src/fwd2c.h:663-668): the fill without the path store.
     Score and rr[2] against the reference's own HomScore for every golden pair (one batch), and against the oracle
     on other band shoulders."""
-    gs = [golden(n) for n in golden_names("galign_")]
+    gs = [golden(n) for n in golden_names("galign_") if "_rect_" not in n]
     scores, rr = ctx.score_groups([stage_golden(g) for g in gs])
     for k, g in enumerate(gs):
         want = g["homscore"]
@@ -111,9 +113,14 @@ def test_matches_oracle_on_other_bands(ctx, oracle):
 def test_bad_arguments_fail_loudly(ctx):
     g = golden("galign_gpf_raw3x3")
     A, B, gp = stage_golden(g)
-    gp.alnmode = 4          # GPF_ALN (rectangle): not built
+    gp.alnmode = 4          # GPF_ALN (rectangle with gap profiles): not built
     with pytest.raises(P.PgError) as e:
         ctx.align_groups([(A, B, gp)])
+    assert e.value.code == 4
+    # the rectangle form of HomScoreC (forwardA with island reports) is refused, not approximated by the banded one
+    g = golden("galign_rect_single_p01")
+    with pytest.raises(P.PgError) as e:
+        ctx.score_groups([stage_golden(g)])
     assert e.value.code == 4
 
 
@@ -168,6 +175,57 @@ def test_tiny_windows_match_oracle(ctx, oracle):
             s1, p1 = ctx.align_groups([(A, B, gp)])
             assert abs(s1[0] - want_s) <= REL_TOL * max(1.0, abs(want_s)), (la, lb)
             assert [tuple(x) for x in p1[0].tolist()] == want_p, (la, lb)
+
+
+def test_rectangle_form_matches_oracle_beyond_one_stripe(ctx, oracle, monkeypatch):
+    """NGP_ALN (forwardA + initA, src/fwd2c.h:111-135,231-356): the rect goldens cover ~100-column inputs; here their
+    columns are repeated 3..9 times so that the rows span several 256-row stripes / a thread-block cluster, alone and
+    in one batch with banded pairs, against the oracle (itself pinned on the rect goldens)."""
+    def tile(d, k):
+        t = dict(d)
+        n = d["right"] - d["left"]
+        for key in ("pos", "cfq", "dfq", "efq", "res", "vss", "sfq", "tfq", "rfq"):
+            v = d[key]
+            t[key] = v[:1] + v[1:n + 1] * k + v[n + 1:]
+        t["right"] = d["left"] + n * k
+        t["len"] = d["len"] + n * (k - 1)
+        return t
+    cases = []
+    for name, ka, kb in (("galign_rect_single_rag62", 3, 4), ("galign_rect_single_p24_twopiece", 9, 5),
+                         ("galign_rect_ngp_gapless4x3_twopiece", 7, 7), ("galign_rect_ngp_gapless3x4_wt_f32", 4, 8)):
+        g = golden(name)
+        ga, gb = tile(g["groups"][0], ka), tile(g["groups"][1], kb)
+        want_s, want_p, cells = oracle.align_groups(oracle.group_arrays(ga), oracle.group_arrays(gb), np.array(g["matrix"]),
+                                                    oracle.gparams_from_dump(g))
+        assert cells == (ga["right"] - ga["left"]) * (gb["right"] - gb["left"])
+        pm, pc, h = g["pwdm"], g["pwdc"], g["header"]
+        A, B = G.stage_pair(ga, gb, pm["a_mode"], pm["b_mode"], g["matrix"])
+        gp = P.gparams_from_pwd(pm["alnmode"], pm["Noll"], pm["codonk1"], int(h["sh"]), A["vec"].shape[1], float(h["u"]),
+                                float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
+        cases.append(((A, B, gp), want_s, want_p))
+    assert max(c[0][0]["right"] for c in cases) > 600
+    banded = [golden(n) for n in ("galign_gpf_twopiece", "galign_ngp_gapless4x3")]
+    for cap in (None, "1"):
+        if cap is None:
+            monkeypatch.delenv("PG_K3_CLUSTER", raising=False)
+        else:
+            monkeypatch.setenv("PG_K3_CLUSTER", cap)
+        for batch in ([c[0] for c in cases] + [stage_golden(g) for g in banded], [cases[1][0]]):
+            scores, pts = ctx.align_groups(batch)
+            for k, c in enumerate(cases if len(batch) > 1 else [cases[1]]):
+                assert abs(scores[k] - c[1]) <= REL_TOL * max(1.0, abs(c[1])), (cap, k)
+                assert [tuple(x) for x in pts[k].tolist()] == c[2], (cap, k)
+            for k, g in enumerate(banded if len(batch) > 1 else []):
+                w = g["alignc"]
+                assert abs(scores[len(cases) + k] - w["score"]) <= REL_TOL * max(1.0, abs(w["score"]))
+                assert pts[len(cases) + k].tolist() == w["skl"]
+    # b must be staged from position 0 (forwardA's iterator starts there)
+    A, B, gp = cases[0][0]
+    B2 = dict(B)
+    B2["left"] = 1
+    with pytest.raises(P.PgError) as e:
+        ctx.align_groups([(A, B2, gp)])
+    assert e.value.code == 3
 
 
 def test_cluster_latency_kernel_matches_reference(ctx, monkeypatch):

@@ -120,11 +120,15 @@ def test_reference_group_align2_on_gpu_library(name, tmp_path):
         gen_msa.write_native(fb, rows_b, "B")
     else:
         pytest.skip("sample files live under /root/reference only")
-    env = dict(os.environ, ALN_TAB=os.path.join(refio.REFDIR, "table"))
+    env = dict(os.environ, ALN_TAB=os.path.join(refio.REFDIR, "table"), PRRN_GPU_STATS="1")
+    env.pop("PRRN_GPU_ALLOW_REF", None)
     import subprocess
     out = subprocess.run([refio.driver(flavour, gpu=True), "galign", fa, "fb=" + fb] + ["%s=%s" % kvp for kvp in kv.items()],
                          env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-500:]
+    # the driver's alignC, HomScore and align2 calls all ran in the library (HomScore through the shim's own dispatch:
+    # maln2.o folds HomScoreC into HomScore), none on the reference's Fwd2c
+    assert "3 calls on the GPU (1 of them score-only" in out.stderr and "0 calls left on the reference" in out.stderr, out.stderr[-600:]
     d = refio.parse_galign(out.stdout)
     for key in ("alignc", "align2"):
         assert abs(d[key]["score"] - g[key]["score"]) <= 1e-5 * max(1.0, abs(g[key]["score"])), key
@@ -143,6 +147,7 @@ def _galign_inputs(name, tmp_path):
     MG.galign_case = lambda nm, a, b, flavour="d", files=None, **kv: captured.__setitem__(nm, (a, b, flavour, files, kv))
     try:
         MG.galign_cases()
+        MG.galign_rect_cases()
     finally:
         MG.galign_case = real
     rows_a, rows_b, flavour, files, kv = captured[name]
@@ -150,6 +155,35 @@ def _galign_inputs(name, tmp_path):
     gen_msa.write_native(fa, rows_a, "A")
     gen_msa.write_native(fb, rows_b, "B")
     return fa, fb, flavour, kv
+
+
+RECT_CASES = ["galign_rect_ngp_gapless4x3", "galign_rect_ngp_gapless4x3_twopiece", "galign_rect_ngp_gapless3x4_wt_f32",
+              "galign_rect_single_p01", "galign_rect_single_p24_twopiece", "galign_rect_single_rag03_twopiece_u1",
+              "galign_rect_single_rag62"]
+
+
+@pytest.mark.parametrize("name", RECT_CASES)
+def test_reference_rectangle_alignC_on_gpu_library(name, tmp_path):
+    """algmode.bnd = 0 on groups without gap profile: align2 calls alignC<DPunit>(seqs, pwd, scr, true) (src/maln2.cc:
+    1906), i.e. forwardA + initA; the shim stages b one column further and K3 runs its rectangle form.  The driver's
+    HomScore call (the rectangle form of HomScoreC, not built) is announced and left on the reference's code."""
+    import subprocess
+    g = golden(name)
+    fa, fb, flavour, kv = _galign_inputs(name, tmp_path)
+    drv = refio.driver(flavour, gpu=True)
+    if not os.path.exists(drv):
+        pytest.skip("oracle/_ref/ref_driver_%s_gpu is not built" % flavour)
+    env = dict(os.environ, ALN_TAB=os.path.join(refio.REFDIR, "table"), PRRN_GPU_ALLOW_REF="1", PRRN_GPU_STATS="1")
+    out = subprocess.run([drv, "galign", fa, "fb=" + fb] + ["%s=%s" % kvp for kvp in kv.items()],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    left = [ln for ln in out.stderr.splitlines() if "left on the reference's own code" in ln]
+    assert left and all("HomScoreC" in ln for ln in left), out.stderr[-800:]
+    d = refio.parse_galign(out.stdout)
+    assert d["pwdm"]["alnmode"] == 1
+    for key in ("alignc", "align2"):
+        assert abs(d[key]["score"] - g[key]["score"]) <= 1e-5 * max(1.0, abs(g[key]["score"])), key
+        assert d[key]["skl"] == g[key]["skl"], key
 
 
 def test_concurrent_workers_become_one_batch(tmp_path):

@@ -26,7 +26,7 @@ class K3Prm(C.Structure):
                 ("bgop", C.c_double), ("u2divu1", C.c_double), ("v2divv1", C.c_double), ("gop1", C.c_double),
                 ("gep1", C.c_double), ("gop2", C.c_double), ("gep2", C.c_double), ("ltg_a", C.c_double), ("ltg_b", C.c_double),
                 ("rtg_a", C.c_double), ("rtg_b", C.c_double), ("last_c", C.c_int32), ("last_r", C.c_int32),
-                ("novmf", C.c_int32), ("origin_r", C.c_int32), ("rl", C.c_int32), ("pad2", C.c_int32)]
+                ("novmf", C.c_int32), ("origin_r", C.c_int32), ("rl", C.c_int32), ("rect", C.c_int32)]
 
 
 @pytest.fixture(scope="module")
@@ -65,6 +65,9 @@ def test_wavefront_emulation_matches_reference(emul3, name):
     p = K3Prm(mode, pm["Noll"], pm["codonk1"], lw - r0, up - r0, capa, capb,
               A["vec"].shape[1], float(np.float32(float(h["u"]))), -float(np.float32(float(h["v"]))), pc["vgop1"],
               lgep / bgep if bgep < 0 else 0.0, lgop / bgop if bgop < 0 else 0.0, bgop, bgep, lgop, lgep, 1.0, 1.0)
+    if pm["alnmode"] == G.NGP_ALN:      # forwardA: the whole rectangle; b staged one column further (position right)
+        p.rect, p.lw, p.up = 1, -(A["right"] - A["left"]), B["right"] - B["left"]
+        assert len(B["cfq"]) >= B["right"] - B["left"] + 2 and B["left"] == 0
     want = d["alignc"]
     for T in (256, 7, 33, -33, -5):     # rows per stripe: one stripe, many, ragged last; negative: reversed thread order
         out = np.zeros(2 * (A["len"] + B["len"] + 8), np.int32)

@@ -169,6 +169,23 @@ def galign_cases():
     galign_case("galign_dna_gpf_twopiece", A, B, molc="n", ls=3, wt=1)
 
 
+def galign_rect_cases():
+    """alignC over the whole rectangle (algmode.bnd = 0 -> alnmode NGP_ALN, forwardA + initA) for the groups that
+    have no gap profile: gapless groups with thickness and single sequences."""
+    import gen_msa
+    gl = gen_msa.synth_msa(7, 80, 0.2, 0.6, 43, gapless=True)
+    galign_case("galign_rect_ngp_gapless4x3", gl[:4], gl[4:], mtx="blosum62", bnd=0)
+    galign_case("galign_rect_ngp_gapless4x3_twopiece", gl[:4], gl[4:], mtx="blosum62", ls=3, bnd=0)
+    galign_case("galign_rect_ngp_gapless3x4_wt_f32", gl[4:], gl[:4], flavour="f", wt=1, bnd=0)
+    p = gen_synth.synth_set(10, 120, 0.1, 0.7, 11)
+    rag = [s[a:len(s) - b] for s, a, b in zip(gen_synth.synth_set(10, 160, 0.1, 0.6, 41),
+                                             [0, 30, 0, 45, 10, 0, 60, 5, 0, 25], [0, 0, 40, 20, 0, 55, 0, 35, 15, 0])]
+    galign_case("galign_rect_single_p01", [p[0]], [p[1]], flavour="f", mtx="blosum62", bnd=0)     # path opens on the diagonal
+    galign_case("galign_rect_single_p24_twopiece", [p[2]], [p[4]], ls=3, bnd=0)                   # path opens with a gap
+    galign_case("galign_rect_single_rag03_twopiece_u1", [rag[0]], [rag[3]], mtx="blosum62", ls=3, u1=1, bnd=0)
+    galign_case("galign_rect_single_rag62", [rag[6]], [rag[2]], mtx="blosum62", bnd=0)            # 100 x 120, far off the main diagonal
+
+
 def alignb_case(name, seqs, flavour="f", **kv):
     """Aln2b1: alignB_ng (stdskl-normalised corner list) + HomScoreB_ng per pair."""
     os.makedirs(TMP, exist_ok=True)
@@ -254,6 +271,7 @@ def main():
     align_case("align_long1300", long_[:4])
     align_case("align_c1_ce13a", sample_pair(), sh=-50)
     galign_cases()
+    galign_rect_cases()
     alignb_cases()
     dna_pair_cases()
 
@@ -267,6 +285,9 @@ if __name__ == "__main__":
         dna_pair_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == "galign":
         galign_cases()
+        galign_rect_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "rect":
+        galign_rect_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == "lcl":      # only the lcl cases
         p24_ = gen_synth.synth_set(24, 120, 0.1, 0.6, 11)
         rag_ = [s[:k] for s, k in zip(gen_synth.synth_set(20, 300, 0.1, 0.7, 21),
