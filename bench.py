@@ -177,6 +177,32 @@ def cpu_reference_run(seqs, threads, reps=1):
     return cells / dt / 1e9, "port", 1, dt, cells
 
 
+def default_scoring_measurement(P, ctx, enc):
+    """C2 again with the reference's DEFAULT scoring (PAM250 log-odds, non-integral, u=2 v=9): the exact-integer DPX
+    kernels do not apply, the fill runs the IEEE float / double kernel K1F, bit-identical to the reference's VTYPE
+    arithmetic.  Host-buffer calls (end to end), best of 3 after a warm-up."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "score_p24_pam_f64.json")) as f:
+            M = np.array(json.load(f)["matrix"])
+        ss = P.SeqSet(enc)
+        out = {"metric": "DP GCUPS (calcdist, band cells), end to end", "unit": "GCUPS",
+               "config": {"workload": "C2 with the reference's default PAM250 matrix (non-integral): kernel K1F"}}
+        for label, vt in (("float", 0), ("double", 1)):
+            prm = P.Params(P.ALPRM(sh=-60), vtype=vt)
+            cells = P.calcdist_cells(ss, prm)
+            ctx.calcdist(ss, prm, M)
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                d = ctx.calcdist(ss, prm, M)
+                dt = time.perf_counter() - t0
+                best = dt if best is None or dt < best else best
+            out[label] = {"value": cells / best / 1e9, "call_ms": best * 1e3, "checksum": float(np.sum(d, dtype=np.float64))}
+        return out
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
 def group_side_measurement():
     """The other half of BASELINE.json's metric: group-to-group DP (kernel K3 + K4) on partitions of a
     200 x ~500 aa family (config 3 shape), with the reference's alignC timed beside it on one host core.
@@ -436,6 +462,7 @@ def main():
                                             ClockSampler(local) if rank == 0 else None)
     gcups = c2.cells_total * args.steps / (ms_total * 1e-3) / 1e9
     ss, npair, M, prm = c2.ss, c2.npair, c2.M, c2.prm
+    c2_enc = c2.enc
     k0, k1 = c2.mine[0]
 
     # ---- end to end through the host-buffer C-ABI call: H2D (sequences, matrix) + D2H (distances)
@@ -530,6 +557,8 @@ def main():
         out["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": cores, "kind": kind,
                                "sample": "first %d of the 1000 sequences: %d pairs, %.3g cells, %.2f s" % (
                                    CPU_SAMPLE_N, CPU_SAMPLE_N * (CPU_SAMPLE_N - 1) // 2, cells, dtc)}
+    if rank == 0 and world == 1 and not args.no_groups:
+        out["default_scoring"] = default_scoring_measurement(P, ctx, c2_enc)
     ctx.close()
     if world > 1 and not args.no_groups:
         gc = group_candidates_measurement(P, torch, dist, rank, world, local)

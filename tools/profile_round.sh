@@ -16,7 +16,10 @@ ncu --set full --clock-control none --import-source on -k "regex:k4_contract|k3_
 python tools/ncu_summary.py $O/${R}_k3.ncu-rep $O/${R}_k4_k3_ncu_full_summary.csv
 ncu --set full --clock-control none --import-source on -k regex:k2_fill_long -c 1 -o $O/${R}_k2long python tools/run_configs.py c5b > /dev/null 2>&1
 python tools/ncu_summary.py $O/${R}_k2long.ncu-rep $O/${R}_k2_long_ncu_full_summary.csv
+python tools/bench_k1f.py > $O/${R}_k1f_bench_c2_pam.jsonl 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k1f_score_kernel<float" -c 1 -o $O/${R}_k1f python tools/bench_k1f.py 300 > /dev/null 2>&1
+python tools/ncu_summary.py $O/${R}_k1f.ncu-rep $O/${R}_k1f_ncu_full_summary.csv
 python tools/run_configs.py c5a c5b c4 > $O/${R}_configs_c4_c5a_c5b.jsonl 2>&1
 python tools/run_prrn.py --arm both small mid c3t4 c4n20 c4n50 c4n60 > $O/${R}_prrn_end_to_end.jsonl 2>&1
 python tools/run_prrn.py --arm gpu c4n100 >> $O/${R}_prrn_end_to_end.jsonl 2>&1
-rm -f $O/${R}_k1p.ncu-rep $O/${R}_k3.ncu-rep $O/${R}_k2long.ncu-rep
+rm -f $O/${R}_k1f.ncu-rep $O/${R}_k1p.ncu-rep $O/${R}_k3.ncu-rep $O/${R}_k2long.ncu-rep
