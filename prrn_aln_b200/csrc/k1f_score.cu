@@ -50,6 +50,27 @@ __device__ __forceinline__ double2 pack16(const double* v) { return make_double2
 __device__ __forceinline__ void unpack16(float* v, float4 x) { v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; }
 __device__ __forceinline__ void unpack16(double* v, double2 x) { v[0] = x.x; v[1] = x.y; }
 
+// The compiler re-derives loop invariants (penalties converted from the argument block, the step count) inside the
+// step loop instead of keeping them in registers; an empty asm with the value as in/out operand makes it a plain
+// register value it cannot rematerialise.
+__device__ __forceinline__ void pin(float& v) { asm volatile("" : "+f"(v)); }
+__device__ __forceinline__ void pin(double& v) { asm volatile("" : "+d"(v)); }
+__device__ __forceinline__ void pin(int& v) { asm volatile("" : "+r"(v)); }
+
+// E[k] = neg for a run-time k in [0, R): a jump table with one move per case (the lanes that cut the band at a step
+// are one or two of 32; the alternative -- the whole array through shared memory -- cost 8 LDS/STS.128 + addressing)
+template <typename T, int R>
+__device__ __forceinline__ void poke(T (&E)[R], int k, T neg)
+{
+    switch (k) {
+#define K1F_POKE(i) case i: if (i < R) E[i < R ? i : 0] = neg; break;
+    K1F_POKE(0) K1F_POKE(1) K1F_POKE(2) K1F_POKE(3) K1F_POKE(4) K1F_POKE(5) K1F_POKE(6) K1F_POKE(7)
+    K1F_POKE(8) K1F_POKE(9) K1F_POKE(10) K1F_POKE(11) K1F_POKE(12) K1F_POKE(13) K1F_POKE(14) K1F_POKE(15)
+#undef K1F_POKE
+    default: break;
+    }
+}
+
 template <typename T> __device__ __forceinline__ T shfl_up(T v) { return __shfl_up_sync(FULL, v, 1); }
 template <typename T> __device__ __forceinline__ T shfl_idx(T v, int src) { return __shfl_sync(FULL, v, src); }
 
@@ -101,7 +122,8 @@ __global__ void __launch_bounds__(NW * 32, Cfg<T, MODE>::BPS) k1f_score_kernel(c
     const int gwarp = blockIdx.x * NW + warp;
     const T* const mtx = reinterpret_cast<const T*>(a.mtx);
     const T* const bnd = reinterpret_cast<const T*>(a.bnd);
-    const T uu = (T)a.uu, vv = (T)a.vv;
+    T uu = (T)a.uu, vv = (T)a.vv;
+    if (sizeof(T) == 4) { pin(uu); pin(vv); }       // double: the argument block already holds them as DADD operands
     const T NEG = k1f_neg<T>();
     // per-warp scratch (multi-pass rows, lastD lines)
     unsigned char* const scratch = a.scratch ? reinterpret_cast<unsigned char*>(a.scratch) + (size_t)gwarp * a.scratch_stride : nullptr;
@@ -184,7 +206,8 @@ __global__ void __launch_bounds__(NW * 32, Cfg<T, MODE>::BPS) k1f_score_kernel(c
                     int recv_hr = 0, recv_gr = 0;
                     const V16* pp = sm_prof + lane;
                     V16* pk = sm_poke + warp * (CH * 32) + lane;
-                    const int nsteps = LS + lanes - 1;
+                    int nsteps = LS + lanes - 1;
+                    if (sizeof(T) == 4) pin(nsteps);
                     if (SWG && pass > 0) maxh = __ldcg(misc);
 
                     for (int step = 0; step < nsteps; ++step) {
@@ -204,7 +227,11 @@ __global__ void __launch_bounds__(NW * 32, Cfg<T, MODE>::BPS) k1f_score_kernel(c
                             if (!SWG) {
                                 // band cut: rows on diagonal lw / up+1 lose their horizontal input
                                 const int kL = n - lwm, kU = n - upm;
-                                if ((unsigned)kL < (unsigned)R || (unsigned)kU < (unsigned)R) {
+                                if (sizeof(T) == 4) {       // measured: float 1,384 -> 1,500 GCUPS with the jump table,
+                                    if ((unsigned)kL < (unsigned)R) poke<T, R>(L.E, kL, NEG);      // double 602 -> 568
+                                    if ((unsigned)kU < (unsigned)R) poke<T, R>(L.E, kU, NEG);
+                                } else if ((unsigned)kL < (unsigned)R || (unsigned)kU < (unsigned)R) {
+                                    // double: the eight 16-byte halves of E through this warp's shared-memory scratch
 #pragma unroll
                                     for (int j = 0; j < CH; ++j) pk[j * 32] = pack16(&L.E[j * VPL]);
                                     T* pks = reinterpret_cast<T*>(pk);
