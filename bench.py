@@ -273,6 +273,61 @@ def group_candidates_measurement(P, torch, dist, rank, world, local):
         return {"error": repr(e)[:300]}
 
 
+def edge_candidates_measurement(P, torch, dist, rank, world, local):
+    """SURVEY.md 8(e), row 2: candidate scoring of the sparse distance graph (AdjacentMat::spaln_job, src/adjmat.cc:
+    119-156, DynScr branch): per query the k-mer search returns a few database sequences and every (query, candidate)
+    pair gets 100 * alnscore2dist.  Here: the C5a set, 32 seeded candidates per query (the search itself is host code
+    outside the path), queries dealt to the ranks by DP cells, pg_dist_pairs per rank (host-buffer call), ONE
+    all-reduce(SUM) of the edge vector."""
+    try:
+        from prrn_aln_b200 import seqcode, sharding
+        seqs = gen_synth.config_set("c5a")
+        enc = [seqcode.encode_protein(x) for x in seqs]
+        ss = P.SeqSet(enc)
+        n = len(enc)
+        rng = np.random.default_rng(11)
+        per = 32
+        qi = np.repeat(np.arange(n), per)
+        si = (qi + 1 + rng.integers(0, n - 1, size=len(qi))) % n       # never the query itself
+        M = blosum62_matrix()
+        prm = P.Params(P.ALPRM(sh=-60), vtype=1)
+        lens = np.array([len(e) for e in enc])
+        ctx = P.Context(local)
+
+        def dist_of(idx):
+            return ctx.dist_pairs(ss, qi[idx], si[idx], prm, M)
+        for _ in range(2):
+            sharding.dist_edges_sharded(dist_of, qi, si, lens, -60, rank, world, dist)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        steps = 3
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            full, mine = sharding.dist_edges_sharded(dist_of, qi, si, lens, -60, rank, world, dist)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        # parity: a seeded sample of this rank's edges against the all-pairs entry of the same pair (a = query, b = hit)
+        bad = 0
+        if len(mine):
+            pick = mine[rng.integers(0, len(mine), size=64)]
+            for e in pick:
+                a_, b_ = int(qi[e]), int(si[e])
+                ref = ctx.dist_pairs(P.SeqSet([enc[a_], enc[b_]]), [0], [1], prm, M)[0]
+                bad += float(full[e]) != float(ref)
+        ctx.close()
+        cells = int(sharding.pair_costs(lens, qi, si, -60).sum())
+        return {"metric": "DP GCUPS (candidate edges of the sparse distance graph, sharded by query, host-buffer calls)",
+                "value": cells * steps / float(dt.item()) / 1e9, "unit": "GCUPS", "n_gpus": world,
+                "ms_per_step": 1e3 * float(dt.item()) / steps, "edges": int(len(qi)), "cells": cells,
+                "checksum": float(full.sum().item()), "sample_mismatches": int(bad),
+                "collective": "nccl all_reduce(sum) of %d doubles" % len(qi) if world > 1 else None, "scaling": "strong"}
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
 def prrn_msa_measurement():
     """The third part of BASELINE.json's metric: `prrn` MSA wall seconds on config 3 (200 x ~500 aa, prrn5 -m blosum62):
     the reference's own prrn5 program as it is (every DP on ONE host core: upstream's threaded mode crashes on
@@ -564,6 +619,10 @@ def main():
         gc = group_candidates_measurement(P, torch, dist, rank, world, local)
         if rank == 0:
             out["group_candidates"] = gc
+    if not args.no_groups:
+        ec = edge_candidates_measurement(P, torch, dist, rank, world, local)
+        if rank == 0:
+            out["edge_candidates"] = ec
     if rank == 0 and world == 1 and not args.no_groups:
         out["group_to_group"] = group_side_measurement()
     if rank == 0 and world == 1 and not args.no_prrn:

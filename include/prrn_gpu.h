@@ -68,6 +68,17 @@ int pg_score_pairs(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx, c
                    int64_t npairs, const pg_params *prm, const void *mtx, int32_t dim,
                    void *out_scores, int32_t *out_ends);
 
+/* ---- edge-list level: stands behind the DynScr branch of
+ *   void AdjacentMat::spaln_job(Seq* sqs[], SrchBlk* bks, AdjMatThQueue* q)   src/adjmat.cc:119-156
+ * i.e. `dist = alnscore2dist(sqs, bks->pwd); dist *= 100.` (src/aln2.cc:289-334) for the candidate pairs
+ * (query a, database sequence b) the k-mer search returns -- the sparse counterpart of calcdist: the same
+ * fill kernels and the same distance epilogue (self scores, |length difference|, algmode.lcl branch with
+ * exg_seq and end points) over an explicit pair list instead of the condensed triangle.  out_dist[p] in
+ * FTYPE (float when vtype == 0, double when 1), bit-identical to pg_calcdist's entry for the same (a, b).
+ * The threshold test (`< alprm.thr`) and fillmat stay with the caller. */
+int pg_dist_pairs(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx, const int32_t *b_idx,
+                  int64_t npairs, const pg_params *prm, const void *mtx, int32_t dim, void *out_dist);
+
 /* ---- per-call level: stands behind
  *   template<class recd_t> SKL* alignC(mSeq* seqs[2], PwdM* pwd, VTYPE* scr, ...)   src/fwd2c.h:670-677
  * for recd_t = DPunit (alnmode NGP_ALB: two single sequences, no internal gaps), i.e. the

@@ -108,6 +108,8 @@ def load_library():
     L.pg_destroy.restype = None
     L.pg_score_pairs.argtypes = [C.c_void_p, C.POINTER(_PgSeqs), C.c_void_p, C.c_void_p, C.c_int64,
                                  C.POINTER(Params), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    L.pg_dist_pairs.argtypes = [C.c_void_p, C.POINTER(_PgSeqs), C.c_void_p, C.c_void_p, C.c_int64,
+                                C.POINTER(Params), C.c_void_p, C.c_int32, C.c_void_p]
     L.pg_align_pairs.argtypes = [C.c_void_p, C.POINTER(_PgSeqs), C.c_void_p, C.c_void_p, C.c_int64,
                                  C.POINTER(Params), C.c_void_p, C.c_int32, C.c_void_p,
                                  C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32))]
@@ -221,6 +223,18 @@ class Context:
                                           C.byref(prm), m.ctypes.data, m.shape[0], out.ctypes.data,
                                           ends.ctypes.data if want_ends else None))
         return (out, ends) if want_ends else out
+
+    def dist_pairs(self, seqs, a_idx, b_idx, prm, mtx):
+        """100 * alnscore2dist(seqs[a], seqs[b]) for an explicit edge list (the DynScr branch of
+        AdjacentMat::spaln_job, reference src/adjmat.cc:119-156): calcdist's distance for sparse candidate pairs."""
+        a = np.ascontiguousarray(a_idx, dtype=np.int32)
+        b = np.ascontiguousarray(b_idx, dtype=np.int32)
+        m = _mtx_for(prm, mtx)
+        out = np.empty(len(a), dtype=prm.ftype)
+        cs = seqs.c_struct()
+        self._check(self.L.pg_dist_pairs(self.h, C.byref(cs), a.ctypes.data, b.ctypes.data, len(a),
+                                         C.byref(prm), m.ctypes.data, m.shape[0], out.ctypes.data))
+        return out
 
     # -- per-call level: batch of alignC<DPunit> ------------------------------------------------
     def align_pairs(self, seqs, a_idx, b_idx, prm, mtx, ng=False):

@@ -806,10 +806,30 @@ extern "C" int pg_calcdist(pg_context* c, const pg_seqs* s, const pg_params* prm
     return rc;
 }
 
-// ---- explicit pairs (alnScoreD batch) -----------------------------------------------------------
+// ---- explicit pairs (alnScoreD batch; with `dist` the distance epilogue of alnscore2dist on top) ---
+static int score_pairs_impl(pg_context* c, const pg_seqs* s, const int32_t* a_idx, const int32_t* b_idx,
+                            int64_t npairs, const pg_params* prm, const void* mtx, int32_t dim,
+                            void* out_scores, int32_t* out_ends, bool dist);
+
 extern "C" int pg_score_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_idx, const int32_t* b_idx,
                               int64_t npairs, const pg_params* prm, const void* mtx, int32_t dim,
                               void* out_scores, int32_t* out_ends)
+{
+    return score_pairs_impl(c, s, a_idx, b_idx, npairs, prm, mtx, dim, out_scores, out_ends, false);
+}
+
+extern "C" int pg_dist_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_idx, const int32_t* b_idx,
+                             int64_t npairs, const pg_params* prm, const void* mtx, int32_t dim, void* out_dist)
+{
+    if (c && prm && (prm->lcl & 16))
+        return fail(c, PG_ERR_UNSUPPORTED, "pg_dist_pairs with algmode.lcl & 16: the reference reads `ends` uninitialised "
+                                           "there (aln2.cc:296-305), there is no defined result to reproduce");
+    return score_pairs_impl(c, s, a_idx, b_idx, npairs, prm, mtx, dim, out_dist, nullptr, true);
+}
+
+static int score_pairs_impl(pg_context* c, const pg_seqs* s, const int32_t* a_idx, const int32_t* b_idx,
+                            int64_t npairs, const pg_params* prm, const void* mtx, int32_t dim,
+                            void* out_scores, int32_t* out_ends, bool dist)
 {
     if (!c) return PG_ERR_ARG;
     if (!s || !prm || !mtx || npairs < 0 || (npairs && (!a_idx || !b_idx || !out_scores)))
@@ -826,7 +846,8 @@ extern "C" int pg_score_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
     if (d->max_code >= dim) { pg_seqs_free(c, d); return fail(c, PG_ERR_ARG, "residue code outside the substitution matrix"); }
     IntScoring sc;
     ScorePlan plan;
-    if ((rc = plan_scoring(c, prm, mtx, dim, d, out_ends != nullptr, &sc, &plan))) { pg_seqs_free(c, d); return rc; }
+    // dist: alnscore2dist's algmode.lcl branch runs the semi-global score with end points (aln2.cc:296-320)
+    if ((rc = plan_scoring(c, prm, mtx, dim, d, dist ? prm->lcl != 0 : out_ends != nullptr, &sc, &plan))) { pg_seqs_free(c, d); return rc; }
     // rows = a (query of the work item), columns = b; sort pairs by a so that one CTA reuses the profile
     std::vector<int32_t> order(npairs);
     std::iota(order.begin(), order.end(), 0);
@@ -872,8 +893,9 @@ extern "C" int pg_score_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
             e = cudaMemcpyAsync(d_po, pair_out.data(), sizeof(int64_t) * npairs, cudaMemcpyHostToDevice, c->stream);
             if (e == cudaSuccess) e = cudaMemcpyAsync(d_ps, pair_s.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, c->stream);
             if (e != cudaSuccess) rc = fail(c, PG_ERR_CUDA, std::string("pg_score_pairs: ") + cudaGetErrorString(e));
-            if (!rc) rc = k1f_run(c, c->stream, d, prm, mtx, dim, plan.mode, 0, items, multipass, d_ps, d_po, 0, 0, -1,
-                                  c->d_out, out_ends ? (int32_t*)c->d_ends : nullptr, nullptr);
+            if (!rc) rc = k1f_run(c, c->stream, d, prm, mtx, dim, plan.mode, dist ? (prm->lcl ? 2 : 1) : 0, items, multipass, d_ps, d_po,
+                                  0, 0, dist && prm->lcl ? (prm->lcl & 15) : -1, c->d_out,
+                                  out_ends ? (int32_t*)c->d_ends : nullptr, nullptr);
             if (!rc) {
                 e = cudaMemcpyAsync(out_scores, c->d_out, esz * npairs, cudaMemcpyDeviceToHost, c->stream);
                 if (e == cudaSuccess && out_ends)
@@ -892,16 +914,19 @@ extern "C" int pg_score_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
     rc = stage_common(c, c->stream, sc, dim, items, multipass, grid, d->max_wlen, &a);
     if (!rc) rc = ensure_cap(c, &c->d_pairs, &c->pairs_cap, (sizeof(int32_t) + sizeof(int64_t)) * (size_t)npairs + 64);
     if (!rc) rc = ensure_cap(c, &c->d_out, &c->out_cap, esz * (size_t)npairs);
+    if (!rc && dist) rc = ensure_cap(c, &c->d_self, &c->self_cap, sizeof(int32_t) * std::max<size_t>(d->v.nseq, 1));
     if (!rc) {
         int64_t* d_po = (int64_t*)c->d_pairs;
         int32_t* d_ps = (int32_t*)((char*)c->d_pairs + sizeof(int64_t) * (size_t)npairs);
         e = cudaMemcpyAsync(d_po, pair_out.data(), sizeof(int64_t) * npairs, cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_ps, pair_s.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && dist) e = k1_self_launch(d->v, a.mtx, dim, (int32_t*)c->d_self, c->stream);
         a.pair_s = d_ps;
         a.pair_out = d_po;
         a.sh = prm->alprm.sh;
         a.u_f32 = prm->alprm.u;
-        a.epilogue = prm->vtype ? PG_EPI_SCORE_F64 : PG_EPI_SCORE_F32;
+        a.self = dist ? (const int32_t*)c->d_self : nullptr;
+        a.epilogue = dist ? (prm->vtype ? PG_EPI_DIST_F64 : PG_EPI_DIST_F32) : (prm->vtype ? PG_EPI_SCORE_F64 : PG_EPI_SCORE_F32);
         a.out = c->d_out;
         if (e == cudaSuccess) e = k1_launch(a, grid, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, c->d_out, esz * npairs, cudaMemcpyDeviceToHost, c->stream);

@@ -50,6 +50,21 @@ def band_cells(lq, ls, sh):
     return np.where((lq > 0) & (ls > 0), c, 0)
 
 
+def pair_costs(lens, a_idx, b_idx, sh):
+    """band_cells for an explicit pair list: lengths have few distinct values, so the cells come from a table over
+    (length of a, length of b) -- 320,000 pairs in a few ms instead of the closed form evaluated per pair."""
+    lens = np.asarray(lens, dtype=np.int64)
+    a_idx = np.asarray(a_idx, dtype=np.int64)
+    b_idx = np.asarray(b_idx, dtype=np.int64)
+    if len(a_idx) == 0:
+        return np.zeros(0, np.int64)
+    uniq, inv = np.unique(lens, return_inverse=True)
+    if len(uniq) * len(uniq) > 4 * len(a_idx) + 4096:         # very ragged set: the table would be the larger job
+        return band_cells(lens[a_idx], lens[b_idx], sh)
+    table = band_cells(uniq[:, None], uniq[None, :], sh)
+    return table[inv[a_idx], inv[b_idx]]
+
+
 def row_costs(lens, sh):
     """cost[j] = cells of the pairs (i, j), i < j -- row j of the condensed triangle (a = i, b = j).  Lengths
     have few distinct values, so the cost is a table over (length of i, length of j) times running counts."""
@@ -170,3 +185,45 @@ def best_of_n_sharded(scores_of, costs, rank, world, dist=None):
     buf = buf.cpu()
     best = int(torch.argmax(buf).item()) if n else -1
     return best, (float(buf[best]) if n else float("-inf")), buf
+
+
+# ---- candidate edges of the sparse distance graph (AdjacentMat::spaln_job, src/adjmat.cc:119-156) ----
+def shard_queries(q_idx, costs, world, rank):
+    """The candidate pairs (query, database sequence) of the SL-forest search are independent per query (SURVEY.md
+    8(e), row 2): all edges of one query go to one rank (the query profile is built once), queries are dealt to
+    the ranks by their DP cells.  Returns the indices of this rank's edges, ascending."""
+    q_idx = np.asarray(q_idx, dtype=np.int64)
+    costs = np.asarray(costs, dtype=np.int64)
+    if len(q_idx) == 0:
+        return np.zeros(0, np.int64)
+    nq = int(q_idx.max()) + 1
+    per_q = np.bincount(q_idx, weights=costs.astype(np.float64), minlength=nq)
+    # thousands of queries of similar cost: deal them in descending order of cost, back and forth over the ranks
+    # (0 1 .. w-1 w-1 .. 1 0 ...); loads then differ by less than one query.  Vectorised; deterministic (stable sort).
+    order = np.argsort(-per_q, kind="stable")
+    pos = np.arange(nq) % (2 * world)
+    owner = np.empty(nq, dtype=np.int64)
+    owner[order] = np.where(pos < world, pos, 2 * world - 1 - pos)
+    return np.nonzero(owner[q_idx] == rank)[0]
+
+
+def dist_edges_sharded(dist_of, q_idx, s_idx, lens, sh, rank, world, dist=None):
+    """Distances of the candidate edges over `world` ranks: rank r evaluates `dist_of(edge indices) -> values`
+    (pg_dist_pairs on its GPU) for its queries' edges; ONE all-reduce(SUM) of a vector that every rank fills only
+    at its own edges (the others hold 0, so the sum is exact) puts all distances on every rank, where the caller
+    applies the threshold and fills the graph (fillmat stays host code)."""
+    import torch
+    q_idx = np.asarray(q_idx, dtype=np.int64)
+    s_idx = np.asarray(s_idx, dtype=np.int64)
+    lens = np.asarray(lens, dtype=np.int64)
+    costs = pair_costs(lens, q_idx, s_idx, sh)
+    mine = shard_queries(q_idx, costs, world, rank)
+    vals = np.asarray(dist_of(mine), dtype=np.float64) if len(mine) else np.zeros(0)
+    buf = torch.zeros(len(q_idx), dtype=torch.float64)
+    if len(mine):
+        buf[torch.as_tensor(mine)] = torch.as_tensor(vals)
+    if world > 1 and dist is not None:
+        if dist.get_backend() == "nccl":
+            buf = buf.cuda()
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return buf.cpu(), mine

@@ -63,6 +63,35 @@ def test_all_score_goldens_through_float_kernel(ctx, name, monkeypatch):
         assert np.array_equal(dist.astype(np.float64), np.array(g["dist"])), "calcdist differs from the reference"
 
 
+@pytest.mark.parametrize("force_float", ["0", "1"])
+@pytest.mark.parametrize("name", [n for n in golden_names("score_") if "dist" in golden(n)])
+def test_edge_list_distances_equal_the_reference_calcdist(ctx, name, force_float, monkeypatch):
+    """pg_dist_pairs (the DynScr branch of AdjacentMat::spaln_job, src/adjmat.cc:119-156: 100 * alnscore2dist per
+    candidate pair) over ALL pairs of a golden set, in a shuffled order with repeats, must reproduce the reference's
+    own calcdist vector bit for bit -- on the exact-integer kernels where they apply and on K1F, global and
+    algmode.lcl branch (trimmed self scores)."""
+    monkeypatch.setenv("PG_FORCE_FLOAT", force_float)
+    g = golden(name)
+    enc = [seqcode.encode_protein(s) for s in g["seqs"]]
+    prm = _params(g)
+    M = np.array(g["matrix"])
+    ia, ib = _pairs(len(enc))
+    rng = np.random.default_rng(5)
+    order = np.concatenate([rng.permutation(len(ia)), rng.integers(0, len(ia), size=17)])
+    got = ctx.dist_pairs(P.SeqSet(enc), np.array(ia)[order], np.array(ib)[order], prm, M)
+    assert got.dtype == prm.ftype
+    assert np.array_equal(got.astype(np.float64), np.array(g["dist"])[order])
+    assert len(ctx.dist_pairs(P.SeqSet(enc), [], [], prm, M)) == 0
+
+
+def test_edge_list_distances_refuse_lcl16(ctx):
+    g = golden("score_p24_lcl16")
+    enc = [seqcode.encode_protein(s) for s in g["seqs"]]
+    with pytest.raises(P.PgError) as e:
+        ctx.dist_pairs(P.SeqSet(enc), [0], [1], _params(g), np.array(g["matrix"]))
+    assert e.value.code == 4
+
+
 def test_calcdist_lcl16_is_refused(ctx):
     g = golden("score_p24_lcl16")
     enc = [seqcode.encode_protein(s) for s in g["seqs"]]

@@ -128,3 +128,63 @@ def test_best_of_n_over_ranks(world):
     for p in procs:
         p.join(timeout=60)
     assert all(b == 1 and v == 9.25 and ok for _, b, v, ok in res), res
+
+
+def test_pair_costs_table_equals_closed_form():
+    rng = np.random.default_rng(6)
+    for lens, npairs in ((rng.integers(270, 330, size=2000), 20000), (rng.integers(0, 5000, size=400), 300)):
+        a, b = rng.integers(0, len(lens), size=npairs), rng.integers(0, len(lens), size=npairs)
+        for sh in (-60, 0, 25):
+            assert np.array_equal(sharding.pair_costs(lens, a, b, sh), sharding.band_cells(lens[a], lens[b], sh))
+    assert len(sharding.pair_costs([5, 6], [], [], -60)) == 0
+
+
+def test_query_split_keeps_a_query_on_one_rank():
+    rng = np.random.default_rng(8)
+    q = np.repeat(np.arange(40), rng.integers(1, 30, size=40))
+    rng.shuffle(q)
+    costs = rng.integers(1000, 90000, size=len(q))
+    for world in (1, 2, 3, 8):
+        parts = [sharding.shard_queries(q, costs, world, r) for r in range(world)]
+        assert sorted(int(i) for p in parts for i in p) == list(range(len(q)))
+        owner = {}
+        for r, p in enumerate(parts):
+            for i in p:
+                assert owner.setdefault(int(q[i]), r) == r
+        loads = [int(costs[p].sum()) for p in parts]
+        per_q = np.bincount(q, weights=costs)
+        assert max(loads) - min(loads) <= per_q.max()
+
+
+def _edge_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(2)
+    lens = rng.integers(50, 400, size=60)
+    qi = np.repeat(np.arange(0, 60, 3), 7)
+    si = rng.integers(0, 60, size=len(qi))
+    truth = (qi * 1000 + si).astype(np.float64) / 8.0
+
+    def dist_of(idx):               # stand-in for pg_dist_pairs on this rank's GPU
+        return truth[idx]
+
+    full, mine = sharding.dist_edges_sharded(dist_of, qi, si, lens, -60, rank, world, dist)
+    q.put((rank, bool(np.array_equal(full.numpy(), truth)), len(mine)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_candidate_edges_over_ranks(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_edge_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert sum(n for _, _, n in res) == 140
