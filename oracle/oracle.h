@@ -126,6 +126,8 @@ int orc_align_groups(const orc_group *a, const orc_group *b, const double *mtx, 
                      double *score, orc_skl *out, int cap, int64_t *cells);
 /* HomScoreC<recd_t>(seqs, pwd, rr) (reference src/fwd2c.h:663-668): the same fill without Vmf; rr = pp[] of forwardB
  * (:468-469, :476-479). */
+int orc_swg_groups(const orc_group *a, const orc_group *b, const double *mtx, int dim, const orc_gparams *p,
+                   double *val, int *box /* mlb nlb mrb nrb lwr upr */, int64_t *cells);
 int orc_homscore_groups(const orc_group *a, const orc_group *b, const double *mtx, int dim, const orc_gparams *p,
                         double *score, long rr[2]);
 

@@ -77,7 +77,9 @@ static const orc_gfreq *g_list(const orc_group *g, const int32_t *offs, int ix)
 
 /* everything below is instantiated for float and double VTYPE */
 #define DEFINE_GROUP_ALIGN(VT, SUFFIX, NEVSEL_V)                                                     \
-typedef struct { VT val; int dir; long ptr; int glb; g_idelta *dla, *dlb; int *gla, *glv; } g_unit_##SUFFIX;\
+typedef struct { VT val; int dir; long ptr; int glb; g_idelta *dla, *dlb; int *gla, *glv;             \
+                 int lwr, upr, mlb, nlb;    /* SwgDPunit (dpunit.h:53-63): the box of the local path */\
+} g_unit_##SUFFIX;                                                                                   \
                                                                                                      \
 static VT g_newgap4_##SUFFIX(const orc_gfreq *cf, const g_idelta *dlc, const orc_gfreq *df, const g_idelta *dld)\
 {   /* gfreq.cc:507-521 */                                                                           \
@@ -456,6 +458,176 @@ static int g_align_##SUFFIX(const orc_group *a, const orc_group *b, const double
     out[0].m = 0; out[0].n = cnt;                                                                    \
     free(buf); free(pool); free(glpool); free(st.v);                                                 \
     return ok ? cnt : -1;                                                                            \
+}                                                                                                    \
+/* ---- Smith-Waterman: Fwd2c<SwgDPunit*>::initC + forwardC (fwd2c.h:178-207,483-659) for algmode.mlt <= 1, i.e.            \
+ * without secondary colonies: the best local score and its box (colony 0).  Records carry (lwr, upr, mlb, nlb);            \
+ * SwgDPunit's own gapopen / update (fwd2c.cc:257-296) for groups without gap profile, the banded rules plus the box        \
+ * for the others (:298-428); a negative cell is cleared together with the horizontal states (and G2, not G: :601-605). */  \
+static void g_swg_blank_##SUFFIX(const g_ctx_##SUFFIX *c, g_unit_##SUFFIX *r, VT v)                                         \
+{   /* clear / reset<SwgDPunit*> (dpunit.cc): blank_swgdpunit / black_swgdpunit */                                          \
+    g_reset_##SUFFIX(c, r);                                                                                                 \
+    r->val = v; r->lwr = INT_MAX / 8 * 7; r->upr = INT_MIN / 8 * 7; r->mlb = r->nlb = 0;                                    \
+}                                                                                                                           \
+static void g_swg_copy_##SUFFIX(const g_ctx_##SUFFIX *c, g_unit_##SUFFIX *d, const g_unit_##SUFFIX *s)                      \
+{                                                                                                                           \
+    if (d == s) return;                                                                                                     \
+    g_copy_##SUFFIX(c, d, s);                                                                                               \
+    d->lwr = s->lwr; d->upr = s->upr; d->mlb = s->mlb; d->nlb = s->nlb;                                                     \
+}                                                                                                                           \
+static VT g_swg_gapopen_##SUFFIX(const g_ctx_##SUFFIX *c, const g_unit_##SUFFIX *r, int ia, int ib, int d3)                 \
+{                                                                                                                           \
+    if (c->mode == 0) return (g_isdiag(r->dir) && d3) ? (VT)c->p->BasicGOP : 0;      /* fwd2c.cc:268-271 */                 \
+    return g_gapopen_##SUFFIX(c, r, ia, ib, d3);                                                                            \
+}                                                                                                                           \
+static void g_swg_update_##SUFFIX(const g_ctx_##SUFFIX *c, g_unit_##SUFFIX *dst, const g_unit_##SUFFIX *src,                \
+                                  int ia, int ib, VT gpn, int d3, int r)                                                    \
+{   /* swg_gdpunit_update (fwd2c.cc:273-289) + the list part of the record type; dst may alias src */                       \
+    const int sdir = src->dir, lwr = src->lwr, upr = src->upr, mlb = src->mlb, nlb = src->nlb;                              \
+    g_update_##SUFFIX(c, dst, src, ia, ib, gpn, d3);                                                                        \
+    dst->lwr = lwr; dst->upr = upr; dst->mlb = mlb; dst->nlb = nlb;                                                         \
+    if (d3 > 0) { dst->dir = G_VERT; if (r < dst->lwr) dst->lwr = r; }                                                      \
+    else if (d3 < 0) { dst->dir = G_HORI; if (r > dst->upr) dst->upr = r; }                                                 \
+    else dst->dir = g_isdiag(sdir) ? G_DIAG : G_NEWD;                                                                       \
+}                                                                                                                           \
+static int g_swg_##SUFFIX(const orc_group *a, const orc_group *b, const double *mtx, int dim,                               \
+                          const orc_gparams *p, double *val, int *box, int64_t *cells)                                      \
+{                                                                                                                           \
+    typedef g_unit_##SUFFIX U;                                                                                              \
+    g_ctx_##SUFFIX C;                                                                                                       \
+    C.a = a; C.b = b; C.p = p; C.mtx = mtx; C.dim = dim;                                                                    \
+    const int am = p->alnmode;                                                                                              \
+    C.mode = am == 6 ? 0 : (am == 9 ? 2 : (am == 10 ? 3 : 1));                                                              \
+    C.wgop = (VT)p->Weighted_GOP; C.bgop = (VT)p->Basic_GOP;                                                                \
+    const VT BasicGOP = (VT)p->BasicGOP, BasicGEP = (VT)p->BasicGEP, LongGOP = (VT)p->LongGOP, LongGEP = (VT)p->LongGEP;    \
+    const VT u2divu1 = BasicGEP < 0 ? (VT)LongGEP / BasicGEP : 0;                                                           \
+    const VT v2divv1 = BasicGOP < 0 ? (VT)LongGOP / BasicGOP : 0;                                                           \
+    const int Noll = p->Noll;                                                                                               \
+    const int al = a->left, ar = a->right, bl = b->left, br = b->right;                                                     \
+    orc_seq sa = {0, a->len, al, ar, 0, 0}, sb = {0, b->len, bl, br, 0, 0};                                                 \
+    orc_window w;                                                                                                           \
+    orc_stripe(&sa, &sb, p->sh, &w);                                                                                        \
+    const int lw = w.lw, up = w.up;                                                                                         \
+    const int capa = (a->hetero > 0 ? a->hetero : 0) + 3, capb = (b->hetero > 0 ? b->hetero : 0) + 3;                       \
+    const int A0 = al - 1, B0 = bl - 1;                                                                                     \
+    const int NB = br - bl + 2;                                                                                             \
+    const int nrec = 6 * NB + 8;                                                                                            \
+    U *buf = (U *)malloc(sizeof(U) * (size_t)nrec);                                                                         \
+    g_idelta *pool = (g_idelta *)malloc(sizeof(g_idelta) * (size_t)nrec * (size_t)(capa + capb));                           \
+    int *glpool = (int *)calloc((size_t)nrec * (size_t)(a->many + b->many), sizeof(int));                                   \
+    for (int i = 0; i < nrec; ++i) {                                                                                        \
+        buf[i].gla = glpool + (size_t)i * (a->many + b->many); buf[i].glv = buf[i].gla + a->many;                           \
+        buf[i].dla = pool + (size_t)i * (capa + capb); buf[i].dlb = buf[i].dla + capa;                                      \
+        g_swg_blank_##SUFFIX(&C, &buf[i], NEVSEL_V);                                                                        \
+    }                                                                                                                       \
+    U *Hp = buf, *Gp = buf + NB, *G2p = buf + 2 * NB, *Hc = buf + 3 * NB, *Gc = buf + 4 * NB, *G2c = buf + 5 * NB;          \
+    U *f1 = buf + 6 * NB, *f2 = f1 + 1, *black = f1 + 2, *dg = f1 + 4, *g = f1 + 5, *g2 = f1 + 6;                           \
+    int64_t ncell = 0;                                                                                                      \
+    VT c0val = 0;                                   /* colony 0, zeroed by Colonies::Colonies (aln2.cc:418-425) */          \
+    int c0[6] = {0, 0, 0, 0, 0, 0};                 /* mlb nlb mrb nrb lwr upr */                                           \
+    (void)BasicGOP;                                                                                                         \
+    /* initC (:178-207): the records in front of the first row / first column, on the diagonal of the cell that             \
+       takes them as its diagonal predecessor */                                                                            \
+    {                                                                                                                       \
+        int rr = br - al; if (up < rr) rr = up;                                                                             \
+        for (int r = bl - al, n = bl; r <= rr && n - bl < NB; ++r, ++n) {                                                   \
+            U *h = &Hp[n - bl];                                                                                             \
+            g_swg_blank_##SUFFIX(&C, h, 0); h->upr = h->lwr = r; h->mlb = al; h->nlb = n;                                   \
+        }                                                                                                                   \
+    }                                                                                                                       \
+    const int rr_col = (bl - ar > lw) ? bl - ar : lw;                                                                       \
+    for (int m = al; m < ar; ++m) {                                                                                         \
+        const int n0 = G_MAX(m + lw, bl), n9 = G_MIN(m + up + 1, br);                                                       \
+        const int ia = m - A0;                                                                                              \
+        if (m > al) {                               /* H(m - 1, bl - 1): initC's second loop, r = bl - m */                 \
+            if (bl - m >= rr_col) { g_swg_blank_##SUFFIX(&C, &Hp[0], 0); Hp[0].upr = Hp[0].lwr = bl - m; Hp[0].mlb = m; Hp[0].nlb = bl; } \
+            else g_swg_blank_##SUFFIX(&C, &Hp[0], NEVSEL_V);                                                                \
+        }                                                                                                                   \
+        g_swg_blank_##SUFFIX(&C, &Hc[0], NEVSEL_V);                                                                         \
+        g_swg_blank_##SUFFIX(&C, f1, NEVSEL_V);                                                                             \
+        g_swg_blank_##SUFFIX(&C, f2, NEVSEL_V);                                                                             \
+        for (int n = n0; n < n9; ++n) {                                                                                     \
+            const int j = n - bl + 1, ib = n - B0, r = n - m;                                                               \
+            ++ncell;                                                                                                        \
+            const int above_inband = (r + 1 <= up);                                                                         \
+            const U *hdiag = &Hp[j - 1];                                                                                    \
+            const U *habove = above_inband ? &Hp[j] : black, *gabove = above_inband ? &Gp[j] : black;                       \
+            const U *g2above = above_inband ? &G2p[j] : black;                                                              \
+            const U *hleft = (n - 1 >= n0) ? &Hc[j - 1] : black;                                                            \
+            const VT diag = hdiag->val;                                                                                     \
+            VT dab = g_sim2_##SUFFIX(&C, ia, ib);                                                                           \
+            VT gop = g_swg_gapopen_##SUFFIX(&C, hdiag, ia, ib, 0);                                                          \
+            g_swg_update_##SUFFIX(&C, dg, hdiag, ia, ib, dab + gop, 0, r);                                                  \
+            VT gnp;                                                                                                         \
+            const U *mx = g;                                                                                                \
+            if (m > al) {                           /* vertical (:531-541) */                                               \
+                VT pua = g_unp_##SUFFIX(&C, a, ia, b, ib);                                                                  \
+                gnp = g_swg_gapopen_##SUFFIX(&C, gabove, ia, ib, 1);                                                        \
+                gop = g_swg_gapopen_##SUFFIX(&C, habove, ia, ib, 1);                                                        \
+                if (!g_isvert(habove->dir) && (habove->val + gop > gabove->val + gnp))                                      \
+                    g_swg_update_##SUFFIX(&C, g, habove, ia, ib, gop, 1, r);                                                \
+                else g_swg_update_##SUFFIX(&C, g, gabove, ia, ib, gnp, 1, r);                                               \
+                g->val += pua;                                                                                              \
+                if (Noll == 3) {                    /* vertical2 (:543-552) */                                              \
+                    gnp = (VT)(v2divv1 * g_swg_gapopen_##SUFFIX(&C, g2above, ia, ib, 1));                                   \
+                    gop = (VT)(v2divv1 * gop);                                                                              \
+                    if (!g_isvert(habove->dir) && (habove->val + gop > g2above->val + gnp))                                 \
+                        g_swg_update_##SUFFIX(&C, g2, habove, ia, ib, gop, 1, r);                                           \
+                    else g_swg_update_##SUFFIX(&C, g2, g2above, ia, ib, gnp, 1, r);                                         \
+                    g2->val += (VT)(u2divu1 * pua);                                                                         \
+                    if (g2->val > mx->val) mx = g2;                                                                         \
+                }                                                                                                           \
+            } else {                                /* first row: the untouched G / G2 records */                           \
+                g_swg_blank_##SUFFIX(&C, g, NEVSEL_V); g_swg_blank_##SUFFIX(&C, g2, NEVSEL_V);                              \
+            }                                                                                                               \
+            if (n > bl) {                           /* horizontal (:555-564) */                                             \
+                VT pub = g_unp_##SUFFIX(&C, b, ib, a, ia);                                                                  \
+                gnp = g_swg_gapopen_##SUFFIX(&C, f1, ia, ib, -1);                                                           \
+                gop = g_swg_gapopen_##SUFFIX(&C, hleft, ia, ib, -1);                                                        \
+                if (!g_ishori(hleft->dir) && (hleft->val + gop > f1->val + gnp))                                            \
+                    g_swg_update_##SUFFIX(&C, f1, hleft, ia, ib, gop, -1, r);                                               \
+                else g_swg_update_##SUFFIX(&C, f1, f1, ia, ib, gnp, -1, r);                                                 \
+                f1->val += pub;                                                                                             \
+                if (f1->val >= mx->val) mx = f1;                                                                            \
+                if (Noll == 3) {                    /* horizontal2 (:566-575) */                                            \
+                    gnp = (VT)(v2divv1 * g_swg_gapopen_##SUFFIX(&C, f2, ia, ib, -1));                                       \
+                    gop = (VT)(v2divv1 * gop);                                                                              \
+                    if (!g_ishori(hleft->dir) && (hleft->val + gop > f2->val + gnp))                                        \
+                        g_swg_update_##SUFFIX(&C, f2, hleft, ia, ib, gop, -1, r);                                           \
+                    else g_swg_update_##SUFFIX(&C, f2, f2, ia, ib, gnp, -1, r);                                             \
+                    f2->val += (VT)(u2divu1 * pub);                                                                         \
+                    if (f2->val >= mx->val) mx = f2;                                                                        \
+                }                                                                                                           \
+            }                                                                                                               \
+            U *h = &Hc[j];                                                                                                  \
+            if (mx->val > dg->val) {                /* non-diagonal (:586-589) */                                           \
+                g_swg_copy_##SUFFIX(&C, h, mx);                                                                             \
+                if (h->lwr > r) h->lwr = r;                                                                                 \
+                if (h->upr < r) h->upr = r;                                                                                 \
+            } else {                                                                                                        \
+                g_swg_copy_##SUFFIX(&C, h, dg);                                                                             \
+                if (h->val > diag) {                                                                                        \
+                    if (diag == 0) { h->upr = h->lwr = r; h->mlb = m; h->nlb = n; }     /* new colony (:591-595) */         \
+                    if (h->val > c0val) {           /* max local score (:596-604) */                                        \
+                        c0val = h->val;                                                                                     \
+                        c0[0] = h->mlb; c0[1] = h->nlb; c0[2] = m + 1; c0[3] = n + 1; c0[4] = h->lwr; c0[5] = h->upr;       \
+                    }                                                                                                       \
+                }                                                                                                           \
+            }                                                                                                               \
+            if (h->val < 0) {                       /* reset to blank (:606-610): h, f1 (twice), f2 and g2 -- not g */      \
+                g_swg_blank_##SUFFIX(&C, h, 0); g_swg_blank_##SUFFIX(&C, f1, 0);                                            \
+                if (Noll == 3) { g_swg_blank_##SUFFIX(&C, f2, 0); g_swg_blank_##SUFFIX(&C, g2, 0); }                        \
+            }                                                                                                               \
+            g_swg_copy_##SUFFIX(&C, &Gc[j], g);                                                                             \
+            g_swg_copy_##SUFFIX(&C, &G2c[j], g2);                                                                           \
+        }                                                                                                                   \
+        U *t;                                                                                                               \
+        t = Hp; Hp = Hc; Hc = t; t = Gp; Gp = Gc; Gc = t; t = G2p; G2p = G2c; G2c = t;                                      \
+    }                                                                                                                       \
+    *val = (double)c0val;                                                                                                   \
+    for (int k = 0; k < 6; ++k) box[k] = c0[k];                                                                             \
+    if (cells) *cells = ncell;                                                                                              \
+    free(buf); free(pool); free(glpool);                                                                                    \
+    return 0;                                                                                                               \
 }
 
 typedef struct { int32_t m, n; long p; } o_rec;
@@ -648,6 +820,13 @@ int orc_align_groups(const orc_group *a, const orc_group *b, const double *mtx, 
 {
     return p->vtype ? g_align_f64(a, b, mtx, dim, p, score, out, cap, cells, 0)
                     : g_align_f32(a, b, mtx, dim, p, score, out, cap, cells, 0);
+}
+
+/* swg1stC<SwgDPunit | _hf | _pf | _nv> (fwd2c.h:697-701) for algmode.mlt <= 1: colony 0 = best local score + box */
+int orc_swg_groups(const orc_group *a, const orc_group *b, const double *mtx, int dim, const orc_gparams *p,
+                   double *val, int *box, int64_t *cells)
+{
+    return p->vtype ? g_swg_f64(a, b, mtx, dim, p, val, box, cells) : g_swg_f32(a, b, mtx, dim, p, val, box, cells);
 }
 
 int orc_homscore_groups(const orc_group *a, const orc_group *b, const double *mtx, int dim, const orc_gparams *p,

@@ -240,6 +240,22 @@ def homscore_groups(A, B, mtx, gp):
     return scr.value, [rr[0], rr[1]]
 
 
+def swg_groups(A, B, mtx, gp):
+    """swg1stC<SwgDPunit*> restatement (Fwd2c::forwardC, algmode.mlt <= 1): (best local score, dict of colony 0's
+    box: mlb nlb mrb nrb lwr upr, cells)."""
+    L = lib()
+    L.orc_swg_groups.restype = C.c_int
+    L.orc_swg_groups.argtypes = [C.POINTER(OrcGroup), C.POINTER(OrcGroup), C.POINTER(C.c_double), C.c_int,
+                                 C.POINTER(OrcGparams), C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    m, mp, dim = _mtx(mtx)
+    ga, gb = _orc_group(A), _orc_group(B)
+    val = C.c_double(0)
+    box = (C.c_int * 6)()
+    cells = C.c_int64(0)
+    L.orc_swg_groups(C.byref(ga), C.byref(gb), mp, dim, C.byref(gp), C.byref(val), box, C.byref(cells))
+    return val.value, dict(zip(("mlb", "nlb", "mrb", "nrb", "lwr", "upr"), [int(x) for x in box])), cells.value
+
+
 def align_b1(a, b, mtx, p, std=True):
     """alignB_ng restatement (+ stdskl when std): (score, [(m, n), ...])."""
     L = lib()

@@ -229,6 +229,27 @@ int main(int argc, const char** argv)
 		VTYPE	hs = HomScore(sq, pwd, rr);
 		printf("homscore "); print_vt(hs); printf(" %ld %ld\n", rr[0], rr[1]);
 	    }
+	    if (algmode.lcl & 16) {	// Smith-Waterman (aln.cc:287-311): swg1st -> Fwd2c::forwardC, swg2nd -> align2 inside the colony's box
+		Colonies*	clns = swg1st(sq, pwd);
+		if (!clns) printf("swg none\n");
+		else {
+		    COLONY*	c0 = clns->at();
+		    printf("swg size %d val ", clns->size()); print_vt(c0->val);
+		    printf(" mlb %d nlb %d mrb %d nrb %d lwr %d upr %d\n", c0->mlb, c0->nlb, c0->mrb, c0->nrb, c0->lwr, c0->upr);
+		    Gsinfo	g2;
+		    SKL*	s2 = c0->val > 0? swg2nd(sq, pwd, &g2, c0): 0;
+		    printf("swg2nd "); print_vt(s2? g2.scr: 0);
+		    if (!s2) printf(" skl 0\n");
+		    else {
+			printf(" skl %d %d :", s2->n, s2->m);
+			for (int k = 1; k <= s2->n; ++k) printf(" %d %d", s2[k].m, s2[k].n);
+			putchar('\n');
+		    }
+		    g2.skl = 0;
+		    delete[] s2;
+		    delete clns;
+		}
+	    }
 	    Gsinfo	gsi;
 	    scr = 0;
 	    skl = align2(sq, pwd, &scr, &gsi);

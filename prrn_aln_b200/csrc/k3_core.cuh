@@ -12,6 +12,7 @@
 // Arithmetic is double for both VTYPE flavours (the group path is floating point with a 1e-5 relative
 // tolerance: BASELINE north_star).
 #pragma once
+#include <string.h>
 #include <stdint.h>
 
 #include "k1_core.cuh"
@@ -73,12 +74,21 @@ struct K3Prm {
     // the window, no first-row / first-column skips, the boundary column without the long-gap switch; staged b holds
     // one more column (position b.right)
     int32_t rect;
+    // Smith-Waterman (Fwd2c<SwgDPunit*>::initC + forwardC, src/fwd2c.h:178-207,483-659, algmode.mlt <= 1): cells are
+    // cleared when negative, records carry the box of their local path in their last four words (capb counts them),
+    // the result is the best cell and its box (colony 0) instead of an end cell and a path
+    int32_t swg, pad3;
 };
 
 // ---- record access -------------------------------------------------------------------------------
 PG_HD int k3_stride(int capa, int capb) { return (4 + capa + capb + 1) & ~1; }      // even: val stays 8-byte aligned
+#if defined(__CUDA_ARCH__)
 PG_HD double k3_val(const int* r) { return *reinterpret_cast<const double*>(r); }
 PG_HD void k3_setval(int* r, double v) { *reinterpret_cast<double*>(r) = v; }
+#else       // host emulation (tests): no type punning under the host compiler's strict-aliasing rules
+static inline double k3_val(const int* r) { double v; memcpy(&v, r, sizeof v); return v; }
+static inline void k3_setval(int* r, double v) { memcpy(r, &v, sizeof v); }
+#endif
 #define K3_PTR(r) ((r)[2])
 PG_HD int k3_dir(const int* r) { return r[3] & 0xff; }
 PG_HD int k3_glb(const int* r) { return (int)((unsigned)r[3] >> 8); }
@@ -453,6 +463,136 @@ PG_HD bool k3_cell_mono(const K3Prm& p, const K3Group& a, const K3Group& b, int 
     if (k3_val(mx) > k3_val(hout)) k3_copy(p, hout, mx);        // fwd2c.h:453
     const int dir = k3_dir(hout);
     return dir == K3_NEWD || dir == K3_NEWV || dir == K3_NEWH;   // fwd2c.h:465-467
+}
+
+// ---- Smith-Waterman cell (forwardC, src/fwd2c.h:483-659, without secondary colonies) ---------------------
+// box of a record: {lwr, upr, mlb, nlb} (SwgDPunit, src/dpunit.h:53-63) in the record's last four words
+#define K3S_POS_INT (0x7fffffff / 8 * 7)
+#define K3S_NEG_INT ((-0x7fffffff - 1) / 8 * 7)
+PG_HD int* k3s_box(const K3Prm& p, int* r) { return r + p.capa + p.capb; }
+PG_HD const int* k3s_box(const K3Prm& p, const int* r) { return r + p.capa + p.capb; }
+// clear / reset<SwgDPunit*> (src/dpunit.cc): blank (val 0) or black (val NEVSEL) record with an empty box
+PG_HD void k3s_blank(const K3Prm& p, int* r, double v)
+{
+    k3_reset(p, r);
+    k3_setval(r, v);
+    int* bx = k3s_box(p, r);
+    bx[0] = K3S_POS_INT; bx[1] = K3S_NEG_INT; bx[2] = 0; bx[3] = 0;
+}
+PG_HD void k3s_copy(const K3Prm& p, int* d, const int* s)
+{
+    if (d == s) return;
+    k3_copy(p, d, s);
+    int* bd = k3s_box(p, d); const int* bs = k3s_box(p, s);
+    bd[0] = bs[0]; bd[1] = bs[1]; bd[2] = bs[2]; bd[3] = bs[3];
+}
+// gapopen: SwgDPunit's own rule for groups without gap profile (src/fwd2c.cc:268-271), the banded rules otherwise
+PG_HD double k3s_gapopen(const K3Prm& p, const K3Group& a, const K3Group& b, const int* r, int ia, int ib, int d3)
+{
+    if (p.mode == 0) return (k3_isdiag(k3_dir(r)) && d3) ? p.gop1 : 0;
+    return k3_gapopen(p, a, b, r, ia, ib, d3);
+}
+// swg_gdpunit_update (src/fwd2c.cc:273-289) + the list part of the record type; dst may alias src; r = n - m (absolute)
+PG_HD void k3s_update(const K3Prm& p, const K3Group& a, const K3Group& b, int* dst, const int* src, int ia, int ib,
+                      double gpn, int d3, int r)
+{
+    const int sdir = k3_dir(src);
+    const int* bs = k3s_box(p, src);
+    const int lwr = bs[0], upr = bs[1], mlb = bs[2], nlb = bs[3];
+    k3_update(p, a, b, dst, src, ia, ib, gpn, d3);
+    int* bd = k3s_box(p, dst);
+    bd[0] = (d3 > 0 && r < lwr) ? r : lwr;
+    bd[1] = (d3 < 0 && r > upr) ? r : upr;
+    bd[2] = mlb; bd[3] = nlb;
+    k3_setdg(dst, d3 > 0 ? K3_VERT : (d3 < 0 ? K3_HORI : (k3_isdiag(sdir) ? K3_DIAG : K3_NEWD)), k3_glb(dst));
+}
+// the best cell so far of one thread (colony 0 in the making)
+struct K3Best { double val; int mlb, nlb, mrb, nrb, lwr, upr; };
+PG_HD void k3s_part_diag(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, int ib, int r, double dab,
+                         const int* hdiag, int* hout)
+{
+    const double gop = k3s_gapopen(p, a, b, hdiag, ia, ib, 0);
+    k3s_update(p, a, b, hout, hdiag, ia, ib, dab + gop, 0, r);
+}
+PG_HD void k3s_part_vert(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, int ib, int r, bool first_row,
+                         const int* habove, const int* gabove, const int* g2above, int* gout, int* g2out)
+{
+    if (first_row) {        // the G rows keep their untouched (black) records (:529-530)
+        k3s_blank(p, gout, K3_NEVSEL);
+        if (p.Noll == 3) k3s_blank(p, g2out, K3_NEVSEL);
+        return;
+    }
+    const double pua = k3_unp(a, ia, b, ib, p.u);           // per cell (:531)
+    double gnp = k3s_gapopen(p, a, b, gabove, ia, ib, 1);
+    double gop = k3s_gapopen(p, a, b, habove, ia, ib, 1);
+    if (!k3_isvert(k3_dir(habove)) && (k3_val(habove) + gop > k3_val(gabove) + gnp))
+        k3s_update(p, a, b, gout, habove, ia, ib, gop, 1, r);
+    else k3s_update(p, a, b, gout, gabove, ia, ib, gnp, 1, r);
+    k3_setval(gout, k3_val(gout) + pua);
+    if (p.Noll == 3) {      // vertical2 (:543-552)
+        gnp = p.v2divv1 * k3s_gapopen(p, a, b, g2above, ia, ib, 1);
+        gop = p.v2divv1 * gop;
+        if (!k3_isvert(k3_dir(habove)) && (k3_val(habove) + gop > k3_val(g2above) + gnp))
+            k3s_update(p, a, b, g2out, habove, ia, ib, gop, 1, r);
+        else k3s_update(p, a, b, g2out, g2above, ia, ib, gnp, 1, r);
+        k3_setval(g2out, k3_val(g2out) + p.u2divu1 * pua);
+    }
+}
+PG_HD void k3s_part_hori(const K3Prm& p, const K3Group& a, const K3Group& b, int ia, int ib, int r, bool first_col,
+                         const int* hleft, int* f1, int* f2)
+{
+    if (first_col) return;  // (:554)
+    const double pub = k3_unp(b, ib, a, ia, p.u);
+    double gnp = k3s_gapopen(p, a, b, f1, ia, ib, -1);
+    double gop = k3s_gapopen(p, a, b, hleft, ia, ib, -1);
+    if (!k3_ishori(k3_dir(hleft)) && (k3_val(hleft) + gop > k3_val(f1) + gnp))
+        k3s_update(p, a, b, f1, hleft, ia, ib, gop, -1, r);
+    else k3s_update(p, a, b, f1, f1, ia, ib, gnp, -1, r);
+    k3_setval(f1, k3_val(f1) + pub);
+    if (p.Noll == 3) {      // horizontal2 (:566-575)
+        gnp = p.v2divv1 * k3s_gapopen(p, a, b, f2, ia, ib, -1);
+        gop = p.v2divv1 * gop;
+        if (!k3_ishori(k3_dir(hleft)) && (k3_val(hleft) + gop > k3_val(f2) + gnp))
+            k3s_update(p, a, b, f2, hleft, ia, ib, gop, -1, r);
+        else k3s_update(p, a, b, f2, f2, ia, ib, gnp, -1, r);
+        k3_setval(f2, k3_val(f2) + p.u2divu1 * pub);
+    }
+}
+// selection and book-keeping (:578-610): m, n absolute positions of the cell, r = n - m, diag = H(m-1, n-1)
+PG_HD void k3s_combine(const K3Prm& p, bool first_row, bool first_col, int m, int n, double diag, int* hout, int* gout,
+                       int* g2out, int* f1, int* f2, K3Best* best)
+{
+    const int r = n - m;
+    const int* mx = gout;
+    if (!first_row && p.Noll == 3 && k3_val(g2out) > k3_val(mx)) mx = g2out;
+    if (!first_col) {
+        if (k3_val(f1) >= k3_val(mx)) mx = f1;
+        if (p.Noll == 3 && k3_val(f2) >= k3_val(mx)) mx = f2;
+    }
+    int* bx = k3s_box(p, hout);
+    if (k3_val(mx) > k3_val(hout)) {            // non-diagonal
+        k3s_copy(p, hout, mx);
+        if (bx[0] > r) bx[0] = r;
+        if (bx[1] < r) bx[1] = r;
+    } else if (k3_val(hout) > diag) {
+        if (diag == 0) { bx[0] = bx[1] = r; bx[2] = m; bx[3] = n; }     // new colony
+        if (k3_val(hout) > best->val) {         // max local score (strict: the first cell of this thread's rows wins)
+            best->val = k3_val(hout);
+            best->mlb = bx[2]; best->nlb = bx[3]; best->mrb = m + 1; best->nrb = n + 1; best->lwr = bx[0]; best->upr = bx[1];
+        }
+    }
+    if (k3_val(hout) < 0) {                     // reset to blank: h, f1 (twice in the reference), f2 and g2 -- not g
+        k3s_blank(p, hout, 0);
+        k3s_blank(p, f1, 0);
+        if (p.Noll == 3) { k3s_blank(p, f2, 0); k3s_blank(p, g2out, 0); }
+    }
+}
+// row-major order of two candidates for colony 0: the reference visits cells row by row and replaces on `>`
+PG_HD bool k3s_better(const K3Best& x, const K3Best& y)
+{
+    if (x.val != y.val) return x.val > y.val;
+    if (x.mrb != y.mrb) return x.mrb < y.mrb;
+    return x.nrb < y.nrb;
 }
 
 // One DP cell of Aln2b1::forwardB_ng (src/fwd2b1.cc:176-249, global mode): a gap opens on >=, the

@@ -34,8 +34,8 @@ static int emul(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int Tsig
         if (la > RCS || lb > RCS) return -2;
     }
     const int st = k3_stride(p.capa, p.capb);
-#define RESET(ptr) do { if (RL) k3r_reset<RCAP, RMODE>(ptr); else k3_reset(p, ptr); } while (0)
-#define RCOPY(d, s) do { if (RL) k3r_copy_words(d, s, st); else k3_copy(p, d, s); } while (0)
+#define RESET(ptr) do { if (RL) k3r_reset<RCAP, RMODE>(ptr); else if (p.swg) k3s_blank(p, ptr, K3_NEVSEL); else k3_reset(p, ptr); } while (0)
+#define RCOPY(d, s) do { if (RL) k3r_copy_words(d, s, st); else if (p.swg) k3s_copy(p, d, s); else k3_copy(p, d, s); } while (0)
     std::vector<int> mem((size_t)st * (3 * (LS + 2) + (LQ + 2) + 9 * T + 2) + 4);
     int* base = mem.data();
     while (((uintptr_t)base & 15) != 0) ++base;     // records are read and written 16 bytes at a time in the RL form
@@ -56,17 +56,24 @@ static int emul(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int Tsig
     vmf.push_back({0, 0, 0});                       // skip 0-th record (fwd2c.h:361)
     vmf.push_back({al, bl, 0});                     // origin (initB)
     // origin + boundary chains
-    k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : (p.rect ? 0 : K3_DIAG), 0); K3_PTR(colH) = 1;
+    k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : ((p.rect || p.swg) ? 0 : K3_DIAG), 0); K3_PTR(colH) = 1;
+    const int r0 = bl - al;
+    if (p.swg) { int* bx = k3s_box(p, colH); bx[0] = bx[1] = r0; bx[2] = al; bx[3] = bl; }
     RCOPY(rowH, colH);
     { int rr = LS < p.up ? LS : p.up; for (int k = 1; k <= rr; ++k) {
-        if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true);
+        if (p.swg) {        // initC (fwd2c.h:186-194): blank records on the diagonals of the first row
+            int* h = rowH + (size_t)k * st; k3s_blank(p, h, 0); int* bx = k3s_box(p, h); bx[0] = bx[1] = r0 + k; bx[2] = al; bx[3] = bl + k;
+        } else if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true);
         else if (RL) k3r_boundary_row<RCAP, RCS, RMODE>(p, ablk_p, bblk_p + (size_t)k * BW, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
         else k3_boundary_row(p, a, b, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st); } }
     { int rr = LQ < -p.lw ? LQ : -p.lw; for (int k = 1; k <= rr; ++k) {
-        if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false);
+        if (p.swg) {        // (:196-206): ... and of the first column
+            int* h = colH + (size_t)k * st; k3s_blank(p, h, 0); int* bx = k3s_box(p, h); bx[0] = bx[1] = r0 - k; bx[2] = al + k; bx[3] = bl;
+        } else if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false);
         else if (RL) k3r_boundary_col<RCAP, RCS, RMODE>(p, ablk_p + (size_t)k * BW, bblk_p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
         else k3_boundary_col(p, a, b, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st); } }
     std::vector<double> pua(T, 0.0);
+    std::vector<K3Best> best(T, K3Best{0.0, 0, 0, 0, 0, 0, 0});
     int last_ptr = 0; double last_val = 0;
     // Continuous schedule (k3_groups.cu): thread t takes rows t, t+T, t+2T, ...; its k-th row meets column n
     // at global step S = k*P + t + n with the period P = max(LS, T + 4), so a thread starts its next row
@@ -106,7 +113,15 @@ static int emul(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int Tsig
             int* g2out = pubG2 + ((size_t)(S & 1) * T + t) * st;
             const double dab = k3_sim(a, b, p, ia, ib);
             bool rec;
-            if (p.mode == 3) rec = k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out);
+            if (p.swg) {
+                const int ra = r + r0;
+                const double diag = k3_val(hdiag);
+                k3s_part_diag(p, a, b, ia, ib, ra, dab, hdiag, hout);
+                k3s_part_vert(p, a, b, ia, ib, ra, first_row, habove, gabove, g2above, gout, g2out);
+                k3s_part_hori(p, a, b, ia, ib, ra, first_col, hleft, F1 + (size_t)t * st, F2 + (size_t)t * st);
+                k3s_combine(p, first_row, first_col, m + al, n + bl, diag, hout, gout, g2out, F1 + (size_t)t * st, F2 + (size_t)t * st, &best[t]);
+                rec = false;
+            } else if (p.mode == 3) rec = k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, F1 + (size_t)t * st, F2 + (size_t)t * st, hout, gout, g2out);
             else if (RL) rec = k3r_cell<RCAP, RCS, RMODE>(p, ablk_p + (size_t)ia * BW, bblk_p + (size_t)ib * BW, a.nils != 0, first_row, first_col,
                                                           dab, &pua[t], hdiag, habove, gabove, g2above, hleft, F1 + (size_t)t * st,
                                                           F2 + (size_t)t * st, hout, gout, g2out, black, st);
@@ -124,6 +139,14 @@ static int emul(const K3Group* ga, const K3Group* gb, const K3Prm* prm, int Tsig
                 if (p.Noll == 3) RCOPY(rowG2 + (size_t)(n + 1) * st, g2out);
             }
         }
+    }
+    if (p.swg) {            // colony 0: the first cell in row-major order that holds the maximum
+        K3Best c0 = best[0];
+        for (int t = 1; t < T; ++t) if (k3s_better(best[t], c0)) c0 = best[t];
+        *score = c0.val;
+        if (cap < 3) return -1;
+        out_pts[0] = c0.mlb; out_pts[1] = c0.nlb; out_pts[2] = c0.mrb; out_pts[3] = c0.nrb; out_pts[4] = c0.lwr; out_pts[5] = c0.upr;
+        return 3;
     }
     vmf.push_back({LQ + al, LS + bl, last_ptr});
     *score = last_val;

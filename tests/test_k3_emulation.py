@@ -26,14 +26,14 @@ class K3Prm(C.Structure):
                 ("bgop", C.c_double), ("u2divu1", C.c_double), ("v2divv1", C.c_double), ("gop1", C.c_double),
                 ("gep1", C.c_double), ("gop2", C.c_double), ("gep2", C.c_double), ("ltg_a", C.c_double), ("ltg_b", C.c_double),
                 ("rtg_a", C.c_double), ("rtg_b", C.c_double), ("last_c", C.c_int32), ("last_r", C.c_int32),
-                ("novmf", C.c_int32), ("origin_r", C.c_int32), ("rl", C.c_int32), ("rect", C.c_int32)]
+                ("novmf", C.c_int32), ("origin_r", C.c_int32), ("rl", C.c_int32), ("rect", C.c_int32), ("swg", C.c_int32), ("pad3", C.c_int32)]
 
 
 @pytest.fixture(scope="module")
 def emul3():
     src = os.path.join(ROOT, "tests", "host_emul", "k3_emul.cc")
     out = os.path.join(ROOT, "tests", "host_emul", "libk3emul.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
+    subprocess.check_call(["g++", "-O2", "-fno-strict-aliasing", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
     L = C.CDLL(out)
     L.k3_emul_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     L.k3_emul_align_rl.argtypes = L.k3_emul_align.argtypes + [C.c_int]
@@ -101,6 +101,36 @@ def test_wavefront_emulation_matches_reference(emul3, name):
             assert [[int(out[2 * i]), int(out[2 * i + 1])] for i in range(n)] == want["skl"], (rl, T)
             ran += 1
     assert ran or need > 6
+
+
+@pytest.mark.parametrize("name", golden_names("galign_swg_"))
+def test_smith_waterman_wavefront_emulation(emul3, name):
+    """The Smith-Waterman form of the K3 cell (k3s_* in k3_core.cuh: forwardC without secondary colonies) through the
+    wavefront emulation: best local score and box of colony 0 against the reference's swg1st, for every stripe
+    height and thread order (the per-thread maxima must reduce to the first maximum in row-major order)."""
+    d = golden(name)
+    pm, pc, h = d["pwdm"], d["pwdc"], d["header"]
+    A, B = G.stage_pair(d["groups"][0], d["groups"][1], pm["a_mode"], pm["b_mode"], d["matrix"], dxd=(pm["DvsP"] == 0))
+    lw, up, _ = d["window"]
+    r0 = B["left"] - A["left"]
+    mode = G.K3_MODE[pm["alnmode"]]
+    capa, capb = max(A["hetero"], 0) + 3, max(B["hetero"], 0) + 3
+    if mode == 4:
+        capa, capb = (A["many"] + 1) // 2 + 1, (B["many"] + 1) // 2 + 1
+    bgep, lgep, bgop, lgop = pc["BasicGEP"], pc["LongGEP"], pc["BasicGOP"], pc["LongGOP"]
+    p = K3Prm(mode, pm["Noll"], pm["codonk1"], lw - r0, up - r0, capa, capb + 4,        # + 4: the box words
+              A["vec"].shape[1], float(np.float32(float(h["u"]))), -float(np.float32(float(h["v"]))), pc["vgop1"],
+              lgep / bgep if bgep < 0 else 0.0, lgop / bgop if bgop < 0 else 0.0, bgop, bgep, lgop, lgep, 1.0, 1.0)
+    p.swg, p.origin_r = 1, r0
+    want = d["swg"]
+    for T in (256, 7, 33, -33, -5):
+        out = np.zeros(16, np.int32)
+        sc = C.c_double(0)
+        ga, gb = _k3group(A), _k3group(B)
+        n = emul3.k3_emul_align(C.byref(ga), C.byref(gb), C.byref(p), T, A["left"], B["left"], C.byref(sc), out.ctypes.data, 8)
+        assert n == 3, T
+        assert abs(sc.value - want["val"]) <= 1e-5 * max(1.0, abs(want["val"])), T
+        assert [int(x) for x in out[:6]] == [want[k] for k in ("mlb", "nlb", "mrb", "nrb", "lwr", "upr")], T
 
 
 def test_aln2b1_cell_emulation(emul3, oracle):

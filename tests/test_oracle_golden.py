@@ -97,6 +97,22 @@ def test_group_alignment_bit_exact(oracle, name):
     assert hs == g["homscore"]["score"] and rr == g["homscore"]["rr"]
 
 
+@pytest.mark.parametrize("name", golden_names("galign_swg_"))
+def test_group_smith_waterman_bit_exact(oracle, name):
+    """orc_swg_groups (swg1stC<SwgDPunit*>: Fwd2c::initC + forwardC restated for algmode.mlt <= 1) on the reference's
+    staged inputs: the best local score and the box of colony 0 identical to the reference's swg1st."""
+    g = golden(name)
+    A, B = oracle.group_arrays(g["groups"][0]), oracle.group_arrays(g["groups"][1])
+    val, box, cells = oracle.swg_groups(A, B, np.array(g["matrix"]), oracle.gparams_from_dump(g))
+    want = g["swg"]
+    assert want["size"] == 0                    # mlt = 1: colony 0 only
+    assert val == want["val"]
+    assert box == {k: want[k] for k in box}
+    lw, up, _ = g["window"]
+    a, b = g["groups"]
+    assert cells == sum(max(0, min(m + up + 1, b["right"]) - max(m + lw, b["left"])) for m in range(a["left"], a["right"]))
+
+
 @pytest.mark.parametrize("name", golden_names("alignb_"))
 def test_aln2b1_bit_exact(oracle, name):
     """orc_align_b1 (Aln2b1: alignB_ng + HomScoreB_ng restated) against the reference."""

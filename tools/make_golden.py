@@ -186,6 +186,33 @@ def galign_rect_cases():
     galign_case("galign_rect_single_rag62", [rag[6]], [rag[2]], mtx="blosum62", bnd=0)            # 100 x 120, far off the main diagonal
 
 
+def galign_swg_cases():
+    """Smith-Waterman on groups (algmode.lcl = 16, mlt = 1): swg1st -> Fwd2c<SwgDPunit*>::forwardC gives the best local
+    score and its box (colony 0); swg2nd aligns inside the box (align2).  The goldens also hold the banded global
+    results of the same inputs."""
+    import gen_msa
+    fam = gen_msa.synth_msa(64, 90, 0.1, 0.5, 41)
+    hh = gen_msa.synth_msa(40, 80, 0.3, 0.8, 45, indel_events=12.0)
+    A, B = gen_msa.split_family(fam, range(0, 12), range(12, 17))
+    galign_case("galign_swg_gpf_prof12_raw5_wt", A, B, wt=1, lcl=16)
+    A, B = gen_msa.split_family(fam, range(0, 8), range(8, 14))
+    galign_case("galign_swg_gpf_twopiece", A, B, ls=3, wt=1, lcl=16)
+    A, B = gen_msa.split_family(fam, range(0, 10), [10])
+    galign_case("galign_swg_hlf_prof10_single", A, B, lcl=16)
+    galign_case("galign_swg_rhf_single_prof10_f32", B, A, flavour="f", wt=1, lcl=16)
+    A, B = gen_msa.split_family(hh, range(0, 22), range(22, 40))
+    galign_case("galign_swg_gpf_highhetero", A, B, wt=1, sh=-40, lcl=16)
+    A, B = gen_msa.split_family(hh, range(0, 2), range(2, 4))
+    galign_case("galign_swg_ntv_2x2_wt", A, B, wt=1, lcl=16)
+    gl = gen_msa.synth_msa(7, 80, 0.2, 0.6, 43, gapless=True)
+    galign_case("galign_swg_ngp_gapless4x3", gl[:4], gl[4:], mtx="blosum62", lcl=16)
+    rnd = gen_synth.synth_set(6, 150, 0.9, 0.9, 77)                                # unrelated: a small island, many resets
+    galign_case("galign_swg_single_unrelated", [rnd[0]], [rnd[4]], flavour="f", mtx="blosum62", lcl=16)
+    rag = [s[a:len(s) - b] for s, a, b in zip(gen_synth.synth_set(10, 160, 0.1, 0.6, 41),
+                                             [0, 30, 0, 45, 10, 0, 60, 5, 0, 25], [0, 0, 40, 20, 0, 55, 0, 35, 15, 0])]
+    galign_case("galign_swg_single_rag03_twopiece", [rag[0]], [rag[3]], mtx="blosum62", ls=3, u1=1, sh=-20, lcl=16)
+
+
 def alignb_case(name, seqs, flavour="f", **kv):
     """Aln2b1: alignB_ng (stdskl-normalised corner list) + HomScoreB_ng per pair."""
     os.makedirs(TMP, exist_ok=True)
@@ -272,6 +299,7 @@ def main():
     align_case("align_c1_ce13a", sample_pair(), sh=-50)
     galign_cases()
     galign_rect_cases()
+    galign_swg_cases()
     alignb_cases()
     dna_pair_cases()
 
@@ -286,8 +314,11 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "galign":
         galign_cases()
         galign_rect_cases()
+        galign_swg_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == "rect":
         galign_rect_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "swg":
+        galign_swg_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == "lcl":      # only the lcl cases
         p24_ = gen_synth.synth_set(24, 120, 0.1, 0.6, 11)
         rag_ = [s[:k] for s, k in zip(gen_synth.synth_set(20, 300, 0.1, 0.7, 21),

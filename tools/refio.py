@@ -144,6 +144,18 @@ def parse_galign(text):
             r.setdefault("mt", []).append(dict(score=float(t[2]), skl=pts))
         elif t[0] == "homscore":
             r["homscore"] = dict(score=float(t[1]), rr=[int(t[2]), int(t[3])])
+        elif t[0] == "swg":
+            if t[1] == "none":
+                r["swg"] = None
+            else:
+                r["swg"] = dict(size=int(t[2]), val=float(t[4]), **{t[k]: int(t[k + 1]) for k in range(5, len(t), 2)})
+        elif t[0] == "swg2nd":
+            pts = None
+            if t[2] == "skl" and t[3] != "0":
+                n = int(t[3])
+                v = [int(x) for x in t[6:6 + 2 * n]]
+                pts = [list(x) for x in zip(v[0::2], v[1::2])]
+            r["swg2nd"] = dict(score=float(t[1]), skl=pts)
         elif t[0] in ("alignc", "align2"):
             off = 1 if t[0] == "alignc" else 3
             scr = float(t[off])
