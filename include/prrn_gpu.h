@@ -169,6 +169,16 @@ int pg_align_groups(pg_context *ctx, const pg_group *a, const pg_group *b, const
  * row; :468-469), rr[1] = the end diagonal. */
 int pg_score_groups(pg_context *ctx, const pg_group *a, const pg_group *b, const pg_gparams *prm, int64_t npairs,
                     double *out_scores, int64_t *out_rr);
+/* ---- per-call level, groups, Smith-Waterman: stands behind
+ *   template<class recd_t> Colonies* swg1stC(mSeq* seqs[2], PwdM* pwd, WINDOW* pwdw = 0)   src/fwd2c.h:697-701
+ * for recd_t = SwgDPunit | SwgDPunit_hf | SwgDPunit_pf | SwgDPunit_nv as swg1st dispatches it (src/maln2.cc:1975-2010;
+ * callers: aln.cc:287-311 under algmode.lcl & 16), i.e. Fwd2c::initC + forwardC (src/fwd2c.h:178-207,483-659), for
+ * algmode.mlt <= 1: no secondary colonies, the result is colony 0 = the best local score and the box of its path.
+ * Same inputs as pg_align_groups (alnmode 6 .. 10).  out_val[p] = COLONY::val, out_box[6 p ..] = mlb nlb mrb nrb lwr upr
+ * (src/aln.h:150-160).  The second pass (swg2ndC: align2 inside the box) is pg_align_groups on that window.
+ * algmode.mlt > 1 (several colonies, with their sequential garbage collection) is not built. */
+int pg_local_groups(pg_context *ctx, const pg_group *a, const pg_group *b, const pg_gparams *prm, int64_t npairs,
+                    double *out_val, int32_t *out_box);
 /* DP cells the reference visits for one group pair (band from stripe(), src/aln2.cc:156-174). */
 int64_t pg_group_cells(const pg_group *a, const pg_group *b, int32_t sh);
 

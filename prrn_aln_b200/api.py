@@ -116,6 +116,7 @@ def load_library():
     L.pg_align_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32))]
     L.pg_score_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.pg_local_groups.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.pg_group_cells.restype = C.c_int64
     L.pg_group_cells.argtypes = [C.POINTER(_PgGroup), C.POINTER(_PgGroup), C.c_int32]
     L.pg_last_kernel_ms.restype = C.c_double
@@ -291,6 +292,18 @@ class Context:
         rr = np.zeros((n, 2), np.int64)
         self._check(self.L.pg_score_groups(self.h, ga, gb, gp, n, out.ctypes.data, rr.ctypes.data))
         return out, rr
+
+    def local_groups(self, pairs):
+        """swg1stC<SwgDPunit*>(seqs, pwd) for a batch (reference src/fwd2c.h:697-701: Fwd2c::forwardC, algmode.mlt <= 1):
+        Smith-Waterman on groups.  Returns (best local scores float64, boxes int32 (n x 6): mlb nlb mrb nrb lwr upr)."""
+        n = len(pairs)
+        ga = (_PgGroup * max(n, 1))(*[_pg_group(p[0]) for p in pairs])
+        gb = (_PgGroup * max(n, 1))(*[_pg_group(p[1]) for p in pairs])
+        gp = (GParams * max(n, 1))(*[p[2] for p in pairs])
+        out = np.empty(n, np.float64)
+        box = np.zeros((n, 6), np.int32)
+        self._check(self.L.pg_local_groups(self.h, ga, gb, gp, n, out.ctypes.data, box.ctypes.data))
+        return out, box
 
     # -- batch level: calcdist(DynScr) ------------------------------------------------------------
     def calcdist(self, seqs, prm, mtx, k_begin=0, k_end=None, out=None):

@@ -156,9 +156,12 @@ __device__ __noinline__ void cl_release(unsigned empty_addr, int S)
 // records of CTA c live in its own part of the store (id = c * vmf_cap + local id).
 // RL (register lists, k3r_core.cuh): 0 = the list-walking cell of k3_core.cuh; 4 / 6 / 8 = words per dynamic list of the
 // branch-free register form (record modes 1 and 2, role-split shared-memory kernels, TGRL rows per CTA).
-template <int TG, bool SPLIT, int MODE, bool SM, bool CL, int RL>
+// SWG: the Smith-Waterman form (forwardC without secondary colonies, k3s_* in k3_core.cuh) -- a compile-time switch
+// so that the banded kernels carry none of it; it runs the one-thread-per-row geometry.
+template <int TG, bool SPLIT, int MODE, bool SM, bool CL, int RL, bool SWG = false>
 __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_kernel(const K3Args a)
 {
+    static_assert(!SWG || (!SPLIT && !CL && !RL && MODE != 3), "Smith-Waterman: one thread per row, single CTA, list-walking cell");
     static_assert(!CL || (SPLIT && SM), "the cluster variant is the role-split shared-memory kernel");
     static_assert(!SPLIT || CL || TG == CTA || RL, "role-split without clusters runs 3 x 256 threads");
     static_assert(!RL || (SPLIT && SM && (MODE == 1 || MODE == 2) && TG == TGRL), "register lists: modes 1 / 2, role-split, shared memory");
@@ -184,8 +187,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
 
 #define GSYNC() do { if (CL) cg::this_cluster().sync(); else if (SPLIT) __syncthreads(); else group_sync<TG>(g); } while (0)
 #define GSTEP() do { if (SPLIT) __syncthreads(); else group_sync<TG>(g); } while (0)       /* end of one step */
-#define RESET(ptr) do { if (RL) k3r_reset<RCAP, RMODE>(ptr); else k3_reset(p, ptr); } while (0)
-#define RCOPY(d, s) do { if (RL) k3r_copy_words(d, s, st); else k3_copy(p, d, s); } while (0)
+#define RESET(ptr) do { if (RL) k3r_reset<RCAP, RMODE>(ptr); else if (SWG) k3s_blank(p, ptr, K3_NEVSEL); else k3_reset(p, ptr); } while (0)
+#define RCOPY(d, s) do { if (RL) k3r_copy_words(d, s, st); else if (SWG) k3s_copy(p, d, s); else k3_copy(p, d, s); } while (0)
     // CL: ring hand-over (see above): full[slot] counts the push of the CTA above, empty[slot] the release by the CTA below
     __shared__ __align__(8) unsigned long long sm_full[XD], sm_empty[XD];
     for (;;) {
@@ -266,19 +269,27 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             vmf[0].m = 0; vmf[0].n = 0; vmf[0].p = 0;                       // skip 0-th record (:361)
             vmf[1].m = P_.al; vmf[1].n = P_.bl; vmf[1].p = 0;                 // origin
             sm_vmf[g] = 2;
-            k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : (p.rect ? 0 : K3_DIAG), 0); K3_PTR(colH) = p.novmf ? p.origin_r : 1;
+            k3_setval(colH, 0); k3_setdg(colH, p.mode == 3 ? K3_NEWD : ((p.rect || SWG) ? 0 : K3_DIAG), 0); K3_PTR(colH) = p.novmf ? p.origin_r : 1;
+            if (SWG) { int* bx = k3s_box(p, colH); bx[0] = bx[1] = p.origin_r; bx[2] = P_.al; bx[3] = P_.bl; }
             const int rr = LQ < -p.lw ? LQ : -p.lw;
             for (int k = 1; k <= rr; ++k) {
-                if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false);
+                if (SWG) {        // initC (fwd2c.h:196-206): blank records on the diagonals below the origin
+                    int* h = colH + (size_t)k * st; k3s_blank(p, h, 0);
+                    int* bx = k3s_box(p, h); bx[0] = bx[1] = p.origin_r - k; bx[2] = P_.al + k; bx[3] = P_.bl;
+                } else if (p.mode == 3) k3_boundary_b1(p, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st, false);
                 else if (RL) k3r_boundary_col<RCAP, RCS, RMODE>(p, A.blk + (size_t)k * BW, B.blk, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
                 else k3_boundary_col(p, A, B, k, colH + (size_t)k * st, colH + (size_t)(k - 1) * st);
             }
         }
         if (t == TG / 2 && role == (SPLIT ? 1 : 0) && crank == 0) {
-            k3_setval(rowH, 0); k3_setdg(rowH, p.mode == 3 ? K3_NEWD : (p.rect ? 0 : K3_DIAG), 0); K3_PTR(rowH) = p.novmf ? p.origin_r : 1;
+            k3_setval(rowH, 0); k3_setdg(rowH, p.mode == 3 ? K3_NEWD : ((p.rect || SWG) ? 0 : K3_DIAG), 0); K3_PTR(rowH) = p.novmf ? p.origin_r : 1;
+            if (SWG) { int* bx = k3s_box(p, rowH); bx[0] = bx[1] = p.origin_r; bx[2] = P_.al; bx[3] = P_.bl; }
             const int rr = LS < p.up ? LS : p.up;
             for (int k = 1; k <= rr; ++k) {
-                if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true);
+                if (SWG) {        // initC (:186-194): ... and above it
+                    int* h = rowH + (size_t)k * st; k3s_blank(p, h, 0);
+                    int* bx = k3s_box(p, h); bx[0] = bx[1] = p.origin_r + k; bx[2] = P_.al; bx[3] = P_.bl + k;
+                } else if (p.mode == 3) k3_boundary_b1(p, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st, true);
                 else if (RL) k3r_boundary_row<RCAP, RCS, RMODE>(p, A.blk, B.blk + (size_t)k * BW, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
                 else k3_boundary_row(p, A, B, k, rowH + (size_t)k * st, rowH + (size_t)(k - 1) * st);
             }
@@ -307,6 +318,8 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             int* const f1 = F1 + (size_t)t * st;
             int* const f2 = F2 + (size_t)t * st;
             double pua = 0;
+            K3Best best = {0.0, 0, 0, 0, 0, 0, 0};         // Smith-Waterman: this thread's candidate for colony 0
+            double diag_v = 0;
             // ring: records 1 and 2 of the first parked row (the boundary row) before the first step
             if (ring_ok && role == 0 && crank == 0) {
                 for (int w = t; w < pf_words; w += TG) {
@@ -402,6 +415,14 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                     const int* hleft = n == 0 ? colL : (left_in ? pubH + ((size_t)g3a * TG + t) * st : black);
                     if (!SPLIT) {
                         const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
+                        if (SWG) {
+                            const int ra = r + p.origin_r;
+                            diag_v = k3_val(hdiag);
+                            k3s_part_diag(p, A, B, ia, ib, ra, dab, hdiag, hout);
+                            k3s_part_vert(p, A, B, ia, ib, ra, m == 0, habove, gabove, g2above, gout, g2out);
+                            k3s_part_hori(p, A, B, ia, ib, ra, n == 0, hleft, f1, f2);
+                            k3s_combine(p, m == 0, n == 0, m + P_.al, n + P_.bl, diag_v, hout, gout, g2out, f1, f2, &best);
+                        } else
                         rec = p.mode == 3
                             ? k3_cell_b1(p, dab, hdiag, habove, gabove, g2above, hleft, f1, f2, hout, gout, g2out)
                             : k3_cell_mono(p, A, B, ia, ib, fr, fc, dab, &pua, hdiag, habove, gabove, g2above, hleft, f1, f2,
@@ -422,6 +443,14 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                         } else {
                             k3r_part_hori<RCAP, RCS, RMODE>(p, ablk, bblk, n == 0, hleft, f1, f2);
                         }
+                    } else if (SWG) {
+                        const int ra = r + p.origin_r;
+                        if (role == 0) {
+                            const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
+                            diag_v = k3_val(hdiag);
+                            k3s_part_diag(p, A, B, ia, ib, ra, dab, hdiag, hout);
+                        } else if (role == 1) k3s_part_vert(p, A, B, ia, ib, ra, m == 0, habove, gabove, g2above, gout, g2out);
+                        else k3s_part_hori(p, A, B, ia, ib, ra, n == 0, hleft, f1, f2);
                     } else if (role == 0) {
                         const double dab = P_.simmat ? __ldg(P_.simmat + (size_t)m * LS + n) : k3_sim(A, B, p, ia, ib);
                         k3_part_diag(p, A, B, ia, ib, dab, hdiag, hout);
@@ -435,7 +464,9 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                 if (SPLIT) {
                     __syncthreads();                                // the three candidates are in shared memory
                     TM_ADD(tm_b1);
-                    if (active && role == 0 && p.mode != 3)
+                    if (active && role == 0 && SWG)
+                        k3s_combine(p, m == 0, n == 0, m + P_.al, n + P_.bl, diag_v, hout, gout, g2out, f1, f2, &best);
+                    else if (active && role == 0 && p.mode != 3)
                         rec = RL ? k3r_combine(p, m == 0, n == 0, hout, gout, g2out, f1, f2, st) : k3_combine(p, m == 0 && !p.rect, n == 0 && !p.rect, hout, gout, g2out, f1, f2);
                     TM_ADD(tm_cmb);
                 }
@@ -493,6 +524,20 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                        total_steps, LQ, LS, tm_wait / 1965., tm_c1 / 1965., tm_b1 / 1965., tm_cmb / 1965., tm_vmf / 1965., tm_c2 / 1965., tm_push / 1965., tm_b2 / 1965.);
 #endif
             if (CL) cg::this_cluster().sync();      // the last cell, the path parts and the parked rows of every CTA
+            if (SWG) {        // colony 0 (Colonies::at(0)): the first cell in row-major order that holds the maximum
+                K3Best* const sb = reinterpret_cast<K3Best*>(pubH);         // the wavefront records are done with
+                GSYNC();
+                if (role == 0) sb[t] = best;
+                GSYNC();
+                if (t == 0 && role == 0 && crank == 0) {
+                    K3Best c0 = sb[0];
+                    for (int i = 1; i < TG; ++i) if (k3s_better(sb[i], c0)) c0 = sb[i];
+                    int* out = a.out_pts + 2 * P_.out_off;
+                    out[0] = c0.mlb; out[1] = c0.nlb; out[2] = c0.mrb; out[3] = c0.nrb; out[4] = c0.lwr; out[5] = c0.upr;
+                    a.out_cnt[pi] = 3;
+                    a.out_score[pi] = c0.val;
+                }
+            }
         }
         // ---- Aln2b1::lastB_ng (fwd2b1.cc:100-143): trailing gaps at true sequence ends cost rtgapf times the
         //      penalty: the last column is relaxed downwards, then the last row rightwards, in place
@@ -540,7 +585,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
             sm_last_val[g] = k3_val(h9);
         }
         // ---- final record + Vmf::traceback (fwd2c.h:475-481, vmf.cc:103-119)
-        if (t == 0 && role == 0 && crank == 0) {
+        if (t == 0 && role == 0 && crank == 0 && !SWG) {
             int* out = a.out_pts + 2 * P_.out_off;
             int cnt = 0;
             const int nrec = sm_vmf[g];
@@ -704,6 +749,21 @@ cudaError_t k3_launch(const K3Args& a, int tg, int mode, int grid_blocks, cudaSt
     // a.all_sm: every pair of the launch keeps its wavefront records and prefetch ring in shared memory for this
     // tg (k3_all_sm): the variant whose cell operands are all shared-memory records.  Otherwise (very long
     // gap-state lists) the generic-address variant, one thread per row, 256 rows per stripe.
+    if (a.swg) {           // Smith-Waterman pairs: their own instantiations of the generic one-thread-per-row kernel
+        auto go = [&](auto kern) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+            if (e != cudaSuccess) return e;
+            kern<<<grid_blocks, CTA, a.smem_bytes, st>>>(a);
+            return cudaGetLastError();
+        };
+        switch (mode) {
+        case 0: return go(k3_fill_kernel<256, false, 0, false, false, 0, true>);
+        case 1: return go(k3_fill_kernel<256, false, 1, false, false, 0, true>);
+        case 2: return go(k3_fill_kernel<256, false, 2, false, false, 0, true>);
+        case 4: return go(k3_fill_kernel<256, false, 4, false, false, 0, true>);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     if (a.rl) return mode == 1 ? launch_rl_cap<1>(a, grid_blocks, st) : launch_rl_cap<2>(a, grid_blocks, st);
     if (!a.all_sm) return launch_tg<256, false, false>(a, mode, grid_blocks, st);
     if (getenv("PG_K3_GENERIC") && tg != 768 && tg != 128) return launch_tg<256, false, false>(a, mode, grid_blocks, st);

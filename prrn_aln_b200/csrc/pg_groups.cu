@@ -124,7 +124,7 @@ struct PgTerm {
 
 static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
                                double* out_scores, int64_t** out_offs, pg_skl** out_pts, const PgTerm* term,
-                               int64_t* out_rr = nullptr, bool score_only = false);
+                               int64_t* out_rr = nullptr, bool score_only = false, bool swg = false);
 
 extern "C" int pg_align_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
                                double* out_scores, int64_t** out_offs, pg_skl** out_pts)
@@ -143,9 +143,28 @@ extern "C" int pg_score_groups(pg_context* c, const pg_group* a, const pg_group*
     return rc;
 }
 
+// swg1stC<SwgDPunit | _hf | _pf | _nv> (src/fwd2c.h:697-701) for algmode.mlt <= 1: Fwd2c::forwardC without secondary
+// colonies; per pair the best local score and the box of colony 0 (src/aln.h:150-160)
+extern "C" int pg_local_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
+                               double* out_val, int32_t* out_box)
+{
+    if (c && npairs > 0 && !out_box) return pg_int_fail(c, PG_ERR_ARG, "pg_local_groups: NULL output");
+    int64_t* offs = nullptr;
+    pg_skl* pts = nullptr;
+    const int rc = pg_int_align_groups(c, a, b, prm, npairs, out_val, &offs, &pts, nullptr, nullptr, false, true);
+    if (!rc)
+        for (int64_t i = 0; i < npairs; ++i) {      // the kernel returns the box as three "corners"
+            const pg_skl* q = pts + offs[i];
+            int32_t* o = out_box + 6 * i;
+            o[0] = q[0].m; o[1] = q[0].n; o[2] = q[1].m; o[3] = q[1].n; o[4] = q[2].m; o[5] = q[2].n;
+        }
+    free(offs); free(pts);
+    return rc;
+}
+
 static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group* b, const pg_gparams* prm, int64_t npairs,
                                double* out_scores, int64_t** out_offs, pg_skl** out_pts, const PgTerm* term,
-                               int64_t* out_rr, bool score_only)
+                               int64_t* out_rr, bool score_only, bool swg)
 {
     if (!c) return PG_ERR_ARG;
     if (npairs < 0 || !out_offs || !out_pts || (npairs && (!a || !b || !prm || !out_scores)))
@@ -166,7 +185,9 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
     std::vector<K3Pair> pairs(npairs);
     std::vector<int64_t> cells(npairs), outoff(npairs + 1);
     size_t blob = 0, arena_words = 0, wave_bytes = 0;
-    const int tg_sel = k3_pick_tg(npairs, c->sm_count);     // threads per alignment (768 = 3 roles x 256 rows)
+    const bool nopath = score_only || swg;
+    // threads per alignment (768 = 3 roles x 256 rows); Smith-Waterman runs the one-thread-per-row kernel
+    const int tg_sel = swg ? 256 : k3_pick_tg(npairs, c->sm_count);
     const int tg = tg_sel == 768 ? 256 : tg_sel;            // rows per stripe
     const int ngrp = k3_threads() / tg;                     // alignments in flight per CTA
     int64_t max_cells = 0;
@@ -181,7 +202,7 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
     int rl_cap[5] = {0, 0, 0, 0, 0};
     {
         const char* ev = getenv("PG_K3_RL");
-        const bool rl_on = tg_sel == 768 && ev && ev[0] == '1';
+        const bool rl_on = tg_sel == 768 && ev && ev[0] == '1' && !swg;
         int need[5] = {0, 0, 0, 0, 0};
         bool ok[5] = {false, rl_on, rl_on, false, false};
         for (int64_t i = 0; i < npairs && rl_on; ++i) {
@@ -219,6 +240,10 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
             return pg_int_fail(c, PG_ERR_UNSUPPORTED, "pg_align_groups: alnmode is not one of NGP_ALN / NGP_ALB / HLF_ALB / RHF_ALB / "
                                                       "GPF_ALB / NTV_ALB (the rectangle modes with gap profiles, local and spliced "
                                                       "modes are not built yet)");
+        }
+        if (swg && (rect || mode == 3)) {
+            free(offs);
+            return pg_int_fail(c, PG_ERR_UNSUPPORTED, "pg_local_groups: alnmode is not one of NGP_ALB / HLF_ALB / RHF_ALB / GPF_ALB / NTV_ALB");
         }
         if (rect && (score_only || B.left != 0)) {
             free(offs);
@@ -258,6 +283,8 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
             kp.capa = (A.many + 1) / 2 + 1; kp.capb = (B.many + 1) / 2 + 1;     // 16-bit run lengths, two per word
         }
         kp.rl = rl; kp.rect = rect ? 1 : 0;
+        kp.swg = swg ? 1 : 0; kp.pad3 = 0;
+        if (swg) kp.capb += 4;          // the box of a Smith-Waterman record: its last four words (k3s_box)
         if (rl) {               // the records of the register-list form: 4 header words + rl words per list, a multiple of 4
             kp.capa = rl;
             kp.capb = mode == 2 ? rl : k3r_rec_words(rl, 1) - 4 - rl;
@@ -269,7 +296,7 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         kp.gop1 = P.BasicGOP; kp.gep1 = P.BasicGEP; kp.gop2 = P.LongGOP; kp.gep2 = P.LongGEP;
         kp.ltg_a = kp.ltg_b = kp.rtg_a = kp.rtg_b = 1.0;
         kp.last_c = kp.last_r = 0;
-        kp.novmf = score_only ? 1 : 0;
+        kp.novmf = nopath ? 1 : 0;
         kp.origin_r = B.left - A.left;
         if (score_only && mode == 3) {
             free(offs);
@@ -340,7 +367,7 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         slots += (size_t)g_mode[m5] * ngrp;
         vslots += (size_t)g_mode[m5] * ngrp * nc_mode[m5];      // path store: one part per CTA of a cluster
     }
-    const int64_t vmf_cap = score_only ? 8 : max_cells + 8;
+    const int64_t vmf_cap = nopath ? 8 : max_cells + 8;
     if (vmf_cap * 8 > 0x7fffffff) { free(offs); return pg_int_fail(c, PG_ERR_RANGE, "pg_align_groups: DP matrix too large for the path store"); }
 
     // ---- stage
@@ -471,6 +498,7 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
                                    (size_t)ka.smem_bytes) ? 1 : 0;
         km.cluster = nc_mode[mode];
         km.rl = rl_cap[mode];
+        km.swg = swg ? 1 : 0;
         if (km.rl) {                            // register-list kernels: 128 rows per CTA, their own shared-memory size
             size_t wb = 0;
             for (int64_t k = k0; k < k1; ++k)

@@ -171,6 +171,8 @@ struct K3Args {
     int32_t rl;                 // register-list form (k3r_core.cuh): words per dynamic list (4 / 6 / 8) of this launch, 0 = classic
     int32_t rows192;            // the records fit shared memory only with 192 rows per CTA: the cluster kernel's geometry,
                                 // also for a "cluster" of one CTA (long gap-state lists: high hetero, two-piece)
+    int32_t swg;                // Smith-Waterman launch (forwardC): the SWG instantiation, results = colony 0
+    int32_t pad_swg;
 };
 
 // profile contraction (k4_contract.cu): S = X_a . Y_b^T per pair, written to K3Pair::simmat

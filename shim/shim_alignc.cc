@@ -23,7 +23,9 @@
 // Results do not depend on how calls were grouped: every alignment of a batch is computed independently.
 //
 // The rectangle form (algmode.bnd = 0) is taken for NGP_ALN: alignC<DPunit>(seqs, pwd, scr, true), forwardA + initA.
-// Calls the CUDA path does not take (rectangle with gap profiles, caller-supplied window, Smith-Waterman, naive groups with nil
+// Smith-Waterman (algmode.lcl & 16): swg1st (first pass, Fwd2c::forwardC) runs pg_local_groups for algmode.mlt <= 1.
+// Calls the CUDA path does not take (rectangle with gap profiles, caller-supplied window, secondary colonies, quick mode on
+// gapped groups, naive groups with nil
 // ends or more than 32 members) are fatal() unless PRRN_GPU_ALLOW_REF=1 (shim_ctx.h); then they run the reference's
 // own Fwd2c -- the reference's code, not a port; nothing here re-implements the DP on the CPU.
 #ifndef _GNU_SOURCE
@@ -54,12 +56,13 @@
 
 // PRRN_GPU_STATS=1: calls / seconds per route, printed to stderr at exit (where does a prrn run spend its time?)
 struct PgStats {
-	long	n_gpu, n_k2, n_score, n_ref, n_batches, max_batch; double t_stage, t_gpu, t_ref, kernel_ms; long cells;
+	long	n_gpu, n_k2, n_score, n_local, n_ref, n_batches, max_batch; double t_stage, t_gpu, t_ref, kernel_ms; long cells;
 	bool	on;
 	std::mutex	mu;
-	PgStats() : n_gpu(0), n_k2(0), n_score(0), n_ref(0), n_batches(0), max_batch(0), t_stage(0), t_gpu(0), t_ref(0),
+	PgStats() : n_gpu(0), n_k2(0), n_score(0), n_local(0), n_ref(0), n_batches(0), max_batch(0), t_stage(0), t_gpu(0), t_ref(0),
 	    kernel_ms(0), cells(0), on(getenv("PRRN_GPU_STATS") != 0) {}
 	~PgStats() {
+	    if (on && n_local) fprintf(stderr, "prrn_gpu swg1st: %ld Smith-Waterman first passes on the GPU\n", n_local);
 	    if (on) fprintf(stderr, "prrn_gpu alignC: %ld calls on the GPU (%ld of them score-only, %ld pairs of single sequences "
 		"on K2) in %ld library calls (mean batch %.2f, largest %ld; staging %.2f s, library %.2f s of which kernels "
 		"%.2f s, %.3g cells), %d contexts, %ld calls left on the reference's Fwd2c (%.2f s)\n",
@@ -285,8 +288,10 @@ extern "C" int pthread_create(pthread_t* th, const pthread_attr_t* attr, void* (
 // ---- what the library takes ---------------------------------------------------------------------------------------
 static const char* pg_untaken(mSeq* seqs[], PwdM* pwd, bool rectangle, WINDOW* pwdw, bool score_only = false)
 {
+	// quick mode (-Q): align2 / HomScore run the DPunit (no gap profile) rules on whatever groups they get
+	// (src/maln2.cc:1882-1896); the library stages by pwd->alnmode
+	if ((algmode.qck & 1) && pwd->alnmode != NGP_ALB && pwd->alnmode != NGP_ALN) return "quick mode (-Q) on groups with gap profile";
 	if (pwdw) return "caller-supplied window";
-	if (algmode.lcl & 16) return "Smith-Waterman local mode (forwardC)";
 	if (rectangle) {		// forwardA + initA: taken for the groups without gap profile (NGP_ALN)
 	    if (score_only) return "rectangle (forwardA) without path, with its island reports";
 	    if (pwd->alnmode != NGP_ALN) return "rectangle (forwardA) with gap profiles or naive groups";
@@ -526,4 +531,53 @@ VTYPE HomScore(mSeq* seqs[], PwdM* pwdm, long rr[])
 		fatal("Mode %d is not supported !\n", pwdm->alnmode);
 	}
 	return (0);
+}
+
+// swg1st (src/maln2.cc:1999-2027): the first pass of the Smith-Waterman mode (aln.cc:287-311 under algmode.lcl & 16),
+// swg1stC<SwgDPunit | _hf | _pf | _nv> = Fwd2c::initC + forwardC (src/fwd2c.h:178-207,483-659,697-701).  As with
+// HomScore the compiler folds swg1stC into swg1st inside maln2.o, so the shim carries the dispatch.  The library takes
+// algmode.mlt <= 1 (colony 0 only: the best local score and the box of its path); the second pass, swg2nd -> swg2ndC ->
+// align2 inside that box, reaches alignC above.
+Colonies* swg1st(mSeq** seqs, PwdM* pwd)
+{
+	if (seqs[0]->left == seqs[0]->right || seqs[1]->left == seqs[1]->right)
+	    return (0);
+	const char*	why = 0;
+	if (algmode.qck & 1) why = "quick mode (-Q) Smith-Waterman";
+	else if (algmode.mlt > 1) why = "Smith-Waterman with secondary colonies (algmode.mlt > 1)";
+	else switch (pwd->alnmode) {
+	    case NGP_ALB: case HLF_ALB: case RHF_ALB: case GPF_ALB: break;
+	    case NTV_ALB:
+		if (seqs[0]->inex.nils || seqs[1]->inex.nils) why = "naive groups (NTV_ALB) with nil ends";
+		else if (seqs[0]->many > 32 || seqs[1]->many > 32) why = "naive groups (NTV_ALB) of more than 32 members";
+		break;
+	    default:
+		fatal("Mode %d is not supported !\n", pwd->alnmode);
+	}
+	if (why) {
+	    pg_refused("swg1st", why);
+	    if (algmode.qck & 1) return swg1stC<SwgDPunit>(seqs, pwd);
+	    switch (pwd->alnmode) {
+		case NGP_ALB: return swg1stC<SwgDPunit>(seqs, pwd);
+		case HLF_ALB:
+		case RHF_ALB: return swg1stC<SwgDPunit_hf>(seqs, pwd);
+		case GPF_ALB: return swg1stC<SwgDPunit_pf>(seqs, pwd);
+		default: return swg1stC<SwgDPunit_nv>(seqs, pwd);
+	    }
+	}
+	PgJob	job;
+	pg_stage_job(seqs, pwd, &job, false);
+	double	val = 0;
+	int32_t	box[6];
+	{
+	    PgLease	ctx;
+	    if (pg_local_groups(ctx, &job.ga, &job.gb, &job.gp, 1, &val, box) != PG_OK)
+		fatal("prrn_gpu swg1st: %s\n", pg_last_error(ctx));
+	}
+	if (pg_stats.on) {std::lock_guard<std::mutex> lk(pg_stats.mu); ++pg_stats.n_local;}
+	Colonies*	cls = new Colonies();
+	COLONY*	c0 = cls->at();		// no secondary colony: sortcolonies() leaves colony 0 in place (aln2.cc:368-372)
+	c0->val = (VTYPE) val;
+	c0->mlb = box[0]; c0->nlb = box[1]; c0->mrb = box[2]; c0->nrb = box[3]; c0->lwr = box[4]; c0->upr = box[5];
+	return (cls);
 }

@@ -228,6 +228,69 @@ def test_rectangle_form_matches_oracle_beyond_one_stripe(ctx, oracle, monkeypatc
     assert e.value.code == 3
 
 
+def test_smith_waterman_goldens_and_oracle(ctx, oracle):
+    """pg_local_groups = swg1stC<SwgDPunit*> (Fwd2c::forwardC, algmode.mlt <= 1): the best local score and the box of
+    colony 0 against the reference's own swg1st (8 goldens, one batch, three times over), then the second pass
+    (swg2nd: align2 inside the box = pg_align_groups on that window) against the reference's swg2nd, and the oracle
+    on inputs of several stripes (columns repeated) and other band shoulders."""
+    gs = [golden(n) for n in golden_names("galign_swg_")]
+    staged = [stage_golden(g) for g in gs]
+    vals, boxes = ctx.local_groups(staged * 3)
+    keys = ("mlb", "nlb", "mrb", "nrb", "lwr", "upr")
+    for k in range(3 * len(gs)):
+        w = gs[k % len(gs)]["swg"]
+        assert abs(vals[k] - w["val"]) <= REL_TOL * max(1.0, abs(w["val"])), gs[k % len(gs)]["name"]
+        assert boxes[k].tolist() == [w[q] for q in keys], gs[k % len(gs)]["name"]
+    # second pass inside the box (swg2ndC swaps left / right with the colony's box and calls align2)
+    batch, want = [], []
+    for g, (A, B, gp), box in zip(gs, staged, boxes):
+        if not g["swg2nd"]["skl"] or g["swg2nd"]["skl"][0] != [int(box[0]), int(box[1])]:
+            continue                # align2 retried with another band: not the plain window call
+        A2, B2 = dict(A), dict(B)
+        for S, lo, hi in ((A2, int(box[0]), int(box[2])), (B2, int(box[1]), int(box[3]))):
+            off = lo - S["left"]
+            npos = hi - lo + 1
+            for key in ("cfq", "efq", "sfq", "tfq", "rfq", "gapmask"):
+                if S.get(key) is not None:
+                    S[key] = np.ascontiguousarray(S[key][off:off + npos])
+            S["vec"] = np.ascontiguousarray(S["vec"][off:off + npos])
+            S["left"], S["right"] = lo, hi
+        batch.append((A2, B2, gp))
+        want.append(g)
+    assert len(batch) >= 5
+    scores, pts = ctx.align_groups(batch)
+    for k, g in enumerate(want):
+        assert abs(scores[k] - g["swg2nd"]["score"]) <= REL_TOL * max(1.0, abs(g["swg2nd"]["score"])), g["name"]
+        assert P.stdskl(pts[k].tolist()) == [tuple(x) for x in g["swg2nd"]["skl"]], g["name"]
+
+    def tile(d, k):
+        t = dict(d)
+        n = d["right"] - d["left"]
+        for key in ("pos", "cfq", "dfq", "efq", "res", "vss", "sfq", "tfq", "rfq"):
+            v = d[key]
+            t[key] = v[:1] + v[1:n + 1] * k
+        t["right"] = d["left"] + n * k
+        t["len"] = d["len"] + n * (k - 1)
+        return t
+    for name, ka, kb, sh in (("galign_swg_single_unrelated", 3, 4, -60), ("galign_swg_gpf_twopiece", 4, 3, -25),
+                             ("galign_swg_hlf_prof10_single", 5, 5, -100), ("galign_swg_ngp_gapless4x3", 4, 4, 10)):
+        g = golden(name)
+        ga, gb = tile(g["groups"][0], ka), tile(g["groups"][1], kb)
+        wv, wb, _ = oracle.swg_groups(oracle.group_arrays(ga), oracle.group_arrays(gb), np.array(g["matrix"]),
+                                      oracle.gparams_from_dump(g, sh=sh))
+        pm, pc, h = g["pwdm"], g["pwdc"], g["header"]
+        A, B = G.stage_pair(ga, gb, pm["a_mode"], pm["b_mode"], g["matrix"], dxd=(pm["DvsP"] == 0))
+        gp = P.gparams_from_pwd(pm["alnmode"], pm["Noll"], pm["codonk1"], sh, A["vec"].shape[1], float(h["u"]),
+                                float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
+        v1, b1 = ctx.local_groups([(A, B, gp)])
+        assert abs(v1[0] - wv) <= REL_TOL * max(1.0, abs(wv)), name
+        assert b1[0].tolist() == [wb[q] for q in keys], name
+    with pytest.raises(P.PgError) as e:         # the rectangle form has no Smith-Waterman variant
+        A, B, gp = stage_golden(golden("galign_rect_single_p01"))
+        ctx.local_groups([(A, B, gp)])
+    assert e.value.code == 4
+
+
 def test_cluster_latency_kernel_matches_reference(ctx, monkeypatch):
     """Groups of ~1,100 columns in a latency-sized batch: K3 runs them on thread-block clusters (2 / 4 / 8 CTAs per
     alignment, rows handed from CTA to CTA through distributed shared memory).  Every score and corner list must

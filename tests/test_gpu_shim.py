@@ -148,6 +148,7 @@ def _galign_inputs(name, tmp_path):
     try:
         MG.galign_cases()
         MG.galign_rect_cases()
+        MG.galign_swg_cases()
     finally:
         MG.galign_case = real
     rows_a, rows_b, flavour, files, kv = captured[name]
@@ -183,6 +184,40 @@ def test_reference_rectangle_alignC_on_gpu_library(name, tmp_path):
     assert d["pwdm"]["alnmode"] == 1
     for key in ("alignc", "align2"):
         assert abs(d[key]["score"] - g[key]["score"]) <= 1e-5 * max(1.0, abs(g[key]["score"])), key
+        assert d[key]["skl"] == g[key]["skl"], key
+
+
+SWG_CASES = ["galign_swg_gpf_prof12_raw5_wt", "galign_swg_gpf_twopiece", "galign_swg_hlf_prof10_single",
+             "galign_swg_rhf_single_prof10_f32", "galign_swg_gpf_highhetero",
+             "galign_swg_ngp_gapless4x3", "galign_swg_single_unrelated", "galign_swg_single_rag03_twopiece"]
+
+
+@pytest.mark.parametrize("name", SWG_CASES)
+def test_reference_smith_waterman_on_gpu_library(name, tmp_path):
+    """algmode.lcl = 16: the reference's swg1st (first pass, Fwd2c::forwardC -> pg_local_groups through the shim's
+    swg1st) and swg2nd (align2 inside the colony's box -> alignC on the library) must return the plain build's colony,
+    score and corner list; nothing may be left on the reference's Fwd2c."""
+    import subprocess
+    g = golden(name)
+    fa, fb, flavour, kv = _galign_inputs(name, tmp_path)
+    drv = refio.driver(flavour, gpu=True)
+    if not os.path.exists(drv):
+        pytest.skip("oracle/_ref/ref_driver_%s_gpu is not built" % flavour)
+    env = dict(os.environ, ALN_TAB=os.path.join(refio.REFDIR, "table"), PRRN_GPU_STATS="1")
+    env.pop("PRRN_GPU_ALLOW_REF", None)
+    out = subprocess.run([drv, "galign", fa, "fb=" + fb] + ["%s=%s" % kvp for kvp in kv.items()],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    assert "1 Smith-Waterman first passes on the GPU" in out.stderr and "0 calls left on the reference" in out.stderr, out.stderr[-600:]
+    d = refio.parse_galign(out.stdout)
+    tol = lambda w: 1e-5 * max(1.0, abs(w))     # noqa: E731
+    assert abs(d["swg"]["val"] - g["swg"]["val"]) <= tol(g["swg"]["val"])
+    assert {k: d["swg"][k] for k in ("size", "mlb", "nlb", "mrb", "nrb", "lwr", "upr")} == \
+           {k: g["swg"][k] for k in ("size", "mlb", "nlb", "mrb", "nrb", "lwr", "upr")}
+    assert abs(d["swg2nd"]["score"] - g["swg2nd"]["score"]) <= tol(g["swg2nd"]["score"])
+    assert d["swg2nd"]["skl"] == g["swg2nd"]["skl"]
+    for key in ("alignc", "align2"):
+        assert abs(d[key]["score"] - g[key]["score"]) <= tol(g[key]["score"]), key
         assert d[key]["skl"] == g[key]["skl"], key
 
 
