@@ -76,6 +76,19 @@ __device__ __forceinline__ int lead_factor(const K1Args& a, uint8_t flags)
     return a.tgapf_zero ? 0 : 1;
 }
 
+// E[k] = -inf for a run-time k in [0, RR)
+template <int RR>
+__device__ __forceinline__ void poke_row(int (&E)[RR], int k)
+{
+    switch (k) {
+#define K1_POKE(i) case i: if (i < RR) E[i < RR ? i : 0] = K1_NEG; break;
+    K1_POKE(0) K1_POKE(1) K1_POKE(2) K1_POKE(3) K1_POKE(4) K1_POKE(5) K1_POKE(6) K1_POKE(7)
+    K1_POKE(8) K1_POKE(9) K1_POKE(10) K1_POKE(11) K1_POKE(12) K1_POKE(13) K1_POKE(14) K1_POKE(15)
+#undef K1_POKE
+    default: break;
+    }
+}
+
 __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k1_score_kernel(const K1Args a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -158,7 +171,6 @@ __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k1_score_kernel(const 
                 const int upm = g.up + 1 + mbase;       // kU = n - upm
                 int recv_h = K1_NEG, recv_f = K1_NEG;
                 const int4* pp = sm_prof + lane;
-                int4* pk = sm_poke + warp * ((R / 4) * 32) + lane;
                 const int nsteps = LS + lanes - 1;
 
                 for (int step = 0; step < nsteps; ++step) {
@@ -172,19 +184,10 @@ __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k1_score_kernel(const 
                         }
                         // band poke: rows on diagonal lw / up+1 lose their horizontal input
                         const int kL = n - lwm, kU = n - upm;
-                        if ((unsigned)kL < (unsigned)R || (unsigned)kU < (unsigned)R) {
-#pragma unroll
-                            for (int j = 0; j < R / 4; ++j)
-                                pk[j * 32] = make_int4(L.E[4 * j], L.E[4 * j + 1], L.E[4 * j + 2], L.E[4 * j + 3]);
-                            int* pki = reinterpret_cast<int*>(pk);
-                            if ((unsigned)kL < (unsigned)R) pki[(kL >> 2) * 128 + (kL & 3)] = K1_NEG;
-                            if ((unsigned)kU < (unsigned)R) pki[(kU >> 2) * 128 + (kU & 3)] = K1_NEG;
-#pragma unroll
-                            for (int j = 0; j < R / 4; ++j) {
-                                int4 v = pk[j * 32];
-                                L.E[4 * j] = v.x; L.E[4 * j + 1] = v.y; L.E[4 * j + 2] = v.z; L.E[4 * j + 3] = v.w;
-                            }
-                        }
+                        // (a jump table with one move per case: the lanes that cut at a step are one or two of 32, and the
+                        //  round trip of the whole E array through shared memory cost 8 LDS / STS.128 in most steps)
+                        if ((unsigned)kL < (unsigned)R) poke_row<R>(L.E, kL);
+                        if ((unsigned)kU < (unsigned)R) poke_row<R>(L.E, kU);
                         const int letter = __ldg(s + n);
                         const int4* pl = pp + letter * ((R / 4) * 32);
                         int sc[R];
