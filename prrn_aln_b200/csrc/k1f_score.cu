@@ -13,6 +13,7 @@
 // Orientation is always the reference's (rows = a, columns = b): Fwd2d_vd is not symmetric.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "k1f_core.cuh"
 #include "pg_internal.h"
@@ -24,8 +25,10 @@ constexpr int MAXDIM = 32;
 constexpr unsigned FULL = 0xffffffffu;
 enum { M_PLAIN = 0, M_LASTD = 1, M_SWG = 2, M_VD = 3 };
 
-template <typename T, int MODE> struct Cfg {
-    static constexpr int R = sizeof(T) == 4 ? (MODE == M_VD ? 8 : 16) : 8;
+// RO: rows per lane chosen by the host for the plain mode (k1f_rows_per_pass: the smallest stripe of 32 x R rows that
+// takes the longest query of the batch in one pass), 0 = the mode's default
+template <typename T, int MODE, int RO = 0> struct Cfg {
+    static constexpr int R = RO ? RO : (sizeof(T) == 4 ? (MODE == M_VD ? 8 : 16) : 8);
     static constexpr int BPS = (sizeof(T) == 8 && MODE == M_VD) ? 2 : 3;
 };
 
@@ -103,10 +106,10 @@ __device__ __forceinline__ T self_window(const uint8_t* p, int lo, int hi, const
     return acc;
 }
 
-template <typename T, int MODE>
-__global__ void __launch_bounds__(NW * 32, Cfg<T, MODE>::BPS) k1f_score_kernel(const K1FArgs a)
+template <typename T, int MODE, int RO = 0>
+__global__ void __launch_bounds__(NW * 32, Cfg<T, MODE, RO>::BPS) k1f_score_kernel(const K1FArgs a)
 {
-    constexpr int R = Cfg<T, MODE>::R;
+    constexpr int R = Cfg<T, MODE, RO>::R;
     constexpr int VPL = Lay<T, R>::VPL, CH = Lay<T, R>::CH;
     constexpr int ROWS_PER_PASS = 32 * R;
     constexpr bool SWG = MODE == M_SWG, VD = MODE == M_VD, LINES = MODE == M_LASTD || MODE == M_VD;
@@ -366,27 +369,48 @@ __global__ void k1f_self_kernel(PgDevSeqs s, const T* mtx, int dim, T* self)
     self[i] = self_window<T>(s.res + s.offs[i] + s.left[i], 0, s.wlen[i], mtx, dim);
 }
 
-template <typename T, int MODE>
+template <typename T, int MODE, int RO = 0>
 cudaError_t launch_one(const K1FArgs& a, int sm_count, cudaStream_t st)
 {
-    constexpr int R = Cfg<T, MODE>::R;
+    constexpr int R = Cfg<T, MODE, RO>::R;
     const size_t smem = smem_bytes(a.dim, Lay<T, R>::LETTER);
-    cudaError_t e = cudaFuncSetAttribute(k1f_score_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k1f_score_kernel<T, MODE, RO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem_bytes(MAXDIM, Lay<T, R>::LETTER));
     if (e != cudaSuccess) return e;
-    k1f_score_kernel<T, MODE><<<sm_count * Cfg<T, MODE>::BPS, NW * 32, smem, st>>>(a);
+    k1f_score_kernel<T, MODE, RO><<<sm_count * Cfg<T, MODE, RO>::BPS, NW * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 int k1f_warps_per_block() { return NW; }
-int k1f_rows_per_pass(int vtype, int mode) { return 32 * (vtype ? 8 : (mode == M_VD ? 8 : 16)); }
+// Rows of one pass = 32 lanes x R rows.  Plain mode: R follows the longest query of the batch, so that short sets do
+// not leave most lanes of the warp idle (R = 16 on 300-row queries: 19 of 32 lanes) and a query just over 256 rows in
+// double does not need a second pass of a few lanes.
+int k1f_rows_per_pass(int vtype, int mode, int max_wlen)
+{
+    int r = vtype ? 8 : (mode == M_VD ? 8 : 16);
+    static const bool fixed = getenv("PG_K1F_FIXED_ROWS") != nullptr;      // A/B switch: the mode's default R always
+    if (mode == M_PLAIN && max_wlen > 0 && !fixed) {
+        if (!vtype) r = max_wlen <= 128 ? 4 : (max_wlen <= 256 ? 8 : (max_wlen <= 384 ? 12 : 16));
+        else if (max_wlen > 256 && max_wlen <= 320) r = 10;
+    }
+    return 32 * r;
+}
 int k1f_grid_blocks(int sm_count, int vtype, int mode) { return sm_count * ((vtype && mode == M_VD) ? 2 : 3); }
 
 cudaError_t k1f_launch(const K1FArgs& a, int sm_count, cudaStream_t st)
 {
     if (a.dim < 1 || a.dim > MAXDIM) return cudaErrorInvalidValue;
+    if (a.mode == M_PLAIN) {
+        switch (a.vtype ? -a.rows_per_lane : a.rows_per_lane) {
+        case 4: return launch_one<float, M_PLAIN, 4>(a, sm_count, st);
+        case 8: return launch_one<float, M_PLAIN, 8>(a, sm_count, st);
+        case 12: return launch_one<float, M_PLAIN, 12>(a, sm_count, st);
+        case -10: return launch_one<double, M_PLAIN, 10>(a, sm_count, st);
+        default: break;
+        }
+    }
     if (a.vtype) {
         switch (a.mode) {
         case M_PLAIN: return launch_one<double, M_PLAIN>(a, sm_count, st);

@@ -19,7 +19,7 @@ from prrn_aln_b200 import seqcode  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-    seqs = gen_synth.config_set("c2", n)
+    seqs = gen_synth.config_set(sys.argv[2] if len(sys.argv) > 2 else "c2", n)
     enc = [seqcode.encode_protein(s) for s in seqs]
     ss = P.SeqSet(enc)
     with open(os.path.join(ROOT, "tests", "golden", "score_p24_pam_f64.json")) as f:
