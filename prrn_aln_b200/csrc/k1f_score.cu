@@ -384,18 +384,27 @@ cudaError_t launch_one(const K1FArgs& a, int sm_count, cudaStream_t st)
 }  // namespace
 
 int k1f_warps_per_block() { return NW; }
-// Rows of one pass = 32 lanes x R rows.  Plain mode: R follows the longest query of the batch, so that short sets do
-// not leave most lanes of the warp idle (R = 16 on 300-row queries: 19 of 32 lanes) and a query just over 256 rows in
-// double does not need a second pass of a few lanes.
-int k1f_rows_per_pass(int vtype, int mode, int max_wlen)
+// Rows of one pass = 32 lanes x R rows.  Plain mode: R follows the window lengths of the batch, so that short sets do not
+// leave most lanes of the warp idle (R = 16 on 300-row queries: 19 of 32 lanes) and queries just over 256 rows in double
+// do not need a second pass of a few lanes.  Cost of a query = passes x (R + the step's fixed instructions counted in
+// rows); every sequence counts as a query once (calcdist: each is the row side of about half its pairs).
+int k1f_rows_per_pass(int vtype, int mode, const int32_t* wlen, int nseq)
 {
-    int r = vtype ? 8 : (mode == M_VD ? 8 : 16);
+    const int dflt = vtype ? 8 : (mode == M_VD ? 8 : 16);
     static const bool fixed = getenv("PG_K1F_FIXED_ROWS") != nullptr;      // A/B switch: the mode's default R always
-    if (mode == M_PLAIN && max_wlen > 0 && !fixed) {
-        if (!vtype) r = max_wlen <= 128 ? 4 : (max_wlen <= 256 ? 8 : (max_wlen <= 384 ? 12 : 16));
-        else if (max_wlen > 256 && max_wlen <= 320) r = 10;
+    if (mode != M_PLAIN || fixed || !wlen || nseq <= 0) return 32 * dflt;
+    static const int cand_f[4] = {4, 8, 12, 16}, cand_d[4] = {4, 6, 8, 10};
+    const int* cand = vtype ? cand_d : cand_f;
+    const int nc = 4, fixed_rows = vtype ? 3 : 12;
+    int best = dflt;
+    double best_cost = -1;
+    for (int c = 0; c < nc; ++c) {
+        const int rpp = 32 * cand[c];
+        double cost = 0;
+        for (int i = 0; i < nseq; ++i) cost += (double)((wlen[i] + rpp - 1) / rpp) * (cand[c] + fixed_rows);
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && cand[c] == dflt)) { best_cost = cost; best = cand[c]; }
     }
-    return 32 * r;
+    return 32 * best;
 }
 int k1f_grid_blocks(int sm_count, int vtype, int mode) { return sm_count * ((vtype && mode == M_VD) ? 2 : 3); }
 
@@ -407,6 +416,8 @@ cudaError_t k1f_launch(const K1FArgs& a, int sm_count, cudaStream_t st)
         case 4: return launch_one<float, M_PLAIN, 4>(a, sm_count, st);
         case 8: return launch_one<float, M_PLAIN, 8>(a, sm_count, st);
         case 12: return launch_one<float, M_PLAIN, 12>(a, sm_count, st);
+        case -4: return launch_one<double, M_PLAIN, 4>(a, sm_count, st);
+        case -6: return launch_one<double, M_PLAIN, 6>(a, sm_count, st);
         case -10: return launch_one<double, M_PLAIN, 10>(a, sm_count, st);
         default: break;
         }

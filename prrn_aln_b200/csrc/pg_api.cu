@@ -277,7 +277,7 @@ static int k1f_run(pg_context* c, cudaStream_t st, pg_dev_seqs* d, const pg_para
     a.u_f32 = prm->alprm.u;
     a.out = d_out; a.out_ends = d_out_ends;
     a.exg_override = exg_override;
-    a.rows_per_lane = k1f_rows_per_pass(vt, mode, d->max_wlen) / 32;
+    a.rows_per_lane = k1f_rows_per_pass(vt, mode, d->h_wlen.data(), (int)d->h_wlen.size()) / 32;
     PG_CUDA(c, k1f_launch(a, c->sm_count, st));
     if (n_launches) *n_launches = launches;
     return PG_OK;
@@ -670,7 +670,7 @@ extern "C" int pg_calcdist_dev(pg_context* c, pg_dev_seqs* d, const pg_params* p
         bool fmp = false;
         const int vt = prm->vtype ? 1 : 0;
         build_calcdist_items_rows_a(d, k_begin, k_end, k1f_grid_blocks(c->sm_count, vt, plan.mode),
-                                    k1f_rows_per_pass(vt, plan.mode, d->max_wlen), &fitems, &fmp);
+                                    k1f_rows_per_pass(vt, plan.mode, d->h_wlen.data(), (int)d->h_wlen.size()), &fitems, &fmp);
         return k1f_run(c, st, d, prm, mtx, dim, plan.mode, prm->lcl ? 2 : 1, fitems, fmp, nullptr, nullptr, k_begin, k_end,
                        prm->lcl ? (prm->lcl & 15) : -1, d_out_dist, nullptr, n_launches);
     }
@@ -858,7 +858,7 @@ static int score_pairs_impl(pg_context* c, const pg_seqs* s, const int32_t* a_id
     for (int64_t p = 0; p < npairs; ++p) { pair_s[p] = b_idx[order[p]]; pair_out[p] = order[p]; }
     const int vt = prm->vtype ? 1 : 0;
     const int grid = plan.integer ? c->sm_count * k1_blocks_per_sm() : k1f_grid_blocks(c->sm_count, vt, plan.mode);
-    const int NWv = k1_warps_per_block(), rpp = plan.integer ? k1_rows_per_pass() : k1f_rows_per_pass(vt, plan.mode, d->max_wlen);
+    const int NWv = k1_warps_per_block(), rpp = plan.integer ? k1_rows_per_pass() : k1f_rows_per_pass(vt, plan.mode, d->h_wlen.data(), (int)d->h_wlen.size());
     int64_t ch = (npairs + (int64_t)16 * grid - 1) / ((int64_t)16 * grid);
     ch = std::max<int64_t>(NWv, std::min<int64_t>(ch, 32 * NWv));
     ch = (ch + NWv - 1) / NWv * NWv;

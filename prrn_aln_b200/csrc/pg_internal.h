@@ -110,7 +110,7 @@ struct K1FArgs {
     int64_t scratch_stride;     // bytes per warp
     int32_t off_rowv, off_rowr, off_col, off_row, off_colr, off_rowr2, off_misc;
     int32_t exg_override;       // -1: inex flags from the sequences; else bits 0-1 = a's exgl/exgr, 2-3 = b's
-    int32_t rows_per_lane;      // k1f_rows_per_pass(vtype, mode, longest window) / 32: which instantiation runs
+    int32_t rows_per_lane;      // k1f_rows_per_pass(vtype, mode, window lengths) / 32: which instantiation runs
 };
 
 struct K2Rec;
@@ -266,7 +266,7 @@ int k1p_blocks_per_sm();
 cudaError_t k1f_launch(const K1FArgs& a, int sm_count, cudaStream_t st);
 cudaError_t k1f_self_launch(const PgDevSeqs& s, const void* mtx, int dim, int vtype, void* self, cudaStream_t st);
 int k1f_warps_per_block();
-int k1f_rows_per_pass(int vtype, int mode, int max_wlen);
+int k1f_rows_per_pass(int vtype, int mode, const int32_t* wlen, int nseq);
 int k1f_grid_blocks(int sm_count, int vtype, int mode);
 // k2_align.cu
 cudaError_t k2_fill_launch(const K2Args& a, int grid_blocks, cudaStream_t st);
