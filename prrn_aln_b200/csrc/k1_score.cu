@@ -17,22 +17,22 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include "k1_core.cuh"
 #include "pg_internal.h"
 
 namespace {
 
-constexpr int R = 16;           // rows per lane
 constexpr int NW = 8;           // warps per CTA
-constexpr int ROWS_PER_PASS = 32 * R;
 constexpr int MAXDIM = 32;      // profile letters (dim <= 32)
 constexpr int BLOCKS_PER_SM = 3;
 constexpr unsigned FULL = 0xffffffffu;
 
-// dynamic shared memory: prof[dim][R/4][32] int4 (2 KB per letter) | poke[NW][R/4][32] int4 | item
-__host__ __device__ inline size_t smem_bytes(int dim)
+// dynamic shared memory: prof[dim][R/4][32] int4 (2 KB per letter at R = 16) | item
+__host__ __device__ inline size_t smem_bytes(int dim, int R)
 {
-    return (size_t)(dim + NW) * (R / 4) * 32 * sizeof(int4) + 16;
+    return (size_t)dim * (R / 4) * 32 * sizeof(int4) + 16;
 }
 
 __device__ __forceinline__ void epilogue_store(const K1Args& a, int64_t slot, int score, int qi, int si,
@@ -89,12 +89,15 @@ __device__ __forceinline__ void poke_row(int (&E)[RR], int k)
     }
 }
 
+// R = rows per lane (4 / 8 / 12 / 16, chosen per batch by k1_rows_per_pass: the smallest stripe of 32 x R rows that takes
+// the batch's queries in one pass leaves the fewest lanes idle)
+template <int R>
 __global__ void __launch_bounds__(NW * 32, BLOCKS_PER_SM) k1_score_kernel(const K1Args a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int4* const sm_prof = reinterpret_cast<int4*>(smem_raw);
-    int4* const sm_poke = sm_prof + a.dim * (R / 4) * 32;
-    int* const sm_item = reinterpret_cast<int*>(sm_poke + NW * (R / 4) * 32);
+    constexpr int ROWS_PER_PASS = 32 * R;
+    int* const sm_item = reinterpret_cast<int*>(sm_prof + a.dim * (R / 4) * 32);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -237,19 +240,46 @@ __global__ void k1_self_kernel(PgDevSeqs s, const int32_t* mtx, int dim, int32_t
 
 }  // namespace
 
-int k1_rows_per_pass() { return ROWS_PER_PASS; }
+// cost of a query = passes x (R + the step's fixed instructions counted in rows: a DPX cell is ~5 instructions, the
+// step's bookkeeping ~80)
+int k1_rows_per_pass(const int32_t* wlen, int nseq)
+{
+    static const bool fixed = getenv("PG_K1_FIXED_ROWS") != nullptr;       // A/B switch
+    if (fixed || !wlen || nseq <= 0) return 32 * 16;
+    static const int cand[4] = {4, 8, 12, 16};
+    int best = 16;
+    double best_cost = -1;
+    for (int c = 0; c < 4; ++c) {
+        const int rpp = 32 * cand[c];
+        double cost = 0;
+        for (int i = 0; i < nseq; ++i) cost += (double)((wlen[i] + rpp - 1) / rpp) * (cand[c] + 16);
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && cand[c] == 16)) { best_cost = cost; best = cand[c]; }
+    }
+    return 32 * best;
+}
 int k1_warps_per_block() { return NW; }
 int k1_blocks_per_sm() { return BLOCKS_PER_SM; }
+
+template <int R>
+static cudaError_t k1_launch_r(const K1Args& a, int grid_blocks, cudaStream_t st)
+{
+    const size_t smem = smem_bytes(a.dim, R);
+    cudaError_t e = cudaFuncSetAttribute(k1_score_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes(MAXDIM, R));
+    if (e != cudaSuccess) return e;
+    k1_score_kernel<R><<<grid_blocks, NW * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
 
 cudaError_t k1_launch(const K1Args& a, int grid_blocks, cudaStream_t st)
 {
     if (a.dim < 1 || a.dim > MAXDIM) return cudaErrorInvalidValue;
-    const size_t smem = smem_bytes(a.dim);
-    cudaError_t e = cudaFuncSetAttribute(k1_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem_bytes(MAXDIM));
-    if (e != cudaSuccess) return e;
-    k1_score_kernel<<<grid_blocks, NW * 32, smem, st>>>(a);
-    return cudaGetLastError();
+    switch (a.rows_per_lane) {
+    case 4: return k1_launch_r<4>(a, grid_blocks, st);
+    case 8: return k1_launch_r<8>(a, grid_blocks, st);
+    case 12: return k1_launch_r<12>(a, grid_blocks, st);
+    default: return k1_launch_r<16>(a, grid_blocks, st);
+    }
 }
 
 cudaError_t k1_self_launch(const PgDevSeqs& s, const int32_t* mtx, int dim, int32_t* self, cudaStream_t st)

@@ -404,7 +404,7 @@ static void build_calcdist_items(const pg_dev_seqs* d, int64_t k0, int64_t k1, i
     items->clear();
     *multipass = false;
     if (k1 <= k0) return;
-    const int NWv = k1_warps_per_block(), rpp = k1_rows_per_pass();
+    const int NWv = k1_warps_per_block(), rpp = k1_rows_per_pass(d->h_wlen.data(), (int)d->h_wlen.size());
     const int jlo = row_of_k(k0), jhi = row_of_k(k1 - 1);
     int64_t total = k1 - k0;
     int64_t ch = (total + (int64_t)16 * grid_blocks - 1) / ((int64_t)16 * grid_blocks);
@@ -763,6 +763,7 @@ extern "C" int pg_calcdist_dev(pg_context* c, pg_dev_seqs* d, const pg_params* p
     a.self = (const int32_t*)c->d_self;
     a.epilogue = prm->vtype ? PG_EPI_DIST_F64 : PG_EPI_DIST_F32;
     a.out = d_out_dist;
+    a.rows_per_lane = k1_rows_per_pass(d->h_wlen.data(), (int)d->h_wlen.size()) / 32;
     PG_CUDA(c, k1_launch(a, grid, st));
     if (n_launches) *n_launches = 2;
     // Host staging vectors (items, integer matrix) are pageable: cudaMemcpyAsync has already copied
@@ -858,7 +859,7 @@ static int score_pairs_impl(pg_context* c, const pg_seqs* s, const int32_t* a_id
     for (int64_t p = 0; p < npairs; ++p) { pair_s[p] = b_idx[order[p]]; pair_out[p] = order[p]; }
     const int vt = prm->vtype ? 1 : 0;
     const int grid = plan.integer ? c->sm_count * k1_blocks_per_sm() : k1f_grid_blocks(c->sm_count, vt, plan.mode);
-    const int NWv = k1_warps_per_block(), rpp = plan.integer ? k1_rows_per_pass() : k1f_rows_per_pass(vt, plan.mode, d->h_wlen.data(), (int)d->h_wlen.size());
+    const int NWv = k1_warps_per_block(), rpp = plan.integer ? k1_rows_per_pass(d->h_wlen.data(), (int)d->h_wlen.size()) : k1f_rows_per_pass(vt, plan.mode, d->h_wlen.data(), (int)d->h_wlen.size());
     int64_t ch = (npairs + (int64_t)16 * grid - 1) / ((int64_t)16 * grid);
     ch = std::max<int64_t>(NWv, std::min<int64_t>(ch, 32 * NWv));
     ch = (ch + NWv - 1) / NWv * NWv;
@@ -929,6 +930,7 @@ static int score_pairs_impl(pg_context* c, const pg_seqs* s, const int32_t* a_id
         a.self = dist ? (const int32_t*)c->d_self : nullptr;
         a.epilogue = dist ? (prm->vtype ? PG_EPI_DIST_F64 : PG_EPI_DIST_F32) : (prm->vtype ? PG_EPI_SCORE_F64 : PG_EPI_SCORE_F32);
         a.out = c->d_out;
+        a.rows_per_lane = k1_rows_per_pass(d->h_wlen.data(), (int)d->h_wlen.size()) / 32;
         if (e == cudaSuccess) e = k1_launch(a, grid, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, c->d_out, esz * npairs, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

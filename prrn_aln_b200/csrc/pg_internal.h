@@ -55,6 +55,8 @@ struct K1Args {
     void* out;
     int2* rowbuf;               // multi-pass scratch: [grid warps][rowbuf_stride]
     int64_t rowbuf_stride;
+    int32_t rows_per_lane;      // k1_rows_per_pass(window lengths) / 32: which instantiation runs (0 = 16)
+    int32_t pad_rows;
 };
 
 // packed (int16 x 2) score kernel: a pair of queries against a run of subjects
@@ -252,7 +254,7 @@ int pg_int_align_pairs_fp(pg_context* c, const pg_seqs* s, const int32_t* a_idx,
 
 // kernels (k1_score.cu)
 cudaError_t k1_launch(const K1Args& a, int grid_blocks, cudaStream_t st);
-int k1_rows_per_pass();
+int k1_rows_per_pass(const int32_t* wlen, int nseq);
 int k1_warps_per_block();
 int k1_blocks_per_sm();
 cudaError_t k1_self_launch(const PgDevSeqs& s, const int32_t* mtx, int dim, int32_t* self, cudaStream_t st);
