@@ -345,6 +345,67 @@ __global__ void __launch_bounds__(128) k2_trace_kernel(const K2Args a, int npair
     }
 }
 
+// One WARP per alignment: the back-walk is a chain of dependent loads (the next cell is known only after the nibble of
+// this one: ~0.35 us per move -- 20.9 ms for the 60,000 moves of a 30 kb pair, more than its fill).  Paths run straight
+// most of the time, so the 32 lanes read the next 32 cells of the current run at once (diagonal in state H, up in G,
+// left in F) and a ballot finds where the run really ends; one load latency per run (or per 32 moves) instead of per
+// move.  Lane 0 then replays the moves (sequential memory, no dependent loads).
+__device__ int k2_backwalk_warp(const unsigned long long* words, int LQ, int LS, int RL, unsigned char* moves)
+{
+    const int lane = threadIdx.x & 31;
+    int nmv = 0, m = LQ - 1, n = LS - 1, state = 0;     // uniform over the warp
+    while (m >= 0 && n >= 0) {
+        const int mj = m - (state != 2 ? lane : 0), nj = n - (state != 1 ? lane : 0);
+        const bool inr = mj >= 0 && nj >= 0;
+        const unsigned nib = inr ? k2_nibble(words, LS, RL, mj, nj) : 0u;
+        if (state == 0) {
+            const unsigned bal = __ballot_sync(FULL, !inr || (nib & 3u) != 0u);
+            const int f = bal ? __ffs(bal) - 1 : 32;            // lanes below f continue the diagonal run
+            if (lane < f) moves[nmv + lane] = 1;
+            nmv += f; m -= f; n -= f;
+            if (f < 32) {
+                const unsigned nf = __shfl_sync(FULL, nib, f);
+                if (m >= 0 && n >= 0) state = (int)(nf & 3u);   // the cell where the run ends: a gap state takes over
+            }
+        } else {
+            const unsigned obit = state == 1 ? 4u : 8u;         // the gap opened here: last cell of the run
+            const unsigned bal = __ballot_sync(FULL, !inr || (nib & obit) != 0u);
+            const int f = bal ? __ffs(bal) - 1 : 32;
+            const bool opened = f < 32 && (state == 1 ? m - f >= 0 : n - f >= 0);
+            if (lane < f) moves[nmv + lane] = (unsigned char)(state == 1 ? 3 : 5);
+            if (opened && lane == f) moves[nmv + f] = (unsigned char)(state == 1 ? 2 : 4);
+            const int used = f + (opened ? 1 : 0);
+            nmv += used;
+            if (state == 1) m -= used; else n -= used;
+            if (opened) state = 0;
+        }
+    }
+    for (int j = lane; j <= n; j += 32) moves[nmv + j] = 6;     // boundary row, then boundary column
+    if (n >= 0) nmv += n + 1;
+    for (int j = lane; j <= m; j += 32) moves[nmv + j] = 7;
+    if (m >= 0) nmv += m + 1;
+    __syncwarp();
+    return nmv;
+}
+
+__global__ void __launch_bounds__(32) k2_trace_warp_kernel(const K2Args a, int npairs)
+{
+    for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
+        const int qi = a.pair_q[p], si = a.pair_s[p];
+        const int LQ = a.seqs.wlen[qi], LS = a.seqs.wlen[si];
+        const int ql = a.seqs.left[qi], sl = a.seqs.left[si];
+        const int64_t off = a.len_off[p];
+        int* out = a.out_pts + 2 * off;
+        if (LQ == 0 || LS == 0) {
+            if (threadIdx.x == 0) { out[0] = ql + LQ; out[1] = sl + LS; out[2] = ql; out[3] = sl; a.out_cnt[p] = 2; }
+            continue;
+        }
+        const int nmv = k2_backwalk_warp(a.dirs + a.dir_off[p], LQ, LS, a.rows_per_lane ? a.rows_per_lane : R, a.moves + off);
+        if (threadIdx.x == 0) a.out_cnt[p] = k2_replay(a.moves + off, nmv, LQ, LS, ql, sl, a.recs + off, out);
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 int k2_rows_per_lane() { return R; }
@@ -402,6 +463,13 @@ cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, cudaSt
 
 cudaError_t k2_trace_launch(const K2Args& a, int npairs, cudaStream_t st)
 {
+    // few alignments (a long pair, a handful of candidates): one warp each, runs of the path read 32 cells at a time;
+    // large batches: one thread each, the parallelism is across alignments
+    static const bool thread_only = getenv("PG_K2_TRACE_THREAD") != nullptr;    // A/B switch
+    if (npairs <= 148 * 64 && !thread_only) {
+        k2_trace_warp_kernel<<<npairs < 1 ? 1 : npairs, 32, 0, st>>>(a, npairs);
+        return cudaGetLastError();
+    }
     int blocks = (npairs + 127) / 128;
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 16) blocks = 148 * 16;

@@ -126,8 +126,8 @@ struct K2Rec { int m, n, p; };
 // LQ+LS+4 entries of 2 ints) with absolute coordinates (window offsets ql, sl added) and returns the
 // number of corners.  Move codes: 1 D, 2 V open, 3 V extend, 4 H open, 5 H extend, 6 boundary H,
 // 7 boundary V.
-PG_HD int k2_trace(const unsigned long long* words, int LQ, int LS, int R, int ql, int sl, unsigned char* moves,
-                   K2Rec* recs, int* out)
+// walk the direction bits back from the end cell; returns the number of moves (last move first)
+PG_HD int k2_backwalk(const unsigned long long* words, int LQ, int LS, int R, unsigned char* moves)
 {
     int nmv = 0;
     int m = LQ - 1, n = LS - 1, state = 0;       // 0 H, 1 G, 2 F
@@ -147,6 +147,12 @@ PG_HD int k2_trace(const unsigned long long* words, int LQ, int LS, int R, int q
     }
     for (; n >= 0; --n) moves[nmv++] = 6;
     for (; m >= 0; --m) moves[nmv++] = 7;
+    return nmv;
+}
+
+// forward replay of the moves with the reference's record rules, then Vmf::traceback
+PG_HD int k2_replay(const unsigned char* moves, int nmv, int LQ, int LS, int ql, int sl, K2Rec* recs, int* out)
+{
 
     // forward replay of the reference's (dir, ptr) bookkeeping along the path
     int nrec = 0;
@@ -190,4 +196,11 @@ PG_HD int k2_trace(const unsigned long long* words, int LQ, int LS, int R, int q
     out[2 * cnt] = LQ + ql; out[2 * cnt + 1] = LS + sl; ++cnt;
     for (int q = hptr; q >= 0; q = recs[q].p) { out[2 * cnt] = recs[q].m; out[2 * cnt + 1] = recs[q].n; ++cnt; }
     return cnt;
+}
+
+PG_HD int k2_trace(const unsigned long long* words, int LQ, int LS, int R, int ql, int sl, unsigned char* moves,
+                   K2Rec* recs, int* out)
+{
+    const int nmv = k2_backwalk(words, LQ, LS, R, moves);
+    return k2_replay(moves, nmv, LQ, LS, ql, sl, recs, out);
 }
