@@ -465,7 +465,7 @@ cudaError_t k2_trace_launch(const K2Args& a, int npairs, cudaStream_t st)
 {
     // few alignments (a long pair, a handful of candidates): one warp each, runs of the path read 32 cells at a time;
     // large batches: one thread each, the parallelism is across alignments
-    static const bool thread_only = getenv("PG_K2_TRACE_THREAD") != nullptr;    // A/B switch
+    const bool thread_only = getenv("PG_K2_TRACE_THREAD") != nullptr;           // A/B and test switch
     if (npairs <= 148 * 64 && !thread_only) {
         k2_trace_warp_kernel<<<npairs < 1 ? 1 : npairs, 32, 0, st>>>(a, npairs);
         return cudaGetLastError();

@@ -106,8 +106,15 @@ def test_integer_goldens_through_float_path(ctx, monkeypatch):
             assert P.stdskl(raw[k]) == [tuple(x) for x in p["skl"]], (name, p["i"], p["j"])
 
 
-def test_raw_corner_lists_match_oracle_fuzz(ctx, oracle):
-    """Tiny adversarial pairs: the raw Vmf back-walk lists (before stdskl) must be identical."""
+@pytest.mark.parametrize("trace", ["warp", "thread"])
+def test_raw_corner_lists_match_oracle_fuzz(ctx, oracle, trace, monkeypatch):
+    """Tiny adversarial pairs: the raw Vmf back-walk lists (before stdskl) must be identical -- with the back-walk of
+    small batches (one warp per alignment, runs read 32 cells at a time) and with the one of large batches (one thread
+    per alignment; PG_K2_TRACE_THREAD forces it)."""
+    if trace == "thread":
+        monkeypatch.setenv("PG_K2_TRACE_THREAD", "1")
+    else:
+        monkeypatch.delenv("PG_K2_TRACE_THREAD", raising=False)
     M = np.array(golden("score_p24_blosum62")["matrix"])
     rng = np.random.default_rng(99)
     for sh, u, v in ((0, 1, 0), (1, 2, 9), (3, 3, 5), (-30, 2, 1), (-100, 1, 12)):
