@@ -429,7 +429,8 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
                 fill_side(b[i], prm[i].kdim, sob[i], h.data());
             }
         };
-        int nth = h_bytes < ((size_t)8 << 20) ? 1 : (int)std::min<int64_t>(4, std::max(1u, std::thread::hardware_concurrency()));
+        static const int nth_max = getenv("PG_STAGE_THREADS") ? std::max(1, atoi(getenv("PG_STAGE_THREADS"))) : 4;
+        int nth = h_bytes < ((size_t)8 << 20) ? 1 : (int)std::min<int64_t>(nth_max, std::max(1u, std::thread::hardware_concurrency()));
         nth = (int)std::min<int64_t>(nth, npairs);
         if (nth <= 1) fill_range(0, npairs);
         else {
