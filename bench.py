@@ -38,7 +38,7 @@ BASE_N = 1000               # config 2: 1,000 proteins of ~400 aa
 SH = -60                    # prrn5 default band shoulder (src/prrn5.cc:1272)
 OPS_PER_CELL = 9            # 5 add + 4 max per cell, affine score-only
 DPX_OPS_PER_INSTR = 2       # one viaddmax / vimax3 retires two of those scalar operations
-TRAFFIC_NCU = 1835776       # dram__bytes_read + write per k1p_score_kernel launch (profiles/r2_k1p_score_ncu_full_summary.csv)
+TRAFFIC_NCU = 1835520       # dram__bytes_read + write per k1p_score_kernel launch (profiles/r2_k1p_score_ncu_full_summary.csv)
 CPU_SAMPLE_N = 400          # bounded CPU sample: first 400 sequences (79,800 pairs, ~1.1e10 cells)
 
 
