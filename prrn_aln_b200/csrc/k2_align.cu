@@ -388,6 +388,79 @@ __device__ int k2_backwalk_warp(const unsigned long long* words, int LQ, int LS,
     return nmv;
 }
 
+// The forward replay (k2_replay's record rules) by the whole warp: 32 moves per load, the runs inside a chunk found by
+// ballot, one state update per RUN (a diagonal run can start a record only at its first move, a gap run only at its
+// end).  Every lane carries the same state; lane 0 writes.  The path records chain strictly in order of creation (a gap
+// run creates none between its opening and its end), so Vmf::traceback's list is the records in reverse order: the
+// lanes copy it out side by side instead of walking the chain.
+__device__ int k2_replay_warp(const unsigned char* moves, int nmv, int LQ, int LS, int ql, int sl, K2Rec* recs, int* out)
+{
+    const int lane = threadIdx.x & 31;
+    int nrec = 0;
+    if (lane == 0) { recs[0].m = ql; recs[0].n = sl; recs[0].p = -1; }
+    nrec = 1;
+    int hdir = K2_DIAG, hptr = 0, gdir = 0, gptr = 0, cm = -1, cn = -1;
+    int base = nmv - 1;
+    unsigned char mine = base - lane >= 0 ? moves[base - lane] : 0;     // forward order: lane j = j-th move of the chunk
+    while (base >= 0) {
+        const int cnt = base + 1 < 32 ? base + 1 : 32;
+        const int nbase = base - 32;
+        const unsigned char ahead = nbase - lane >= 0 ? moves[nbase - lane] : 0;    // next chunk, in flight while this one runs
+        const int next_first = __shfl_sync(FULL, (int)ahead, 0);
+        int j = 0;
+        while (j < cnt) {
+            const int c = __shfl_sync(FULL, (int)mine, j);
+            const unsigned diff = __ballot_sync(FULL, lane >= j && lane < cnt && (int)mine != c);
+            const int e = diff ? __ffs(diff) - 1 : cnt;
+            int len = e - j;
+            const int nxt = e < cnt ? __shfl_sync(FULL, (int)mine, e) : (nbase >= 0 ? next_first : 0);
+            switch (c) {
+            case 6: cn += len; hdir = K2_HORI; break;
+            case 7: cm += len; hdir = K2_VERT; break;
+            case 1:
+                ++cm; ++cn;
+                hdir = k2_isdiag(hdir) ? K2_DIAG : K2_NEWD;
+                if (hdir == K2_NEWD) {
+                    if (lane == 0) { recs[nrec].m = cm + ql; recs[nrec].n = cn + sl; recs[nrec].p = hptr; }
+                    hptr = nrec++;
+                }
+                if (len > 1) { cm += len - 1; cn += len - 1; hdir = K2_DIAG; }
+                break;
+            case 2: case 4:         // gap openings: one cell each (several in a row are separate one-cell gaps)
+                for (; len > 0; --len) {
+                    if (c == 2) { ++cm; gdir = k2_ishori(hdir) ? K2_NEWV : K2_VERT; } else { ++cn; gdir = k2_isvert(hdir) ? K2_NEWH : K2_HORI; }
+                    gptr = hptr;
+                    const int after = len > 1 ? c : nxt;
+                    if (after != c + 1) {   // the run ends here: H takes the gap state
+                        hdir = gdir; hptr = gptr;
+                        if (hdir == K2_NEWV || hdir == K2_NEWH) {
+                            if (lane == 0) { recs[nrec].m = cm + ql; recs[nrec].n = cn + sl; recs[nrec].p = hptr; }
+                            hptr = nrec++;
+                        }
+                    }
+                }
+                break;
+            case 3: case 5:         // extensions
+                if (c == 3) { cm += len; gdir = K2_VERT; } else { cn += len; gdir = K2_HORI; }
+                if (nxt != c) { hdir = gdir; hptr = gptr; }
+                break;
+            default: break;
+            }
+            j = e;
+        }
+        base = nbase;
+        mine = ahead;
+    }
+    __syncwarp();
+    // final record (fwd2c.h:476) + the records in reverse order of creation (= Vmf::traceback, vmf.cc:103-119)
+    if (lane == 0) { out[0] = LQ + ql; out[1] = LS + sl; }
+    for (int q = lane; q < nrec; q += 32) {
+        const K2Rec r = recs[nrec - 1 - q];
+        out[2 * (q + 1)] = r.m; out[2 * (q + 1) + 1] = r.n;
+    }
+    return nrec + 1;
+}
+
 __global__ void __launch_bounds__(32) k2_trace_warp_kernel(const K2Args a, int npairs)
 {
     for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
@@ -401,7 +474,8 @@ __global__ void __launch_bounds__(32) k2_trace_warp_kernel(const K2Args a, int n
             continue;
         }
         const int nmv = k2_backwalk_warp(a.dirs + a.dir_off[p], LQ, LS, a.rows_per_lane ? a.rows_per_lane : R, a.moves + off);
-        if (threadIdx.x == 0) a.out_cnt[p] = k2_replay(a.moves + off, nmv, LQ, LS, ql, sl, a.recs + off, out);
+        const int cnt = k2_replay_warp(a.moves + off, nmv, LQ, LS, ql, sl, a.recs + off, out);
+        if (threadIdx.x == 0) a.out_cnt[p] = cnt;
         __syncwarp();
     }
 }
