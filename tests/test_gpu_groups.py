@@ -291,6 +291,61 @@ def test_smith_waterman_goldens_and_oracle(ctx, oracle):
     assert e.value.code == 4
 
 
+def test_smith_waterman_and_rectangle_on_odd_windows(ctx, oracle):
+    """Windows of 1 .. 300 columns cut out of tiled goldens (first / last stripe rows, single rows and columns, bands
+    that leave a corner empty): pg_local_groups and the rectangle form against the oracle, all in two batches."""
+    rng = np.random.default_rng(17)
+    keys = ("mlb", "nlb", "mrb", "nrb", "lwr", "upr")
+
+    def window(d, k, lo, ln):
+        """columns lo .. lo+ln of the group tiled k times (array index 0 = position lo - 1)"""
+        n = d["right"] - d["left"]
+        t = dict(d)
+        for key in ("pos", "cfq", "dfq", "efq", "res", "vss", "sfq", "tfq", "rfq"):
+            v = d[key]
+            full = v[:1] + v[1:n + 1] * k + v[n + 1:]
+            t[key] = full[lo:lo + ln + 2]           # one column more than the banded forms read (the rectangle's b)
+        t["left"], t["right"], t["len"] = 0, ln, ln
+        return t
+    sizes = [(1, 1), (1, 9), (8, 1), (2, 300), (257, 3), (33, 257), (300, 41), (129, 130), (64, 64), (255, 256)]
+    swg_batch, swg_want, rect_batch, rect_want = [], [], [], []
+    for name in ("galign_swg_single_unrelated", "galign_swg_gpf_twopiece", "galign_swg_hlf_prof10_single"):
+        g = golden(name)
+        pm, pc, h = g["pwdm"], g["pwdc"], g["header"]
+        for la, lb in sizes:
+            ga = window(g["groups"][0], 5, int(rng.integers(0, 60)), la)
+            gb = window(g["groups"][1], 5, int(rng.integers(0, 60)), lb)
+            sh = int(rng.choice([-100, -60, -20, 0, 5]))
+            wv, wb, _ = oracle.swg_groups(oracle.group_arrays(ga), oracle.group_arrays(gb), np.array(g["matrix"]),
+                                          oracle.gparams_from_dump(g, sh=sh))
+            A, B = G.stage_pair(ga, gb, pm["a_mode"], pm["b_mode"], g["matrix"], dxd=(pm["DvsP"] == 0))
+            gp = P.gparams_from_pwd(pm["alnmode"], pm["Noll"], pm["codonk1"], sh, A["vec"].shape[1], float(h["u"]),
+                                    float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
+            swg_batch.append((A, B, gp))
+            swg_want.append((wv, [wb[q] for q in keys], name, la, lb, sh))
+    vals, boxes = ctx.local_groups(swg_batch)
+    for k, (wv, wb, name, la, lb, sh) in enumerate(swg_want):
+        assert abs(vals[k] - wv) <= REL_TOL * max(1.0, abs(wv)), (name, la, lb, sh)
+        assert boxes[k].tolist() == wb, (name, la, lb, sh)
+    for name in ("galign_rect_single_rag62", "galign_rect_ngp_gapless4x3_twopiece"):
+        g = golden(name)
+        pm, pc, h = g["pwdm"], g["pwdc"], g["header"]
+        for la, lb in sizes:
+            ga = window(g["groups"][0], 5, int(rng.integers(0, 60)), la)
+            gb = window(g["groups"][1], 5, int(rng.integers(0, 60)), lb)
+            ws, wp, _ = oracle.align_groups(oracle.group_arrays(ga), oracle.group_arrays(gb), np.array(g["matrix"]),
+                                            oracle.gparams_from_dump(g))
+            A, B = G.stage_pair(ga, gb, pm["a_mode"], pm["b_mode"], g["matrix"])
+            gp = P.gparams_from_pwd(pm["alnmode"], pm["Noll"], pm["codonk1"], int(h["sh"]), A["vec"].shape[1], float(h["u"]),
+                                    float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
+            rect_batch.append((A, B, gp))
+            rect_want.append((ws, wp, name, la, lb))
+    scores, pts = ctx.align_groups(rect_batch)
+    for k, (ws, wp, name, la, lb) in enumerate(rect_want):
+        assert abs(scores[k] - ws) <= REL_TOL * max(1.0, abs(ws)), (name, la, lb)
+        assert [tuple(x) for x in pts[k].tolist()] == wp, (name, la, lb)
+
+
 def test_cluster_latency_kernel_matches_reference(ctx, monkeypatch):
     """Groups of ~1,100 columns in a latency-sized batch: K3 runs them on thread-block clusters (2 / 4 / 8 CTAs per
     alignment, rows handed from CTA to CTA through distributed shared memory).  Every score and corner list must
