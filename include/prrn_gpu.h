@@ -117,7 +117,9 @@ int pg_align_pairs_ng(pg_context *ctx, const pg_seqs *seqs, const int32_t *a_idx
  * alignC<DPunit>(seqs, pwd, scr, true), src/maln2.cc:1906) runs the rectangle form, forwardA + initA (src/fwd2c.h:
  * 111-135,231-356): every cell of the window, no band; it needs b.left = 0 and b's per-column arrays ONE COLUMN
  * LONGER (npos + 1 entries: forwardA reads b's thickness at position b.right, :240-249).  The rectangle forms with
- * gap profiles (HLF_ALN / RHF_ALN / GPF_ALN / NTV_ALN) and the rectangle HomScoreC return PG_ERR_UNSUPPORTED.
+ * gap profiles (HLF_ALN / RHF_ALN / GPF_ALN / NTV_ALN) return PG_ERR_UNSUPPORTED: forwardA copies its records by struct
+ * assignment (`*hdiag = *h`, :124,247), which for the record types with list pointers aliases the gap states of different
+ * cells -- the reference's result there is not a function of the inputs alone.  So does the rectangle HomScoreC.
  * Precondition as in the reference: PwdM pwd(seqs) already ran (sequences
  * swapped if pwd->swp, mkthick / Gfq / convseq done).  A pg_group is what Fwd2c reads from one mSeq
  * through mSeqItr for the columns left-1 .. right-1 (npos = right - left + 1 entries):
