@@ -12,6 +12,8 @@
 #include <thread>
 #include <vector>
 
+#include <atomic>
+
 #include "pg_internal.h"
 #include "k3r_core.cuh"
 
@@ -422,11 +424,22 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
         return pairs[x].prm.mode != pairs[y].prm.mode ? pairs[x].prm.mode < pairs[y].prm.mode : cells[x] > cells[y];
     });
     std::vector<K3Pair> sorted(npairs);
+    std::atomic<int> up_err(0);
     {   // staging copies of the pairs are independent: large batches are filled by up to 4 host threads
+        // ... and every finished piece (about 8 MB) goes to the device at once: the upload of the blob runs under the
+        //     staging of the rest instead of after it (the pieces are disjoint byte ranges of one pinned buffer)
         auto fill_range = [&](int64_t i0, int64_t i1) {
+            cudaSetDevice(c->device);
+            size_t sent = soa[i0].cfq;
             for (int64_t i = i0; i < i1; ++i) {
                 fill_side(a[i], prm[i].kdim, soa[i], h.data());
                 fill_side(b[i], prm[i].kdim, sob[i], h.data());
+                const size_t end = i + 1 < npairs ? soa[i + 1].cfq : blob;
+                if (end - sent >= ((size_t)8 << 20) || i + 1 == i1) {
+                    if (end > sent && cudaMemcpyAsync(d + sent, h.data() + sent, end - sent, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+                        up_err.store(1);
+                    sent = end;
+                }
             }
         };
         static const int nth_max = getenv("PG_STAGE_THREADS") ? std::max(1, atoi(getenv("PG_STAGE_THREADS"))) : 4;
@@ -475,7 +488,9 @@ static int pg_int_align_groups(pg_context* c, const pg_group* a, const pg_group*
     }
     std::vector<int32_t> h_pts(2 * (size_t)outoff[npairs]), h_cnt(npairs);
     std::vector<double> h_scr(npairs);
-    e = cudaMemcpyAsync(d, h.data(), h.size(), cudaMemcpyHostToDevice, c->stream);
+    // the group data went up piece by piece while it was staged; what is left is the pair table and the K4 block offsets
+    e = up_err.load() ? cudaErrorUnknown
+                      : cudaMemcpyAsync(d + blob, h.data() + blob, h.size() - blob, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->d_counter, 0, 8 * sizeof(int32_t), c->stream);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev0, c->stream);
     if (e == cudaSuccess && sim_bytes) e = k4_launch(k4, k4_blocks, c->stream);
