@@ -345,6 +345,123 @@ __global__ void __launch_bounds__(128) k2_trace_kernel(const K2Args a, int npair
     }
 }
 
+
+// ---- the same kernel, second form -----------------------------------------------------------------------------------
+// Same stripes, same hand-over through L2 in 32-column chunks, same direction-word layout; what changed is inside a
+// step: the query profile is laid out [letter][row][lane] as plain words (RR conflict-free LDS.32 instead of int4
+// chunks that need RR % 4 == 0), and the band cut is an unrolled compare-and-move on the register array instead of a
+// round trip of E[] through shared memory.  30 kb pair, RR = 8: 17.4 -> 15.3 ms.
+// (Tried with it, end of round 2: W > 1 consecutive stripes per CTA, one warp per scheduler, handing the bottom row down
+// through a shared-memory ring one column per step, so that narrow stripes -- faster per step -- would not pay the ~87
+// steps by which a stripe trails the one above through L2.  Results identical, but 38 - 47 ms for every W > 1 unless the
+// kernel also contained a printf call, with which RR = 4, W = 4 ran in 14.2 ms; fences, spin back-off and the ring's
+// layout made no difference.  Not understood, so not shipped.)
+template <int RR>
+__global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int npass)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    int* const prof = reinterpret_cast<int*>(smem_raw);            // [letter][k][lane]
+    const int negv = -a.v;
+    const int qi = a.pair_q[0], si = a.pair_s[0];
+    const uint8_t* q = a.seqs.res + a.seqs.offs[qi] + a.seqs.left[qi];
+    const uint8_t* s = a.seqs.res + a.seqs.offs[si] + a.seqs.left[si];
+    const int LQ = a.seqs.wlen[qi], LS = a.seqs.wlen[si];
+    K1Geom g;
+    g.LQ = LQ; g.LS = LS; g.u = a.u; g.v = a.v;
+    k1_band(LQ, LS, a.sh, &g.lw, &g.up);
+    g.topOpen = -a.v; g.topExt = -a.u; g.leftOpen = -a.v; g.leftExt = -a.u;
+    unsigned char* const dir_base = reinterpret_cast<unsigned char*>(a.dirs + a.dir_off[0]);
+    constexpr int RPP = 32 * RR;
+
+    for (;;) {
+        int pass = 0;
+        if (lane == 0) pass = atomicAdd(a.ticket, 1);
+        pass = __shfl_sync(FULL, pass, 0);
+        if (pass >= npass) break;
+        const int pbase = pass * RPP;
+        for (int idx = lane; idx < a.dim * RPP; idx += 32) {
+            const int letter = idx / RPP, rem = idx - letter * RPP;
+            const int k = rem >> 5, ln = rem & 31;
+            const int row = pbase + ln * RR + k;
+            prof[idx] = row < LQ ? a.mtx[(int)q[row] * a.dim + letter] + 2 * a.u : 0;
+        }
+        __syncwarp();
+        const int rows_here = min(LQ - pbase, RPP);
+        const int lanes = (rows_here + RR - 1) / RR;
+        const int mbase = pbase + lane * RR;
+        const bool last_pass = pass == npass - 1;
+        const int2* const row_in = a.rowbuf + (int64_t)(pass - 1) * LS;
+        int2* const row_out = a.rowbuf + (int64_t)pass * LS;
+        const int* const prog_in = a.progress + (pass - 1);
+        unsigned char* const words = dir_base + ((int64_t)pass * (LS + 31) * 32 + lane) * (RR / 2);
+
+        K2Lane<RR> L;
+        k2_lane_init(L, g, mbase);
+        const int lwm = g.lw + mbase;
+        const int upm = g.up + 1 + mbase;
+        int recv_h = K1_NEG, recv_g = K1_NEG;
+        const int nsteps = LS + lanes - 1;
+        int avail = 0;
+        int2 chunk = make_int2(K1_NEG, K1_NEG);
+        int nxt = (lane < lanes && LS > 0) ? (int)__ldg(s) : 0;
+
+        for (int step = 0; step < nsteps; ++step) {
+            const int n = step - lane;
+            int in_h = K1_NEG, in_g = K1_NEG;
+            if (pass > 0) {                                         // uniform over the warp
+                if ((step & 31) == 0 && step < LS) {                // lane 0 enters a new chunk of 32 columns
+                    const int need = min(step + 32, LS);
+                    if (lane == 0) while (avail < need) avail = ld_acquire(prog_in);
+                    __syncwarp();
+                    if (step + lane < LS) chunk = __ldcg(row_in + step + lane);
+                }
+                in_h = __shfl_sync(FULL, chunk.x, step & 31);
+                in_g = __shfl_sync(FULL, chunk.y, step & 31);
+            }
+            int h_dn = K1_NEG, g_dn = K1_NEG;
+            if (n >= 0 && n < LS && lane < lanes) {
+                int h_up = recv_h, g_up = recv_g;
+                if (lane == 0) {
+                    if (pass == 0) { h_up = k1_top(g, n); g_up = K1_NEG; }
+                    else { h_up = in_h; g_up = in_g; }
+                }
+                const int kL = n - lwm, kU = n - upm;
+#pragma unroll
+                for (int k = 0; k < RR; ++k) if (k == kL || k == kU) L.E[k] = K1_NEG;
+                const int letter = nxt;
+                nxt = (int)__ldg(s + n + 1);
+                int sc[RR];
+#pragma unroll
+                for (int k = 0; k < RR; ++k) sc[k] = prof[(letter * RR + k) * 32 + lane];
+                const unsigned long long bits = k2_lane_step(L, sc, negv, h_up, g_up, mbase == 0, &h_dn, &g_dn);
+                unsigned char* const wp = words + (int64_t)step * 32 * (RR / 2);
+                if (RR == 16) __stcs(reinterpret_cast<unsigned long long*>(wp), bits);
+                else if (RR == 8) __stcs(reinterpret_cast<unsigned*>(wp), (unsigned)bits);
+                else __stcs(reinterpret_cast<unsigned short*>(wp), (unsigned short)bits);
+                if (lane == lanes - 1) {
+                    if (!last_pass) {
+                        __stcg(row_out + n, make_int2(h_dn, g_dn));
+                        if ((n % PUB) == PUB - 1 || n == LS - 1) st_release(a.progress + pass, n + 1);
+                    }
+                }
+            }
+            recv_h = __shfl_up_sync(FULL, h_dn, 1);
+            recv_g = __shfl_up_sync(FULL, g_dn, 1);
+        }
+        if (last_pass) {
+            const int tl = (rows_here - 1) / RR, kf = (rows_here - 1) % RR;
+            int val = 0;
+#pragma unroll
+            for (int k = 0; k < RR; ++k)
+                if (k == kf) val = L.H[k];
+            val = __shfl_sync(FULL, val, tl);
+            if (lane == 0) a.score[0] = val - (LQ + LS) * a.u;
+        }
+        __syncwarp();
+    }
+}
+
 // One WARP per alignment: the back-walk is a chain of dependent loads (the next cell is known only after the nibble of
 // this one: ~0.35 us per move -- 20.9 ms for the 60,000 moves of a 30 kb pair, more than its fill).  Paths run straight
 // most of the time, so the 32 lanes read the next 32 cells of the current run at once (diagonal in state H, up in G,
@@ -509,6 +626,8 @@ int k2_long_rows(int LQ, int LS)
         if (v == 4 || v == 8 || v == 16) return v;
     }
     (void)LS;
+    // second form of the kernel (k2_fill_long2_kernel): 16 / 8 / 4 rows 21.1 / 16.9 / 16.1 ms on the 30 kb pair
+    if (!getenv("PG_K2_LONG_V1")) return LQ >= 4096 ? 4 : 16;
     return LQ >= 4096 ? 8 : 16;
 }
 
@@ -525,9 +644,26 @@ static cudaError_t long_launch(const K2Args& a, int npass, int sm_count, cudaStr
     return cudaGetLastError();
 }
 
+template <int RR>
+static cudaError_t long2_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st)
+{
+    const size_t smem = (size_t)a.dim * RR * 32 * sizeof(int);
+    cudaError_t e = cudaFuncSetAttribute(k2_fill_long2_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)MAXDIM * RR * 32 * sizeof(int)));
+    if (e != cudaSuccess) return e;
+    int blocks = npass < sm_count * 16 ? npass : sm_count * 16;
+    k2_fill_long2_kernel<RR><<<blocks, 32, smem, st>>>(a, npass);
+    return cudaGetLastError();
+}
+
 cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st)
 {
-    if (a.dim < 1 || a.dim > MAXDIM) return cudaErrorInvalidValue;
+    if (!getenv("PG_K2_LONG_V1"))           // A/B switch: the first form of the kernel
+        switch (a.rows_per_lane) {
+        case 4: return long2_launch<4>(a, npass, sm_count, st);
+        case 8: return long2_launch<8>(a, npass, sm_count, st);
+        default: return long2_launch<16>(a, npass, sm_count, st);
+        }
     switch (a.rows_per_lane) {
     case 4: return long_launch<4>(a, npass, sm_count, st);
     case 8: return long_launch<8>(a, npass, sm_count, st);
