@@ -351,11 +351,7 @@ __global__ void __launch_bounds__(128) k2_trace_kernel(const K2Args a, int npair
 // step: the query profile is laid out [letter][row][lane] as plain words (RR conflict-free LDS.32 instead of int4
 // chunks that need RR % 4 == 0), and the band cut is an unrolled compare-and-move on the register array instead of a
 // round trip of E[] through shared memory.  30 kb pair, RR = 8: 17.4 -> 15.3 ms.
-// (Tried with it, end of round 2: W > 1 consecutive stripes per CTA, one warp per scheduler, handing the bottom row down
-// through a shared-memory ring one column per step, so that narrow stripes -- faster per step -- would not pay the ~87
-// steps by which a stripe trails the one above through L2.  Results identical, but 38 - 47 ms for every W > 1 unless the
-// kernel also contained a printf call, with which RR = 4, W = 4 ran in 14.2 ms; fences, spin back-off and the ring's
-// layout made no difference.  Not understood, so not shipped.)
+// (The multi-warp variant of it, k2_fill_wide_kernel below, is opt-in.)
 template <int RR>
 __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int npass)
 {
@@ -459,6 +455,163 @@ __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int n
             if (lane == 0) a.score[0] = val - (LQ + LS) * a.u;
         }
         __syncwarp();
+    }
+}
+
+
+// ---- W consecutive stripes per CTA ---------------------------------------------------------------------------------
+// Narrow stripes are faster per step (a lone warp runs a lane-step as one dependent chain), but every stripe of the
+// kernels above trails the one above by ~87 steps (32-column chunks through L2).  Here W warps of one CTA, one per
+// scheduler, hold W consecutive stripes and hand the bottom row down through a shared-memory ring, one column per step:
+// warp w + 1 trails warp w by the 32 steps of the systolic skew and nothing more; only the last warp of a CTA goes through
+// the L2 row buffer to the first warp of the next CTA.  Stripe = warp: the direction words keep k2_fill_kernel's layout.
+// A ring slot = {h, g, column + 1, -} in one 16-byte shared-memory access, so value and tag travel together without a
+// fence.  The lane that polls (lane 0) or publishes (the last lane) does so in a divergent branch: the __syncwarp() right
+// after it matters -- without it the polling lane ran on ALONE through the whole cell code before the warp reconverged at
+// the shuffles, i.e. every step was executed twice (38 - 47 ms instead of 14.5).
+// OPT-IN (PG_K2_WIDE = 2 | 4 with PG_K2_LONG_ROWS = 4 | 8): measured against k2_fill_long2_kernel<4> on DNA pairs of 6 /
+// 12 / 20 / 30 / 45 kb, 4 rows x 4 warps: 2.9 / 5.8 / 14.3 / 14.5 / 21.8 ms against 3.1 / 6.3 / 10.6 / 16.2 / 24.9 -- 8 to 13 %
+// faster at four lengths and 35 % slower at one; the other shapes (8 x 2, 8 x 4, 4 x 2) run in the slow regime at 30 kb.
+// Results are identical everywhere; what tips a run into the slow regime is not understood, so the default stays the
+// single-warp stripe.
+constexpr int WRING = 64;
+__device__ __forceinline__ void ring_put(unsigned addr, int h, int g, int tag)
+{
+    asm volatile("st.volatile.shared.v4.s32 [%0], {%1, %2, %3, %3};" ::"r"(addr), "r"(h), "r"(g), "r"(tag) : "memory");
+}
+__device__ __forceinline__ int4 ring_get(unsigned addr)
+{
+    int4 v;
+    asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+template <int RR, int W>
+__global__ void __launch_bounds__(32 * W) k2_fill_wide_kernel(const K2Args a, int npass)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(16) int4 ring[W][WRING];
+    __shared__ int cons[W];             // columns warp w has taken from the warp above
+    __shared__ int sm_ticket;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int* const prof = reinterpret_cast<int*>(smem_raw) + (size_t)w * a.dim * RR * 32;      // [letter][k][lane]
+    const int negv = -a.v;
+    const int qi = a.pair_q[0], si = a.pair_s[0];
+    const uint8_t* q = a.seqs.res + a.seqs.offs[qi] + a.seqs.left[qi];
+    const uint8_t* s = a.seqs.res + a.seqs.offs[si] + a.seqs.left[si];
+    const int LQ = a.seqs.wlen[qi], LS = a.seqs.wlen[si];
+    K1Geom g;
+    g.LQ = LQ; g.LS = LS; g.u = a.u; g.v = a.v;
+    k1_band(LQ, LS, a.sh, &g.lw, &g.up);
+    g.topOpen = -a.v; g.topExt = -a.u; g.leftOpen = -a.v; g.leftExt = -a.u;
+    unsigned char* const dir_base = reinterpret_cast<unsigned char*>(a.dirs + a.dir_off[0]);
+    constexpr int RPP = 32 * RR;
+    volatile int* const vcons = cons;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sm_ticket = atomicAdd(a.ticket, 1);
+        if (lane == 0) cons[w] = 0;
+        ring[w][lane] = make_int4(0, 0, 0, 0); ring[w][lane + 32] = make_int4(0, 0, 0, 0);      // tag 0 = nothing yet
+        __syncthreads();
+        const int pass0 = sm_ticket * W;
+        if (pass0 >= npass) break;
+        const int pass = pass0 + w;
+        if (pass >= npass) continue;        // (the barrier at the top of the loop is reached by every warp)
+        const int pbase = pass * RPP;
+        for (int idx = lane; idx < a.dim * RPP; idx += 32) {
+            const int letter = idx / RPP, rem = idx - letter * RPP;
+            const int k = rem >> 5, ln = rem & 31;
+            const int row = pbase + ln * RR + k;
+            prof[idx] = row < LQ ? a.mtx[(int)q[row] * a.dim + letter] + 2 * a.u : 0;
+        }
+        __syncwarp();
+        const int rows_here = min(LQ - pbase, RPP);
+        const int lanes = (rows_here + RR - 1) / RR;
+        const int mbase = pbase + lane * RR;
+        const bool last_pass = pass == npass - 1;
+        const bool from_l2 = w == 0 && pass > 0;                    // the stripe above lives in the previous CTA
+        const bool from_ring = w > 0;
+        const bool to_l2 = w == W - 1 && !last_pass;                // the stripe below lives in the next CTA
+        const bool to_ring = w < W - 1 && !last_pass;
+        const int2* const row_in = a.rowbuf + (int64_t)(pass - 1) * LS;
+        int2* const row_out = a.rowbuf + (int64_t)pass * LS;
+        const int* const prog_in = a.progress + (pass - 1);
+        unsigned char* const words = dir_base + ((int64_t)pass * (LS + 31) * 32 + lane) * (RR / 2);
+
+        K2Lane<RR> L;
+        k2_lane_init(L, g, mbase);
+        const int lwm = g.lw + mbase;
+        const int upm = g.up + 1 + mbase;
+        int recv_h = K1_NEG, recv_g = K1_NEG;
+        const int nsteps = LS + lanes - 1;
+        int avail = 0;
+        int2 chunk = make_int2(K1_NEG, K1_NEG);
+        int nxt = (lane < lanes && LS > 0) ? (int)__ldg(s) : 0;
+
+        for (int step = 0; step < nsteps; ++step) {
+            const int n = step - lane;
+            int in_h = K1_NEG, in_g = K1_NEG;
+            if (from_l2) {                                          // uniform over the warp
+                if ((step & 31) == 0 && step < LS) {
+                    const int need = min(step + 32, LS);
+                    if (lane == 0) while (avail < need) avail = ld_acquire(prog_in);
+                    __syncwarp();
+                    if (step + lane < LS) chunk = __ldcg(row_in + step + lane);
+                }
+                in_h = __shfl_sync(FULL, chunk.x, step & 31);
+                in_g = __shfl_sync(FULL, chunk.y, step & 31);
+            } else if (from_ring) {                                 // uniform: the warp above, through the ring
+                if (lane == 0 && step < LS) {
+                    const unsigned slot = (unsigned)__cvta_generic_to_shared(&ring[w - 1][step & (WRING - 1)]);
+                    int4 v = ring_get(slot);
+                    while (v.z != step + 1) v = ring_get(slot);     // (a __nanosleep here oversleeps every step: 14.5 -> 26.7 ms)
+                    in_h = v.x; in_g = v.y;
+                    vcons[w] = step + 1;
+                }
+                __syncwarp();                                       // the other 31 lanes wait HERE, not at the shuffles below
+            }
+            int h_dn = K1_NEG, g_dn = K1_NEG;
+            if (n >= 0 && n < LS && lane < lanes) {
+                int h_up = recv_h, g_up = recv_g;
+                if (lane == 0) {
+                    if (pass == 0) { h_up = k1_top(g, n); g_up = K1_NEG; }
+                    else { h_up = in_h; g_up = in_g; }
+                }
+                const int kL = n - lwm, kU = n - upm;
+#pragma unroll
+                for (int k = 0; k < RR; ++k) if (k == kL || k == kU) L.E[k] = K1_NEG;
+                const int letter = nxt;
+                nxt = (int)__ldg(s + n + 1);
+                int sc[RR];
+#pragma unroll
+                for (int k = 0; k < RR; ++k) sc[k] = prof[(letter * RR + k) * 32 + lane];
+                const unsigned long long bits = k2_lane_step(L, sc, negv, h_up, g_up, mbase == 0, &h_dn, &g_dn);
+                unsigned char* const wp = words + (int64_t)step * 32 * (RR / 2);
+                if (RR == 8) __stcs(reinterpret_cast<unsigned*>(wp), (unsigned)bits);
+                else __stcs(reinterpret_cast<unsigned short*>(wp), (unsigned short)bits);
+                if (lane == lanes - 1) {
+                    if (to_l2) {
+                        __stcg(row_out + n, make_int2(h_dn, g_dn));
+                        if ((n % PUB) == PUB - 1 || n == LS - 1) st_release(a.progress + pass, n + 1);
+                    } else if (to_ring) {
+                        while (n - vcons[w + 1] >= WRING) { }       // the warp below has not read this slot's last value yet
+                        ring_put((unsigned)__cvta_generic_to_shared(&ring[w][n & (WRING - 1)]), h_dn, g_dn, n + 1);
+                    }
+                }
+            }
+            __syncwarp();
+            recv_h = __shfl_up_sync(FULL, h_dn, 1);
+            recv_g = __shfl_up_sync(FULL, g_dn, 1);
+        }
+        if (last_pass) {
+            const int tl = (rows_here - 1) / RR, kf = (rows_here - 1) % RR;
+            int val = 0;
+#pragma unroll
+            for (int k = 0; k < RR; ++k)
+                if (k == kf) val = L.H[k];
+            val = __shfl_sync(FULL, val, tl);
+            if (lane == 0) a.score[0] = val - (LQ + LS) * a.u;
+        }
     }
 }
 
@@ -656,8 +809,28 @@ static cudaError_t long2_launch(const K2Args& a, int npass, int sm_count, cudaSt
     return cudaGetLastError();
 }
 
+template <int RR, int W>
+static cudaError_t wide_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st)
+{
+    const size_t smem = (size_t)W * a.dim * RR * 32 * sizeof(int);
+    cudaError_t e = cudaFuncSetAttribute(k2_fill_wide_kernel<RR, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)W * MAXDIM * RR * 32 * sizeof(int)));
+    if (e != cudaSuccess) return e;
+    const int ctas = (npass + W - 1) / W;       // a CTA waits only for one that took its ticket earlier: any grid works
+    const int blocks = ctas < sm_count * 4 ? ctas : sm_count * 4;
+    k2_fill_wide_kernel<RR, W><<<blocks, 32 * W, smem, st>>>(a, npass);
+    return cudaGetLastError();
+}
+
 cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st)
 {
+    if (const char* wv = getenv("PG_K2_WIDE")) {        // W stripes per CTA (2 or 4), rows per lane from PG_K2_LONG_ROWS (4 or 8)
+        const int wn = atoi(wv);
+        if (a.rows_per_lane == 4 && wn == 2) return wide_launch<4, 2>(a, npass, sm_count, st);
+        if (a.rows_per_lane == 4 && wn == 4) return wide_launch<4, 4>(a, npass, sm_count, st);
+        if (a.rows_per_lane == 8 && wn == 2) return wide_launch<8, 2>(a, npass, sm_count, st);
+        if (a.rows_per_lane == 8 && wn == 4) return wide_launch<8, 4>(a, npass, sm_count, st);
+    }
     if (!getenv("PG_K2_LONG_V1"))           // A/B switch: the first form of the kernel
         switch (a.rows_per_lane) {
         case 4: return long2_launch<4>(a, npass, sm_count, st);
