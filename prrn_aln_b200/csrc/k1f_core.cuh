@@ -102,12 +102,64 @@ PG_HD void k1f_lane_init(K1FLane<T, R, VD>& L, const K1FPair<T>& g, int mbase, T
 // Hands (H, gg) of its last row to the lane below.
 // SWG (swgforwardD, fwd2d1.cc:162-189): cells are clamped at 0 and the maximum over the in-band cells
 // is tracked; out-of-band cells are masked to -inf (rel = n - mbase - lw, span = up - lw).
+// Two IEEE single-precision additions in one instruction (add.rn.f32x2, SASS FADD2: sm_100 packed FP32).  Each half
+// rounds exactly like a scalar add.rn.f32, so results stay bit-identical; it is used where two rows of a lane add
+// independently of the vertical chain (h_diag + S, and the final "- uu" of the eager ff): 7 -> 6 instructions per
+// cell.  Measured on B200 (tools/bench_k1f.py, C2 with PAM250, float): 1,517 -> 1,553 GCUPS end to end, the 300-aa
+// set 1,298 -> 1,325, same checksums (-DK1F_NO_PACKED_ADD builds the scalar form).
+#if !defined(K1F_NO_PACKED_ADD)
+#define K1F_PACKED_ADD 1
+#endif
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void k1f_add2(float& r0, float& r1, float a0, float a1, float b0, float b1)
+{
+    asm("{ .reg .b64 pa, pb, pc;\n\t"
+        "mov.b64 pa, {%2, %3};\n\t"
+        "mov.b64 pb, {%4, %5};\n\t"
+        "add.rn.f32x2 pc, pa, pb;\n\t"
+        "mov.b64 {%0, %1}, pc; }"
+        : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+#endif
+template <typename T> struct k1f_is_float { static constexpr bool value = false; };
+template <> struct k1f_is_float<float> { static constexpr bool value = true; };
+
 template <typename T, int R, bool SWG, bool VD>
 PG_HD void k1f_lane_step(K1FLane<T, R, VD>& L, T* sc, T vv, T uu, T h_up, T g_up, T* h_dn, T* g_dn, int rel,
                          unsigned span, T* maxh, int hr_up = 0, int gr_up = 0, int* hr_dn = nullptr,
                          int* gr_dn = nullptr)
 {
     // phase 1 (independent per row): h_diag + S, consumed old H[k-1]
+#if defined(__CUDA_ARCH__) && defined(K1F_PACKED_ADD)
+    if constexpr (k1f_is_float<T>::value && !VD && !SWG && R >= 2) {
+#pragma unroll
+        for (int k = 0; k + 1 < R; k += 2)
+            k1f_add2(sc[k], sc[k + 1], k ? L.H[k - 1] : L.hdiag, L.H[k], sc[k], sc[k + 1]);
+        if (R & 1) sc[R - 1] = L.H[R - 2] + sc[R - 1];
+        const T uv = uu + vv;
+        (void)uv;
+        T habove = h_up, gabove = g_up, h = h_up, g = g_up;
+        T t[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const T f = L.E[k];
+            g = k1f_max(habove - vv, gabove) - uu;               // :148
+            h = k1f_max(k1f_max(sc[k], f), g);                   // :150
+            t[k] = k1f_max(h - vv, f);
+            L.H[k] = h;
+            habove = h;
+            gabove = g;
+        }
+        const T nu = -uu;
+#pragma unroll
+        for (int k = 0; k + 1 < R; k += 2) k1f_add2(L.E[k], L.E[k + 1], t[k], t[k + 1], nu, nu);
+        if (R & 1) L.E[R - 1] = t[R - 1] - uu;
+        L.hdiag = h_up;
+        *h_dn = h;
+        *g_dn = g;
+        return;
+    }
+#endif
     sc[0] = L.hdiag + sc[0];                                     // fwd2d1.cc:149
 #pragma unroll
     for (int k = 1; k < R; ++k) sc[k] = L.H[k - 1] + sc[k];
