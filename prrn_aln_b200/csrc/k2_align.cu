@@ -402,7 +402,16 @@ __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int n
         int2 chunk = make_int2(K1_NEG, K1_NEG);
         int nxt = (lane < lanes && LS > 0) ? (int)__ldg(s) : 0;
 
-        for (int step = 0; step < nsteps; ++step) {
+        // running pointers instead of index * stride products (64-bit multiplies per step otherwise)
+        unsigned char* wp = words;                                  // direction bits of this lane at `step`
+        const uint8_t* sp = s + 1 - lane;                           // residue of column n + 1 (running)
+        int2* op = row_out - lane;                                  // slot of column n in the row below (running)
+        const bool publisher = lane == lanes - 1 && !last_pass;     // the lane that owns the bottom row of the stripe
+        // band cut as a bit mask per lane: bit k set <=> row k loses its horizontal input at this column
+        // (k == n - lwm or k == n - upm); shifts beyond 31 (either side) give 0 in PTX
+        const int cl0 = -lane - lwm, cu0 = -lane - upm;             // kL = step + cl0, kU = step + cu0
+
+        for (int step = 0; step < nsteps; ++step, wp += 32 * (RR / 2), ++sp, ++op) {
             const int n = step - lane;
             int in_h = K1_NEG, in_g = K1_NEG;
             if (pass > 0) {                                         // uniform over the warp
@@ -422,25 +431,31 @@ __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int n
                     if (pass == 0) { h_up = k1_top(g, n); g_up = K1_NEG; }
                     else { h_up = in_h; g_up = in_g; }
                 }
-                const int kL = n - lwm, kU = n - upm;
+                unsigned cut;
+                asm("{ .reg .u32 ma, mb;\n\t"
+                    "shl.b32 ma, 1, %1;\n\t"
+                    "shl.b32 mb, 1, %2;\n\t"
+                    "or.b32 %0, ma, mb; }" : "=r"(cut) : "r"(step + cl0), "r"(step + cu0));
 #pragma unroll
-                for (int k = 0; k < RR; ++k) if (k == kL || k == kU) L.E[k] = K1_NEG;
+                for (int k = 0; k < RR; ++k) if (cut & (1u << k)) L.E[k] = K1_NEG;
                 const int letter = nxt;
-                nxt = (int)__ldg(s + n + 1);
+                nxt = (int)__ldg(sp);
                 int sc[RR];
 #pragma unroll
                 for (int k = 0; k < RR; ++k) sc[k] = prof[(letter * RR + k) * 32 + lane];
                 const unsigned long long bits = k2_lane_step(L, sc, negv, h_up, g_up, mbase == 0, &h_dn, &g_dn);
-                unsigned char* const wp = words + (int64_t)step * 32 * (RR / 2);
                 if (RR == 16) __stcs(reinterpret_cast<unsigned long long*>(wp), bits);
                 else if (RR == 8) __stcs(reinterpret_cast<unsigned*>(wp), (unsigned)bits);
                 else __stcs(reinterpret_cast<unsigned short*>(wp), (unsigned short)bits);
-                if (lane == lanes - 1) {
-                    if (!last_pass) {
-                        __stcg(row_out + n, make_int2(h_dn, g_dn));
-                        if ((n % PUB) == PUB - 1 || n == LS - 1) st_release(a.progress + pass, n + 1);
-                    }
-                }
+                // the bottom row goes to the stripe below: a predicated store (no divergent block for one lane);
+                // the counter follows every PUB columns, data first (release)
+                asm volatile("{ .reg .pred pp;\n\t"
+                             "setp.ne.b32 pp, %0, 0;\n\t"
+                             "@pp st.global.cg.v2.s32 [%1], {%2, %3}; }" ::"r"((int)publisher), "l"(op), "r"(h_dn), "r"(g_dn) : "memory");
+                const int pubnow = publisher && ((n & (PUB - 1)) == PUB - 1 || n == LS - 1);
+                asm volatile("{ .reg .pred pq;\n\t"
+                             "setp.ne.b32 pq, %0, 0;\n\t"
+                             "@pq st.release.gpu.global.s32 [%1], %2; }" ::"r"(pubnow), "l"(a.progress + pass), "r"(n + 1) : "memory");
             }
             recv_h = __shfl_up_sync(FULL, h_dn, 1);
             recv_g = __shfl_up_sync(FULL, g_dn, 1);
