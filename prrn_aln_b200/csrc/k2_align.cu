@@ -176,6 +176,16 @@ __device__ __forceinline__ int ld_acquire(const int* p)
     return v;
 }
 
+// Hand-over slots of the second form (k2_fill_long2_kernel): the row buffer is filled with 0x80 bytes before the launch;
+// a real H value never has that pattern (drifted scores stay above K1_NEG - (LQ + LS) * (u + v) > 0x80808080 as int).
+constexpr unsigned K2_SLOT_EMPTY = 0x80808080u;
+__device__ __forceinline__ unsigned long long ld_relaxed64(const int2* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // RR rows per lane: a stripe is 32 * RR rows.  One warp alone on its scheduler runs a lane-step as one dependent
 // chain (about 30 cycles per row + 150 of fixed work), so narrow stripes (RR = 4: 128 rows, 235 warps for a 30 kb
 // query) finish the matrix in LS + stripes * skew steps of a quarter of the length.  The bottom row of the stripe
@@ -352,7 +362,7 @@ __global__ void __launch_bounds__(128) k2_trace_kernel(const K2Args a, int npair
 // chunks that need RR % 4 == 0), and the band cut is an unrolled compare-and-move on the register array instead of a
 // round trip of E[] through shared memory.  30 kb pair, RR = 8: 17.4 -> 15.3 ms.
 // (The multi-warp variant of it, k2_fill_wide_kernel below, is opt-in.)
-template <int RR>
+template <int RR, int CH>
 __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int npass)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -389,7 +399,6 @@ __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int n
         const bool last_pass = pass == npass - 1;
         const int2* const row_in = a.rowbuf + (int64_t)(pass - 1) * LS;
         int2* const row_out = a.rowbuf + (int64_t)pass * LS;
-        const int* const prog_in = a.progress + (pass - 1);
         unsigned char* const words = dir_base + ((int64_t)pass * (LS + 31) * 32 + lane) * (RR / 2);
 
         K2Lane<RR> L;
@@ -398,7 +407,6 @@ __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int n
         const int upm = g.up + 1 + mbase;
         int recv_h = K1_NEG, recv_g = K1_NEG;
         const int nsteps = LS + lanes - 1;
-        int avail = 0;
         int2 chunk = make_int2(K1_NEG, K1_NEG);
         int nxt = (lane < lanes && LS > 0) ? (int)__ldg(s) : 0;
 
@@ -410,22 +418,26 @@ __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int n
         // band cut as a bit mask per lane: bit k set <=> row k loses its horizontal input at this column
         // (k == n - lwm or k == n - upm); shifts beyond 31 (either side) give 0 in PTX
         const int cl0 = -lane - lwm, cu0 = -lane - upm;             // kL = step + cl0, kU = step + cu0
+        const unsigned LSa = lane < lanes ? (unsigned)LS : 0u;      // this lane works at column n iff (unsigned)n < LSa
 
         for (int step = 0; step < nsteps; ++step, wp += 32 * (RR / 2), ++sp, ++op) {
             const int n = step - lane;
             int in_h = K1_NEG, in_g = K1_NEG;
             if (pass > 0) {                                         // uniform over the warp
-                if ((step & 31) == 0 && step < LS) {                // lane 0 enters a new chunk of 32 columns
-                    const int need = min(step + 32, LS);
-                    if (lane == 0) while (avail < need) avail = ld_acquire(prog_in);
-                    __syncwarp();
-                    if (step + lane < LS) chunk = __ldcg(row_in + step + lane);
+                if ((step & (CH - 1)) == 0 && step < LS) {          // lane 0 enters a new chunk of CH columns
+                    // the slots are their own flags: the warp re-reads its CH slots until none holds the fill pattern
+                    const bool want = lane < CH && step + lane < LS;
+                    unsigned long long w = 0;
+                    do {
+                        if (want) w = ld_relaxed64(row_in + step + lane);
+                    } while (__any_sync(FULL, want && (unsigned)w == K2_SLOT_EMPTY));
+                    chunk = make_int2((int)(unsigned)w, (int)(unsigned)(w >> 32));
                 }
-                in_h = __shfl_sync(FULL, chunk.x, step & 31);
-                in_g = __shfl_sync(FULL, chunk.y, step & 31);
+                in_h = __shfl_sync(FULL, chunk.x, step & (CH - 1));
+                in_g = __shfl_sync(FULL, chunk.y, step & (CH - 1));
             }
             int h_dn = K1_NEG, g_dn = K1_NEG;
-            if (n >= 0 && n < LS && lane < lanes) {
+            if ((unsigned)n < LSa) {
                 int h_up = recv_h, g_up = recv_g;
                 if (lane == 0) {
                     if (pass == 0) { h_up = k1_top(g, n); g_up = K1_NEG; }
@@ -447,15 +459,13 @@ __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int n
                 if (RR == 16) __stcs(reinterpret_cast<unsigned long long*>(wp), bits);
                 else if (RR == 8) __stcs(reinterpret_cast<unsigned*>(wp), (unsigned)bits);
                 else __stcs(reinterpret_cast<unsigned short*>(wp), (unsigned short)bits);
-                // the bottom row goes to the stripe below: a predicated store (no divergent block for one lane);
-                // the counter follows every PUB columns, data first (release)
+                // the bottom row goes to the stripe below: ONE predicated 64-bit store per column (single-copy atomic, so
+                // (h, g) arrive together); no counter, no fence -- a slot that no longer holds the fill pattern is valid
                 asm volatile("{ .reg .pred pp;\n\t"
+                             ".reg .b64 pw;\n\t"
                              "setp.ne.b32 pp, %0, 0;\n\t"
-                             "@pp st.global.cg.v2.s32 [%1], {%2, %3}; }" ::"r"((int)publisher), "l"(op), "r"(h_dn), "r"(g_dn) : "memory");
-                const int pubnow = publisher && ((n & (PUB - 1)) == PUB - 1 || n == LS - 1);
-                asm volatile("{ .reg .pred pq;\n\t"
-                             "setp.ne.b32 pq, %0, 0;\n\t"
-                             "@pq st.release.gpu.global.s32 [%1], %2; }" ::"r"(pubnow), "l"(a.progress + pass), "r"(n + 1) : "memory");
+                             "mov.b64 pw, {%2, %3};\n\t"
+                             "@pp st.relaxed.gpu.global.b64 [%1], pw; }" ::"r"((int)publisher), "l"(op), "r"(h_dn), "r"(g_dn) : "memory");
             }
             recv_h = __shfl_up_sync(FULL, h_dn, 1);
             recv_g = __shfl_up_sync(FULL, g_dn, 1);
@@ -812,16 +822,26 @@ static cudaError_t long_launch(const K2Args& a, int npass, int sm_count, cudaStr
     return cudaGetLastError();
 }
 
-template <int RR>
-static cudaError_t long2_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st)
+template <int RR, int CH>
+static cudaError_t long2_launch(const K2Args& a, int npass, int sm_count, size_t rowbuf_bytes, cudaStream_t st)
 {
     const size_t smem = (size_t)a.dim * RR * 32 * sizeof(int);
-    cudaError_t e = cudaFuncSetAttribute(k2_fill_long2_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k2_fill_long2_kernel<RR, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)((size_t)MAXDIM * RR * 32 * sizeof(int)));
     if (e != cudaSuccess) return e;
+    // every hand-over slot starts out "empty" (K2_SLOT_EMPTY)
+    if ((e = cudaMemsetAsync(a.rowbuf, 0x80, rowbuf_bytes, st)) != cudaSuccess) return e;
     int blocks = npass < sm_count * 16 ? npass : sm_count * 16;
-    k2_fill_long2_kernel<RR><<<blocks, 32, smem, st>>>(a, npass);
+    k2_fill_long2_kernel<RR, CH><<<blocks, 32, smem, st>>>(a, npass);
     return cudaGetLastError();
+}
+template <int RR>
+static cudaError_t long2_launch_ch(const K2Args& a, int npass, int sm_count, size_t rowbuf_bytes, cudaStream_t st)
+{
+    static const int ch = getenv("PG_K2_CHUNK") ? atoi(getenv("PG_K2_CHUNK")) : 16;     // A/B switch: 8, 16 or 32 columns (30 kb pair: 8.58 / 8.09 / 8.30 ms)
+    if (ch == 8) return long2_launch<RR, 8>(a, npass, sm_count, rowbuf_bytes, st);
+    if (ch == 16) return long2_launch<RR, 16>(a, npass, sm_count, rowbuf_bytes, st);
+    return long2_launch<RR, 32>(a, npass, sm_count, rowbuf_bytes, st);
 }
 
 template <int RR, int W>
@@ -837,7 +857,7 @@ static cudaError_t wide_launch(const K2Args& a, int npass, int sm_count, cudaStr
     return cudaGetLastError();
 }
 
-cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st)
+cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, size_t rowbuf_bytes, cudaStream_t st)
 {
     if (const char* wv = getenv("PG_K2_WIDE")) {        // W stripes per CTA (2 or 4), rows per lane from PG_K2_LONG_ROWS (4 or 8)
         const int wn = atoi(wv);
@@ -848,9 +868,9 @@ cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, cudaSt
     }
     if (!getenv("PG_K2_LONG_V1"))           // A/B switch: the first form of the kernel
         switch (a.rows_per_lane) {
-        case 4: return long2_launch<4>(a, npass, sm_count, st);
-        case 8: return long2_launch<8>(a, npass, sm_count, st);
-        default: return long2_launch<16>(a, npass, sm_count, st);
+        case 4: return long2_launch_ch<4>(a, npass, sm_count, rowbuf_bytes, st);
+        case 8: return long2_launch_ch<8>(a, npass, sm_count, rowbuf_bytes, st);
+        default: return long2_launch_ch<16>(a, npass, sm_count, rowbuf_bytes, st);
         }
     switch (a.rows_per_lane) {
     case 4: return long_launch<4>(a, npass, sm_count, st);

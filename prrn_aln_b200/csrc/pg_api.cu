@@ -1095,12 +1095,14 @@ extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
         a.moves = (unsigned char*)(tb + o_mv); a.recs = (K2Rec*)(tb + o_rc); a.out_pts = (int32_t*)(tb + o_out);
         a.out_cnt = (int32_t*)(pb + o_cn);
         int long_npass = 0;
+        size_t long_rb = 0;
         if (long_pair) {
             // row buffers of all stripes + progress counters + ticket, zeroed
             a.rows_per_lane = k2_long_rows(d->h_wlen[pq[0]], max_ls);
             long_npass = (d->h_wlen[pq[0]] + 32 * a.rows_per_lane - 1) / (32 * a.rows_per_lane);
             const size_t rb = sizeof(int2) * (size_t)long_npass * (size_t)max_ls;
             const size_t need = up256(rb) + sizeof(int32_t) * (size_t)(long_npass + 2);
+            long_rb = rb;
             if ((rc = ensure_cap(c, &c->d_rowbuf, &c->rowbuf_cap, need))) break;
             a.rowbuf = (int2*)c->d_rowbuf;
             a.progress = (int32_t*)((char*)c->d_rowbuf + up256(rb));
@@ -1108,7 +1110,7 @@ extern "C" int pg_align_pairs(pg_context* c, const pg_seqs* s, const int32_t* a_
             if (e == cudaSuccess) e = cudaMemsetAsync(a.progress, 0, sizeof(int32_t) * (size_t)(long_npass + 2), c->stream);
         }
         if (e == cudaSuccess) e = cudaEventRecord(c->ev0, c->stream);
-        if (e == cudaSuccess) e = long_pair ? k2_fill_long_launch(a, long_npass, c->sm_count, c->stream)
+        if (e == cudaSuccess) e = long_pair ? k2_fill_long_launch(a, long_npass, c->sm_count, long_rb, c->stream)
                                             : k2_fill_launch(a, grid, c->stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev1, c->stream);
         c->ev_valid = e == cudaSuccess;

@@ -273,7 +273,7 @@ int k1f_grid_blocks(int sm_count, int vtype, int mode);
 // k2_align.cu
 cudaError_t k2_fill_launch(const K2Args& a, int grid_blocks, cudaStream_t st);
 cudaError_t k2_trace_launch(const K2Args& a, int npairs, cudaStream_t st);
-cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, cudaStream_t st);
+cudaError_t k2_fill_long_launch(const K2Args& a, int npass, int sm_count, size_t rowbuf_bytes, cudaStream_t st);
 int k2_rows_per_lane();
 int k2_long_rows(int LQ, int LS);     // rows per lane of the striped long-pair kernel
 int k2_warps_per_block();
