@@ -179,6 +179,11 @@ __device__ __forceinline__ int ld_acquire(const int* p)
 // Hand-over slots of the second form (k2_fill_long2_kernel): the row buffer is filled with 0x80 bytes before the launch;
 // a real H value never has that pattern (drifted scores stay above K1_NEG - (LQ + LS) * (u + v) > 0x80808080 as int).
 constexpr unsigned K2_SLOT_EMPTY = 0x80808080u;
+// the step loop of the second form is unrolled: the loop-carried values (what the shuffles hand on, the running pointers)
+// otherwise change registers through ~14 moves per step (30 kb pair: 7.99 ms rolled, 7.50 ms unrolled twice)
+#ifndef K2_LONG_UNROLL
+#define K2_LONG_UNROLL 2
+#endif
 __device__ __forceinline__ unsigned long long ld_relaxed64(const int2* p)
 {
     unsigned long long v;
@@ -420,6 +425,7 @@ __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int n
         const int cl0 = -lane - lwm, cu0 = -lane - upm;             // kL = step + cl0, kU = step + cu0
         const unsigned LSa = lane < lanes ? (unsigned)LS : 0u;      // this lane works at column n iff (unsigned)n < LSa
 
+#pragma unroll K2_LONG_UNROLL
         for (int step = 0; step < nsteps; ++step, wp += 32 * (RR / 2), ++sp, ++op) {
             const int n = step - lane;
             int in_h = K1_NEG, in_g = K1_NEG;
@@ -805,7 +811,8 @@ int k2_long_rows(int LQ, int LS)
     }
     (void)LS;
     // second form of the kernel (k2_fill_long2_kernel): 16 / 8 / 4 rows 21.1 / 16.9 / 16.1 ms on the 30 kb pair
-    if (!getenv("PG_K2_LONG_V1")) return LQ >= 4096 ? 4 : 16;
+    // with the flag-less hand-over narrow stripes win at every length (3 kb pair: 1.66 ms with 16 rows, 0.81 with 4)
+    if (!getenv("PG_K2_LONG_V1")) return 4;
     return LQ >= 4096 ? 8 : 16;
 }
 

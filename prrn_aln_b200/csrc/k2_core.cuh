@@ -31,7 +31,7 @@ template <int R>
 struct K2Lane {
     int H[R];       // Ht(mbase+k, n-1)
     int E[R];       // horizontal state for the coming column (eager)
-    unsigned eopen; // bit k: that state was opened (not extended) when it was computed
+    unsigned long long eopen;   // bit 4k + 3 (its place in the direction word): that state was opened (not extended) when it was computed
     int hdiag;      // Ht(mbase-1, n-1)
 };
 
@@ -60,8 +60,8 @@ PG_HD unsigned long long k2_lane_step(K2Lane<R>& L, const int* sc, int negv, int
     bool gopen = x0 > g_up;
     int g = x0 > g_up ? x0 : g_up;
     if (first_row) { g = K1_NEG; gopen = false; }
-    unsigned long long bits = 0;
-    unsigned eopen_next = 0;
+    unsigned long long bits = L.eopen;          // bit 3 of every nibble is already in place
+    unsigned long long eopen_next = 0;
     int h = h_up, gcur = g_up;
     // The VALUES go through max() only, so that the chain from one row to the next is two operations
     // (h = max(t, g); g' = max(h - v, g)) and everything else -- t = max(diagonal, horizontal), the tie-rule
@@ -77,7 +77,7 @@ PG_HD unsigned long long k2_lane_step(K2Lane<R>& L, const int* sc, int negv, int
         const bool nd = e_gt_d || g > d;         // a gap state wins only if strictly better (:453)
         h = t > g ? t : g;
         const unsigned src = nd ? (fge ? 2u : 1u) : 0u;
-        const unsigned nib = src | (gopen ? 4u : 0u) | (((L.eopen >> k) & 1u) << 3);
+        const unsigned nib = src | (gopen ? 4u : 0u);
         bits |= (unsigned long long)nib << (4 * k);
         const int x = h + negv;
         gcur = g;
@@ -85,7 +85,7 @@ PG_HD unsigned long long k2_lane_step(K2Lane<R>& L, const int* sc, int negv, int
         g = x > g ? x : g;
         const bool eo = x > e;                   // next column's horizontal state (:426-429)
         L.E[k] = x > e ? x : e;
-        eopen_next |= (eo ? 1u : 0u) << k;
+        eopen_next |= (unsigned long long)(eo ? 8u : 0u) << (4 * k);
         diag = L.H[k];
         L.H[k] = h;
     }
