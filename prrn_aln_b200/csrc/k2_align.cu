@@ -184,6 +184,7 @@ constexpr unsigned K2_SLOT_EMPTY = 0x80808080u;
 #ifndef K2_LONG_UNROLL
 #define K2_LONG_UNROLL 2
 #endif
+constexpr int K2_LONG_UNROLL_N = K2_LONG_UNROLL;
 __device__ __forceinline__ unsigned long long ld_relaxed64(const int2* p)
 {
     unsigned long long v;
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int n
         const int cl0 = -lane - lwm, cu0 = -lane - upm;             // kL = step + cl0, kU = step + cu0
         const unsigned LSa = lane < lanes ? (unsigned)LS : 0u;      // this lane works at column n iff (unsigned)n < LSa
 
-#pragma unroll K2_LONG_UNROLL
+#pragma unroll K2_LONG_UNROLL_N
         for (int step = 0; step < nsteps; ++step, wp += 32 * (RR / 2), ++sp, ++op) {
             const int n = step - lane;
             int in_h = K1_NEG, in_g = K1_NEG;
