@@ -203,6 +203,44 @@ def default_scoring_measurement(P, ctx, enc):
         return {"error": repr(e)[:300]}
 
 
+def long_pair_measurement(P, ctx):
+    """BASELINE config 5, second half: ONE DNA pair of 30 kb x 30 kb -- alignC<DPunit> with path on the striped
+    wavefront kernel of K2 (single-warp stripes of 128 rows, bottom rows handed down through flag-less slots in L2),
+    device traceback included.  Host-buffer calls, best of 5 after the first call (which grows the direction-bit
+    store); the corner list is compared with the reference's own `aln` run on this pair (tests/golden)."""
+    try:
+        from prrn_aln_b200 import seqcode
+        dna = gen_synth.synth_set(2, 30000, 0.2, 0.2, 5, gen_synth.NT)
+        e2 = [seqcode.encode_dna(s) for s in dna]
+        Mn = np.full((18, 18), -4.0)
+        np.fill_diagonal(Mn, 2.0)
+        prm = P.Params(P.ALPRM(u=2, v=6, sh=-50))
+        ss = P.SeqSet(e2)
+        cells = int(P.calcdist_cells(ss, prm))
+        ctx.align_pairs(ss, [0], [1], prm, Mn)
+        best, fill = None, None
+        for _ in range(5):
+            t0 = time.perf_counter()
+            sc, raw = ctx.align_pairs(ss, [0], [1], prm, Mn)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best:
+                best, fill = dt, ctx.last_kernel_ms()
+        pts = P.stdskl(raw[0])
+        out = {"metric": "DP GCUPS (one pair with path, band cells)", "unit": "GCUPS", "value": cells / (fill * 1e-3) / 1e9,
+               "fill_kernel_ms": fill, "e2e": {"value": cells / best / 1e9, "unit": "GCUPS", "call_ms": best * 1e3},
+               "cells": cells, "score": float(sc[0]), "corners": len(pts), "replicas_only": True,
+               "config": {"workload": "C5b: one synthetic DNA pair 29,979 x 30,017 nt (seed 5, 20 % divergence), match 2 "
+                                      "mismatch -4, u=2 v=6 sh=-50; fill + device traceback + D2H of the corner list"}}
+        gpath = os.path.join(ROOT, "tests", "golden", "align_c5b_30k.json")
+        if os.path.exists(gpath):
+            with open(gpath) as f:
+                g = json.load(f)["pairs"][0]
+            out["equals_reference_alignment"] = bool(float(sc[0]) == g["score"] and pts == [tuple(x) for x in g["skl"]])
+        return out
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
 def group_side_measurement():
     """The other half of BASELINE.json's metric: group-to-group DP (kernel K3 + K4) on partitions of a
     200 x ~500 aa family (config 3 shape), with the reference's alignC timed beside it on one host core.
@@ -614,6 +652,7 @@ def main():
                                    CPU_SAMPLE_N, CPU_SAMPLE_N * (CPU_SAMPLE_N - 1) // 2, cells, dtc)}
     if rank == 0 and world == 1 and not args.no_groups:
         out["default_scoring"] = default_scoring_measurement(P, ctx, c2_enc)
+        out["long_pair"] = long_pair_measurement(P, ctx)
     ctx.close()
     if world > 1 and not args.no_groups:
         gc = group_candidates_measurement(P, torch, dist, rank, world, local)
