@@ -368,12 +368,18 @@ __global__ void __launch_bounds__(128) k2_trace_kernel(const K2Args a, int npair
 // chunks that need RR % 4 == 0), and the band cut is an unrolled compare-and-move on the register array instead of a
 // round trip of E[] through shared memory.  30 kb pair, RR = 8: 17.4 -> 15.3 ms.
 // (The multi-warp variant of it, k2_fill_wide_kernel below, is opt-in.)
-template <int RR, int CH>
+template <int RR, int CH, bool BULK>
 __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int npass)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     int* const prof = reinterpret_cast<int*>(smem_raw);            // [letter][k][lane]
+    // BULK: the direction bits of DB steps (a contiguous DB * 32 * RR / 2 bytes of the wavefront-ordered store) are
+    // collected in shared memory and leave the SM as ONE bulk copy (cp.async.bulk shared -> global, the TMA engine),
+    // two buffers in flight; otherwise one 2 * RR-byte store per lane and step
+    constexpr int DB = 16;
+    constexpr unsigned DSTEP = 32 * (RR / 2);                       // bytes of direction bits per step
+    const unsigned stage_sh = (unsigned)__cvta_generic_to_shared(smem_raw) + (((unsigned)a.dim * RR * 32 * 4 + 127u) & ~127u);
     const int negv = -a.v;
     const int qi = a.pair_q[0], si = a.pair_s[0];
     const uint8_t* q = a.seqs.res + a.seqs.offs[qi] + a.seqs.left[qi];
@@ -463,7 +469,12 @@ __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int n
 #pragma unroll
                 for (int k = 0; k < RR; ++k) sc[k] = prof[(letter * RR + k) * 32 + lane];
                 const unsigned long long bits = k2_lane_step(L, sc, negv, h_up, g_up, mbase == 0, &h_dn, &g_dn);
-                if (RR == 16) __stcs(reinterpret_cast<unsigned long long*>(wp), bits);
+                if (BULK) {
+                    const unsigned sa = stage_sh + ((unsigned)step & (2 * DB - 1)) * DSTEP + (unsigned)lane * (RR / 2);
+                    if (RR == 16) asm volatile("st.shared.b64 [%0], %1;" ::"r"(sa), "l"(bits) : "memory");
+                    else if (RR == 8) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sa), "r"((unsigned)bits) : "memory");
+                    else asm volatile("st.shared.b16 [%0], %1;" ::"r"(sa), "h"((unsigned short)bits) : "memory");
+                } else if (RR == 16) __stcs(reinterpret_cast<unsigned long long*>(wp), bits);
                 else if (RR == 8) __stcs(reinterpret_cast<unsigned*>(wp), (unsigned)bits);
                 else __stcs(reinterpret_cast<unsigned short*>(wp), (unsigned short)bits);
                 // the bottom row goes to the stripe below: ONE predicated 64-bit store per column (single-copy atomic, so
@@ -476,6 +487,23 @@ __global__ void __launch_bounds__(32) k2_fill_long2_kernel(const K2Args a, int n
             }
             recv_h = __shfl_up_sync(FULL, h_dn, 1);
             recv_g = __shfl_up_sync(FULL, g_dn, 1);
+            if (BULK && (((step & (DB - 1)) == DB - 1) || step == nsteps - 1)) {        // uniform: a block of DB steps is complete
+                const int s0 = step & ~(DB - 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // every lane: its stores before the bulk copy
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\t"
+                                 "cp.async.bulk.commit_group;\n\t"
+                                 "cp.async.bulk.wait_group.read 1;"                    // the other buffer has been read out
+                                 ::"l"(words - (size_t)lane * (RR / 2) + (size_t)s0 * DSTEP),
+                                   "r"(stage_sh + ((unsigned)s0 & (2 * DB - 1)) * DSTEP), "r"((unsigned)(step + 1 - s0) * DSTEP) : "memory");
+                }
+                __syncwarp();
+            }
+        }
+        if (BULK) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncwarp();
         }
         if (last_pass) {
             const int tl = (rows_here - 1) / RR, kf = (rows_here - 1) % RR;
@@ -830,26 +858,32 @@ static cudaError_t long_launch(const K2Args& a, int npass, int sm_count, cudaStr
     return cudaGetLastError();
 }
 
-template <int RR, int CH>
+template <int RR, int CH, bool BULK>
 static cudaError_t long2_launch(const K2Args& a, int npass, int sm_count, size_t rowbuf_bytes, cudaStream_t st)
 {
-    const size_t smem = (size_t)a.dim * RR * 32 * sizeof(int);
-    cudaError_t e = cudaFuncSetAttribute(k2_fill_long2_kernel<RR, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((size_t)MAXDIM * RR * 32 * sizeof(int)));
+    const size_t stage = BULK ? (size_t)2 * 16 * 32 * (RR / 2) + 128 : 0;
+    const size_t smem = (size_t)a.dim * RR * 32 * sizeof(int) + stage;
+    cudaError_t e = cudaFuncSetAttribute(k2_fill_long2_kernel<RR, CH, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((size_t)MAXDIM * RR * 32 * sizeof(int) + stage));
     if (e != cudaSuccess) return e;
     // every hand-over slot starts out "empty" (K2_SLOT_EMPTY)
     if ((e = cudaMemsetAsync(a.rowbuf, 0x80, rowbuf_bytes, st)) != cudaSuccess) return e;
     int blocks = npass < sm_count * 16 ? npass : sm_count * 16;
-    k2_fill_long2_kernel<RR, CH><<<blocks, 32, smem, st>>>(a, npass);
+    k2_fill_long2_kernel<RR, CH, BULK><<<blocks, 32, smem, st>>>(a, npass);
     return cudaGetLastError();
 }
 template <int RR>
 static cudaError_t long2_launch_ch(const K2Args& a, int npass, int sm_count, size_t rowbuf_bytes, cudaStream_t st)
 {
-    static const int ch = getenv("PG_K2_CHUNK") ? atoi(getenv("PG_K2_CHUNK")) : 16;     // A/B switch: 8, 16 or 32 columns (30 kb pair: 8.58 / 8.09 / 8.30 ms)
-    if (ch == 8) return long2_launch<RR, 8>(a, npass, sm_count, rowbuf_bytes, st);
-    if (ch == 16) return long2_launch<RR, 16>(a, npass, sm_count, rowbuf_bytes, st);
-    return long2_launch<RR, 32>(a, npass, sm_count, rowbuf_bytes, st);
+    // A/B and test switches, read per call.  Hand-over chunk of 8 / 16 / 32 columns: 30 kb pair 8.58 / 8.09 / 8.30 ms.
+    // PG_K2_BULK=1: the direction bits leave through bulk copies (UBLKCP.G.S, 1 KB per 16 steps) -- identical results,
+    // 7.45 -> 8.79 ms: the proxy fence + hand-shake in front of every copy cost more than 16 two-byte stores per lane.
+    const int ch = getenv("PG_K2_CHUNK") ? atoi(getenv("PG_K2_CHUNK")) : 16;
+    const bool bulk = getenv("PG_K2_BULK") && getenv("PG_K2_BULK")[0] == '1';
+    if (bulk) return long2_launch<RR, 16, true>(a, npass, sm_count, rowbuf_bytes, st);
+    if (ch == 8) return long2_launch<RR, 8, false>(a, npass, sm_count, rowbuf_bytes, st);
+    if (ch == 32) return long2_launch<RR, 32, false>(a, npass, sm_count, rowbuf_bytes, st);
+    return long2_launch<RR, 16, false>(a, npass, sm_count, rowbuf_bytes, st);
 }
 
 template <int RR, int W>

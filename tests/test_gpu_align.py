@@ -166,6 +166,23 @@ def test_all_pairs_c2_subset_and_path_properties(ctx, oracle):
         assert s == float(scores[k]), k
 
 
+@pytest.mark.parametrize("env", [{"PG_K2_CHUNK": "8"}, {"PG_K2_CHUNK": "32"}, {"PG_K2_BULK": "1"}, {"PG_K2_LONG_ROWS": "8"},
+                                 {"PG_K2_LONG_ROWS": "16", "PG_K2_BULK": "1"}, {"PG_K2_LONG_V1": "1"}])
+def test_long_pair_kernel_variants(ctx, monkeypatch, env):
+    """The striped long-pair fill in its other forms (hand-over chunk width, direction bits through bulk copies,
+    rows per lane, the first form with progress counters) against the reference's corner list of the 6 kb DNA pair."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = golden("align_dna6k")
+    enc = [seqcode.encode_dna(s) for s in g["seqs"]]
+    ia = [p["i"] for p in g["pairs"]]
+    ib = [p["j"] for p in g["pairs"]]
+    scores, raw = ctx.align_pairs(P.SeqSet(enc), ia, ib, _params(g), np.array(g["matrix"]))
+    for k, p in enumerate(g["pairs"]):
+        assert float(scores[k]) == p["score"]
+        assert P.stdskl(raw[k]) == [tuple(x) for x in p["skl"]]
+
+
 def test_long_pair_multi_pass(ctx, oracle):
     seqs = gen_synth.synth_set(2, 2600, 0.1, 0.3, 41)
     enc = [seqcode.encode_protein(s) for s in seqs]
