@@ -91,6 +91,28 @@ __device__ __forceinline__ void mbar_remote_arrive(unsigned local_addr, unsigned
     asm volatile("{ .reg .b32 ra; mapa.shared::cluster.u32 ra, %0, %1; "
                  "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra]; }" ::"r"(local_addr), "r"(rank) : "memory");
 }
+// The release above is MEMBAR.ALL.CTA + MEMBAR.ALL.GPU in SASS, in front of every per-step signal.  The default
+// hand-over (K3Args.cluster_fence == 0) therefore lets the DATA complete the barrier: the records travel as st.async
+// (each store performs complete_tx of its 8 bytes on full[slot] of the receiving CTA), the receiving CTA arms
+// full[slot] itself for every use (arrive.expect_tx with the bytes of one push, a local operation), and the only
+// remote arrive left -- "slot free again", which orders no data -- is relaxed.
+__device__ __forceinline__ void mbar_remote_arrive_relaxed(unsigned local_addr, unsigned rank)
+{
+    asm volatile("{ .reg .b32 ra; mapa.shared::cluster.u32 ra, %0, %1; "
+                 "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra]; }" ::"r"(local_addr), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void mbar_arm_tx(unsigned addr, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_remote_async_v2(unsigned local_addr, unsigned local_mbar, unsigned rank, int2 v)
+{
+    asm volatile("{ .reg .b32 ra, rm; mapa.shared::cluster.u32 ra, %0, %2; mapa.shared::cluster.u32 rm, %1, %2; "
+                 "st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [ra], {%3, %4}, [rm]; }"
+                 ::"r"(local_addr), "r"(local_mbar), "r"(rank), "r"(v.x), "r"(v.y) : "memory");
+}
+// bytes one push puts into a ring slot: nrec records of ceil(st / 2) 8-byte stores
+__device__ __forceinline__ unsigned cl_push_bytes(int st, bool three) { return (three ? 3u : 2u) * (unsigned)((st + 1) / 2) * 8u; }
 // The wait acquires at CTA scope by default: what a neighbour hands over per step are shared-memory records, read
 // through DSMEM (never cached in L1) after this wait and a __syncthreads, and parked rows in global memory that are
 // read with ld.global.cg hundreds of steps later; a cluster-scope acquire makes ptxas invalidate L1 (CCTL.IVALL)
@@ -116,13 +138,22 @@ __device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity, bool f
 // CTA below once that slot is free again, then signal it.  Not inlined: its temporaries must not lengthen live
 // ranges inside the per-cell code (the kernel sits at the 80-register limit).
 __device__ __noinline__ void cl_push(const int* srcH, const int* srcG, const int* srcG2, unsigned ring_addr, unsigned full_addr,
-                                     unsigned empty_addr, int S, int st, int lane, bool fenced)
+                                     unsigned empty_addr, int S, int st, int lane, int fence_mode)
 {
     const int xs = S % XD;
-    if (S >= XD && lane == 0) mbar_wait(empty_addr + 8u * xs, (unsigned)(S / XD - 1) & 1u, fenced);
+    if (S >= XD && lane == 0) mbar_wait(empty_addr + 8u * xs, (unsigned)(S / XD - 1) & 1u, fence_mode == 1);
     __syncwarp();
     const unsigned below = (unsigned)(cl_rank() + 1);
     const unsigned dst = ring_addr + 4u * (unsigned)(xs * 3 * st);
+    if (fence_mode == 0) {                      // the stores themselves complete full[xs] of the CTA below
+        const unsigned mb = full_addr + 8u * xs;
+        for (int w = 2 * lane; w < st; w += 64) {
+            st_remote_async_v2(dst + 4 * w, mb, below, *reinterpret_cast<const int2*>(srcH + w));
+            st_remote_async_v2(dst + 4 * (st + w), mb, below, *reinterpret_cast<const int2*>(srcG + w));
+            if (srcG2) st_remote_async_v2(dst + 4 * (2 * st + w), mb, below, *reinterpret_cast<const int2*>(srcG2 + w));
+        }
+        return;
+    }
     for (int w = 2 * lane; w < st; w += 64) {
         st_remote_v2(dst + 4 * w, below, *reinterpret_cast<const int2*>(srcH + w));
         st_remote_v2(dst + 4 * (st + w), below, *reinterpret_cast<const int2*>(srcG + w));
@@ -135,9 +166,13 @@ __device__ __noinline__ void cl_wait_above(unsigned full_addr, int S, bool fence
 {
     mbar_wait(full_addr + 8u * (unsigned)((S - 1) % XD), (unsigned)((S - 1) / XD) & 1u, fenced);
 }
-__device__ __noinline__ void cl_release(unsigned empty_addr, int S)
+__device__ __noinline__ void cl_release(unsigned empty_addr, unsigned full_addr, int S, int fence_mode, unsigned tx)
 {
-    mbar_remote_arrive(empty_addr + 8u * (unsigned)((S - 2) % XD), (unsigned)(cl_rank() - 1));
+    const unsigned slot = (unsigned)((S - 2) % XD);
+    if (fence_mode == 0) {
+        mbar_arm_tx(full_addr + 8u * slot, tx);         // the next use of the slot: one arrival (this one) + the bytes of a push
+        mbar_remote_arrive_relaxed(empty_addr + 8u * slot, (unsigned)(cl_rank() - 1));
+    } else mbar_remote_arrive(empty_addr + 8u * slot, (unsigned)(cl_rank() - 1));
 }
 
 // TG threads per alignment: the whole CTA for few pairs (latency), down to one warp per alignment for
@@ -358,6 +393,10 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
 #define TM_START() do {} while (0)
 #define TM_ADD(acc) do {} while (0)
 #endif
+            // CL, data-completed hand-over: this CTA arms every slot of its ring for its first use (later uses are armed
+            // when the slot is given back); a push that arrives earlier just leaves the count negative until then
+            if (CL && crank > 0 && t == 0 && role == 0 && a.cluster_fence == 0)
+                for (int i = 0; i < XD; ++i) mbar_arm_tx(smem_addr(&sm_full[i]), cl_push_bytes(st, n3));
             for (int S = 0; S < total_steps; ++S) {
                 TM_START();
                 // prefetch the parked record thread 0 reads as "above" at step S + 2: index n2 + 1 of stripe k2 - 1
@@ -375,7 +414,7 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                 int* gout = pubG + ((size_t)(S & 1) * TG + t) * st;
                 int* g2out = pubG2 + ((size_t)(S & 1) * TG + t) * st;
                 if (CL && crank > 0 && t == 0 && role <= 1 && S >= 1)     // the row above has finished step S - 1 (pushed into our ring)
-                    cl_wait_above(smem_addr(sm_full), S, a.cluster_fence != 0);
+                    cl_wait_above(smem_addr(sm_full), S, a.cluster_fence == 1);
                 TM_ADD(tm_wait);
                 if (active) {
                     const int ia = m + 1, ib = n + 1;
@@ -510,9 +549,9 @@ __global__ void __launch_bounds__(SPLIT ? 3 * TG : CTA, SPLIT ? 1 : 2) k3_fill_k
                     if (crank < NC - 1 && t >= TG - 32)
                         cl_push(pubH + ((size_t)(S % 3) * TG + (TG - 1)) * st, pubG + ((size_t)(S & 1) * TG + (TG - 1)) * st,
                                 n3 ? pubG2 + ((size_t)(S & 1) * TG + (TG - 1)) * st : nullptr, smem_addr(xring), smem_addr(sm_full),
-                                smem_addr(sm_empty), S, st, t - (TG - 32), a.cluster_fence != 0);
+                                smem_addr(sm_empty), S, st, t - (TG - 32), a.cluster_fence);
                     // the slot of step S - 2 has now served as "above" (S - 1) and "diagonal" (S): give it back
-                    if (crank > 0 && t == 0 && S >= 2) cl_release(smem_addr(sm_empty), S);
+                    if (crank > 0 && t == 0 && S >= 2) cl_release(smem_addr(sm_empty), smem_addr(sm_full), S, a.cluster_fence, cl_push_bytes(st, n3));
                 }
                 TM_ADD(tm_push);
                 GSTEP();
@@ -634,7 +673,7 @@ cudaError_t launch_cluster(const K3Args& a, int clusters, cudaStream_t st)
 {
     auto kern = k3_fill_kernel<TGCL, true, MODE, true, true, 0>;
     K3Args ac = a;
-    { const char* f = getenv("PG_K3_CLUSTER_FENCE"); ac.cluster_fence = f && f[0] == '1'; }
+    { const char* f = getenv("PG_K3_CLUSTER_FENCE"); ac.cluster_fence = f && f[0] >= '0' && f[0] <= '2' ? f[0] - '0' : 0; }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
     if (e != cudaSuccess) return e;
     int carve = (int)((a.smem_bytes + 2048) * 100LL / (228 * 1024)) + 1;
@@ -661,7 +700,7 @@ cudaError_t launch_rl(const K3Args& a, int units, cudaStream_t st)
 {
     const bool cl = a.cluster > 1;
     K3Args ac = a;
-    { const char* f = getenv("PG_K3_CLUSTER_FENCE"); ac.cluster_fence = f && f[0] == '1'; }
+    { const char* f = getenv("PG_K3_CLUSTER_FENCE"); ac.cluster_fence = f && f[0] >= '0' && f[0] <= '2' ? f[0] - '0' : 0; }
     const void* kern = cl ? (const void*)k3_fill_kernel<TGRL, true, MODE, true, true, RL>
                           : (const void*)k3_fill_kernel<TGRL, true, MODE, true, false, RL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);

@@ -170,7 +170,7 @@ struct K3Args {
     int32_t smem_bytes;         // dynamic shared memory per CTA for the wavefront records
     int32_t all_sm;             // every pair fits the all-shared-memory variant (k3_sm_fits)
     int32_t cluster;            // latency mode: CTAs (thread-block cluster size) per alignment, 1 = none
-    int32_t cluster_fence;      // cluster variant: cluster-scope acquire in the per-step hand-shake (PG_K3_CLUSTER_FENCE)
+    int32_t cluster_fence;      // cluster variant, per-step hand-over (PG_K3_CLUSTER_FENCE): 0 st.async records complete the barrier (default), 1 release arrives + cluster-scope acquires, 2 release arrives + CTA-scope waits
     int32_t rl;                 // register-list form (k3r_core.cuh): words per dynamic list (4 / 6 / 8) of this launch, 0 = classic
     int32_t rows192;            // the records fit shared memory only with 192 rows per CTA: the cluster kernel's geometry,
                                 // also for a "cluster" of one CTA (long gap-state lists: high hetero, two-piece)

@@ -367,13 +367,16 @@ def test_cluster_latency_kernel_matches_reference(ctx, monkeypatch):
                                 float(h["v"]), pc["vgop1"], pc["BasicGOP"], pc["BasicGEP"], pc["LongGOP"], pc["LongGEP"])
         staged.append((A, B, gp))
     assert max(int(s[0]["right"] - s[0]["left"]) for s in staged) > 256      # more rows than one CTA holds
-    for cap in (None, "fenced", "8", "2", "1"):
+    for cap in (None, "fenced", "release", "8", "2", "1"):
         monkeypatch.delenv("PG_K3_CLUSTER_FENCE", raising=False)
-        if cap is None:
+        if cap is None:                  # default: the records complete the barrier themselves (st.async + complete_tx)
             monkeypatch.delenv("PG_K3_CLUSTER", raising=False)
-        elif cap == "fenced":            # cluster-scope acquire in the per-step hand-shake
+        elif cap == "fenced":            # release arrives + cluster-scope acquire in the per-step hand-shake
             monkeypatch.delenv("PG_K3_CLUSTER", raising=False)
             monkeypatch.setenv("PG_K3_CLUSTER_FENCE", "1")
+        elif cap == "release":           # release arrives, CTA-scope waits (the default before the st.async form)
+            monkeypatch.delenv("PG_K3_CLUSTER", raising=False)
+            monkeypatch.setenv("PG_K3_CLUSTER_FENCE", "2")
         else:
             monkeypatch.setenv("PG_K3_CLUSTER", cap)
         for batch in (staged, staged[:1]):
