@@ -687,18 +687,6 @@ __device__ int k2_backwalk_warp(const unsigned long long* words, int LQ, int LS,
     while (m >= 0 && n >= 0) {
         const int mj = m - (state != 2 ? lane : 0), nj = n - (state != 1 ? lane : 0);
         const bool inr = mj >= 0 && nj >= 0;
-        // the 32 cells after these, in the direction of the run, are asked into L2 now: the store is wavefront-ordered
-        // (64 bytes per step and stripe), so wherever this run ends and the next one starts -- a few columns or rows to the
-        // side -- its cells lie in the same few lines, and the next round's load finds them in L2 instead of HBM
-        {
-            const int pm = mj - (state != 2 ? 32 : 0), pn = nj - (state != 1 ? 32 : 0);
-            if (pm >= 0 && pn >= 0) {
-                const int rpp = 32 * RL;
-                const int pass = pm / rpp, rm = pm - pass * rpp, pl = rm / RL;
-                const long long slot = ((long long)pass * (LS + 31) + (pn + pl)) * 32 + pl;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char*>(words) + slot * (RL / 2)));
-            }
-        }
         const unsigned nib = inr ? k2_nibble(words, LS, RL, mj, nj) : 0u;
         if (state == 0) {
             const unsigned bal = __ballot_sync(FULL, !inr || (nib & 3u) != 0u);
